@@ -1,0 +1,196 @@
+/*
+ * pyamg_b200.h -- C ABI of the B200-native AMG solve-phase engine (libpyamg_b200.so).
+ *
+ * This is the drop-in boundary for pyamg's solve phase.  Plain pointers and
+ * sizes only; no torch / numpy / C++ types cross it.  Three groups of entry points:
+ *
+ *  (1) amgb_hierarchy_* / amgb_solve / amgb_cycle -- replaces MultilevelSolver.solve and the
+ *      recursive cycle driver MultilevelSolver.__solve (pyamg/multilevel.py:398-582, :584-662).
+ *      The hierarchy (A_k, P_k, R_k as CSR/BSR host arrays, smoother descriptors, the dense
+ *      coarse pseudo-inverse) is uploaded ONCE to HBM; every solve() then takes HOST b/x0 and
+ *      returns HOST x, exactly like the reference's NumPy-in / NumPy-out call.
+ *  (2) amgb_host_* -- same argument lists as the reference's pybind11 FFI for its native sweeps
+ *      (pyamg/amg_core/relaxation_bind.cpp: jacobi :847-854, bsr_jacobi, gauss_seidel,
+ *      gauss_seidel_indexed, block_jacobi <- relaxation.h:309-346, :472-562, :48-76, :736-768,
+ *      :1021-1090): HOST arrays in, x updated in place.  Each array parameter is followed by
+ *      its length, as the reference's binding generator emits them (bindthem.py:74-81).
+ *  (3) amgb_dev_* -- the individual sm_100a kernels on DEVICE pointers + a CUDA stream, for
+ *      callers that keep vectors resident (Krylov accelerators, the multi-GPU layer, tests).
+ *
+ * All values are fp64, all indices int32 (the reference's only index instantiation,
+ * pyamg/amg_core/instantiate.yml:2-6).  Every function returns 0 on success and a negative
+ * AMGB_E* code on failure; amgb_last_error() gives the message (thread-local).  Nothing here
+ * ever falls back to a CPU implementation: without a CUDA device every call fails.
+ */
+#ifndef PYAMG_B200_H
+#define PYAMG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMGB_OK 0
+#define AMGB_EINVAL (-1)      /* bad argument (maps to ValueError/TypeError in the Python mirror) */
+#define AMGB_ECUDA (-2)       /* CUDA runtime / NCCL failure */
+#define AMGB_ENOTIMPL (-3)    /* smoother / format outside the hot-path scope (NotImplementedError) */
+#define AMGB_ESTATE (-4)      /* call order violated (e.g. solve before finalize) */
+
+/* smoother kinds (what lvl.presmoother / lvl.postsmoother resolve to; SURVEY.md descriptor table) */
+#define AMGB_SM_NONE 0
+#define AMGB_SM_JACOBI 1          /* relaxation.jacobi        (CSR, or BSR viewed point-wise)   */
+#define AMGB_SM_GAUSS_SEIDEL 2    /* relaxation.gauss_seidel / gauss_seidel_indexed: a row list
+                                     executed in dependency waves == the sequential sweep       */
+#define AMGB_SM_BLOCK_JACOBI 3    /* relaxation.block_jacobi  (BSR + Dinv)                       */
+
+#define AMGB_SWEEP_FORWARD 0
+#define AMGB_SWEEP_BACKWARD 1
+#define AMGB_SWEEP_SYMMETRIC 2
+
+#define AMGB_CYCLE_V 0
+#define AMGB_CYCLE_W 1
+#define AMGB_CYCLE_F 2
+
+typedef struct amgb_hierarchy amgb_hierarchy;
+
+/* A sparse operator in HOST memory. block_r == block_c == 1 means CSR; otherwise BSR with
+ * row-major block_r x block_c blocks (scipy bsr_array.data layout).  n_rows/n_cols are POINT
+ * dimensions. indptr has n_rows/block_r + 1 entries. */
+typedef struct {
+    int32_t n_rows, n_cols;
+    int32_t block_r, block_c;
+    int64_t nnz_blocks;           /* len(indices) */
+    const int32_t *indptr;
+    const int32_t *indices;
+    const double *data;           /* nnz_blocks * block_r * block_c values */
+} amgb_matrix;
+
+/* One smoother application (pre or post) on a level. */
+typedef struct {
+    int32_t kind;                 /* AMGB_SM_* */
+    int32_t iterations;
+    int32_t sweep;                /* AMGB_SWEEP_* (Gauss-Seidel only) */
+    int32_t blocksize;            /* block Jacobi only */
+    double omega;                 /* Jacobi / block Jacobi: already divided by rho (smoothing.py:501-508);
+                                     Gauss-Seidel: SOR factor (forward/backward only, relaxation.py:326-338) */
+    const int32_t *indices;       /* Gauss-Seidel: explicit row list (gauss_seidel_indexed), or NULL
+                                     for the natural order 0..n-1 (gauss_seidel) */
+    int64_t n_indices;
+    const double *Dinv;           /* block Jacobi: (n/bs, bs, bs) row-major block-diagonal inverses */
+} amgb_smoother;
+
+const char *amgb_last_error(void);
+int amgb_version(void);
+int amgb_device_count(void);
+
+/* ---- (1) hierarchy + cycle driver ----------------------------------------------------------- */
+int amgb_hierarchy_create(int device, amgb_hierarchy **out);
+void amgb_hierarchy_destroy(amgb_hierarchy *h);
+
+/* Append level k (call in order k = 0, 1, ...).  For every level but the last pass P, R and the
+ * two smoothers; for the coarsest pass P = R = NULL (smoothers ignored). Arrays are copied to
+ * HBM before the call returns. */
+int amgb_hierarchy_add_level(amgb_hierarchy *h, const amgb_matrix *A, const amgb_matrix *P,
+                             const amgb_matrix *R, const amgb_smoother *pre,
+                             const amgb_smoother *post);
+
+/* Coarsest-level solver: dense pseudo-inverse (n x n row-major) computed by the caller on the
+ * CPU (scipy.linalg.pinv, multilevel.py:717-721) and applied on the GPU.  coarse_is_zero != 0
+ * reproduces GenericSolver.__call__'s "A.nnz == 0 => x = 0" branch (multilevel.py:801-803). */
+int amgb_hierarchy_set_coarse_pinv(amgb_hierarchy *h, int32_t n, const double *pinv,
+                                   int32_t coarse_is_zero);
+
+/* Allocate work vectors, build wave schedules, capture CUDA graphs.  stream == NULL -> the
+ * engine's own stream; otherwise every launch goes to the caller's stream (a cudaStream_t). */
+int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream);
+
+/* MultilevelSolver.solve without accel (multilevel.py:398-582): HOST b (n), HOST x (in: x0,
+ * out: solution), stop when ||b - A x|| < tol * ||b|| (||b|| := 1 if 0) tested after each cycle, or
+ * after maxiter cycles.  residuals (if non-NULL) receives ||r_0||, ||r_1||, ... (maxiter+1 slots);
+ * *n_residuals its count; *info = 0 on convergence else the iteration count (:574-582). */
+int amgb_solve(amgb_hierarchy *h, const double *b_host, double *x_host, double tol,
+               int32_t maxiter, int32_t cycle, int32_t cycles_per_level, double *residuals,
+               int32_t *n_residuals, int32_t *info);
+
+/* The same on DEVICE vectors (no host copies): x_dev in/out, b_dev in. Runs exactly `ncycles`
+ * cycles (tol = 0 semantics); if norms2_dev != NULL it receives ncycles+1 squared residual norms. */
+int amgb_solve_device(amgb_hierarchy *h, const double *b_dev, double *x_dev, int32_t ncycles,
+                      int32_t cycle, int32_t cycles_per_level, double *norms2_dev);
+
+/* One multigrid cycle x <- cycle(x, b) on the engine's level-0 device vectors / introspection */
+int amgb_hierarchy_num_levels(const amgb_hierarchy *h);
+int64_t amgb_hierarchy_device_bytes(const amgb_hierarchy *h);
+/* kernels launched by the most recent amgb_solve / amgb_solve_device call */
+int64_t amgb_hierarchy_last_launches(const amgb_hierarchy *h);
+/* pinned host buffers for the e2e path (cudaHostAlloc / cudaFreeHost) */
+int amgb_host_alloc(size_t bytes, void **out);
+int amgb_host_free(void *p);
+
+/* ---- (2) reference-FFI-shaped host entry points --------------------------------------------- */
+/* amg_core.jacobi (relaxation.h:309-346) */
+int amgb_host_jacobi(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                     const double *Ax, int Ax_size, double *x, int x_size, const double *b,
+                     int b_size, double *temp, int temp_size, int32_t row_start,
+                     int32_t row_stop, int32_t row_step, const double *omega, int omega_size);
+/* amg_core.gauss_seidel (relaxation.h:48-76) -- executed as dependency waves, same result */
+int amgb_host_gauss_seidel(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                           const double *Ax, int Ax_size, double *x, int x_size,
+                           const double *b, int b_size, int32_t row_start, int32_t row_stop,
+                           int32_t row_step);
+/* amg_core.sor_gauss_seidel (relaxation.h:116-145) */
+int amgb_host_sor_gauss_seidel(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                               const double *Ax, int Ax_size, double *x, int x_size,
+                               const double *b, int b_size, int32_t row_start, int32_t row_stop,
+                               int32_t row_step, double omega);
+/* amg_core.gauss_seidel_indexed (relaxation.h:736-768) */
+int amgb_host_gauss_seidel_indexed(const int32_t *Ap, int Ap_size, const int32_t *Aj,
+                                   int Aj_size, const double *Ax, int Ax_size, double *x,
+                                   int x_size, const double *b, int b_size, const int32_t *Id,
+                                   int Id_size, int32_t row_start, int32_t row_stop,
+                                   int32_t row_step);
+/* amg_core.bsr_jacobi (relaxation.h:472-562) */
+int amgb_host_bsr_jacobi(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                         const double *Ax, int Ax_size, double *x, int x_size, const double *b,
+                         int b_size, double *temp, int temp_size, int32_t row_start,
+                         int32_t row_stop, int32_t row_step, int32_t blocksize,
+                         const double *omega, int omega_size);
+/* amg_core.block_jacobi (relaxation.h:1021-1090) */
+int amgb_host_block_jacobi(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                           const double *Ax, int Ax_size, double *x, int x_size,
+                           const double *b, int b_size, const double *Tx, int Tx_size,
+                           double *temp, int temp_size, int32_t row_start, int32_t row_stop,
+                           int32_t row_step, const double *omega, int omega_size,
+                           int32_t blocksize);
+/* scipy.sparse._sparsetools.csr_matvec / bsr_matvec as the cycle uses them (y = A x) */
+int amgb_host_matvec(const amgb_matrix *A, const double *x, double *y);
+
+/* ---- (3) device kernels ------------------------------------------------------------------- */
+/* lanes: lanes per row (power of two 1..32), 0 = choose from the mean row length */
+int amgb_dev_csr_spmv(int32_t n_rows, const int32_t *Ap, const int32_t *Aj, const double *Ax,
+                      const double *x, double *y, int lanes, void *stream);
+/* r = b - A x; partials (>= amgb_dev_partials_len(n_rows, lanes) doubles) may be NULL */
+int amgb_dev_csr_residual(int32_t n_rows, const int32_t *Ap, const int32_t *Aj,
+                          const double *Ax, const double *x, const double *b, double *r,
+                          double *partials, double *norm2_out, int lanes, void *stream);
+/* x += P xc */
+int amgb_dev_csr_spmv_add(int32_t n_rows, const int32_t *Ap, const int32_t *Aj,
+                          const double *Ax, const double *xc, double *x, int lanes, void *stream);
+/* fused Jacobi + residual: x_out = jacobi(x_in), r_out (nullable) = b - A x_in */
+int amgb_dev_csr_jacobi(int32_t n_rows, const int32_t *Ap, const int32_t *Aj, const double *Ax,
+                        const double *x_in, const double *b, double *x_out, double *r_out,
+                        double omega, int lanes, void *stream);
+/* Gauss-Seidel over an independent set: rows == NULL -> rows row0 .. row0+n-1 */
+int amgb_dev_csr_gs_wave(int32_t n, int32_t row0, const int32_t *rows, const int32_t *Ap,
+                         const int32_t *Aj, const double *Ax, double *x, const double *b,
+                         double omega, int lanes, void *stream);
+int64_t amgb_dev_partials_len(int32_t n_rows, int lanes);
+int amgb_dev_dense_matvec(int32_t m, int32_t n, const double *M, const double *x, double *y,
+                          void *stream);
+int amgb_dev_fill(double *x, int64_t n, double v, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYAMG_B200_H */

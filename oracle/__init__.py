@@ -1,0 +1,380 @@
+"""CPU oracle for the AMG solve-phase hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this package; the product (pyamg_b200/) never does and has no CPU fallback.
+
+Two layers, both restating the reference (paths relative to /root/reference/):
+
+* native sweeps + matvecs: oracle/amg_oracle.c through ctypes (``kernels='oracle'``), or the
+  reference's own relaxation.h compiled as oracle/_ref/libamg_ref.so (``kernels='ref'``;
+  its SpMV leg is SciPy's csr_matvec/bsr_matvec -- exactly what the reference calls);
+* Python wrappers with the signatures of pyamg/relaxation/relaxation.py (``jacobi`` :349-420,
+  ``gauss_seidel`` :265-346, ``gauss_seidel_indexed`` :662-731, ``block_jacobi`` :423-499,
+  ``make_system`` :15-97) and the cycle driver of pyamg/multilevel.py (``solve`` :398-582,
+  ``__solve`` :584-662, 'pinv' coarse solver :717-721).
+
+Parity status: PINNED -- see tests/test_oracle.py (reference KATs, golden fixtures produced
+by the real reference via tests/golden/make_golden.py, and libamg_ref.so cross-checks).
+"""
+import ctypes
+import os
+
+import numpy as np
+import scipy.sparse as sparse
+from scipy.linalg import pinv
+
+from .build import build_oracle
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_I = ctypes.POINTER(ctypes.c_int)
+_D = ctypes.POINTER(ctypes.c_double)
+_libs = {}
+
+
+def _ip(a):
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return a.ctypes.data_as(_I)
+
+
+def _dp(a):
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(_D)
+
+
+def lib(kind="oracle"):
+    """Load (building if needed) the oracle C library, or the compiled reference shim."""
+    if kind not in _libs:
+        paths = build_oracle()
+        p = paths["oracle" if kind == "oracle" else "ref"]
+        if p is None:
+            raise FileNotFoundError("oracle/_ref/libamg_ref.so not built (needs /root/reference)")
+        _libs[kind] = ctypes.CDLL(p)
+    return _libs[kind]
+
+
+def have_ref():
+    return build_oracle()["ref"] is not None
+
+
+# --------------------------------------------------------------------------------------
+# matvecs
+# --------------------------------------------------------------------------------------
+def matvec(A, x, kernels="oracle"):
+    """A @ x the way the reference gets it (SciPy sparsetools), or the C restatement."""
+    if kernels == "ref":
+        return A @ x
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty(A.shape[0], dtype=np.float64)
+    L = lib("oracle")
+    if A.format == "csr":
+        L.oracle_csr_matvec(ctypes.c_int(A.shape[0]), _ip(A.indptr), _ip(A.indices),
+                            _dp(A.data), _dp(x), _dp(y))
+    elif A.format == "bsr":
+        R, C = A.blocksize
+        data = np.ascontiguousarray(A.data).ravel()
+        L.oracle_bsr_matvec(ctypes.c_int(A.shape[0] // R), ctypes.c_int(R), ctypes.c_int(C),
+                            _ip(A.indptr), _ip(A.indices), _dp(data), _dp(x), _dp(y))
+    else:
+        raise ValueError("matvec: csr or bsr expected")
+    return y
+
+
+# --------------------------------------------------------------------------------------
+# relaxation wrappers (signatures of pyamg/relaxation/relaxation.py)
+# --------------------------------------------------------------------------------------
+def make_system(A, x, b, formats=None):
+    """pyamg/relaxation/relaxation.py:15-97 (validation contract)."""
+    if formats is None:
+        pass
+    elif formats == ["csr"]:
+        if sparse.issparse(A) and A.format == "csr":
+            pass
+        elif sparse.issparse(A) and A.format == "bsr":
+            A = A.tocsr()
+        else:
+            A = sparse.csr_array(A)
+    elif sparse.issparse(A) and A.format in formats:
+        pass
+    else:
+        A = sparse.csr_array(A).asformat(formats[0])
+    if not isinstance(x, np.ndarray):
+        raise ValueError("expected numpy array for argument x")
+    if not isinstance(b, np.ndarray):
+        raise ValueError("expected numpy array for argument b")
+    M, N = A.shape
+    if M != N:
+        raise ValueError("expected square matrix")
+    if x.shape not in [(M,), (M, 1)]:
+        raise ValueError("x has invalid dimensions")
+    if b.shape not in [(M,), (M, 1)]:
+        raise ValueError("b has invalid dimensions")
+    if A.dtype != x.dtype or A.dtype != b.dtype:
+        raise TypeError("arguments A, x, and b must have the same dtype")
+    if not x.flags.carray:
+        raise ValueError("x must be contiguous in memory")
+    return A, np.ravel(x), np.ravel(b)
+
+
+def _f64(*arrs):
+    for a in arrs:
+        if a.dtype != np.float64:
+            raise TypeError("oracle is fp64-only (BASELINE.json: fp64)")
+
+
+def jacobi(A, x, b, iterations=1, omega=1.0, kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:349-420."""
+    A, x, b = make_system(A, x, b, formats=["csr", "bsr"])
+    _f64(A, x, b)
+    n = A.shape[0]
+    if n == 0:
+        return
+    temp = np.empty_like(x)
+    om = ctypes.c_double(float(omega))
+    if A.format == "csr":
+        for _ in range(iterations):
+            if kernels == "ref":
+                lib("ref").ref_jacobi(_ip(A.indptr), n, _ip(A.indices), _dp(A.data), A.nnz,
+                                      _dp(x), _dp(b), _dp(temp), 0, n, 1, om)
+            else:
+                lib().oracle_jacobi(_ip(A.indptr), _ip(A.indices), _dp(A.data), _dp(x), _dp(b),
+                                    _dp(temp), 0, n, 1, om)
+    else:
+        R, C = A.blocksize
+        if R != C:
+            raise ValueError("BSR blocks must be square")
+        data = np.ascontiguousarray(A.data).ravel()
+        nb = n // R
+        for _ in range(iterations):
+            if kernels == "ref":
+                lib("ref").ref_bsr_jacobi(_ip(A.indptr), nb, _ip(A.indices), _dp(data),
+                                          len(A.indices), _dp(x), _dp(b), _dp(temp),
+                                          0, nb, 1, R, om)
+            else:
+                lib().oracle_bsr_jacobi(_ip(A.indptr), _ip(A.indices), _dp(data), _dp(x),
+                                        _dp(b), _dp(temp), 0, nb, 1, R, om)
+
+
+def gauss_seidel(A, x, b, iterations=1, sweep="forward", omega=1.0, kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:265-346 (CSR path; 'symmetric' = fwd then bwd WITHOUT omega,
+    :326-330; omega != 1 -> sor_gauss_seidel :335-338)."""
+    A, x, b = make_system(A, x, b, formats=["csr"])
+    _f64(A, x, b)
+    n = A.shape[0]
+    if sweep == "forward":
+        rs = (0, n, 1)
+    elif sweep == "backward":
+        rs = (n - 1, -1, -1)
+    elif sweep == "symmetric":
+        for _ in range(iterations):
+            gauss_seidel(A, x, b, iterations=1, sweep="forward", kernels=kernels)
+            gauss_seidel(A, x, b, iterations=1, sweep="backward", kernels=kernels)
+        return
+    else:
+        raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+    for _ in range(iterations):
+        if omega != 1.0:
+            lib().oracle_sor_gauss_seidel(_ip(A.indptr), _ip(A.indices), _dp(A.data), _dp(x),
+                                          _dp(b), *rs, ctypes.c_double(float(omega)))
+        elif kernels == "ref":
+            lib("ref").ref_gauss_seidel(_ip(A.indptr), n, _ip(A.indices), _dp(A.data), A.nnz,
+                                        _dp(x), _dp(b), *rs)
+        else:
+            lib().oracle_gauss_seidel(_ip(A.indptr), _ip(A.indices), _dp(A.data), _dp(x),
+                                      _dp(b), *rs)
+
+
+def sor(A, x, b, omega, iterations=1, sweep="forward", kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:100-154."""
+    A, x, b = make_system(A, x, b, formats=["csr", "bsr"])
+    for _ in range(iterations):
+        gauss_seidel(A, x, b, iterations=1, sweep=sweep, omega=omega, kernels=kernels)
+
+
+def gauss_seidel_indexed(A, x, b, indices, iterations=1, sweep="forward", kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:662-731."""
+    A, x, b = make_system(A, x, b, formats=["csr"])
+    _f64(A, x, b)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    m = len(indices)
+    if sweep == "forward":
+        rs = (0, m, 1)
+    elif sweep == "backward":
+        rs = (m - 1, -1, -1)
+    elif sweep == "symmetric":
+        for _ in range(iterations):
+            gauss_seidel_indexed(A, x, b, indices, 1, "forward", kernels)
+            gauss_seidel_indexed(A, x, b, indices, 1, "backward", kernels)
+        return
+    else:
+        raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+    n = A.shape[0]
+    for _ in range(iterations):
+        if kernels == "ref":
+            lib("ref").ref_gauss_seidel_indexed(_ip(A.indptr), n, _ip(A.indices), _dp(A.data),
+                                                A.nnz, _dp(x), _dp(b), _ip(indices), m, *rs)
+        else:
+            lib().oracle_gauss_seidel_indexed(_ip(A.indptr), _ip(A.indices), _dp(A.data),
+                                              _dp(x), _dp(b), _ip(indices), *rs)
+
+
+def jacobi_indexed(A, x, b, indices, omega=1.0):
+    """pyamg/relaxation/relaxation.py:734-790 -> relaxation.h:382-427."""
+    A, x, b = make_system(A, x, b, formats=["csr"])
+    _f64(A, x, b)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    lib().oracle_jacobi_indexed(_ip(A.indptr), _ip(A.indices), _dp(A.data), _dp(x),
+                                A.shape[0], _dp(b), _ip(indices), len(indices),
+                                ctypes.c_double(float(omega)))
+
+
+def block_jacobi(A, x, b, Dinv=None, blocksize=1, iterations=1, omega=1.0, kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:423-499 (Dinv must be given: computing it is setup)."""
+    A, x, b = make_system(A, x, b, formats=["csr", "bsr"])
+    _f64(A, x, b)
+    A = A.tobsr(blocksize=(blocksize, blocksize))
+    if Dinv is None:
+        raise ValueError("oracle.block_jacobi needs Dinv (setup-time quantity)")
+    if Dinv.shape[0] != A.shape[0] // blocksize:
+        raise ValueError("Dinv and A have incompatible dimensions")
+    if Dinv.shape[1] != blocksize or Dinv.shape[2] != blocksize:
+        raise ValueError("Dinv and blocksize are incompatible")
+    nb = A.shape[0] // blocksize
+    if nb == 0:
+        return
+    temp = np.empty_like(x)
+    data = np.ascontiguousarray(A.data).ravel()
+    dinv = np.ascontiguousarray(Dinv, dtype=np.float64).ravel()
+    om = ctypes.c_double(float(omega))
+    for _ in range(iterations):
+        if kernels == "ref":
+            lib("ref").ref_block_jacobi(_ip(A.indptr), nb, _ip(A.indices), _dp(data),
+                                        len(A.indices), _dp(x), _dp(b), _dp(dinv), _dp(temp),
+                                        0, nb, 1, om, blocksize)
+        else:
+            lib().oracle_block_jacobi(_ip(A.indptr), _ip(A.indices), _dp(data), _dp(x), _dp(b),
+                                      _dp(dinv), _dp(temp), 0, nb, 1, om, blocksize)
+
+
+_SMOOTHERS = {
+    "jacobi": jacobi,
+    "gauss_seidel": gauss_seidel,
+    "gauss_seidel_indexed": gauss_seidel_indexed,
+    "block_jacobi": block_jacobi,
+    "sor": sor,
+}
+
+
+# --------------------------------------------------------------------------------------
+# hierarchy spec + cycle driver
+# --------------------------------------------------------------------------------------
+def smoother_spec(sm):
+    """(function-name, kwargs) of a per-level smoother object, or None.
+
+    Accepts what pyamg's change_smoothers stores (functools.partial with .func/.keywords,
+    pyamg/relaxation/smoothing.py:494-579), the no-op `none` function (:833-837), or an
+    already-neutral (name, kwargs) tuple.
+    """
+    if sm is None:
+        return None
+    if isinstance(sm, tuple):
+        return (sm[0], dict(sm[1]))
+    func = getattr(sm, "func", None)
+    if func is not None:
+        return (func.__name__, dict(sm.keywords))
+    if getattr(sm, "__name__", "") == "none":
+        return None
+    raise NotImplementedError(f"oracle: smoother {sm!r} is not introspectable")
+
+
+def hierarchy_spec(ml):
+    """Neutral description of a MultilevelSolver-like object (pyamg's or pyamg_b200's)."""
+    levels = []
+    for lvl in ml.levels:
+        d = {"A": lvl.A}
+        if hasattr(lvl, "P"):
+            d["P"] = lvl.P
+            d["R"] = lvl.R if hasattr(lvl, "R") else lvl.P.T.conjugate()
+            d["pre"] = smoother_spec(getattr(lvl, "presmoother", None))
+            d["post"] = smoother_spec(getattr(lvl, "postsmoother", None))
+        levels.append(d)
+    return levels
+
+
+def _smooth(spec, A, x, b, kernels):
+    if spec is None:
+        return
+    name, kw = spec
+    fn = _SMOOTHERS.get(name)
+    if fn is None:
+        raise NotImplementedError(f"oracle: smoother '{name}' out of hot-path scope")
+    fn(A, x, b, kernels=kernels, **kw)
+
+
+class Cycle:
+    """Restatement of MultilevelSolver.solve/__solve (pyamg/multilevel.py:398-662), V/W/F cycles,
+    'pinv' coarse solve (:717-721, GenericSolver.__call__ :797-816)."""
+
+    def __init__(self, levels, coarse_pinv=None, kernels="oracle"):
+        self.levels = levels
+        self.kernels = kernels
+        self.coarse_pinv = coarse_pinv
+
+    def coarse_solve(self, A, b):
+        if A.nnz == 0:
+            return np.zeros(b.shape)
+        if self.coarse_pinv is None:
+            self.coarse_pinv = pinv(A.toarray())
+        return np.dot(self.coarse_pinv, b)
+
+    def solve(self, b, x0=None, tol=1e-5, maxiter=100, cycle="V", residuals=None,
+              callback=None, cycles_per_level=1, return_info=False):
+        x = np.zeros_like(b) if x0 is None else np.array(x0)
+        A = self.levels[0]["A"]
+        cycle = str(cycle).upper()
+        normb = np.linalg.norm(b)
+        if normb == 0.0:
+            normb = 1.0
+        normr = np.linalg.norm(b - matvec(A, np.ravel(x), self.kernels).reshape(b.shape))
+        if residuals is not None:
+            residuals[:] = [normr]
+        b = np.ravel(np.asarray(b, dtype=np.float64))
+        x = np.ravel(np.asarray(x, dtype=np.float64))
+        it = 0
+        while True:
+            if len(self.levels) == 1:
+                x = self.coarse_solve(A, b)
+            else:
+                self._solve(0, x, b, cycle, cycles_per_level)
+            it += 1
+            normr = np.linalg.norm(b - matvec(A, x, self.kernels))
+            if residuals is not None:
+                residuals.append(normr)
+            if callback is not None:
+                callback(x)
+            if normr < tol * normb:
+                return (x, 0) if return_info else x
+            if it == maxiter:
+                return (x, it) if return_info else x
+
+    def _solve(self, lvl, x, b, cycle, cycles_per_level=1):
+        L = self.levels[lvl]
+        A = L["A"]
+        _smooth(L["pre"], A, x, b, self.kernels)
+        residual = b - matvec(A, x, self.kernels)
+        coarse_b = matvec(L["R"], residual, self.kernels)
+        coarse_x = np.zeros_like(coarse_b)
+        if lvl == len(self.levels) - 2:
+            coarse_x[:] = self.coarse_solve(self.levels[-1]["A"], coarse_b)
+        elif cycle == "V":
+            self._solve(lvl + 1, coarse_x, coarse_b, "V")
+        elif cycle == "W":
+            self._solve(lvl + 1, coarse_x, coarse_b, cycle)
+            self._solve(lvl + 1, coarse_x, coarse_b, cycle)
+        elif cycle == "F":
+            self._solve(lvl + 1, coarse_x, coarse_b, cycle, cycles_per_level)
+            for _ in range(cycles_per_level):
+                self._solve(lvl + 1, coarse_x, coarse_b, "V", 1)
+        else:
+            raise TypeError(f"Unrecognized cycle type ({cycle})")
+        x += matvec(L["P"], coarse_x, self.kernels)
+        _smooth(L["post"], A, x, b, self.kernels)

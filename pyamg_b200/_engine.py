@@ -1,0 +1,181 @@
+"""ctypes binding of the C ABI in include/pyamg_b200.h (libpyamg_b200.so).
+
+There is deliberately NO fallback: if the CUDA library is missing or no CUDA device is visible,
+every entry point raises.  (The reference-side binding a pyamg maintainer would add is this file's
+shape: see INTEGRATION.md.)
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+
+OK, EINVAL, ECUDA, ENOTIMPL, ESTATE = 0, -1, -2, -3, -4
+SM_NONE, SM_JACOBI, SM_GAUSS_SEIDEL, SM_BLOCK_JACOBI = 0, 1, 2, 3
+SWEEPS = {"forward": 0, "backward": 1, "symmetric": 2}
+CYCLES = {"V": 0, "W": 1, "F": 2}
+
+
+class Matrix(ctypes.Structure):
+    _fields_ = [("n_rows", ctypes.c_int32), ("n_cols", ctypes.c_int32),
+                ("block_r", ctypes.c_int32), ("block_c", ctypes.c_int32),
+                ("nnz_blocks", ctypes.c_int64),
+                ("indptr", c_i32p), ("indices", c_i32p), ("data", c_f64p)]
+
+
+class Smoother(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("iterations", ctypes.c_int32),
+                ("sweep", ctypes.c_int32), ("blocksize", ctypes.c_int32),
+                ("omega", ctypes.c_double),
+                ("indices", c_i32p), ("n_indices", ctypes.c_int64),
+                ("Dinv", c_f64p)]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/pyamg_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "amgb_last_error", "amgb_version", "amgb_device_count",
+    "amgb_hierarchy_create", "amgb_hierarchy_destroy", "amgb_hierarchy_add_level",
+    "amgb_hierarchy_set_coarse_pinv", "amgb_hierarchy_finalize", "amgb_solve",
+    "amgb_solve_device", "amgb_hierarchy_num_levels", "amgb_hierarchy_device_bytes",
+    "amgb_hierarchy_last_launches", "amgb_host_alloc", "amgb_host_free",
+    "amgb_host_jacobi", "amgb_host_gauss_seidel", "amgb_host_sor_gauss_seidel",
+    "amgb_host_gauss_seidel_indexed",
+    "amgb_host_bsr_jacobi", "amgb_host_block_jacobi", "amgb_host_matvec",
+    "amgb_dev_csr_spmv", "amgb_dev_csr_residual", "amgb_dev_csr_spmv_add", "amgb_dev_csr_jacobi",
+    "amgb_dev_csr_gs_wave", "amgb_dev_partials_len", "amgb_dev_dense_matvec", "amgb_dev_fill",
+]
+
+
+def lib():
+    """Load libpyamg_b200.so (building it in-tree when nvcc is around). Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build_extension()
+    if not os.path.exists(path):
+        raise EngineError("libpyamg_b200.so is missing: run `python -m pyamg_b200.build` "
+                          "(there is no CPU fallback)")
+    L = ctypes.CDLL(path)
+    L.amgb_last_error.restype = ctypes.c_char_p
+    L.amgb_hierarchy_device_bytes.restype = ctypes.c_int64
+    L.amgb_hierarchy_last_launches.restype = ctypes.c_int64
+    L.amgb_dev_partials_len.restype = ctypes.c_int64
+    L.amgb_hierarchy_destroy.restype = None
+    vp, i32, i64, f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+    L.amgb_hierarchy_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    L.amgb_hierarchy_destroy.argtypes = [vp]
+    L.amgb_hierarchy_add_level.argtypes = [vp, ctypes.POINTER(Matrix), ctypes.POINTER(Matrix),
+                                           ctypes.POINTER(Matrix), ctypes.POINTER(Smoother),
+                                           ctypes.POINTER(Smoother)]
+    L.amgb_hierarchy_set_coarse_pinv.argtypes = [vp, i32, c_f64p, i32]
+    L.amgb_hierarchy_finalize.argtypes = [vp, vp]
+    L.amgb_solve.argtypes = [vp, vp, vp, f64, i32, i32, i32, c_f64p, c_i32p, c_i32p]
+    L.amgb_solve_device.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.amgb_hierarchy_num_levels.argtypes = [vp]
+    L.amgb_hierarchy_device_bytes.argtypes = [vp]
+    L.amgb_hierarchy_last_launches.argtypes = [vp]
+    L.amgb_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    L.amgb_host_free.argtypes = [vp]
+    ci = ctypes.c_int
+    L.amgb_host_jacobi.argtypes = [c_i32p, ci, c_i32p, ci, c_f64p, ci, c_f64p, ci, c_f64p, ci,
+                                   c_f64p, ci, i32, i32, i32, c_f64p, ci]
+    L.amgb_host_gauss_seidel.argtypes = [c_i32p, ci, c_i32p, ci, c_f64p, ci, c_f64p, ci, c_f64p, ci,
+                                         i32, i32, i32]
+    L.amgb_host_sor_gauss_seidel.argtypes = [c_i32p, ci, c_i32p, ci, c_f64p, ci, c_f64p, ci, c_f64p, ci,
+                                             i32, i32, i32, f64]
+    L.amgb_host_gauss_seidel_indexed.argtypes = [c_i32p, ci, c_i32p, ci, c_f64p, ci, c_f64p, ci,
+                                                 c_f64p, ci, c_i32p, ci, i32, i32, i32]
+    L.amgb_host_bsr_jacobi.argtypes = [c_i32p, ci, c_i32p, ci, c_f64p, ci, c_f64p, ci, c_f64p, ci,
+                                       c_f64p, ci, i32, i32, i32, i32, c_f64p, ci]
+    L.amgb_host_block_jacobi.argtypes = [c_i32p, ci, c_i32p, ci, c_f64p, ci, c_f64p, ci, c_f64p, ci,
+                                         c_f64p, ci, c_f64p, ci, i32, i32, i32, c_f64p, ci, i32]
+    L.amgb_host_matvec.argtypes = [ctypes.POINTER(Matrix), c_f64p, c_f64p]
+    L.amgb_dev_csr_spmv.argtypes = [i32, vp, vp, vp, vp, vp, ci, vp]
+    L.amgb_dev_csr_residual.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, ci, vp]
+    L.amgb_dev_csr_spmv_add.argtypes = [i32, vp, vp, vp, vp, vp, ci, vp]
+    L.amgb_dev_csr_jacobi.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, f64, ci, vp]
+    L.amgb_dev_csr_gs_wave.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, f64, ci, vp]
+    L.amgb_dev_partials_len.argtypes = [i32, ci]
+    L.amgb_dev_dense_matvec.argtypes = [i32, i32, vp, vp, vp, vp]
+    L.amgb_dev_fill.argtypes = [vp, i64, f64, vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    """Map C error codes onto the exception types the reference raises for the same misuse."""
+    if rc == OK:
+        return
+    msg = lib().amgb_last_error().decode("utf8", "replace")
+    if rc == EINVAL:
+        raise ValueError(msg)
+    if rc == ENOTIMPL:
+        raise NotImplementedError(msg)
+    if rc == ESTATE:
+        raise EngineError("engine state: " + msg)
+    raise EngineError("CUDA: " + msg)
+
+
+def require_gpu():
+    if lib().amgb_device_count() < 1:
+        raise EngineError("no CUDA device visible: pyamg_b200 has no CPU fallback")
+
+
+def i32p(a):
+    return a.ctypes.data_as(c_i32p)
+
+
+def f64p(a):
+    return a.ctypes.data_as(c_f64p)
+
+
+def as_matrix(M, keep):
+    """scipy csr/bsr (any object with .format/.indptr/.indices/.data) -> C `amgb_matrix`.
+
+    Normalised arrays are appended to `keep` so they outlive the ctypes struct.
+    """
+    fmt = getattr(M, "format", None)
+    if fmt not in ("csr", "bsr"):
+        M = M.tocsr()
+        fmt = "csr"
+    if M.dtype != np.float64:
+        if np.issubdtype(M.dtype, np.complexfloating):
+            raise NotImplementedError("complex operators are outside the fp64 hot path")
+        M = M.astype(np.float64)
+    indptr = np.ascontiguousarray(M.indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(M.indices, dtype=np.int32)
+    data = np.ascontiguousarray(M.data, dtype=np.float64)
+    R, C = (M.blocksize if fmt == "bsr" else (1, 1))
+    keep += [indptr, indices, data]
+    return Matrix(int(M.shape[0]), int(M.shape[1]), int(R), int(C), int(len(indices)),
+                  i32p(indptr), i32p(indices), f64p(data.reshape(-1)))
+
+
+def pinned_empty(n, dtype=np.float64):
+    """Page-locked host array (cudaHostAlloc) for the e2e path; freed when garbage-collected."""
+    dtype = np.dtype(dtype)
+    p = ctypes.c_void_p()
+    check(lib().amgb_host_alloc(ctypes.c_size_t(int(n) * dtype.itemsize), ctypes.byref(p)))
+    buf = (ctypes.c_char * (int(n) * dtype.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+    _PINNED[id(arr)] = (p, arr)   # keep alive; released by free_pinned
+    return arr
+
+
+_PINNED = {}
+
+
+def free_pinned(arr):
+    ent = _PINNED.pop(id(arr), None)
+    if ent is not None:
+        lib().amgb_host_free(ent[0])

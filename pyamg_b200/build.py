@@ -1,0 +1,52 @@
+"""In-tree build of libpyamg_b200.so (sm_100a only).
+
+  python -m pyamg_b200.build            # or __graft_entry__.build()
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels with the gpurun snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+LIB = os.path.join(PKG, "libpyamg_b200.so")
+SOURCES = [os.path.join(PKG, "csrc", "engine.cu")]
+HEADERS = [os.path.join(PKG, "csrc", f) for f in sorted(os.listdir(os.path.join(PKG, "csrc")))
+           if f.endswith((".cuh", ".h"))] + [os.path.join(ROOT, "include", "pyamg_b200.h")]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(s) > t for s in SOURCES + HEADERS if os.path.exists(s))
+
+
+def build_extension(force=False, verbose=False):
+    """Compile the CUDA engine if missing or older than its sources. Returns the .so path."""
+    if not force and not is_stale():
+        return LIB
+    nvcc = nvcc_path()
+    if nvcc is None:
+        if os.path.exists(LIB):
+            return LIB   # GPU box without nvcc on PATH: use the prebuilt library
+        raise RuntimeError("nvcc not found and libpyamg_b200.so is not built")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + SOURCES
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_extension(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,217 @@
+// csr_kernels.cuh -- sm_100a CUDA kernels for the AMG solve-phase hot path (CSR operators).
+//
+// One kernel family, "G lanes per row": a group of G consecutive lanes (G = 2..32, chosen
+// per operator from its mean row length) owns one row, strides over the row's (col,val)
+// pairs with coalesced streaming loads, gathers x through the read-only/L1 path, and folds
+// the partial sums with warp shuffles.  The epilogue is a template parameter so that every
+// step of the V-cycle is ONE pass over its operator:
+//
+//   OP_SPMV    y_i  = sum_j a_ij x_j                          (restriction  b_c = R r;  SciPy csr_matvec,
+//                                                              reference call site pyamg/multilevel.py:614)
+//   OP_RESID   r_i  = b_i - sum_j a_ij x_j  [+ |r|^2 partials] (multilevel.py:612, :545/:567 with the norm fused)
+//   OP_PADD    x_i += sum_j p_ij xc_j                          (multilevel.py:660, correction fused into the SpMV)
+//   OP_JACOBI  x'_i = (1-w) x_i + w (b_i - sum_{j!=i} a_ij x_j)/a_ii ; optional r_i = b_i - (A x)_i
+//                                                              (pyamg/amg_core/relaxation.h:309-346; the Jacobi sweep
+//                                                              fused with the residual SpMV: one pass, two outputs)
+//   OP_GS      x_i  = w (b_i - sum_{j!=i} a_ij x_j)/a_ii + (1-w) x_i  in place, over an independent set of rows
+//                                                              (relaxation.h:48-76 / :736-768 executed wave by wave)
+//
+// Reference quirks honoured: the diagonal is found by col==row (indices
+// may be unsorted), the LAST stored duplicate of the diagonal wins, a zero diagonal leaves the
+// row untouched.
+//
+// Roofline: all of these are HBM-bound (0.17 flop/byte); algorithmic bytes per launch are
+// 12*nnz + 4*(n+1) + {16,24,24,32(+8),24(+4 indexed)}*n  (SURVEY.md 8(d)).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace amgb {
+
+enum CsrOp { OP_SPMV = 0, OP_RESID = 1, OP_PADD = 2, OP_JACOBI = 3, OP_GS = 4 };
+
+struct CsrRowArgs {
+    int n;                 // rows handled by this launch
+    int row0;              // first row (contiguous mode, rows == nullptr)
+    const int *rows;       // explicit row list (indexed mode) or nullptr
+    const int *Ap;
+    const int *Aj;
+    const double *Ax;
+    const double *x;       // gathered vector (for OP_GS this aliases y)
+    const double *b;
+    double *y;             // output: y / r / x (PADD, GS in place) / x' (JACOBI)
+    double *r;             // OP_JACOBI: optional residual by-product (nullptr = skip)
+    double omega;
+    double *partials;      // OP_RESID / OP_JACOBI(r): optional per-block sum of r_i^2 (nullptr = skip)
+};
+
+// streaming loads for the operator arrays: read once, keep them out of L1 so the x gathers own it
+__device__ __forceinline__ int ld_stream_i32(const int *p)
+{
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+    return v;
+}
+
+// block-wide sum of one double per thread -> thread 0 (fixed order: deterministic)
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v)
+{
+    __shared__ double s_part[THREADS / 32];
+    v = group_sum<32>(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) s_part[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < THREADS / 32; i++) t += s_part[i];
+    }
+    return t;
+}
+
+constexpr int kCsrThreads = 256;
+
+template <int G, int OP, bool INDEXED>
+__global__ void __launch_bounds__(kCsrThreads) csr_rows_kernel(const CsrRowArgs a)
+{
+    constexpr bool kNeedDiag = (OP == OP_JACOBI || OP == OP_GS);
+    const int lane = threadIdx.x & (G - 1);
+    const long long k = ((long long)blockIdx.x * kCsrThreads + threadIdx.x) / G;
+    const bool active = k < a.n;
+    double r2 = 0.0;  // this thread's contribution to |r|^2
+
+    // inactive groups still take part in the shuffles / block reduction below
+    int row = 0, start = 0, end = 0;
+    if (active) {
+        row = INDEXED ? a.rows[k] : a.row0 + (int)k;
+        start = a.Ap[row];
+        end = a.Ap[row + 1];
+    }
+    double sum = 0.0, diag = 0.0;
+    int jd = -1;
+    for (int jj = start + lane; jj < end; jj += G) {
+        const int c = ld_stream_i32(a.Aj + jj);
+        const double v = ld_stream_f64(a.Ax + jj);
+        if (kNeedDiag && c == row) {
+            diag = v;   // later duplicates overwrite: jj increases within a lane
+            jd = jj;
+        } else {
+            const double xv = (OP == OP_GS) ? a.x[c] : __ldg(a.x + c);
+            sum += v * xv;
+        }
+    }
+    sum = group_sum<G>(sum);
+    if (kNeedDiag) {
+        // last stored diagonal duplicate wins (relaxation.h:66-69): keep the one with max jj
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            const int jo = __shfl_xor_sync(0xffffffffu, jd, o, G);
+            const double dv = __shfl_xor_sync(0xffffffffu, diag, o, G);
+            if (jo > jd) { jd = jo; diag = dv; }
+        }
+    }
+    if (active && lane == 0) {
+        if (OP == OP_SPMV) {
+            a.y[row] = sum;
+        } else if (OP == OP_RESID) {
+            const double r = a.b[row] - sum;
+            a.y[row] = r;
+            r2 = r * r;
+        } else if (OP == OP_PADD) {
+            a.y[row] += sum;
+        } else if (OP == OP_JACOBI) {
+            const double xi = a.x[row];
+            const double bi = a.b[row];
+            double xn = xi;
+            if (diag != 0.0) xn = (1.0 - a.omega) * xi + a.omega * ((bi - sum) / diag);
+            a.y[row] = xn;
+            if (a.r != nullptr) {
+                const double r = bi - sum - diag * xi;   // residual of the INPUT iterate
+                a.r[row] = r;
+                r2 = r * r;
+            }
+        } else {  // OP_GS (omega != 1: sor_gauss_seidel, relaxation.h:116-145)
+            if (diag != 0.0) {
+                const double g = (a.b[row] - sum) / diag;
+                a.y[row] = (a.omega == 1.0) ? g : a.omega * g + (1.0 - a.omega) * a.y[row];
+            }
+        }
+    }
+    if ((OP == OP_RESID || OP == OP_JACOBI) && a.partials != nullptr) {
+        const double t = block_sum<kCsrThreads>(r2);
+        if (threadIdx.x == 0) a.partials[blockIdx.x] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small vector kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void fill_kernel(double *x, long long n, double v)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) x[i] = v;
+}
+
+// partials[b] = sum of x_i^2 over block b's grid-stride share (fixed grid -> deterministic)
+constexpr int kSumsqBlocks = 148 * 8;
+__global__ void __launch_bounds__(256) sumsq_partials_kernel(const double *__restrict__ x, long long n,
+                                                             double *__restrict__ partials)
+{
+    double t = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        t += x[i] * x[i];
+    t = block_sum<256>(t);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+// out[slot] = sum(partials[0..m)) in a fixed order (single block) -> deterministic norms
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *partials, int m,
+                                                               double *out)
+{
+    double t = 0.0;
+    for (int i = threadIdx.x; i < m; i += 1024) t += partials[i];
+    t = block_sum<1024>(t);
+    if (threadIdx.x == 0) *out = t;
+}
+
+// y (m) = M (m x n, row-major) * x (n): the cached dense pseudo-inverse of the coarsest
+// operator applied to the coarse rhs (pyamg/multilevel.py:717-721, `np.dot(self.P, b)`).
+// One warp per row; coarsest grids have 2..500 unknowns, so this is latency-, not bandwidth-bound.
+__global__ void dense_matvec_kernel(int m, int n, const double *__restrict__ M,
+                                    const double *__restrict__ x, double *__restrict__ y)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int l = threadIdx.x & 31;
+    if (w >= m) return;
+    double s = 0.0;
+    for (int j = l; j < n; j += 32) s += M[(size_t)w * n + j] * x[j];
+    s = group_sum<32>(s);
+    if (l == 0) y[w] = s;
+}
+
+// gather/scatter used for permuted layouts and halo packing: out[i] = in[idx[i]]
+__global__ void gather_kernel(const double *__restrict__ in, const int *__restrict__ idx,
+                              double *__restrict__ out, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = in[idx[i]];
+}
+
+}  // namespace amgb

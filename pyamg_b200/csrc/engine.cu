@@ -1,0 +1,1166 @@
+// engine.cu -- B200-native AMG solve-phase engine: hierarchy in HBM, cycle driver, C ABI.
+//
+// Replaces (paths relative to the reference tree):
+//   pyamg/multilevel.py:398-582   MultilevelSolver.solve      -> amgb_solve
+//   pyamg/multilevel.py:584-662   MultilevelSolver.__solve    -> Engine::cycle (V/W/F, captured as CUDA graphs)
+//   pyamg/multilevel.py:717-721   'pinv' coarse solver apply   -> dense_matvec_kernel
+//   pyamg/relaxation/relaxation.py + pyamg/amg_core/relaxation.h sweeps -> csr_kernels.cuh
+//   scipy csr_matvec/bsr_matvec call sites multilevel.py:545,567,612,614,660 -> csr_rows_kernel<...>
+//
+// Design: one process per GPU; every operator of the hierarchy lives in HBM as int32/fp64 CSR
+// (BSR blocks are expanded to point CSR at upload: same per-row summation order as bsr_matvec);
+// all level vectors are preallocated; a cycle is a fixed launch sequence, captured once per
+// cycle type into a CUDA graph so that the launch-latency-bound coarse levels cost ~1 graph node
+// each instead of a Python round trip.  No CPU fallback anywhere.
+#include "../../include/pyamg_b200.h"
+#include "csr_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace amgb;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(AMGB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_) +      \
+                                        " (" __FILE__ ":" + std::to_string(__LINE__) + ")");  \
+    } while (0)
+
+#define RET(call)                 \
+    do {                          \
+        int rc_ = (call);         \
+        if (rc_ != AMGB_OK) return rc_; \
+    } while (0)
+
+extern "C" const char *amgb_last_error(void) { return g_err.c_str(); }
+extern "C" int amgb_version(void) { return 100; }
+extern "C" int amgb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------
+static int pick_lanes(long long nnz, long long n_rows)
+{
+    const char *env = getenv("AMGB_LANES");
+    if (env != nullptr) {
+        int v = atoi(env);
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) return v;
+    }
+    if (n_rows <= 0) return 4;
+    const double avg = (double)nnz / (double)n_rows;
+    int g = 2;
+    while (g < 32 && (double)g < avg) g <<= 1;   // smallest power of two >= mean row length
+    return g;
+}
+
+static inline long long csr_grid(long long n, int lanes)
+{
+    return (n * lanes + kCsrThreads - 1) / kCsrThreads;
+}
+
+template <int OP, bool INDEXED>
+static int launch_csr_g(int lanes, const CsrRowArgs &a, cudaStream_t s)
+{
+    if (a.n <= 0) return AMGB_OK;
+    const long long grid = csr_grid(a.n, lanes);
+    if (grid > 2147483647LL) return fail(AMGB_EINVAL, "launch grid too large");
+    const dim3 g((unsigned)grid), b(kCsrThreads);
+    switch (lanes) {
+    case 1: csr_rows_kernel<1, OP, INDEXED><<<g, b, 0, s>>>(a); break;
+    case 2: csr_rows_kernel<2, OP, INDEXED><<<g, b, 0, s>>>(a); break;
+    case 4: csr_rows_kernel<4, OP, INDEXED><<<g, b, 0, s>>>(a); break;
+    case 8: csr_rows_kernel<8, OP, INDEXED><<<g, b, 0, s>>>(a); break;
+    case 16: csr_rows_kernel<16, OP, INDEXED><<<g, b, 0, s>>>(a); break;
+    case 32: csr_rows_kernel<32, OP, INDEXED><<<g, b, 0, s>>>(a); break;
+    default: return fail(AMGB_EINVAL, "lanes must be a power of two in 1..32");
+    }
+    CK(cudaGetLastError());
+    return AMGB_OK;
+}
+
+static int launch_csr(int op, int lanes, const CsrRowArgs &a, cudaStream_t s)
+{
+    const bool idx = a.rows != nullptr;
+    switch (op) {
+    case OP_SPMV: return idx ? launch_csr_g<OP_SPMV, true>(lanes, a, s) : launch_csr_g<OP_SPMV, false>(lanes, a, s);
+    case OP_RESID: return idx ? launch_csr_g<OP_RESID, true>(lanes, a, s) : launch_csr_g<OP_RESID, false>(lanes, a, s);
+    case OP_PADD: return idx ? launch_csr_g<OP_PADD, true>(lanes, a, s) : launch_csr_g<OP_PADD, false>(lanes, a, s);
+    case OP_JACOBI: return idx ? launch_csr_g<OP_JACOBI, true>(lanes, a, s) : launch_csr_g<OP_JACOBI, false>(lanes, a, s);
+    case OP_GS: return idx ? launch_csr_g<OP_GS, true>(lanes, a, s) : launch_csr_g<OP_GS, false>(lanes, a, s);
+    }
+    return fail(AMGB_EINVAL, "unknown csr op");
+}
+
+static int launch_fill(double *x, long long n, double v, cudaStream_t s)
+{
+    if (n <= 0) return AMGB_OK;
+    long long grid = std::min<long long>((n + 255) / 256, 148 * 16);
+    fill_kernel<<<(unsigned)grid, 256, 0, s>>>(x, n, v);
+    CK(cudaGetLastError());
+    return AMGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// device containers
+// ------------------------------------------------------------------------------------------
+struct HostCsr {   // point CSR on the host (BSR already expanded)
+    int n_rows = 0, n_cols = 0;
+    std::vector<int> Ap, Aj;
+    std::vector<double> Ax;
+};
+
+struct DevCsr {
+    int n_rows = 0, n_cols = 0;
+    long long nnz = 0;
+    int *Ap = nullptr, *Aj = nullptr;
+    double *Ax = nullptr;
+    int lanes = 8;
+};
+
+struct WaveSchedule {       // a sequential sweep over a row list, regrouped into dependency waves
+    int *rows = nullptr;    // device, wave-major
+    std::vector<long long> ptr;   // wave w = rows[ptr[w] .. ptr[w+1])
+    bool natural_single = false;  // one wave covering rows 0..n-1 in order -> contiguous launch
+};
+
+struct Smoother {
+    int kind = AMGB_SM_NONE;
+    int iterations = 1;
+    int sweep = AMGB_SWEEP_FORWARD;
+    int bs = 1;
+    double omega = 1.0;
+    WaveSchedule ws;
+    double *Dinv = nullptr;
+};
+
+struct Level {
+    DevCsr A, P, R;
+    bool has_pr = false;
+    Smoother pre, post;
+    double *x = nullptr, *x_home = nullptr, *xalt = nullptr, *b = nullptr, *r = nullptr;
+};
+
+static int validate_matrix(const amgb_matrix *M, const char *name)
+{
+    if (M == nullptr) return fail(AMGB_EINVAL, std::string(name) + ": null matrix");
+    if (M->block_r < 1 || M->block_c < 1) return fail(AMGB_EINVAL, std::string(name) + ": bad blocksize");
+    if (M->n_rows < 0 || M->n_cols < 0 || M->n_rows % M->block_r || M->n_cols % M->block_c)
+        return fail(AMGB_EINVAL, std::string(name) + ": dimensions not divisible by blocksize");
+    if (M->indptr == nullptr || (M->nnz_blocks > 0 && (M->indices == nullptr || M->data == nullptr)))
+        return fail(AMGB_EINVAL, std::string(name) + ": null arrays");
+    const int nb = M->n_rows / M->block_r;
+    if (M->indptr[0] != 0 || (long long)M->indptr[nb] != M->nnz_blocks)
+        return fail(AMGB_EINVAL, std::string(name) + ": indptr inconsistent with nnz");
+    if (M->nnz_blocks * M->block_r * M->block_c > 2147483647LL)
+        return fail(AMGB_EINVAL, std::string(name) + ": nnz exceeds int32 (reference index type)");
+    return AMGB_OK;
+}
+
+// BSR -> point CSR keeping the storage order (block by block, columns ascending inside a block):
+// the per-row summation order then equals scipy's bsr_matvec.
+static int to_host_csr(const amgb_matrix *M, HostCsr &H, const char *name)
+{
+    RET(validate_matrix(M, name));
+    const int R = M->block_r, C = M->block_c, nb = M->n_rows / R;
+    H.n_rows = M->n_rows;
+    H.n_cols = M->n_cols;
+    const long long nnz = M->nnz_blocks * R * C;
+    H.Ap.resize((size_t)M->n_rows + 1);
+    H.Aj.resize((size_t)nnz);
+    H.Ax.resize((size_t)nnz);
+    const int ncb = M->n_cols / C;
+    if (R == 1 && C == 1) {
+        std::copy(M->indptr, M->indptr + nb + 1, H.Ap.begin());
+        std::copy(M->indices, M->indices + nnz, H.Aj.begin());
+        std::copy(M->data, M->data + nnz, H.Ax.begin());
+        for (long long k = 0; k < nnz; k++)
+            if (H.Aj[k] < 0 || H.Aj[k] >= M->n_cols)
+                return fail(AMGB_EINVAL, std::string(name) + ": column index out of range");
+        for (int i = 0; i < nb; i++)
+            if (H.Ap[i + 1] < H.Ap[i]) return fail(AMGB_EINVAL, std::string(name) + ": indptr not monotone");
+        return AMGB_OK;
+    }
+    long long pos = 0;
+    for (int I = 0; I < nb; I++) {
+        const int s = M->indptr[I], e = M->indptr[I + 1];
+        if (e < s) return fail(AMGB_EINVAL, std::string(name) + ": indptr not monotone");
+        for (int r = 0; r < R; r++) {
+            H.Ap[(size_t)I * R + r] = (int)pos;
+            for (int jj = s; jj < e; jj++) {
+                const int J = M->indices[jj];
+                if (J < 0 || J >= ncb) return fail(AMGB_EINVAL, std::string(name) + ": block column out of range");
+                const double *blk = M->data + (size_t)jj * R * C + (size_t)r * C;
+                for (int c = 0; c < C; c++) {
+                    H.Aj[pos] = J * C + c;
+                    H.Ax[pos] = blk[c];
+                    pos++;
+                }
+            }
+        }
+    }
+    H.Ap[M->n_rows] = (int)pos;
+    return AMGB_OK;
+}
+
+// sequential sweep over `list` (nullptr = 0..n-1) -> dependency waves.  Position k (row i) goes to
+// wave 1 + max(last write wave of any j it reads, last wave in which x_i was read or written), so
+// executing waves in order, rows of one wave concurrently, reproduces the sequential result.
+static void build_waves(const HostCsr &A, const int *list, long long m, std::vector<int> &rows_sorted,
+                        std::vector<long long> &ptr)
+{
+    const int n = A.n_rows;
+    std::vector<int> wwave((size_t)n, 0), rwave((size_t)n, 0), w((size_t)m);
+    int maxw = 0;
+    for (long long k = 0; k < m; k++) {
+        const int i = list ? list[k] : (int)k;
+        int wv = std::max(rwave[i], wwave[i]);
+        for (int jj = A.Ap[i]; jj < A.Ap[i + 1]; jj++) {
+            const int j = A.Aj[jj];
+            if (j != i && j < n) wv = std::max(wv, wwave[j]);
+        }
+        wv += 1;
+        w[(size_t)k] = wv;
+        wwave[i] = wv;
+        for (int jj = A.Ap[i]; jj < A.Ap[i + 1]; jj++) {
+            const int j = A.Aj[jj];
+            if (j != i && j < n) rwave[j] = std::max(rwave[j], wv);
+        }
+        maxw = std::max(maxw, wv);
+    }
+    ptr.assign((size_t)maxw + 1, 0);
+    for (long long k = 0; k < m; k++) ptr[(size_t)w[(size_t)k]]++;
+    for (int q = 0; q < maxw; q++) ptr[(size_t)q + 1] += ptr[(size_t)q];
+    rows_sorted.resize((size_t)m);
+    std::vector<long long> cur(ptr.begin(), ptr.end() - 1);
+    for (long long k = 0; k < m; k++) {
+        const int i = list ? list[k] : (int)k;
+        rows_sorted[(size_t)cur[(size_t)w[(size_t)k] - 1]++] = i;
+    }
+    for (int q = 0; q < maxw; q++)   // ascending rows inside a wave: better locality, same result
+        std::sort(rows_sorted.begin() + ptr[(size_t)q], rows_sorted.begin() + ptr[(size_t)q + 1]);
+}
+
+// ------------------------------------------------------------------------------------------
+// the engine
+// ------------------------------------------------------------------------------------------
+struct amgb_hierarchy {
+    int device = 0;
+    std::vector<Level> levels;
+    std::vector<void *> allocs;
+    long long dev_bytes = 0;
+    bool finalized = false;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    double *coarse_pinv = nullptr;
+    int coarse_n = 0;
+    bool coarse_zero = false;
+    bool have_coarse = false;
+
+    double *partials = nullptr;   // level-0 residual-norm partial sums
+    long long n_partials = 0;
+    double *norms2 = nullptr;     // device array of squared residual norms
+    int norms2_cap = 0;
+    double *norm_host = nullptr;  // pinned scalar for the tol test
+    double *sumsq_parts = nullptr;
+
+    cudaGraphExec_t graph[3] = {nullptr, nullptr, nullptr};
+    int graph_cpl[3] = {0, 0, 0};
+    long long graph_nodes[3] = {0, 0, 0};
+    long long launches = 0;        // kernels issued by the current (or captured) sequence
+    long long last_launches = 0;
+    bool use_graph = true;
+
+    template <typename T>
+    int dalloc(T **p, long long count)
+    {
+        *p = nullptr;
+        size_t bytes = (size_t)std::max<long long>(count, 1) * sizeof(T);
+        bytes = (bytes + 255) & ~(size_t)255;
+        void *q = nullptr;
+        CK(cudaMalloc(&q, bytes));
+        allocs.push_back(q);
+        dev_bytes += (long long)bytes;
+        *p = (T *)q;
+        return AMGB_OK;
+    }
+
+    template <typename T>
+    int upload(T **p, const T *src, long long count)
+    {
+        RET(dalloc(p, count));
+        if (count > 0) CK(cudaMemcpy(*p, src, (size_t)count * sizeof(T), cudaMemcpyHostToDevice));
+        return AMGB_OK;
+    }
+
+    int upload_csr(const HostCsr &H, DevCsr &D)
+    {
+        D.n_rows = H.n_rows;
+        D.n_cols = H.n_cols;
+        D.nnz = (long long)H.Aj.size();
+        RET(upload(&D.Ap, H.Ap.data(), (long long)H.Ap.size()));
+        RET(upload(&D.Aj, H.Aj.data(), D.nnz));
+        RET(upload(&D.Ax, H.Ax.data(), D.nnz));
+        D.lanes = pick_lanes(D.nnz, D.n_rows);
+        return AMGB_OK;
+    }
+
+    int setup_smoother(const amgb_smoother *in, const HostCsr &A, Smoother &s)
+    {
+        s = Smoother();
+        if (in == nullptr || in->kind == AMGB_SM_NONE) return AMGB_OK;
+        s.kind = in->kind;
+        s.iterations = in->iterations;
+        s.sweep = in->sweep;
+        s.omega = in->omega;
+        if (s.iterations < 0) return fail(AMGB_EINVAL, "smoother iterations < 0");
+        if (A.n_rows != A.n_cols) return fail(AMGB_EINVAL, "expected square matrix");   // relaxation.py:81-82
+        switch (in->kind) {
+        case AMGB_SM_JACOBI: return AMGB_OK;
+        case AMGB_SM_GAUSS_SEIDEL: {
+            if (s.sweep < 0 || s.sweep > 2)
+                return fail(AMGB_EINVAL, "valid sweep directions: \"forward\", \"backward\", and \"symmetric\"");
+            const long long m = in->indices ? in->n_indices : A.n_rows;
+            for (long long k = 0; in->indices && k < m; k++)
+                if (in->indices[k] < 0 || in->indices[k] >= A.n_rows)
+                    return fail(AMGB_EINVAL, "gauss_seidel_indexed: row index out of range");
+            std::vector<int> rows;
+            build_waves(A, in->indices, m, rows, s.ws.ptr);
+            RET(upload(&s.ws.rows, rows.data(), m));
+            return AMGB_OK;
+        }
+        case AMGB_SM_BLOCK_JACOBI: {
+            s.bs = in->blocksize;
+            if (s.bs < 1 || s.bs > 8 || A.n_rows % s.bs)
+                return fail(AMGB_ENOTIMPL, "block_jacobi: blocksize must be 1..8 and divide n");
+            if (in->Dinv == nullptr) return fail(AMGB_EINVAL, "block_jacobi: Dinv required");
+            RET(upload(&s.Dinv, in->Dinv, (long long)A.n_rows * s.bs));
+            return AMGB_OK;
+        }
+        }
+        return fail(AMGB_ENOTIMPL, "smoother kind outside the hot-path scope");
+    }
+
+    // ---- launch sequence pieces (all on `stream`) ----
+    int spmv(int op, const DevCsr &M, const double *x, const double *b, double *y, double omega = 0.0,
+             double *r = nullptr, double *parts = nullptr)
+    {
+        CsrRowArgs a;
+        a.n = M.n_rows; a.row0 = 0; a.rows = nullptr;
+        a.Ap = M.Ap; a.Aj = M.Aj; a.Ax = M.Ax;
+        a.x = x; a.b = b; a.y = y; a.r = r; a.omega = omega; a.partials = parts;
+        launches += (a.n > 0);
+        return launch_csr(op, M.lanes, a, stream);
+    }
+
+    int gs_wave(const DevCsr &A, const WaveSchedule &ws, long long w, double *x, const double *b, double omega)
+    {
+        CsrRowArgs a;
+        a.n = (int)(ws.ptr[(size_t)w + 1] - ws.ptr[(size_t)w]);
+        a.row0 = 0; a.rows = ws.rows + ws.ptr[(size_t)w];
+        a.Ap = A.Ap; a.Aj = A.Aj; a.Ax = A.Ax;
+        a.x = x; a.b = b; a.y = x; a.r = nullptr; a.omega = omega; a.partials = nullptr;
+        launches += (a.n > 0);
+        return launch_csr(OP_GS, A.lanes, a, stream);
+    }
+
+    int block_jacobi(Level &L, const Smoother &s);   // defined below (needs its kernel)
+
+    int smooth(Level &L, const Smoother &s)
+    {
+        switch (s.kind) {
+        case AMGB_SM_NONE: return AMGB_OK;
+        case AMGB_SM_JACOBI:
+            for (int it = 0; it < s.iterations; it++) {
+                RET(spmv(OP_JACOBI, L.A, L.x, L.b, L.xalt, s.omega));
+                std::swap(L.x, L.xalt);
+            }
+            return AMGB_OK;
+        case AMGB_SM_GAUSS_SEIDEL: {
+            const long long nw = (long long)s.ws.ptr.size() - 1;
+            // relaxation.py:326-330: the symmetric sweep recurses WITHOUT omega (plain GS)
+            const double om = (s.sweep == AMGB_SWEEP_SYMMETRIC) ? 1.0 : s.omega;
+            for (int it = 0; it < s.iterations; it++) {
+                if (s.sweep == AMGB_SWEEP_FORWARD || s.sweep == AMGB_SWEEP_SYMMETRIC)
+                    for (long long w = 0; w < nw; w++) RET(gs_wave(L.A, s.ws, w, L.x, L.b, om));
+                if (s.sweep == AMGB_SWEEP_BACKWARD)
+                    for (long long w = nw - 1; w >= 0; w--) RET(gs_wave(L.A, s.ws, w, L.x, L.b, om));
+                // symmetric: the backward pass starts with the wave the forward pass ended on;
+                // relaxing an independent set twice in a row is idempotent (same inputs, same
+                // arithmetic), so that launch is skipped -- bit-identical to running it.
+                if (s.sweep == AMGB_SWEEP_SYMMETRIC)
+                    for (long long w = nw - 2; w >= 0; w--) RET(gs_wave(L.A, s.ws, w, L.x, L.b, om));
+            }
+            return AMGB_OK;
+        }
+        case AMGB_SM_BLOCK_JACOBI: return block_jacobi(L, s);
+        }
+        return fail(AMGB_ENOTIMPL, "smoother kind");
+    }
+
+    int coarse_solve(Level &Lc)
+    {
+        if (coarse_zero) return launch_count_fill(Lc.x, Lc.A.n_rows);
+        const int n = coarse_n;
+        const int threads = 128, rows_per_block = threads / 32;
+        dense_matvec_kernel<<<(n + rows_per_block - 1) / rows_per_block, threads, 0, stream>>>(
+            n, n, coarse_pinv, Lc.b, Lc.x);
+        CK(cudaGetLastError());
+        launches++;
+        return AMGB_OK;
+    }
+
+    int launch_count_fill(double *x, long long n)
+    {
+        launches += (n > 0);
+        return launch_fill(x, n, 0.0, stream);
+    }
+
+    // MultilevelSolver.__solve (multilevel.py:584-662)
+    int cycle(int lvl, int kind, int cpl)
+    {
+        Level &L = levels[(size_t)lvl];
+        Level &C = levels[(size_t)lvl + 1];
+        RET(smooth(L, L.pre));                                          // :610
+        RET(spmv(OP_RESID, L.A, L.x, L.b, L.r));                        // :612
+        RET(spmv(OP_SPMV, L.R, L.r, nullptr, C.b));                     // :614
+        if (lvl == (int)levels.size() - 2) {
+            RET(coarse_solve(C));                                       // :617-618
+        } else {
+            RET(launch_count_fill(C.x, C.A.n_rows));                    // :615
+            if (kind == AMGB_CYCLE_V) {
+                RET(cycle(lvl + 1, AMGB_CYCLE_V, 1));                   // :619-620
+            } else if (kind == AMGB_CYCLE_W) {
+                RET(cycle(lvl + 1, kind, cpl));                         // :621-623
+                RET(cycle(lvl + 1, kind, cpl));
+            } else if (kind == AMGB_CYCLE_F) {
+                RET(cycle(lvl + 1, kind, cpl));                         // :624-627
+                for (int q = 0; q < cpl; q++) RET(cycle(lvl + 1, AMGB_CYCLE_V, 1));
+            } else {
+                return fail(AMGB_EINVAL, "Unrecognized cycle type");    // :658 (TypeError)
+            }
+        }
+        RET(spmv(OP_PADD, L.P, C.x, nullptr, L.x));                     // :660
+        RET(smooth(L, L.post));                                         // :662
+        if (L.x != L.x_home) {   // odd number of Jacobi ping-pongs: bring the iterate home
+            CK(cudaMemcpyAsync(L.x_home, L.x, sizeof(double) * (size_t)L.A.n_rows,
+                               cudaMemcpyDeviceToDevice, stream));
+            launches++;
+            std::swap(L.x, L.xalt);
+        }
+        return AMGB_OK;
+    }
+
+    // ||b - A x||^2 on level 0 -> norms2[slot]   (multilevel.py:545, :567 with the norm fused)
+    int residual_norm2(int slot)
+    {
+        Level &L = levels[0];
+        RET(spmv(OP_RESID, L.A, L.x, L.b, L.r, 0.0, nullptr, partials));
+        reduce_partials_kernel<<<1, 1024, 0, stream>>>(partials, (int)n_partials, norms2 + slot);
+        CK(cudaGetLastError());
+        launches++;
+        return AMGB_OK;
+    }
+
+    int one_iteration(int kind, int cpl)
+    {
+        if (levels.size() == 1) {   // multilevel.py:559-561: x = coarse_solver(A, b)
+            return coarse_solve(levels[0]);
+        }
+        if (!use_graph) return cycle(0, kind, cpl);
+        if (graph[kind] == nullptr || graph_cpl[kind] != cpl) {
+            if (graph[kind] != nullptr) { cudaGraphExecDestroy(graph[kind]); graph[kind] = nullptr; }
+            const long long before = launches;
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            int rc = cycle(0, kind, cpl);
+            cudaError_t e = cudaStreamEndCapture(stream, &g);
+            if (rc != AMGB_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess) return fail(AMGB_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+            graph_nodes[kind] = launches - before;
+            launches = before;
+            CK(cudaGraphInstantiate(&graph[kind], g, 0));
+            cudaGraphDestroy(g);
+            graph_cpl[kind] = cpl;
+        }
+        CK(cudaGraphLaunch(graph[kind], stream));
+        launches += graph_nodes[kind];
+        return AMGB_OK;
+    }
+
+    int ensure_norms(int need)
+    {
+        if (need <= norms2_cap) return AMGB_OK;
+        int cap = std::max(need, 128);
+        RET(dalloc(&norms2, cap));
+        norms2_cap = cap;
+        return AMGB_OK;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// block Jacobi (relaxation.h:1021-1090) on the point-CSR expansion of a BSR operator:
+// one group of G lanes per BLOCK row; for each of its bs point rows the off-block-diagonal
+// products are summed (entries whose column block equals the row block are skipped, exactly
+// the `if (i == j) continue` of the reference), then x_I = (1-w) x_I + w Dinv_I (b_I - rsum).
+// ------------------------------------------------------------------------------------------
+template <int G, int BS>
+__global__ void __launch_bounds__(kCsrThreads) block_jacobi_kernel(int nb, const int *__restrict__ Ap,
+                                                                   const int *__restrict__ Aj,
+                                                                   const double *__restrict__ Ax,
+                                                                   const double *__restrict__ x,
+                                                                   const double *__restrict__ b,
+                                                                   const double *__restrict__ Dinv,
+                                                                   double *__restrict__ y, double omega)
+{
+    const int lane = threadIdx.x & (G - 1);
+    const long long I = ((long long)blockIdx.x * kCsrThreads + threadIdx.x) / G;
+    const bool active = I < nb;
+    double rs[BS];
+#pragma unroll
+    for (int k = 0; k < BS; k++) {
+        double sum = 0.0;
+        if (active) {
+            const int row = (int)I * BS + k;
+            const int s = Ap[row], e = Ap[row + 1];
+            for (int jj = s + lane; jj < e; jj += G) {
+                const int c = ld_stream_i32(Aj + jj);
+                const double v = ld_stream_f64(Ax + jj);
+                if (c / BS != (int)I) sum += v * __ldg(x + c);
+            }
+        }
+        rs[k] = group_sum<G>(sum);
+    }
+    if (active && lane == 0) {
+        const size_t base = (size_t)I * BS;
+#pragma unroll
+        for (int k = 0; k < BS; k++) rs[k] = b[base + k] - rs[k];
+#pragma unroll
+        for (int k = 0; k < BS; k++) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < BS; c++) v += Dinv[base * BS + (size_t)k * BS + c] * rs[c];
+            y[base + k] = (1.0 - omega) * x[base + k] + omega * v;
+        }
+    }
+}
+
+template <int BS>
+static int launch_block_jacobi(int lanes, int nb, const DevCsr &A, const double *x, const double *b,
+                               const double *Dinv, double *y, double omega, cudaStream_t s)
+{
+    if (nb <= 0) return AMGB_OK;
+    const dim3 g((unsigned)csr_grid(nb, lanes)), t(kCsrThreads);
+    switch (lanes) {
+    case 1: block_jacobi_kernel<1, BS><<<g, t, 0, s>>>(nb, A.Ap, A.Aj, A.Ax, x, b, Dinv, y, omega); break;
+    case 2: block_jacobi_kernel<2, BS><<<g, t, 0, s>>>(nb, A.Ap, A.Aj, A.Ax, x, b, Dinv, y, omega); break;
+    case 4: block_jacobi_kernel<4, BS><<<g, t, 0, s>>>(nb, A.Ap, A.Aj, A.Ax, x, b, Dinv, y, omega); break;
+    case 8: block_jacobi_kernel<8, BS><<<g, t, 0, s>>>(nb, A.Ap, A.Aj, A.Ax, x, b, Dinv, y, omega); break;
+    case 16: block_jacobi_kernel<16, BS><<<g, t, 0, s>>>(nb, A.Ap, A.Aj, A.Ax, x, b, Dinv, y, omega); break;
+    default: block_jacobi_kernel<32, BS><<<g, t, 0, s>>>(nb, A.Ap, A.Aj, A.Ax, x, b, Dinv, y, omega); break;
+    }
+    CK(cudaGetLastError());
+    return AMGB_OK;
+}
+
+static int dispatch_block_jacobi(int bs, int lanes, int nb, const DevCsr &A, const double *x,
+                                 const double *b, const double *Dinv, double *y, double omega,
+                                 cudaStream_t s)
+{
+    switch (bs) {
+    case 1: return launch_block_jacobi<1>(lanes, nb, A, x, b, Dinv, y, omega, s);
+    case 2: return launch_block_jacobi<2>(lanes, nb, A, x, b, Dinv, y, omega, s);
+    case 3: return launch_block_jacobi<3>(lanes, nb, A, x, b, Dinv, y, omega, s);
+    case 4: return launch_block_jacobi<4>(lanes, nb, A, x, b, Dinv, y, omega, s);
+    case 5: return launch_block_jacobi<5>(lanes, nb, A, x, b, Dinv, y, omega, s);
+    case 6: return launch_block_jacobi<6>(lanes, nb, A, x, b, Dinv, y, omega, s);
+    case 7: return launch_block_jacobi<7>(lanes, nb, A, x, b, Dinv, y, omega, s);
+    case 8: return launch_block_jacobi<8>(lanes, nb, A, x, b, Dinv, y, omega, s);
+    }
+    return fail(AMGB_ENOTIMPL, "block_jacobi: blocksize must be 1..8");
+}
+
+int amgb_hierarchy::block_jacobi(Level &L, const Smoother &s)
+{
+    const int nb = L.A.n_rows / s.bs;
+    for (int it = 0; it < s.iterations; it++) {
+        RET(dispatch_block_jacobi(s.bs, L.A.lanes, nb, L.A, L.x, L.b, s.Dinv, L.xalt, s.omega, stream));
+        launches++;
+        std::swap(L.x, L.xalt);
+    }
+    return AMGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI (1): hierarchy
+// ------------------------------------------------------------------------------------------
+extern "C" int amgb_hierarchy_create(int device, amgb_hierarchy **out)
+{
+    if (out == nullptr) return fail(AMGB_EINVAL, "out is null");
+    *out = nullptr;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(AMGB_EINVAL, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    amgb_hierarchy *h = new amgb_hierarchy();
+    h->device = device;
+    const char *ng = getenv("AMGB_NO_GRAPH");
+    h->use_graph = !(ng && ng[0] == '1');
+    *out = h;
+    return AMGB_OK;
+}
+
+extern "C" void amgb_hierarchy_destroy(amgb_hierarchy *h)
+{
+    if (h == nullptr) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int k = 0; k < 3; k++)
+        if (h->graph[k]) cudaGraphExecDestroy(h->graph[k]);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->norm_host) cudaFreeHost(h->norm_host);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int amgb_hierarchy_add_level(amgb_hierarchy *h, const amgb_matrix *A, const amgb_matrix *P,
+                                        const amgb_matrix *R, const amgb_smoother *pre,
+                                        const amgb_smoother *post)
+{
+    if (h == nullptr) return fail(AMGB_EINVAL, "null hierarchy");
+    if (h->finalized) return fail(AMGB_ESTATE, "hierarchy already finalized");
+    CK(cudaSetDevice(h->device));
+    if (!h->levels.empty() && !h->levels.back().has_pr)
+        return fail(AMGB_ESTATE, "previous level was added as the coarsest (no P/R)");
+    HostCsr HA;
+    RET(to_host_csr(A, HA, "A"));
+    if (HA.n_rows != HA.n_cols) return fail(AMGB_EINVAL, "expected square matrix");
+    if (!h->levels.empty() && h->levels.back().P.n_cols != HA.n_rows)
+        return fail(AMGB_EINVAL, "level size does not match the previous level's P");
+    Level L;
+    RET(h->upload_csr(HA, L.A));
+    if ((P == nullptr) != (R == nullptr)) return fail(AMGB_EINVAL, "P and R must be given together");
+    if (P != nullptr) {
+        HostCsr HP, HR;
+        RET(to_host_csr(P, HP, "P"));
+        RET(to_host_csr(R, HR, "R"));
+        if (HP.n_rows != HA.n_rows || HR.n_cols != HA.n_rows || HR.n_rows != HP.n_cols)
+            return fail(AMGB_EINVAL, "P/R shapes inconsistent with A");
+        RET(h->upload_csr(HP, L.P));
+        RET(h->upload_csr(HR, L.R));
+        L.has_pr = true;
+        RET(h->setup_smoother(pre, HA, L.pre));
+        RET(h->setup_smoother(post, HA, L.post));
+    }
+    h->levels.push_back(L);
+    return AMGB_OK;
+}
+
+extern "C" int amgb_hierarchy_set_coarse_pinv(amgb_hierarchy *h, int32_t n, const double *pinv,
+                                              int32_t coarse_is_zero)
+{
+    if (h == nullptr) return fail(AMGB_EINVAL, "null hierarchy");
+    if (h->levels.empty()) return fail(AMGB_ESTATE, "no levels");
+    if (n != h->levels.back().A.n_rows) return fail(AMGB_EINVAL, "pinv size != coarsest level size");
+    CK(cudaSetDevice(h->device));
+    h->coarse_zero = coarse_is_zero != 0;
+    h->coarse_n = n;
+    if (!h->coarse_zero) {
+        if (pinv == nullptr) return fail(AMGB_EINVAL, "pinv is null");
+        RET(h->upload(&h->coarse_pinv, pinv, (long long)n * n));
+    }
+    h->have_coarse = true;
+    return AMGB_OK;
+}
+
+extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
+{
+    if (h == nullptr) return fail(AMGB_EINVAL, "null hierarchy");
+    if (h->finalized) return fail(AMGB_ESTATE, "already finalized");
+    if (h->levels.empty()) return fail(AMGB_ESTATE, "no levels");
+    if (h->levels.back().has_pr) return fail(AMGB_ESTATE, "last level must be added without P/R");
+    if (!h->have_coarse) return fail(AMGB_ESTATE, "coarse solver not set");
+    CK(cudaSetDevice(h->device));
+    if (stream != nullptr) {
+        h->stream = (cudaStream_t)stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    for (Level &L : h->levels) {
+        const long long n = L.A.n_rows;
+        RET(h->dalloc(&L.x_home, n));
+        RET(h->dalloc(&L.xalt, n));
+        RET(h->dalloc(&L.b, n));
+        RET(h->dalloc(&L.r, n));
+        L.x = L.x_home;
+    }
+    h->n_partials = csr_grid(h->levels[0].A.n_rows, h->levels[0].A.lanes);
+    RET(h->dalloc(&h->partials, h->n_partials));
+    RET(h->ensure_norms(128));
+    RET(h->dalloc(&h->sumsq_parts, kSumsqBlocks));
+    CK(cudaHostAlloc((void **)&h->norm_host, sizeof(double) * 2, cudaHostAllocDefault));
+    h->finalized = true;
+    return AMGB_OK;
+}
+
+extern "C" int amgb_hierarchy_num_levels(const amgb_hierarchy *h) { return h ? (int)h->levels.size() : 0; }
+extern "C" int64_t amgb_hierarchy_device_bytes(const amgb_hierarchy *h) { return h ? h->dev_bytes : 0; }
+extern "C" int64_t amgb_hierarchy_last_launches(const amgb_hierarchy *h) { return h ? h->last_launches : 0; }
+
+extern "C" int amgb_host_alloc(size_t bytes, void **out)
+{
+    if (out == nullptr) return fail(AMGB_EINVAL, "out is null");
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return AMGB_OK;
+}
+extern "C" int amgb_host_free(void *p)
+{
+    if (p) CK(cudaFreeHost(p));
+    return AMGB_OK;
+}
+
+static int check_cycle_args(amgb_hierarchy *h, int32_t cycle, int32_t cpl)
+{
+    if (h == nullptr) return fail(AMGB_EINVAL, "null hierarchy");
+    if (!h->finalized) return fail(AMGB_ESTATE, "hierarchy not finalized");
+    if (cycle < 0 || cycle > 2) return fail(AMGB_EINVAL, "Unrecognized cycle type");
+    if (cpl < 0) return fail(AMGB_EINVAL, "cycles_per_level < 0");
+    return AMGB_OK;
+}
+
+extern "C" int amgb_solve(amgb_hierarchy *h, const double *b_host, double *x_host, double tol,
+                          int32_t maxiter, int32_t cycle, int32_t cycles_per_level, double *residuals,
+                          int32_t *n_residuals, int32_t *info)
+{
+    RET(check_cycle_args(h, cycle, cycles_per_level));
+    if (b_host == nullptr || x_host == nullptr) return fail(AMGB_EINVAL, "null host vector");
+    if (maxiter < 1) return fail(AMGB_EINVAL, "maxiter must be >= 1");
+    CK(cudaSetDevice(h->device));
+    Level &L0 = h->levels[0];
+    const size_t bytes = sizeof(double) * (size_t)L0.A.n_rows;
+    cudaStream_t s = h->stream;
+    h->launches = 0;
+    RET(h->ensure_norms(maxiter + 1));
+    L0.x = L0.x_home;
+    CK(cudaMemcpyAsync(L0.b, b_host, bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(L0.x, x_host, bytes, cudaMemcpyHostToDevice, s));
+
+    // normb (multilevel.py:540-542) is only needed by the stop test; reduce it on the device
+    double normb = 1.0;
+    if (tol > 0.0) {
+        sumsq_partials_kernel<<<kSumsqBlocks, 256, 0, s>>>(L0.b, L0.A.n_rows, h->sumsq_parts);
+        CK(cudaGetLastError());
+        reduce_partials_kernel<<<1, 1024, 0, s>>>(h->sumsq_parts, kSumsqBlocks, h->norms2);
+        CK(cudaGetLastError());
+        h->launches += 2;
+        CK(cudaMemcpyAsync(h->norm_host, h->norms2, sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        normb = std::sqrt(h->norm_host[0]);
+        if (normb == 0.0) normb = 1.0;
+    }
+    RET(h->residual_norm2(0));                                     // :545
+    int it = 0, conv = -1;
+    while (true) {
+        RET(h->one_iteration(cycle, cycles_per_level));            // :559-563
+        it++;
+        RET(h->residual_norm2(it));                                // :567
+        if (tol > 0.0) {
+            CK(cudaMemcpyAsync(h->norm_host, h->norms2 + it, sizeof(double), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (std::sqrt(h->norm_host[0]) < tol * normb) { conv = 0; break; }   // :574
+        }
+        if (it == maxiter) { conv = it; break; }                  // :579
+    }
+    CK(cudaMemcpyAsync(x_host, L0.x, bytes, cudaMemcpyDeviceToHost, s));
+    std::vector<double> n2((size_t)it + 1);
+    CK(cudaMemcpyAsync(n2.data(), h->norms2, sizeof(double) * ((size_t)it + 1), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (residuals != nullptr)
+        for (int k = 0; k <= it; k++) residuals[k] = std::sqrt(n2[(size_t)k]);
+    if (n_residuals != nullptr) *n_residuals = it + 1;
+    // tol == 0 can still "converge" if the residual is exactly... never < 0: matches `normr < tol*normb`
+    if (info != nullptr) *info = conv;
+    h->last_launches = h->launches;
+    return AMGB_OK;
+}
+
+extern "C" int amgb_solve_device(amgb_hierarchy *h, const double *b_dev, double *x_dev, int32_t ncycles,
+                                 int32_t cycle, int32_t cycles_per_level, double *norms2_dev)
+{
+    RET(check_cycle_args(h, cycle, cycles_per_level));
+    if (b_dev == nullptr || x_dev == nullptr) return fail(AMGB_EINVAL, "null device vector");
+    if (ncycles < 0) return fail(AMGB_EINVAL, "ncycles < 0");
+    CK(cudaSetDevice(h->device));
+    Level &L0 = h->levels[0];
+    const size_t bytes = sizeof(double) * (size_t)L0.A.n_rows;
+    cudaStream_t s = h->stream;
+    h->launches = 0;
+    L0.x = L0.x_home;
+    CK(cudaMemcpyAsync(L0.b, b_dev, bytes, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(L0.x, x_dev, bytes, cudaMemcpyDeviceToDevice, s));
+    if (norms2_dev != nullptr) {
+        RET(h->ensure_norms(ncycles + 1));
+        RET(h->residual_norm2(0));
+    }
+    for (int it = 1; it <= ncycles; it++) {
+        RET(h->one_iteration(cycle, cycles_per_level));
+        if (norms2_dev != nullptr) RET(h->residual_norm2(it));
+    }
+    CK(cudaMemcpyAsync(x_dev, L0.x, bytes, cudaMemcpyDeviceToDevice, s));
+    if (norms2_dev != nullptr)
+        CK(cudaMemcpyAsync(norms2_dev, h->norms2, sizeof(double) * ((size_t)ncycles + 1),
+                           cudaMemcpyDeviceToDevice, s));
+    h->last_launches = h->launches;
+    return AMGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI (3): device kernels
+// ------------------------------------------------------------------------------------------
+static int resolve_lanes(int lanes, int32_t n_rows, const int32_t *Ap, cudaStream_t s, int *out)
+{
+    if (lanes == 0) {
+        int nnz = 0;
+        if (n_rows > 0) {
+            CK(cudaMemcpyAsync(&nnz, Ap + n_rows, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        lanes = pick_lanes(nnz, n_rows);
+    }
+    if (lanes < 1 || lanes > 32 || (lanes & (lanes - 1))) return fail(AMGB_EINVAL, "lanes must be a power of two in 1..32");
+    *out = lanes;
+    return AMGB_OK;
+}
+
+extern "C" int64_t amgb_dev_partials_len(int32_t n_rows, int lanes)
+{
+    if (lanes <= 0) lanes = 32;
+    return csr_grid(n_rows, lanes) + 1;
+}
+
+static CsrRowArgs mk_args(int n, int row0, const int *rows, const int *Ap, const int *Aj, const double *Ax,
+                          const double *x, const double *b, double *y, double *r, double omega, double *parts)
+{
+    CsrRowArgs a;
+    a.n = n; a.row0 = row0; a.rows = rows; a.Ap = Ap; a.Aj = Aj; a.Ax = Ax;
+    a.x = x; a.b = b; a.y = y; a.r = r; a.omega = omega; a.partials = parts;
+    return a;
+}
+
+extern "C" int amgb_dev_csr_spmv(int32_t n_rows, const int32_t *Ap, const int32_t *Aj, const double *Ax,
+                                 const double *x, double *y, int lanes, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    RET(resolve_lanes(lanes, n_rows, Ap, s, &lanes));
+    return launch_csr(OP_SPMV, lanes, mk_args(n_rows, 0, nullptr, Ap, Aj, Ax, x, nullptr, y, nullptr, 0.0, nullptr), s);
+}
+
+extern "C" int amgb_dev_csr_residual(int32_t n_rows, const int32_t *Ap, const int32_t *Aj, const double *Ax,
+                                     const double *x, const double *b, double *r, double *partials,
+                                     double *norm2_out, int lanes, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    RET(resolve_lanes(lanes, n_rows, Ap, s, &lanes));
+    if ((partials == nullptr) != (norm2_out == nullptr))
+        return fail(AMGB_EINVAL, "partials and norm2_out must be given together");
+    RET(launch_csr(OP_RESID, lanes, mk_args(n_rows, 0, nullptr, Ap, Aj, Ax, x, b, r, nullptr, 0.0, partials), s));
+    if (partials != nullptr) {
+        reduce_partials_kernel<<<1, 1024, 0, s>>>(partials, (int)csr_grid(n_rows, lanes), norm2_out);
+        CK(cudaGetLastError());
+    }
+    return AMGB_OK;
+}
+
+extern "C" int amgb_dev_csr_spmv_add(int32_t n_rows, const int32_t *Ap, const int32_t *Aj, const double *Ax,
+                                     const double *xc, double *x, int lanes, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    RET(resolve_lanes(lanes, n_rows, Ap, s, &lanes));
+    return launch_csr(OP_PADD, lanes, mk_args(n_rows, 0, nullptr, Ap, Aj, Ax, xc, nullptr, x, nullptr, 0.0, nullptr), s);
+}
+
+extern "C" int amgb_dev_csr_jacobi(int32_t n_rows, const int32_t *Ap, const int32_t *Aj, const double *Ax,
+                                   const double *x_in, const double *b, double *x_out, double *r_out,
+                                   double omega, int lanes, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (x_in == x_out) return fail(AMGB_EINVAL, "jacobi: x_in and x_out must differ");
+    RET(resolve_lanes(lanes, n_rows, Ap, s, &lanes));
+    return launch_csr(OP_JACOBI, lanes, mk_args(n_rows, 0, nullptr, Ap, Aj, Ax, x_in, b, x_out, r_out, omega, nullptr), s);
+}
+
+extern "C" int amgb_dev_csr_gs_wave(int32_t n, int32_t row0, const int32_t *rows, const int32_t *Ap,
+                                    const int32_t *Aj, const double *Ax, double *x, const double *b,
+                                    double omega, int lanes, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (lanes == 0) lanes = 8;
+    if (lanes < 1 || lanes > 32 || (lanes & (lanes - 1))) return fail(AMGB_EINVAL, "lanes must be a power of two in 1..32");
+    return launch_csr(OP_GS, lanes, mk_args(n, row0, rows, Ap, Aj, Ax, x, b, x, nullptr, omega, nullptr), s);
+}
+
+extern "C" int amgb_dev_dense_matvec(int32_t m, int32_t n, const double *M, const double *x, double *y,
+                                     void *stream)
+{
+    if (m <= 0) return AMGB_OK;
+    dense_matvec_kernel<<<(m + 3) / 4, 128, 0, (cudaStream_t)stream>>>(m, n, M, x, y);
+    CK(cudaGetLastError());
+    return AMGB_OK;
+}
+
+extern "C" int amgb_dev_fill(double *x, int64_t n, double v, void *stream)
+{
+    return launch_fill(x, n, v, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI (2): reference-FFI-shaped host entry points.  Upload, run the same kernels, download.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Scratch {   // RAII device scratch for the host-shaped calls
+    std::vector<void *> ptrs;
+    ~Scratch() { for (void *p : ptrs) cudaFree(p); }
+    template <typename T>
+    int up(T **d, const T *h, long long n)
+    {
+        void *q = nullptr;
+        CK(cudaMalloc(&q, (size_t)std::max<long long>(n, 1) * sizeof(T)));
+        ptrs.push_back(q);
+        if (n > 0 && h != nullptr) CK(cudaMemcpy(q, h, (size_t)n * sizeof(T), cudaMemcpyHostToDevice));
+        *d = (T *)q;
+        return AMGB_OK;
+    }
+};
+
+int check_csr_host(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size, const double *Ax,
+                   int Ax_size, int x_size, int b_size, int vals_per_entry)
+{
+    if (Ap == nullptr || Ap_size < 1) return fail(AMGB_EINVAL, "Ap missing");
+    if (Aj_size > 0 && (Aj == nullptr || Ax == nullptr)) return fail(AMGB_EINVAL, "Aj/Ax missing");
+    if ((long long)Aj_size * vals_per_entry != (long long)Ax_size) return fail(AMGB_EINVAL, "Aj/Ax size mismatch");
+    if (Ap[Ap_size - 1] != Aj_size) return fail(AMGB_EINVAL, "Ap[-1] != len(Aj)");
+    if (x_size != b_size) return fail(AMGB_EINVAL, "x and b sizes differ");
+    return AMGB_OK;
+}
+
+// rows visited by `for (i = start; i != stop; i += step)`
+int range_rows(int start, int stop, int step, int n, std::vector<int> &rows)
+{
+    rows.clear();
+    if (step == 0) return fail(AMGB_EINVAL, "row_step == 0");
+    if ((stop - start) % step != 0) return fail(AMGB_EINVAL, "row range never terminates");
+    if ((stop - start) / step < 0) return fail(AMGB_EINVAL, "row range never terminates");
+    for (int i = start; i != stop; i += step) {
+        if (i < 0 || i >= n) return fail(AMGB_EINVAL, "row index out of range");
+        rows.push_back(i);
+    }
+    return AMGB_OK;
+}
+}  // namespace
+
+extern "C" int amgb_host_jacobi(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                                const double *Ax, int Ax_size, double *x, int x_size, const double *b,
+                                int b_size, double *temp, int temp_size, int32_t row_start,
+                                int32_t row_stop, int32_t row_step, const double *omega, int omega_size)
+{
+    RET(check_csr_host(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x_size, b_size, 1));
+    const int n = Ap_size - 1;
+    if (x_size != n || temp_size < n || omega == nullptr || omega_size < 1)
+        return fail(AMGB_EINVAL, "jacobi: bad vector sizes");
+    std::vector<int> rows;
+    RET(range_rows(row_start, row_stop, row_step, n, rows));
+    if (rows.empty()) return AMGB_OK;
+    Scratch sc;
+    int *dAp, *dAj, *drows;
+    double *dAx, *dx, *db, *dy;
+    RET(sc.up(&dAp, Ap, Ap_size)); RET(sc.up(&dAj, Aj, Aj_size)); RET(sc.up(&dAx, Ax, Ax_size));
+    RET(sc.up(&dx, (const double *)x, n)); RET(sc.up(&db, b, n)); RET(sc.up(&dy, (const double *)x, n));
+    RET(sc.up(&drows, rows.data(), (long long)rows.size()));
+    const int lanes = pick_lanes(Aj_size, n);
+    RET(launch_csr(OP_JACOBI, lanes, mk_args((int)rows.size(), 0, drows, dAp, dAj, dAx, dx, db, dy, nullptr, omega[0], nullptr), 0));
+    CK(cudaDeviceSynchronize());
+    for (int i : rows) temp[i] = x[i];                      // relaxation.h:325-327
+    CK(cudaMemcpy(x, dy, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    return AMGB_OK;
+}
+
+static int host_gs_common(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size, const double *Ax,
+                          int Ax_size, double *x, int x_size, const double *b, int b_size,
+                          const std::vector<int> &list, double omega = 1.0)
+{
+    RET(check_csr_host(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x_size, b_size, 1));
+    const int n = Ap_size - 1;
+    if (x_size != n) return fail(AMGB_EINVAL, "gauss_seidel: bad vector sizes");
+    if (list.empty()) return AMGB_OK;
+    HostCsr H;
+    H.n_rows = H.n_cols = n;
+    H.Ap.assign(Ap, Ap + Ap_size);
+    H.Aj.assign(Aj, Aj + Aj_size);
+    for (int c : H.Aj) if (c < 0 || c >= n) return fail(AMGB_EINVAL, "column index out of range");
+    std::vector<int> rows;
+    std::vector<long long> ptr;
+    build_waves(H, list.data(), (long long)list.size(), rows, ptr);
+    Scratch sc;
+    int *dAp, *dAj, *drows;
+    double *dAx, *dx, *db;
+    RET(sc.up(&dAp, Ap, Ap_size)); RET(sc.up(&dAj, Aj, Aj_size)); RET(sc.up(&dAx, Ax, Ax_size));
+    RET(sc.up(&dx, (const double *)x, n)); RET(sc.up(&db, b, n));
+    RET(sc.up(&drows, rows.data(), (long long)rows.size()));
+    const int lanes = pick_lanes(Aj_size, n);
+    for (size_t w = 0; w + 1 < ptr.size(); w++)
+        RET(launch_csr(OP_GS, lanes, mk_args((int)(ptr[w + 1] - ptr[w]), 0, drows + ptr[w], dAp, dAj, dAx, dx, db, dx, nullptr, omega, nullptr), 0));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(x, dx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    return AMGB_OK;
+}
+
+extern "C" int amgb_host_gauss_seidel(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                                      const double *Ax, int Ax_size, double *x, int x_size, const double *b,
+                                      int b_size, int32_t row_start, int32_t row_stop, int32_t row_step)
+{
+    if (Ap == nullptr || Ap_size < 1) return fail(AMGB_EINVAL, "Ap missing");
+    std::vector<int> list;
+    RET(range_rows(row_start, row_stop, row_step, Ap_size - 1, list));
+    return host_gs_common(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x, x_size, b, b_size, list);
+}
+
+extern "C" int amgb_host_sor_gauss_seidel(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                                          const double *Ax, int Ax_size, double *x, int x_size, const double *b,
+                                          int b_size, int32_t row_start, int32_t row_stop, int32_t row_step,
+                                          double omega)
+{
+    if (Ap == nullptr || Ap_size < 1) return fail(AMGB_EINVAL, "Ap missing");
+    std::vector<int> list;
+    RET(range_rows(row_start, row_stop, row_step, Ap_size - 1, list));
+    return host_gs_common(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x, x_size, b, b_size, list, omega);
+}
+
+extern "C" int amgb_host_gauss_seidel_indexed(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                                              const double *Ax, int Ax_size, double *x, int x_size,
+                                              const double *b, int b_size, const int32_t *Id, int Id_size,
+                                              int32_t row_start, int32_t row_stop, int32_t row_step)
+{
+    if (Ap == nullptr || Ap_size < 1) return fail(AMGB_EINVAL, "Ap missing");
+    std::vector<int> pos, list;
+    RET(range_rows(row_start, row_stop, row_step, Id_size, pos));
+    for (int k : pos) {
+        if (Id[k] < 0 || Id[k] >= Ap_size - 1) return fail(AMGB_EINVAL, "row index out of range");
+        list.push_back(Id[k]);
+    }
+    return host_gs_common(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x, x_size, b, b_size, list);
+}
+
+extern "C" int amgb_host_bsr_jacobi(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                                    const double *Ax, int Ax_size, double *x, int x_size, const double *b,
+                                    int b_size, double *temp, int temp_size, int32_t row_start,
+                                    int32_t row_stop, int32_t row_step, int32_t blocksize,
+                                    const double *omega, int omega_size)
+{
+    if (blocksize < 1) return fail(AMGB_EINVAL, "blocksize < 1");
+    RET(check_csr_host(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x_size, b_size, blocksize * blocksize));
+    const int nb = Ap_size - 1, n = nb * blocksize;
+    if (x_size != n || temp_size < n || omega == nullptr || omega_size < 1)
+        return fail(AMGB_EINVAL, "bsr_jacobi: bad vector sizes");
+    std::vector<int> brows;
+    RET(range_rows(row_start, row_stop, row_step, nb, brows));
+    if (brows.empty()) return AMGB_OK;
+    amgb_matrix M;
+    M.n_rows = M.n_cols = n; M.block_r = M.block_c = blocksize; M.nnz_blocks = Aj_size;
+    M.indptr = Ap; M.indices = Aj; M.data = Ax;
+    HostCsr H;
+    RET(to_host_csr(&M, H, "A"));
+    std::vector<int> rows;
+    for (int I : brows) for (int k = 0; k < blocksize; k++) rows.push_back(I * blocksize + k);
+    Scratch sc;
+    int *dAp, *dAj, *drows;
+    double *dAx, *dx, *db, *dy;
+    RET(sc.up(&dAp, H.Ap.data(), (long long)H.Ap.size())); RET(sc.up(&dAj, H.Aj.data(), (long long)H.Aj.size()));
+    RET(sc.up(&dAx, H.Ax.data(), (long long)H.Ax.size()));
+    RET(sc.up(&dx, (const double *)x, n)); RET(sc.up(&db, b, n)); RET(sc.up(&dy, (const double *)x, n));
+    RET(sc.up(&drows, rows.data(), (long long)rows.size()));
+    const int lanes = pick_lanes((long long)H.Aj.size(), n);
+    RET(launch_csr(OP_JACOBI, lanes, mk_args((int)rows.size(), 0, drows, dAp, dAj, dAx, dx, db, dy, nullptr, omega[0], nullptr), 0));
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < (int)rows.size(); i++) temp[i] = x[i];   // relaxation.h:506-508
+    CK(cudaMemcpy(x, dy, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    return AMGB_OK;
+}
+
+extern "C" int amgb_host_block_jacobi(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                                      const double *Ax, int Ax_size, double *x, int x_size, const double *b,
+                                      int b_size, const double *Tx, int Tx_size, double *temp, int temp_size,
+                                      int32_t row_start, int32_t row_stop, int32_t row_step,
+                                      const double *omega, int omega_size, int32_t blocksize)
+{
+    if (blocksize < 1 || blocksize > 8) return fail(AMGB_ENOTIMPL, "block_jacobi: blocksize must be 1..8");
+    RET(check_csr_host(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x_size, b_size, blocksize * blocksize));
+    const int nb = Ap_size - 1, n = nb * blocksize;
+    if (x_size != n || temp_size < n || omega == nullptr || omega_size < 1 || Tx == nullptr ||
+        Tx_size != nb * blocksize * blocksize)
+        return fail(AMGB_EINVAL, "block_jacobi: bad vector sizes");
+    if (!(row_start == 0 && row_stop == nb && row_step == 1))
+        return fail(AMGB_ENOTIMPL, "block_jacobi: only the full forward range (what relaxation.py:483-484 passes)");
+    if (nb == 0) return AMGB_OK;
+    amgb_matrix M;
+    M.n_rows = M.n_cols = n; M.block_r = M.block_c = blocksize; M.nnz_blocks = Aj_size;
+    M.indptr = Ap; M.indices = Aj; M.data = Ax;
+    HostCsr H;
+    RET(to_host_csr(&M, H, "A"));
+    Scratch sc;
+    DevCsr D;
+    double *dx, *db, *dy, *dD;
+    RET(sc.up(&D.Ap, H.Ap.data(), (long long)H.Ap.size())); RET(sc.up(&D.Aj, H.Aj.data(), (long long)H.Aj.size()));
+    RET(sc.up(&D.Ax, H.Ax.data(), (long long)H.Ax.size()));
+    RET(sc.up(&dx, (const double *)x, n)); RET(sc.up(&db, b, n)); RET(sc.up(&dy, (const double *)x, n));
+    RET(sc.up(&dD, Tx, Tx_size));
+    D.n_rows = D.n_cols = n;
+    const int lanes = pick_lanes((long long)H.Aj.size(), n);
+    RET(dispatch_block_jacobi(blocksize, lanes, nb, D, dx, db, dD, dy, omega[0], 0));
+    CK(cudaDeviceSynchronize());
+    std::memcpy(temp, x, sizeof(double) * (size_t)n);           // relaxation.h:1043-1045
+    CK(cudaMemcpy(x, dy, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    return AMGB_OK;
+}
+
+extern "C" int amgb_host_matvec(const amgb_matrix *A, const double *x, double *y)
+{
+    HostCsr H;
+    RET(to_host_csr(A, H, "A"));
+    if (x == nullptr || y == nullptr) return fail(AMGB_EINVAL, "null vector");
+    Scratch sc;
+    int *dAp, *dAj;
+    double *dAx, *dx, *dy;
+    RET(sc.up(&dAp, H.Ap.data(), (long long)H.Ap.size())); RET(sc.up(&dAj, H.Aj.data(), (long long)H.Aj.size()));
+    RET(sc.up(&dAx, H.Ax.data(), (long long)H.Ax.size()));
+    RET(sc.up(&dx, x, H.n_cols)); RET(sc.up(&dy, (const double *)nullptr, H.n_rows));
+    const int lanes = pick_lanes((long long)H.Aj.size(), H.n_rows);
+    RET(launch_csr(OP_SPMV, lanes, mk_args(H.n_rows, 0, nullptr, dAp, dAj, dAx, dx, nullptr, dy, nullptr, 0.0, nullptr), 0));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(y, dy, sizeof(double) * (size_t)H.n_rows, cudaMemcpyDeviceToHost));
+    return AMGB_OK;
+}

@@ -1,0 +1,123 @@
+"""Save / load a multigrid hierarchy (operators + smoother descriptors) as one .npz file.
+
+The reference has no persistence ("the hierarchy is just a Python list"); this is
+the engine's resume path -- setup of the large BASELINE configs costs minutes of CPU, the upload
+seconds -- and the container of the golden fixtures under tests/golden/.
+
+Layout: ``meta`` (JSON: per level the operator formats/shapes/blocksizes and the smoother
+descriptors ``{"fn": <relaxation function name>, "name": <registry __name__>, "kw": {...}}``),
+arrays ``L<k>_<A|P|R>_{indptr,indices,data}``, ``L<k>_<pre|post>_<indices|Dinv>``, ``coarse_P``,
+plus any extra arrays the caller adds (golden vectors).
+"""
+import json
+from functools import partial, update_wrapper
+
+import numpy as np
+from scipy import sparse
+
+from .multilevel import MultilevelSolver
+from .relaxation import relaxation
+
+_ARRAY_KW = ("indices", "Dinv")
+
+
+def _put_matrix(out, key, M):
+    if getattr(M, "format", None) not in ("csr", "bsr"):
+        M = M.tocsr()
+    out[key + "_indptr"] = np.asarray(M.indptr, dtype=np.int32)
+    out[key + "_indices"] = np.asarray(M.indices, dtype=np.int32)
+    out[key + "_data"] = np.asarray(M.data, dtype=np.float64)
+    return {"format": M.format, "shape": [int(M.shape[0]), int(M.shape[1])],
+            "blocksize": [int(v) for v in (M.blocksize if M.format == "bsr" else (1, 1))]}
+
+
+def _get_matrix(z, key, m):
+    arrs = (z[key + "_data"], z[key + "_indices"], z[key + "_indptr"])
+    if m["format"] == "bsr":
+        return sparse.bsr_array(arrs, shape=tuple(m["shape"]), blocksize=tuple(m["blocksize"]))
+    return sparse.csr_array(arrs, shape=tuple(m["shape"]))
+
+
+def _put_smoother(out, key, sm):
+    if sm is None or (getattr(sm, "func", None) is None and getattr(sm, "__name__", "") == "none"):
+        return None
+    func = getattr(sm, "func", None)
+    if func is None:
+        raise NotImplementedError(f"cannot serialise closure smoother {sm!r}")
+    kw = {}
+    for k, v in sm.keywords.items():
+        if k in _ARRAY_KW:
+            out[f"{key}_{k}"] = np.asarray(v)
+        elif isinstance(v, (str, bool)) or v is None:
+            kw[k] = v
+        elif np.isscalar(v) or (isinstance(v, np.ndarray) and v.size == 1):
+            f = float(np.real(np.asarray(v).reshape(-1)[0]))
+            kw[k] = int(f) if k in ("iterations", "blocksize") else f
+        else:
+            raise NotImplementedError(f"smoother keyword {k}={v!r}")
+    return {"fn": func.__name__, "name": getattr(sm, "__name__", func.__name__), "kw": kw}
+
+
+def _get_smoother(z, key, d):
+    if d is None:
+        def none(A, x, b):
+            pass
+        return none
+    fn = getattr(relaxation, d["fn"])
+    kw = dict(d["kw"])
+    for k in _ARRAY_KW:
+        if f"{key}_{k}" in z:
+            kw[k] = z[f"{key}_{k}"]
+    sm = partial(fn, **kw)
+    update_wrapper(sm, getattr(relaxation, d["name"], fn))
+    return sm
+
+
+def save_hierarchy(path, ml, extra=None, compressed=True):
+    """Write ``ml`` (a pyamg or pyamg_b200 MultilevelSolver) to ``path``; ``extra`` = more arrays."""
+    out, meta = {}, {"levels": []}
+    for k, lvl in enumerate(ml.levels):
+        m = {"A": _put_matrix(out, f"L{k}_A", lvl.A)}
+        if k < len(ml.levels) - 1:
+            R = lvl.R if hasattr(lvl, "R") else lvl.P.T.conjugate()
+            m["P"] = _put_matrix(out, f"L{k}_P", lvl.P)
+            m["R"] = _put_matrix(out, f"L{k}_R", R)
+            m["pre"] = _put_smoother(out, f"L{k}_pre", getattr(lvl, "presmoother", None))
+            m["post"] = _put_smoother(out, f"L{k}_post", getattr(lvl, "postsmoother", None))
+        meta["levels"].append(m)
+    name = ml.coarse_solver.name() if hasattr(ml.coarse_solver, "name") else "'pinv'"
+    meta["coarse_solver"] = name
+    meta["symmetric_smoothing"] = bool(getattr(ml, "symmetric_smoothing", False))
+    cached = getattr(ml.coarse_solver, "P", None)
+    if cached is not None:
+        out["coarse_P"] = np.asarray(cached, dtype=np.float64)
+    if extra:
+        meta["extra"] = sorted(extra)
+        for k, v in extra.items():
+            out["X_" + k] = np.asarray(v)
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    (np.savez_compressed if compressed else np.savez)(path, **out)
+
+
+def load_hierarchy(path, device=0, stream=None):
+    """Read a hierarchy written by ``save_hierarchy``. Returns ``(MultilevelSolver, extra_dict)``."""
+    import ast
+    z = np.load(path)
+    meta = json.loads(bytes(z["meta"]).decode())
+    levels = []
+    for k, m in enumerate(meta["levels"]):
+        lvl = MultilevelSolver.Level()
+        lvl.A = _get_matrix(z, f"L{k}_A", m["A"])
+        if "P" in m:
+            lvl.P = _get_matrix(z, f"L{k}_P", m["P"])
+            lvl.R = _get_matrix(z, f"L{k}_R", m["R"])
+            lvl.presmoother = _get_smoother(z, f"L{k}_pre", m["pre"])
+            lvl.postsmoother = _get_smoother(z, f"L{k}_post", m["post"])
+        levels.append(lvl)
+    ml = MultilevelSolver(levels, coarse_solver=ast.literal_eval(meta["coarse_solver"]),
+                          device=device, stream=stream)
+    ml.symmetric_smoothing = meta.get("symmetric_smoothing", False)
+    if "coarse_P" in z:
+        ml.coarse_solver.P = np.ascontiguousarray(z["coarse_P"], dtype=np.float64)
+    extra = {k: z["X_" + k] for k in meta.get("extra", [])}
+    return ml, extra

@@ -1,0 +1,354 @@
+"""MultilevelSolver: the reference's hierarchy container and cycle API, executed on a B200.
+
+Mirror of pyamg/multilevel.py.  The object API is kept (``levels`` list of ``Level`` structs with
+``A, P, R, presmoother, postsmoother``; ``solve`` :398-582 with the same keyword arguments, return
+values and stop test; ``aspreconditioner`` :355-396; ``psolve``; ``change_solve_matrix``;
+``__repr__`` and the three complexity measures :184-318), but ``solve`` no longer recurses through
+NumPy/SciPy: the hierarchy is uploaded once to HBM and the cycle (pre-smooth, residual,
+restriction, coarse solve, prolongation + correction, post-smooth) runs as sm_100a CUDA kernels
+captured in a CUDA graph (csrc/engine.cu).  Host arrays in, a new host array out.
+
+Build it from
+  * a reference solver:  ``MultilevelSolver.from_pyamg(pyamg.ruge_stuben_solver(A))``
+    (setup stays on the reference's CPU path; closures are parsed for omega / Dinv / row lists), or
+  * a list of ``Level`` objects exactly as the reference's constructors do, followed by
+    ``pyamg_b200.relaxation.smoothing.change_smoothers``.
+
+No CPU fallback: without libpyamg_b200.so and a CUDA device ``solve`` raises.
+"""
+import ctypes
+from warnings import warn
+
+import numpy as np
+import scipy.linalg
+import scipy.sparse.linalg as sla
+from scipy.sparse.linalg import LinearOperator
+
+from . import _engine as E
+from .relaxation import smoothing
+
+__all__ = ["MultilevelSolver", "coarse_grid_solver"]
+
+
+def coarse_grid_solver(solver):
+    """Coarse-level solver descriptor (pyamg/multilevel.py:665-826).
+
+    The engine applies the coarsest solve as a dense matrix-vector product with a matrix computed
+    once on the CPU: the pseudo-inverse for 'pinv'/'pinv2' (what the reference caches, :717-721),
+    the plain inverse for the direct methods 'lu'/'cholesky'/'splu' (same solve, different
+    rounding).  Iterative / relaxation coarse solvers are outside the accelerated path.
+    """
+    def unpack_arg(v):
+        if isinstance(v, tuple):
+            return v[0], v[1]
+        return v, {}
+
+    name, kwargs = unpack_arg(solver)
+    if name in ("pinv", "pinv2"):
+        def dense(A):
+            return scipy.linalg.pinv(A.toarray(), **kwargs)
+    elif name in ("lu", "cholesky", "splu"):
+        def dense(A):
+            return scipy.linalg.inv(A.toarray())
+    elif name is None:
+        def dense(A):
+            return np.zeros(A.shape)
+    elif isinstance(name, str) or callable(name):
+        raise NotImplementedError(f"coarse solver {name!r} is not on the GPU hot path; use 'pinv' "
+                                  "(the reference's default), 'lu', 'cholesky', 'splu' or None")
+    else:
+        raise ValueError(f"unknown solver: {name}")
+
+    class GenericSolver:
+        """Holds the cached dense operator; applied on the GPU by the cycle engine."""
+
+        def dense_operator(self, A):
+            if not hasattr(self, "P"):
+                self.P = np.ascontiguousarray(dense(A), dtype=np.float64)
+            return self.P
+
+        def __repr__(self):
+            return "coarse_grid_solver(" + repr(solver) + ")"
+
+        @classmethod
+        def name(cls):
+            return repr(solver)
+
+    return GenericSolver()
+
+
+class MultilevelSolver:
+    """Stores a multigrid hierarchy and runs the multigrid cycle on the GPU.
+
+    Parameters and attributes as pyamg.multilevel.MultilevelSolver (multilevel.py:17-182).
+    """
+
+    class Level:
+        """One level of the hierarchy: a struct with A (+ P, R, presmoother, postsmoother)."""
+
+        def __init__(self):
+            self.A = None
+
+    def __init__(self, levels, coarse_solver="pinv", device=0, stream=None):
+        self.symmetric_smoothing = False
+        self.levels = levels
+        self.coarse_solver = coarse_grid_solver(coarse_solver)
+        self.device = device
+        self._stream = stream
+        self._h = None
+        for level in levels[:-1]:
+            if not hasattr(level, "R"):
+                level.R = level.P.T.conjugate()     # multilevel.py:180-182
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def from_pyamg(cls, ml, device=0, stream=None):
+        """Adopt a hierarchy built by the reference (any ``pyamg`` constructor): same Level
+        objects, same smoother closures, same coarse solver kind (and its cached pinv if any)."""
+        name = ml.coarse_solver.name() if hasattr(ml.coarse_solver, "name") else "'pinv'"
+        try:
+            import ast
+            spec = ast.literal_eval(name)
+        except (ValueError, SyntaxError) as exc:
+            raise NotImplementedError(f"coarse solver {name} is not on the GPU hot path") from exc
+        new = cls(list(ml.levels), coarse_solver=spec, device=device, stream=stream)
+        new.symmetric_smoothing = getattr(ml, "symmetric_smoothing", False)
+        cached = getattr(ml.coarse_solver, "P", None)
+        if cached is not None:
+            new.coarse_solver.P = np.ascontiguousarray(cached, dtype=np.float64)
+        return new
+
+    def _invalidate(self):
+        """Drop the device copy (levels or smoothers changed); re-uploaded on the next solve."""
+        if self._h is not None:
+            E.lib().amgb_hierarchy_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self._invalidate()
+        except Exception:
+            pass
+
+    def upload(self):
+        """Upload the hierarchy to HBM (idempotent). Returns the device footprint in bytes."""
+        if self._h is not None:
+            return int(E.lib().amgb_hierarchy_device_bytes(self._h))
+        E.require_gpu()
+        L = E.lib()
+        h = ctypes.c_void_p()
+        E.check(L.amgb_hierarchy_create(int(self.device), ctypes.byref(h)))
+        try:
+            nlv = len(self.levels)
+            for k, lvl in enumerate(self.levels):
+                keep = []
+                A = E.as_matrix(lvl.A, keep)
+                if k < nlv - 1:
+                    P = E.as_matrix(lvl.P, keep)
+                    R = E.as_matrix(lvl.R, keep)
+                    pre = smoothing.describe(getattr(lvl, "presmoother", None), lvl.A, keep)
+                    post = smoothing.describe(getattr(lvl, "postsmoother", None), lvl.A, keep)
+                    E.check(L.amgb_hierarchy_add_level(h, ctypes.byref(A), ctypes.byref(P),
+                                                       ctypes.byref(R), ctypes.byref(pre),
+                                                       ctypes.byref(post)))
+                else:
+                    E.check(L.amgb_hierarchy_add_level(h, ctypes.byref(A), None, None, None, None))
+            Ac = self.levels[-1].A
+            if Ac.nnz == 0:     # GenericSolver.__call__, multilevel.py:801-803
+                E.check(L.amgb_hierarchy_set_coarse_pinv(h, Ac.shape[0], None, 1))
+            else:
+                Pd = self.coarse_solver.dense_operator(Ac)
+                E.check(L.amgb_hierarchy_set_coarse_pinv(h, Ac.shape[0], E.f64p(Pd.reshape(-1)), 0))
+            E.check(L.amgb_hierarchy_finalize(h, ctypes.c_void_p(self._stream or 0)))
+        except Exception:
+            L.amgb_hierarchy_destroy(h)
+            raise
+        self._h = h
+        return int(L.amgb_hierarchy_device_bytes(h))
+
+    @property
+    def handle(self):
+        self.upload()
+        return self._h
+
+    def last_launches(self):
+        """CUDA kernels launched by the most recent solve (graph nodes counted individually)."""
+        return int(E.lib().amgb_hierarchy_last_launches(self._h)) if self._h is not None else 0
+
+    # ------------------------------------------------------------------ reporting (host only)
+    def __repr__(self):
+        """Basic statistics of the hierarchy (multilevel.py:184-209)."""
+        output = "MultilevelSolver\n"
+        output += f"Number of Levels:     {len(self.levels)}\n"
+        output += f"Operator Complexity:  {self.operator_complexity():6.3f}\n"
+        output += f"Grid Complexity:      {self.grid_complexity():6.3f}\n"
+        output += f"Coarse Solver:        {self.coarse_solver.name()}\n"
+        total_nnz = sum(level.A.nnz for level in self.levels)
+        output += "  level   unknowns     nonzeros\n"
+        for n, level in enumerate(self.levels):
+            A = level.A
+            ratio = 100 * A.nnz / total_nnz
+            output += f"{n:>6} {A.shape[1]:>11} {A.nnz:>12} [{ratio:2.2f}%]\n"
+        return output
+
+    def cycle_complexity(self, cycle="V"):
+        """Nonzeros touched by one cycle relative to the fine level (multilevel.py:211-283)."""
+        cycle = str(cycle).upper()
+        nnz = [level.A.nnz for level in self.levels]
+
+        def V(level):
+            if len(self.levels) == 1:
+                return nnz[0]
+            if level == len(self.levels) - 2:
+                return 2 * nnz[level] + nnz[level + 1]
+            return 2 * nnz[level] + V(level + 1)
+
+        def W(level):
+            if len(self.levels) == 1:
+                return nnz[0]
+            if level == len(self.levels) - 2:
+                return 2 * nnz[level] + nnz[level + 1]
+            return 2 * nnz[level] + 2 * W(level + 1)
+
+        def F(level):
+            if len(self.levels) == 1:
+                return nnz[0]
+            if level == len(self.levels) - 2:
+                return 2 * nnz[level] + nnz[level + 1]
+            return 2 * nnz[level] + F(level + 1) + V(level + 1)
+
+        if cycle == "V":
+            flops = V(0)
+        elif cycle in ("W", "AMLI"):
+            flops = W(0)
+        elif cycle == "F":
+            flops = F(0)
+        else:
+            raise TypeError(f"Unrecognized cycle type ({cycle})")
+        return float(flops) / float(nnz[0])
+
+    def operator_complexity(self):
+        return sum(level.A.nnz for level in self.levels) / float(self.levels[0].A.nnz)
+
+    def grid_complexity(self):
+        return sum(level.A.shape[0] for level in self.levels) / float(self.levels[0].A.shape[0])
+
+    # ------------------------------------------------------------------ solve-phase API
+    def change_solve_matrix(self, A):
+        """Change the fine-level matrix and rebuild its smoothers (multilevel.py:320-337)."""
+        self.levels[0].A = A
+        smoothing.rebuild_smoother(self.levels[0])
+        self._invalidate()
+
+    def psolve(self, b):
+        """Legacy interface: one iteration (multilevel.py:339-353)."""
+        return self.solve(b, maxiter=1)
+
+    def aspreconditioner(self, cycle="V"):
+        """LinearOperator applying one cycle from x0 = 0 (multilevel.py:355-396)."""
+        shape = self.levels[0].A.shape
+        dtype = self.levels[0].A.dtype
+
+        def matvec(b):
+            return self.solve(b, maxiter=1, cycle=cycle, tol=1e-12)
+
+        return LinearOperator(shape, matvec, dtype=dtype)
+
+    def solve(self, b, x0=None, tol=1e-5, maxiter=100, cycle="V", accel=None, callback=None,
+              residuals=None, cycles_per_level=1, return_info=False):
+        """Execute multigrid cycling on the GPU (pyamg/multilevel.py:398-582; same arguments)."""
+        b = np.asarray(b)
+        if x0 is None:
+            x = np.zeros_like(b)
+        else:
+            x = np.array(x0)    # copy (:467)
+
+        A = self.levels[0].A
+        cycle = str(cycle).upper()
+
+        if cycle == "AMLI":
+            raise NotImplementedError("AMLI cycles are not on the GPU hot path yet (SURVEY.md 8(f)-2)")
+        if cycle not in E.CYCLES:
+            raise TypeError(f"Unrecognized cycle type ({cycle})")      # :658
+
+        if accel is not None:
+            # Krylov acceleration: the Krylov method runs in SciPy on the host, every M @ r is one
+            # GPU cycle (multilevel.py:479-535; GPU-resident Krylov is SURVEY.md 8(f)-1)
+            if (accel == "cg") and (not self.symmetric_smoothing):
+                warn("Incompatible non-symmetric multigrid preconditioner "
+                     "detected, due to presmoother/postsmoother combination. "
+                     "CG requires SPD preconditioner, not just SPD matrix.")
+            if isinstance(accel, str):
+                accel = getattr(sla, accel)
+            M = self.aspreconditioner(cycle=cycle)
+            if residuals is not None:
+                residuals[:] = [np.linalg.norm(b - A @ x)]
+
+                def callback_wrapper(xk):
+                    if np.isscalar(xk):
+                        residuals.append(xk)
+                    else:
+                        residuals.append(np.linalg.norm(b - A @ xk))
+                    if callback is not None:
+                        callback(xk)
+            else:
+                callback_wrapper = callback
+            x, info = accel(A, b, x0=x0, maxiter=maxiter, M=M, callback=callback_wrapper,
+                            rtol=tol, atol=0)
+            if return_info:
+                return x, info
+            return x
+
+        if np.iscomplexobj(b) or np.iscomplexobj(x):
+            raise NotImplementedError("complex systems are outside the fp64 hot path")
+        n = A.shape[0]
+        if b.size != n or x.size != n:
+            raise ValueError("b / x0 have invalid dimensions")
+        if maxiter < 1:
+            raise ValueError("maxiter must be at least 1")
+        out_shape = b.shape
+        bh = np.ascontiguousarray(np.ravel(b), dtype=np.float64)        # :551-554
+        xh = np.ascontiguousarray(np.ravel(x), dtype=np.float64)
+
+        L = E.lib()
+        h = self.handle
+        cyc = E.CYCLES[cycle]
+        info = ctypes.c_int32(0)
+        nres = ctypes.c_int32(0)
+
+        if callback is None:
+            res = np.empty(maxiter + 1, dtype=np.float64)
+            E.check(L.amgb_solve(h, bh.ctypes.data, xh.ctypes.data, float(tol), int(maxiter), cyc,
+                                 int(cycles_per_level), E.f64p(res), ctypes.byref(nres),
+                                 ctypes.byref(info)))
+            if residuals is not None:
+                residuals[:] = list(res[:nres.value])
+            status = info.value
+        else:
+            # callback(x) wants the host iterate after every cycle: one engine call per cycle
+            res = np.empty(2, dtype=np.float64)
+            it = 0
+            normb = np.linalg.norm(bh)
+            if normb == 0.0:
+                normb = 1.0
+            while True:
+                E.check(L.amgb_solve(h, bh.ctypes.data, xh.ctypes.data, 0.0, 1, cyc,
+                                     int(cycles_per_level), E.f64p(res), ctypes.byref(nres),
+                                     ctypes.byref(info)))
+                if it == 0 and residuals is not None:
+                    residuals[:] = [res[0]]
+                it += 1
+                if residuals is not None:
+                    residuals.append(res[1])
+                callback(xh)
+                if res[1] < tol * normb:
+                    status = 0
+                    break
+                if it == maxiter:
+                    status = it
+                    break
+
+        xout = xh.reshape(out_shape)
+        if return_info:
+            return xout, status
+        return xout

@@ -1,0 +1,205 @@
+"""GPU relaxation sweeps with the call signatures of pyamg/relaxation/relaxation.py.
+
+Each function validates its arguments exactly like the reference's ``make_system``
+(relaxation.py:15-97: ValueError for non-arrays / wrong sizes / non-contiguous x, TypeError for
+mixed dtypes), then hands HOST arrays to the reference-FFI-shaped C entry points of
+libpyamg_b200.so (``amgb_host_*``), which upload, run the sm_100a kernels and write x back in
+place.  They exist so the reference's smoother tests can run against the CUDA kernels unchanged;
+inside a multigrid cycle the same kernels run on resident data (multilevel.MultilevelSolver).
+
+There is no CPU path: without a GPU these raise.
+"""
+from warnings import warn
+
+import numpy as np
+from scipy import sparse
+
+from .. import _engine as E
+
+__all__ = ["make_system", "jacobi", "gauss_seidel", "gauss_seidel_indexed", "block_jacobi", "sor"]
+
+
+def make_system(A, x, b, formats=None):
+    """Return A,x,b suitable for relaxation or raise an exception (relaxation.py:15-97)."""
+    if formats is None:
+        pass
+    elif formats == ["csr"]:
+        if sparse.issparse(A) and A.format == "csr":
+            pass
+        elif sparse.issparse(A) and A.format == "bsr":
+            A = A.tocsr()
+        else:
+            warn("implicit conversion to CSR", sparse.SparseEfficiencyWarning)
+            A = sparse.csr_array(A)
+    elif sparse.issparse(A) and A.format in formats:
+        pass
+    else:
+        A = sparse.csr_array(A).asformat(formats[0])
+
+    if not isinstance(x, np.ndarray):
+        raise ValueError("expected numpy array for argument x")
+    if not isinstance(b, np.ndarray):
+        raise ValueError("expected numpy array for argument b")
+    M, N = A.shape
+    if M != N:
+        raise ValueError("expected square matrix")
+    if x.shape not in [(M,), (M, 1)]:
+        raise ValueError("x has invalid dimensions")
+    if b.shape not in [(M,), (M, 1)]:
+        raise ValueError("b has invalid dimensions")
+    if A.dtype != x.dtype or A.dtype != b.dtype:
+        raise TypeError("arguments A, x, and b must have the same dtype")
+    if not x.flags.carray:
+        raise ValueError("x must be contiguous in memory")
+    return A, np.ravel(x), np.ravel(b)
+
+
+def _fp64(A):
+    """The engine computes in fp64 only (BASELINE.json); the reference's f32/complex overloads
+    (instantiate.yml:2-6) are outside the accelerated path and fail loudly."""
+    if A.dtype != np.float64:
+        raise NotImplementedError(f"pyamg_b200 relaxes fp64 systems only (got {A.dtype})")
+
+
+def _csr_args(A):
+    Ap = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    Aj = np.ascontiguousarray(A.indices, dtype=np.int32)
+    Ax = np.ascontiguousarray(A.data, dtype=np.float64).reshape(-1)
+    return Ap, Aj, Ax
+
+
+def jacobi(A, x, b, iterations=1, omega=1.0):
+    """Weighted Jacobi, in place on x (relaxation.py:349-420 -> relaxation.h:309-346 / :472-562)."""
+    A, x, b = make_system(A, x, b, formats=["csr", "bsr"])
+    _fp64(A)
+    n = A.shape[0]
+    if n == 0:
+        return
+    E.require_gpu()
+    L = E.lib()
+    temp = np.empty_like(x)
+    om = np.array([omega], dtype=np.float64)
+    b = np.ascontiguousarray(b)
+    Ap, Aj, Ax = _csr_args(A)
+    if A.format == "csr":
+        for _ in range(iterations):
+            E.check(L.amgb_host_jacobi(E.i32p(Ap), len(Ap), E.i32p(Aj), len(Aj), E.f64p(Ax), len(Ax),
+                                       E.f64p(x), n, E.f64p(b), n, E.f64p(temp), n,
+                                       0, n, 1, E.f64p(om), 1))
+    else:
+        R, C = A.blocksize
+        if R != C:
+            raise ValueError("BSR blocks must be square")
+        for _ in range(iterations):
+            E.check(L.amgb_host_bsr_jacobi(E.i32p(Ap), len(Ap), E.i32p(Aj), len(Aj), E.f64p(Ax),
+                                           len(Ax), E.f64p(x), n, E.f64p(b), n, E.f64p(temp), n,
+                                           0, n // R, 1, R, E.f64p(om), 1))
+
+
+def gauss_seidel(A, x, b, iterations=1, sweep="forward", omega=1.0):
+    """Gauss-Seidel, in place on x (relaxation.py:265-346 -> relaxation.h:48-76; omega != 1 is SOR,
+    relaxation.h:116-145 -- and, as in the reference, the symmetric sweep ignores omega).
+
+    The sequential sweep is executed as dependency waves (rows of a wave are mutually
+    independent), which reproduces the lexicographic result.
+    """
+    A, x, b = make_system(A, x, b, formats=["csr", "bsr"])
+    _fp64(A)
+    if A.format == "bsr":
+        # point-wise GS on BSR == GS on the CSR expansion (pinned by test_relaxation.py:224-249)
+        R, C = A.blocksize
+        if R != C:
+            raise ValueError("BSR blocks must be square")
+        A = A.tocsr()
+    n = A.shape[0]
+    if sweep == "forward":
+        rs = (0, n, 1)
+    elif sweep == "backward":
+        rs = (n - 1, -1, -1)
+    elif sweep == "symmetric":
+        for _ in range(iterations):
+            gauss_seidel(A, x, b, iterations=1, sweep="forward")
+            gauss_seidel(A, x, b, iterations=1, sweep="backward")
+        return
+    else:
+        raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+    if n == 0:
+        return
+    E.require_gpu()
+    L = E.lib()
+    b = np.ascontiguousarray(b)
+    Ap, Aj, Ax = _csr_args(A)
+    for _ in range(iterations):
+        if omega != 1.0:
+            E.check(L.amgb_host_sor_gauss_seidel(E.i32p(Ap), len(Ap), E.i32p(Aj), len(Aj), E.f64p(Ax),
+                                                 len(Ax), E.f64p(x), n, E.f64p(b), n, *rs, float(omega)))
+        else:
+            E.check(L.amgb_host_gauss_seidel(E.i32p(Ap), len(Ap), E.i32p(Aj), len(Aj), E.f64p(Ax),
+                                             len(Ax), E.f64p(x), n, E.f64p(b), n, *rs))
+
+
+def sor(A, x, b, omega, iterations=1, sweep="forward"):
+    """SOR (relaxation.py:100-154): Gauss-Seidel with the in-sweep damping omega."""
+    A, x, b = make_system(A, x, b, formats=["csr", "bsr"])
+    for _ in range(iterations):
+        gauss_seidel(A, x, b, iterations=1, sweep=sweep, omega=omega)
+
+
+def gauss_seidel_indexed(A, x, b, indices, iterations=1, sweep="forward"):
+    """Gauss-Seidel over an explicit row list (relaxation.py:662-731 -> relaxation.h:736-768);
+    with rows sorted by colour this is the reference's multi-colour GS."""
+    A, x, b = make_system(A, x, b, formats=["csr"])
+    _fp64(A)
+    indices = np.ascontiguousarray(np.asarray(indices, dtype="intc"), dtype=np.int32)
+    m = len(indices)
+    if sweep == "forward":
+        rs = (0, m, 1)
+    elif sweep == "backward":
+        rs = (m - 1, -1, -1)
+    elif sweep == "symmetric":
+        for _ in range(iterations):
+            gauss_seidel_indexed(A, x, b, indices, iterations=1, sweep="forward")
+            gauss_seidel_indexed(A, x, b, indices, iterations=1, sweep="backward")
+        return
+    else:
+        raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+    if m == 0:
+        return
+    E.require_gpu()
+    L = E.lib()
+    n = A.shape[0]
+    b = np.ascontiguousarray(b)
+    Ap, Aj, Ax = _csr_args(A)
+    for _ in range(iterations):
+        E.check(L.amgb_host_gauss_seidel_indexed(E.i32p(Ap), len(Ap), E.i32p(Aj), len(Aj), E.f64p(Ax),
+                                                 len(Ax), E.f64p(x), n, E.f64p(b), n,
+                                                 E.i32p(indices), m, *rs))
+
+
+def block_jacobi(A, x, b, Dinv=None, blocksize=1, iterations=1, omega=1.0):
+    """Block Jacobi, in place on x (relaxation.py:423-499 -> relaxation.h:1021-1090)."""
+    A, x, b = make_system(A, x, b, formats=["csr", "bsr"])
+    _fp64(A)
+    A = A.tobsr(blocksize=(blocksize, blocksize))
+    if Dinv is None:
+        from ..util import get_block_diag
+        Dinv = get_block_diag(A, blocksize=blocksize, inv_flag=True)
+    elif Dinv.shape[0] != int(A.shape[0] / blocksize):
+        raise ValueError("Dinv and A have incompatible dimensions")
+    elif (Dinv.shape[1] != blocksize) or (Dinv.shape[2] != blocksize):
+        raise ValueError("Dinv and blocksize are incompatible")
+    nb = int(A.shape[0] / blocksize)
+    if nb <= 0:
+        return
+    E.require_gpu()
+    L = E.lib()
+    n = A.shape[0]
+    temp = np.empty_like(x)
+    om = np.array([omega], dtype=np.float64)
+    b = np.ascontiguousarray(b)
+    Ap, Aj, Ax = _csr_args(A)
+    Tx = np.ascontiguousarray(Dinv, dtype=np.float64).reshape(-1)
+    for _ in range(iterations):
+        E.check(L.amgb_host_block_jacobi(E.i32p(Ap), len(Ap), E.i32p(Aj), len(Aj), E.f64p(Ax), len(Ax),
+                                         E.f64p(x), n, E.f64p(b), n, E.f64p(Tx), len(Tx),
+                                         E.f64p(temp), n, 0, nb, 1, E.f64p(om), 1, blocksize))

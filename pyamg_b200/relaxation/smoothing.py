@@ -1,0 +1,255 @@
+"""Smoother factory: resolve a smoother spec into per-level closures.
+
+Mirror of pyamg/relaxation/smoothing.py for the smoothers on the hot path:
+``change_smoothers`` :75-369 (spec grammar ``name | (name, {opts}) | [per-level list] | None``,
+short lists repeat their last entry, ``ml.symmetric_smoothing`` truth table), ``setup_jacobi``
+:501-508, ``setup_gauss_seidel`` :494-498, ``setup_block_jacobi`` :552-579, ``setup_sor`` :620-624,
+``setup_none`` :833-837, ``rebuild_smoother`` :881-908.  Extra (not in the reference registry):
+``gauss_seidel_indexed`` / ``multicolor_gauss_seidel`` which install the reference's
+``relaxation.gauss_seidel_indexed`` over a colour-sorted row list -- BASELINE config 3.
+
+What is stored on the level is exactly what the reference stores: a ``functools.partial`` of the
+relaxation function whose ``__name__`` is the registry key and whose ``.keywords`` carry
+``iterations``, ``omega`` (already divided by rho), ``sweep``, ``Dinv``, ``blocksize``.  The cycle
+engine parses those closures (``describe``), so hierarchies built by the reference and
+hierarchies equipped here are interchangeable.
+"""
+from functools import partial, update_wrapper
+
+import numpy as np
+from scipy import sparse
+
+from . import relaxation
+from ..util import approximate_spectral_radius, get_block_diag, get_diagonal
+from .. import _engine as E
+
+DEFAULT_SWEEP = "forward"
+DEFAULT_NITER = 1
+SYMMETRIC_RELAXATION = ["jacobi", "block_jacobi", None]
+
+
+def _unpack_arg(v):
+    if isinstance(v, tuple):
+        return v[0], v[1]
+    return v, {}
+
+
+def rho_D_inv_A(A):
+    """(approx.) spectral radius of D^-1 A, cached on the matrix (smoothing.py:372-400)."""
+    if not hasattr(A, "rho_D_inv"):
+        D_inv = get_diagonal(A, inv=True)
+        D_inv_A = sparse.dia_array((D_inv, 0), shape=(len(D_inv), len(D_inv))) @ sparse.csr_array(A)
+        A.rho_D_inv = approximate_spectral_radius(D_inv_A)
+    return A.rho_D_inv
+
+
+def rho_block_D_inv_A(A, Dinv):
+    """(approx.) spectral radius of blockdiag(A)^-1 A (smoothing.py:403-449)."""
+    if not hasattr(A, "rho_block_D_inv"):
+        bs = Dinv.shape[1]
+        nb = Dinv.shape[0]
+        Dinv_bsr = sparse.bsr_array((Dinv, np.arange(nb), np.arange(nb + 1)), shape=A.shape)
+        A.rho_block_D_inv = approximate_spectral_radius(Dinv_bsr @ sparse.bsr_array(A, blocksize=(bs, bs)))
+    return A.rho_block_D_inv
+
+
+def setup_gauss_seidel(lvl, iterations=DEFAULT_NITER, sweep=DEFAULT_SWEEP):
+    smoother = partial(relaxation.gauss_seidel, iterations=iterations, sweep=sweep)
+    update_wrapper(smoother, relaxation.gauss_seidel)
+    return smoother
+
+
+def setup_jacobi(lvl, iterations=DEFAULT_NITER, omega=1.0, withrho=True):
+    if withrho:
+        omega = omega / rho_D_inv_A(lvl.A)
+    smoother = partial(relaxation.jacobi, iterations=iterations, omega=omega)
+    update_wrapper(smoother, relaxation.jacobi)
+    return smoother
+
+
+def setup_block_jacobi(lvl, iterations=DEFAULT_NITER, omega=1.0, Dinv=None, blocksize=None,
+                       withrho=True):
+    if blocksize is None and Dinv is None:
+        if sparse.issparse(lvl.A) and lvl.A.format == "csr":
+            blocksize = 1
+        elif sparse.issparse(lvl.A) and lvl.A.format == "bsr":
+            blocksize = lvl.A.blocksize[0]
+    elif blocksize is None:
+        blocksize = Dinv.shape[1]
+    if blocksize == 1:
+        smoother = setup_jacobi(lvl, iterations=iterations, omega=omega, withrho=withrho)
+        update_wrapper(smoother, relaxation.block_jacobi)   # __name__ stays the registry key
+        return smoother
+    if Dinv is None:
+        Dinv = get_block_diag(lvl.A, blocksize=blocksize, inv_flag=True)
+    if withrho:
+        omega = omega / rho_block_D_inv_A(lvl.A, Dinv)
+    smoother = partial(relaxation.block_jacobi, iterations=iterations, omega=omega, Dinv=Dinv,
+                       blocksize=blocksize)
+    update_wrapper(smoother, relaxation.block_jacobi)
+    return smoother
+
+
+def setup_sor(lvl, omega=0.5, iterations=DEFAULT_NITER, sweep=DEFAULT_SWEEP):
+    smoother = partial(relaxation.sor, iterations=iterations, omega=omega, sweep=sweep)
+    update_wrapper(smoother, relaxation.sor)
+    return smoother
+
+
+def setup_gauss_seidel_indexed(lvl, indices=None, iterations=DEFAULT_NITER, sweep=DEFAULT_SWEEP,
+                               coloring="greedy"):
+    """Multi-colour Gauss-Seidel: ``relaxation.gauss_seidel_indexed`` over rows sorted by colour
+    (``order = argsort(colours, kind='stable')``).  If ``indices`` is not
+    given a vertex colouring of A's graph is computed here."""
+    if indices is None:
+        from ..graph import vertex_coloring
+        colors = vertex_coloring(lvl.A, method=coloring)
+        indices = np.argsort(colors, kind="stable").astype(np.int32)
+    smoother = partial(relaxation.gauss_seidel_indexed, indices=np.asarray(indices, dtype=np.int32),
+                       iterations=iterations, sweep=sweep)
+    update_wrapper(smoother, relaxation.gauss_seidel_indexed)
+    return smoother
+
+
+def setup_none(lvl):
+    def none(A, x, b):
+        pass
+    return none
+
+
+_REGISTER = {
+    "gauss_seidel": setup_gauss_seidel,
+    "jacobi": setup_jacobi,
+    "block_jacobi": setup_block_jacobi,
+    "sor": setup_sor,
+    "gauss_seidel_indexed": setup_gauss_seidel_indexed,
+    "multicolor_gauss_seidel": setup_gauss_seidel_indexed,
+    "none": setup_none,
+}
+
+# in the reference's registry (smoothing.py:840-878) but outside the accelerated path
+_OUT_OF_SCOPE = ["schwarz", "strength_based_schwarz", "block_gauss_seidel", "richardson", "chebyshev",
+                 "jacobi_ne", "gauss_seidel_ne", "gauss_seidel_nr", "cf_jacobi", "fc_jacobi",
+                 "cf_block_jacobi", "fc_block_jacobi", "gmres", "cg", "cgne", "cgnr"]
+
+
+def _setup_call(fn):
+    if fn is None:
+        fn = "none"
+    if not isinstance(fn, str):
+        raise ValueError(f"Input function must be a string or None: fn={fn}")
+    if fn in _OUT_OF_SCOPE:
+        raise NotImplementedError(f"smoother '{fn}' is not on the GPU hot path (no CPU fallback)")
+    if fn not in _REGISTER:
+        raise ValueError(f"Function {fn} does not have a setup")
+    return _REGISTER[fn]
+
+
+def _is_symmetric_pair(fn1, kw1, fn2, kw2):
+    """Truth table of smoothing.py:226-262."""
+    if kw1.get("iterations", DEFAULT_NITER) != kw2.get("iterations", DEFAULT_NITER):
+        return False
+    if fn1 != fn2:
+        return False
+    if fn1 not in SYMMETRIC_RELAXATION:
+        s1 = kw1.get("sweep", DEFAULT_SWEEP)
+        s2 = kw2.get("sweep", DEFAULT_SWEEP)
+        if (s1, s2) not in [("forward", "backward"), ("backward", "forward"), ("symmetric", "symmetric")]:
+            return False
+    return True
+
+
+def change_smoothers(ml, presmoother, postsmoother):
+    """Install pre/post smoothers on every level but the coarsest (smoothing.py:75-369)."""
+    ml.symmetric_smoothing = True
+    if isinstance(presmoother, (str, tuple)) or presmoother is None:
+        presmoother = [presmoother]
+    elif not isinstance(presmoother, list):
+        raise ValueError('Unrecognized presmoother -- use a string:\n '
+                         '"method" or ("method", opts) or list thereof.')
+    if isinstance(postsmoother, (str, tuple)) or postsmoother is None:
+        postsmoother = [postsmoother]
+    elif not isinstance(postsmoother, list):
+        raise ValueError('Unrecognized postsmoother -- use a string:\n '
+                         '"method" or ("method", opts) or list thereof.')
+    nlv = len(ml.levels) - 1
+    for i in range(nlv):
+        fn1, kw1 = _unpack_arg(presmoother[min(i, len(presmoother) - 1)])
+        fn2, kw2 = _unpack_arg(postsmoother[min(i, len(postsmoother) - 1)])
+        ml.levels[i].presmoother = _setup_call(fn1)(ml.levels[i], **kw1)
+        ml.levels[i].postsmoother = _setup_call(fn2)(ml.levels[i], **kw2)
+        if i < max(len(presmoother), len(postsmoother)) and not _is_symmetric_pair(fn1, kw1, fn2, kw2):
+            ml.symmetric_smoothing = False
+    if hasattr(ml, "_invalidate"):
+        ml._invalidate()
+
+
+def rebuild_smoother(lvl):
+    """Rebuild the pre/post smoothers of a level from their registry names (smoothing.py:881-908)."""
+    try:
+        fn1 = lvl.presmoother.__name__
+        fn2 = lvl.postsmoother.__name__
+    except AttributeError as exc:
+        raise AttributeError("The pre/post smoothers need to be functions.") from exc
+    lvl.presmoother = _setup_call(fn1)(lvl)
+    lvl.postsmoother = _setup_call(fn2)(lvl)
+
+
+# --------------------------------------------------------------------------------------------
+# closure -> engine descriptor
+# --------------------------------------------------------------------------------------------
+def describe(sm, A, keep):
+    """Parse a level's smoother object into the C ``amgb_smoother`` descriptor.
+
+    Accepts the closures of the reference (pyamg/relaxation/smoothing.py, see the descriptor
+    table in SURVEY.md) and the ones built above: a ``functools.partial`` whose ``.func.__name__``
+    names the relaxation routine, the no-op ``none`` function, or None.  Anything else -- the
+    closure-based smoothers (richardson, chebyshev, schwarz, Krylov, ...) -- is outside the
+    accelerated path: NotImplementedError, never a CPU fallback.
+    """
+    S = E.Smoother()
+    S.kind, S.iterations, S.sweep, S.blocksize, S.omega = E.SM_NONE, 1, 0, 1, 1.0
+    S.indices, S.n_indices, S.Dinv = None, 0, None
+    if sm is None:
+        return S
+    func = getattr(sm, "func", None)
+    if func is None:
+        if getattr(sm, "__name__", None) == "none":
+            return S
+        raise NotImplementedError(
+            f"smoother {getattr(sm, '__name__', sm)!r} is a closure the GPU engine cannot introspect; "
+            "supported: jacobi, gauss_seidel, gauss_seidel_indexed (multi-colour), block_jacobi, sor, None")
+    name = func.__name__
+    kw = dict(sm.keywords)
+    S.iterations = int(kw.get("iterations", 1))
+    if name == "jacobi":
+        S.kind = E.SM_JACOBI
+        S.omega = float(np.real(kw.get("omega", 1.0)))
+    elif name in ("gauss_seidel", "sor", "gauss_seidel_indexed"):
+        S.kind = E.SM_GAUSS_SEIDEL
+        sweep = kw.get("sweep", "forward")
+        if sweep not in E.SWEEPS:
+            raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+        S.sweep = E.SWEEPS[sweep]
+        S.omega = float(np.real(kw.get("omega", 1.0))) if name != "gauss_seidel_indexed" else 1.0
+        if name == "gauss_seidel_indexed":
+            idx = np.ascontiguousarray(np.asarray(kw["indices"], dtype="intc"), dtype=np.int32)
+            keep.append(idx)
+            S.indices = E.i32p(idx)
+            S.n_indices = len(idx)
+    elif name == "block_jacobi":
+        S.kind = E.SM_BLOCK_JACOBI
+        S.omega = float(np.real(kw.get("omega", 1.0)))
+        bs = int(kw.get("blocksize", 1))
+        Dinv = kw.get("Dinv", None)
+        if Dinv is None:
+            Dinv = get_block_diag(A, blocksize=bs, inv_flag=True)
+        Dinv = np.ascontiguousarray(Dinv, dtype=np.float64)
+        if Dinv.shape != (A.shape[0] // bs, bs, bs):
+            raise ValueError("Dinv and A have incompatible dimensions")
+        keep.append(Dinv)
+        S.blocksize = bs
+        S.Dinv = E.f64p(Dinv.reshape(-1))
+    else:
+        raise NotImplementedError(f"smoother '{name}' is not on the GPU hot path (no CPU fallback)")
+    return S

@@ -1,0 +1,82 @@
+"""Setup-time helpers the smoother factory needs (host, NumPy/SciPy; run once per hierarchy).
+
+These are NOT on the hot path.  When a hierarchy comes from the reference, omega and Dinv are
+read from its smoother closures (SURVEY.md hazard 2) and nothing here runs.  They exist so that
+``pyamg_b200.relaxation.smoothing.change_smoothers`` can equip hierarchies built without the
+reference (bench inputs on the GPU box) with the same quantities:
+  get_diagonal                 <-> pyamg/util/utils.py:541-600
+  get_block_diag               <-> pyamg/util/utils.py:603-692
+  approximate_spectral_radius  <-> pyamg/util/linalg.py:255-383 (Arnoldi estimate of rho)
+"""
+import numpy as np
+from scipy import sparse
+
+
+def get_diagonal(A, inv=False):
+    """diag(A) (or its entry-wise inverse with 0 where the diagonal is 0)."""
+    D = np.asarray(sparse.csr_array(A).diagonal(), dtype=np.float64)
+    if inv:
+        Dinv = np.zeros_like(D)
+        mask = D != 0.0
+        Dinv[mask] = 1.0 / D[mask]
+        return Dinv
+    return D
+
+
+def get_block_diag(A, blocksize, inv_flag=True):
+    """(n/bs, bs, bs) array of the diagonal blocks of A, pseudo-inverted if inv_flag."""
+    if A.shape[0] != A.shape[1]:
+        raise ValueError("Expected square matrix")
+    if A.shape[0] % blocksize != 0:
+        raise ValueError("blocksize and A.shape must be compatible")
+    if not sparse.issparse(A) or A.format != "bsr" or A.blocksize != (blocksize, blocksize):
+        A = sparse.bsr_array(A, blocksize=(blocksize, blocksize))
+    nb = A.shape[0] // blocksize
+    block_diag = np.zeros((nb, blocksize, blocksize), dtype=np.float64)
+    rows = np.repeat(np.arange(nb), np.diff(A.indptr))
+    on_diag = np.nonzero(rows == A.indices)[0]
+    block_diag[A.indices[on_diag]] = A.data[on_diag]   # last duplicate wins
+    if inv_flag:
+        block_diag = np.linalg.pinv(block_diag)
+    return np.ascontiguousarray(block_diag)
+
+
+def approximate_spectral_radius(A, maxiter=15, restarts=5, seed=20260922):
+    """Largest |Ritz value| of a restarted Arnoldi process started from a seeded random vector.
+
+    Same estimator family as the reference (Arnoldi, 15 steps, 5 restarts); the start vector is
+    seeded here, so the value is reproducible (the reference's is not: SURVEY.md hazard 2).
+    """
+    A = sparse.csr_array(A) if not sparse.issparse(A) else A
+    n = A.shape[0]
+    if n == 0:
+        return 0.0
+    rng = np.random.default_rng(seed)
+    v0 = rng.random(n)
+    maxiter = int(min(maxiter, n))
+    rho = 0.0
+    for _ in range(restarts + 1):
+        V = np.zeros((maxiter + 1, n))
+        H = np.zeros((maxiter + 1, maxiter))
+        nv = np.linalg.norm(v0)
+        if nv == 0.0:
+            break
+        V[0] = v0 / nv
+        m = maxiter
+        for j in range(maxiter):
+            w = A @ V[j]
+            for i in range(j + 1):     # modified Gram-Schmidt
+                H[i, j] = np.dot(V[i], w)
+                w -= H[i, j] * V[i]
+            H[j + 1, j] = np.linalg.norm(w)
+            if H[j + 1, j] < 1e-12 * max(1.0, abs(H[:j + 1, :j + 1]).max()):
+                m = j + 1
+                break
+            V[j + 1] = w / H[j + 1, j]
+        ev, evec = np.linalg.eig(H[:m, :m])
+        k = int(np.argmax(np.abs(ev)))
+        rho = float(np.abs(ev[k]))
+        v0 = np.real(V[:m].T @ evec[:, k])   # restart from the dominant Ritz vector
+        if m < maxiter:
+            break
+    return rho

@@ -1,0 +1,46 @@
+"""pytest configuration: `gpu` marker + shared helpers.
+
+`-m "not gpu"`: oracle vs golden vectors, host logic, C-ABI symbol export (no compute calls).
+`-m gpu`      : parity tests proper, through the C ABI of libpyamg_b200.so on a real B200.
+"""
+import glob
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+GOLDEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def golden_path(name):
+    return os.path.join(GOLDEN_DIR, name + ".npz")
+
+
+@pytest.fixture(scope="session")
+def load_golden():
+    from pyamg_b200.hierarchy_io import load_hierarchy
+    cache = {}
+
+    def _load(name):
+        if name not in cache:
+            cache[name] = load_hierarchy(golden_path(name))
+        return cache[name]
+
+    return _load
+
+
+def relerr(a, b):
+    import numpy as np
+    a = np.asarray(a, dtype=float).ravel()
+    b = np.asarray(b, dtype=float).ravel()
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)

@@ -1,0 +1,158 @@
+"""Generate the golden fixtures under tests/golden/ by running the REAL reference.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    # 1. build the reference in a scratch dir (SURVEY.md 8(c) recipe; nothing is copied here)
+    D=/tmp/pyamg_ref; mkdir -p $D; cp -r /root/reference/pyamg $D/pyamg; cd $D/pyamg/amg_core
+    for h in air evolution_strength graph krylov linalg relaxation ruge_stuben smoothed_aggregation; do
+      g++ -O2 -std=c++11 -ftemplate-depth=2048 -shared -fPIC -fvisibility=hidden \
+          $(python3 -m pybind11 --includes) ${h}_bind.cpp \
+          -o ${h}$(python3 -c "import sysconfig;print(sysconfig.get_config_var('EXT_SUFFIX'))") & done; wait
+    mkdir $D/pyamg-0.0.0.dist-info
+    printf 'Metadata-Version: 2.1\nName: pyamg\nVersion: 0.0.0+oracle\n' > $D/pyamg-0.0.0.dist-info/METADATA
+    # 2. generate
+    cd /root/repo && PYTHONPATH=/tmp/pyamg_ref python tests/golden/make_golden.py
+
+Every fixture is one .npz written by pyamg_b200.hierarchy_io.save_hierarchy: the hierarchy the
+reference built (operators, smoother closures' parameters, cached coarse pinv) plus, as extra
+arrays, the rhs ``b``, the reference's ``x_ref = ml.solve(b, tol=0, maxiter=N)``, its residual
+history, W/F-cycle results, and single-sweep outputs of the reference's own relaxation routines and
+SciPy matvecs on level 0 (``k_*``).  Configs are the five BASELINE.json families at sizes the CPU
+suite runs in seconds.  rhs seed = 20260922.
+"""
+import os
+import sys
+
+import numpy as np
+
+import pyamg
+from pyamg.gallery import poisson, stencil_grid, linear_elasticity
+from pyamg.gallery.diffusion import diffusion_stencil_2d
+from pyamg.graph import vertex_coloring
+from pyamg.relaxation import relaxation as ref_relax
+from functools import partial, update_wrapper
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from pyamg_b200.hierarchy_io import save_hierarchy  # noqa: E402
+
+SEED = 20260922
+NCYC = 6
+
+
+def install_multicolor_gs(ml, sweep="symmetric"):
+    """replace every level's smoothers by gauss_seidel_indexed over the
+    MIS-colour-sorted row list (the reference's only expression of multi-colour GS)."""
+    for lvl in ml.levels[:-1]:
+        c = vertex_coloring(lvl.A, "MIS")
+        order = np.argsort(c, kind="stable").astype(np.int32)
+        for which in ("presmoother", "postsmoother"):
+            sm = partial(ref_relax.gauss_seidel_indexed, indices=order, iterations=1, sweep=sweep)
+            update_wrapper(sm, ref_relax.gauss_seidel_indexed)
+            setattr(lvl, which, sm)
+
+
+def kernel_goldens(ml, rng):
+    """Single-sweep outputs of the reference's native kernels on level 0."""
+    lvl = ml.levels[0]
+    A = lvl.A
+    n = A.shape[0]
+    x = rng.random(n)
+    b = rng.random(n)
+    out = {"k_x": x, "k_b": b, "k_Ax": A @ x, "k_Rx": lvl.R @ x,
+           "k_Pxc": lvl.P @ rng.random(lvl.P.shape[1])}
+    out["k_xc"] = None
+    xc = rng.random(lvl.P.shape[1])
+    out["k_xc"] = xc
+    out["k_Pxc"] = lvl.P @ xc
+    for which in ("presmoother", "postsmoother"):
+        y = x.copy()
+        getattr(lvl, which)(A, y, b)
+        out["k_" + which] = y
+    Acsr = A.tocsr()
+    y = x.copy()
+    ref_relax.jacobi(Acsr, y, b, iterations=1, omega=0.7)
+    out["k_jacobi_w07"] = y
+    y = x.copy()
+    ref_relax.gauss_seidel(Acsr, y, b, iterations=1, sweep="symmetric")
+    out["k_gs_symmetric"] = y
+    y = x.copy()
+    ref_relax.gauss_seidel(Acsr, y, b, iterations=2, sweep="backward")
+    out["k_gs_backward2"] = y
+    y = x.copy()
+    ref_relax.sor(Acsr, y, b, omega=1.3, iterations=1, sweep="forward")
+    out["k_sor_13"] = y
+    return out
+
+
+def emit(name, ml, extra_kw=None, ncyc=NCYC):
+    rng = np.random.default_rng(SEED)
+    n = ml.levels[0].A.shape[0]
+    b = rng.random(n)
+    extra = {"b": b}
+    res = []
+    extra["x_ref"] = ml.solve(b, tol=0, maxiter=ncyc, residuals=res)   # also caches coarse pinv
+    extra["residuals"] = np.array(res)
+    extra["x_ref_W"] = ml.solve(b, tol=0, maxiter=2, cycle="W")
+    extra["x_ref_F"] = ml.solve(b, tol=0, maxiter=2, cycle="F")
+    x0 = rng.random(n)
+    res = []
+    xt, info = ml.solve(b, x0=x0, tol=1e-6, maxiter=50, residuals=res, return_info=True)
+    extra.update({"x0": x0, "x_ref_tol": xt, "residuals_tol": np.array(res),
+                  "info_tol": np.array([info])})
+    extra.update(kernel_goldens(ml, rng))
+    if extra_kw:
+        extra.update(extra_kw)
+    path = os.path.join(HERE, name + ".npz")
+    save_hierarchy(path, ml, extra=extra)
+    sizes = [lv.A.shape[0] for lv in ml.levels]
+    print(f"{name}: levels={sizes} fmt={[lv.A.format for lv in ml.levels]} "
+          f"res {extra['residuals'][0]:.3e}->{extra['residuals'][-1]:.3e} "
+          f"tol-its={len(res) - 1} info={info}  {os.path.getsize(path) / 1024:.0f} KB")
+
+
+def main():
+    # cfg1 family: RS, default symmetric (lexicographic) Gauss-Seidel
+    np.random.seed(SEED)
+    A = poisson((30, 30), format="csr")
+    emit("cfg1_rs_gs_poisson2d", pyamg.ruge_stuben_solver(A))
+
+    # cfg2 family: SA + weighted Jacobi (P, R and coarse A are BSR(1,1))
+    np.random.seed(SEED)
+    A = poisson((40, 40), format="csr")
+    sm = ("jacobi", {"omega": 4.0 / 3.0})
+    emit("cfg2_sa_jacobi_poisson2d", pyamg.smoothed_aggregation_solver(A, presmoother=sm, postsmoother=sm))
+
+    # cfg3 family: RS on 3D Poisson with multi-colour GS (gauss_seidel_indexed over MIS colours)
+    np.random.seed(SEED)
+    A = poisson((12, 12, 12), format="csr")
+    ml = pyamg.ruge_stuben_solver(A)
+    install_multicolor_gs(ml)
+    emit("cfg3_rs_mcgs_poisson3d", ml)
+
+    # cfg4 family: anisotropic diffusion, SA (evolution strength: the symmetric default diverges,
+    # SURVEY.md 8(d)-4) + Jacobi, two sweeps pre / one post to exercise the ping-pong parity
+    np.random.seed(SEED)
+    S = diffusion_stencil_2d(epsilon=0.001, theta=np.pi / 6, type="FE")
+    A = stencil_grid(S, (48, 48), format="csr")
+    ml = pyamg.smoothed_aggregation_solver(A, strength=("evolution", {}),
+                                           presmoother=("jacobi", {"omega": 4.0 / 3.0, "iterations": 2}),
+                                           postsmoother=("jacobi", {"omega": 4.0 / 3.0}))
+    emit("cfg4_sa_jacobi_aniso2d", ml)
+
+    # cfg5 family: linear elasticity BSR(2,2) -> (3,3), SA with rigid-body modes, block Jacobi
+    np.random.seed(SEED)
+    A, B = linear_elasticity((14, 14))
+    ml = pyamg.smoothed_aggregation_solver(A, B=B, presmoother="block_jacobi", postsmoother="block_jacobi")
+    emit("cfg5_sa_bjacobi_elasticity", ml)
+
+    # extra: RS with forward/backward SOR-free GS pair and None post-smoother (descriptor coverage)
+    np.random.seed(SEED)
+    A = poisson((9, 9, 9), format="csr")
+    ml = pyamg.ruge_stuben_solver(A, presmoother=("gauss_seidel", {"sweep": "forward", "iterations": 2}),
+                                  postsmoother=None, max_coarse=5)
+    emit("cfg6_rs_gsfwd_none_poisson3d", ml)
+
+
+if __name__ == "__main__":
+    main()
