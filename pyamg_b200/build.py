@@ -31,6 +31,28 @@ def is_stale():
     return any(os.path.getmtime(s) > t for s in SOURCES + HEADERS if os.path.exists(s))
 
 
+HOST_LIB = os.path.join(PKG, "libpyamg_b200_host.so")
+HOST_SOURCES = [os.path.join(PKG, "csrc", "host_setup.cpp")]
+
+
+def build_host_library(force=False, verbose=False):
+    """Compile the host-side setup helpers (plain C++, no CUDA). Returns the .so path."""
+    stale = (not os.path.exists(HOST_LIB)) or any(
+        os.path.getmtime(s) > os.path.getmtime(HOST_LIB) for s in HOST_SOURCES)
+    if not force and not stale:
+        return HOST_LIB
+    cxx = shutil.which("g++")
+    if cxx is None:
+        if os.path.exists(HOST_LIB):
+            return HOST_LIB
+        raise RuntimeError("g++ not found and libpyamg_b200_host.so is not built")
+    cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-shared", "-o", HOST_LIB] + HOST_SOURCES
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    return HOST_LIB
+
+
 def build_extension(force=False, verbose=False):
     """Compile the CUDA engine if missing or older than its sources. Returns the .so path."""
     if not force and not is_stale():
@@ -50,3 +72,4 @@ def build_extension(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build_extension(force="--force" in sys.argv, verbose=True))
+    print(build_host_library(force="--force" in sys.argv, verbose=True))

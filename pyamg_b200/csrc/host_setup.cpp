@@ -1,0 +1,281 @@
+// host_setup.cpp -- host-side (CPU, C++) hierarchy-setup helpers: libpyamg_b200_host.so.
+//
+// NOT on the solve-phase hot path.  The reference's setup (strength / splitting / interpolation,
+// pyamg/amg_core/ruge_stuben.h + graph.h) stays the authority whenever a hierarchy comes from the
+// reference.  These routines exist so that the BASELINE inputs -- ruge_stuben_solver hierarchies,
+// colour-sorted Gauss-Seidel row lists -- can be synthesised on the GPU box, where the reference
+// is not installed, with the same published algorithms (Ruge & Stueben 1987; Briggs/Henson/
+// McCormick 2000 ch. 8) and the same tie-breaking, so the hierarchies coincide with the
+// reference's (checked in tests/test_setup.py against splittings / operators the reference
+// produced).  SURVEY.md 8(f)-3/4 "next" rows start here.
+//
+//   amgb_setup_classical_strength  <->  classical_strength_of_connection (abs norm)   ruge_stuben.h:64-110
+//                                       + |.|, row scaling, zero drop                 strength.py:236-241
+//   amgb_setup_rs_splitting        <->  rs_cf_splitting (first pass)                  ruge_stuben.h:285-466
+//   amgb_setup_classical_interp_*  <->  remove_strong_FF_connections + rs_classical_interpolation_pass1/2
+//                                                                                     ruge_stuben.h:1083-1383
+//   amgb_setup_greedy_coloring     <->  role of vertex_coloring (graph.h:218-235); first-fit greedy
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <limits>
+#include <vector>
+
+extern "C" {
+
+// S = pattern of strong connections of A (|a_ij| >= theta * max_{k != i} |a_ik|, diagonal always kept),
+// values |a_ij| / max_j |S_ij| per row, exact zeros dropped.  Sp/Sj/Sx/Sidx sized like A; Sidx[k] is
+// the position in A of S's k-th entry (so A's values on S's pattern are Ax[Sidx]).  Returns nnz(S).
+int64_t amgb_setup_classical_strength(int32_t n, const int32_t *Ap, const int32_t *Aj, const double *Ax,
+                                      double theta, int32_t *Sp, int32_t *Sj, double *Sx, int32_t *Sidx)
+{
+    int64_t nnz = 0;
+    Sp[0] = 0;
+    for (int32_t i = 0; i < n; i++) {
+        double max_off = std::numeric_limits<double>::min();
+        for (int32_t jj = Ap[i]; jj < Ap[i + 1]; jj++)
+            if (Aj[jj] != i) max_off = std::max(max_off, std::fabs(Ax[jj]));
+        const double thr = theta * max_off;
+        const int64_t row_begin = nnz;
+        double row_max = 0.0;
+        for (int32_t jj = Ap[i]; jj < Ap[i + 1]; jj++) {
+            const double v = std::fabs(Ax[jj]);
+            if (Aj[jj] == i || v >= thr) {
+                Sj[nnz] = Aj[jj];
+                Sx[nnz] = v;
+                Sidx[nnz] = jj;
+                row_max = std::max(row_max, v);
+                nnz++;
+            }
+        }
+        // scale by the largest entry of the row, then drop exact zeros
+        int64_t w = row_begin;
+        for (int64_t k = row_begin; k < nnz; k++) {
+            const double v = (row_max != 0.0) ? Sx[k] / row_max : Sx[k];
+            if (v != 0.0) { Sj[w] = Sj[k]; Sx[w] = v; Sidx[w] = Sidx[k]; w++; }
+        }
+        nnz = w;
+        Sp[i + 1] = (int32_t)nnz;
+    }
+    return nnz;
+}
+
+namespace {
+// Nodes kept sorted by an integer key in one array; each key owns a contiguous slice.  Raising or
+// lowering a key by one is a swap with the slice boundary -- the classic O(1) bucket update used
+// for the Ruge-Stueben measure.  Boundary conventions (raise: to the END of the slice, which then
+// becomes the first slot of key+1; lower: to the BEGINNING, which becomes the last slot of key-1)
+// determine the tie-breaking and hence the splitting.
+struct MeasureBuckets {
+    std::vector<int32_t> key, slot_of, node_at, first, size;
+    void build(const std::vector<int32_t> &keys, int32_t nkeys)
+    {
+        const int32_t n = (int32_t)keys.size();
+        key = keys;
+        first.assign((size_t)nkeys, 0);
+        size.assign((size_t)nkeys, 0);
+        slot_of.resize((size_t)n);
+        node_at.resize((size_t)n);
+        for (int32_t i = 0; i < n; i++) size[(size_t)key[i]]++;
+        int32_t run = 0;
+        for (int32_t k = 0; k < nkeys; k++) { first[k] = run; run += size[k]; size[k] = 0; }
+        for (int32_t i = 0; i < n; i++) {   // ascending node id inside a slice
+            const int32_t s = first[key[i]] + size[key[i]]++;
+            node_at[s] = i;
+            slot_of[i] = s;
+        }
+    }
+    void swap_slots(int32_t a, int32_t b)
+    {
+        const int32_t na = node_at[a], nb = node_at[b];
+        node_at[a] = nb; node_at[b] = na;
+        slot_of[na] = b; slot_of[nb] = a;
+    }
+    void raise(int32_t v)
+    {
+        const int32_t k = key[v];
+        const int32_t last = first[k] + size[k] - 1;
+        swap_slots(slot_of[v], last);
+        size[k]--;
+        size[k + 1]++;
+        first[k + 1] = last;
+        key[v] = k + 1;
+    }
+    void lower(int32_t v)
+    {
+        const int32_t k = key[v];
+        const int32_t head = first[k];
+        swap_slots(slot_of[v], head);
+        size[k]--;
+        size[k - 1]++;
+        first[k]++;
+        first[k - 1] = first[k] - size[k - 1];
+        key[v] = k - 1;
+    }
+};
+}  // namespace
+
+// First-pass Ruge-Stueben C/F splitting on the strength graph S (no diagonal) and its transpose T.
+// splitting[i] = 1 (C) or 0 (F).
+void amgb_setup_rs_splitting(int32_t n, const int32_t *Sp, const int32_t *Sj, const int32_t *Tp,
+                             const int32_t *Tj, int32_t *splitting)
+{
+    enum { F_PT = 0, C_PT = 1, UNDECIDED = 2, NEW_F = 3 };
+    std::vector<int32_t> measure((size_t)n);
+    int32_t top = 0;
+    for (int32_t i = 0; i < n; i++) {
+        measure[i] = Tp[i + 1] - Tp[i];      // how many points depend strongly on i
+        top = std::max(top, measure[i]);
+    }
+    MeasureBuckets q;
+    q.build(measure, std::max(2 * top, n + 1) + 2);
+    for (int32_t i = 0; i < n; i++) {
+        const bool isolated = q.key[i] == 0 || (q.key[i] == 1 && Tj[Tp[i]] == i);
+        splitting[i] = isolated ? F_PT : UNDECIDED;
+    }
+    for (int32_t slot = n - 1; slot >= 0; slot--) {   // always the largest remaining measure
+        const int32_t i = q.node_at[slot];
+        q.size[q.key[i]]--;
+        if (q.key[i] <= 0) break;
+        if (splitting[i] != UNDECIDED) continue;
+        splitting[i] = C_PT;
+        // points that depend on the new C point become F points ...
+        for (int32_t jj = Tp[i]; jj < Tp[i + 1]; jj++)
+            if (splitting[Tj[jj]] == UNDECIDED) splitting[Tj[jj]] = NEW_F;
+        // ... and every undecided point such an F point depends on gets more attractive
+        for (int32_t jj = Tp[i]; jj < Tp[i + 1]; jj++) {
+            const int32_t j = Tj[jj];
+            if (splitting[j] != NEW_F) continue;
+            splitting[j] = F_PT;
+            for (int32_t kk = Sp[j]; kk < Sp[j + 1]; kk++) {
+                const int32_t k = Sj[kk];
+                if (splitting[k] == UNDECIDED && q.key[k] < n - 1) q.raise(k);
+            }
+        }
+        // points the new C point depends on are less needed as C points
+        for (int32_t jj = Sp[i]; jj < Sp[i + 1]; jj++) {
+            const int32_t j = Sj[jj];
+            if (splitting[j] == UNDECIDED && q.key[j] != 0) q.lower(j);
+        }
+    }
+    for (int32_t i = 0; i < n; i++)
+        if (splitting[i] != C_PT) splitting[i] = F_PT;
+}
+
+static inline int sign_of(double v) { return v < 0 ? -1 : 1; }
+
+// Modified classical interpolation, pass 0+1: on the strength pattern S (same row order as A's
+// strong entries, diagonal allowed) zero out -- keep[jj] = 0 -- strong F-F connections of F rows
+// that share no strong C point, then count the entries of P.  Pp has n+1 entries.
+void amgb_setup_classical_interp_count(int32_t n, const int32_t *Sp, const int32_t *Sj,
+                                       const int32_t *splitting, uint8_t *keep, int32_t *Pp)
+{
+    const int64_t nnzS = Sp[n];
+    for (int64_t k = 0; k < nnzS; k++) keep[k] = 1;
+    for (int32_t i = 0; i < n; i++) {
+        if (splitting[i] != 0) continue;
+        for (int32_t jj = Sp[i]; jj < Sp[i + 1]; jj++) {
+            const int32_t j = Sj[jj];
+            if (splitting[j] != 0) continue;
+            bool common = false;
+            for (int32_t ii = Sp[i]; ii < Sp[i + 1] && !common; ii++) {
+                const int32_t c = Sj[ii];
+                if (splitting[c] != 1) continue;
+                for (int32_t kk = Sp[j]; kk < Sp[j + 1]; kk++)
+                    if (Sj[kk] == c) { common = true; break; }
+            }
+            if (!common) keep[jj] = 0;
+        }
+    }
+    int32_t nnz = 0;
+    Pp[0] = 0;
+    for (int32_t i = 0; i < n; i++) {
+        if (splitting[i] == 1) {
+            nnz++;
+        } else {
+            for (int32_t jj = Sp[i]; jj < Sp[i + 1]; jj++)
+                if (keep[jj] && splitting[Sj[jj]] == 1 && Sj[jj] != i) nnz++;
+        }
+        Pp[i + 1] = nnz;
+    }
+}
+
+// pass 2: weights.  For an F point i with strong C set C_i and strong F set F_i (after the F-F
+// filter):  w_ij = -( a_ij + sum_{k in F_i} a_ik a~_kj / sum_{l in C_i} a~_kl ) / ( a_ii + sum_{weak} a_im ),
+// where a~_kx = a_kx if sign(a_kx) != sign(a_kk), else 0 ("modified" classical interpolation).
+// Sv holds A's values on the (filtered) strength pattern: Sv[jj] = a_{i,Sj[jj]}.
+void amgb_setup_classical_interp_fill(int32_t n, const int32_t *Ap, const int32_t *Aj, const double *Ax,
+                                      const int32_t *Sp, const int32_t *Sj, const double *Sv,
+                                      const uint8_t *keep, const int32_t *splitting, const int32_t *Pp,
+                                      int32_t *Pj, double *Px)
+{
+    std::vector<int32_t> cmap((size_t)n);
+    for (int32_t i = 0, c = 0; i < n; i++) { cmap[i] = c; c += splitting[i]; }
+    for (int32_t i = 0; i < n; i++) {
+        if (splitting[i] == 1) {
+            Pj[Pp[i]] = cmap[i];
+            Px[Pp[i]] = 1.0;
+            continue;
+        }
+        double denom = 0.0;
+        for (int32_t mm = Ap[i]; mm < Ap[i + 1]; mm++) denom += Ax[mm];
+        for (int32_t mm = Sp[i]; mm < Sp[i + 1]; mm++)
+            if (keep[mm] && Sj[mm] != i) denom -= Sv[mm];
+        int32_t out = Pp[i];
+        for (int32_t jj = Sp[i]; jj < Sp[i + 1]; jj++) {
+            const int32_t j = Sj[jj];
+            if (!keep[jj] || splitting[j] != 1) continue;
+            double numer = Sv[jj];
+            for (int32_t kk = Sp[i]; kk < Sp[i + 1]; kk++) {
+                const int32_t k = Sj[kk];
+                if (!keep[kk] || splitting[k] != 0 || k == i) continue;
+                const double a_ik = Sv[kk];
+                double a_kj = 0.0, a_kk = 0.0;
+                for (int32_t s = Ap[k]; s < Ap[k + 1]; s++) {
+                    if (Aj[s] == j) a_kj = Ax[s];
+                    else if (Aj[s] == k) a_kk = Ax[s];
+                }
+                if (sign_of(a_kj) == sign_of(a_kk)) a_kj = 0.0;
+                if (std::fabs(a_kj) > 1e-15 * std::fabs(a_ik)) {
+                    double inner = 0.0;
+                    for (int32_t ll = Sp[i]; ll < Sp[i + 1]; ll++) {
+                        const int32_t l = Sj[ll];
+                        if (!keep[ll] || splitting[l] != 1) continue;
+                        for (int32_t s = Ap[k]; s < Ap[k + 1]; s++) {
+                            if (Aj[s] == l) {
+                                if (sign_of(Ax[s]) != sign_of(a_kk)) inner += Ax[s];
+                                break;
+                            }
+                        }
+                    }
+                    numer += a_ik * a_kj / inner;
+                }
+            }
+            Pj[out] = cmap[j];
+            Px[out] = -numer / denom;
+            out++;
+        }
+    }
+}
+
+// First-fit greedy vertex colouring in natural order (diagonal ignored). Returns #colours.
+int32_t amgb_setup_greedy_coloring(int32_t n, const int32_t *Ap, const int32_t *Aj, int32_t *colors)
+{
+    std::vector<int32_t> mark;   // mark[c] == i  <=>  colour c is taken by a neighbour of i
+    int32_t ncol = 0;
+    for (int32_t i = 0; i < n; i++) colors[i] = -1;
+    for (int32_t i = 0; i < n; i++) {
+        for (int32_t jj = Ap[i]; jj < Ap[i + 1]; jj++) {
+            const int32_t j = Aj[jj];
+            if (j != i && j >= 0 && j < n && colors[j] >= 0) mark[(size_t)colors[j]] = i;
+        }
+        int32_t c = 0;
+        while (c < ncol && mark[(size_t)c] == i) c++;
+        if (c == ncol) { mark.push_back(-1); ncol++; }
+        colors[i] = c;
+    }
+    return ncol;
+}
+
+}  // extern "C"

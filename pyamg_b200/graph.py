@@ -1,0 +1,36 @@
+"""Graph helpers used at smoother-setup time (host): vertex colouring for multi-colour GS.
+
+Plays the role of pyamg.graph.vertex_coloring (pyamg/graph.py:84-126); the default here is a
+first-fit greedy colouring in natural order (red-black on 5/7-point stencils).  Any colouring --
+including the reference's 'MIS' one -- gives a valid multi-colour sweep: the engine derives the
+dependency waves from the row list itself (csrc/engine.cu build_waves), so a colouring only
+influences speed, never correctness, and the CPU oracle sweeps the same row list sequentially.
+"""
+import numpy as np
+from scipy import sparse
+
+from . import _host as H
+
+
+def vertex_coloring(G, method="greedy"):
+    """Colours (int32 array, starting at 0) such that no edge of G joins equal colours."""
+    if method not in ("greedy",):
+        raise NotImplementedError(f"colouring method {method!r}: only 'greedy' is built in; pass the "
+                                  "colours/row list from pyamg.graph.vertex_coloring explicitly")
+    G = sparse.csr_array(G)
+    if G.shape[0] != G.shape[1]:
+        raise ValueError("expected square matrix")
+    # symmetrise the pattern so the colouring is valid for structurally non-symmetric operators too
+    if (abs(G) != abs(G).T).nnz != 0:
+        G = (abs(G) + abs(G).T).tocsr()
+    n = G.shape[0]
+    Ap = np.ascontiguousarray(G.indptr, dtype=np.int32)
+    Aj = np.ascontiguousarray(G.indices, dtype=np.int32)
+    colors = np.empty(n, dtype=np.int32)
+    H.lib().amgb_setup_greedy_coloring(n, H.ip(Ap), H.ip(Aj), H.ip(colors))
+    return colors
+
+
+def color_order(colors):
+    """Row list sorted by colour (stable): the ``indices`` of gauss_seidel_indexed."""
+    return np.argsort(colors, kind="stable").astype(np.int32)

@@ -1,0 +1,152 @@
+"""CPU tests of the host side: C-ABI export list, smoother-closure parsing, the smoother factory's
+truth tables, hierarchy (de)serialisation, reporting methods, and loud failure without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import pyamg_b200
+from pyamg_b200 import _engine as E
+from pyamg_b200.relaxation import smoothing, relaxation
+from conftest import GOLDEN, ROOT
+from kats import poisson1d
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "pyamg_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(amgb_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    L = E.lib()
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(E.SYMBOLS) == declared
+    assert L.amgb_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    if E.lib().amgb_device_count() > 0:
+        pytest.skip("GPU present")
+    A = poisson1d(4)
+    with pytest.raises(E.EngineError):
+        relaxation.jacobi(A, np.zeros(4), np.ones(4))
+    lvl = pyamg_b200.MultilevelSolver.Level()
+    lvl.A = A
+    with pytest.raises(E.EngineError):
+        pyamg_b200.MultilevelSolver([lvl]).solve(np.ones(4))
+    h = ctypes.c_void_p()
+    assert E.lib().amgb_hierarchy_create(0, ctypes.byref(h)) != 0
+    assert E.lib().amgb_last_error()
+
+
+def test_validation_precedes_device_use():
+    """make_system's contract (relaxation.py:15-97) is enforced on the host, GPU or not."""
+    A = poisson1d(4)
+    with pytest.raises(ValueError):
+        relaxation.jacobi(A, [0.0] * 4, np.zeros(4))
+    with pytest.raises(TypeError):
+        relaxation.jacobi(A, np.zeros(4, dtype=np.float32), np.zeros(4))
+    with pytest.raises(ValueError):
+        relaxation.gauss_seidel(A, np.zeros(8)[::2], np.zeros(4))
+    with pytest.raises(ValueError):
+        relaxation.gauss_seidel(A, np.zeros(4), np.zeros(4), sweep="sideways")
+    with pytest.raises(ValueError):
+        relaxation.block_jacobi(A, np.zeros(4), np.zeros(4), Dinv=np.zeros((3, 2, 2)), blocksize=2)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_closure_parsing_of_reference_built_hierarchies(name, load_golden):
+    ml, _ = load_golden(name)
+    for lvl in ml.levels[:-1]:
+        for which in ("presmoother", "postsmoother"):
+            keep = []
+            S = smoothing.describe(getattr(lvl, which), lvl.A, keep)
+            sm = getattr(lvl, which)
+            if getattr(sm, "func", None) is None:
+                assert S.kind == E.SM_NONE
+                continue
+            fn = sm.func.__name__
+            assert S.iterations == sm.keywords.get("iterations", 1)
+            if fn == "jacobi":
+                assert S.kind == E.SM_JACOBI and S.omega == pytest.approx(float(sm.keywords["omega"]))
+            elif fn == "block_jacobi":
+                assert S.kind == E.SM_BLOCK_JACOBI and S.blocksize == sm.keywords["blocksize"]
+            else:
+                assert S.kind == E.SM_GAUSS_SEIDEL
+                assert S.sweep == E.SWEEPS[sm.keywords.get("sweep", "forward")]
+                assert (S.n_indices > 0) == ("indices" in sm.keywords)
+
+
+def test_unsupported_smoothers_fail_loudly():
+    def richardson(A, x, b):
+        pass
+    with pytest.raises(NotImplementedError):
+        smoothing.describe(richardson, poisson1d(3), [])
+    with pytest.raises(NotImplementedError):
+        smoothing._setup_call("chebyshev")
+    with pytest.raises(ValueError):
+        smoothing._setup_call("no_such_smoother")
+    with pytest.raises(NotImplementedError):
+        pyamg_b200.coarse_grid_solver("cg")
+
+
+def _two_level():
+    A = poisson1d(8)
+    P = sp.csr_array(np.kron(np.eye(4), np.ones((2, 1))))
+    l0, l1 = pyamg_b200.MultilevelSolver.Level(), pyamg_b200.MultilevelSolver.Level()
+    l0.A, l0.P = A, P
+    l1.A = sp.csr_array(P.T @ A @ P)
+    return pyamg_b200.MultilevelSolver([l0, l1])
+
+
+def test_change_smoothers_grammar_and_symmetry_flag():
+    """pyamg/relaxation/tests/test_smoothing.py:94-145 (truth table, __name__ kept)."""
+    ml = _two_level()
+    assert hasattr(ml.levels[0], "R")                       # multilevel.py:180-182
+    cases = [(("gauss_seidel", {"sweep": "symmetric"}), ("gauss_seidel", {"sweep": "symmetric"}), True),
+             (("gauss_seidel", {"sweep": "forward"}), ("gauss_seidel", {"sweep": "backward"}), True),
+             (("gauss_seidel", {"sweep": "forward"}), ("gauss_seidel", {"sweep": "forward"}), False),
+             ("jacobi", "jacobi", True),
+             (("jacobi", {"iterations": 2}), "jacobi", False),
+             ("jacobi", "gauss_seidel", False),
+             (None, None, True)]
+    for pre, post, sym in cases:
+        pyamg_b200.change_smoothers(ml, pre, post)
+        assert ml.symmetric_smoothing is sym, (pre, post)
+    pyamg_b200.change_smoothers(ml, "block_jacobi", ("jacobi", {"omega": 4.0 / 3.0}))
+    assert ml.levels[0].presmoother.__name__ == "block_jacobi"      # rewrapped Jacobi keeps the registry name
+    assert ml.levels[0].presmoother.func is relaxation.jacobi
+    w = ml.levels[0].postsmoother.keywords["omega"]
+    rho = smoothing.rho_D_inv_A(ml.levels[0].A)
+    assert w == pytest.approx(4.0 / 3.0 / rho) and 1.7 < rho < 2.0   # rho(D^-1 A) of 1-D Poisson -> 2
+    with pytest.raises(ValueError):
+        pyamg_b200.change_smoothers(ml, 3.14, None)
+    smoothing.rebuild_smoother(ml.levels[0])
+    assert ml.levels[0].presmoother.__name__ == "block_jacobi"
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_hierarchy_io_roundtrip_and_reports(name, load_golden, tmp_path):
+    from pyamg_b200.hierarchy_io import save_hierarchy, load_hierarchy
+    ml, ex = load_golden(name)
+    p = str(tmp_path / "h.npz")
+    save_hierarchy(p, ml, extra={"b": ex["b"]})
+    ml2, ex2 = load_hierarchy(p)
+    assert np.array_equal(ex2["b"], ex["b"])
+    assert len(ml2.levels) == len(ml.levels)
+    for a, b in zip(ml.levels, ml2.levels):
+        assert (a.A != b.A).nnz == 0 and a.A.format == b.A.format
+        if hasattr(a, "P"):
+            assert (a.P != b.P).nnz == 0 and (a.R != b.R).nnz == 0
+            assert a.presmoother.__name__ == b.presmoother.__name__
+    assert np.array_equal(ml.coarse_solver.P, ml2.coarse_solver.P)
+    text = repr(ml)
+    assert "MultilevelSolver" in text and f"Number of Levels:     {len(ml.levels)}" in text
+    nnz = [lv.A.nnz for lv in ml.levels]
+    assert ml.operator_complexity() == pytest.approx(sum(nnz) / nnz[0])
+    assert ml.grid_complexity() == pytest.approx(sum(lv.A.shape[0] for lv in ml.levels) / ml.levels[0].A.shape[0])
+    assert ml.cycle_complexity("W") >= ml.cycle_complexity("F") >= ml.cycle_complexity("V")
+    with pytest.raises(TypeError):
+        ml.cycle_complexity("Z")
