@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- V-cycles/s of the B200 AMG solve-phase engine on BASELINE.json's headline config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid G]
+
+Workload (config.workload): BASELINE.json configs[2] -- gallery.poisson((256,256,256)) 7-pt fp64,
+ruge_stuben_solver hierarchy (classical strength 0.25, RS splitting, classical interpolation),
+multi-colour Gauss-Seidel (symmetric, gauss_seidel_indexed over colour-sorted rows) pre and post,
+'pinv' coarse solve; rhs = default_rng(20260922).random(n), x0 = 0.  The reference package is not
+installed on the GPU box, so the hierarchy is built by this repo's host-side setup
+(pyamg_b200.classical, validated to reproduce the reference's hierarchies: tests/test_setup.py).
+
+A "step" is one V-cycle plus the per-cycle residual-norm check, exactly what one iteration of the
+reference's MultilevelSolver.solve does (pyamg/multilevel.py:558-582).
+  value    : V-cycles/s with b, x resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e      : V-cycles/s through the C-ABI amgb_solve with pinned HOST b/x, one cycle per call (the
+             aspreconditioner() pattern): H2D b + x0 and D2H x inside the timed region every step
+  roofline : the dominant kernel class of the cycle, algorithmic bytes / CUDA-event time, vs
+             MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference : the reference's compiled relaxation.h (oracle/_ref) + SciPy
+             matvecs driven by the oracle's restatement of __solve, 1 host core (the reference is
+             single-threaded and holds the GIL), same hierarchy
+Inputs are far larger than L2 (level-0 operator alone is 1.4 GB), so no explicit L2 flush is needed.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+SEED = 20260922
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def peak_hbm():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def build_hierarchy(grid, stream=None, device=0):
+    """poisson(grid) + RS hierarchy + multi-colour symmetric GS on every level (BASELINE configs[2])."""
+    from pyamg_b200.gallery import poisson
+    from pyamg_b200.classical import ruge_stuben_solver
+    t0 = time.time()
+    A = poisson(grid)
+    t1 = time.time()
+    sm = ("gauss_seidel_indexed", {"sweep": "symmetric"})
+    np.random.seed(SEED)
+    ml = ruge_stuben_solver(A, presmoother=sm, postsmoother=sm, device=device, stream=stream)
+    t2 = time.time()
+    log(f"gallery {t1 - t0:.1f}s, setup {t2 - t1:.1f}s, levels {[lv.A.shape[0] for lv in ml.levels]}, "
+        f"op-cx {ml.operator_complexity():.3f}")
+    return ml
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                for ln in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in ln.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_cycles_per_s(ml, b, ncyc, kernels):
+    """The reference's CPU path (compiled relaxation.h + SciPy matvec, or the C port) on this host."""
+    import oracle
+    cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A),
+                       kernels=kernels)
+    cyc.solve(b, tol=0, maxiter=1)                     # touch everything once
+    t0 = time.perf_counter()
+    cyc.solve(b, tol=0, maxiter=ncyc)
+    dt = time.perf_counter() - t0
+    return ncyc / dt, dt
+
+
+def run_reference(args, grid):
+    """--impl reference: the reference's own CPU implementation of the path, rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import oracle
+    ml = build_hierarchy(grid)
+    n = ml.levels[0].A.shape[0]
+    b = np.random.default_rng(SEED).random(n)
+    kernels = "ref" if oracle.have_ref() else "oracle"
+    cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A),
+                       kernels=kernels)
+    x = np.zeros(n)
+    for _ in range(args.warmup):
+        x = cyc.solve(b, x0=x, tol=0, maxiter=1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        x = cyc.solve(b, x0=x, tol=0, maxiter=1)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    kind = "reference" if kernels == "ref" else "port"
+    print(json.dumps({
+        "impl": "reference", "metric": "V-cycles/sec", "value": v, "unit": "V-cycles/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(grid, ml, 1),
+        "cpu_baseline": {"value": v, "unit": "V-cycles/s", "cores": 1, "kind": kind,
+                         "sample": f"{args.steps} x (1 V-cycle + residual check) on the full hierarchy; "
+                                   f"host has {os.cpu_count()} cores, the reference path is single-threaded"},
+        "e2e": {"value": v, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_config(grid, ml, ngpus):
+    return {"workload": f"gallery.poisson({tuple(grid)}) 7-pt fp64 CSR, ruge_stuben_solver hierarchy "
+                        f"({len(ml.levels)} levels, op-cx {ml.operator_complexity():.3f}), symmetric multi-colour "
+                        "Gauss-Seidel pre+post (gauss_seidel_indexed over colour-sorted rows), pinv coarse solve, "
+                        "V(1,1)-cycle + per-cycle residual check",
+            "n": int(ml.levels[0].A.shape[0]), "nnz": int(ml.levels[0].A.nnz),
+            "sum_nnz_A": int(sum(lv.A.nnz for lv in ml.levels)),
+            "parallelism": "1 GPU" if ngpus == 1 else f"{ngpus} independent replicas (one per GPU)",
+            "l2": "inputs larger than L2 (level-0 operator 1.4 GB); no flush needed"}
+
+
+OPS = {0: "spmv(restrict)", 1: "residual", 2: "prolong+add", 3: "jacobi", 4: "gs_wave", 5: "block_jacobi"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=256, help="grid points per dimension (3-D)")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="V-cycles timed for cpu_baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    grid = (args.grid,) * 3
+
+    if args.impl == "reference":
+        run_reference(args, grid)
+        return
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from pyamg_b200 import _engine as E
+
+    stream = torch.cuda.current_stream().cuda_stream
+    ml = build_hierarchy(grid, stream=stream, device=local)
+    n = ml.levels[0].A.shape[0]
+    t0 = time.time()
+    dev_bytes = ml.upload()
+    log(f"upload + wave scheduling {time.time() - t0:.1f}s, {dev_bytes / 1e9:.2f} GB in HBM")
+    L, h = E.lib(), ml.handle
+    b_host = E.pinned_empty(n)
+    x_host = E.pinned_empty(n)
+    b_host[:] = np.random.default_rng(SEED).random(n)
+    dev = torch.device("cuda", local)
+    b = torch.from_numpy(b_host).to(dev)
+    x = torch.zeros(n, dtype=torch.float64, device=dev)
+    norms = torch.zeros(args.steps + args.warmup + 2, dtype=torch.float64, device=dev)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def cycles(k):
+        E.check(L.amgb_solve_device(h, P(b), P(x), k, 0, 1, P(norms)))
+
+    # ---- device-resident throughput -------------------------------------------------------
+    cycles(args.warmup)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    cycles(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = ml.last_launches()
+    res = np.sqrt(norms[:args.steps + 1].cpu().numpy())
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+
+    # ---- end to end through the C ABI with host buffers (one cycle per call) ---------------
+    nres, info = ctypes.c_int32(0), ctypes.c_int32(0)
+    rbuf = np.empty(4)
+    x_host[:] = 0.0
+
+    def e2e_step():
+        E.check(L.amgb_solve(h, b_host.ctypes.data, x_host.ctypes.data, 0.0, 1, 0, 1, E.f64p(rbuf),
+                             ctypes.byref(nres), ctypes.byref(info)))
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    clocks = sampler.summary()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+
+    # ---- per-kernel roofline: CUDA events around every launch of one cycle ----------------
+    peak, peak_src = peak_hbm()
+    ml.profile_cycle()                                   # warm
+    recs = np.concatenate([ml.profile_cycle() for _ in range(3)])
+    groups = {}
+    for lvl, op, rows, nnz, nbytes, t in recs:
+        g = groups.setdefault((int(lvl), int(op)), [0.0, 0.0, 0])
+        g[0] += nbytes; g[1] += t; g[2] += 1
+    total_ms = sum(g[1] for g in groups.values())
+    table = sorted(((k, g) for k, g in groups.items()), key=lambda kv: -kv[1][1])
+    kernels = [{"level": k[0], "op": OPS[k[1]], "launches_per_cycle": g[2] // 3, "ms_per_cycle": round(g[1] / 3, 4),
+                "share": round(g[1] / total_ms, 3), "GBps": round(g[0] / g[1] / 1e6, 1),
+                "frac": round(g[0] / g[1] / 1e6 / peak, 3)} for k, g in table[:8]]
+    (dk, dg) = table[0]
+    roofline = {"bound": "hbm", "achieved": dg[0] / dg[1] / 1e6, "peak": peak, "unit": "GB/s",
+                "frac": dg[0] / dg[1] / 1e6 / peak, "traffic": None,
+                "kernel": f"level {dk[0]} {OPS[dk[1]]} (csr_rows_kernel)", "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                "bytes_per_launch": dg[0] / dg[2], "ms_per_launch": dg[1] / dg[2]}
+
+    # ---- fine-level kernels in isolation (metric: fine-level SpMV GB/s vs roofline) --------
+    A0 = ml.levels[0].A
+    Ap = torch.from_numpy(np.ascontiguousarray(A0.indptr, dtype=np.int32)).to(dev)
+    Aj = torch.from_numpy(np.ascontiguousarray(A0.indices, dtype=np.int32)).to(dev)
+    Ax = torch.from_numpy(np.ascontiguousarray(A0.data)).to(dev)
+    y, r = torch.empty_like(x), torch.empty_like(x)
+    st = ctypes.c_void_p(stream)
+
+    def tkern(fn, reps=10):
+        for _ in range(3):
+            fn()
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        c.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(c) / reps
+
+    nnz0 = A0.nnz
+    t_spmv = tkern(lambda: E.check(L.amgb_dev_csr_spmv(n, P(Ap), P(Aj), P(Ax), P(b), P(y), 0, st)))
+    t_jac = tkern(lambda: E.check(L.amgb_dev_csr_jacobi(n, P(Ap), P(Aj), P(Ax), P(b), P(x), P(y), P(r), 0.8, 0, st)))
+    by_spmv = 12 * nnz0 + 4 * (n + 1) + 16 * n
+    by_jac = 12 * nnz0 + 4 * (n + 1) + 32 * n
+    fine = {"spmv_ms": t_spmv, "spmv_GBps": by_spmv / t_spmv / 1e6, "spmv_frac": by_spmv / t_spmv / 1e6 / peak,
+            "jacobi_residual_fused_ms": t_jac, "jacobi_residual_fused_GBps": by_jac / t_jac / 1e6,
+            "jacobi_residual_fused_frac": by_jac / t_jac / 1e6 / peak}
+
+    # ---- CPU baseline: the reference's path on this box's host cores (bounded sample) ------
+    import oracle
+    kern = "ref" if oracle.have_ref() else "oracle"
+    cpu_v, cpu_dt = cpu_cycles_per_s(ml, b_host.copy(), args.cpu_sample, kern)
+    cpu = {"value": cpu_v, "unit": "V-cycles/s", "cores": 1, "kind": "reference" if kern == "ref" else "port",
+           "sample": f"{args.cpu_sample} V-cycles (+ residual checks) on the same hierarchy and rhs, {cpu_dt:.1f}s; "
+                     f"compiled reference relaxation.h + SciPy matvec, single-threaded by construction; "
+                     f"host has {os.cpu_count()} cores"}
+
+    value = world * args.steps / (ms * 1e-3)
+    out = {
+        "metric": "V-cycles/sec", "value": value, "unit": "V-cycles/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(grid, ml, world),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": world * args.steps / e2e_dt, "unit": "V-cycles/s", "h2d_bytes_per_step": 16 * n,
+                "d2h_bytes_per_step": 8 * n + 16,
+                "path": "C ABI amgb_solve(b_host, x_host, maxiter=1) per step, pinned host buffers"},
+        "gpu_launches": int(launches), "clocks": clocks, "fine_level": fine, "kernels": kernels,
+        "residual_reduction_per_cycle": float((res[-1] / res[0]) ** (1.0 / max(len(res) - 1, 1))),
+        "hbm_bytes": int(dev_bytes),
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+
+
+if __name__ == "__main__":
+    main()

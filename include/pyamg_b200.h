@@ -124,6 +124,11 @@ int amgb_hierarchy_num_levels(const amgb_hierarchy *h);
 int64_t amgb_hierarchy_device_bytes(const amgb_hierarchy *h);
 /* kernels launched by the most recent amgb_solve / amgb_solve_device call */
 int64_t amgb_hierarchy_last_launches(const amgb_hierarchy *h);
+/* One un-graphed cycle with a CUDA-event pair around every operator launch (measurement aid).
+ * rec[6k..6k+5] = level, op (0 spmv, 1 residual, 2 prolong+add, 3 jacobi, 4 gs wave, 5 block jacobi),
+ * rows, nnz, algorithmic bytes (SURVEY.md 8(d) formulas), milliseconds. */
+int amgb_profile_cycle(amgb_hierarchy *h, int32_t cycle, double *rec, int32_t max_records,
+                       int32_t *n_records);
 /* pinned host buffers for the e2e path (cudaHostAlloc / cudaFreeHost) */
 int amgb_host_alloc(size_t bytes, void **out);
 int amgb_host_free(void *p);

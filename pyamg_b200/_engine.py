@@ -47,7 +47,7 @@ SYMBOLS = [
     "amgb_hierarchy_create", "amgb_hierarchy_destroy", "amgb_hierarchy_add_level",
     "amgb_hierarchy_set_coarse_pinv", "amgb_hierarchy_finalize", "amgb_solve",
     "amgb_solve_device", "amgb_hierarchy_num_levels", "amgb_hierarchy_device_bytes",
-    "amgb_hierarchy_last_launches", "amgb_host_alloc", "amgb_host_free",
+    "amgb_hierarchy_last_launches", "amgb_profile_cycle", "amgb_host_alloc", "amgb_host_free",
     "amgb_host_jacobi", "amgb_host_gauss_seidel", "amgb_host_sor_gauss_seidel",
     "amgb_host_gauss_seidel_indexed",
     "amgb_host_bsr_jacobi", "amgb_host_block_jacobi", "amgb_host_matvec",
@@ -84,6 +84,7 @@ def lib():
     L.amgb_hierarchy_num_levels.argtypes = [vp]
     L.amgb_hierarchy_device_bytes.argtypes = [vp]
     L.amgb_hierarchy_last_launches.argtypes = [vp]
+    L.amgb_profile_cycle.argtypes = [vp, i32, c_f64p, i32, c_i32p]
     L.amgb_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     L.amgb_host_free.argtypes = [vp]
     ci = ctypes.c_int

@@ -144,6 +144,7 @@ struct DevCsr {
 struct WaveSchedule {       // a sequential sweep over a row list, regrouped into dependency waves
     int *rows = nullptr;    // device, wave-major
     std::vector<long long> ptr;   // wave w = rows[ptr[w] .. ptr[w+1])
+    std::vector<long long> nnz;   // stored entries of the rows of wave w (roofline accounting)
     bool natural_single = false;  // one wave covering rows 0..n-1 in order -> contiguous launch
 };
 
@@ -155,6 +156,13 @@ struct Smoother {
     double omega = 1.0;
     WaveSchedule ws;
     double *Dinv = nullptr;
+};
+
+struct ProfRec {               // one launch of a profiled cycle (amgb_profile_cycle)
+    int level, op, lanes;
+    long long rows, nnz;
+    double bytes;
+    cudaEvent_t e0, e1;
 };
 
 struct Level {
@@ -291,6 +299,9 @@ struct amgb_hierarchy {
     cudaGraphExec_t graph[3] = {nullptr, nullptr, nullptr};
     int graph_cpl[3] = {0, 0, 0};
     long long graph_nodes[3] = {0, 0, 0};
+    bool profiling = false;
+    int cur_level = 0;
+    std::vector<ProfRec> prof;
     long long launches = 0;        // kernels issued by the current (or captured) sequence
     long long last_launches = 0;
     bool use_graph = true;
@@ -351,6 +362,10 @@ struct amgb_hierarchy {
             std::vector<int> rows;
             build_waves(A, in->indices, m, rows, s.ws.ptr);
             RET(upload(&s.ws.rows, rows.data(), m));
+            s.ws.nnz.assign(s.ws.ptr.size() - 1, 0);
+            for (size_t w = 0; w + 1 < s.ws.ptr.size(); w++)
+                for (long long k = s.ws.ptr[w]; k < s.ws.ptr[w + 1]; k++)
+                    s.ws.nnz[w] += A.Ap[(size_t)rows[(size_t)k] + 1] - A.Ap[(size_t)rows[(size_t)k]];
             return AMGB_OK;
         }
         case AMGB_SM_BLOCK_JACOBI: {
@@ -365,6 +380,25 @@ struct amgb_hierarchy {
         return fail(AMGB_ENOTIMPL, "smoother kind outside the hot-path scope");
     }
 
+    // ---- per-launch timing (profile mode only; never inside a graph capture) ----
+    int prof_begin(int op, int lanes, long long rows, long long nnz, double bytes)
+    {
+        if (!profiling) return AMGB_OK;
+        ProfRec r;
+        r.level = cur_level; r.op = op; r.lanes = lanes; r.rows = rows; r.nnz = nnz; r.bytes = bytes;
+        CK(cudaEventCreate(&r.e0));
+        CK(cudaEventCreate(&r.e1));
+        CK(cudaEventRecord(r.e0, stream));
+        prof.push_back(r);
+        return AMGB_OK;
+    }
+    int prof_end()
+    {
+        if (!profiling) return AMGB_OK;
+        CK(cudaEventRecord(prof.back().e1, stream));
+        return AMGB_OK;
+    }
+
     // ---- launch sequence pieces (all on `stream`) ----
     int spmv(int op, const DevCsr &M, const double *x, const double *b, double *y, double omega = 0.0,
              double *r = nullptr, double *parts = nullptr)
@@ -374,7 +408,14 @@ struct amgb_hierarchy {
         a.Ap = M.Ap; a.Aj = M.Aj; a.Ax = M.Ax;
         a.x = x; a.b = b; a.y = y; a.r = r; a.omega = omega; a.partials = parts;
         launches += (a.n > 0);
-        return launch_csr(op, M.lanes, a, stream);
+        // algorithmic bytes: 12 nnz + 4 (n+1) + 8 per vector pass
+        const double vec = (op == OP_SPMV) ? 8.0 * M.n_cols + 8.0 * M.n_rows
+                         : (op == OP_PADD) ? 8.0 * M.n_cols + 16.0 * M.n_rows
+                         : (op == OP_RESID) ? 24.0 * M.n_rows
+                         : (24.0 + (r ? 8.0 : 0.0)) * M.n_rows;
+        RET(prof_begin(op, M.lanes, M.n_rows, M.nnz, 12.0 * M.nnz + 4.0 * (M.n_rows + 1) + vec));
+        RET(launch_csr(op, M.lanes, a, stream));
+        return prof_end();
     }
 
     int gs_wave(const DevCsr &A, const WaveSchedule &ws, long long w, double *x, const double *b, double omega)
@@ -385,7 +426,10 @@ struct amgb_hierarchy {
         a.Ap = A.Ap; a.Aj = A.Aj; a.Ax = A.Ax;
         a.x = x; a.b = b; a.y = x; a.r = nullptr; a.omega = omega; a.partials = nullptr;
         launches += (a.n > 0);
-        return launch_csr(OP_GS, A.lanes, a, stream);
+        // one wave of a sweep: its share of 12 nnz + 4 (n+1) + 4 n (row list) + 24 n
+        RET(prof_begin(OP_GS, A.lanes, a.n, ws.nnz[(size_t)w], 12.0 * ws.nnz[(size_t)w] + 36.0 * a.n));
+        RET(launch_csr(OP_GS, A.lanes, a, stream));
+        return prof_end();
     }
 
     int block_jacobi(Level &L, const Smoother &s);   // defined below (needs its kernel)
@@ -445,6 +489,7 @@ struct amgb_hierarchy {
     {
         Level &L = levels[(size_t)lvl];
         Level &C = levels[(size_t)lvl + 1];
+        cur_level = lvl;
         RET(smooth(L, L.pre));                                          // :610
         RET(spmv(OP_RESID, L.A, L.x, L.b, L.r));                        // :612
         RET(spmv(OP_SPMV, L.R, L.r, nullptr, C.b));                     // :614
@@ -464,6 +509,7 @@ struct amgb_hierarchy {
                 return fail(AMGB_EINVAL, "Unrecognized cycle type");    // :658 (TypeError)
             }
         }
+        cur_level = lvl;
         RET(spmv(OP_PADD, L.P, C.x, nullptr, L.x));                     // :660
         RET(smooth(L, L.post));                                         // :662
         if (L.x != L.x_home) {   // odd number of Jacobi ping-pongs: bring the iterate home
@@ -608,7 +654,10 @@ int amgb_hierarchy::block_jacobi(Level &L, const Smoother &s)
 {
     const int nb = L.A.n_rows / s.bs;
     for (int it = 0; it < s.iterations; it++) {
+        RET(prof_begin(5, L.A.lanes, L.A.n_rows, L.A.nnz,
+                       12.0 * L.A.nnz + 4.0 * (L.A.n_rows + 1) + (24.0 + 8.0 * s.bs) * L.A.n_rows));
         RET(dispatch_block_jacobi(s.bs, L.A.lanes, nb, L.A, L.x, L.b, s.Dinv, L.xalt, s.omega, stream));
+        RET(prof_end());
         launches++;
         std::swap(L.x, L.xalt);
     }
@@ -836,6 +885,39 @@ extern "C" int amgb_solve_device(amgb_hierarchy *h, const double *b_dev, double 
         CK(cudaMemcpyAsync(norms2_dev, h->norms2, sizeof(double) * ((size_t)ncycles + 1),
                            cudaMemcpyDeviceToDevice, s));
     h->last_launches = h->launches;
+    return AMGB_OK;
+}
+
+// One un-graphed cycle with a CUDA-event pair around every operator launch of the cycle.
+// rec[k*6 + {0..5}] = level, op (0 spmv/R, 1 residual, 2 prolong+add, 3 jacobi, 4 gs wave, 5 block jacobi),
+// rows, nnz, algorithmic bytes, milliseconds.  Returns the number of records (<= max_records).
+extern "C" int amgb_profile_cycle(amgb_hierarchy *h, int32_t cycle, double *rec, int32_t max_records,
+                                  int32_t *n_records)
+{
+    RET(check_cycle_args(h, cycle, 1));
+    if (rec == nullptr || n_records == nullptr) return fail(AMGB_EINVAL, "null output");
+    if (h->levels.size() < 2) { *n_records = 0; return AMGB_OK; }
+    CK(cudaSetDevice(h->device));
+    h->prof.clear();
+    h->profiling = true;
+    int rc = h->cycle(0, cycle, 1);
+    h->profiling = false;
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    int n = 0;
+    for (ProfRec &r : h->prof) {
+        float ms = 0.f;
+        if (rc == AMGB_OK && e == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && n < max_records) {
+            double *o = rec + (size_t)n * 6;
+            o[0] = r.level; o[1] = r.op; o[2] = (double)r.rows; o[3] = (double)r.nnz; o[4] = r.bytes; o[5] = ms;
+            n++;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    h->prof.clear();
+    *n_records = n;
+    if (rc != AMGB_OK) return rc;
+    if (e != cudaSuccess) return fail(AMGB_ECUDA, std::string("profile sync: ") + cudaGetErrorString(e));
     return AMGB_OK;
 }
 

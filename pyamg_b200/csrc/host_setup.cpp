@@ -278,4 +278,16 @@ int32_t amgb_setup_greedy_coloring(int32_t n, const int32_t *Ap, const int32_t *
     return ncol;
 }
 
+// 1 if no stored off-diagonal entry joins two rows of equal colour (checks a colouring computed on a
+// pattern assumed symmetric), else 0.
+int32_t amgb_setup_coloring_is_valid(int32_t n, const int32_t *Ap, const int32_t *Aj, const int32_t *colors)
+{
+    for (int32_t i = 0; i < n; i++)
+        for (int32_t jj = Ap[i]; jj < Ap[i + 1]; jj++) {
+            const int32_t j = Aj[jj];
+            if (j != i && j >= 0 && j < n && colors[j] == colors[i]) return 0;
+        }
+    return 1;
+}
+
 }  // extern "C"

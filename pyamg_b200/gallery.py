@@ -24,24 +24,35 @@ def stencil_grid(S, grid, dtype=np.float64, format="csr"):
         raise ValueError("grid dimensions must be positive")
     N = int(np.prod(grid))
     strides = np.cumprod((1,) + grid[::-1])[:-1][::-1]          # last dimension fastest
-    coords = np.indices(grid, dtype=np.int64).reshape(len(grid), -1)
-    rows_all = np.arange(N, dtype=np.int64)
-    rows, cols, vals = [], [], []
-    for idx in zip(*np.nonzero(S)):
-        off = [i - s // 2 for i, s in zip(idx, S.shape)]
-        ok = np.ones(N, dtype=bool)
-        for d, o in enumerate(off):
-            c = coords[d] + o
-            ok &= (c >= 0) & (c < grid[d])
-        shift = int(sum(o * st for o, st in zip(off, strides)))
-        r = rows_all[ok]
-        rows.append(r)
-        cols.append(r + shift)
-        vals.append(np.full(r.shape, S[idx], dtype=dtype))
-    A = sparse.coo_array((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(N, N))
-    A = A.tocsr()          # sums duplicates, sorts column indices
-    A.indptr = A.indptr.astype(np.int32)
-    A.indices = A.indices.astype(np.int32)
+    offs = [tuple(i - s // 2 for i, s in zip(idx, S.shape)) for idx in zip(*np.nonzero(S))]
+    vals = [S[idx] for idx in zip(*np.nonzero(S))]
+    shifts = [int(sum(o * st for o, st in zip(off, strides))) for off in offs]
+    order = np.argsort(shifts, kind="stable")
+    offs = [offs[k] for k in order]
+    vals = np.array([vals[k] for k in order], dtype=dtype)
+    shifts = np.array([shifts[k] for k in order], dtype=np.int64)
+    # per-dimension validity of every offset (Dirichlet cut-off), combined by broadcasting
+    ns = len(offs)
+    valid = np.ones((N, ns), dtype=bool)
+    for d, g in enumerate(grid):
+        c = np.arange(g, dtype=np.int64)
+        ok_d = np.stack([(c + off[d] >= 0) & (c + off[d] < g) for off in offs], axis=1)      # (g, ns)
+        shape = [1] * len(grid) + [ns]
+        shape[d] = g
+        valid &= np.broadcast_to(ok_d.reshape(shape), grid + (ns,)).reshape(N, ns)
+    if len(set(shifts.tolist())) == ns and N < 2**31 - 1:
+        # fast path: offsets sorted by shift == columns ascending inside every row -> CSR directly
+        indptr = np.zeros(N + 1, dtype=np.int64)
+        np.cumsum(valid.sum(axis=1), out=indptr[1:])
+        cols = (np.arange(N, dtype=np.int32)[:, None] + shifts.astype(np.int32)[None, :])[valid]
+        data = np.broadcast_to(vals[None, :], (N, ns))[valid]
+        A = sparse.csr_array((data, cols, indptr.astype(np.int32)), shape=(N, N))
+    else:
+        # degenerate grids (a dimension shorter than the stencil) alias offsets: sum duplicates
+        r, k = np.nonzero(valid)
+        A = sparse.coo_array((vals[k], (r, r + shifts[k])), shape=(N, N)).tocsr()
+        A.indptr = A.indptr.astype(np.int32)
+        A.indices = A.indices.astype(np.int32)
     return A.asformat(format)
 
 

@@ -20,14 +20,18 @@ def vertex_coloring(G, method="greedy"):
     G = sparse.csr_array(G)
     if G.shape[0] != G.shape[1]:
         raise ValueError("expected square matrix")
-    # symmetrise the pattern so the colouring is valid for structurally non-symmetric operators too
-    if (abs(G) != abs(G).T).nnz != 0:
-        G = (abs(G) + abs(G).T).tocsr()
     n = G.shape[0]
-    Ap = np.ascontiguousarray(G.indptr, dtype=np.int32)
-    Aj = np.ascontiguousarray(G.indices, dtype=np.int32)
-    colors = np.empty(n, dtype=np.int32)
-    H.lib().amgb_setup_greedy_coloring(n, H.ip(Ap), H.ip(Aj), H.ip(colors))
+
+    def run(M):
+        Ap = np.ascontiguousarray(M.indptr, dtype=np.int32)
+        Aj = np.ascontiguousarray(M.indices, dtype=np.int32)
+        colors = np.empty(n, dtype=np.int32)
+        H.lib().amgb_setup_greedy_coloring(n, H.ip(Ap), H.ip(Aj), H.ip(colors))
+        return colors, bool(H.lib().amgb_setup_coloring_is_valid(n, H.ip(Ap), H.ip(Aj), H.ip(colors)))
+
+    colors, ok = run(G)
+    if not ok:     # structurally non-symmetric operator: colour the symmetrised pattern instead
+        colors, ok = run((abs(G) + abs(G).T).tocsr())
     return colors
 
 

@@ -175,6 +175,17 @@ class MultilevelSolver:
         """CUDA kernels launched by the most recent solve (graph nodes counted individually)."""
         return int(E.lib().amgb_hierarchy_last_launches(self._h)) if self._h is not None else 0
 
+    def profile_cycle(self, cycle="V", max_records=200000):
+        """Time every operator launch of one (un-graphed) cycle with CUDA events.
+
+        Returns a float array (n, 6): level, op (0 spmv/restrict, 1 residual, 2 prolong+add, 3 jacobi,
+        4 gs wave, 5 block jacobi), rows, nnz, algorithmic bytes, milliseconds."""
+        rec = np.empty(max_records * 6, dtype=np.float64)
+        nrec = ctypes.c_int32(0)
+        E.check(E.lib().amgb_profile_cycle(self.handle, E.CYCLES[str(cycle).upper()], E.f64p(rec),
+                                           int(max_records), ctypes.byref(nrec)))
+        return rec[:nrec.value * 6].reshape(-1, 6).copy()
+
     # ------------------------------------------------------------------ reporting (host only)
     def __repr__(self):
         """Basic statistics of the hierarchy (multilevel.py:184-209)."""

@@ -1,0 +1,61 @@
+"""CPU tests of the host-side setup (pyamg_b200.classical / gallery / graph): the hierarchies it
+builds coincide with the ones the REAL reference built (golden fixtures), so bench inputs generated
+on the GPU box are the BASELINE configs' hierarchies."""
+import numpy as np
+import pytest
+
+from pyamg_b200.classical import ruge_stuben_solver
+from pyamg_b200.gallery import poisson, stencil_grid, diffusion_stencil_2d
+from pyamg_b200.graph import vertex_coloring, color_order
+
+CASES = [("cfg1_rs_gs_poisson2d", (30, 30), {}), ("cfg3_rs_mcgs_poisson3d", (12, 12, 12), {}),
+         ("cfg6_rs_gsfwd_none_poisson3d", (9, 9, 9), {"max_coarse": 5})]
+
+
+@pytest.mark.parametrize("name,grid,kw", CASES)
+def test_rs_setup_reproduces_reference_hierarchy(name, grid, kw, load_golden):
+    ref, _ = load_golden(name)
+    ml = ruge_stuben_solver(poisson(grid), presmoother=None, postsmoother=None, **kw)
+    assert [lv.A.shape for lv in ml.levels] == [lv.A.shape for lv in ref.levels]
+    for a, b in zip(ml.levels, ref.levels):
+        assert abs(a.A - b.A).max() < 1e-12
+        if hasattr(b, "P"):
+            assert a.P.shape == b.P.shape and abs(a.P - b.P).max() < 1e-13
+            assert abs(a.R - b.R).max() < 1e-13
+    assert ml.operator_complexity() == pytest.approx(ref.operator_complexity(), rel=1e-12)
+
+
+def test_gallery_matches_reference_operators(load_golden):
+    ref, _ = load_golden("cfg4_sa_jacobi_aniso2d")
+    A = stencil_grid(diffusion_stencil_2d(epsilon=0.001, theta=np.pi / 6, type="FE"), (48, 48))
+    assert abs(A - ref.levels[0].A).max() < 1e-15
+    ref, _ = load_golden("cfg2_sa_jacobi_poisson2d")
+    assert abs(poisson((40, 40)) - ref.levels[0].A).max() == 0
+    P = poisson((2, 3)).toarray()           # pyamg/gallery/laplacian.py docstring example
+    assert np.array_equal(P[0], [4, -1, 0, -1, 0, 0]) and np.array_equal(P[4], [0, -1, 0, -1, 4, -1])
+    with pytest.raises(ValueError):
+        stencil_grid(np.ones((2, 2)), (4, 4))
+
+
+@pytest.mark.parametrize("grid", [(17,), (9, 11), (6, 5, 7)])
+def test_greedy_coloring_is_valid_and_red_black_on_stencils(grid):
+    """pyamg/tests/test_graph.py:41-47 criterion: no edge joins equal colours; all colours used."""
+    A = poisson(grid)
+    c = vertex_coloring(A)
+    coo = A.tocoo()
+    off = coo.row != coo.col
+    assert np.all(c[coo.row[off]] != c[coo.col[off]])
+    assert set(c.tolist()) == set(range(c.max() + 1))
+    assert c.max() + 1 == 2
+    order = color_order(c)
+    assert sorted(order.tolist()) == list(range(A.shape[0])) and np.all(np.diff(c[order]) >= 0)
+
+
+def test_setup_rejects_options_outside_its_scope():
+    A = poisson((8, 8))
+    with pytest.raises(NotImplementedError):
+        ruge_stuben_solver(A, strength="symmetric")
+    with pytest.raises(NotImplementedError):
+        ruge_stuben_solver(A, CF="PMIS")
+    with pytest.raises(NotImplementedError):
+        ruge_stuben_solver(A, interpolation="direct")
