@@ -64,6 +64,8 @@ def build_extension(force=False, verbose=False):
         raise RuntimeError("nvcc not found and libpyamg_b200.so is not built")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + SOURCES
+    if os.environ.get("AMGB_PTXAS_V"):
+        cmd.insert(1, "-Xptxas=-v")
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)

@@ -14,6 +14,7 @@
 // each instead of a Python round trip.  No CPU fallback anywhere.
 #include "../../include/pyamg_b200.h"
 #include "csr_kernels.cuh"
+#include "tile_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -125,7 +126,62 @@ static int launch_fill(double *x, long long n, double v, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------
-// device containers
+// tile-kernel launch
+// ------------------------------------------------------------------------------------------
+static int g_tile_ctas_per_sm = 2;
+static int g_num_sms = 148;
+
+template <int OP>
+static int launch_tile_op(int G, const TileArgs &a, int grid, cudaStream_t s)
+{
+    const dim3 g((unsigned)grid), b(kTileWarps * 32);
+#define AMGB_TILE_CASE(GG)                                                                              \
+    case GG: {                                                                                          \
+        static bool attr_done = false;                                                                  \
+        if (!attr_done) {                                                                               \
+            CK(cudaFuncSetAttribute(csr_tile_kernel<GG, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)kTileSmemBytes));                                              \
+            attr_done = true;                                                                           \
+        }                                                                                               \
+        csr_tile_kernel<GG, OP><<<g, b, kTileSmemBytes, s>>>(a);                                        \
+        break;                                                                                          \
+    }
+    switch (G) {
+        AMGB_TILE_CASE(1)
+        AMGB_TILE_CASE(2)
+        AMGB_TILE_CASE(4)
+        AMGB_TILE_CASE(8)
+        AMGB_TILE_CASE(16)
+        AMGB_TILE_CASE(32)
+    default: return fail(AMGB_EINVAL, "tile kernel: G must be a power of two in 1..32");
+    }
+#undef AMGB_TILE_CASE
+    CK(cudaGetLastError());
+    return AMGB_OK;
+}
+
+static int launch_tile(int op, int G, const TileArgs &a, int grid, cudaStream_t s)
+{
+    if (a.tile_end <= a.tile_begin) return AMGB_OK;
+    switch (op) {
+    case OP_SPMV: return launch_tile_op<OP_SPMV>(G, a, grid, s);
+    case OP_RESID: return launch_tile_op<OP_RESID>(G, a, grid, s);
+    case OP_PADD: return launch_tile_op<OP_PADD>(G, a, grid, s);
+    case OP_JACOBI: return launch_tile_op<OP_JACOBI>(G, a, grid, s);
+    case OP_GS: return launch_tile_op<OP_GS>(G, a, grid, s);
+    }
+    return fail(AMGB_EINVAL, "unknown tile op");
+}
+
+static inline int tile_grid(int ntiles)
+{
+    const int full = g_num_sms * g_tile_ctas_per_sm;
+    const int need = (ntiles + kTileWarps - 1) / kTileWarps;
+    return std::max(1, std::min(full, need));
+}
+
+// ------------------------------------------------------------------------------------------
+// host / device containers
 // ------------------------------------------------------------------------------------------
 struct HostCsr {   // point CSR on the host (BSR already expanded)
     int n_rows = 0, n_cols = 0;
@@ -138,14 +194,27 @@ struct DevCsr {
     long long nnz = 0;
     int *Ap = nullptr, *Aj = nullptr;
     double *Ax = nullptr;
-    int lanes = 8;
+    int lanes = 8;               // rows kernel: lanes per row
+    // tile kernel
+    TileDesc *tiles = nullptr;   // n_tiles + 1
+    int n_tiles = 0;
+    int tile_G = 1;
 };
 
 struct WaveSchedule {       // a sequential sweep over a row list, regrouped into dependency waves
-    int *rows = nullptr;    // device, wave-major
+    int *rows = nullptr;    // device, wave-major (level numbering)
     std::vector<long long> ptr;   // wave w = rows[ptr[w] .. ptr[w+1])
     std::vector<long long> nnz;   // stored entries of the rows of wave w (roofline accounting)
-    bool natural_single = false;  // one wave covering rows 0..n-1 in order -> contiguous launch
+    bool contiguous = false;      // rows of wave w are exactly ptr[w] .. ptr[w+1]-1 (wave-major permuted level)
+    std::vector<int> tile_ptr;    // contiguous: tiles of wave w = [tile_ptr[w], tile_ptr[w+1])
+};
+
+struct SmootherSpec {       // host copy of an amgb_smoother
+    int kind = AMGB_SM_NONE, iterations = 1, sweep = 0, bs = 1;
+    double omega = 1.0;
+    bool has_list = false;
+    std::vector<int> list;
+    std::vector<double> Dinv;
 };
 
 struct Smoother {
@@ -163,6 +232,12 @@ struct ProfRec {               // one launch of a profiled cycle (amgb_profile_c
     long long rows, nnz;
     double bytes;
     cudaEvent_t e0, e1;
+};
+
+struct HostLevel {
+    HostCsr A, P, R;
+    bool has_pr = false;
+    SmootherSpec pre, post;
 };
 
 struct Level {
@@ -183,7 +258,7 @@ static int validate_matrix(const amgb_matrix *M, const char *name)
     const int nb = M->n_rows / M->block_r;
     if (M->indptr[0] != 0 || (long long)M->indptr[nb] != M->nnz_blocks)
         return fail(AMGB_EINVAL, std::string(name) + ": indptr inconsistent with nnz");
-    if (M->nnz_blocks * M->block_r * M->block_c > 2147483647LL)
+    if (M->nnz_blocks * M->block_r * M->block_c > 2147483647LL - 16)
         return fail(AMGB_EINVAL, std::string(name) + ": nnz exceeds int32 (reference index type)");
     return AMGB_OK;
 }
@@ -272,11 +347,88 @@ static void build_waves(const HostCsr &A, const int *list, long long m, std::vec
         std::sort(rows_sorted.begin() + ptr[(size_t)q], rows_sorted.begin() + ptr[(size_t)q + 1]);
 }
 
+// B = A[order, :][:, colpos]  (order: new row -> old row, or null; colpos: old col -> new col, or null);
+// the entry order inside a row is kept, so per-row summation order is unchanged.
+static void permute_csr(const HostCsr &A, const int *order, const int *colpos, HostCsr &B)
+{
+    B.n_rows = A.n_rows;
+    B.n_cols = A.n_cols;
+    B.Ap.resize(A.Ap.size());
+    B.Aj.resize(A.Aj.size());
+    B.Ax.resize(A.Ax.size());
+    long long pos = 0;
+    for (int i = 0; i < A.n_rows; i++) {
+        const int o = order ? order[i] : i;
+        B.Ap[(size_t)i] = (int)pos;
+        for (int jj = A.Ap[o]; jj < A.Ap[o + 1]; jj++) {
+            B.Aj[(size_t)pos] = colpos ? colpos[A.Aj[jj]] : A.Aj[jj];
+            B.Ax[(size_t)pos] = A.Ax[jj];
+            pos++;
+        }
+    }
+    B.Ap[(size_t)A.n_rows] = (int)pos;
+}
+
+static int pick_tile_G(long long nnz, long long n_rows)
+{
+    const char *env = getenv("AMGB_TILE_G");
+    if (env != nullptr) {
+        int v = atoi(env);
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) return v;
+    }
+    if (n_rows <= 0) return 1;
+    const double avg = (double)nnz / (double)n_rows;
+    int g = 1;
+    while (g < 32 && avg > 12.0 * g) g <<= 1;     // ~6-12 stored entries per lane
+    return g;
+}
+
+// whole rows, <= kTileNnz entries and <= kTileRows rows per tile, no tile across a `breaks` row
+// (sorted, e.g. Gauss-Seidel wave boundaries); a row longer than kTileNnz is a tile of its own.
+// Row counts are rounded down to a multiple of the rows reduced per pass (32/G) where possible.
+static void build_tiles(const HostCsr &A, int G, const std::vector<long long> *breaks,
+                        std::vector<TileDesc> &tiles, std::vector<int> *tile_ptr)
+{
+    const int n = A.n_rows, rpp = 32 / G;
+    tiles.clear();
+    if (tile_ptr) tile_ptr->assign(1, 0);
+    size_t bi = 1;                       // next break to honour: (*breaks)[bi]
+    int r = 0;
+    while (r < n) {
+        long long limit = n;
+        if (breaks) {
+            while (bi < breaks->size() && (*breaks)[bi] <= r) {
+                bi++;
+            }
+            if (bi < breaks->size()) limit = (*breaks)[bi];
+        }
+        int e = r;
+        long long nz = 0;
+        while (e < limit && e - r < kTileRows) {
+            const long long len = A.Ap[(size_t)e + 1] - A.Ap[(size_t)e];
+            if (nz + len > kTileNnz) break;
+            nz += len;
+            e++;
+        }
+        if (e == r) {
+            e = r + 1;                                   // a single long row
+        } else if (e < limit && e - r > rpp) {
+            e = r + ((e - r) / rpp) * rpp;               // full passes only
+        }
+        tiles.push_back(TileDesc{r, A.Ap[(size_t)r]});
+        r = e;
+        if (tile_ptr && breaks && bi < breaks->size() && r == (*breaks)[bi]) tile_ptr->push_back((int)tiles.size());
+    }
+    tiles.push_back(TileDesc{n, A.Ap[(size_t)n]});       // sentinel
+    if (tile_ptr && tile_ptr->back() != (int)tiles.size() - 1) tile_ptr->push_back((int)tiles.size() - 1);
+}
+
 // ------------------------------------------------------------------------------------------
 // the engine
 // ------------------------------------------------------------------------------------------
 struct amgb_hierarchy {
     int device = 0;
+    std::vector<HostLevel> host;      // until finalize
     std::vector<Level> levels;
     std::vector<void *> allocs;
     long long dev_bytes = 0;
@@ -284,10 +436,15 @@ struct amgb_hierarchy {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
 
+    std::vector<double> coarse_host;
     double *coarse_pinv = nullptr;
     int coarse_n = 0;
     bool coarse_zero = false;
     bool have_coarse = false;
+
+    // level-0 wave-major permutation (device): order0[new] = old, pos0[old] = new; null = identity
+    int *order0 = nullptr, *pos0 = nullptr;
+    double *io_tmp = nullptr;
 
     double *partials = nullptr;   // level-0 residual-norm partial sums
     long long n_partials = 0;
@@ -305,6 +462,8 @@ struct amgb_hierarchy {
     long long launches = 0;        // kernels issued by the current (or captured) sequence
     long long last_launches = 0;
     bool use_graph = true;
+    bool use_tiles = true;
+    bool use_permute = true;
 
     template <typename T>
     int dalloc(T **p, long long count)
@@ -320,64 +479,34 @@ struct amgb_hierarchy {
         return AMGB_OK;
     }
 
+    // `pad` extra elements are allocated (and zeroed) past the payload: the TMA reads whole 16-byte groups
     template <typename T>
-    int upload(T **p, const T *src, long long count)
+    int upload(T **p, const T *src, long long count, int pad = 0)
     {
-        RET(dalloc(p, count));
+        RET(dalloc(p, count + pad));
+        if (pad > 0) CK(cudaMemset((void *)(*p + count), 0, sizeof(T) * (size_t)pad));
         if (count > 0) CK(cudaMemcpy(*p, src, (size_t)count * sizeof(T), cudaMemcpyHostToDevice));
         return AMGB_OK;
     }
 
-    int upload_csr(const HostCsr &H, DevCsr &D)
+    int upload_csr(const HostCsr &H, DevCsr &D, const std::vector<long long> *breaks = nullptr,
+                   std::vector<int> *tile_ptr = nullptr)
     {
         D.n_rows = H.n_rows;
         D.n_cols = H.n_cols;
         D.nnz = (long long)H.Aj.size();
-        RET(upload(&D.Ap, H.Ap.data(), (long long)H.Ap.size()));
-        RET(upload(&D.Aj, H.Aj.data(), D.nnz));
-        RET(upload(&D.Ax, H.Ax.data(), D.nnz));
+        RET(upload(&D.Ap, H.Ap.data(), (long long)H.Ap.size(), 8));
+        RET(upload(&D.Aj, H.Aj.data(), D.nnz, 8));
+        RET(upload(&D.Ax, H.Ax.data(), D.nnz, 8));
         D.lanes = pick_lanes(D.nnz, D.n_rows);
+        if (use_tiles) {
+            D.tile_G = pick_tile_G(D.nnz, D.n_rows);
+            std::vector<TileDesc> tiles;
+            build_tiles(H, D.tile_G, breaks, tiles, tile_ptr);
+            D.n_tiles = (int)tiles.size() - 1;
+            RET(upload(&D.tiles, tiles.data(), (long long)tiles.size()));
+        }
         return AMGB_OK;
-    }
-
-    int setup_smoother(const amgb_smoother *in, const HostCsr &A, Smoother &s)
-    {
-        s = Smoother();
-        if (in == nullptr || in->kind == AMGB_SM_NONE) return AMGB_OK;
-        s.kind = in->kind;
-        s.iterations = in->iterations;
-        s.sweep = in->sweep;
-        s.omega = in->omega;
-        if (s.iterations < 0) return fail(AMGB_EINVAL, "smoother iterations < 0");
-        if (A.n_rows != A.n_cols) return fail(AMGB_EINVAL, "expected square matrix");   // relaxation.py:81-82
-        switch (in->kind) {
-        case AMGB_SM_JACOBI: return AMGB_OK;
-        case AMGB_SM_GAUSS_SEIDEL: {
-            if (s.sweep < 0 || s.sweep > 2)
-                return fail(AMGB_EINVAL, "valid sweep directions: \"forward\", \"backward\", and \"symmetric\"");
-            const long long m = in->indices ? in->n_indices : A.n_rows;
-            for (long long k = 0; in->indices && k < m; k++)
-                if (in->indices[k] < 0 || in->indices[k] >= A.n_rows)
-                    return fail(AMGB_EINVAL, "gauss_seidel_indexed: row index out of range");
-            std::vector<int> rows;
-            build_waves(A, in->indices, m, rows, s.ws.ptr);
-            RET(upload(&s.ws.rows, rows.data(), m));
-            s.ws.nnz.assign(s.ws.ptr.size() - 1, 0);
-            for (size_t w = 0; w + 1 < s.ws.ptr.size(); w++)
-                for (long long k = s.ws.ptr[w]; k < s.ws.ptr[w + 1]; k++)
-                    s.ws.nnz[w] += A.Ap[(size_t)rows[(size_t)k] + 1] - A.Ap[(size_t)rows[(size_t)k]];
-            return AMGB_OK;
-        }
-        case AMGB_SM_BLOCK_JACOBI: {
-            s.bs = in->blocksize;
-            if (s.bs < 1 || s.bs > 8 || A.n_rows % s.bs)
-                return fail(AMGB_ENOTIMPL, "block_jacobi: blocksize must be 1..8 and divide n");
-            if (in->Dinv == nullptr) return fail(AMGB_EINVAL, "block_jacobi: Dinv required");
-            RET(upload(&s.Dinv, in->Dinv, (long long)A.n_rows * s.bs));
-            return AMGB_OK;
-        }
-        }
-        return fail(AMGB_ENOTIMPL, "smoother kind outside the hot-path scope");
     }
 
     // ---- per-launch timing (profile mode only; never inside a graph capture) ----
@@ -403,32 +532,59 @@ struct amgb_hierarchy {
     int spmv(int op, const DevCsr &M, const double *x, const double *b, double *y, double omega = 0.0,
              double *r = nullptr, double *parts = nullptr)
     {
-        CsrRowArgs a;
-        a.n = M.n_rows; a.row0 = 0; a.rows = nullptr;
-        a.Ap = M.Ap; a.Aj = M.Aj; a.Ax = M.Ax;
-        a.x = x; a.b = b; a.y = y; a.r = r; a.omega = omega; a.partials = parts;
-        launches += (a.n > 0);
+        if (M.n_rows <= 0) return AMGB_OK;
+        launches++;
         // algorithmic bytes: 12 nnz + 4 (n+1) + 8 per vector pass
         const double vec = (op == OP_SPMV) ? 8.0 * M.n_cols + 8.0 * M.n_rows
                          : (op == OP_PADD) ? 8.0 * M.n_cols + 16.0 * M.n_rows
                          : (op == OP_RESID) ? 24.0 * M.n_rows
                          : (24.0 + (r ? 8.0 : 0.0)) * M.n_rows;
-        RET(prof_begin(op, M.lanes, M.n_rows, M.nnz, 12.0 * M.nnz + 4.0 * (M.n_rows + 1) + vec));
-        RET(launch_csr(op, M.lanes, a, stream));
+        RET(prof_begin(op, M.tiles ? M.tile_G : M.lanes, M.n_rows, M.nnz, 12.0 * M.nnz + 4.0 * (M.n_rows + 1) + vec));
+        if (M.tiles != nullptr) {
+            TileArgs a;
+            a.tiles = M.tiles; a.tile_begin = 0; a.tile_end = M.n_tiles;
+            a.Ap = M.Ap; a.Aj = M.Aj; a.Ax = M.Ax; a.x = x; a.b = b; a.y = y; a.r = r; a.omega = omega;
+            a.partials = parts;
+            const int grid = parts ? tile_grid(1 << 30) : tile_grid(M.n_tiles);   // fixed grid when reducing
+            RET(launch_tile(op, M.tile_G, a, grid, stream));
+        } else {
+            CsrRowArgs a;
+            a.n = M.n_rows; a.row0 = 0; a.rows = nullptr;
+            a.Ap = M.Ap; a.Aj = M.Aj; a.Ax = M.Ax;
+            a.x = x; a.b = b; a.y = y; a.r = r; a.omega = omega; a.partials = parts;
+            RET(launch_csr(op, M.lanes, a, stream));
+        }
         return prof_end();
+    }
+
+    long long partials_len(const DevCsr &M) const
+    {
+        return M.tiles ? (long long)g_num_sms * g_tile_ctas_per_sm : csr_grid(M.n_rows, M.lanes);
     }
 
     int gs_wave(const DevCsr &A, const WaveSchedule &ws, long long w, double *x, const double *b, double omega)
     {
-        CsrRowArgs a;
-        a.n = (int)(ws.ptr[(size_t)w + 1] - ws.ptr[(size_t)w]);
-        a.row0 = 0; a.rows = ws.rows + ws.ptr[(size_t)w];
-        a.Ap = A.Ap; a.Aj = A.Aj; a.Ax = A.Ax;
-        a.x = x; a.b = b; a.y = x; a.r = nullptr; a.omega = omega; a.partials = nullptr;
-        launches += (a.n > 0);
+        const int nrow = (int)(ws.ptr[(size_t)w + 1] - ws.ptr[(size_t)w]);
+        if (nrow <= 0) return AMGB_OK;
+        launches++;
         // one wave of a sweep: its share of 12 nnz + 4 (n+1) + 4 n (row list) + 24 n
-        RET(prof_begin(OP_GS, A.lanes, a.n, ws.nnz[(size_t)w], 12.0 * ws.nnz[(size_t)w] + 36.0 * a.n));
-        RET(launch_csr(OP_GS, A.lanes, a, stream));
+        RET(prof_begin(OP_GS, (ws.contiguous && A.tiles) ? A.tile_G : A.lanes, nrow, ws.nnz[(size_t)w],
+                       12.0 * ws.nnz[(size_t)w] + 36.0 * nrow));
+        if (ws.contiguous && A.tiles != nullptr) {
+            TileArgs a;
+            a.tiles = A.tiles; a.tile_begin = ws.tile_ptr[(size_t)w]; a.tile_end = ws.tile_ptr[(size_t)w + 1];
+            a.Ap = A.Ap; a.Aj = A.Aj; a.Ax = A.Ax; a.x = x; a.b = b; a.y = x; a.r = nullptr; a.omega = omega;
+            a.partials = nullptr;
+            RET(launch_tile(OP_GS, A.tile_G, a, tile_grid(a.tile_end - a.tile_begin), stream));
+        } else {
+            CsrRowArgs a;
+            a.n = nrow;
+            a.row0 = ws.contiguous ? (int)ws.ptr[(size_t)w] : 0;
+            a.rows = ws.contiguous ? nullptr : ws.rows + ws.ptr[(size_t)w];
+            a.Ap = A.Ap; a.Aj = A.Aj; a.Ax = A.Ax;
+            a.x = x; a.b = b; a.y = x; a.r = nullptr; a.omega = omega; a.partials = nullptr;
+            RET(launch_csr(OP_GS, A.lanes, a, stream));
+        }
         return prof_end();
     }
 
@@ -525,8 +681,9 @@ struct amgb_hierarchy {
     int residual_norm2(int slot)
     {
         Level &L = levels[0];
+        cur_level = 0;
         RET(spmv(OP_RESID, L.A, L.x, L.b, L.r, 0.0, nullptr, partials));
-        reduce_partials_kernel<<<1, 1024, 0, stream>>>(partials, (int)n_partials, norms2 + slot);
+        reduce_partials_kernel<<<1, 1024, 0, stream>>>(partials, (int)partials_len(L.A), norms2 + slot);
         CK(cudaGetLastError());
         launches++;
         return AMGB_OK;
@@ -566,6 +723,21 @@ struct amgb_hierarchy {
         norms2_cap = cap;
         return AMGB_OK;
     }
+
+    // level-0 vectors live in wave-major order: dst[i] = src[idx[i]]
+    int gather(const double *src, const int *idx, double *dst, long long n)
+    {
+        if (n <= 0) return AMGB_OK;
+        const long long grid = std::min<long long>((n + 255) / 256, (long long)g_num_sms * 16);
+        gather_kernel<<<(unsigned)grid, 256, 0, stream>>>(src, idx, dst, n);
+        CK(cudaGetLastError());
+        launches++;
+        return AMGB_OK;
+    }
+
+    int make_smoother(const SmootherSpec &sp, const HostCsr &Aperm, const std::vector<int> *pos,
+                      const WaveSchedule *shared, Smoother &s);
+    int finalize_levels();
 };
 
 // ------------------------------------------------------------------------------------------
@@ -664,6 +836,147 @@ int amgb_hierarchy::block_jacobi(Level &L, const Smoother &s)
     return AMGB_OK;
 }
 
+// smoother on the (possibly permuted) level operator.  `pos` maps original row ids to the level's
+// numbering (null = identity).  If `shared` is given the schedule is the level's own wave-major
+// layout (contiguous waves); otherwise waves are derived here and executed through a row list.
+int amgb_hierarchy::make_smoother(const SmootherSpec &sp, const HostCsr &Aperm, const std::vector<int> *pos,
+                                  const WaveSchedule *shared, Smoother &s)
+{
+    s = Smoother();
+    s.kind = sp.kind;
+    s.iterations = sp.iterations;
+    s.sweep = sp.sweep;
+    s.omega = sp.omega;
+    s.bs = sp.bs;
+    if (sp.kind == AMGB_SM_GAUSS_SEIDEL) {
+        if (shared != nullptr) {
+            s.ws = *shared;
+            return AMGB_OK;
+        }
+        std::vector<int> list;
+        const int *lp = nullptr;
+        long long m = Aperm.n_rows;
+        if (sp.has_list) {
+            list = sp.list;
+            if (pos) for (int &v : list) v = (*pos)[(size_t)v];
+            lp = list.data();
+            m = (long long)list.size();
+        } else if (pos) {            // natural order of the ORIGINAL numbering
+            list.resize((size_t)Aperm.n_rows);
+            for (int i = 0; i < Aperm.n_rows; i++) list[(size_t)i] = (*pos)[(size_t)i];
+            lp = list.data();
+        }
+        std::vector<int> rows;
+        build_waves(Aperm, lp, m, rows, s.ws.ptr);
+        RET(upload(&s.ws.rows, rows.data(), m));
+        s.ws.nnz.assign(s.ws.ptr.size() - 1, 0);
+        for (size_t w = 0; w + 1 < s.ws.ptr.size(); w++)
+            for (long long k = s.ws.ptr[w]; k < s.ws.ptr[w + 1]; k++)
+                s.ws.nnz[w] += Aperm.Ap[(size_t)rows[(size_t)k] + 1] - Aperm.Ap[(size_t)rows[(size_t)k]];
+    } else if (sp.kind == AMGB_SM_BLOCK_JACOBI) {
+        RET(upload(&s.Dinv, sp.Dinv.data(), (long long)sp.Dinv.size()));
+    }
+    return AMGB_OK;
+}
+
+static bool is_permutation(const std::vector<int> &list, int n)
+{
+    if ((int)list.size() != n) return false;
+    std::vector<char> seen((size_t)n, 0);
+    for (int v : list) {
+        if (v < 0 || v >= n || seen[(size_t)v]) return false;
+        seen[(size_t)v] = 1;
+    }
+    return true;
+}
+
+// Decide the wave-major row permutation of every Gauss-Seidel level, permute A/P/R accordingly on the
+// host, build tiles, upload everything.
+int amgb_hierarchy::finalize_levels()
+{
+    const int nl = (int)host.size();
+    // order[l][new] = old ; pos[l][old] = new ; empty = identity
+    std::vector<std::vector<int>> order((size_t)nl), pos((size_t)nl);
+    std::vector<WaveSchedule> layout((size_t)nl);     // contiguous schedule of a permuted level
+    std::vector<int> layout_src((size_t)nl, -1);      // 0 = from pre, 1 = from post
+    for (int l = 0; l < nl; l++) {
+        HostLevel &H = host[(size_t)l];
+        if (!H.has_pr || !use_permute) continue;
+        // block smoothers address x in natural block numbering: such levels are never permuted
+        if (H.pre.kind == AMGB_SM_BLOCK_JACOBI || H.post.kind == AMGB_SM_BLOCK_JACOBI) continue;
+        const SmootherSpec *src = nullptr;
+        if (H.pre.kind == AMGB_SM_GAUSS_SEIDEL) { src = &H.pre; layout_src[(size_t)l] = 0; }
+        else if (H.post.kind == AMGB_SM_GAUSS_SEIDEL) { src = &H.post; layout_src[(size_t)l] = 1; }
+        if (src == nullptr) continue;
+        if (src->has_list && !is_permutation(src->list, H.A.n_rows)) { layout_src[(size_t)l] = -1; continue; }
+        std::vector<int> rows;
+        WaveSchedule &W = layout[(size_t)l];
+        build_waves(H.A, src->has_list ? src->list.data() : nullptr, H.A.n_rows, rows, W.ptr);
+        if (W.ptr.size() - 1 > (size_t)H.A.n_rows / 8 + 64) {
+            // (near-)sequential dependency chain, e.g. lexicographic GS on a banded operator: a
+            // wave-major layout would scatter every row; keep the natural numbering + row lists
+            layout_src[(size_t)l] = -1;
+            W = WaveSchedule();
+            continue;
+        }
+        order[(size_t)l] = rows;
+        pos[(size_t)l].resize(rows.size());
+        for (size_t i = 0; i < rows.size(); i++) pos[(size_t)l][(size_t)rows[i]] = (int)i;
+        W.contiguous = true;
+        W.nnz.assign(W.ptr.size() - 1, 0);
+        for (size_t w = 0; w + 1 < W.ptr.size(); w++)
+            for (long long k = W.ptr[w]; k < W.ptr[w + 1]; k++)
+                W.nnz[w] += H.A.Ap[(size_t)rows[(size_t)k] + 1] - H.A.Ap[(size_t)rows[(size_t)k]];
+    }
+    levels.resize((size_t)nl);
+    for (int l = 0; l < nl; l++) {
+        HostLevel &H = host[(size_t)l];
+        Level &L = levels[(size_t)l];
+        L.has_pr = H.has_pr;
+        const bool permuted = !order[(size_t)l].empty();
+        const int *ord = permuted ? order[(size_t)l].data() : nullptr;
+        const int *ps = permuted ? pos[(size_t)l].data() : nullptr;
+        const int *psn = (l + 1 < nl && !order[(size_t)l + 1].empty()) ? pos[(size_t)l + 1].data() : nullptr;
+        const int *ordn = (l + 1 < nl && !order[(size_t)l + 1].empty()) ? order[(size_t)l + 1].data() : nullptr;
+        HostCsr Ap_;
+        const HostCsr *Ause = &H.A;
+        if (permuted) { permute_csr(H.A, ord, ps, Ap_); Ause = &Ap_; }
+        WaveSchedule &W = layout[(size_t)l];
+        if (permuted) {
+            RET(upload_csr(*Ause, L.A, &W.ptr, &W.tile_ptr));
+            if (!use_tiles) W.tile_ptr.clear();
+        } else {
+            RET(upload_csr(*Ause, L.A));
+        }
+        if (H.has_pr) {
+            HostCsr T;
+            if (ord || psn) { permute_csr(H.P, ord, psn, T); RET(upload_csr(T, L.P)); }
+            else RET(upload_csr(H.P, L.P));
+            if (ordn || ps) { permute_csr(H.R, ordn, ps, T); RET(upload_csr(T, L.R)); }
+            else RET(upload_csr(H.R, L.R));
+            const std::vector<int> *pv = permuted ? &pos[(size_t)l] : nullptr;
+            const bool same_lists = H.pre.kind == AMGB_SM_GAUSS_SEIDEL && H.post.kind == AMGB_SM_GAUSS_SEIDEL &&
+                                    H.pre.has_list == H.post.has_list && H.pre.list == H.post.list;
+            const WaveSchedule *sh_pre = (permuted && (layout_src[(size_t)l] == 0)) ? &W : nullptr;
+            const WaveSchedule *sh_post = (permuted && (layout_src[(size_t)l] == 1 || same_lists)) ? &W : nullptr;
+            if (H.pre.kind != AMGB_SM_GAUSS_SEIDEL) sh_pre = nullptr;
+            if (H.post.kind != AMGB_SM_GAUSS_SEIDEL) sh_post = nullptr;
+            RET(make_smoother(H.pre, *Ause, pv, sh_pre, L.pre));
+            RET(make_smoother(H.post, *Ause, pv, sh_post, L.post));
+        }
+        if (l == 0 && permuted) {
+            RET(upload(&order0, order[0].data(), (long long)order[0].size()));
+            RET(upload(&pos0, pos[0].data(), (long long)pos[0].size()));
+            RET(dalloc(&io_tmp, H.A.n_rows));
+        }
+        // block Jacobi / point permutation do not mix: block smoothers keep the natural numbering
+        H = HostLevel();                 // release the host copy level by level
+    }
+    host.clear();
+    host.shrink_to_fit();
+    return AMGB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // C ABI (1): hierarchy
 // ------------------------------------------------------------------------------------------
@@ -675,10 +988,16 @@ extern "C" int amgb_hierarchy_create(int device, amgb_hierarchy **out)
     CK(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(AMGB_EINVAL, "no such CUDA device");
     CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    g_num_sms = prop.multiProcessorCount;
+    g_tile_ctas_per_sm = std::max(1, (int)(prop.sharedMemPerMultiprocessor / (kTileSmemBytes + 1024)));
     amgb_hierarchy *h = new amgb_hierarchy();
     h->device = device;
-    const char *ng = getenv("AMGB_NO_GRAPH");
-    h->use_graph = !(ng && ng[0] == '1');
+    auto flag = [](const char *name) { const char *v = getenv(name); return v && v[0] == '1'; };
+    h->use_graph = !flag("AMGB_NO_GRAPH");
+    h->use_tiles = !flag("AMGB_NO_TILES");
+    h->use_permute = !flag("AMGB_NO_PERMUTE");
     *out = h;
     return AMGB_OK;
 }
@@ -696,51 +1015,78 @@ extern "C" void amgb_hierarchy_destroy(amgb_hierarchy *h)
     delete h;
 }
 
+static int copy_smoother(const amgb_smoother *in, const HostCsr &A, SmootherSpec &s)
+{
+    s = SmootherSpec();
+    if (in == nullptr || in->kind == AMGB_SM_NONE) return AMGB_OK;
+    s.kind = in->kind;
+    s.iterations = in->iterations;
+    s.sweep = in->sweep;
+    s.omega = in->omega;
+    if (s.iterations < 0) return fail(AMGB_EINVAL, "smoother iterations < 0");
+    switch (in->kind) {
+    case AMGB_SM_JACOBI: return AMGB_OK;
+    case AMGB_SM_GAUSS_SEIDEL:
+        if (s.sweep < 0 || s.sweep > 2)
+            return fail(AMGB_EINVAL, "valid sweep directions: \"forward\", \"backward\", and \"symmetric\"");
+        if (in->indices != nullptr) {
+            s.has_list = true;
+            s.list.assign(in->indices, in->indices + in->n_indices);
+            for (int v : s.list)
+                if (v < 0 || v >= A.n_rows) return fail(AMGB_EINVAL, "gauss_seidel_indexed: row index out of range");
+        }
+        return AMGB_OK;
+    case AMGB_SM_BLOCK_JACOBI:
+        s.bs = in->blocksize;
+        if (s.bs < 1 || s.bs > 8 || A.n_rows % s.bs)
+            return fail(AMGB_ENOTIMPL, "block_jacobi: blocksize must be 1..8 and divide n");
+        if (in->Dinv == nullptr) return fail(AMGB_EINVAL, "block_jacobi: Dinv required");
+        s.Dinv.assign(in->Dinv, in->Dinv + (size_t)A.n_rows * s.bs);
+        return AMGB_OK;
+    }
+    return fail(AMGB_ENOTIMPL, "smoother kind outside the hot-path scope");
+}
+
 extern "C" int amgb_hierarchy_add_level(amgb_hierarchy *h, const amgb_matrix *A, const amgb_matrix *P,
                                         const amgb_matrix *R, const amgb_smoother *pre,
                                         const amgb_smoother *post)
 {
     if (h == nullptr) return fail(AMGB_EINVAL, "null hierarchy");
     if (h->finalized) return fail(AMGB_ESTATE, "hierarchy already finalized");
-    CK(cudaSetDevice(h->device));
-    if (!h->levels.empty() && !h->levels.back().has_pr)
+    if (!h->host.empty() && !h->host.back().has_pr)
         return fail(AMGB_ESTATE, "previous level was added as the coarsest (no P/R)");
-    HostCsr HA;
-    RET(to_host_csr(A, HA, "A"));
-    if (HA.n_rows != HA.n_cols) return fail(AMGB_EINVAL, "expected square matrix");
-    if (!h->levels.empty() && h->levels.back().P.n_cols != HA.n_rows)
-        return fail(AMGB_EINVAL, "level size does not match the previous level's P");
-    Level L;
-    RET(h->upload_csr(HA, L.A));
-    if ((P == nullptr) != (R == nullptr)) return fail(AMGB_EINVAL, "P and R must be given together");
-    if (P != nullptr) {
-        HostCsr HP, HR;
-        RET(to_host_csr(P, HP, "P"));
-        RET(to_host_csr(R, HR, "R"));
-        if (HP.n_rows != HA.n_rows || HR.n_cols != HA.n_rows || HR.n_rows != HP.n_cols)
-            return fail(AMGB_EINVAL, "P/R shapes inconsistent with A");
-        RET(h->upload_csr(HP, L.P));
-        RET(h->upload_csr(HR, L.R));
+    h->host.emplace_back();
+    HostLevel &L = h->host.back();
+    int rc = to_host_csr(A, L.A, "A");
+    if (rc == AMGB_OK && L.A.n_rows != L.A.n_cols) rc = fail(AMGB_EINVAL, "expected square matrix");   // relaxation.py:81-82
+    if (rc == AMGB_OK && h->host.size() > 1 && h->host[h->host.size() - 2].P.n_cols != L.A.n_rows)
+        rc = fail(AMGB_EINVAL, "level size does not match the previous level's P");
+    if (rc == AMGB_OK && (P == nullptr) != (R == nullptr)) rc = fail(AMGB_EINVAL, "P and R must be given together");
+    if (rc == AMGB_OK && P != nullptr) {
+        rc = to_host_csr(P, L.P, "P");
+        if (rc == AMGB_OK) rc = to_host_csr(R, L.R, "R");
+        if (rc == AMGB_OK && (L.P.n_rows != L.A.n_rows || L.R.n_cols != L.A.n_rows || L.R.n_rows != L.P.n_cols))
+            rc = fail(AMGB_EINVAL, "P/R shapes inconsistent with A");
         L.has_pr = true;
-        RET(h->setup_smoother(pre, HA, L.pre));
-        RET(h->setup_smoother(post, HA, L.post));
+        if (rc == AMGB_OK) rc = copy_smoother(pre, L.A, L.pre);
+        if (rc == AMGB_OK) rc = copy_smoother(post, L.A, L.post);
     }
-    h->levels.push_back(L);
-    return AMGB_OK;
+    if (rc != AMGB_OK) h->host.pop_back();
+    return rc;
 }
 
 extern "C" int amgb_hierarchy_set_coarse_pinv(amgb_hierarchy *h, int32_t n, const double *pinv,
                                               int32_t coarse_is_zero)
 {
     if (h == nullptr) return fail(AMGB_EINVAL, "null hierarchy");
-    if (h->levels.empty()) return fail(AMGB_ESTATE, "no levels");
-    if (n != h->levels.back().A.n_rows) return fail(AMGB_EINVAL, "pinv size != coarsest level size");
-    CK(cudaSetDevice(h->device));
+    if (h->finalized) return fail(AMGB_ESTATE, "hierarchy already finalized");
+    if (h->host.empty()) return fail(AMGB_ESTATE, "no levels");
+    if (n != h->host.back().A.n_rows) return fail(AMGB_EINVAL, "pinv size != coarsest level size");
     h->coarse_zero = coarse_is_zero != 0;
     h->coarse_n = n;
     if (!h->coarse_zero) {
         if (pinv == nullptr) return fail(AMGB_EINVAL, "pinv is null");
-        RET(h->upload(&h->coarse_pinv, pinv, (long long)n * n));
+        h->coarse_host.assign(pinv, pinv + (size_t)n * n);
     }
     h->have_coarse = true;
     return AMGB_OK;
@@ -750,8 +1096,8 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
 {
     if (h == nullptr) return fail(AMGB_EINVAL, "null hierarchy");
     if (h->finalized) return fail(AMGB_ESTATE, "already finalized");
-    if (h->levels.empty()) return fail(AMGB_ESTATE, "no levels");
-    if (h->levels.back().has_pr) return fail(AMGB_ESTATE, "last level must be added without P/R");
+    if (h->host.empty()) return fail(AMGB_ESTATE, "no levels");
+    if (h->host.back().has_pr) return fail(AMGB_ESTATE, "last level must be added without P/R");
     if (!h->have_coarse) return fail(AMGB_ESTATE, "coarse solver not set");
     CK(cudaSetDevice(h->device));
     if (stream != nullptr) {
@@ -760,6 +1106,9 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
     }
+    RET(h->finalize_levels());
+    if (!h->coarse_zero) RET(h->upload(&h->coarse_pinv, h->coarse_host.data(), (long long)h->coarse_host.size()));
+    h->coarse_host.clear();
     for (Level &L : h->levels) {
         const long long n = L.A.n_rows;
         RET(h->dalloc(&L.x_home, n));
@@ -768,7 +1117,7 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
         RET(h->dalloc(&L.r, n));
         L.x = L.x_home;
     }
-    h->n_partials = csr_grid(h->levels[0].A.n_rows, h->levels[0].A.lanes);
+    h->n_partials = std::max<long long>(h->partials_len(h->levels[0].A), 1);
     RET(h->dalloc(&h->partials, h->n_partials));
     RET(h->ensure_norms(128));
     RET(h->dalloc(&h->sumsq_parts, kSumsqBlocks));
@@ -777,7 +1126,10 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
     return AMGB_OK;
 }
 
-extern "C" int amgb_hierarchy_num_levels(const amgb_hierarchy *h) { return h ? (int)h->levels.size() : 0; }
+extern "C" int amgb_hierarchy_num_levels(const amgb_hierarchy *h)
+{
+    return h ? (int)(h->finalized ? h->levels.size() : h->host.size()) : 0;
+}
 extern "C" int64_t amgb_hierarchy_device_bytes(const amgb_hierarchy *h) { return h ? h->dev_bytes : 0; }
 extern "C" int64_t amgb_hierarchy_last_launches(const amgb_hierarchy *h) { return h ? h->last_launches : 0; }
 
@@ -802,6 +1154,38 @@ static int check_cycle_args(amgb_hierarchy *h, int32_t cycle, int32_t cpl)
     return AMGB_OK;
 }
 
+// bring b / x0 into the level-0 buffers (wave-major order if level 0 is permuted)
+static int load_level0(amgb_hierarchy *h, const double *b, const double *x, cudaMemcpyKind kind)
+{
+    Level &L0 = h->levels[0];
+    const size_t bytes = sizeof(double) * (size_t)L0.A.n_rows;
+    cudaStream_t s = h->stream;
+    L0.x = L0.x_home;
+    if (h->order0 == nullptr) {
+        CK(cudaMemcpyAsync(L0.b, b, bytes, kind, s));
+        CK(cudaMemcpyAsync(L0.x, x, bytes, kind, s));
+        return AMGB_OK;
+    }
+    CK(cudaMemcpyAsync(h->io_tmp, b, bytes, kind, s));
+    RET(h->gather(h->io_tmp, h->order0, L0.b, L0.A.n_rows));
+    CK(cudaMemcpyAsync(h->io_tmp, x, bytes, kind, s));
+    RET(h->gather(h->io_tmp, h->order0, L0.x, L0.A.n_rows));
+    return AMGB_OK;
+}
+
+static int store_level0(amgb_hierarchy *h, double *x, cudaMemcpyKind kind)
+{
+    Level &L0 = h->levels[0];
+    const size_t bytes = sizeof(double) * (size_t)L0.A.n_rows;
+    if (h->order0 == nullptr) {
+        CK(cudaMemcpyAsync(x, L0.x, bytes, kind, h->stream));
+        return AMGB_OK;
+    }
+    RET(h->gather(L0.x, h->pos0, h->io_tmp, L0.A.n_rows));
+    CK(cudaMemcpyAsync(x, h->io_tmp, bytes, kind, h->stream));
+    return AMGB_OK;
+}
+
 extern "C" int amgb_solve(amgb_hierarchy *h, const double *b_host, double *x_host, double tol,
                           int32_t maxiter, int32_t cycle, int32_t cycles_per_level, double *residuals,
                           int32_t *n_residuals, int32_t *info)
@@ -811,13 +1195,10 @@ extern "C" int amgb_solve(amgb_hierarchy *h, const double *b_host, double *x_hos
     if (maxiter < 1) return fail(AMGB_EINVAL, "maxiter must be >= 1");
     CK(cudaSetDevice(h->device));
     Level &L0 = h->levels[0];
-    const size_t bytes = sizeof(double) * (size_t)L0.A.n_rows;
     cudaStream_t s = h->stream;
     h->launches = 0;
     RET(h->ensure_norms(maxiter + 1));
-    L0.x = L0.x_home;
-    CK(cudaMemcpyAsync(L0.b, b_host, bytes, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(L0.x, x_host, bytes, cudaMemcpyHostToDevice, s));
+    RET(load_level0(h, b_host, x_host, cudaMemcpyHostToDevice));
 
     // normb (multilevel.py:540-542) is only needed by the stop test; reduce it on the device
     double normb = 1.0;
@@ -845,14 +1226,13 @@ extern "C" int amgb_solve(amgb_hierarchy *h, const double *b_host, double *x_hos
         }
         if (it == maxiter) { conv = it; break; }                  // :579
     }
-    CK(cudaMemcpyAsync(x_host, L0.x, bytes, cudaMemcpyDeviceToHost, s));
+    RET(store_level0(h, x_host, cudaMemcpyDeviceToHost));
     std::vector<double> n2((size_t)it + 1);
     CK(cudaMemcpyAsync(n2.data(), h->norms2, sizeof(double) * ((size_t)it + 1), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (residuals != nullptr)
         for (int k = 0; k <= it; k++) residuals[k] = std::sqrt(n2[(size_t)k]);
     if (n_residuals != nullptr) *n_residuals = it + 1;
-    // tol == 0 can still "converge" if the residual is exactly... never < 0: matches `normr < tol*normb`
     if (info != nullptr) *info = conv;
     h->last_launches = h->launches;
     return AMGB_OK;
@@ -865,13 +1245,9 @@ extern "C" int amgb_solve_device(amgb_hierarchy *h, const double *b_dev, double 
     if (b_dev == nullptr || x_dev == nullptr) return fail(AMGB_EINVAL, "null device vector");
     if (ncycles < 0) return fail(AMGB_EINVAL, "ncycles < 0");
     CK(cudaSetDevice(h->device));
-    Level &L0 = h->levels[0];
-    const size_t bytes = sizeof(double) * (size_t)L0.A.n_rows;
     cudaStream_t s = h->stream;
     h->launches = 0;
-    L0.x = L0.x_home;
-    CK(cudaMemcpyAsync(L0.b, b_dev, bytes, cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(L0.x, x_dev, bytes, cudaMemcpyDeviceToDevice, s));
+    RET(load_level0(h, b_dev, x_dev, cudaMemcpyDeviceToDevice));
     if (norms2_dev != nullptr) {
         RET(h->ensure_norms(ncycles + 1));
         RET(h->residual_norm2(0));
@@ -880,7 +1256,7 @@ extern "C" int amgb_solve_device(amgb_hierarchy *h, const double *b_dev, double 
         RET(h->one_iteration(cycle, cycles_per_level));
         if (norms2_dev != nullptr) RET(h->residual_norm2(it));
     }
-    CK(cudaMemcpyAsync(x_dev, L0.x, bytes, cudaMemcpyDeviceToDevice, s));
+    RET(store_level0(h, x_dev, cudaMemcpyDeviceToDevice));
     if (norms2_dev != nullptr)
         CK(cudaMemcpyAsync(norms2_dev, h->norms2, sizeof(double) * ((size_t)ncycles + 1),
                            cudaMemcpyDeviceToDevice, s));

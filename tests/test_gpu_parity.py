@@ -63,6 +63,23 @@ def test_vcycle_matches_oracle_on_fresh_rhs(name, load_golden):
     assert relerr(xg, xo) < TOL
 
 
+@pytest.mark.parametrize("env", [{"AMGB_NO_TILES": "1"}, {"AMGB_NO_PERMUTE": "1"},
+                                 {"AMGB_NO_TILES": "1", "AMGB_NO_PERMUTE": "1"}, {"AMGB_NO_GRAPH": "1"},
+                                 {"AMGB_TILE_G": "4"}, {"AMGB_TILE_G": "32"}])
+@pytest.mark.parametrize("name", GOLDEN)
+def test_every_kernel_path_matches_reference_golden(name, env, monkeypatch):
+    """The lanes-per-row kernels, the un-permuted layout, the un-graphed cycle and forced lane-group
+    widths of the TMA tile kernel must all reproduce the reference (the env is read per hierarchy)."""
+    from pyamg_b200.hierarchy_io import load_hierarchy
+    from conftest import golden_path
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    ml, ex = load_hierarchy(golden_path(name))
+    x = ml.solve(ex["b"], tol=0, maxiter=len(ex["residuals"]) - 1)
+    assert relerr(x, ex["x_ref"]) < TOL
+    assert relerr(ml.solve(ex["b"], tol=0, maxiter=2, cycle="W"), ex["x_ref_W"]) < TOL
+
+
 def test_callback_residuals_and_psolve(load_golden):
     ml, ex = load_golden("cfg3_rs_mcgs_poisson3d")
     seen, res = [], []
