@@ -128,23 +128,53 @@ static int launch_fill(double *x, long long n, double v, cudaStream_t s)
 // ------------------------------------------------------------------------------------------
 // tile-kernel launch
 // ------------------------------------------------------------------------------------------
-static int g_tile_ctas_per_sm = 2;
 static int g_num_sms = 148;
+static int g_tile_cfg = 0;          // AMGB_TILE_CFG: which TileCfg geometry (tile_kernels.cuh)
+static int g_tile_ctas_per_sm = 2;  // resident CTAs per SM for that geometry (AMGB_TILE_CTAS caps it)
+static int g_tile_T = 512, g_tile_rmax = 128, g_tile_warps = 8;
+static int g_tile_hints = 1;        // AMGB_NO_HINTS=1 disables the L2 eviction hints
 
-template <int OP>
-static int launch_tile_op(int G, const TileArgs &a, int grid, cudaStream_t s)
+template <class C>
+static void tile_cfg_select(size_t smem_per_sm)
 {
-    const dim3 g((unsigned)grid), b(kTileWarps * 32);
-#define AMGB_TILE_CASE(GG)                                                                              \
-    case GG: {                                                                                          \
-        static bool attr_done = false;                                                                  \
-        if (!attr_done) {                                                                               \
-            CK(cudaFuncSetAttribute(csr_tile_kernel<GG, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)kTileSmemBytes));                                              \
-            attr_done = true;                                                                           \
-        }                                                                                               \
-        csr_tile_kernel<GG, OP><<<g, b, kTileSmemBytes, s>>>(a);                                        \
-        break;                                                                                          \
+    g_tile_T = C::T;
+    g_tile_rmax = C::RMAX;
+    g_tile_warps = C::WARPS;
+    g_tile_ctas_per_sm = std::max(1, (int)(smem_per_sm / (tile_smem_bytes<C>() + 1024)));
+    g_tile_ctas_per_sm = std::min(g_tile_ctas_per_sm, 2048 / (C::WARPS * 32));
+}
+
+static void tile_configure(size_t smem_per_sm)
+{
+    const char *e = getenv("AMGB_TILE_CFG");
+    g_tile_cfg = e ? atoi(e) : 1;   // measured best on B200 (tools/tune_tiles.py): T=256, 3 CTAs/SM
+    switch (g_tile_cfg) {
+    case 0: tile_cfg_select<TileCfg0>(smem_per_sm); break;
+    case 2: tile_cfg_select<TileCfg2>(smem_per_sm); break;
+    case 3: tile_cfg_select<TileCfg3>(smem_per_sm); break;
+    default: g_tile_cfg = 1; tile_cfg_select<TileCfg1>(smem_per_sm); break;
+    }
+    const char *c = getenv("AMGB_TILE_CTAS");
+    if (c && atoi(c) >= 1) g_tile_ctas_per_sm = std::min(g_tile_ctas_per_sm, atoi(c));
+    const char *nh = getenv("AMGB_NO_HINTS");
+    g_tile_hints = !(nh && nh[0] == '1');
+}
+
+template <int OP, class C>
+static int launch_tile_cfg(int G, const TileArgs &a, int grid, cudaStream_t s)
+{
+    const dim3 g((unsigned)grid), b(C::WARPS * 32);
+    constexpr size_t smem = tile_smem_bytes<C>();
+#define AMGB_TILE_CASE(GG)                                                                               \
+    case GG: {                                                                                           \
+        static bool attr_done = false;                                                                   \
+        if (!attr_done) {                                                                                \
+            CK(cudaFuncSetAttribute(csr_tile_kernel<GG, OP, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)smem));                                                         \
+            attr_done = true;                                                                            \
+        }                                                                                                \
+        csr_tile_kernel<GG, OP, C><<<g, b, smem, s>>>(a);                                                \
+        break;                                                                                           \
     }
     switch (G) {
         AMGB_TILE_CASE(1)
@@ -160,9 +190,21 @@ static int launch_tile_op(int G, const TileArgs &a, int grid, cudaStream_t s)
     return AMGB_OK;
 }
 
-static int launch_tile(int op, int G, const TileArgs &a, int grid, cudaStream_t s)
+template <int OP>
+static int launch_tile_op(int G, const TileArgs &a, int grid, cudaStream_t s)
+{
+    switch (g_tile_cfg) {
+    case 0: return launch_tile_cfg<OP, TileCfg0>(G, a, grid, s);
+    case 2: return launch_tile_cfg<OP, TileCfg2>(G, a, grid, s);
+    case 3: return launch_tile_cfg<OP, TileCfg3>(G, a, grid, s);
+    default: return launch_tile_cfg<OP, TileCfg1>(G, a, grid, s);
+    }
+}
+
+static int launch_tile(int op, int G, TileArgs a, int grid, cudaStream_t s)
 {
     if (a.tile_end <= a.tile_begin) return AMGB_OK;
+    a.hints = g_tile_hints;
     switch (op) {
     case OP_SPMV: return launch_tile_op<OP_SPMV>(G, a, grid, s);
     case OP_RESID: return launch_tile_op<OP_RESID>(G, a, grid, s);
@@ -176,7 +218,7 @@ static int launch_tile(int op, int G, const TileArgs &a, int grid, cudaStream_t 
 static inline int tile_grid(int ntiles)
 {
     const int full = g_num_sms * g_tile_ctas_per_sm;
-    const int need = (ntiles + kTileWarps - 1) / kTileWarps;
+    const int need = (ntiles + g_tile_warps - 1) / g_tile_warps;
     return std::max(1, std::min(full, need));
 }
 
@@ -383,8 +425,8 @@ static int pick_tile_G(long long nnz, long long n_rows)
     return g;
 }
 
-// whole rows, <= kTileNnz entries and <= kTileRows rows per tile, no tile across a `breaks` row
-// (sorted, e.g. Gauss-Seidel wave boundaries); a row longer than kTileNnz is a tile of its own.
+// whole rows, <= T entries and <= RMAX rows per tile (current tile geometry), no tile across a `breaks` row
+// (sorted, e.g. Gauss-Seidel wave boundaries); a row longer than T is a tile of its own.
 // Row counts are rounded down to a multiple of the rows reduced per pass (32/G) where possible.
 static void build_tiles(const HostCsr &A, int G, const std::vector<long long> *breaks,
                         std::vector<TileDesc> &tiles, std::vector<int> *tile_ptr)
@@ -404,9 +446,9 @@ static void build_tiles(const HostCsr &A, int G, const std::vector<long long> *b
         }
         int e = r;
         long long nz = 0;
-        while (e < limit && e - r < kTileRows) {
+        while (e < limit && e - r < g_tile_rmax) {
             const long long len = A.Ap[(size_t)e + 1] - A.Ap[(size_t)e];
-            if (nz + len > kTileNnz) break;
+            if (nz + len > g_tile_T) break;
             nz += len;
             e++;
         }
@@ -991,7 +1033,7 @@ extern "C" int amgb_hierarchy_create(int device, amgb_hierarchy **out)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     g_num_sms = prop.multiProcessorCount;
-    g_tile_ctas_per_sm = std::max(1, (int)(prop.sharedMemPerMultiprocessor / (kTileSmemBytes + 1024)));
+    tile_configure(prop.sharedMemPerMultiprocessor);
     amgb_hierarchy *h = new amgb_hierarchy();
     h->device = device;
     auto flag = [](const char *name) { const char *v = getenv(name); return v && v[0] == '1'; };
@@ -1111,10 +1153,10 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
     h->coarse_host.clear();
     for (Level &L : h->levels) {
         const long long n = L.A.n_rows;
-        RET(h->dalloc(&L.x_home, n));
-        RET(h->dalloc(&L.xalt, n));
-        RET(h->dalloc(&L.b, n));
-        RET(h->dalloc(&L.r, n));
+        RET(h->dalloc(&L.x_home, n + 2));      // +2: the TMA reads whole 16-byte groups
+        RET(h->dalloc(&L.xalt, n + 2));
+        RET(h->dalloc(&L.b, n + 2));
+        RET(h->dalloc(&L.r, n + 2));
         L.x = L.x_home;
     }
     h->n_partials = std::max<long long>(h->partials_len(h->levels[0].A), 1);

@@ -4,16 +4,20 @@
 // Why: the hot path is HBM-bound CSR traffic (12 B per stored entry, 0.17 flop/B).  A lanes-per-row
 // kernel (csr_kernels.cuh) keeps only a few hundred bytes per warp in flight and pays a dependent
 // row-pointer -> entries -> gather latency chain per row group.  Here every warp owns a ring of
-// shared-memory stages; one elected lane asks the TMA for the NEXT tile's three contiguous segments
-// (values, column indices, row pointers -- each a single 16-B-aligned bulk copy) while the warp reduces
-// the CURRENT tile out of shared memory.  The copy engine, not the LSU, streams the operator; the
-// warps only issue the x gathers and the fused epilogue.  Bytes in flight per SM = warps x stage size
-// (~100 KB), independent of register pressure.
+// shared-memory stages; one elected lane asks the TMA for the NEXT tile's contiguous segments
+// (values, column indices, row pointers, and the b / x_old slices the epilogue needs -- each a single
+// 16-B-aligned bulk copy) while the warp reduces the CURRENT tile out of shared memory.  The copy
+// engine, not the LSU, streams the operator; the warps only issue the x gathers and the fused
+// epilogue store.  Bytes in flight per SM = warps x stage size, independent of register pressure.
 //
 // Tiles are built on the host at upload (engine.cu build_tiles): whole rows, at most T stored entries
 // and RMAX rows, never crossing a Gauss-Seidel wave boundary; a row longer than T is a tile of its own
 // and is streamed straight from global memory.  Work distribution is static (tile t -> warp t mod
 // #warps), the grid persistent: 148 SMs x resident CTAs.
+//
+// L2 policy: the operator stream is read exactly once per launch -> evict-first; the gathered vector
+// is re-read by every row that references it (and, for multi-colour Gauss-Seidel, by every wave) ->
+// evict-last, so it survives in the 126 MB L2 while the operator streams past it.
 //
 // Epilogues (template OP, same semantics as csr_kernels.cuh / the reference, file:line there):
 //   OP_SPMV, OP_RESID (+|r|^2), OP_PADD, OP_JACOBI (+ optional residual by-product), OP_GS (rows of one
@@ -37,23 +41,37 @@ struct TileArgs {
     double *r;
     double omega;
     double *partials;        // one per CTA (grid is fixed), or nullptr
+    int hints;               // 1: L2 eviction hints (operator stream evict-first, x gathers evict-last)
 };
 
-constexpr int kTileWarps = 8;            // warps per CTA
-constexpr int kTileNnz = 512;            // T: stored entries per tile
-constexpr int kTileRows = 128;           // RMAX: rows per tile
-constexpr int kTileStages = 2;
+// Tile geometry (compile-time): T stored entries and RMAX rows per tile, ring depth, warps per CTA.
+// Shared memory per CTA = WARPS * STAGES * (12 T + 20 RMAX + ~150) bytes; what is left of the
+// 228 KB/SM is L1 for the x gathers, so smaller tiles trade TMA efficiency for gather hit rate.
+template <int T_, int RMAX_, int STAGES_, int WARPS_>
+struct TileCfg {
+    static constexpr int T = T_, RMAX = RMAX_, STAGES = STAGES_, WARPS = WARPS_;
+};
+using TileCfg0 = TileCfg<512, 128, 2, 8>;
+using TileCfg1 = TileCfg<256, 64, 2, 8>;
+using TileCfg2 = TileCfg<256, 64, 3, 8>;
+using TileCfg3 = TileCfg<128, 32, 4, 8>;
 
-struct __align__(16) TileStage {
-    double val[kTileNnz + 8];
-    int col[kTileNnz + 8];
-    int ptr[kTileRows + 8];
+template <class C>
+struct __align__(16) TileStageT {
+    double val[C::T + 8];
+    double bseg[C::RMAX + 4];    // b[row0..row1)          (RESID / JACOBI / GS)
+    double xseg[C::RMAX + 4];    // x[row0..row1), old     (JACOBI)
+    int col[C::T + 8];
+    int ptr[C::RMAX + 8];
 };
-struct __align__(16) TileWarpSmem {
-    TileStage st[kTileStages];
-    unsigned long long bar[kTileStages];
+template <class C>
+struct __align__(16) TileWarpSmemT {
+    TileStageT<C> st[C::STAGES];
+    unsigned long long bar[C::STAGES];
+    unsigned long long pad_;
 };
-constexpr size_t kTileSmemBytes = sizeof(TileWarpSmem) * kTileWarps;
+template <class C>
+constexpr size_t tile_smem_bytes() { return sizeof(TileWarpSmemT<C>) * C::WARPS; }
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -79,6 +97,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ unsigned long long policy_evict_first()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 // 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA, SASS UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
 {
@@ -87,76 +117,114 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, unsigned bytes, unsigned long long *bar,
+                                              unsigned long long policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ double ld_x_hint_nc(const double *p, unsigned long long policy)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ double ld_x_hint(const double *p, unsigned long long policy)
+{
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy) : "memory");
+    return v;
+}
 
-// One lane: ask the TMA for tile t's segments.  All three sources start on 16-byte boundaries: the
-// entry range is widened to a multiple of 4 entries on both sides (the arrays are padded at upload).
-__device__ __forceinline__ void tile_issue(const TileArgs &a, int t, TileStage &st, unsigned long long *bar)
+// One lane: ask the TMA for tile t's segments.  Every source starts on a 16-byte boundary: entry ranges
+// are widened to multiples of 4 entries, vector ranges to multiples of 2 (the arrays are padded at upload).
+template <class C, int OP>
+__device__ __forceinline__ void tile_issue(const TileArgs &a, int t, TileStageT<C> &st, unsigned long long *bar,
+                                           unsigned long long pol)
 {
     const TileDesc d0 = a.tiles[t], d1 = a.tiles[t + 1];
     const int len = d1.nz0 - d0.nz0;
-    if (len > kTileNnz) {          // long row: streamed from global memory, nothing to stage
+    if (len > C::T) {              // long row: streamed from global memory, nothing to stage
         mbar_expect_tx(bar, 0);
         return;
     }
+    constexpr bool kB = (OP == OP_RESID || OP == OP_JACOBI || OP == OP_GS);
+    constexpr bool kX = (OP == OP_JACOBI);
     const int s4 = d0.nz0 & ~3;
     const int cnt = ((d1.nz0 + 3) & ~3) - s4;
     const int r4 = d0.row0 & ~3;
     const int rcnt = ((d1.row0 + 1 + 3) & ~3) - r4;
-    mbar_expect_tx(bar, (unsigned)(cnt * 12 + rcnt * 4));
+    const int v2 = d0.row0 & ~1;
+    const int vcnt = ((d1.row0 + 1) & ~1) - v2;
+    mbar_expect_tx(bar, (unsigned)(cnt * 12 + rcnt * 4 + ((kB ? 1 : 0) + (kX ? 1 : 0)) * vcnt * 8));
     if (cnt > 0) {
-        bulk_g2s(st.val, a.Ax + s4, (unsigned)cnt * 8u, bar);
-        bulk_g2s(st.col, a.Aj + s4, (unsigned)cnt * 4u, bar);
+        if (a.hints) {
+            bulk_g2s_hint(st.val, a.Ax + s4, (unsigned)cnt * 8u, bar, pol);
+            bulk_g2s_hint(st.col, a.Aj + s4, (unsigned)cnt * 4u, bar, pol);
+        } else {
+            bulk_g2s(st.val, a.Ax + s4, (unsigned)cnt * 8u, bar);
+            bulk_g2s(st.col, a.Aj + s4, (unsigned)cnt * 4u, bar);
+        }
     }
     bulk_g2s(st.ptr, a.Ap + r4, (unsigned)rcnt * 4u, bar);
+    if (kB && vcnt > 0) bulk_g2s(st.bseg, a.b + v2, (unsigned)vcnt * 8u, bar);
+    if (kX && vcnt > 0) bulk_g2s(st.xseg, a.x + v2, (unsigned)vcnt * 8u, bar);
 }
 
 // G lanes per row inside a tile (G = 1: thread per row -- 5/7-point stencils; larger G for the
 // denser coarse operators).  32/G rows are reduced per pass.
-template <int G, int OP>
-__global__ void __launch_bounds__(kTileWarps * 32, 2) csr_tile_kernel(const TileArgs a)
+template <int G, int OP, class C>
+__global__ void __launch_bounds__(C::WARPS * 32) csr_tile_kernel(const TileArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool kNeedDiag = (OP == OP_JACOBI || OP == OP_GS);
     constexpr int RPP = 32 / G;                       // rows per pass
+    constexpr int STAGES = C::STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane & (G - 1), grp = lane / G;
-    TileWarpSmem &ws = reinterpret_cast<TileWarpSmem *>(smem_raw)[warp];
+    TileWarpSmemT<C> &ws = reinterpret_cast<TileWarpSmemT<C> *>(smem_raw)[warp];
 
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kTileStages; s++) mbar_init(&ws.bar[s], 1);
+        for (int s = 0; s < STAGES; s++) mbar_init(&ws.bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    const unsigned long long pol_first = policy_evict_first();
+    const unsigned long long pol_last = policy_evict_last();
 
-    const int nwarps = gridDim.x * kTileWarps;
+    const int nwarps = gridDim.x * C::WARPS;
     // consecutive tiles go to the warps of one CTA: neighbouring rows share x lines in L1
-    int t = a.tile_begin + blockIdx.x * kTileWarps + warp;
+    int t = a.tile_begin + blockIdx.x * C::WARPS + warp;
     unsigned phase = 0;       // bit s = parity to wait for on stage s
     double r2 = 0.0;
 
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kTileStages - 1; s++)
-            if (t + s * nwarps < a.tile_end) tile_issue(a, t + s * nwarps, ws.st[s], &ws.bar[s]);
+        for (int s = 0; s < STAGES - 1; s++)
+            if (t + s * nwarps < a.tile_end) tile_issue<C, OP>(a, t + s * nwarps, ws.st[s], &ws.bar[s], pol_first);
     }
     int stage = 0;
     for (; t < a.tile_end; t += nwarps) {
         // keep the ring full: the stage consumed in the previous iteration is free again
-        const int tn = t + (kTileStages - 1) * nwarps;
-        const int sn = (stage + kTileStages - 1) % kTileStages;
-        if (lane == 0 && tn < a.tile_end) tile_issue(a, tn, ws.st[sn], &ws.bar[sn]);
+        const int tn = t + (STAGES - 1) * nwarps;
+        const int sn = (stage + STAGES - 1) % STAGES;
+        if (lane == 0 && tn < a.tile_end) tile_issue<C, OP>(a, tn, ws.st[sn], &ws.bar[sn], pol_first);
 
         const TileDesc d0 = a.tiles[t], d1 = a.tiles[t + 1];
         const int row0 = d0.row0, nrows = d1.row0 - d0.row0;
         const int s0 = d0.nz0, len = d1.nz0 - d0.nz0;
         mbar_wait(&ws.bar[stage], (phase >> stage) & 1u);
         phase ^= 1u << stage;
-        const TileStage &st = ws.st[stage];
+        const TileStageT<C> &st = ws.st[stage];
 
-        if (len <= kTileNnz) {
+        if (len <= C::T) {
             const int soff = s0 & ~3;                 // smem index = global entry index - soff
             const int poff = row0 & ~3;
+            const int voff = row0 & ~1;
             for (int rbase = 0; rbase < nrows; rbase += RPP) {
                 const int lr = rbase + grp;
                 const bool active = lr < nrows;
@@ -168,11 +236,13 @@ __global__ void __launch_bounds__(kTileWarps * 32, 2) csr_tile_kernel(const Tile
                 }
                 double sum = 0.0, diag = 0.0;
                 int jd = -1;
-#pragma unroll 4
+#pragma unroll 8
                 for (int jj = jb + sub; jj < je; jj += G) {
                     const int c = st.col[jj];
                     const double v = st.val[jj];
-                    const double xv = (OP == OP_GS) ? a.x[c] : __ldg(a.x + c);
+                    double xv;
+                    if (a.hints) xv = (OP == OP_GS) ? ld_x_hint(a.x + c, pol_last) : ld_x_hint_nc(a.x + c, pol_last);
+                    else xv = (OP == OP_GS) ? a.x[c] : __ldg(a.x + c);
                     if (kNeedDiag && c == row) {
                         diag = v;
                         jd = jj;
@@ -195,13 +265,13 @@ __global__ void __launch_bounds__(kTileWarps * 32, 2) csr_tile_kernel(const Tile
                     if (OP == OP_SPMV) {
                         a.y[row] = sum;
                     } else if (OP == OP_RESID) {
-                        const double r = a.b[row] - sum;
+                        const double r = st.bseg[row - voff] - sum;
                         a.y[row] = r;
                         r2 += r * r;
                     } else if (OP == OP_PADD) {
                         a.y[row] += sum;
                     } else if (OP == OP_JACOBI) {
-                        const double xi = a.x[row], bi = a.b[row];
+                        const double xi = st.xseg[row - voff], bi = st.bseg[row - voff];
                         double xn = xi;
                         if (diag != 0.0) xn = (1.0 - a.omega) * xi + a.omega * ((bi - sum) / diag);
                         a.y[row] = xn;
@@ -212,7 +282,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, 2) csr_tile_kernel(const Tile
                         }
                     } else {
                         if (diag != 0.0) {
-                            const double g = (a.b[row] - sum) / diag;
+                            const double g = (st.bseg[row - voff] - sum) / diag;
                             a.y[row] = (a.omega == 1.0) ? g : a.omega * g + (1.0 - a.omega) * a.y[row];
                         }
                     }
@@ -254,10 +324,10 @@ __global__ void __launch_bounds__(kTileWarps * 32, 2) csr_tile_kernel(const Tile
             }
         }
         __syncwarp();             // every lane is done with this stage before the TMA refills it
-        stage = (stage + 1) % kTileStages;
+        stage = (stage + 1) % STAGES;
     }
     if ((OP == OP_RESID || OP == OP_JACOBI) && a.partials != nullptr) {
-        const double tsum = block_sum<kTileWarps * 32>(r2);
+        const double tsum = block_sum<C::WARPS * 32>(r2);
         if (threadIdx.x == 0) a.partials[blockIdx.x] = tsum;
     }
 }
