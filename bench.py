@@ -155,7 +155,8 @@ def workload_config(grid, ml, ngpus):
             "l2": "inputs larger than L2 (level-0 operator 1.4 GB); no flush needed"}
 
 
-OPS = {0: "spmv(restrict)", 1: "residual", 2: "prolong+add", 3: "jacobi", 4: "gs_wave", 5: "block_jacobi"}
+OPS = {0: "spmv(restrict)", 1: "residual", 2: "prolong+add", 3: "jacobi", 4: "gs_wave", 5: "block_jacobi",
+       6: "coarse_tail(cluster kernel)"}
 
 
 def main():

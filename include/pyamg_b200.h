@@ -125,7 +125,8 @@ int64_t amgb_hierarchy_device_bytes(const amgb_hierarchy *h);
 /* kernels launched by the most recent amgb_solve / amgb_solve_device call */
 int64_t amgb_hierarchy_last_launches(const amgb_hierarchy *h);
 /* One un-graphed cycle with a CUDA-event pair around every operator launch (measurement aid).
- * rec[6k..6k+5] = level, op (0 spmv, 1 residual, 2 prolong+add, 3 jacobi, 4 gs wave, 5 block jacobi),
+ * rec[6k..6k+5] = level, op (0 spmv, 1 residual, 2 prolong+add, 3 jacobi, 4 gs wave, 5 block jacobi,
+ * 6 coarse tail = all levels below in one cluster kernel, rows = #steps),
  * rows, nnz, algorithmic bytes (SURVEY.md 8(d) formulas), milliseconds. */
 int amgb_profile_cycle(amgb_hierarchy *h, int32_t cycle, double *rec, int32_t max_records,
                        int32_t *n_records);

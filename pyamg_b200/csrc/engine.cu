@@ -15,6 +15,7 @@
 #include "../../include/pyamg_b200.h"
 #include "csr_kernels.cuh"
 #include "tile_kernels.cuh"
+#include "tail_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -507,6 +508,36 @@ struct amgb_hierarchy {
     bool use_tiles = true;
     bool use_permute = true;
 
+    // coarse tail: levels >= tail_level run inside one cluster kernel (tail_kernel.cuh)
+    int tail_level = 1 << 30;
+    int tail_csize = 1;
+    long long tail_nnz_limit = 600000;     // AMGB_TAIL_NNZ: levels at most this large run in the cluster tail
+    long long tile_min_nnz = 0;            // AMGB_TILE_MIN_NNZ: smaller launches use the lanes-per-row kernel
+    bool recording = false;
+    std::vector<TailStep> rec;
+    double rec_bytes = 0.0;
+    struct TailProg { TailStep *dev = nullptr; int n = 0, cpl = -1, lvl = -1; double bytes = 0.0; } tail_prog[3];
+
+    int record(int op, int G, int row0, int nrows, const int *rows, const DevCsr *M, const double *x,
+               const double *b, double *y, double omega, double bytes, const double *dense = nullptr, int ncols = 0)
+    {
+        TailStep st;
+        if (op <= T_GS && nrows > 0) {
+            // one pass over the step's rows: as many lanes per row as the cluster can spare, but no more
+            // than the row length warrants (G from pick_lanes is the smallest power of two >= mean length)
+            const int nthreads = tail_csize * kTailThreads;
+            int fill = 1;
+            while (fill < 32 && (long long)fill * 2 * nrows <= nthreads) fill <<= 1;
+            G = std::max(1, std::min(G, fill));
+        }
+        st.op = op; st.G = G; st.row0 = row0; st.nrows = nrows; st.rows = rows;
+        st.Ap = M ? M->Ap : nullptr; st.Aj = M ? M->Aj : nullptr; st.Ax = M ? M->Ax : dense;
+        st.x = x; st.b = b; st.y = y; st.omega = omega; st.ncols = ncols; st.pad_ = 0;
+        rec.push_back(st);
+        rec_bytes += bytes;
+        return AMGB_OK;
+    }
+
     template <typename T>
     int dalloc(T **p, long long count)
     {
@@ -575,14 +606,16 @@ struct amgb_hierarchy {
              double *r = nullptr, double *parts = nullptr)
     {
         if (M.n_rows <= 0) return AMGB_OK;
-        launches++;
         // algorithmic bytes: 12 nnz + 4 (n+1) + 8 per vector pass
         const double vec = (op == OP_SPMV) ? 8.0 * M.n_cols + 8.0 * M.n_rows
                          : (op == OP_PADD) ? 8.0 * M.n_cols + 16.0 * M.n_rows
                          : (op == OP_RESID) ? 24.0 * M.n_rows
                          : (24.0 + (r ? 8.0 : 0.0)) * M.n_rows;
+        if (recording)   // same op codes in TailOp for the five CSR epilogues
+            return record(op, M.lanes, 0, M.n_rows, nullptr, &M, x, b, y, omega, 12.0 * M.nnz + 4.0 * (M.n_rows + 1) + vec);
+        launches++;
         RET(prof_begin(op, M.tiles ? M.tile_G : M.lanes, M.n_rows, M.nnz, 12.0 * M.nnz + 4.0 * (M.n_rows + 1) + vec));
-        if (M.tiles != nullptr) {
+        if (M.tiles != nullptr && (M.nnz >= tile_min_nnz || parts != nullptr)) {
             TileArgs a;
             a.tiles = M.tiles; a.tile_begin = 0; a.tile_end = M.n_tiles;
             a.Ap = M.Ap; a.Aj = M.Aj; a.Ax = M.Ax; a.x = x; a.b = b; a.y = y; a.r = r; a.omega = omega;
@@ -608,11 +641,15 @@ struct amgb_hierarchy {
     {
         const int nrow = (int)(ws.ptr[(size_t)w + 1] - ws.ptr[(size_t)w]);
         if (nrow <= 0) return AMGB_OK;
+        if (recording)
+            return record(T_GS, A.lanes, ws.contiguous ? (int)ws.ptr[(size_t)w] : 0, nrow,
+                          ws.contiguous ? nullptr : ws.rows + ws.ptr[(size_t)w], &A, x, b, x, omega,
+                          12.0 * ws.nnz[(size_t)w] + 36.0 * nrow);
         launches++;
         // one wave of a sweep: its share of 12 nnz + 4 (n+1) + 4 n (row list) + 24 n
         RET(prof_begin(OP_GS, (ws.contiguous && A.tiles) ? A.tile_G : A.lanes, nrow, ws.nnz[(size_t)w],
                        12.0 * ws.nnz[(size_t)w] + 36.0 * nrow));
-        if (ws.contiguous && A.tiles != nullptr) {
+        if (ws.contiguous && A.tiles != nullptr && ws.nnz[(size_t)w] >= tile_min_nnz) {
             TileArgs a;
             a.tiles = A.tiles; a.tile_begin = ws.tile_ptr[(size_t)w]; a.tile_end = ws.tile_ptr[(size_t)w + 1];
             a.Ap = A.Ap; a.Aj = A.Aj; a.Ax = A.Ax; a.x = x; a.b = b; a.y = x; a.r = nullptr; a.omega = omega;
@@ -668,6 +705,9 @@ struct amgb_hierarchy {
     {
         if (coarse_zero) return launch_count_fill(Lc.x, Lc.A.n_rows);
         const int n = coarse_n;
+        if (recording)
+            return record(T_DENSE, 32, 0, n, nullptr, nullptr, Lc.b, nullptr, Lc.x, 0.0, 8.0 * n * n + 16.0 * n,
+                          coarse_pinv, n);
         const int threads = 128, rows_per_block = threads / 32;
         dense_matvec_kernel<<<(n + rows_per_block - 1) / rows_per_block, threads, 0, stream>>>(
             n, n, coarse_pinv, Lc.b, Lc.x);
@@ -678,6 +718,7 @@ struct amgb_hierarchy {
 
     int launch_count_fill(double *x, long long n)
     {
+        if (recording) return n > 0 ? record(T_FILL, 1, 0, (int)n, nullptr, nullptr, nullptr, nullptr, x, 0.0, 8.0 * n) : AMGB_OK;
         launches += (n > 0);
         return launch_fill(x, n, 0.0, stream);
     }
@@ -691,32 +732,92 @@ struct amgb_hierarchy {
         RET(smooth(L, L.pre));                                          // :610
         RET(spmv(OP_RESID, L.A, L.x, L.b, L.r));                        // :612
         RET(spmv(OP_SPMV, L.R, L.r, nullptr, C.b));                     // :614
-        if (lvl == (int)levels.size() - 2) {
-            RET(coarse_solve(C));                                       // :617-618
-        } else {
-            RET(launch_count_fill(C.x, C.A.n_rows));                    // :615
-            if (kind == AMGB_CYCLE_V) {
-                RET(cycle(lvl + 1, AMGB_CYCLE_V, 1));                   // :619-620
-            } else if (kind == AMGB_CYCLE_W) {
-                RET(cycle(lvl + 1, kind, cpl));                         // :621-623
-                RET(cycle(lvl + 1, kind, cpl));
-            } else if (kind == AMGB_CYCLE_F) {
-                RET(cycle(lvl + 1, kind, cpl));                         // :624-627
-                for (int q = 0; q < cpl; q++) RET(cycle(lvl + 1, AMGB_CYCLE_V, 1));
-            } else {
-                return fail(AMGB_EINVAL, "Unrecognized cycle type");    // :658 (TypeError)
-            }
-        }
+        if (lvl + 1 >= tail_level && !recording) RET(run_tail(lvl, kind, cpl));
+        else RET(descend(lvl, kind, cpl));
         cur_level = lvl;
         RET(spmv(OP_PADD, L.P, C.x, nullptr, L.x));                     // :660
         RET(smooth(L, L.post));                                         // :662
         if (L.x != L.x_home) {   // odd number of Jacobi ping-pongs: bring the iterate home
-            CK(cudaMemcpyAsync(L.x_home, L.x, sizeof(double) * (size_t)L.A.n_rows,
-                               cudaMemcpyDeviceToDevice, stream));
-            launches++;
+            if (recording) {
+                RET(record(T_COPY, 1, 0, L.A.n_rows, nullptr, nullptr, L.x, nullptr, L.x_home, 0.0, 16.0 * L.A.n_rows));
+            } else {
+                CK(cudaMemcpyAsync(L.x_home, L.x, sizeof(double) * (size_t)L.A.n_rows,
+                                   cudaMemcpyDeviceToDevice, stream));
+                launches++;
+            }
             std::swap(L.x, L.xalt);
         }
         return AMGB_OK;
+    }
+
+    // everything between restriction and prolongation at level lvl (multilevel.py:615-656)
+    int descend(int lvl, int kind, int cpl)
+    {
+        Level &C = levels[(size_t)lvl + 1];
+        if (lvl == (int)levels.size() - 2) return coarse_solve(C);      // :617-618
+        RET(launch_count_fill(C.x, C.A.n_rows));                        // :615
+        if (kind == AMGB_CYCLE_V) {
+            RET(cycle(lvl + 1, AMGB_CYCLE_V, 1));                       // :619-620
+        } else if (kind == AMGB_CYCLE_W) {
+            RET(cycle(lvl + 1, kind, cpl));                             // :621-623
+            RET(cycle(lvl + 1, kind, cpl));
+        } else if (kind == AMGB_CYCLE_F) {
+            RET(cycle(lvl + 1, kind, cpl));                             // :624-627
+            for (int q = 0; q < cpl; q++) RET(cycle(lvl + 1, AMGB_CYCLE_V, 1));
+        } else {
+            return fail(AMGB_EINVAL, "Unrecognized cycle type");        // :658 (TypeError)
+        }
+        return AMGB_OK;
+    }
+
+    // the same, for levels >= tail_level: recorded once, replayed by one cluster kernel
+    int ensure_tail_prog(int lvl, int kind, int cpl)
+    {
+        TailProg &tp = tail_prog[kind];
+        if (tp.dev == nullptr || tp.cpl != cpl || tp.lvl != lvl) {
+            recording = true;
+            rec.clear();
+            rec_bytes = 0.0;
+            const int rc = descend(lvl, kind, cpl);
+            recording = false;
+            if (rc != AMGB_OK) return rc;
+            RET(upload(&tp.dev, rec.data(), (long long)rec.size()));
+            tp.n = (int)rec.size(); tp.cpl = cpl; tp.lvl = lvl; tp.bytes = rec_bytes;
+            rec.clear();
+        }
+        return AMGB_OK;
+    }
+
+    // programs must exist before a graph capture starts (recording allocates and copies)
+    int prepare_tail(int kind, int cpl)
+    {
+        if (tail_level >= (int)levels.size()) return AMGB_OK;
+        RET(ensure_tail_prog(tail_level - 1, kind, cpl));
+        if (kind == AMGB_CYCLE_F) RET(ensure_tail_prog(tail_level - 1, AMGB_CYCLE_V, 1));
+        return AMGB_OK;
+    }
+
+    int run_tail(int lvl, int kind, int cpl)
+    {
+        TailProg &tp = tail_prog[kind];
+        if (tp.dev == nullptr || tp.cpl != cpl || tp.lvl != lvl)
+            return fail(AMGB_ESTATE, "coarse tail program not prepared");
+        if (tp.n == 0) return AMGB_OK;
+        launches++;
+        cur_level = lvl + 1;
+        RET(prof_begin(6, tail_csize, tp.n, 0, tp.bytes));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)tail_csize);
+        cfg.blockDim = dim3(kTailThreads);
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)tail_csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const TailStep *prog = tp.dev;
+        int nsteps = tp.n;
+        CK(cudaLaunchKernelEx(&cfg, tail_kernel, prog, nsteps));
+        return prof_end();
     }
 
     // ||b - A x||^2 on level 0 -> norms2[slot]   (multilevel.py:545, :567 with the norm fused)
@@ -736,6 +837,7 @@ struct amgb_hierarchy {
         if (levels.size() == 1) {   // multilevel.py:559-561: x = coarse_solver(A, b)
             return coarse_solve(levels[0]);
         }
+        RET(prepare_tail(kind, cpl));
         if (!use_graph) return cycle(0, kind, cpl);
         if (graph[kind] == nullptr || graph_cpl[kind] != cpl) {
             if (graph[kind] != nullptr) { cudaGraphExecDestroy(graph[kind]); graph[kind] = nullptr; }
@@ -868,6 +970,7 @@ int amgb_hierarchy::block_jacobi(Level &L, const Smoother &s)
 {
     const int nb = L.A.n_rows / s.bs;
     for (int it = 0; it < s.iterations; it++) {
+        if (recording) return fail(AMGB_ESTATE, "block Jacobi inside the cluster tail");
         RET(prof_begin(5, L.A.lanes, L.A.n_rows, L.A.nnz,
                        12.0 * L.A.nnz + 4.0 * (L.A.n_rows + 1) + (24.0 + 8.0 * s.bs) * L.A.n_rows));
         RET(dispatch_block_jacobi(s.bs, L.A.lanes, nb, L.A, L.x, L.b, s.Dinv, L.xalt, s.omega, stream));
@@ -1149,6 +1252,47 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
         h->own_stream = true;
     }
     RET(h->finalize_levels());
+    {   // coarse tail: the deepest run of levels whose operators are all small and block-smoother free
+        const char *nt = getenv("AMGB_NO_TAIL");
+        const char *tn = getenv("AMGB_TAIL_NNZ");
+        if (tn && atoll(tn) > 0) h->tail_nnz_limit = atoll(tn);
+        const char *tm = getenv("AMGB_TILE_MIN_NNZ");
+        if (tm && atoll(tm) >= 0) h->tile_min_nnz = atoll(tm);
+        const int nl = (int)h->levels.size();
+        int tl = nl;
+        for (int l = nl - 1; l >= 1; l--) {
+            const Level &L = h->levels[(size_t)l];
+            const bool blocky = L.has_pr && (L.pre.kind == AMGB_SM_BLOCK_JACOBI || L.post.kind == AMGB_SM_BLOCK_JACOBI);
+            if (L.A.nnz > h->tail_nnz_limit || blocky) break;
+            tl = l;
+        }
+        if (!(nt && nt[0] == '1') && tl < nl) {
+            CK(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            const char *cs = getenv("AMGB_TAIL_CLUSTER");
+            int want = cs ? atoi(cs) : 16;
+            h->tail_csize = 1;
+            for (int c = 16; c >= 1; c >>= 1) {
+                if (c > want) continue;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)c); cfg.blockDim = dim3(kTailThreads);
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = (unsigned)c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                int nclusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&nclusters, tail_kernel, &cfg) == cudaSuccess && nclusters >= 1) {
+                    h->tail_csize = c;
+                    break;
+                }
+                cudaGetLastError();
+            }
+            h->tail_level = tl;
+        }
+        const char *vb = getenv("AMGB_VERBOSE");
+        if (vb && vb[0] == '1')
+            fprintf(stderr, "[amgb] levels=%d tail_level=%d cluster=%d tile_cfg=%d ctas/sm=%d hints=%d\n", nl,
+                    h->tail_level < nl ? h->tail_level : -1, h->tail_csize, g_tile_cfg, g_tile_ctas_per_sm, g_tile_hints);
+    }
     if (!h->coarse_zero) RET(h->upload(&h->coarse_pinv, h->coarse_host.data(), (long long)h->coarse_host.size()));
     h->coarse_host.clear();
     for (Level &L : h->levels) {
@@ -1307,7 +1451,8 @@ extern "C" int amgb_solve_device(amgb_hierarchy *h, const double *b_dev, double 
 }
 
 // One un-graphed cycle with a CUDA-event pair around every operator launch of the cycle.
-// rec[k*6 + {0..5}] = level, op (0 spmv/R, 1 residual, 2 prolong+add, 3 jacobi, 4 gs wave, 5 block jacobi),
+// rec[k*6 + {0..5}] = level, op (0 spmv/R, 1 residual, 2 prolong+add, 3 jacobi, 4 gs wave, 5 block jacobi,
+// 6 = the whole coarse tail as one cluster kernel: rows = #steps),
 // rows, nnz, algorithmic bytes, milliseconds.  Returns the number of records (<= max_records).
 extern "C" int amgb_profile_cycle(amgb_hierarchy *h, int32_t cycle, double *rec, int32_t max_records,
                                   int32_t *n_records)
@@ -1317,6 +1462,7 @@ extern "C" int amgb_profile_cycle(amgb_hierarchy *h, int32_t cycle, double *rec,
     if (h->levels.size() < 2) { *n_records = 0; return AMGB_OK; }
     CK(cudaSetDevice(h->device));
     h->prof.clear();
+    RET(h->prepare_tail(cycle, 1));
     h->profiling = true;
     int rc = h->cycle(0, cycle, 1);
     h->profiling = false;

@@ -65,11 +65,14 @@ def test_vcycle_matches_oracle_on_fresh_rhs(name, load_golden):
 
 @pytest.mark.parametrize("env", [{"AMGB_NO_TILES": "1"}, {"AMGB_NO_PERMUTE": "1"},
                                  {"AMGB_NO_TILES": "1", "AMGB_NO_PERMUTE": "1"}, {"AMGB_NO_GRAPH": "1"},
-                                 {"AMGB_TILE_G": "4"}, {"AMGB_TILE_G": "32"}])
+                                 {"AMGB_TILE_G": "4"}, {"AMGB_TILE_G": "32"}, {"AMGB_TILE_CFG": "0"},
+                                 {"AMGB_TILE_CFG": "3", "AMGB_NO_HINTS": "1"}, {"AMGB_NO_TAIL": "1"},
+                                 {"AMGB_TAIL_CLUSTER": "1"}, {"AMGB_TAIL_CLUSTER": "4"}])
 @pytest.mark.parametrize("name", GOLDEN)
 def test_every_kernel_path_matches_reference_golden(name, env, monkeypatch):
-    """The lanes-per-row kernels, the un-permuted layout, the un-graphed cycle and forced lane-group
-    widths of the TMA tile kernel must all reproduce the reference (the env is read per hierarchy)."""
+    """The lanes-per-row kernels, the un-permuted layout, the un-graphed cycle, forced lane-group widths
+    and geometries of the TMA tile kernel, and the cluster tail kernel (off / 1 CTA / 4 CTAs / default 16)
+    must all reproduce the reference (the env is read per hierarchy)."""
     from pyamg_b200.hierarchy_io import load_hierarchy
     from conftest import golden_path
     for k, v in env.items():
