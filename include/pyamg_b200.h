@@ -134,6 +134,19 @@ int amgb_profile_cycle(amgb_hierarchy *h, int32_t cycle, double *rec, int32_t ma
 int amgb_host_alloc(size_t bytes, void **out);
 int amgb_host_free(void *p);
 
+/* ---- (1b) one resident operator (tile kernels) on device vectors ----------------------------- */
+typedef struct amgb_operator amgb_operator;
+/* Upload M (CSR/BSR host arrays) and build its TMA tiles.  wave_ptr (n_waves+1 entries, or NULL) marks
+ * contiguous row ranges that are mutually independent Gauss-Seidel waves (tiles never cross them). */
+int amgb_operator_create(int device, const amgb_matrix *M, const int64_t *wave_ptr, int32_t n_waves,
+                         void *stream, amgb_operator **out);
+void amgb_operator_destroy(amgb_operator *op);
+/* kind: 0 y = M x | 1 y = b - M x (+ |y|^2 -> norm2_out) | 2 y += M x | 3 y = jacobi(x; b, omega), r = b - M x
+ * (r optional) | 4 Gauss-Seidel sweep of wave `wave`, in place on y (pass x == y).  DEVICE pointers; x must
+ * hold M.n_cols entries followed by at least 2 readable doubles (16-byte TMA reads). */
+int amgb_operator_apply(amgb_operator *op, int32_t kind, const double *x, const double *b, double *y,
+                        double *r, double omega, double *norm2_out, int32_t wave);
+
 /* ---- (2) reference-FFI-shaped host entry points --------------------------------------------- */
 /* amg_core.jacobi (relaxation.h:309-346) */
 int amgb_host_jacobi(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
@@ -195,6 +208,12 @@ int64_t amgb_dev_partials_len(int32_t n_rows, int lanes);
 int amgb_dev_dense_matvec(int32_t m, int32_t n, const double *M, const double *x, double *y,
                           void *stream);
 int amgb_dev_fill(double *x, int64_t n, double v, void *stream);
+/* out[i] = in[idx[i]] (halo packing, permuted layouts) */
+int amgb_dev_gather(const double *in, const int32_t *idx, double *out, int64_t n, void *stream);
+/* HOST helper (no CUDA): dependency waves of the sequential sweep over `list` (NULL = 0..n-1);
+ * wave_of[k] is the 1-based wave of list position k. */
+int amgb_wave_schedule(int32_t n, const int32_t *Ap, const int32_t *Aj, const int32_t *list, int64_t m,
+                       int32_t *wave_of, int32_t *n_waves);
 
 #ifdef __cplusplus
 }

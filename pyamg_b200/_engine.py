@@ -48,11 +48,13 @@ SYMBOLS = [
     "amgb_hierarchy_set_coarse_pinv", "amgb_hierarchy_finalize", "amgb_solve",
     "amgb_solve_device", "amgb_hierarchy_num_levels", "amgb_hierarchy_device_bytes",
     "amgb_hierarchy_last_launches", "amgb_profile_cycle", "amgb_host_alloc", "amgb_host_free",
+    "amgb_operator_create", "amgb_operator_destroy", "amgb_operator_apply",
     "amgb_host_jacobi", "amgb_host_gauss_seidel", "amgb_host_sor_gauss_seidel",
     "amgb_host_gauss_seidel_indexed",
     "amgb_host_bsr_jacobi", "amgb_host_block_jacobi", "amgb_host_matvec",
     "amgb_dev_csr_spmv", "amgb_dev_csr_residual", "amgb_dev_csr_spmv_add", "amgb_dev_csr_jacobi",
     "amgb_dev_csr_gs_wave", "amgb_dev_partials_len", "amgb_dev_dense_matvec", "amgb_dev_fill",
+    "amgb_dev_gather", "amgb_wave_schedule",
 ]
 
 
@@ -85,6 +87,11 @@ def lib():
     L.amgb_hierarchy_device_bytes.argtypes = [vp]
     L.amgb_hierarchy_last_launches.argtypes = [vp]
     L.amgb_profile_cycle.argtypes = [vp, i32, c_f64p, i32, c_i32p]
+    L.amgb_operator_create.argtypes = [ctypes.c_int, ctypes.POINTER(Matrix), ctypes.POINTER(ctypes.c_int64), i32,
+                                       vp, ctypes.POINTER(vp)]
+    L.amgb_operator_destroy.argtypes = [vp]
+    L.amgb_operator_destroy.restype = None
+    L.amgb_operator_apply.argtypes = [vp, i32, vp, vp, vp, vp, f64, vp, i32]
     L.amgb_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     L.amgb_host_free.argtypes = [vp]
     ci = ctypes.c_int
@@ -109,6 +116,8 @@ def lib():
     L.amgb_dev_partials_len.argtypes = [i32, ci]
     L.amgb_dev_dense_matvec.argtypes = [i32, i32, vp, vp, vp, vp]
     L.amgb_dev_fill.argtypes = [vp, i64, f64, vp]
+    L.amgb_dev_gather.argtypes = [vp, vp, vp, i64, vp]
+    L.amgb_wave_schedule.argtypes = [i32, c_i32p, c_i32p, c_i32p, i64, c_i32p, c_i32p]
     _lib = L
     return L
 

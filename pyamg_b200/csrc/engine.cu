@@ -434,7 +434,6 @@ static void build_tiles(const HostCsr &A, int G, const std::vector<long long> *b
 {
     const int n = A.n_rows, rpp = 32 / G;
     tiles.clear();
-    if (tile_ptr) tile_ptr->assign(1, 0);
     size_t bi = 1;                       // next break to honour: (*breaks)[bi]
     int r = 0;
     while (r < n) {
@@ -460,10 +459,17 @@ static void build_tiles(const HostCsr &A, int G, const std::vector<long long> *b
         }
         tiles.push_back(TileDesc{r, A.Ap[(size_t)r]});
         r = e;
-        if (tile_ptr && breaks && bi < breaks->size() && r == (*breaks)[bi]) tile_ptr->push_back((int)tiles.size());
     }
     tiles.push_back(TileDesc{n, A.Ap[(size_t)n]});       // sentinel
-    if (tile_ptr && tile_ptr->back() != (int)tiles.size() - 1) tile_ptr->push_back((int)tiles.size() - 1);
+    if (tile_ptr && breaks) {
+        // tile range of every [breaks[w], breaks[w+1]) row range (empty ranges allowed): tiles start on breaks
+        tile_ptr->clear();
+        size_t t = 0;
+        for (size_t w = 0; w < breaks->size(); w++) {
+            while (t + 1 < tiles.size() && tiles[t].row0 < (*breaks)[w]) t++;
+            tile_ptr->push_back((int)t);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1486,6 +1492,118 @@ extern "C" int amgb_profile_cycle(amgb_hierarchy *h, int32_t cycle, double *rec,
 }
 
 // ------------------------------------------------------------------------------------------
+// C ABI (1b): one resident operator with the tile kernels -- the building block of the multi-GPU layer
+// (pyamg_b200/dist.py) and of Krylov-style callers that keep their vectors on the device.
+// ------------------------------------------------------------------------------------------
+struct amgb_operator {
+    amgb_hierarchy *pool = nullptr;      // owns the device allocations
+    DevCsr M;
+    WaveSchedule waves;                  // optional contiguous wave ranges (Gauss-Seidel)
+    double *partials = nullptr;
+};
+
+extern "C" int amgb_operator_create(int device, const amgb_matrix *Min, const int64_t *wave_ptr, int32_t n_waves,
+                                    void *stream, amgb_operator **out)
+{
+    if (out == nullptr) return fail(AMGB_EINVAL, "out is null");
+    *out = nullptr;
+    amgb_hierarchy *pool = nullptr;
+    RET(amgb_hierarchy_create(device, &pool));
+    std::unique_ptr<amgb_operator> op(new amgb_operator());
+    op->pool = pool;
+    auto bail = [&](int rc) { amgb_hierarchy_destroy(pool); return rc; };
+    HostCsr H;
+    int rc = to_host_csr(Min, H, "M");
+    if (rc != AMGB_OK) return bail(rc);
+    if (stream != nullptr) pool->stream = (cudaStream_t)stream;
+    else {
+        if (cudaStreamCreateWithFlags(&pool->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(AMGB_ECUDA, "stream"));
+        pool->own_stream = true;
+    }
+    if (wave_ptr != nullptr && n_waves > 0) {
+        WaveSchedule &W = op->waves;
+        W.ptr.assign(wave_ptr, wave_ptr + n_waves + 1);
+        if (W.ptr.front() != 0 || W.ptr.back() > H.n_rows) return bail(fail(AMGB_EINVAL, "wave_ptr out of range"));
+        for (int w = 0; w < n_waves; w++)
+            if (W.ptr[(size_t)w + 1] < W.ptr[(size_t)w]) return bail(fail(AMGB_EINVAL, "wave_ptr not monotone"));
+        W.contiguous = true;
+        W.nnz.assign((size_t)n_waves, 0);
+        for (int w = 0; w < n_waves; w++)
+            W.nnz[(size_t)w] = H.Ap[(size_t)W.ptr[(size_t)w + 1]] - H.Ap[(size_t)W.ptr[(size_t)w]];
+        std::vector<long long> breaks(W.ptr);
+        if (breaks.back() != H.n_rows) breaks.push_back(H.n_rows);
+        rc = pool->upload_csr(H, op->M, &breaks, &W.tile_ptr);
+        if (!pool->use_tiles) W.tile_ptr.clear();
+    } else {
+        rc = pool->upload_csr(H, op->M);
+    }
+    if (rc != AMGB_OK) return bail(rc);
+    rc = pool->dalloc(&op->partials, std::max<long long>(pool->partials_len(op->M), 1));
+    if (rc != AMGB_OK) return bail(rc);
+    *out = op.release();
+    return AMGB_OK;
+}
+
+extern "C" void amgb_operator_destroy(amgb_operator *op)
+{
+    if (op == nullptr) return;
+    amgb_hierarchy_destroy(op->pool);
+    delete op;
+}
+
+// kind: 0 y = M x | 1 y = b - M x (norm2_out, if given, receives |y|^2) | 2 y += M x |
+//       3 y = jacobi(x; b, omega), r (optional) = b - M x | 4 Gauss-Seidel on wave `wave` of y (= x) in place.
+// All pointers are DEVICE pointers; x must have M.n_cols entries (+2 readable doubles of padding).
+extern "C" int amgb_operator_apply(amgb_operator *op, int32_t kind, const double *x, const double *b, double *y,
+                                   double *r, double omega, double *norm2_out, int32_t wave)
+{
+    if (op == nullptr) return fail(AMGB_EINVAL, "null operator");
+    amgb_hierarchy *h = op->pool;
+    CK(cudaSetDevice(h->device));
+    if (kind < 0 || kind > 4) return fail(AMGB_EINVAL, "unknown operator kind");
+    if (kind == OP_GS) {
+        if (wave < 0 || (size_t)wave + 1 >= op->waves.ptr.size()) return fail(AMGB_EINVAL, "wave index out of range");
+        return h->gs_wave(op->M, op->waves, wave, y, b, omega);
+    }
+    double *parts = (norm2_out != nullptr && (kind == OP_RESID || kind == OP_JACOBI)) ? op->partials : nullptr;
+    RET(h->spmv(kind, op->M, x, b, y, omega, r, parts));
+    if (parts != nullptr) {
+        reduce_partials_kernel<<<1, 1024, 0, h->stream>>>(parts, (int)h->partials_len(op->M), norm2_out);
+        CK(cudaGetLastError());
+    }
+    return AMGB_OK;
+}
+
+// Dependency waves of a sequential sweep (host only, no CUDA): wave_of[k] (1-based) for list position k.
+// The multi-GPU layer uses it to give every rank the same global wave structure.
+extern "C" int amgb_wave_schedule(int32_t n, const int32_t *Ap, const int32_t *Aj, const int32_t *list, int64_t m,
+                                  int32_t *wave_of, int32_t *n_waves)
+{
+    if (Ap == nullptr || wave_of == nullptr || n < 0 || m < 0) return fail(AMGB_EINVAL, "wave_schedule: bad arguments");
+    std::vector<int> wwave((size_t)n, 0), rwave((size_t)n, 0);
+    int maxw = 0;
+    for (int64_t k = 0; k < m; k++) {
+        const int i = list ? list[k] : (int)k;
+        if (i < 0 || i >= n) return fail(AMGB_EINVAL, "wave_schedule: row index out of range");
+        int wv = std::max(rwave[(size_t)i], wwave[(size_t)i]);
+        for (int jj = Ap[i]; jj < Ap[i + 1]; jj++) {
+            const int j = Aj[jj];
+            if (j != i && j >= 0 && j < n) wv = std::max(wv, wwave[(size_t)j]);
+        }
+        wv += 1;
+        wave_of[k] = wv;
+        wwave[(size_t)i] = wv;
+        for (int jj = Ap[i]; jj < Ap[i + 1]; jj++) {
+            const int j = Aj[jj];
+            if (j != i && j >= 0 && j < n) rwave[(size_t)j] = std::max(rwave[(size_t)j], wv);
+        }
+        maxw = std::max(maxw, wv);
+    }
+    if (n_waves) *n_waves = maxw;
+    return AMGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // C ABI (3): device kernels
 // ------------------------------------------------------------------------------------------
 static int resolve_lanes(int lanes, int32_t n_rows, const int32_t *Ap, cudaStream_t s, int *out)
@@ -1575,6 +1693,15 @@ extern "C" int amgb_dev_dense_matvec(int32_t m, int32_t n, const double *M, cons
 {
     if (m <= 0) return AMGB_OK;
     dense_matvec_kernel<<<(m + 3) / 4, 128, 0, (cudaStream_t)stream>>>(m, n, M, x, y);
+    CK(cudaGetLastError());
+    return AMGB_OK;
+}
+
+extern "C" int amgb_dev_gather(const double *in, const int32_t *idx, double *out, int64_t n, void *stream)
+{
+    if (n <= 0) return AMGB_OK;
+    const long long grid = std::min<long long>((n + 255) / 256, (long long)148 * 16);
+    gather_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(in, idx, out, n);
     CK(cudaGetLastError());
     return AMGB_OK;
 }

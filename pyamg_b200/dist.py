@@ -1,0 +1,474 @@
+"""Multi-GPU V-cycle: the big (fine) levels row-partitioned across ranks, the rest replicated.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  The reference has no
+distributed path; this layer adds the decomposition the north star names:
+
+* every level whose operator has more than ``dist_nnz`` stored entries is partitioned into contiguous
+  row blocks (natural ordering of that level: gallery grids number the last dimension fastest, so a
+  block is a slab and its halo one grid plane per side); all coarser levels are REPLICATED -- every
+  rank runs the same cycle on them (no broadcast needed), "replicas only" below the partition;
+* before every operator application that gathers a partitioned vector (Gauss-Seidel wave, Jacobi
+  sweep, residual, restriction of a partitioned coarse level, prolongation from one) the ranks
+  exchange the boundary entries of that vector with ONE all-gather (``ncclAllGather``): rank p packs
+  the entries other ranks reference (``send_idx``), the gathered blocks land directly behind the
+  owned part of the vector, and the local operator's column indices already point there -- no unpack;
+* restriction onto a replicated level is a partial product ``R[:, owned] r_owned`` followed by
+  ``ncclAllReduce(sum)``; the residual norm of the stop test is an 8-byte all-reduce.
+
+Numerics: local rows keep the reference's per-row entry order, Gauss-Seidel waves are the GLOBAL
+dependency waves, so the iterates equal the single-GPU ones except for the summation order of the
+all-reduced restriction (1e-16 relative; parity bar 1e-12).
+
+The arithmetic is delegated to a backend (``GpuBackend`` here: sm_100a tile kernels through
+``amgb_operator_*`` + NCCL).  The partitioning / halo-plan code is pure NumPy and is exercised on
+CPU with gloo (tests/test_dist_cpu.py) against the sequential oracle.
+"""
+import ctypes
+
+import numpy as np
+from scipy import sparse
+
+from . import _engine as E
+from .relaxation import smoothing
+
+OP_SPMV, OP_RESID, OP_PADD, OP_JACOBI, OP_GS = 0, 1, 2, 3, 4
+
+
+def block_bounds(n, world):
+    """Contiguous, balanced row blocks: rank p owns [bounds[p], bounds[p+1])."""
+    return np.array([(n * p) // world for p in range(world + 1)], dtype=np.int64)
+
+
+def coarse_bounds_from_splitting(splitting, fine_bounds):
+    """Coarse blocks aligned with the fine slabs: rank p owns the C points of its fine rows."""
+    csum = np.concatenate([[0], np.cumsum(np.asarray(splitting, dtype=np.int64))])
+    return csum[fine_bounds]
+
+
+def wave_schedule(A, order=None):
+    """1-based dependency-wave id of every position of the sequential sweep over `order` (engine's rule)."""
+    A = sparse.csr_array(A)
+    n = A.shape[0]
+    Ap = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    Aj = np.ascontiguousarray(A.indices, dtype=np.int32)
+    m = n if order is None else len(order)
+    lst = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+    wave = np.empty(m, dtype=np.int32)
+    nw = ctypes.c_int32(0)
+    E.check(E.lib().amgb_wave_schedule(n, E.i32p(Ap), E.i32p(Aj), None if lst is None else E.i32p(lst), m,
+                                       E.i32p(wave), ctypes.byref(nw)))
+    return wave, int(nw.value)
+
+
+class _Space:
+    """A partitioned vector space (one hierarchy level): ownership, local order, halo plan."""
+
+    def __init__(self, n, bounds, rank):
+        self.n, self.bounds, self.rank = n, np.asarray(bounds, dtype=np.int64), rank
+        self.world = len(bounds) - 1
+        self.lo, self.hi = int(bounds[rank]), int(bounds[rank + 1])
+        self.n_own = self.hi - self.lo
+        self.local_of_owned = np.arange(self.n_own, dtype=np.int64)   # owned global j -> local index (j - lo)
+        self.needs = [set() for _ in range(self.world)]              # filled by add_reader
+        self._remote = [[] for _ in range(self.world)]
+
+    def add_reader(self, M, row_bounds):
+        """Matrix M (rows partitioned by row_bounds) gathers vectors of this space: record, for every
+        rank q, the columns it references but does not own."""
+        M = sparse.csr_array(M)
+        for q in range(self.world):
+            r0, r1 = int(row_bounds[q]), int(row_bounds[q + 1])
+            cols = M.indices[M.indptr[r0]:M.indptr[r1]]
+            lo, hi = int(self.bounds[q]), int(self.bounds[q + 1])
+            rem = cols[(cols < lo) | (cols >= hi)]
+            if rem.size:
+                self._remote[q].append(np.unique(rem))
+
+    def finish(self):
+        """Boundary sets B_p (what each rank must send), padded size, and the send list of this rank."""
+        need = [np.unique(np.concatenate(r)) if r else np.empty(0, dtype=np.int64) for r in self._remote]
+        allneed = np.unique(np.concatenate(need)) if any(x.size for x in need) else np.empty(0, dtype=np.int64)
+        self.B = [allneed[(allneed >= self.bounds[p]) & (allneed < self.bounds[p + 1])].astype(np.int64)
+                  for p in range(self.world)]
+        self.maxB = max(1, max(len(b) for b in self.B))
+        self.n_ext = self.n_own + self.world * self.maxB
+        del self._remote
+
+    def set_local_order(self, perm_global_rows):
+        """perm_global_rows: owned GLOBAL indices in the order they are stored locally."""
+        pos = np.empty(self.n_own, dtype=np.int64)
+        pos[np.asarray(perm_global_rows, dtype=np.int64) - self.lo] = np.arange(self.n_own)
+        self.local_of_owned = pos
+        self.order = np.asarray(perm_global_rows, dtype=np.int64)
+
+    def send_idx(self):
+        return self.local_of_owned[self.B[self.rank] - self.lo].astype(np.int32)
+
+    def map_cols(self, cols):
+        """global column ids -> indices into this rank's extended vector [owned | gathered blocks]."""
+        cols = np.asarray(cols, dtype=np.int64)
+        out = np.empty(cols.shape, dtype=np.int64)
+        own = (cols >= self.lo) & (cols < self.hi)
+        out[own] = self.local_of_owned[cols[own] - self.lo]
+        rem = ~own
+        if rem.any():
+            rc = cols[rem]
+            q = np.searchsorted(self.bounds, rc, side="right") - 1
+            off = np.empty(rc.shape, dtype=np.int64)
+            for p in np.unique(q):
+                m = q == p
+                k = np.searchsorted(self.B[p], rc[m])
+                if np.any(k >= len(self.B[p])) or np.any(self.B[p][np.minimum(k, len(self.B[p]) - 1)] != rc[m]):
+                    raise RuntimeError("halo plan is missing a referenced column")
+                off[m] = self.n_own + p * self.maxB + k
+            out[rem] = off
+        return out
+
+
+class _Replicated:
+    """A replicated vector space (every rank holds all n entries)."""
+
+    def __init__(self, n):
+        self.n = self.n_own = self.n_ext = n
+        self.world = 1
+
+    def map_cols(self, cols):
+        return np.asarray(cols, dtype=np.int64)
+
+
+def _local_rows(M, rows_global, colspace, n_cols_ext):
+    """Rows `rows_global` (in that order) of M with columns renumbered into colspace's extended layout."""
+    M = sparse.csr_array(M)
+    rows_global = np.asarray(rows_global, dtype=np.int64)
+    starts, ends = M.indptr[rows_global], M.indptr[rows_global + 1]
+    lens = (ends - starts).astype(np.int64)
+    indptr = np.zeros(len(rows_global) + 1, dtype=np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    take = np.repeat(starts.astype(np.int64) - indptr[:-1], lens) + np.arange(indptr[-1], dtype=np.int64)
+    cols = colspace.map_cols(M.indices[take])
+    return sparse.csr_array((np.ascontiguousarray(M.data[take], dtype=np.float64), cols.astype(np.int32),
+                             indptr.astype(np.int32)), shape=(len(rows_global), n_cols_ext))
+
+
+class DistLevel:
+    pass
+
+
+def build_plan(ml, world, rank, n_dist=None, dist_nnz=20_000_000):
+    """Partition the leading levels of hierarchy `ml` for (world, rank). Returns (levels, n_dist).
+
+    Pure host code; every rank runs it on the same (replicated) host hierarchy and keeps its part."""
+    nl = len(ml.levels)
+    if n_dist is None:
+        n_dist = 0
+        while n_dist < nl - 1 and ml.levels[n_dist].A.nnz > dist_nnz:
+            n_dist += 1
+        n_dist = max(n_dist, 1) if nl > 1 else 0
+    n_dist = min(n_dist, nl - 1)
+    # ownership: level 0 in balanced slabs; a coarse level follows its parent's slabs when a C/F
+    # splitting is known (classical AMG), else balanced blocks
+    bounds = [block_bounds(ml.levels[0].A.shape[0], world)]
+    for l in range(1, n_dist):
+        sp = getattr(ml.levels[l - 1], "splitting", None)
+        if sp is not None and len(sp) == ml.levels[l - 1].A.shape[0] and int(np.sum(sp)) == ml.levels[l].A.shape[0]:
+            bounds.append(coarse_bounds_from_splitting(sp, bounds[l - 1]))
+        else:
+            bounds.append(block_bounds(ml.levels[l].A.shape[0], world))
+    spaces = [_Space(ml.levels[l].A.shape[0], bounds[l], rank) for l in range(n_dist)]
+    for l in range(n_dist):
+        lvl = ml.levels[l]
+        spaces[l].add_reader(lvl.A, bounds[l])                         # smoother / residual gather x_l
+        if l + 1 < n_dist:
+            spaces[l].add_reader(lvl.R, bounds[l + 1])                 # restriction gathers r_l
+            spaces[l + 1].add_reader(lvl.P, bounds[l])                 # prolongation gathers x_{l+1}
+    for s in spaces:
+        s.finish()
+
+    out = []
+    for l in range(n_dist):
+        lvl, sp = ml.levels[l], spaces[l]
+        D = DistLevel()
+        D.space = sp
+        keep = []
+        D.pre = smoothing.describe(getattr(lvl, "presmoother", None), lvl.A, keep)
+        D.post = smoothing.describe(getattr(lvl, "postsmoother", None), lvl.A, keep)
+        D._keep = keep
+        for S in (D.pre, D.post):
+            if S.kind == E.SM_BLOCK_JACOBI:
+                raise NotImplementedError("block Jacobi on a partitioned level")
+        # global dependency waves of the (pre) Gauss-Seidel sweep decide the local storage order
+        D.wave_ptr = None
+        gs = D.pre if D.pre.kind == E.SM_GAUSS_SEIDEL else (D.post if D.post.kind == E.SM_GAUSS_SEIDEL else None)
+        owned = np.arange(sp.lo, sp.hi, dtype=np.int64)
+        if gs is not None:
+            n = lvl.A.shape[0]
+            lst = None
+            if gs.n_indices:
+                lst = np.ctypeslib.as_array(gs.indices, shape=(gs.n_indices,)).copy()
+                if len(lst) != n or len(np.unique(lst)) != n:
+                    raise NotImplementedError("partitioned Gauss-Seidel needs a row list that is a permutation")
+            for other in (D.pre, D.post):
+                if other.kind == E.SM_GAUSS_SEIDEL and other is not gs:
+                    lo = None if not other.n_indices else np.ctypeslib.as_array(other.indices, shape=(other.n_indices,))
+                    same = (lo is None and lst is None) or (lo is not None and lst is not None and np.array_equal(lo, lst))
+                    if not same:
+                        raise NotImplementedError("pre/post Gauss-Seidel with different row lists on a partitioned level")
+            wave_pos, nw = wave_schedule(lvl.A, lst)
+            wave_of_row = np.empty(n, dtype=np.int32)
+            wave_of_row[np.arange(n) if lst is None else lst] = wave_pos
+            w_own = wave_of_row[sp.lo:sp.hi]
+            order = np.argsort(w_own, kind="stable")
+            owned = owned[order]
+            D.wave_ptr = np.concatenate([[0], np.cumsum(np.bincount(w_own - 1, minlength=nw))]).astype(np.int64)
+            D.n_waves = nw
+        sp.set_local_order(owned)
+        out.append(D)
+    for l in range(n_dist):
+        lvl, sp, D = ml.levels[l], spaces[l], out[l]
+        D.A = _local_rows(lvl.A, sp.order, sp, sp.n_ext)
+        D.send_idx = sp.send_idx()
+        if l + 1 < n_dist:
+            nxt = spaces[l + 1]
+            D.next_partitioned = True
+            D.P = _local_rows(lvl.P, sp.order, nxt, nxt.n_ext)
+            D.R = _local_rows(lvl.R, nxt.order, sp, sp.n_ext)
+        else:
+            D.next_partitioned = False
+            nc = lvl.P.shape[1]
+            D.P = _local_rows(lvl.P, sp.order, _Replicated(nc), nc)
+            # partial restriction: all coarse rows, owned fine columns only (local numbering)
+            Rcsc = sparse.csr_array(lvl.R)[:, sp.lo:sp.hi].tocsr()
+            Rcsc.indices = sp.local_of_owned[Rcsc.indices].astype(np.int32)
+            D.R = sparse.csr_array((Rcsc.data, Rcsc.indices, Rcsc.indptr), shape=(nc, sp.n_own))
+    return out, n_dist
+
+
+# ------------------------------------------------------------------------------------------------
+# cycle driver (backend-agnostic)
+# ------------------------------------------------------------------------------------------------
+class DistributedSolver:
+    """V-cycles with the leading levels partitioned across ``backend.world`` ranks.
+
+    ``solve_device``-style use: ``load(b_global)``, ``cycles(k)``, ``gather_x()``; residual norms are
+    all-reduced.  Only V-cycles (the partitioned recursion has one coarse visit per level)."""
+
+    def __init__(self, ml, backend, n_dist=None, dist_nnz=20_000_000):
+        from .multilevel import MultilevelSolver
+        self.ml, self.be = ml, backend
+        self.plan, self.n_dist = build_plan(ml, backend.world, backend.rank, n_dist=n_dist, dist_nnz=dist_nnz)
+        be = backend
+        self.lv = []
+        for D in self.plan:
+            sp = D.space
+            L = DistLevel()
+            L.D, L.sp = D, sp
+            L.A = be.operator(D.A, D.wave_ptr)
+            L.P = be.operator(D.P, None)
+            L.R = be.operator(D.R, None)
+            L.send_idx = be.index(D.send_idx)
+            L.send = be.vector(sp.maxB)
+            L.x, L.xalt, L.b, L.r = (be.vector(sp.n_ext) for _ in range(4))
+            self.lv.append(L)
+        # replicated remainder: an ordinary engine hierarchy on every rank
+        self.sub = backend.sub_solver(MultilevelSolver, ml, self.n_dist)
+        nrep = ml.levels[self.n_dist].A.shape[0]
+        self.bc_rep, self.xc_rep = be.vector(nrep), be.vector(nrep)
+        self.norm2 = be.vector(1)
+        self.launches = 0
+
+    # -- communication --------------------------------------------------------------------------
+    def halo(self, L, v):
+        """All-gather the boundary entries of partitioned vector v into its halo region."""
+        if self.be.world == 1:
+            return
+        self.be.gather(v, L.send_idx, L.send, len(L.D.send_idx))
+        self.be.allgather(L.send, v, L.sp.n_own, L.sp.maxB)
+
+    # -- smoothers --------------------------------------------------------------------------------
+    def smooth(self, L, S):
+        be = self.be
+        if S.kind == E.SM_NONE:
+            return
+        if S.kind == E.SM_JACOBI:
+            for _ in range(S.iterations):
+                self.halo(L, L.x)
+                be.apply(L.A, OP_JACOBI, L.x, L.b, L.xalt, omega=S.omega)
+                L.x, L.xalt = L.xalt, L.x
+            return
+        nw = L.D.n_waves
+        om = 1.0 if S.sweep == E.SWEEPS["symmetric"] else S.omega
+        for _ in range(S.iterations):
+            seq = []
+            if S.sweep in (E.SWEEPS["forward"], E.SWEEPS["symmetric"]):
+                seq += list(range(nw))
+            if S.sweep == E.SWEEPS["backward"]:
+                seq += list(range(nw - 1, -1, -1))
+            if S.sweep == E.SWEEPS["symmetric"]:
+                seq += list(range(nw - 2, -1, -1))      # the repeated middle wave is idempotent
+            for w in seq:
+                self.halo(L, L.x)
+                be.apply(L.A, OP_GS, L.x, L.b, L.x, omega=om, wave=w)
+
+    # -- one V-cycle on partitioned level l (multilevel.py:584-662) --------------------------------
+    def cycle(self, l):
+        be, L = self.be, self.lv[l]
+        D = L.D
+        self.smooth(L, D.pre)
+        self.halo(L, L.x)
+        be.apply(L.A, OP_RESID, L.x, L.b, L.r)
+        if D.next_partitioned:
+            C = self.lv[l + 1]
+            self.halo(L, L.r)
+            be.apply(L.R, OP_SPMV, L.r, None, C.b)
+            be.fill(C.x, 0.0)
+            self.cycle(l + 1)
+            self.halo(C, C.x)
+            be.apply(L.P, OP_PADD, C.x, None, L.x)
+        else:
+            be.apply(L.R, OP_SPMV, L.r, None, self.bc_rep)
+            be.allreduce(self.bc_rep)
+            be.fill(self.xc_rep, 0.0)
+            self.sub.cycle_device(self.bc_rep, self.xc_rep)
+            be.apply(L.P, OP_PADD, self.xc_rep, None, L.x)
+        self.smooth(L, D.post)
+
+    # -- public -------------------------------------------------------------------------------------
+    def load(self, b_global, x0_global=None):
+        L = self.lv[0]
+        sp = L.sp
+        self.be.set_owned(L.b, np.asarray(b_global, dtype=np.float64)[sp.order])
+        if x0_global is None:
+            self.be.fill(L.x, 0.0)
+        else:
+            self.be.set_owned(L.x, np.asarray(x0_global, dtype=np.float64)[sp.order])
+
+    def residual_norm(self):
+        L = self.lv[0]
+        self.halo(L, L.x)
+        self.be.apply(L.A, OP_RESID, L.x, L.b, L.r, norm2=self.norm2)
+        self.be.allreduce(self.norm2)
+        return self.norm2
+
+    def cycles(self, k, norms=None):
+        """k V-cycles; if `norms` (backend vector, k+1 slots) is given the residual norms^2 are stored."""
+        if norms is not None:
+            self.be.copy_scalar(self.residual_norm(), norms, 0)
+        for it in range(1, k + 1):
+            if self.n_dist == 0:
+                raise RuntimeError("nothing is partitioned")
+            self.cycle(0)
+            if norms is not None:
+                self.be.copy_scalar(self.residual_norm(), norms, it)
+
+    def gather_x(self):
+        """The full iterate on every rank (host array, original numbering)."""
+        L = self.lv[0]
+        sp = L.sp
+        own = self.be.get_owned(L.x, sp.n_own)
+        nat = np.empty(sp.n_own, dtype=np.float64)
+        nat[sp.order - sp.lo] = own                      # back to the natural order of the owned block
+        return self.be.allgather_host(nat)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU backend: engine tile kernels + NCCL
+# ------------------------------------------------------------------------------------------------
+class GpuBackend:
+    """torch CUDA tensors for memory, ``amgb_operator_*`` kernels for arithmetic, torch.distributed
+    (NCCL) for the collectives.  world == 1 works without an initialised process group."""
+
+    def __init__(self, device=0, rank=0, world=1, group=None):
+        import torch
+        self.torch = torch
+        self.rank, self.world, self.group = rank, world, group
+        self.device = torch.device("cuda", device)
+        self.dev_index = device
+        E.require_gpu()
+        self.L = E.lib()
+        self.stream = torch.cuda.current_stream(self.device)
+        self._ops = []
+        self.kernel_launches = 0
+
+    # memory
+    def vector(self, n):
+        return self.torch.zeros(int(n) + 2, dtype=self.torch.float64, device=self.device)   # +2: TMA padding
+
+    def index(self, idx):
+        return self.torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int32)).to(self.device)
+
+    def fill(self, v, val):
+        v.fill_(val)
+
+    def set_owned(self, v, host):
+        v[:len(host)].copy_(self.torch.from_numpy(np.ascontiguousarray(host)))
+
+    def get_owned(self, v, n):
+        return v[:n].cpu().numpy()
+
+    def copy_scalar(self, src, dst, slot):
+        dst[slot:slot + 1].copy_(src[:1])
+
+    # operators
+    def operator(self, M, wave_ptr):
+        keep = []
+        Mc = E.as_matrix(M, keep)
+        h = ctypes.c_void_p()
+        wp, nw = None, 0
+        if wave_ptr is not None:
+            wp = np.ascontiguousarray(wave_ptr, dtype=np.int64)
+            nw = len(wp) - 1
+        E.check(self.L.amgb_operator_create(self.dev_index, ctypes.byref(Mc),
+                                            None if wp is None else wp.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                            nw, ctypes.c_void_p(self.stream.cuda_stream), ctypes.byref(h)))
+        self._ops.append(h)
+        return h
+
+    def apply(self, op, kind, x, b, y, r=None, omega=0.0, wave=-1, norm2=None):
+        P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        E.check(self.L.amgb_operator_apply(op, kind, P(x), P(b), P(y), P(r), float(omega), P(norm2), int(wave)))
+        self.kernel_launches += 1
+
+    def gather(self, v, idx, out, n):
+        if n > 0:
+            E.check(self.L.amgb_dev_gather(ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(idx.data_ptr()),
+                                           ctypes.c_void_p(out.data_ptr()), int(n),
+                                           ctypes.c_void_p(self.stream.cuda_stream)))
+            self.kernel_launches += 1
+
+    # collectives
+    def allgather(self, send, v, n_own, maxB):
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(v[n_own:n_own + self.world * maxB], send[:maxB], group=self.group)
+
+    def allreduce(self, v):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(v[:v.numel() - 2], group=self.group)
+
+    def allgather_host(self, own):
+        """Concatenation of every rank's owned block (host array) -- result path, not timed."""
+        if self.world == 1:
+            return own
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, own, group=self.group)
+        return np.concatenate(parts)
+
+    def sub_solver(self, MultilevelSolver, ml, first):
+        sub = MultilevelSolver(list(ml.levels[first:]), coarse_solver="pinv", device=self.dev_index,
+                               stream=self.stream.cuda_stream)
+        sub.coarse_solver = ml.coarse_solver
+        be = self
+
+        class _Sub:
+            def cycle_device(self_inner, b, x):
+                E.check(be.L.amgb_solve_device(sub.handle, ctypes.c_void_p(b.data_ptr()), ctypes.c_void_p(x.data_ptr()),
+                                               1, 0, 1, None))
+                be.kernel_launches += sub.last_launches()
+        self._sub = sub
+        return _Sub()
+
+    def close(self):
+        for h in self._ops:
+            self.L.amgb_operator_destroy(h)
+        self._ops = []

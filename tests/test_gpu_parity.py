@@ -272,3 +272,24 @@ def test_linearity_and_larger_random_hierarchy_properties():
     assert (res[-1] / res[0]) ** (1.0 / (len(res) - 1)) < 0.3
     cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.P)
     assert relerr(ml.solve(b1, tol=0, maxiter=3), cyc.solve(b1, tol=0, maxiter=3)) < TOL
+
+
+@pytest.mark.parametrize("name,n_dist", [("cfg3_rs_mcgs_poisson3d", 2), ("cfg4_sa_jacobi_aniso2d", 3),
+                                         ("cfg1_rs_gs_poisson2d", 1)])
+def test_distributed_layer_single_rank_on_gpu(name, n_dist, load_golden):
+    """pyamg_b200.dist with the GPU backend at world_size 1 (tile kernels through amgb_operator_*, local
+    wave-major order, replicated sub-hierarchy): same iterates as the oracle."""
+    from pyamg_b200.dist import DistributedSolver, GpuBackend
+    ml, ex = load_golden(name)
+    be = GpuBackend(device=0, rank=0, world=1)
+    ds = DistributedSolver(ml, be, n_dist=n_dist)
+    ds.load(ex["b"])
+    norms = be.vector(5)
+    ds.cycles(4, norms=norms)
+    x = ds.gather_x()
+    cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.P)
+    res = []
+    xo = cyc.solve(ex["b"], tol=0, maxiter=4, residuals=res)
+    assert relerr(x, xo) < TOL
+    assert np.allclose(np.sqrt(norms[:5].cpu().numpy()), res, rtol=1e-9)
+    be.close()
