@@ -283,6 +283,10 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set: keep stdout to the one JSON line
+        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("AMGB_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["AMGB_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from pyamg_b200 import _engine as E
 
@@ -293,6 +297,9 @@ def main():
     assert stream != 0
     ml = build_hierarchy(grid, stream=stream, device=local)
     n = ml.levels[0].A.shape[0]
+    if world > 1:
+        run_distributed(args, grid, ml, local, rank, world, tstream)
+        return
     t0 = time.time()
     dev_bytes = ml.upload()
     log(f"upload + wave scheduling {time.time() - t0:.1f}s, {dev_bytes / 1e9:.2f} GB in HBM")
@@ -308,10 +315,6 @@ def main():
 
     def cycles(k):
         E.check(L.amgb_solve_device(h, P(b), P(x), k, 0, 1, P(norms)))
-
-    if world > 1:
-        run_distributed(args, grid, ml, local, rank, world, tstream)
-        return
 
     # ---- device-resident throughput -------------------------------------------------------
     cycles(args.warmup)

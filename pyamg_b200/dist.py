@@ -385,7 +385,13 @@ class GpuBackend:
         self.dev_index = device
         E.require_gpu()
         self.L = E.lib()
+        # every torch op, NCCL collective and engine kernel of this backend must share ONE stream; the
+        # engine treats a NULL handle as "create my own", so never hand it torch's default stream
+        torch.cuda.set_device(self.device)
         self.stream = torch.cuda.current_stream(self.device)
+        if self.stream.cuda_stream == 0:
+            self.stream = torch.cuda.Stream(device=self.device)
+            torch.cuda.set_stream(self.stream)
         self._ops = []
         self.kernel_launches = 0
 
