@@ -130,10 +130,19 @@ static int launch_fill(double *x, long long n, double v, cudaStream_t s)
 // tile-kernel launch
 // ------------------------------------------------------------------------------------------
 static int g_num_sms = 148;
-static int g_tile_cfg = 0;          // AMGB_TILE_CFG: which TileCfg geometry (tile_kernels.cuh)
-static int g_tile_ctas_per_sm = 2;  // resident CTAs per SM for that geometry (AMGB_TILE_CTAS caps it)
-static int g_tile_T = 512, g_tile_rmax = 128, g_tile_warps = 8;
+static int g_tile_cfg = 6;          // AMGB_TILE_CFG: which TileCfg geometry (tile_kernels.cuh)
+static int g_tile_ctas[5] = {2, 2, 2, 2, 2};   // resident CTAs per SM of csr_tile_kernel<*, OP, cfg>, per OP
+static int g_tile_ctas_cap = 64;                 // AMGB_TILE_CTAS
+static int g_tile_T = 256, g_tile_rmax = 64, g_tile_warps = 8;
 static int g_tile_hints = 1;        // AMGB_NO_HINTS=1 disables the L2 eviction hints
+
+template <class C, int OP>
+static void tile_cfg_op(size_t smem_per_sm)
+{
+    int c = std::max(1, (int)(smem_per_sm / (tile_smem_bytes<C, OP>() + 1024)));
+    c = std::min(c, 2048 / (C::WARPS * 32));
+    g_tile_ctas[OP] = std::max(1, std::min(c, g_tile_ctas_cap));
+}
 
 template <class C>
 static void tile_cfg_select(size_t smem_per_sm)
@@ -141,22 +150,29 @@ static void tile_cfg_select(size_t smem_per_sm)
     g_tile_T = C::T;
     g_tile_rmax = C::RMAX;
     g_tile_warps = C::WARPS;
-    g_tile_ctas_per_sm = std::max(1, (int)(smem_per_sm / (tile_smem_bytes<C>() + 1024)));
-    g_tile_ctas_per_sm = std::min(g_tile_ctas_per_sm, 2048 / (C::WARPS * 32));
+    tile_cfg_op<C, OP_SPMV>(smem_per_sm);
+    tile_cfg_op<C, OP_RESID>(smem_per_sm);
+    tile_cfg_op<C, OP_PADD>(smem_per_sm);
+    tile_cfg_op<C, OP_JACOBI>(smem_per_sm);
+    tile_cfg_op<C, OP_GS>(smem_per_sm);
 }
 
 static void tile_configure(size_t smem_per_sm)
 {
+    const char *c = getenv("AMGB_TILE_CTAS");
+    // 6 CTAs/SM = 48 warps/SM measured best (7 fits for some epilogues but starves L1: GS drops 35 %)
+    g_tile_ctas_cap = (c && atoi(c) >= 1) ? atoi(c) : 6;
     const char *e = getenv("AMGB_TILE_CFG");
-    g_tile_cfg = e ? atoi(e) : 1;   // measured best on B200 (tools/tune_tiles.py): T=256, 3 CTAs/SM
+    g_tile_cfg = e ? atoi(e) : 6;   // measured best on B200 (tools/tune_tiles.py, profiles/r01_tune_tiles*.jsonl)
     switch (g_tile_cfg) {
     case 0: tile_cfg_select<TileCfg0>(smem_per_sm); break;
+    case 1: tile_cfg_select<TileCfg1>(smem_per_sm); break;
     case 2: tile_cfg_select<TileCfg2>(smem_per_sm); break;
     case 3: tile_cfg_select<TileCfg3>(smem_per_sm); break;
-    default: g_tile_cfg = 1; tile_cfg_select<TileCfg1>(smem_per_sm); break;
+    case 4: tile_cfg_select<TileCfg4>(smem_per_sm); break;
+    case 5: tile_cfg_select<TileCfg5>(smem_per_sm); break;
+    default: g_tile_cfg = 6; tile_cfg_select<TileCfg6>(smem_per_sm); break;
     }
-    const char *c = getenv("AMGB_TILE_CTAS");
-    if (c && atoi(c) >= 1) g_tile_ctas_per_sm = std::min(g_tile_ctas_per_sm, atoi(c));
     const char *nh = getenv("AMGB_NO_HINTS");
     g_tile_hints = !(nh && nh[0] == '1');
 }
@@ -165,7 +181,7 @@ template <int OP, class C>
 static int launch_tile_cfg(int G, const TileArgs &a, int grid, cudaStream_t s)
 {
     const dim3 g((unsigned)grid), b(C::WARPS * 32);
-    constexpr size_t smem = tile_smem_bytes<C>();
+    constexpr size_t smem = tile_smem_bytes<C, OP>();
 #define AMGB_TILE_CASE(GG)                                                                               \
     case GG: {                                                                                           \
         static bool attr_done = false;                                                                   \
@@ -196,9 +212,12 @@ static int launch_tile_op(int G, const TileArgs &a, int grid, cudaStream_t s)
 {
     switch (g_tile_cfg) {
     case 0: return launch_tile_cfg<OP, TileCfg0>(G, a, grid, s);
+    case 1: return launch_tile_cfg<OP, TileCfg1>(G, a, grid, s);
     case 2: return launch_tile_cfg<OP, TileCfg2>(G, a, grid, s);
     case 3: return launch_tile_cfg<OP, TileCfg3>(G, a, grid, s);
-    default: return launch_tile_cfg<OP, TileCfg1>(G, a, grid, s);
+    case 4: return launch_tile_cfg<OP, TileCfg4>(G, a, grid, s);
+    case 5: return launch_tile_cfg<OP, TileCfg5>(G, a, grid, s);
+    default: return launch_tile_cfg<OP, TileCfg6>(G, a, grid, s);
     }
 }
 
@@ -216,9 +235,9 @@ static int launch_tile(int op, int G, TileArgs a, int grid, cudaStream_t s)
     return fail(AMGB_EINVAL, "unknown tile op");
 }
 
-static inline int tile_grid(int ntiles)
+static inline int tile_grid(int op, int ntiles)
 {
-    const int full = g_num_sms * g_tile_ctas_per_sm;
+    const int full = g_num_sms * g_tile_ctas[op];
     const int need = (ntiles + g_tile_warps - 1) / g_tile_warps;
     return std::max(1, std::min(full, need));
 }
@@ -626,7 +645,7 @@ struct amgb_hierarchy {
             a.tiles = M.tiles; a.tile_begin = 0; a.tile_end = M.n_tiles;
             a.Ap = M.Ap; a.Aj = M.Aj; a.Ax = M.Ax; a.x = x; a.b = b; a.y = y; a.r = r; a.omega = omega;
             a.partials = parts;
-            const int grid = parts ? tile_grid(1 << 30) : tile_grid(M.n_tiles);   // fixed grid when reducing
+            const int grid = parts ? tile_grid(op, 1 << 30) : tile_grid(op, M.n_tiles);   // fixed grid when reducing
             RET(launch_tile(op, M.tile_G, a, grid, stream));
         } else {
             CsrRowArgs a;
@@ -638,9 +657,15 @@ struct amgb_hierarchy {
         return prof_end();
     }
 
+    long long partials_used(const DevCsr &M, int op) const   // slots the kernel of `op` actually writes
+    {
+        return M.tiles ? (long long)g_num_sms * g_tile_ctas[op] : csr_grid(M.n_rows, M.lanes);
+    }
     long long partials_len(const DevCsr &M) const
     {
-        return M.tiles ? (long long)g_num_sms * g_tile_ctas_per_sm : csr_grid(M.n_rows, M.lanes);
+        // residual / Jacobi partial sums: one slot per CTA of the (fixed) persistent grid
+        return M.tiles ? (long long)g_num_sms * std::max(g_tile_ctas[OP_RESID], g_tile_ctas[OP_JACOBI])
+                       : csr_grid(M.n_rows, M.lanes);
     }
 
     int gs_wave(const DevCsr &A, const WaveSchedule &ws, long long w, double *x, const double *b, double omega)
@@ -660,7 +685,7 @@ struct amgb_hierarchy {
             a.tiles = A.tiles; a.tile_begin = ws.tile_ptr[(size_t)w]; a.tile_end = ws.tile_ptr[(size_t)w + 1];
             a.Ap = A.Ap; a.Aj = A.Aj; a.Ax = A.Ax; a.x = x; a.b = b; a.y = x; a.r = nullptr; a.omega = omega;
             a.partials = nullptr;
-            RET(launch_tile(OP_GS, A.tile_G, a, tile_grid(a.tile_end - a.tile_begin), stream));
+            RET(launch_tile(OP_GS, A.tile_G, a, tile_grid(OP_GS, a.tile_end - a.tile_begin), stream));
         } else {
             CsrRowArgs a;
             a.n = nrow;
@@ -832,7 +857,7 @@ struct amgb_hierarchy {
         Level &L = levels[0];
         cur_level = 0;
         RET(spmv(OP_RESID, L.A, L.x, L.b, L.r, 0.0, nullptr, partials));
-        reduce_partials_kernel<<<1, 1024, 0, stream>>>(partials, (int)partials_len(L.A), norms2 + slot);
+        reduce_partials_kernel<<<1, 1024, 0, stream>>>(partials, (int)partials_used(L.A, OP_RESID), norms2 + slot);
         CK(cudaGetLastError());
         launches++;
         return AMGB_OK;
@@ -1297,7 +1322,7 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
         const char *vb = getenv("AMGB_VERBOSE");
         if (vb && vb[0] == '1')
             fprintf(stderr, "[amgb] levels=%d tail_level=%d cluster=%d tile_cfg=%d ctas/sm=%d hints=%d\n", nl,
-                    h->tail_level < nl ? h->tail_level : -1, h->tail_csize, g_tile_cfg, g_tile_ctas_per_sm, g_tile_hints);
+                    h->tail_level < nl ? h->tail_level : -1, h->tail_csize, g_tile_cfg, g_tile_ctas[OP_GS], g_tile_hints);
     }
     if (!h->coarse_zero) RET(h->upload(&h->coarse_pinv, h->coarse_host.data(), (long long)h->coarse_host.size()));
     h->coarse_host.clear();
@@ -1568,7 +1593,7 @@ extern "C" int amgb_operator_apply(amgb_operator *op, int32_t kind, const double
     double *parts = (norm2_out != nullptr && (kind == OP_RESID || kind == OP_JACOBI)) ? op->partials : nullptr;
     RET(h->spmv(kind, op->M, x, b, y, omega, r, parts));
     if (parts != nullptr) {
-        reduce_partials_kernel<<<1, 1024, 0, h->stream>>>(parts, (int)h->partials_len(op->M), norm2_out);
+        reduce_partials_kernel<<<1, 1024, 0, h->stream>>>(parts, (int)h->partials_used(op->M, kind), norm2_out);
         CK(cudaGetLastError());
     }
     return AMGB_OK;

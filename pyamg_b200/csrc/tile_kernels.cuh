@@ -55,23 +55,30 @@ using TileCfg0 = TileCfg<512, 128, 2, 8>;
 using TileCfg1 = TileCfg<256, 64, 2, 8>;
 using TileCfg2 = TileCfg<256, 64, 3, 8>;
 using TileCfg3 = TileCfg<128, 32, 4, 8>;
+using TileCfg4 = TileCfg<256, 64, 1, 8>;     // single stage, ~48 warps/SM: cross-warp overlap only
+using TileCfg5 = TileCfg<128, 32, 2, 8>;     // ~1.3 KB stages, 6+ CTAs/SM
+using TileCfg6 = TileCfg<224, 64, 1, 8>;     // 32 seven-point rows per tile; 7-8 CTAs/SM = 56-64 warps/SM
 
-template <class C>
+// the b / x_old slices are staged only for the epilogues that read them: shared memory is what limits
+// the number of resident warps, and resident warps are what hides the gather latency
+template <class C, int OP>
 struct __align__(16) TileStageT {
+    static constexpr bool kB = (OP == OP_RESID || OP == OP_JACOBI || OP == OP_GS);
+    static constexpr bool kX = (OP == OP_JACOBI);
     double val[C::T + 8];
-    double bseg[C::RMAX + 4];    // b[row0..row1)          (RESID / JACOBI / GS)
-    double xseg[C::RMAX + 4];    // x[row0..row1), old     (JACOBI)
+    double bseg[kB ? C::RMAX + 4 : 2];    // b[row0..row1)
+    double xseg[kX ? C::RMAX + 4 : 2];    // x[row0..row1), old iterate
     int col[C::T + 8];
     int ptr[C::RMAX + 8];
 };
-template <class C>
+template <class C, int OP>
 struct __align__(16) TileWarpSmemT {
-    TileStageT<C> st[C::STAGES];
+    TileStageT<C, OP> st[C::STAGES];
     unsigned long long bar[C::STAGES];
     unsigned long long pad_;
 };
-template <class C>
-constexpr size_t tile_smem_bytes() { return sizeof(TileWarpSmemT<C>) * C::WARPS; }
+template <class C, int OP>
+constexpr size_t tile_smem_bytes() { return sizeof(TileWarpSmemT<C, OP>) * C::WARPS; }
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -142,7 +149,7 @@ __device__ __forceinline__ double ld_x_hint(const double *p, unsigned long long 
 // One lane: ask the TMA for tile t's segments.  Every source starts on a 16-byte boundary: entry ranges
 // are widened to multiples of 4 entries, vector ranges to multiples of 2 (the arrays are padded at upload).
 template <class C, int OP>
-__device__ __forceinline__ void tile_issue(const TileArgs &a, int t, TileStageT<C> &st, unsigned long long *bar,
+__device__ __forceinline__ void tile_issue(const TileArgs &a, int t, TileStageT<C, OP> &st, unsigned long long *bar,
                                            unsigned long long pol)
 {
     const TileDesc d0 = a.tiles[t], d1 = a.tiles[t + 1];
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(C::WARPS * 32) csr_tile_kernel(const TileArgs 
     constexpr int STAGES = C::STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane & (G - 1), grp = lane / G;
-    TileWarpSmemT<C> &ws = reinterpret_cast<TileWarpSmemT<C> *>(smem_raw)[warp];
+    TileWarpSmemT<C, OP> &ws = reinterpret_cast<TileWarpSmemT<C, OP> *>(smem_raw)[warp];
 
     if (lane == 0) {
 #pragma unroll
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(C::WARPS * 32) csr_tile_kernel(const TileArgs 
         const int s0 = d0.nz0, len = d1.nz0 - d0.nz0;
         mbar_wait(&ws.bar[stage], (phase >> stage) & 1u);
         phase ^= 1u << stage;
-        const TileStageT<C> &st = ws.st[stage];
+        const TileStageT<C, OP> &st = ws.st[stage];
 
         if (len <= C::T) {
             const int soff = s0 & ~3;                 // smem index = global entry index - soff

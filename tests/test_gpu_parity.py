@@ -65,7 +65,8 @@ def test_vcycle_matches_oracle_on_fresh_rhs(name, load_golden):
 
 @pytest.mark.parametrize("env", [{"AMGB_NO_TILES": "1"}, {"AMGB_NO_PERMUTE": "1"},
                                  {"AMGB_NO_TILES": "1", "AMGB_NO_PERMUTE": "1"}, {"AMGB_NO_GRAPH": "1"},
-                                 {"AMGB_TILE_G": "4"}, {"AMGB_TILE_G": "32"}, {"AMGB_TILE_CFG": "0"},
+                                 {"AMGB_TILE_G": "4"}, {"AMGB_TILE_G": "32"}, {"AMGB_TILE_CFG": "0"}, {"AMGB_TILE_CFG": "1"},
+                                 {"AMGB_TILE_CFG": "4"},
                                  {"AMGB_TILE_CFG": "3", "AMGB_NO_HINTS": "1"}, {"AMGB_NO_TAIL": "1"},
                                  {"AMGB_TAIL_CLUSTER": "1"}, {"AMGB_TAIL_CLUSTER": "4"}])
 @pytest.mark.parametrize("name", GOLDEN)

@@ -33,8 +33,7 @@ P = lambda t: ctypes.c_void_p(t.data_ptr())
 L = E.lib()
 
 settings = [dict(zip(("AMGB_TILE_CFG", "AMGB_TILE_CTAS", "AMGB_NO_HINTS"), v)) for v in
-            [("0", "9", "0"), ("0", "9", "1"), ("1", "9", "0"), ("1", "2", "0"), ("1", "3", "0"), ("2", "9", "0"),
-             ("2", "1", "0"), ("3", "9", "0"), ("3", "3", "0"), ("0", "1", "0")]]
+            [("6", "9", "0"), ("4", "9", "0"), ("6", "6", "0")]]
 if a.settings:
     settings = [dict(zip(("AMGB_TILE_CFG", "AMGB_TILE_CTAS", "AMGB_NO_HINTS"), s.split(","))) for s in a.settings.split(";")]
 
