@@ -104,15 +104,28 @@ __global__ void __launch_bounds__(kCsrThreads) csr_rows_kernel(const CsrRowArgs 
     }
     double sum = 0.0, diag = 0.0;
     int jd = -1;
-    for (int jj = start + lane; jj < end; jj += G) {
-        const int c = ld_stream_i32(a.Aj + jj);
-        const double v = ld_stream_f64(a.Ax + jj);
-        if (kNeedDiag && c == row) {
-            diag = v;   // later duplicates overwrite: jj increases within a lane
-            jd = jj;
-        } else {
-            const double xv = (OP == OP_GS) ? a.x[c] : __ldg(a.x + c);
-            sum += v * xv;
+    // chunks of U independent (col,val) loads, then U independent gathers: the per-row latency chain is
+    // row-pointer -> entries -> gathers, whatever the row length
+    constexpr int U = 4;
+    for (int j0 = start + lane; j0 < end; j0 += G * U) {
+        int c[U];
+        double v[U], xv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int jj = j0 + u * G;
+            const bool ok = jj < end;
+            c[u] = ok ? ld_stream_i32(a.Aj + jj) : -1;
+            v[u] = ok ? ld_stream_f64(a.Ax + jj) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool skip = c[u] < 0 || (kNeedDiag && c[u] == row);
+            xv[u] = skip ? 0.0 : ((OP == OP_GS) ? a.x[c[u]] : __ldg(a.x + c[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (kNeedDiag && c[u] == row && c[u] >= 0) { diag = v[u]; jd = j0 + u * G; }   // later duplicates overwrite
+            else sum += v[u] * xv[u];
         }
     }
     sum = group_sum<G>(sum);

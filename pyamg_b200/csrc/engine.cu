@@ -537,7 +537,8 @@ struct amgb_hierarchy {
     int tail_level = 1 << 30;
     int tail_csize = 1;
     long long tail_nnz_limit = 600000;     // AMGB_TAIL_NNZ: levels at most this large run in the cluster tail
-    long long tile_min_nnz = 0;            // AMGB_TILE_MIN_NNZ: smaller launches use the lanes-per-row kernel
+    double tail_solo_bytes = 400000.0;     // AMGB_TAIL_SOLO_BYTES: steps moving at most this much run on one CTA
+    long long tile_min_nnz = 1500000;            // AMGB_TILE_MIN_NNZ: smaller launches use the lanes-per-row kernel
     bool recording = false;
     std::vector<TailStep> rec;
     double rec_bytes = 0.0;
@@ -547,17 +548,19 @@ struct amgb_hierarchy {
                const double *b, double *y, double omega, double bytes, const double *dense = nullptr, int ncols = 0)
     {
         TailStep st;
+        // small steps run on CTA 0 alone (no cluster barrier); the bound is on the bytes one SM must pull
+        const bool solo = tail_csize > 1 && bytes <= tail_solo_bytes;
         if (op <= T_GS && nrows > 0) {
             // one pass over the step's rows: as many lanes per row as the cluster can spare, but no more
             // than the row length warrants (G from pick_lanes is the smallest power of two >= mean length)
-            const int nthreads = tail_csize * kTailThreads;
+            const int nthreads = (solo ? 1 : tail_csize) * kTailThreads;
             int fill = 1;
             while (fill < 32 && (long long)fill * 2 * nrows <= nthreads) fill <<= 1;
             G = std::max(1, std::min(G, fill));
         }
         st.op = op; st.G = G; st.row0 = row0; st.nrows = nrows; st.rows = rows;
         st.Ap = M ? M->Ap : nullptr; st.Aj = M ? M->Aj : nullptr; st.Ax = M ? M->Ax : dense;
-        st.x = x; st.b = b; st.y = y; st.omega = omega; st.ncols = ncols; st.pad_ = 0;
+        st.x = x; st.b = b; st.y = y; st.omega = omega; st.ncols = ncols; st.solo = solo ? 1 : 0;
         rec.push_back(st);
         rec_bytes += bytes;
         return AMGB_OK;
@@ -1287,6 +1290,8 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
         const char *nt = getenv("AMGB_NO_TAIL");
         const char *tn = getenv("AMGB_TAIL_NNZ");
         if (tn && atoll(tn) > 0) h->tail_nnz_limit = atoll(tn);
+        const char *sb = getenv("AMGB_TAIL_SOLO_BYTES");
+        if (sb) h->tail_solo_bytes = atof(sb);
         const char *tm = getenv("AMGB_TILE_MIN_NNZ");
         if (tm && atoll(tm) >= 0) h->tile_min_nnz = atoll(tm);
         const int nl = (int)h->levels.size();

@@ -33,7 +33,7 @@ struct TailStep {
     double *y;             // output (see csr_kernels.cuh epilogues); T_FILL/T_COPY target
     double omega;
     int ncols;
-    int pad_;
+    int solo;              // 1: small step, executed by CTA 0 alone (__syncthreads, L1-cached loads)
 };
 
 constexpr int kTailThreads = 1024;
@@ -55,7 +55,14 @@ __device__ __forceinline__ unsigned cluster_size()
     return r;
 }
 
-template <int G>
+// SOLO = true: the step runs inside one CTA; vectors may be read through L1 (same-SM coherent).
+template <bool SOLO>
+__device__ __forceinline__ double ld_vec(const double *p)
+{
+    return SOLO ? *p : __ldcg(p);
+}
+
+template <int G, bool SOLO>
 __device__ __forceinline__ void tail_rows(const TailStep &st, int tid, int nthreads)
 {
     const int lane = tid & (G - 1);
@@ -72,11 +79,28 @@ __device__ __forceinline__ void tail_rows(const TailStep &st, int tid, int nthre
         }
         double sum = 0.0, diag = 0.0;
         int jd = -1;
-        for (int jj = start + lane; jj < end; jj += G) {
-            const int c = __ldg(st.Aj + jj);
-            const double v = __ldg(st.Ax + jj);
-            if (need_diag && c == row) { diag = v; jd = jj; }
-            else sum += v * __ldcg(st.x + c);
+        // latency-bound: issue a chunk of U independent (col,val) loads, then U independent gathers
+        constexpr int U = 8;
+        for (int j0 = start + lane; j0 < end; j0 += G * U) {
+            int c[U];
+            double v[U], xv[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int jj = j0 + u * G;
+                const bool ok = jj < end;
+                c[u] = ok ? __ldg(st.Aj + jj) : -1;
+                v[u] = ok ? __ldg(st.Ax + jj) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const bool isd = need_diag && c[u] == row;
+                xv[u] = (c[u] >= 0 && !isd) ? ld_vec<SOLO>(st.x + c[u]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (need_diag && c[u] == row && c[u] >= 0) { diag = v[u]; jd = j0 + u * G; }
+                else sum += v[u] * xv[u];
+            }
         }
         sum = group_sum<G>(sum);
         if (need_diag) {
@@ -90,56 +114,76 @@ __device__ __forceinline__ void tail_rows(const TailStep &st, int tid, int nthre
         if (active && lane == 0) {
             switch (st.op) {
             case T_SPMV: st.y[row] = sum; break;
-            case T_RESID: st.y[row] = __ldcg(st.b + row) - sum; break;
-            case T_PADD: st.y[row] = __ldcg(st.y + row) + sum; break;
+            case T_RESID: st.y[row] = ld_vec<SOLO>(st.b + row) - sum; break;
+            case T_PADD: st.y[row] = ld_vec<SOLO>(st.y + row) + sum; break;
             case T_JACOBI: {
-                const double xi = __ldcg(st.x + row), bi = __ldcg(st.b + row);
+                const double xi = ld_vec<SOLO>(st.x + row), bi = ld_vec<SOLO>(st.b + row);
                 st.y[row] = (diag != 0.0) ? (1.0 - st.omega) * xi + st.omega * ((bi - sum) / diag) : xi;
                 break;
             }
             default:   // T_GS
                 if (diag != 0.0) {
-                    const double g = (__ldcg(st.b + row) - sum) / diag;
-                    st.y[row] = (st.omega == 1.0) ? g : st.omega * g + (1.0 - st.omega) * __ldcg(st.y + row);
+                    const double g = (ld_vec<SOLO>(st.b + row) - sum) / diag;
+                    st.y[row] = (st.omega == 1.0) ? g : st.omega * g + (1.0 - st.omega) * ld_vec<SOLO>(st.y + row);
                 }
             }
         }
     }
 }
 
+template <bool SOLO>
+__device__ __forceinline__ void tail_step(const TailStep &st, int tid, int nthreads)
+{
+    if (st.op <= T_GS) {
+        switch (st.G) {
+        case 1: tail_rows<1, SOLO>(st, tid, nthreads); break;
+        case 2: tail_rows<2, SOLO>(st, tid, nthreads); break;
+        case 4: tail_rows<4, SOLO>(st, tid, nthreads); break;
+        case 8: tail_rows<8, SOLO>(st, tid, nthreads); break;
+        case 16: tail_rows<16, SOLO>(st, tid, nthreads); break;
+        default: tail_rows<32, SOLO>(st, tid, nthreads); break;
+        }
+    } else if (st.op == T_FILL) {
+        for (int i = tid; i < st.nrows; i += nthreads) st.y[i] = 0.0;
+    } else if (st.op == T_COPY) {
+        for (int i = tid; i < st.nrows; i += nthreads) st.y[i] = ld_vec<SOLO>(st.x + i);
+    } else {   // T_DENSE: y = M x, one warp per row (coarsest-level pseudo-inverse)
+        const int w = tid >> 5, l = tid & 31, nw = nthreads >> 5;
+        for (int base = 0; base < st.nrows; base += nw) {
+            const int r = base + w;
+            double acc = 0.0;
+            if (r < st.nrows)
+                for (int j = l; j < st.ncols; j += 32)
+                    acc += __ldg(st.Ax + (size_t)r * st.ncols + j) * ld_vec<SOLO>(st.x + j);
+            acc = group_sum<32>(acc);
+            if (r < st.nrows && l == 0) st.y[r] = acc;
+        }
+    }
+}
+
+// Steps flagged `solo` are too small to be worth a cluster-wide barrier: CTA 0 runs them alone, separated
+// by __syncthreads, reading vectors through its own L1; the other CTAs wait at the next cluster barrier.
 __global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailStep *__restrict__ steps, int nsteps)
 {
+    const int rank = (int)cluster_rank();
     const int nthreads = (int)cluster_size() * kTailThreads;
-    const int tid = (int)cluster_rank() * kTailThreads + threadIdx.x;
+    const int tid = rank * kTailThreads + threadIdx.x;
+    bool in_solo = false;
     TailStep next = steps[0];
     for (int s = 0; s < nsteps; s++) {
         const TailStep st = next;
         if (s + 1 < nsteps) next = steps[s + 1];     // the step list is immutable: fetch ahead of the barrier
-        if (st.op <= T_GS) {
-            switch (st.G) {
-            case 1: tail_rows<1>(st, tid, nthreads); break;
-            case 2: tail_rows<2>(st, tid, nthreads); break;
-            case 4: tail_rows<4>(st, tid, nthreads); break;
-            case 8: tail_rows<8>(st, tid, nthreads); break;
-            case 16: tail_rows<16>(st, tid, nthreads); break;
-            default: tail_rows<32>(st, tid, nthreads); break;
+        if (st.solo) {
+            in_solo = true;
+            if (rank == 0) {
+                tail_step<true>(st, threadIdx.x, kTailThreads);
+                __syncthreads();
             }
-        } else if (st.op == T_FILL) {
-            for (int i = tid; i < st.nrows; i += nthreads) st.y[i] = 0.0;
-        } else if (st.op == T_COPY) {
-            for (int i = tid; i < st.nrows; i += nthreads) st.y[i] = __ldcg(st.x + i);
-        } else {   // T_DENSE: y = M x, one warp per row (coarsest-level pseudo-inverse)
-            const int w = tid >> 5, l = tid & 31, nw = nthreads >> 5;
-            for (int base = 0; base < st.nrows; base += nw) {
-                const int r = base + w;
-                double acc = 0.0;
-                if (r < st.nrows)
-                    for (int j = l; j < st.ncols; j += 32) acc += __ldg(st.Ax + (size_t)r * st.ncols + j) * __ldcg(st.x + j);
-                acc = group_sum<32>(acc);
-                if (r < st.nrows && l == 0) st.y[r] = acc;
-            }
+        } else {
+            if (in_solo) { cluster_barrier(); in_solo = false; }   // publish CTA 0's solo results
+            tail_step<false>(st, tid, nthreads);
+            cluster_barrier();
         }
-        cluster_barrier();
     }
 }
 

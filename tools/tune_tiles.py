@@ -34,10 +34,13 @@ L = E.lib()
 
 settings = [dict(zip(("AMGB_TILE_CFG", "AMGB_TILE_CTAS", "AMGB_NO_HINTS"), v)) for v in
             [("6", "9", "0"), ("4", "9", "0"), ("6", "6", "0")]]
-if a.settings:
-    settings = [dict(zip(("AMGB_TILE_CFG", "AMGB_TILE_CTAS", "AMGB_NO_HINTS"), s.split(","))) for s in a.settings.split(";")]
+if a.settings:      # "K=V,K=V;K=V" -> one dict of environment overrides per setting
+    settings = [dict(kv.split("=") for kv in s.split(",") if kv) for s in a.settings.split(";")]
+ALL_KEYS = sorted({k for st in settings for k in st})
 
 for st in settings:
+    for k in ALL_KEYS:
+        os.environ.pop(k, None)
     os.environ.update(st)
     ml._invalidate()
     t0 = time.time()
