@@ -87,8 +87,19 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.1)
 
+    def sample_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                  "-i", str(self.gpu)], capture_output=True, text=True, timeout=20).stdout
+            for ln in out.strip().splitlines():
+                self.rows.append([c.strip() for c in ln.split(",")])
+        except Exception:
+            pass
+
     def summary(self):
         self.stop_flag = True
+        if not self.rows:
+            self.sample_once()      # the region was shorter than one nvidia-smi round trip
         sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -142,6 +153,25 @@ def run_reference(args, grid):
                                    f"host has {os.cpu_count()} cores, the reference path is single-threaded"},
         "e2e": {"value": v, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
+
+
+def ncu_traffic(ml, dk):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_ncu_tile_kernels.csv: dram__bytes_read.sum + dram__bytes_write.sum), or None when the
+    capture does not cover this kernel / problem size."""
+    try:
+        lvl, op = dk
+        if ml.levels[0].A.shape[0] != 256 ** 3 or op != 4 or lvl not in (0, 1):
+            return None
+        tag = "tile<G=1 OP=4>" if lvl == 0 else "tile<G=2 OP=4>"
+        vals = []
+        for ln in open(os.path.join(ROOT, "profiles", "r01_ncu_tile_kernels.csv")):
+            f = ln.strip().split(",")
+            if f[0] == tag:
+                vals.append(float(f[2]) * 1e9 + float(f[3]) * 1e6)
+        return float(np.mean(vals)) if vals else None
+    except Exception:
+        return None
 
 
 def workload_config(grid, ml, ngpus):
@@ -380,7 +410,7 @@ def main():
                 "frac": round(g[0] / g[1] / 1e6 / peak, 3)} for k, g in table[:8]]
     (dk, dg) = table[0]
     roofline = {"bound": "hbm", "achieved": dg[0] / dg[1] / 1e6, "peak": peak, "unit": "GB/s",
-                "frac": dg[0] / dg[1] / 1e6 / peak, "traffic": None,
+                "frac": dg[0] / dg[1] / 1e6 / peak, "traffic": ncu_traffic(ml, dk),
                 "kernel": f"level {dk[0]} {OPS[dk[1]]} (csr_tile_kernel: TMA-staged CSR, wave-major rows)", "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
                 "bytes_per_launch": dg[0] / dg[2], "ms_per_launch": dg[1] / dg[2]}
 

@@ -132,7 +132,7 @@ static int launch_fill(double *x, long long n, double v, cudaStream_t s)
 static int g_num_sms = 148;
 static int g_tile_cfg = 6;          // AMGB_TILE_CFG: which TileCfg geometry (tile_kernels.cuh)
 static int g_tile_ctas[5] = {2, 2, 2, 2, 2};   // resident CTAs per SM of csr_tile_kernel<*, OP, cfg>, per OP
-static int g_tile_ctas_cap = 64;                 // AMGB_TILE_CTAS
+static int g_tile_ctas_cap = 0;                  // AMGB_TILE_CTAS (0 = per-epilogue optimum)
 static int g_tile_T = 256, g_tile_rmax = 64, g_tile_warps = 8;
 static int g_tile_hints = 1;        // AMGB_NO_HINTS=1 disables the L2 eviction hints
 
@@ -141,7 +141,11 @@ static void tile_cfg_op(size_t smem_per_sm)
 {
     int c = std::max(1, (int)(smem_per_sm / (tile_smem_bytes<C, OP>() + 1024)));
     c = std::min(c, 2048 / (C::WARPS * 32));
-    g_tile_ctas[OP] = std::max(1, std::min(c, g_tile_ctas_cap));
+    // measured optimum per epilogue (tools/microbench.py, 256^3 7-point, B200): resident warps hide the
+    // gather latency, but the shared memory they pin shrinks L1 -- the sweet spot depends on the stage size
+    static const int kBest[5] = {6, 7, 6, 5, 6};   // SpMV, residual, prolong+add, Jacobi, Gauss-Seidel
+    const int cap = g_tile_ctas_cap > 0 ? g_tile_ctas_cap : kBest[OP];
+    g_tile_ctas[OP] = std::max(1, std::min(c, cap));
 }
 
 template <class C>
@@ -160,8 +164,7 @@ static void tile_cfg_select(size_t smem_per_sm)
 static void tile_configure(size_t smem_per_sm)
 {
     const char *c = getenv("AMGB_TILE_CTAS");
-    // 6 CTAs/SM = 48 warps/SM measured best (7 fits for some epilogues but starves L1: GS drops 35 %)
-    g_tile_ctas_cap = (c && atoi(c) >= 1) ? atoi(c) : 6;
+    g_tile_ctas_cap = (c && atoi(c) >= 1) ? atoi(c) : 0;   // 0 = per-epilogue measured optimum
     const char *e = getenv("AMGB_TILE_CFG");
     g_tile_cfg = e ? atoi(e) : 6;   // measured best on B200 (tools/tune_tiles.py, profiles/r01_tune_tiles*.jsonl)
     switch (g_tile_cfg) {
