@@ -114,6 +114,20 @@ int amgb_solve(amgb_hierarchy *h, const double *b_host, double *x_host, double t
                int32_t maxiter, int32_t cycle, int32_t cycles_per_level, double *residuals,
                int32_t *n_residuals, int32_t *info);
 
+/* amgb_solve with flags: AMGB_FLAG_X0_ZERO = the initial guess is zero, x_host is output only (saves the
+ * host->device copy of x0; what aspreconditioner() and solve(x0=None) need). */
+#define AMGB_FLAG_X0_ZERO 1
+int amgb_solve_ex(amgb_hierarchy *h, const double *b_host, double *x_host, double tol, int32_t maxiter,
+                  int32_t cycle, int32_t cycles_per_level, int32_t flags, double *residuals,
+                  int32_t *n_residuals, int32_t *info);
+
+/* MultilevelSolver.solve(accel='cg') with every vector resident in HBM: pyamg's preconditioned CG
+ * (pyamg/krylov/_cg.py:97-196, criteria 'rr') with M = one multigrid cycle from x0 = 0
+ * (aspreconditioner, multilevel.py:355-396).  residuals: maxiter+1 slots; *info: 0 converged,
+ * k = maxiter reached, -1 = indefinite matrix / preconditioner detected (the reference's warning). */
+int amgb_solve_cg(amgb_hierarchy *h, const double *b_host, double *x_host, double tol, int32_t maxiter,
+                  int32_t cycle, int32_t flags, double *residuals, int32_t *n_residuals, int32_t *info);
+
 /* The same on DEVICE vectors (no host copies): x_dev in/out, b_dev in. Runs exactly `ncycles`
  * cycles (tol = 0 semantics); if norms2_dev != NULL it receives ncycles+1 squared residual norms. */
 int amgb_solve_device(amgb_hierarchy *h, const double *b_dev, double *x_dev, int32_t ncycles,

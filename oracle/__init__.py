@@ -310,6 +310,60 @@ def _smooth(spec, A, x, b, kernels):
     fn(A, x, b, kernels=kernels, **kw)
 
 
+def cg(A, b, x0=None, tol=1e-5, maxiter=None, M=None, callback=None, residuals=None, kernels="oracle"):
+    """pyamg/krylov/_cg.py:11-196 with criteria='rr' (the default the reference's solve(accel='cg') uses)."""
+    b = np.ravel(np.asarray(b, dtype=np.float64))
+    n = len(b)
+    x = np.zeros(n) if x0 is None else np.array(np.ravel(x0), dtype=np.float64)
+    if maxiter is None:
+        maxiter = int(1.3 * n) + 2
+    elif maxiter < 1:
+        raise ValueError("Number of iterations must be positive")
+    r = b - matvec(A, x, kernels)
+    z = M(r)
+    p = z.copy()
+    rz = np.inner(r, z)
+    normr = np.linalg.norm(r)
+    if residuals is not None:
+        residuals[:] = [normr]
+    normb = np.linalg.norm(b)
+    if normb == 0.0:
+        normb = 1.0
+    rtol = tol * normb
+    if normr < rtol:
+        return x, 0
+    it = 0
+    while True:
+        Ap = matvec(A, p, kernels)
+        rz_old = rz
+        pAp = np.inner(Ap, p)
+        if pAp < 0.0:
+            return x, -1
+        alpha = rz / pAp
+        x += alpha * p
+        if np.mod(it, 8) and it > 0:
+            r -= alpha * Ap
+        else:
+            r = b - matvec(A, x, kernels)
+        z = M(r)
+        rz = np.inner(r, z)
+        if rz < 0.0:
+            return x, -1
+        beta = rz / rz_old
+        p *= beta
+        p += z
+        it += 1
+        normr = np.linalg.norm(r)
+        if residuals is not None:
+            residuals.append(normr)
+        if callback is not None:
+            callback(x)
+        if normr < rtol:
+            return x, 0
+        if it == maxiter:
+            return x, it
+
+
 class Cycle:
     """Restatement of MultilevelSolver.solve/__solve (pyamg/multilevel.py:398-662), V/W/F cycles,
     'pinv' coarse solve (:717-721, GenericSolver.__call__ :797-816)."""
@@ -327,7 +381,15 @@ class Cycle:
         return np.dot(self.coarse_pinv, b)
 
     def solve(self, b, x0=None, tol=1e-5, maxiter=100, cycle="V", residuals=None,
-              callback=None, cycles_per_level=1, return_info=False):
+              callback=None, cycles_per_level=1, return_info=False, accel=None):
+        if accel == "cg":      # multilevel.py:479-508 with pyamg.krylov.cg; M = aspreconditioner (:390-396)
+            x, info = cg(self.levels[0]["A"], b, x0=x0, tol=tol, maxiter=maxiter,
+                         M=lambda r: self.solve(r, maxiter=1, cycle=cycle, tol=1e-12),
+                         callback=callback, residuals=residuals, kernels=self.kernels)
+            x = x.reshape(np.shape(b))
+            return (x, info) if return_info else x
+        if accel is not None:
+            raise NotImplementedError("oracle: accel other than 'cg'")
         x = np.zeros_like(b) if x0 is None else np.array(x0)
         A = self.levels[0]["A"]
         cycle = str(cycle).upper()

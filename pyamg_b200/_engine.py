@@ -18,6 +18,7 @@ OK, EINVAL, ECUDA, ENOTIMPL, ESTATE = 0, -1, -2, -3, -4
 SM_NONE, SM_JACOBI, SM_GAUSS_SEIDEL, SM_BLOCK_JACOBI = 0, 1, 2, 3
 SWEEPS = {"forward": 0, "backward": 1, "symmetric": 2}
 CYCLES = {"V": 0, "W": 1, "F": 2}
+FLAG_X0_ZERO = 1
 
 
 class Matrix(ctypes.Structure):
@@ -45,7 +46,7 @@ _lib = None
 SYMBOLS = [
     "amgb_last_error", "amgb_version", "amgb_device_count",
     "amgb_hierarchy_create", "amgb_hierarchy_destroy", "amgb_hierarchy_add_level",
-    "amgb_hierarchy_set_coarse_pinv", "amgb_hierarchy_finalize", "amgb_solve",
+    "amgb_hierarchy_set_coarse_pinv", "amgb_hierarchy_finalize", "amgb_solve", "amgb_solve_ex", "amgb_solve_cg",
     "amgb_solve_device", "amgb_hierarchy_num_levels", "amgb_hierarchy_device_bytes",
     "amgb_hierarchy_last_launches", "amgb_profile_cycle", "amgb_host_alloc", "amgb_host_free",
     "amgb_operator_create", "amgb_operator_destroy", "amgb_operator_apply",
@@ -82,6 +83,8 @@ def lib():
     L.amgb_hierarchy_set_coarse_pinv.argtypes = [vp, i32, c_f64p, i32]
     L.amgb_hierarchy_finalize.argtypes = [vp, vp]
     L.amgb_solve.argtypes = [vp, vp, vp, f64, i32, i32, i32, c_f64p, c_i32p, c_i32p]
+    L.amgb_solve_ex.argtypes = [vp, vp, vp, f64, i32, i32, i32, i32, c_f64p, c_i32p, c_i32p]
+    L.amgb_solve_cg.argtypes = [vp, vp, vp, f64, i32, i32, i32, c_f64p, c_i32p, c_i32p]
     L.amgb_solve_device.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     L.amgb_hierarchy_num_levels.argtypes = [vp]
     L.amgb_hierarchy_device_bytes.argtypes = [vp]

@@ -193,6 +193,25 @@ __global__ void __launch_bounds__(256) sumsq_partials_kernel(const double *__res
     if (threadIdx.x == 0) partials[blockIdx.x] = t;
 }
 
+// partials[b] = sum of x_i*y_i over block b's grid-stride share (fixed grid -> deterministic dot products)
+__global__ void __launch_bounds__(256) dot_partials_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                                                           long long n, double *__restrict__ partials)
+{
+    double t = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        t += x[i] * y[i];
+    t = block_sum<256>(t);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+// y = a*x + b*y  (Krylov vector updates)
+__global__ void axpby_kernel(double a, const double *__restrict__ x, double b, double *__restrict__ y, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) y[i] = a * x[i] + b * y[i];
+}
+
 // out[slot] = sum(partials[0..m)) in a fixed order (single block) -> deterministic norms
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *partials, int m,
                                                                double *out)

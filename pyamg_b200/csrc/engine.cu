@@ -523,6 +523,7 @@ struct amgb_hierarchy {
     int norms2_cap = 0;
     double *norm_host = nullptr;  // pinned scalar for the tol test
     double *sumsq_parts = nullptr;
+    double *kry[4] = {nullptr, nullptr, nullptr, nullptr};   // Krylov work vectors (allocated on first use)
 
     cudaGraphExec_t graph[3] = {nullptr, nullptr, nullptr};
     int graph_cpl[3] = {0, 0, 0};
@@ -1388,11 +1389,13 @@ static int load_level0(amgb_hierarchy *h, const double *b, const double *x, cuda
     L0.x = L0.x_home;
     if (h->order0 == nullptr) {
         CK(cudaMemcpyAsync(L0.b, b, bytes, kind, s));
+        if (x == nullptr) return h->launch_count_fill(L0.x, L0.A.n_rows);
         CK(cudaMemcpyAsync(L0.x, x, bytes, kind, s));
         return AMGB_OK;
     }
     CK(cudaMemcpyAsync(h->io_tmp, b, bytes, kind, s));
     RET(h->gather(h->io_tmp, h->order0, L0.b, L0.A.n_rows));
+    if (x == nullptr) return h->launch_count_fill(L0.x, L0.A.n_rows);   // x0 = 0: nothing to copy
     CK(cudaMemcpyAsync(h->io_tmp, x, bytes, kind, s));
     RET(h->gather(h->io_tmp, h->order0, L0.x, L0.A.n_rows));
     return AMGB_OK;
@@ -1411,9 +1414,20 @@ static int store_level0(amgb_hierarchy *h, double *x, cudaMemcpyKind kind)
     return AMGB_OK;
 }
 
+extern "C" int amgb_solve_ex(amgb_hierarchy *h, const double *b_host, double *x_host, double tol, int32_t maxiter,
+                             int32_t cycle, int32_t cycles_per_level, int32_t flags, double *residuals,
+                             int32_t *n_residuals, int32_t *info);
+
 extern "C" int amgb_solve(amgb_hierarchy *h, const double *b_host, double *x_host, double tol,
                           int32_t maxiter, int32_t cycle, int32_t cycles_per_level, double *residuals,
                           int32_t *n_residuals, int32_t *info)
+{
+    return amgb_solve_ex(h, b_host, x_host, tol, maxiter, cycle, cycles_per_level, 0, residuals, n_residuals, info);
+}
+
+extern "C" int amgb_solve_ex(amgb_hierarchy *h, const double *b_host, double *x_host, double tol, int32_t maxiter,
+                             int32_t cycle, int32_t cycles_per_level, int32_t flags, double *residuals,
+                             int32_t *n_residuals, int32_t *info)
 {
     RET(check_cycle_args(h, cycle, cycles_per_level));
     if (b_host == nullptr || x_host == nullptr) return fail(AMGB_EINVAL, "null host vector");
@@ -1423,7 +1437,7 @@ extern "C" int amgb_solve(amgb_hierarchy *h, const double *b_host, double *x_hos
     cudaStream_t s = h->stream;
     h->launches = 0;
     RET(h->ensure_norms(maxiter + 1));
-    RET(load_level0(h, b_host, x_host, cudaMemcpyHostToDevice));
+    RET(load_level0(h, b_host, (flags & AMGB_FLAG_X0_ZERO) ? nullptr : x_host, cudaMemcpyHostToDevice));
 
     // normb (multilevel.py:540-542) is only needed by the stop test; reduce it on the device
     double normb = 1.0;
@@ -1485,6 +1499,112 @@ extern "C" int amgb_solve_device(amgb_hierarchy *h, const double *b_dev, double 
     if (norms2_dev != nullptr)
         CK(cudaMemcpyAsync(norms2_dev, h->norms2, sizeof(double) * ((size_t)ncycles + 1),
                            cudaMemcpyDeviceToDevice, s));
+    h->last_launches = h->launches;
+    return AMGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// GPU-resident preconditioned CG: ml.solve(accel='cg') with every vector in HBM.
+// Restates pyamg/krylov/_cg.py:97-196 (criteria 'rr': stop when ||r|| < tol ||b||; r recomputed from
+// b - A x every 8th step, updated by r -= alpha A p otherwise; aborts on p'Ap < 0 or r'z < 0) with
+// M = one multigrid cycle from x0 = 0 (MultilevelSolver.aspreconditioner, multilevel.py:355-396).
+// r lives in the level-0 rhs buffer (the cycle never writes it), z is the cycle's level-0 iterate.
+// Dot products are two-stage with a fixed grid (bit-reproducible); their values are read on the host
+// once per iteration -- two tiny synchronisations against a ~10 ms cycle.
+// ------------------------------------------------------------------------------------------
+static int dev_dot(amgb_hierarchy *h, const double *x, const double *y, long long n, double *out_host)
+{
+    dot_partials_kernel<<<kSumsqBlocks, 256, 0, h->stream>>>(x, y, n, h->sumsq_parts);
+    CK(cudaGetLastError());
+    reduce_partials_kernel<<<1, 1024, 0, h->stream>>>(h->sumsq_parts, kSumsqBlocks, h->norms2);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    CK(cudaMemcpyAsync(h->norm_host, h->norms2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *out_host = h->norm_host[0];
+    return AMGB_OK;
+}
+
+static int dev_axpby(amgb_hierarchy *h, double a, const double *x, double b, double *y, long long n)
+{
+    if (n <= 0) return AMGB_OK;
+    const long long grid = std::min<long long>((n + 255) / 256, (long long)g_num_sms * 16);
+    axpby_kernel<<<(unsigned)grid, 256, 0, h->stream>>>(a, x, b, y, n);
+    CK(cudaGetLastError());
+    h->launches++;
+    return AMGB_OK;
+}
+
+extern "C" int amgb_solve_cg(amgb_hierarchy *h, const double *b_host, double *x_host, double tol, int32_t maxiter,
+                             int32_t cycle, int32_t flags, double *residuals, int32_t *n_residuals, int32_t *info)
+{
+    RET(check_cycle_args(h, cycle, 1));
+    if (b_host == nullptr || x_host == nullptr) return fail(AMGB_EINVAL, "null host vector");
+    if (maxiter < 1) return fail(AMGB_EINVAL, "Number of iterations must be positive");    // _cg.py:95-96
+    CK(cudaSetDevice(h->device));
+    Level &L0 = h->levels[0];
+    const long long n = L0.A.n_rows;
+    cudaStream_t s = h->stream;
+    h->launches = 0;
+    if (h->kry[0] == nullptr)
+        for (int k = 0; k < 4; k++) RET(h->dalloc(&h->kry[k], n + 2));
+    double *xk = h->kry[0], *p = h->kry[1], *Ap = h->kry[2], *bk = h->kry[3];
+    double *r = L0.b;                                     // CG residual = rhs of the preconditioner
+    // b -> bk, x0 -> xk (level-0 numbering)
+    RET(load_level0(h, b_host, (flags & AMGB_FLAG_X0_ZERO) ? nullptr : x_host, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(bk, L0.b, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(xk, L0.x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    auto precond = [&]() -> int {                         // z = M r: one cycle from zero on (L0.x, L0.b = r)
+        L0.x = L0.x_home;
+        RET(h->launch_count_fill(L0.x, n));
+        return h->one_iteration(cycle, 1);
+    };
+    double normb2 = 0, rz = 0, rr = 0, pAp = 0;
+    RET(dev_dot(h, bk, bk, n, &normb2));
+    double normb = std::sqrt(normb2);
+    if (normb == 0.0) normb = 1.0;
+    RET(h->spmv(OP_RESID, L0.A, xk, bk, r));              // r = b - A x        (:99)
+    RET(precond());                                       // z = M r            (:100)
+    CK(cudaMemcpyAsync(p, L0.x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));   // p = z (:101)
+    RET(dev_dot(h, r, L0.x, n, &rz));                     // rz = <r, z>        (:102)
+    RET(dev_dot(h, r, r, n, &rr));
+    std::vector<double> res;
+    res.push_back(std::sqrt(rr));                         // residuals[:] = [normr] (:104-106)
+    const double rtol = tol * normb;                      // criteria 'rr'      (:114-115)
+    int it = 0, status = -2;
+    if (res.back() < rtol) status = 0;                    // :133-134
+    while (status == -2) {
+        RET(h->spmv(OP_SPMV, L0.A, p, nullptr, Ap));      // Ap = A p           (:142)
+        const double rz_old = rz;
+        RET(dev_dot(h, Ap, p, n, &pAp));                  // curvature of A     (:145-148)
+        if (pAp < 0.0) { status = -1; break; }
+        const double alpha = rz / pAp;                    // :150
+        RET(dev_axpby(h, alpha, p, 1.0, xk, n));          // x += alpha p       (:151)
+        if ((it % 8) != 0 && it > 0) {
+            RET(dev_axpby(h, -alpha, Ap, 1.0, r, n));     // r -= alpha Ap      (:153-154)
+        } else {
+            RET(h->spmv(OP_RESID, L0.A, xk, bk, r));      // r = b - A x        (:155-156)
+        }
+        RET(precond());                                   // z = M r            (:158)
+        RET(dev_dot(h, r, L0.x, n, &rz));                 // :159
+        if (rz < 0.0) { status = -1; break; }             // curvature of M     (:161-163)
+        const double beta = rz / rz_old;                  // :165
+        RET(dev_axpby(h, 1.0, L0.x, beta, p, n));         // p = beta p + z     (:166-167)
+        it++;
+        RET(dev_dot(h, r, r, n, &rr));
+        res.push_back(std::sqrt(rr));                     // :171-174
+        if (res.back() < rtol) { status = 0; break; }     // :190-191
+        if (it == maxiter) { status = it; break; }        // :193-194
+    }
+    // x out (original numbering)
+    CK(cudaMemcpyAsync(L0.x_home, xk, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    L0.x = L0.x_home;
+    RET(store_level0(h, x_host, cudaMemcpyDeviceToHost));
+    CK(cudaStreamSynchronize(s));
+    if (residuals != nullptr)
+        for (size_t k = 0; k < res.size() && k < (size_t)maxiter + 1; k++) residuals[k] = res[k];
+    if (n_residuals != nullptr) *n_residuals = (int32_t)res.size();
+    if (info != nullptr) *info = status;
     h->last_launches = h->launches;
     return AMGB_OK;
 }

@@ -77,6 +77,63 @@ def coarse_grid_solver(solver):
     return GenericSolver()
 
 
+def _cg_host(A, b, x0=None, tol=1e-5, maxiter=None, M=None, callback=None, residuals=None):
+    """pyamg.krylov.cg (pyamg/krylov/_cg.py:11-196, criteria 'rr') on the host -- the path taken when a
+    callback needs host iterates; ``M`` is the GPU cycle as a LinearOperator.  Same steps as amgb_solve_cg."""
+    b = np.ravel(np.asarray(b, dtype=np.float64))
+    n = len(b)
+    x = np.zeros(n) if x0 is None else np.array(np.ravel(x0), dtype=np.float64)
+    if maxiter is None:
+        maxiter = int(1.3 * n) + 2
+    elif maxiter < 1:
+        raise ValueError("Number of iterations must be positive")
+    r = b - A @ x
+    z = M @ r
+    p = z.copy()
+    rz = np.inner(r, z)
+    normr = np.linalg.norm(r)
+    if residuals is not None:
+        residuals[:] = [normr]
+    normb = np.linalg.norm(b)
+    if normb == 0.0:
+        normb = 1.0
+    rtol = tol * normb
+    if normr < rtol:
+        return x, 0
+    it = 0
+    while True:
+        Ap = A @ p
+        rz_old = rz
+        pAp = np.inner(Ap, p)
+        if pAp < 0.0:
+            warn("\nIndefinite matrix detected in CG, aborting\n")
+            return x, -1
+        alpha = rz / pAp
+        x += alpha * p
+        if np.mod(it, 8) and it > 0:
+            r -= alpha * Ap
+        else:
+            r = b - A @ x
+        z = M @ r
+        rz = np.inner(r, z)
+        if rz < 0.0:
+            warn("\nIndefinite preconditioner detected in CG, aborting\n")
+            return x, -1
+        beta = rz / rz_old
+        p *= beta
+        p += z
+        it += 1
+        normr = np.linalg.norm(r)
+        if residuals is not None:
+            residuals.append(normr)
+        if callback is not None:
+            callback(x)
+        if normr < rtol:
+            return x, 0
+        if it == maxiter:
+            return x, it
+
+
 class MultilevelSolver:
     """Stores a multigrid hierarchy and runs the multigrid cycle on the GPU.
 
@@ -251,6 +308,30 @@ class MultilevelSolver:
         smoothing.rebuild_smoother(self.levels[0])
         self._invalidate()
 
+    def _solve_cg_device(self, b, x0, tol, maxiter, cycle, residuals, return_info):
+        """solve(accel='cg') on the GPU: pyamg's CG (pyamg/krylov/_cg.py) preconditioned by one cycle."""
+        b = np.asarray(b)
+        n = self.levels[0].A.shape[0]
+        if b.size != n or (x0 is not None and np.asarray(x0).size != n):
+            raise ValueError("b / x0 have invalid dimensions")
+        if maxiter is None:
+            maxiter = int(1.3 * n) + 2                        # _cg.py:92-93
+        elif maxiter < 1:
+            raise ValueError("Number of iterations must be positive")
+        bh = np.ascontiguousarray(np.ravel(b), dtype=np.float64)
+        xh = np.zeros(n) if x0 is None else np.array(np.ravel(x0), dtype=np.float64)
+        res = np.empty(int(maxiter) + 1, dtype=np.float64)
+        nres, info = ctypes.c_int32(0), ctypes.c_int32(0)
+        E.check(E.lib().amgb_solve_cg(self.handle, bh.ctypes.data, xh.ctypes.data, float(tol), int(maxiter),
+                                      E.CYCLES[cycle], E.FLAG_X0_ZERO if x0 is None else 0, E.f64p(res),
+                                      ctypes.byref(nres), ctypes.byref(info)))
+        if info.value == -1:
+            warn("\nIndefinite matrix or preconditioner detected in CG, aborting\n")
+        if residuals is not None:
+            residuals[:] = list(res[:nres.value])
+        xout = xh.reshape(b.shape)
+        return (xout, info.value) if return_info else xout
+
     def psolve(self, b):
         """Legacy interface: one iteration (multilevel.py:339-353)."""
         return self.solve(b, maxiter=1)
@@ -283,32 +364,45 @@ class MultilevelSolver:
             raise TypeError(f"Unrecognized cycle type ({cycle})")      # :658
 
         if accel is not None:
-            # Krylov acceleration: the Krylov method runs in SciPy on the host, every M @ r is one
-            # GPU cycle (multilevel.py:479-535; GPU-resident Krylov is SURVEY.md 8(f)-1)
+            # Check for symmetric smoothing scheme when using CG (multilevel.py:481-485)
             if (accel == "cg") and (not self.symmetric_smoothing):
                 warn("Incompatible non-symmetric multigrid preconditioner "
                      "detected, due to presmoother/postsmoother combination. "
                      "CG requires SPD preconditioner, not just SPD matrix.")
-            if isinstance(accel, str):
+            if accel == "cg" and callback is None and not np.iscomplexobj(b):
+                # pyamg.krylov.cg (what the reference resolves 'cg' to, multilevel.py:495-499) with every
+                # vector resident in HBM: amgb_solve_cg
+                return self._solve_cg_device(b, x0, tol, maxiter, cycle, residuals, return_info)
+            if accel == "cg":
+                accel = _cg_host           # same algorithm on the host (callback wants host iterates)
+            elif isinstance(accel, str):
                 accel = getattr(sla, accel)
             M = self.aspreconditioner(cycle=cycle)
-            if residuals is not None:
-                residuals[:] = [np.linalg.norm(b - A @ x)]
+            try:  # PyAMG style interface which has a residuals parameter (multilevel.py:503-508)
+                x, info = accel(A, b, x0=x0, tol=tol, maxiter=maxiter, M=M, callback=callback,
+                                residuals=residuals)
+                if return_info:
+                    return x, info
+                return x
+            except TypeError:
+                # scipy.sparse.linalg style interface (multilevel.py:509-535)
+                if residuals is not None:
+                    residuals[:] = [np.linalg.norm(b - A @ x)]
 
-                def callback_wrapper(xk):
-                    if np.isscalar(xk):
-                        residuals.append(xk)
-                    else:
-                        residuals.append(np.linalg.norm(b - A @ xk))
-                    if callback is not None:
-                        callback(xk)
-            else:
-                callback_wrapper = callback
-            x, info = accel(A, b, x0=x0, maxiter=maxiter, M=M, callback=callback_wrapper,
-                            rtol=tol, atol=0)
-            if return_info:
-                return x, info
-            return x
+                    def callback_wrapper(xk):
+                        if np.isscalar(xk):
+                            residuals.append(xk)
+                        else:
+                            residuals.append(np.linalg.norm(b - A @ xk))
+                        if callback is not None:
+                            callback(xk)
+                else:
+                    callback_wrapper = callback
+                x, info = accel(A, b, x0=x0, maxiter=maxiter, M=M, callback=callback_wrapper,
+                                rtol=tol, atol=0)
+                if return_info:
+                    return x, info
+                return x
 
         if np.iscomplexobj(b) or np.iscomplexobj(x):
             raise NotImplementedError("complex systems are outside the fp64 hot path")
@@ -329,9 +423,10 @@ class MultilevelSolver:
 
         if callback is None:
             res = np.empty(maxiter + 1, dtype=np.float64)
-            E.check(L.amgb_solve(h, bh.ctypes.data, xh.ctypes.data, float(tol), int(maxiter), cyc,
-                                 int(cycles_per_level), E.f64p(res), ctypes.byref(nres),
-                                 ctypes.byref(info)))
+            flags = E.FLAG_X0_ZERO if x0 is None else 0       # x0 = 0: no host->device copy of the guess
+            E.check(L.amgb_solve_ex(h, bh.ctypes.data, xh.ctypes.data, float(tol), int(maxiter), cyc,
+                                    int(cycles_per_level), flags, E.f64p(res), ctypes.byref(nres),
+                                    ctypes.byref(info)))
             if residuals is not None:
                 residuals[:] = list(res[:nres.value])
             status = info.value

@@ -85,7 +85,7 @@ def kernel_goldens(ml, rng):
     return out
 
 
-def emit(name, ml, extra_kw=None, ncyc=NCYC):
+def emit(name, ml, extra_kw=None, ncyc=NCYC, cg_anyway=True):
     rng = np.random.default_rng(SEED)
     n = ml.levels[0].A.shape[0]
     b = rng.random(n)
@@ -100,6 +100,16 @@ def emit(name, ml, extra_kw=None, ncyc=NCYC):
     xt, info = ml.solve(b, x0=x0, tol=1e-6, maxiter=50, residuals=res, return_info=True)
     extra.update({"x0": x0, "x_ref_tol": xt, "residuals_tol": np.array(res),
                   "info_tol": np.array([info])})
+    if ml.symmetric_smoothing or cg_anyway:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = []
+            xc, info = ml.solve(b, tol=1e-10, maxiter=10, accel="cg", residuals=res, return_info=True)
+            extra.update({"x_ref_cg": xc, "residuals_cg": np.array(res), "info_cg": np.array([info])})
+            res = []
+            xc, info = ml.solve(b, x0=x0, tol=1e-3, maxiter=30, accel="cg", cycle="W", residuals=res, return_info=True)
+            extra.update({"x_ref_cgW": xc, "residuals_cgW": np.array(res), "info_cgW": np.array([info])})
     extra.update(kernel_goldens(ml, rng))
     if extra_kw:
         extra.update(extra_kw)

@@ -294,3 +294,30 @@ def test_distributed_layer_single_rank_on_gpu(name, n_dist, load_golden):
     assert relerr(x, xo) < TOL
     assert np.allclose(np.sqrt(norms[:5].cpu().numpy()), res, rtol=1e-9)
     be.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_gpu_resident_pcg_matches_reference_golden(name, load_golden):
+    """solve(accel='cg') with every vector in HBM (amgb_solve_cg) against the real reference's
+    ml.solve(accel='cg'): same iteration count, info flag, residual history and iterate."""
+    import warnings
+    ml, ex = load_golden(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # non-symmetric smoother pairs warn, exactly like the reference
+        res = []
+        x, info = ml.solve(ex["b"], tol=1e-10, maxiter=10, accel="cg", residuals=res, return_info=True)
+        assert info == int(ex["info_cg"][0]) and len(res) == len(ex["residuals_cg"])
+        assert relerr(x, ex["x_ref_cg"]) < 1e-11
+        assert np.allclose(res, ex["residuals_cg"], rtol=1e-7, atol=1e-12 * ex["residuals_cg"][0])
+        res = []
+        x0 = ex["x0"].copy()
+        x, info = ml.solve(ex["b"], x0=x0, tol=1e-3, maxiter=30, accel="cg", cycle="W", residuals=res, return_info=True)
+        assert np.array_equal(x0, ex["x0"])
+        assert info == int(ex["info_cgW"][0]) and len(res) == len(ex["residuals_cgW"])
+        assert relerr(x, ex["x_ref_cgW"]) < 1e-11
+        # callback path: pyamg's CG on the host with the GPU cycle as M -- same numbers
+        seen = []
+        xc, infoc = ml.solve(ex["b"], tol=1e-10, maxiter=10, accel="cg", callback=lambda xk: seen.append(1),
+                             return_info=True)
+        assert infoc == int(ex["info_cg"][0]) and len(seen) == len(ex["residuals_cg"]) - 1
+        assert relerr(xc, ex["x_ref_cg"]) < 1e-11

@@ -161,3 +161,21 @@ def test_oracle_equals_compiled_reference(name, load_golden):
     a = oracle.Cycle(spec, coarse_pinv=ml.coarse_solver.P, kernels="oracle").solve(ex["b"], tol=0, maxiter=3)
     r = oracle.Cycle(spec, coarse_pinv=ml.coarse_solver.P, kernels="ref").solve(ex["b"], tol=0, maxiter=3)
     assert np.array_equal(a, r)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_oracle_pcg_matches_reference(name, load_golden):
+    """ml.solve(accel='cg') = pyamg.krylov.cg preconditioned by one cycle (multilevel.py:479-508,
+    krylov/_cg.py:97-196): V-cycle from x0 = 0 with tol 1e-10, and W-cycle from x0 with tol 1e-3."""
+    ml, ex = load_golden(name)
+    cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.P)
+    res = []
+    x, info = cyc.solve(ex["b"], tol=1e-10, maxiter=10, accel="cg", residuals=res, return_info=True)
+    assert info == int(ex["info_cg"][0]) and len(res) == len(ex["residuals_cg"])
+    assert relerr(x, ex["x_ref_cg"]) < TIGHT
+    assert np.allclose(res, ex["residuals_cg"], rtol=1e-10)
+    res = []
+    x, info = cyc.solve(ex["b"], x0=ex["x0"], tol=1e-3, maxiter=30, accel="cg", cycle="W", residuals=res,
+                        return_info=True)
+    assert info == int(ex["info_cgW"][0]) and len(res) == len(ex["residuals_cgW"])
+    assert relerr(x, ex["x_ref_cgW"]) < TIGHT
