@@ -26,6 +26,8 @@ def lib():
         L.amgb_setup_classical_interp_fill.argtypes = [i32, _I, _I, _D, _I, _I, _D, _U8, _I, _I, _I, _D]
         L.amgb_setup_greedy_coloring.restype = i32
         L.amgb_setup_greedy_coloring.argtypes = [i32, _I, _I, _I]
+        L.amgb_setup_greedy_coloring_ordered.restype = i32
+        L.amgb_setup_greedy_coloring_ordered.argtypes = [i32, _I, _I, i32, _I]
         L.amgb_setup_coloring_is_valid.restype = i32
         L.amgb_setup_coloring_is_valid.argtypes = [i32, _I, _I, _I]
         _lib = L

@@ -59,6 +59,18 @@ __device__ __forceinline__ double ld_stream_f64(const double *p)
     return v;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still running; it must not touch anything
+// the predecessor produces before pdl_wait().  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 template <int G>
 __device__ __forceinline__ double group_sum(double v)
 {
@@ -94,6 +106,10 @@ __global__ void __launch_bounds__(kCsrThreads) csr_rows_kernel(const CsrRowArgs 
     const long long k = ((long long)blockIdx.x * kCsrThreads + threadIdx.x) / G;
     const bool active = k < a.n;
     double r2 = 0.0;  // this thread's contribution to |r|^2
+    // PDL: the operator (row list, row pointers, entries) is immutable, so its loads may overlap the
+    // tail of the previous launch; every VECTOR access below comes after pdl_wait().  On the small,
+    // latency-bound levels this hides two of the three dependent round trips of a wave.
+    pdl_launch_dependents();
 
     // inactive groups still take part in the shuffles / block reduction below
     int row = 0, start = 0, end = 0;
@@ -117,6 +133,7 @@ __global__ void __launch_bounds__(kCsrThreads) csr_rows_kernel(const CsrRowArgs 
             c[u] = ok ? ld_stream_i32(a.Aj + jj) : -1;
             v[u] = ok ? ld_stream_f64(a.Ax + jj) : 0.0;
         }
+        pdl_wait();
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const bool skip = c[u] < 0 || (kNeedDiag && c[u] == row);
@@ -128,6 +145,7 @@ __global__ void __launch_bounds__(kCsrThreads) csr_rows_kernel(const CsrRowArgs 
             else sum += v[u] * xv[u];
         }
     }
+    pdl_wait();          // rows without entries never entered the loop
     sum = group_sum<G>(sum);
     if (kNeedDiag) {
         // last stored diagonal duplicate wins (relaxation.h:66-69): keep the one with max jj

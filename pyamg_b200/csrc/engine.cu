@@ -84,20 +84,42 @@ static inline long long csr_grid(long long n, int lanes)
     return (n * lanes + kCsrThreads - 1) / kCsrThreads;
 }
 
+static int g_use_pdl = 1;    // AMGB_NO_PDL=1: plain stream-ordered launches for the lanes-per-row kernel
+
+template <int G, int OP, bool INDEXED>
+static int launch_rows_one(const CsrRowArgs &a, unsigned grid, cudaStream_t s)
+{
+    if (!g_use_pdl) {
+        csr_rows_kernel<G, OP, INDEXED><<<grid, kCsrThreads, 0, s>>>(a);
+        return AMGB_OK;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kCsrThreads);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, csr_rows_kernel<G, OP, INDEXED>, a));
+    return AMGB_OK;
+}
+
 template <int OP, bool INDEXED>
 static int launch_csr_g(int lanes, const CsrRowArgs &a, cudaStream_t s)
 {
     if (a.n <= 0) return AMGB_OK;
     const long long grid = csr_grid(a.n, lanes);
     if (grid > 2147483647LL) return fail(AMGB_EINVAL, "launch grid too large");
-    const dim3 g((unsigned)grid), b(kCsrThreads);
+    const unsigned g = (unsigned)grid;
     switch (lanes) {
-    case 1: csr_rows_kernel<1, OP, INDEXED><<<g, b, 0, s>>>(a); break;
-    case 2: csr_rows_kernel<2, OP, INDEXED><<<g, b, 0, s>>>(a); break;
-    case 4: csr_rows_kernel<4, OP, INDEXED><<<g, b, 0, s>>>(a); break;
-    case 8: csr_rows_kernel<8, OP, INDEXED><<<g, b, 0, s>>>(a); break;
-    case 16: csr_rows_kernel<16, OP, INDEXED><<<g, b, 0, s>>>(a); break;
-    case 32: csr_rows_kernel<32, OP, INDEXED><<<g, b, 0, s>>>(a); break;
+    case 1: RET((launch_rows_one<1, OP, INDEXED>(a, g, s))); break;
+    case 2: RET((launch_rows_one<2, OP, INDEXED>(a, g, s))); break;
+    case 4: RET((launch_rows_one<4, OP, INDEXED>(a, g, s))); break;
+    case 8: RET((launch_rows_one<8, OP, INDEXED>(a, g, s))); break;
+    case 16: RET((launch_rows_one<16, OP, INDEXED>(a, g, s))); break;
+    case 32: RET((launch_rows_one<32, OP, INDEXED>(a, g, s))); break;
     default: return fail(AMGB_EINVAL, "lanes must be a power of two in 1..32");
     }
     CK(cudaGetLastError());
@@ -178,6 +200,8 @@ static void tile_configure(size_t smem_per_sm)
     }
     const char *nh = getenv("AMGB_NO_HINTS");
     g_tile_hints = !(nh && nh[0] == '1');
+    const char *np = getenv("AMGB_NO_PDL");
+    g_use_pdl = !(np && np[0] == '1');
 }
 
 template <int OP, class C>
@@ -540,7 +564,10 @@ struct amgb_hierarchy {
     // coarse tail: levels >= tail_level run inside one cluster kernel (tail_kernel.cuh)
     int tail_level = 1 << 30;
     int tail_csize = 1;
-    long long tail_nnz_limit = 600000;     // AMGB_TAIL_NNZ: levels at most this large run in the cluster tail
+    // AMGB_TAIL_NNZ: levels with at most this many entries run in the cluster tail kernel.  Default 0 = off:
+    // with programmatic dependent launch the per-wave launches of a CUDA graph pipeline better (measured
+    // 9.8 ms vs 10.3 ms per 256^3 cycle, profiles/r01_tune_small_levels.txt); the tail remains selectable.
+    long long tail_nnz_limit = 0;
     double tail_solo_bytes = 400000.0;     // AMGB_TAIL_SOLO_BYTES: steps moving at most this much run on one CTA
     long long tile_min_nnz = 1500000;            // AMGB_TILE_MIN_NNZ: smaller launches use the lanes-per-row kernel
     bool recording = false;
@@ -1293,7 +1320,7 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
     {   // coarse tail: the deepest run of levels whose operators are all small and block-smoother free
         const char *nt = getenv("AMGB_NO_TAIL");
         const char *tn = getenv("AMGB_TAIL_NNZ");
-        if (tn && atoll(tn) > 0) h->tail_nnz_limit = atoll(tn);
+        if (tn && atoll(tn) >= 0) h->tail_nnz_limit = atoll(tn);
         const char *sb = getenv("AMGB_TAIL_SOLO_BYTES");
         if (sb) h->tail_solo_bytes = atof(sb);
         const char *tm = getenv("AMGB_TILE_MIN_NNZ");

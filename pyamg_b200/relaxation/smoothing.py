@@ -97,7 +97,7 @@ def setup_sor(lvl, omega=0.5, iterations=DEFAULT_NITER, sweep=DEFAULT_SWEEP):
 
 
 def setup_gauss_seidel_indexed(lvl, indices=None, iterations=DEFAULT_NITER, sweep=DEFAULT_SWEEP,
-                               coloring="greedy"):
+                               coloring="smallest_last"):
     """Multi-colour Gauss-Seidel: ``relaxation.gauss_seidel_indexed`` over rows sorted by colour
     (``order = argsort(colours, kind='stable')``).  If ``indices`` is not
     given a vertex colouring of A's graph is computed here."""

@@ -68,7 +68,9 @@ def test_vcycle_matches_oracle_on_fresh_rhs(name, load_golden):
                                  {"AMGB_TILE_G": "4"}, {"AMGB_TILE_G": "32"}, {"AMGB_TILE_CFG": "0"}, {"AMGB_TILE_CFG": "1"},
                                  {"AMGB_TILE_CFG": "4"},
                                  {"AMGB_TILE_CFG": "3", "AMGB_NO_HINTS": "1"}, {"AMGB_NO_TAIL": "1"},
-                                 {"AMGB_TAIL_CLUSTER": "1"}, {"AMGB_TAIL_CLUSTER": "4"}])
+                                 {"AMGB_TAIL_NNZ": "600000"}, {"AMGB_TAIL_NNZ": "600000", "AMGB_TAIL_CLUSTER": "1"},
+                                 {"AMGB_TAIL_NNZ": "600000", "AMGB_TAIL_CLUSTER": "4"}, {"AMGB_NO_PDL": "1"},
+                                 {"AMGB_NO_TAIL": "1", "AMGB_NO_TILES": "1"}, {"AMGB_TAIL_NNZ": "600000", "AMGB_TAIL_SOLO_BYTES": "0"}])
 @pytest.mark.parametrize("name", GOLDEN)
 def test_every_kernel_path_matches_reference_golden(name, env, monkeypatch):
     """The lanes-per-row kernels, the un-permuted layout, the un-graphed cycle, forced lane-group widths

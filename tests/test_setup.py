@@ -37,11 +37,12 @@ def test_gallery_matches_reference_operators(load_golden):
         stencil_grid(np.ones((2, 2)), (4, 4))
 
 
+@pytest.mark.parametrize("method", ["greedy", "smallest_last", "LDF"])
 @pytest.mark.parametrize("grid", [(17,), (9, 11), (6, 5, 7)])
-def test_greedy_coloring_is_valid_and_red_black_on_stencils(grid):
+def test_greedy_coloring_is_valid_and_red_black_on_stencils(grid, method):
     """pyamg/tests/test_graph.py:41-47 criterion: no edge joins equal colours; all colours used."""
     A = poisson(grid)
-    c = vertex_coloring(A)
+    c = vertex_coloring(A, method)
     coo = A.tocoo()
     off = coo.row != coo.col
     assert np.all(c[coo.row[off]] != c[coo.col[off]])
@@ -59,3 +60,18 @@ def test_setup_rejects_options_outside_its_scope():
         ruge_stuben_solver(A, CF="PMIS")
     with pytest.raises(NotImplementedError):
         ruge_stuben_solver(A, interpolation="direct")
+
+
+def test_colorings_are_valid_on_dense_coarse_operators(load_golden):
+    """Coarse RS operators (unsorted columns, 20-100 entries per row): every method yields a proper colouring,
+    smallest-last never needs more colours than the degeneracy bound allows."""
+    ml, _ = load_golden("cfg3_rs_mcgs_poisson3d")
+    for lvl in ml.levels[1:-1]:
+        coo = lvl.A.tocoo()
+        off = coo.row != coo.col
+        for method in ("greedy", "smallest_last", "LDF"):
+            c = vertex_coloring(lvl.A, method)
+            assert np.all(c[coo.row[off]] != c[coo.col[off]]), method
+            assert c.max() + 1 <= np.diff(lvl.A.indptr).max()
+    with pytest.raises(NotImplementedError):
+        vertex_coloring(ml.levels[0].A, "JP")
