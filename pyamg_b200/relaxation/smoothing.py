@@ -103,8 +103,15 @@ def setup_gauss_seidel_indexed(lvl, indices=None, iterations=DEFAULT_NITER, swee
     given a vertex colouring of A's graph is computed here."""
     if indices is None:
         from ..graph import vertex_coloring
-        colors = vertex_coloring(lvl.A, method=coloring)
-        indices = np.argsort(colors, kind="stable").astype(np.int32)
+        cache = getattr(lvl.A, "_b200_color_order", None)       # pre and post usually ask for the same list
+        if cache is None or cache[0] != coloring:
+            colors = vertex_coloring(lvl.A, method=coloring)
+            cache = (coloring, np.argsort(colors, kind="stable").astype(np.int32))
+            try:
+                lvl.A._b200_color_order = cache
+            except AttributeError:
+                pass
+        indices = cache[1]
     smoother = partial(relaxation.gauss_seidel_indexed, indices=np.asarray(indices, dtype=np.int32),
                        iterations=iterations, sweep=sweep)
     update_wrapper(smoother, relaxation.gauss_seidel_indexed)
