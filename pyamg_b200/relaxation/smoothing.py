@@ -97,12 +97,17 @@ def setup_sor(lvl, omega=0.5, iterations=DEFAULT_NITER, sweep=DEFAULT_SWEEP):
 
 
 def setup_gauss_seidel_indexed(lvl, indices=None, iterations=DEFAULT_NITER, sweep=DEFAULT_SWEEP,
-                               coloring="smallest_last"):
+                               coloring="auto"):
     """Multi-colour Gauss-Seidel: ``relaxation.gauss_seidel_indexed`` over rows sorted by colour
     (``order = argsort(colours, kind='stable')``).  If ``indices`` is not
-    given a vertex colouring of A's graph is computed here."""
+    given a vertex colouring of A's graph is computed here.  ``coloring='auto'``: natural-order greedy on
+    big levels (its lattice-like colour classes keep the x gathers local: smallest-last was measured 30 %
+    slower on the 8.4 M-row level of the 256^3 hierarchy) and smallest-last below 2 M rows, where the
+    number of dependent waves, not bandwidth, decides (60 -> 52 colours on the densest level)."""
     if indices is None:
         from ..graph import vertex_coloring
+        if coloring == "auto":
+            coloring = "greedy" if lvl.A.shape[0] > 2_000_000 else "smallest_last"
         cache = getattr(lvl.A, "_b200_color_order", None)       # pre and post usually ask for the same list
         if cache is None or cache[0] != coloring:
             colors = vertex_coloring(lvl.A, method=coloring)
