@@ -24,11 +24,29 @@ def nvcc_path():
     return None
 
 
+def _digest(paths):
+    """Content hash of the sources: file times do not survive the copy to the GPU box."""
+    import hashlib
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        if os.path.exists(p):
+            h.update(os.path.basename(p).encode())
+            h.update(open(p, "rb").read())
+    return h.hexdigest()
+
+
+def _stamp_ok(lib, paths):
+    stamp = lib + ".sha256"
+    return os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == _digest(paths)
+
+
+def _write_stamp(lib, paths):
+    with open(lib + ".sha256", "w") as f:
+        f.write(_digest(paths))
+
+
 def is_stale():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(s) > t for s in SOURCES + HEADERS if os.path.exists(s))
+    return not _stamp_ok(LIB, SOURCES + HEADERS)
 
 
 HOST_LIB = os.path.join(PKG, "libpyamg_b200_host.so")
@@ -37,9 +55,7 @@ HOST_SOURCES = [os.path.join(PKG, "csrc", "host_setup.cpp")]
 
 def build_host_library(force=False, verbose=False):
     """Compile the host-side setup helpers (plain C++, no CUDA). Returns the .so path."""
-    stale = (not os.path.exists(HOST_LIB)) or any(
-        os.path.getmtime(s) > os.path.getmtime(HOST_LIB) for s in HOST_SOURCES)
-    if not force and not stale:
+    if not force and _stamp_ok(HOST_LIB, HOST_SOURCES):
         return HOST_LIB
     cxx = shutil.which("g++")
     if cxx is None:
@@ -50,6 +66,7 @@ def build_host_library(force=False, verbose=False):
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
+    _write_stamp(HOST_LIB, HOST_SOURCES)
     return HOST_LIB
 
 
@@ -69,6 +86,7 @@ def build_extension(force=False, verbose=False):
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
+    _write_stamp(LIB, SOURCES + HEADERS)
     return LIB
 
 

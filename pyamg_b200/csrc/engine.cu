@@ -192,10 +192,7 @@ static void tile_configure(size_t smem_per_sm)
     switch (g_tile_cfg) {
     case 0: tile_cfg_select<TileCfg0>(smem_per_sm); break;
     case 1: tile_cfg_select<TileCfg1>(smem_per_sm); break;
-    case 2: tile_cfg_select<TileCfg2>(smem_per_sm); break;
-    case 3: tile_cfg_select<TileCfg3>(smem_per_sm); break;
     case 4: tile_cfg_select<TileCfg4>(smem_per_sm); break;
-    case 5: tile_cfg_select<TileCfg5>(smem_per_sm); break;
     default: g_tile_cfg = 6; tile_cfg_select<TileCfg6>(smem_per_sm); break;
     }
     const char *nh = getenv("AMGB_NO_HINTS");
@@ -240,10 +237,7 @@ static int launch_tile_op(int G, const TileArgs &a, int grid, cudaStream_t s)
     switch (g_tile_cfg) {
     case 0: return launch_tile_cfg<OP, TileCfg0>(G, a, grid, s);
     case 1: return launch_tile_cfg<OP, TileCfg1>(G, a, grid, s);
-    case 2: return launch_tile_cfg<OP, TileCfg2>(G, a, grid, s);
-    case 3: return launch_tile_cfg<OP, TileCfg3>(G, a, grid, s);
     case 4: return launch_tile_cfg<OP, TileCfg4>(G, a, grid, s);
-    case 5: return launch_tile_cfg<OP, TileCfg5>(G, a, grid, s);
     default: return launch_tile_cfg<OP, TileCfg6>(G, a, grid, s);
     }
 }

@@ -53,10 +53,7 @@ struct TileCfg {
 };
 using TileCfg0 = TileCfg<512, 128, 2, 8>;
 using TileCfg1 = TileCfg<256, 64, 2, 8>;
-using TileCfg2 = TileCfg<256, 64, 3, 8>;
-using TileCfg3 = TileCfg<128, 32, 4, 8>;
 using TileCfg4 = TileCfg<256, 64, 1, 8>;     // single stage, ~48 warps/SM: cross-warp overlap only
-using TileCfg5 = TileCfg<128, 32, 2, 8>;     // ~1.3 KB stages, 6+ CTAs/SM
 using TileCfg6 = TileCfg<224, 64, 1, 8>;     // 32 seven-point rows per tile; 7-8 CTAs/SM = 56-64 warps/SM
 
 // the b / x_old slices are staged only for the epilogues that read them: shared memory is what limits

@@ -67,7 +67,7 @@ def test_vcycle_matches_oracle_on_fresh_rhs(name, load_golden):
                                  {"AMGB_NO_TILES": "1", "AMGB_NO_PERMUTE": "1"}, {"AMGB_NO_GRAPH": "1"},
                                  {"AMGB_TILE_G": "4"}, {"AMGB_TILE_G": "32"}, {"AMGB_TILE_CFG": "0"}, {"AMGB_TILE_CFG": "1"},
                                  {"AMGB_TILE_CFG": "4"},
-                                 {"AMGB_TILE_CFG": "3", "AMGB_NO_HINTS": "1"}, {"AMGB_NO_TAIL": "1"},
+                                 {"AMGB_TILE_CFG": "4", "AMGB_NO_HINTS": "1"}, {"AMGB_NO_TAIL": "1"},
                                  {"AMGB_TAIL_NNZ": "600000"}, {"AMGB_TAIL_NNZ": "600000", "AMGB_TAIL_CLUSTER": "1"},
                                  {"AMGB_TAIL_NNZ": "600000", "AMGB_TAIL_CLUSTER": "4"}, {"AMGB_NO_PDL": "1"},
                                  {"AMGB_NO_TAIL": "1", "AMGB_NO_TILES": "1"}, {"AMGB_TAIL_NNZ": "600000", "AMGB_TAIL_SOLO_BYTES": "0"}])

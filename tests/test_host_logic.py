@@ -150,3 +150,51 @@ def test_hierarchy_io_roundtrip_and_reports(name, load_golden, tmp_path):
     assert ml.cycle_complexity("W") >= ml.cycle_complexity("F") >= ml.cycle_complexity("V")
     with pytest.raises(TypeError):
         ml.cycle_complexity("Z")
+
+
+@pytest.mark.parametrize("seed,symmetric,kind", [(1, True, "perm"), (2, False, "perm"), (3, False, "repeats"),
+                                                 (4, True, "natural"), (5, False, "subset")])
+def test_wave_schedule_reproduces_the_sequential_sweep(seed, symmetric, kind):
+    """The engine's dependency-wave rule (csrc/engine.cu build_waves == amgb_wave_schedule): executing the
+    waves in order -- rows of one wave in ANY order, here reversed -- gives exactly the sequential
+    gauss_seidel_indexed sweep, for symmetric and non-symmetric patterns, permutations, repeated and partial
+    row lists; and no wave contains two rows that reference each other."""
+    import oracle
+    from pyamg_b200.dist import wave_schedule
+    rng = np.random.default_rng(seed)
+    n = 120
+    M = sp.random(n, n, density=0.06, random_state=seed, format="csr")
+    if symmetric:
+        M = (M + M.T).tocsr()
+    A = (M + sp.diags_array(4.0 + rng.random(n))).tocsr()
+    A.indptr, A.indices = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    if kind == "perm":
+        lst = rng.permutation(n).astype(np.int32)
+    elif kind == "repeats":
+        lst = rng.integers(0, n, size=2 * n).astype(np.int32)
+    elif kind == "subset":
+        lst = rng.permutation(n)[: n // 3].astype(np.int32)
+    else:
+        lst = None
+    wave, nw = wave_schedule(A, lst)
+    rows = np.arange(n, dtype=np.int32) if lst is None else lst
+    assert wave.min() == 1 and wave.max() == nw
+    x0, b = rng.random(n), rng.random(n)
+    xs = x0.copy()
+    oracle.gauss_seidel_indexed(A, xs, b, rows, sweep="forward")
+    xw = x0.copy()
+    pattern = (A != 0).astype(np.int8)
+    for w in range(1, nw + 1):
+        members = rows[wave == w][::-1]
+        sub = pattern[members][:, members]
+        assert sub.nnz == len(np.unique(members)) or len(np.unique(members)) < len(members) or \
+            (sub - sp.diags_array(sub.diagonal())).nnz == 0
+        oracle.gauss_seidel_indexed(A, xw, b, members.astype(np.int32), sweep="forward")
+    assert np.array_equal(xw, xs)
+    # the backward sweep is the waves in reverse order
+    xs = x0.copy()
+    oracle.gauss_seidel_indexed(A, xs, b, rows, sweep="backward")
+    xw = x0.copy()
+    for w in range(nw, 0, -1):
+        oracle.gauss_seidel_indexed(A, xw, b, rows[wave == w].astype(np.int32), sweep="forward")
+    assert np.array_equal(xw, xs)
