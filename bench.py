@@ -50,16 +50,27 @@ def peak_hbm():
         return 6650.0, "fallback"
 
 
+WORKLOAD = {"name": "cfg3"}      # set by --workload; the default is BASELINE.json's headline config
+
+
 def build_hierarchy(grid, stream=None, device=0):
-    """poisson(grid) + RS hierarchy + multi-colour symmetric GS on every level (BASELINE configs[2])."""
+    """cfg3 (default): poisson(grid) + RS hierarchy + multi-colour symmetric GS on every level (BASELINE
+    configs[2]).  cfg2: 2-D poisson(grid[:2]) + smoothed aggregation + weighted Jacobi (BASELINE configs[1])."""
     from pyamg_b200.gallery import poisson
     from pyamg_b200.classical import ruge_stuben_solver
+    from pyamg_b200.aggregation import smoothed_aggregation_solver
     t0 = time.time()
-    A = poisson(grid)
-    t1 = time.time()
-    sm = ("gauss_seidel_indexed", {"sweep": "symmetric"})
     np.random.seed(SEED)
-    ml = ruge_stuben_solver(A, presmoother=sm, postsmoother=sm, device=device, stream=stream)
+    if WORKLOAD["name"] == "cfg2":
+        A = poisson(tuple(grid)[:2])
+        t1 = time.time()
+        sm = ("jacobi", {"omega": 4.0 / 3.0})
+        ml = smoothed_aggregation_solver(A, presmoother=sm, postsmoother=sm, device=device, stream=stream)
+    else:
+        A = poisson(grid)
+        t1 = time.time()
+        sm = ("gauss_seidel_indexed", {"sweep": "symmetric"})
+        ml = ruge_stuben_solver(A, presmoother=sm, postsmoother=sm, device=device, stream=stream)
     t2 = time.time()
     log(f"gallery {t1 - t0:.1f}s, setup {t2 - t1:.1f}s, levels {[lv.A.shape[0] for lv in ml.levels]}, "
         f"op-cx {ml.operator_complexity():.3f}")
@@ -175,6 +186,13 @@ def ncu_traffic(ml, dk):
 
 
 def workload_config(grid, ml, ngpus):
+    if WORKLOAD["name"] == "cfg2":
+        return {"workload": f"gallery.poisson({tuple(grid)[:2]}) 5-pt fp64 CSR, smoothed_aggregation_solver hierarchy "
+                            f"({len(ml.levels)} levels, op-cx {ml.operator_complexity():.3f}), weighted Jacobi omega=4/3 "
+                            "pre+post, pinv coarse solve, V(1,1)-cycle + per-cycle residual check",
+                "n": int(ml.levels[0].A.shape[0]), "nnz": int(ml.levels[0].A.nnz),
+                "sum_nnz_A": int(sum(lv.A.nnz for lv in ml.levels)),
+                "parallelism": "1 GPU" if ngpus == 1 else f"{ngpus} GPUs", "l2": "inputs larger than L2"}
     return {"workload": f"gallery.poisson({tuple(grid)}) 7-pt fp64 CSR, ruge_stuben_solver hierarchy "
                         f"({len(ml.levels)} levels, op-cx {ml.operator_complexity():.3f}), symmetric multi-colour "
                         "Gauss-Seidel pre+post (gauss_seidel_indexed over colour-sorted rows), pinv coarse solve, "
@@ -298,7 +316,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=256, help="grid points per dimension (3-D)")
     ap.add_argument("--cpu-sample", type=int, default=2, help="V-cycles timed for cpu_baseline")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2"],
+                    help="cfg3 = BASELINE configs[2] (headline, default); cfg2 = configs[1]: 2-D Poisson, SA + Jacobi "
+                         "(use --grid 2000)")
     args = ap.parse_args()
+    WORKLOAD["name"] = args.workload
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     grid = (args.grid,) * 3
 

@@ -28,6 +28,12 @@ def lib():
         L.amgb_setup_greedy_coloring.argtypes = [i32, _I, _I, _I]
         L.amgb_setup_greedy_coloring_ordered.restype = i32
         L.amgb_setup_greedy_coloring_ordered.argtypes = [i32, _I, _I, i32, _I]
+        L.amgb_setup_symmetric_strength.restype = ctypes.c_int64
+        L.amgb_setup_symmetric_strength.argtypes = [i32, _I, _I, _D, f64, _I, _I]
+        L.amgb_setup_standard_aggregation.restype = i32
+        L.amgb_setup_standard_aggregation.argtypes = [i32, _I, _I, _I, _I]
+        L.amgb_setup_gauss_seidel.restype = None
+        L.amgb_setup_gauss_seidel.argtypes = [i32, _I, _I, _D, _D, _D, i32, i32]
         L.amgb_setup_coloring_is_valid.restype = i32
         L.amgb_setup_coloring_is_valid.argtypes = [i32, _I, _I, _I]
         _lib = L

@@ -349,6 +349,102 @@ int32_t amgb_setup_greedy_coloring_ordered(int32_t n, const int32_t *Ap, const i
     return ncol;
 }
 
+// ---- smoothed aggregation (scalar problems) --------------------------------------------------------
+// Symmetric strength (Vanek/Mandel/Brezina 1996): keep a_ij, i != j, iff |a_ij|^2 >= theta^2 |a_ii| |a_jj|;
+// the diagonal is always kept.  Only the pattern is returned (aggregation uses nothing else).
+//   <-> symmetric_strength_of_connection, pyamg/amg_core/smoothed_aggregation.h:56-108
+int64_t amgb_setup_symmetric_strength(int32_t n, const int32_t *Ap, const int32_t *Aj, const double *Ax,
+                                      double theta, int32_t *Sp, int32_t *Sj)
+{
+    std::vector<double> diag((size_t)n, 0.0);
+    for (int32_t i = 0; i < n; i++) {
+        double d = 0.0;
+        for (int32_t jj = Ap[i]; jj < Ap[i + 1]; jj++)
+            if (Aj[jj] == i) d += Ax[jj];                 // duplicates of the diagonal are summed
+        diag[(size_t)i] = std::fabs(d);
+    }
+    int64_t nnz = 0;
+    Sp[0] = 0;
+    for (int32_t i = 0; i < n; i++) {
+        const double eps_i = theta * theta * diag[(size_t)i];
+        for (int32_t jj = Ap[i]; jj < Ap[i + 1]; jj++) {
+            const int32_t j = Aj[jj];
+            if (j == i || Ax[jj] * Ax[jj] >= eps_i * diag[(size_t)j]) Sj[nnz++] = j;
+        }
+        Sp[i + 1] = (int32_t)nnz;
+    }
+    return nnz;
+}
+
+// Standard (greedy, three-pass) aggregation on the strength pattern: pass 1 turns every node whose
+// neighbourhood is still free into the root of an aggregate together with its neighbours; pass 2 attaches
+// leftover nodes to an adjacent aggregate; pass 3 aggregates what remains.  agg[i] = aggregate id or -1
+// (isolated node); roots[] receives the root node of every aggregate.  Returns the number of aggregates.
+//   <-> standard_aggregation, pyamg/amg_core/smoothed_aggregation.h:138-236
+int32_t amgb_setup_standard_aggregation(int32_t n, const int32_t *Sp, const int32_t *Sj, int32_t *agg,
+                                        int32_t *roots)
+{
+    const int32_t FREE = -2, ISOLATED = -1;
+    std::vector<int32_t> tentative((size_t)n, -1);       // pass-2 attachments, resolved after the pass
+    for (int32_t i = 0; i < n; i++) agg[i] = FREE;
+    int32_t count = 0;
+    for (int32_t i = 0; i < n; i++) {                    // pass 1
+        if (agg[i] != FREE) continue;
+        bool any = false, taken = false;
+        for (int32_t jj = Sp[i]; jj < Sp[i + 1] && !taken; jj++) {
+            const int32_t j = Sj[jj];
+            if (j == i) continue;
+            any = true;
+            if (agg[j] != FREE) taken = true;
+        }
+        if (!any) { agg[i] = ISOLATED; continue; }
+        if (taken) continue;
+        roots[count] = i;
+        agg[i] = count;
+        for (int32_t jj = Sp[i]; jj < Sp[i + 1]; jj++) agg[Sj[jj]] = count;
+        count++;
+    }
+    for (int32_t i = 0; i < n; i++) {                    // pass 2: join a neighbour's PASS-1 aggregate
+        if (agg[i] != FREE) continue;
+        for (int32_t jj = Sp[i]; jj < Sp[i + 1]; jj++) {
+            const int32_t a = agg[Sj[jj]];
+            if (a >= 0) { tentative[(size_t)i] = a; break; }
+        }
+    }
+    for (int32_t i = 0; i < n; i++)
+        if (agg[i] == FREE && tentative[(size_t)i] >= 0) agg[i] = tentative[(size_t)i];
+    for (int32_t i = 0; i < n; i++) {                    // pass 3
+        if (agg[i] != FREE) continue;
+        roots[count] = i;
+        agg[i] = count;
+        for (int32_t jj = Sp[i]; jj < Sp[i + 1]; jj++)
+            if (agg[Sj[jj]] == FREE) agg[Sj[jj]] = count;
+        count++;
+    }
+    return count;
+}
+
+// Sequential Gauss-Seidel sweeps on the host for candidate improvement during setup (A x = b, in place);
+// `symmetric` != 0: forward then backward per iteration.  Zero diagonal leaves the row untouched.
+void amgb_setup_gauss_seidel(int32_t n, const int32_t *Ap, const int32_t *Aj, const double *Ax, double *x,
+                             const double *b, int32_t iterations, int32_t symmetric)
+{
+    auto sweep = [&](int32_t start, int32_t stop, int32_t step) {
+        for (int32_t i = start; i != stop; i += step) {
+            double rsum = 0.0, d = 0.0;
+            for (int32_t jj = Ap[i]; jj < Ap[i + 1]; jj++) {
+                if (Aj[jj] == i) d = Ax[jj];
+                else rsum += Ax[jj] * x[Aj[jj]];
+            }
+            if (d != 0.0) x[i] = (b[i] - rsum) / d;
+        }
+    };
+    for (int32_t it = 0; it < iterations; it++) {
+        sweep(0, n, 1);
+        if (symmetric) sweep(n - 1, -1, -1);
+    }
+}
+
 // 1 if no stored off-diagonal entry joins two rows of equal colour (checks a colouring computed on a
 // pattern assumed symmetric), else 0.
 int32_t amgb_setup_coloring_is_valid(int32_t n, const int32_t *Ap, const int32_t *Aj, const int32_t *colors)
