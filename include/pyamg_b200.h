@@ -224,6 +224,11 @@ int amgb_dev_dense_matvec(int32_t m, int32_t n, const double *M, const double *x
 int amgb_dev_fill(double *x, int64_t n, double v, void *stream);
 /* out[i] = in[idx[i]] (halo packing, permuted layouts) */
 int amgb_dev_gather(const double *in, const int32_t *idx, double *out, int64_t n, void *stream);
+/* HOST helper (no CUDA): the TMA tile list for a CSR row-pointer array under geometry (T, RMAX), G lanes per
+ * row and optional row breaks; row0/nz0 get n_tiles+1 descriptors (sentinel last). For tests of the tiling rules. */
+int amgb_debug_build_tiles(int32_t n, const int32_t *Ap, int32_t G, const int64_t *breaks, int32_t n_breaks,
+                           int32_t T, int32_t RMAX, int32_t *row0, int32_t *nz0, int32_t cap, int32_t *tile_ptr,
+                           int32_t *n_tiles);
 /* HOST helper (no CUDA): dependency waves of the sequential sweep over `list` (NULL = 0..n-1);
  * wave_of[k] is the 1-based wave of list position k. */
 int amgb_wave_schedule(int32_t n, const int32_t *Ap, const int32_t *Aj, const int32_t *list, int64_t m,

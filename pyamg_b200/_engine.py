@@ -55,7 +55,7 @@ SYMBOLS = [
     "amgb_host_bsr_jacobi", "amgb_host_block_jacobi", "amgb_host_matvec",
     "amgb_dev_csr_spmv", "amgb_dev_csr_residual", "amgb_dev_csr_spmv_add", "amgb_dev_csr_jacobi",
     "amgb_dev_csr_gs_wave", "amgb_dev_partials_len", "amgb_dev_dense_matvec", "amgb_dev_fill",
-    "amgb_dev_gather", "amgb_wave_schedule",
+    "amgb_dev_gather", "amgb_wave_schedule", "amgb_debug_build_tiles",
 ]
 
 
@@ -120,6 +120,8 @@ def lib():
     L.amgb_dev_dense_matvec.argtypes = [i32, i32, vp, vp, vp, vp]
     L.amgb_dev_fill.argtypes = [vp, i64, f64, vp]
     L.amgb_dev_gather.argtypes = [vp, vp, vp, i64, vp]
+    L.amgb_debug_build_tiles.argtypes = [i32, c_i32p, i32, ctypes.POINTER(ctypes.c_int64), i32, i32, i32, c_i32p,
+                                         c_i32p, i32, c_i32p, c_i32p]
     L.amgb_wave_schedule.argtypes = [i32, c_i32p, c_i32p, c_i32p, i64, c_i32p, c_i32p]
     _lib = L
     return L

@@ -1748,6 +1748,39 @@ extern "C" int amgb_operator_apply(amgb_operator *op, int32_t kind, const double
     return AMGB_OK;
 }
 
+// HOST helper (no CUDA): the tile list the engine would build for a CSR row-pointer array under the
+// geometry (T entries, RMAX rows per tile) with G lanes per row and optional row breaks (e.g. wave
+// boundaries, n_breaks+1 ascending entries starting at 0).  row0/nz0 receive n_tiles+1 descriptors (sentinel
+// last, capacity `cap`), tile_ptr (if non-null, n_breaks+1 entries) the tile range of every break range.
+// Exposed so the tiling invariants can be tested without a GPU.
+extern "C" int amgb_debug_build_tiles(int32_t n, const int32_t *Ap, int32_t G, const int64_t *breaks,
+                                      int32_t n_breaks, int32_t T, int32_t RMAX, int32_t *row0, int32_t *nz0,
+                                      int32_t cap, int32_t *tile_ptr, int32_t *n_tiles)
+{
+    if (Ap == nullptr || row0 == nullptr || nz0 == nullptr || n_tiles == nullptr || n < 0)
+        return fail(AMGB_EINVAL, "build_tiles: bad arguments");
+    if (G < 1 || G > 32 || (G & (G - 1)) || T < 1 || RMAX < 1) return fail(AMGB_EINVAL, "build_tiles: bad geometry");
+    HostCsr H;
+    H.n_rows = H.n_cols = n;
+    H.Ap.assign(Ap, Ap + n + 1);
+    const int saveT = g_tile_T, saveR = g_tile_rmax;
+    g_tile_T = T;
+    g_tile_rmax = RMAX;
+    std::vector<TileDesc> tiles;
+    std::vector<int> tp;
+    std::vector<long long> br;
+    if (breaks != nullptr) br.assign(breaks, breaks + n_breaks + 1);
+    build_tiles(H, G, breaks ? &br : nullptr, tiles, breaks ? &tp : nullptr);
+    g_tile_T = saveT;
+    g_tile_rmax = saveR;
+    if ((int)tiles.size() > cap) return fail(AMGB_EINVAL, "build_tiles: output capacity too small");
+    for (size_t t = 0; t < tiles.size(); t++) { row0[t] = tiles[t].row0; nz0[t] = tiles[t].nz0; }
+    if (tile_ptr != nullptr && breaks != nullptr)
+        for (size_t w = 0; w < tp.size(); w++) tile_ptr[w] = tp[w];
+    *n_tiles = (int32_t)tiles.size() - 1;
+    return AMGB_OK;
+}
+
 // Dependency waves of a sequential sweep (host only, no CUDA): wave_of[k] (1-based) for list position k.
 // The multi-GPU layer uses it to give every rank the same global wave structure.
 extern "C" int amgb_wave_schedule(int32_t n, const int32_t *Ap, const int32_t *Aj, const int32_t *list, int64_t m,

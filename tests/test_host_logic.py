@@ -198,3 +198,44 @@ def test_wave_schedule_reproduces_the_sequential_sweep(seed, symmetric, kind):
     for w in range(nw, 0, -1):
         oracle.gauss_seidel_indexed(A, xw, b, rows[wave == w].astype(np.int32), sweep="forward")
     assert np.array_equal(xw, xs)
+
+
+@pytest.mark.parametrize("G,T,RMAX", [(1, 224, 64), (2, 224, 64), (4, 256, 64), (1, 512, 128), (32, 224, 64)])
+def test_tile_builder_invariants(G, T, RMAX):
+    """The TMA tile list (csrc/engine.cu build_tiles): tiles are consecutive whole-row ranges covering every
+    row once, hold <= T entries and <= RMAX rows unless they are a single over-long row, never cross a break
+    (Gauss-Seidel wave boundary), empty break ranges get empty tile ranges, and multi-pass tiles are cut to a
+    multiple of the rows reduced per pass (32/G)."""
+    rng = np.random.default_rng(G * 1000 + T)
+    n = 3000
+    lens = rng.integers(0, 40, size=n)
+    lens[rng.integers(0, n, size=5)] = T + 50            # rows longer than a tile
+    lens[100:140] = 0                                    # a run of empty rows
+    Ap = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    cuts = np.unique(np.concatenate([[0, n], rng.integers(0, n, size=12)]))
+    breaks = np.sort(np.concatenate([cuts, cuts[3:5]])).astype(np.int64)       # duplicated cuts = empty waves
+    for use_breaks in (False, True):
+        cap = n + 8
+        row0, nz0 = np.empty(cap, dtype=np.int32), np.empty(cap, dtype=np.int32)
+        tp = np.empty(len(breaks), dtype=np.int32)
+        nt = ctypes.c_int32(0)
+        E.check(E.lib().amgb_debug_build_tiles(n, E.i32p(Ap), G, breaks.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+                                               if use_breaks else None, len(breaks) - 1, T, RMAX, E.i32p(row0),
+                                               E.i32p(nz0), cap, E.i32p(tp) if use_breaks else None, ctypes.byref(nt)))
+        nt = nt.value
+        r, z = row0[:nt + 1], nz0[:nt + 1]
+        assert r[0] == 0 and r[-1] == n and np.all(np.diff(r) >= 1)
+        assert np.array_equal(z, Ap[r])
+        rows, ents = np.diff(r), np.diff(z)
+        assert np.all((ents <= T) | (rows == 1))
+        assert np.all(rows <= RMAX)
+        if use_breaks:
+            assert np.all(np.isin(breaks, r))                         # every break is a tile start
+            for w in range(len(breaks) - 1):
+                assert r[tp[w]] == breaks[w] or breaks[w] == breaks[w + 1]
+                covered = r[tp[w + 1]] - r[tp[w]]
+                assert covered == breaks[w + 1] - breaks[w]
+        rpp = 32 // G
+        inner = (rows > rpp) & (ents + lens[np.minimum(r[1:], n - 1)] <= T) & (rows < RMAX)
+        if not use_breaks:
+            assert np.all(rows[inner][:-1] % rpp == 0)
