@@ -62,10 +62,14 @@ def build_host_library(force=False, verbose=False):
         if os.path.exists(HOST_LIB):
             return HOST_LIB
         raise RuntimeError("g++ not found and libpyamg_b200_host.so is not built")
-    cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-shared", "-o", HOST_LIB] + HOST_SOURCES
+    cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-o", HOST_LIB] + HOST_SOURCES
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd)
+    try:
+        subprocess.check_call(cmd)
+    except subprocess.CalledProcessError:          # toolchain without OpenMP: the pragmas are ignored
+        cmd.remove("-fopenmp")
+        subprocess.check_call(cmd)
     _write_stamp(HOST_LIB, HOST_SOURCES)
     return HOST_LIB
 

@@ -41,9 +41,9 @@ def classical_strength_of_connection(A, theta=0.25, return_index=False):
     Sidx = np.empty(A.nnz, dtype=np.int32)
     nnz = H.lib().amgb_setup_classical_strength(n, H.ip(A.indptr), H.ip(A.indices), H.dp(A.data),
                                                 float(theta), H.ip(Sp), H.ip(Sj), H.dp(Sx), H.ip(Sidx))
-    S = sparse.csr_array((Sx[:nnz].copy(), Sj[:nnz].copy(), Sp), shape=(n, n))
+    S = sparse.csr_array((Sx[:nnz], Sj[:nnz], Sp), shape=(n, n))
     if return_index:
-        return S, Sidx[:nnz].copy()
+        return S, Sidx[:nnz]
     return S
 
 

@@ -173,6 +173,8 @@ void amgb_setup_classical_interp_count(int32_t n, const int32_t *Sp, const int32
 {
     const int64_t nnzS = Sp[n];
     for (int64_t k = 0; k < nnzS; k++) keep[k] = 1;
+    // rows are independent here (each writes only its own keep[] entries): threads when built with OpenMP
+#pragma omp parallel for schedule(dynamic, 4096)
     for (int32_t i = 0; i < n; i++) {
         if (splitting[i] != 0) continue;
         for (int32_t jj = Sp[i]; jj < Sp[i + 1]; jj++) {
@@ -212,6 +214,8 @@ void amgb_setup_classical_interp_fill(int32_t n, const int32_t *Ap, const int32_
 {
     std::vector<int32_t> cmap((size_t)n);
     for (int32_t i = 0, c = 0; i < n; i++) { cmap[i] = c; c += splitting[i]; }
+    // every row fills its own, pre-counted slice of P: independent -> threads when built with OpenMP
+#pragma omp parallel for schedule(dynamic, 4096)
     for (int32_t i = 0; i < n; i++) {
         if (splitting[i] == 1) {
             Pj[Pp[i]] = cmap[i];
