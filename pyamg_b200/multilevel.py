@@ -260,39 +260,20 @@ class MultilevelSolver:
         return output
 
     def cycle_complexity(self, cycle="V"):
-        """Nonzeros touched by one cycle relative to the fine level (multilevel.py:211-283)."""
+        """Nonzeros touched by one cycle relative to the fine level (multilevel.py:211-283): every visit
+        of a non-coarsest level costs 2 nnz (pre + post smoothing), a coarse solve nnz of the coarsest level;
+        V visits each level once, W twice per parent visit, F = one F-visit plus one V-visit of the next level."""
         cycle = str(cycle).upper()
-        nnz = [level.A.nnz for level in self.levels]
-
-        def V(level):
-            if len(self.levels) == 1:
-                return nnz[0]
-            if level == len(self.levels) - 2:
-                return 2 * nnz[level] + nnz[level + 1]
-            return 2 * nnz[level] + V(level + 1)
-
-        def W(level):
-            if len(self.levels) == 1:
-                return nnz[0]
-            if level == len(self.levels) - 2:
-                return 2 * nnz[level] + nnz[level + 1]
-            return 2 * nnz[level] + 2 * W(level + 1)
-
-        def F(level):
-            if len(self.levels) == 1:
-                return nnz[0]
-            if level == len(self.levels) - 2:
-                return 2 * nnz[level] + nnz[level + 1]
-            return 2 * nnz[level] + F(level + 1) + V(level + 1)
-
-        if cycle == "V":
-            flops = V(0)
-        elif cycle in ("W", "AMLI"):
-            flops = W(0)
-        elif cycle == "F":
-            flops = F(0)
-        else:
+        if cycle not in ("V", "W", "F", "AMLI"):
             raise TypeError(f"Unrecognized cycle type ({cycle})")
+        nnz = [level.A.nnz for level in self.levels]
+        if len(nnz) == 1:
+            return 1.0
+        # bottom-up: cost of one visit of level l under each recursion pattern
+        v = w = f = 2 * nnz[-2] + nnz[-1]
+        for l in range(len(nnz) - 3, -1, -1):
+            v, w, f = 2 * nnz[l] + v, 2 * nnz[l] + 2 * w, 2 * nnz[l] + f + v
+        flops = {"V": v, "W": w, "AMLI": w, "F": f}[cycle]
         return float(flops) / float(nnz[0])
 
     def operator_complexity(self):
