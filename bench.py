@@ -214,14 +214,24 @@ def run_distributed(args, grid, ml, local, rank, world, tstream):
     n = ml.levels[0].A.shape[0]
     t0 = time.time()
     be = GpuBackend(device=local, rank=rank, world=world)
-    ds = DistributedSolver(ml, be)
-    log(f"partitioned levels {ds.n_dist} of {len(ml.levels)}; halo entries/rank {[int(L.sp.maxB) for L in ds.lv]}; "
+    halo = os.environ.get("AMGB_DIST_HALO", "allgather")       # 'p2p': neighbour send/recv (experimental on GPU)
+    ds = DistributedSolver(ml, be, halo=halo)
+    log(f"halo exchange: {halo}; partitioned levels {ds.n_dist} of {len(ml.levels)}; halo entries/rank {[int(L.sp.maxB) for L in ds.lv]}; "
         f"plan + upload {time.time() - t0:.1f}s")
     b_host = np.random.default_rng(SEED).random(n)
     ds.load(b_host)
     norms = be.vector(args.steps + args.warmup + 2)
     ds.cycles(args.warmup)
     torch.cuda.synchronize()
+    if os.environ.get("AMGB_DIST_GRAPH") == "1":                # experimental: whole distributed cycle as one graph
+        try:
+            ds.capture_graph()
+            ds.cycles(1)
+            torch.cuda.synchronize()
+            log("distributed cycle captured into a CUDA graph")
+        except Exception as exc:                                # noqa: BLE001 - fall back to host-driven launches
+            ds._graph = None
+            log(f"graph capture unavailable ({type(exc).__name__}: {exc}); running host-driven")
     dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()

@@ -63,7 +63,8 @@ def wave_schedule(A, order=None):
 class _Space:
     """A partitioned vector space (one hierarchy level): ownership, local order, halo plan."""
 
-    def __init__(self, n, bounds, rank):
+    def __init__(self, n, bounds, rank, mode="allgather"):
+        self.mode = mode
         self.n, self.bounds, self.rank = n, np.asarray(bounds, dtype=np.int64), rank
         self.world = len(bounds) - 1
         self.lo, self.hi = int(bounds[rank]), int(bounds[rank + 1])
@@ -91,7 +92,18 @@ class _Space:
         self.B = [allneed[(allneed >= self.bounds[p]) & (allneed < self.bounds[p + 1])].astype(np.int64)
                   for p in range(self.world)]
         self.maxB = max(1, max(len(b) for b in self.B))
-        self.n_ext = self.n_own + self.world * self.maxB
+        # neighbour ("p2p") plan: what THIS rank receives from every owner p, and what it sends to every q
+        r = self.rank
+        self.recv_from = [need[r][(need[r] >= self.bounds[p]) & (need[r] < self.bounds[p + 1])].astype(np.int64)
+                          if p != r else np.empty(0, dtype=np.int64) for p in range(self.world)]
+        self.send_to = [need[q][(need[q] >= self.lo) & (need[q] < self.hi)].astype(np.int64)
+                        if q != r else np.empty(0, dtype=np.int64) for q in range(self.world)]
+        self.recv_off = np.concatenate([[0], np.cumsum([len(a) for a in self.recv_from])]).astype(np.int64)
+        self.send_off = np.concatenate([[0], np.cumsum([len(a) for a in self.send_to])]).astype(np.int64)
+        if self.mode == "p2p":
+            self.n_ext = self.n_own + max(1, int(self.recv_off[-1]))
+        else:
+            self.n_ext = self.n_own + self.world * self.maxB
         del self._remote
 
     def set_local_order(self, perm_global_rows):
@@ -102,6 +114,9 @@ class _Space:
         self.order = np.asarray(perm_global_rows, dtype=np.int64)
 
     def send_idx(self):
+        if self.mode == "p2p":      # packed per destination rank, ascending
+            ids = np.concatenate(self.send_to) if self.send_off[-1] else np.empty(0, dtype=np.int64)
+            return self.local_of_owned[ids - self.lo].astype(np.int32)
         return self.local_of_owned[self.B[self.rank] - self.lo].astype(np.int32)
 
     def map_cols(self, cols):
@@ -117,10 +132,12 @@ class _Space:
             off = np.empty(rc.shape, dtype=np.int64)
             for p in np.unique(q):
                 m = q == p
-                k = np.searchsorted(self.B[p], rc[m])
-                if np.any(k >= len(self.B[p])) or np.any(self.B[p][np.minimum(k, len(self.B[p]) - 1)] != rc[m]):
+                table = self.recv_from[p] if self.mode == "p2p" else self.B[p]
+                k = np.searchsorted(table, rc[m])
+                if np.any(k >= len(table)) or np.any(table[np.minimum(k, len(table) - 1)] != rc[m]):
                     raise RuntimeError("halo plan is missing a referenced column")
-                off[m] = self.n_own + p * self.maxB + k
+                base = self.recv_off[p] if self.mode == "p2p" else p * self.maxB
+                off[m] = self.n_own + base + k
             out[rem] = off
         return out
 
@@ -154,7 +171,7 @@ class DistLevel:
     pass
 
 
-def build_plan(ml, world, rank, n_dist=None, dist_nnz=20_000_000):
+def build_plan(ml, world, rank, n_dist=None, dist_nnz=20_000_000, halo="allgather"):
     """Partition the leading levels of hierarchy `ml` for (world, rank). Returns (levels, n_dist).
 
     Pure host code; every rank runs it on the same (replicated) host hierarchy and keeps its part."""
@@ -174,7 +191,9 @@ def build_plan(ml, world, rank, n_dist=None, dist_nnz=20_000_000):
             bounds.append(coarse_bounds_from_splitting(sp, bounds[l - 1]))
         else:
             bounds.append(block_bounds(ml.levels[l].A.shape[0], world))
-    spaces = [_Space(ml.levels[l].A.shape[0], bounds[l], rank) for l in range(n_dist)]
+    if halo not in ("allgather", "p2p"):
+        raise ValueError("halo must be 'allgather' or 'p2p'")
+    spaces = [_Space(ml.levels[l].A.shape[0], bounds[l], rank, mode=halo) for l in range(n_dist)]
     for l in range(n_dist):
         lvl = ml.levels[l]
         spaces[l].add_reader(lvl.A, bounds[l])                         # smoother / residual gather x_l
@@ -252,10 +271,15 @@ class DistributedSolver:
     ``solve_device``-style use: ``load(b_global)``, ``cycles(k)``, ``gather_x()``; residual norms are
     all-reduced.  Only V-cycles (the partitioned recursion has one coarse visit per level)."""
 
-    def __init__(self, ml, backend, n_dist=None, dist_nnz=20_000_000):
+    def __init__(self, ml, backend, n_dist=None, dist_nnz=20_000_000, halo="allgather"):
+        """halo='allgather' (default; one ncclAllGather of the padded boundary blocks per exchange) or 'p2p'
+        (grouped send/recv with exactly the ranks that reference each other's entries: moves
+        world/#neighbours times fewer bytes; host logic covered by the gloo tests)."""
         from .multilevel import MultilevelSolver
-        self.ml, self.be = ml, backend
-        self.plan, self.n_dist = build_plan(ml, backend.world, backend.rank, n_dist=n_dist, dist_nnz=dist_nnz)
+        self.ml, self.be, self.halo_mode = ml, backend, halo
+        self._graph = None
+        self.plan, self.n_dist = build_plan(ml, backend.world, backend.rank, n_dist=n_dist, dist_nnz=dist_nnz,
+                                            halo=halo)
         be = backend
         self.lv = []
         for D in self.plan:
@@ -266,7 +290,7 @@ class DistributedSolver:
             L.P = be.operator(D.P, None)
             L.R = be.operator(D.R, None)
             L.send_idx = be.index(D.send_idx)
-            L.send = be.vector(sp.maxB)
+            L.send = be.vector(max(sp.maxB, int(sp.send_off[-1])))
             L.x, L.xalt, L.b, L.r = (be.vector(sp.n_ext) for _ in range(4))
             self.lv.append(L)
         # replicated remainder: an ordinary engine hierarchy on every rank
@@ -282,7 +306,10 @@ class DistributedSolver:
         if self.be.world == 1:
             return
         self.be.gather(v, L.send_idx, L.send, len(L.D.send_idx))
-        self.be.allgather(L.send, v, L.sp.n_own, L.sp.maxB)
+        if self.halo_mode == "p2p":
+            self.be.exchange(L.send, L.sp.send_off, v, L.sp.n_own, L.sp.recv_off)
+        else:
+            self.be.allgather(L.send, v, L.sp.n_own, L.sp.maxB)
 
     # -- smoothers --------------------------------------------------------------------------------
     def smooth(self, L, S):
@@ -356,9 +383,32 @@ class DistributedSolver:
         for it in range(1, k + 1):
             if self.n_dist == 0:
                 raise RuntimeError("nothing is partitioned")
-            self.cycle(0)
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self.cycle(0)
             if norms is not None:
                 self.be.copy_scalar(self.residual_norm(), norms, it)
+
+    def capture_graph(self):
+        """EXPERIMENTAL (off by default; not yet validated on hardware): capture one distributed V-cycle --
+        engine kernels, NCCL collectives and the replicated sub-hierarchy's own graph -- into a CUDA graph on
+        the backend's stream, so the ~500 host-issued launches per cycle become one replay.  Requires warmed-up
+        cycles (all engine graphs instantiated) and an even number of Jacobi ping-pongs per level."""
+        torch = getattr(self.be, "torch", None)
+        if torch is None:
+            raise NotImplementedError("graph capture needs the GPU backend")
+        for L in self.lv:
+            swaps = sum(S.iterations for S in (L.D.pre, L.D.post) if S.kind == E.SM_JACOBI)
+            if swaps % 2:
+                raise NotImplementedError("odd number of Jacobi sweeps per cycle: buffers would alternate")
+        self.cycle(0)                                  # make sure every lazily built piece exists
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.be.stream):
+            self.cycle(0)
+        self._graph = g
+        return g
 
     def gather_x(self):
         """The full iterate on every rank (host array, original numbering)."""
@@ -445,6 +495,24 @@ class GpuBackend:
     def allgather(self, send, v, n_own, maxB):
         import torch.distributed as dist
         dist.all_gather_into_tensor(v[n_own:n_own + self.world * maxB], send[:maxB], group=self.group)
+
+    def exchange(self, send, send_off, v, n_own, recv_off):
+        """Grouped NCCL send/recv with the ranks that share boundary entries (halo='p2p')."""
+        import torch.distributed as dist
+        ops = []
+        for q in range(self.world):
+            ns = int(send_off[q + 1] - send_off[q])
+            nr = int(recv_off[q + 1] - recv_off[q])
+            if q == self.rank:
+                continue
+            if ns:
+                ops.append(dist.P2POp(dist.isend, send[int(send_off[q]):int(send_off[q + 1])], q, group=self.group))
+            if nr:
+                ops.append(dist.P2POp(dist.irecv, v[n_own + int(recv_off[q]):n_own + int(recv_off[q + 1])], q,
+                                      group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
 
     def allreduce(self, v):
         if self.world > 1:

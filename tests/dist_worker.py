@@ -80,6 +80,23 @@ class NumpyBackend:
         dist.all_gather(parts, torch.from_numpy(send[:maxB].copy()))
         v[n_own:n_own + self.world * maxB] = torch.cat(parts).numpy()
 
+    def exchange(self, send, send_off, v, n_own, recv_off):
+        reqs, bufs = [], []
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            ns, nr = int(send_off[q + 1] - send_off[q]), int(recv_off[q + 1] - recv_off[q])
+            if ns:
+                reqs.append(dist.isend(torch.from_numpy(send[int(send_off[q]):int(send_off[q + 1])].copy()), q))
+            if nr:
+                t = torch.zeros(nr, dtype=torch.float64)
+                bufs.append((t, n_own + int(recv_off[q])))
+                reqs.append(dist.irecv(t, q))
+        for r in reqs:
+            r.wait()
+        for t, off in bufs:
+            v[off:off + len(t)] = t.numpy()
+
     def allreduce(self, v):
         if self.world > 1:
             t = torch.from_numpy(v[:len(v) - 2].copy())
@@ -104,11 +121,12 @@ class NumpyBackend:
 
 def main():
     name, n_dist, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+    halo = sys.argv[4] if len(sys.argv) > 4 else "allgather"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     ml, ex = load_hierarchy(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     be = NumpyBackend(rank, world)
-    ds = D.DistributedSolver(ml, be, n_dist=n_dist)
+    ds = D.DistributedSolver(ml, be, n_dist=n_dist, halo=halo)
     ds.load(ex["b"])
     ncyc = 4
     norms = np.zeros(ncyc + 1)

@@ -21,27 +21,29 @@ def _free_port():
     return p
 
 
-def _run(name, world, n_dist, tmp_path):
-    out = str(tmp_path / f"{name}_{world}_{n_dist}.npz")
+def _run(name, world, n_dist, tmp_path, halo="allgather"):
+    out = str(tmp_path / f"{name}_{world}_{n_dist}_{halo}.npz")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "dist_worker.py"), name, str(n_dist), out]
+           os.path.join(ROOT, "tests", "dist_worker.py"), name, str(n_dist), out, halo]
     env = dict(os.environ, OMP_NUM_THREADS="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
     return np.load(out)
 
 
-@pytest.mark.parametrize("name,world,n_dist", [
-    ("cfg3_rs_mcgs_poisson3d", 2, 2),      # multi-colour GS, two partitioned levels, one replicated tail
-    ("cfg3_rs_mcgs_poisson3d", 3, 1),      # odd world size, only level 0 partitioned
-    ("cfg2_sa_jacobi_poisson2d", 2, 2),    # Jacobi, BSR(1,1) operators, balanced coarse blocks
-    ("cfg1_rs_gs_poisson2d", 2, 1),        # lexicographic GS executed as global dependency waves
-    ("cfg4_sa_jacobi_aniso2d", 2, 3),      # 2 Jacobi sweeps pre (ping-pong), three partitioned levels
+@pytest.mark.parametrize("name,world,n_dist,halo", [
+    ("cfg3_rs_mcgs_poisson3d", 2, 2, "allgather"),   # multi-colour GS, two partitioned levels, replicated tail
+    ("cfg3_rs_mcgs_poisson3d", 3, 1, "allgather"),   # odd world size, only level 0 partitioned
+    ("cfg2_sa_jacobi_poisson2d", 2, 2, "allgather"), # Jacobi, BSR(1,1) operators, balanced coarse blocks
+    ("cfg1_rs_gs_poisson2d", 2, 1, "allgather"),     # lexicographic GS executed as global dependency waves
+    ("cfg4_sa_jacobi_aniso2d", 2, 3, "allgather"),   # 2 Jacobi sweeps pre (ping-pong), three partitioned levels
+    ("cfg3_rs_mcgs_poisson3d", 4, 2, "p2p"),         # neighbour send/recv halo plan, 4 ranks
+    ("cfg4_sa_jacobi_aniso2d", 3, 3, "p2p"),
 ])
-def test_distributed_vcycle_matches_sequential_oracle(name, world, n_dist, tmp_path, load_golden):
+def test_distributed_vcycle_matches_sequential_oracle(name, world, n_dist, halo, tmp_path, load_golden):
     ml, ex = load_golden(name)
-    got = _run(name, world, n_dist, tmp_path)
+    got = _run(name, world, n_dist, tmp_path, halo)
     cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.P)
     res = []
     x = cyc.solve(ex["b"], tol=0, maxiter=4, residuals=res)
