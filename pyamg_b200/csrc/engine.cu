@@ -16,6 +16,7 @@
 #include "csr_kernels.cuh"
 #include "tile_kernels.cuh"
 #include "tail_kernel.cuh"
+#include "resident_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -308,6 +309,11 @@ struct Smoother {
     double omega = 1.0;
     WaveSchedule ws;
     double *Dinv = nullptr;
+    // EXPERIMENTAL resident-vector cluster sweep (AMGB_RESIDENT=1): device copies of the schedule
+    long long *res_wave_ptr = nullptr;
+    int *res_seq = nullptr;
+    int res_seq_len = 0, res_log2m = 0, res_csize = 0;
+    double res_bytes = 0.0;
 };
 
 struct ProfRec {               // one launch of a profiled cycle (amgb_profile_cycle)
@@ -554,6 +560,7 @@ struct amgb_hierarchy {
     bool use_graph = true;
     bool use_tiles = true;
     bool use_permute = true;
+    bool use_resident = false;     // AMGB_RESIDENT=1: experimental DSMEM-resident Gauss-Seidel applications
 
     // coarse tail: levels >= tail_level run inside one cluster kernel (tail_kernel.cuh)
     int tail_level = 1 << 30;
@@ -739,6 +746,7 @@ struct amgb_hierarchy {
             }
             return AMGB_OK;
         case AMGB_SM_GAUSS_SEIDEL: {
+            if (s.res_seq != nullptr && !recording) return resident_apply(L, s);
             const long long nw = (long long)s.ws.ptr.size() - 1;
             // relaxation.py:326-330: the symmetric sweep recurses WITHOUT omega (plain GS)
             const double om = (s.sweep == AMGB_SWEEP_SYMMETRIC) ? 1.0 : s.omega;
@@ -758,6 +766,76 @@ struct amgb_hierarchy {
         case AMGB_SM_BLOCK_JACOBI: return block_jacobi(L, s);
         }
         return fail(AMGB_ENOTIMPL, "smoother kind");
+    }
+
+    // one launch = the whole smoother application (resident_kernel.cuh)
+    int resident_apply(Level &L, const Smoother &s)
+    {
+        ResidentArgs a;
+        a.n = L.A.n_rows; a.log2m = s.res_log2m; a.Ap = L.A.Ap; a.Aj = L.A.Aj; a.Ax = L.A.Ax;
+        a.x = L.x; a.b = L.b; a.omega = (s.sweep == AMGB_SWEEP_SYMMETRIC) ? 1.0 : s.omega;
+        a.wave_ptr = s.res_wave_ptr; a.seq = s.res_seq; a.seq_len = s.res_seq_len; a.G = L.A.lanes;
+        launches++;
+        RET(prof_begin(7, s.res_csize, L.A.n_rows, L.A.nnz, s.res_bytes));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)s.res_csize);
+        cfg.blockDim = dim3(kResidentThreads);
+        cfg.dynamicSmemBytes = sizeof(double) << s.res_log2m;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)s.res_csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, resident_gs_kernel, a));
+        return prof_end();
+    }
+
+    // decide whether a Gauss-Seidel smoother of this level can run resident, and upload its schedule
+    int resident_prepare(Level &L, Smoother &s)
+    {
+        if (!use_resident || s.kind != AMGB_SM_GAUSS_SEIDEL || !s.ws.contiguous) return AMGB_OK;
+        const long long nw = (long long)s.ws.ptr.size() - 1;
+        if (nw < 1 || L.A.n_rows < 1) return AMGB_OK;
+        // largest cluster the device co-schedules with the slice it then needs in shared memory
+        for (int c = 16; c >= 2; c >>= 1) {
+            int log2m = 5;
+            while ((1LL << log2m) * c < L.A.n_rows) log2m++;
+            if (log2m > kResidentMaxLog2m) break;          // even 16 CTAs x 128 KB cannot hold x
+            const size_t smem = sizeof(double) << log2m;
+            CK(cudaFuncSetAttribute(resident_gs_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            CK(cudaFuncSetAttribute(resident_gs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * 1024)));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)c); cfg.blockDim = dim3(kResidentThreads); cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, resident_gs_kernel, &cfg) != cudaSuccess || ncl < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            std::vector<int> seq;
+            double bytes = 0.0;
+            for (int it = 0; it < s.iterations; it++) {
+                if (s.sweep == AMGB_SWEEP_FORWARD || s.sweep == AMGB_SWEEP_SYMMETRIC)
+                    for (long long w = 0; w < nw; w++) seq.push_back((int)w);
+                if (s.sweep == AMGB_SWEEP_BACKWARD)
+                    for (long long w = nw - 1; w >= 0; w--) seq.push_back((int)w);
+                if (s.sweep == AMGB_SWEEP_SYMMETRIC)
+                    for (long long w = nw - 2; w >= 0; w--) seq.push_back((int)w);     // idempotent middle wave skipped
+            }
+            for (int w : seq)
+                bytes += 12.0 * s.ws.nnz[(size_t)w] + 36.0 * (double)(s.ws.ptr[(size_t)w + 1] - s.ws.ptr[(size_t)w]);
+            RET(upload(&s.res_wave_ptr, s.ws.ptr.data(), (long long)s.ws.ptr.size()));
+            RET(upload(&s.res_seq, seq.data(), (long long)seq.size()));
+            s.res_seq_len = (int)seq.size();
+            s.res_log2m = log2m;
+            s.res_csize = c;
+            s.res_bytes = bytes;
+            return AMGB_OK;
+        }
+        return AMGB_OK;
     }
 
     int coarse_solve(Level &Lc)
@@ -1202,6 +1280,7 @@ extern "C" int amgb_hierarchy_create(int device, amgb_hierarchy **out)
     h->use_graph = !flag("AMGB_NO_GRAPH");
     h->use_tiles = !flag("AMGB_NO_TILES");
     h->use_permute = !flag("AMGB_NO_PERMUTE");
+    h->use_resident = flag("AMGB_RESIDENT");
     *out = h;
     return AMGB_OK;
 }
@@ -1311,6 +1390,11 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
         h->own_stream = true;
     }
     RET(h->finalize_levels());
+    for (Level &L : h->levels) {
+        if (!L.has_pr) continue;
+        RET(h->resident_prepare(L, L.pre));
+        RET(h->resident_prepare(L, L.post));
+    }
     {   // coarse tail: the deepest run of levels whose operators are all small and block-smoother free
         const char *nt = getenv("AMGB_NO_TAIL");
         const char *tn = getenv("AMGB_TAIL_NNZ");

@@ -19,6 +19,8 @@ GOLDEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "gpu_experimental: opt-in code paths not yet validated on hardware "
+                                       "(run explicitly with -m gpu_experimental; never part of -m gpu)")
 
 
 def golden_path(name):
