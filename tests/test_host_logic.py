@@ -239,3 +239,40 @@ def test_tile_builder_invariants(G, T, RMAX):
         inner = (rows > rpp) & (ents + lens[np.minimum(r[1:], n - 1)] <= T) & (rows < RMAX)
         if not use_breaks:
             assert np.all(rows[inner][:-1] % rpp == 0)
+
+
+def test_from_pyamg_adopts_a_reference_style_solver_object(load_golden):
+    """Drop-in boundary: `from_pyamg` takes any object with pyamg.MultilevelSolver's attributes -- here a
+    stand-in whose levels/closures/coarse solver were produced by the real reference (golden) -- shares the
+    Level objects, keeps symmetric_smoothing, parses the coarse-solver name and re-uses the cached pinv."""
+    src, _ = load_golden("cfg5_sa_bjacobi_elasticity")
+
+    class RefCoarse:                       # pyamg's GenericSolver: name() -> repr(solver), cached .P after first use
+        P = src.coarse_solver.P
+
+        @classmethod
+        def name(cls):
+            return "'pinv'"
+
+    class RefSolver:
+        levels = src.levels
+        coarse_solver = RefCoarse()
+        symmetric_smoothing = True
+
+    ml = pyamg_b200.MultilevelSolver.from_pyamg(RefSolver())
+    assert ml.levels[0] is src.levels[0] and len(ml.levels) == len(src.levels)
+    assert ml.symmetric_smoothing is True
+    assert ml.coarse_solver.name() == "'pinv'" and ml.coarse_solver.P is not None
+    assert np.array_equal(ml.coarse_solver.dense_operator(ml.levels[-1].A), src.coarse_solver.P)
+    assert "Number of Levels:     3" in repr(ml)
+
+    class Unsupported(RefSolver):
+        class coarse_solver:               # noqa: N801 - mimics an instance with a name() method
+            @staticmethod
+            def name():
+                return "'cg'"
+    with pytest.raises(NotImplementedError):
+        pyamg_b200.MultilevelSolver.from_pyamg(Unsupported())
+    # tuple form ('pinv', {...}) as the reference's coarse_grid_solver accepts it (multilevel.py:710-715)
+    cs = pyamg_b200.coarse_grid_solver(("pinv", {"atol": 1e-12}))
+    assert cs.name() == "('pinv', {'atol': 1e-12})"
