@@ -202,6 +202,25 @@ static void tile_configure(size_t smem_per_sm)
     g_use_pdl = !(np && np[0] == '1');
 }
 
+// The launch helpers read the settings above; every hierarchy keeps the snapshot it was created (and its
+// tiles were built) under and re-activates it at each API entry, so hierarchies created under different
+// AMGB_* settings can coexist in one (single-threaded) process.
+struct TileRuntime {
+    int cfg, ctas[5], ctas_cap, T, rmax, warps, hints, pdl;
+    void capture()
+    {
+        cfg = g_tile_cfg; ctas_cap = g_tile_ctas_cap; T = g_tile_T; rmax = g_tile_rmax; warps = g_tile_warps;
+        hints = g_tile_hints; pdl = g_use_pdl;
+        for (int k = 0; k < 5; k++) ctas[k] = g_tile_ctas[k];
+    }
+    void activate() const
+    {
+        g_tile_cfg = cfg; g_tile_ctas_cap = ctas_cap; g_tile_T = T; g_tile_rmax = rmax; g_tile_warps = warps;
+        g_tile_hints = hints; g_use_pdl = pdl;
+        for (int k = 0; k < 5; k++) g_tile_ctas[k] = ctas[k];
+    }
+};
+
 template <int OP, class C>
 static int launch_tile_cfg(int G, const TileArgs &a, int grid, cudaStream_t s)
 {
@@ -523,6 +542,7 @@ static void build_tiles(const HostCsr &A, int G, const std::vector<long long> *b
 // ------------------------------------------------------------------------------------------
 struct amgb_hierarchy {
     int device = 0;
+    TileRuntime rt;                   // kernel settings this hierarchy was built under
     std::vector<HostLevel> host;      // until finalize
     std::vector<Level> levels;
     std::vector<void *> allocs;
@@ -1275,6 +1295,7 @@ extern "C" int amgb_hierarchy_create(int device, amgb_hierarchy **out)
     g_num_sms = prop.multiProcessorCount;
     tile_configure(prop.sharedMemPerMultiprocessor);
     amgb_hierarchy *h = new amgb_hierarchy();
+    h->rt.capture();
     h->device = device;
     auto flag = [](const char *name) { const char *v = getenv(name); return v && v[0] == '1'; };
     h->use_graph = !flag("AMGB_NO_GRAPH");
@@ -1383,6 +1404,7 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
     if (h->host.back().has_pr) return fail(AMGB_ESTATE, "last level must be added without P/R");
     if (!h->have_coarse) return fail(AMGB_ESTATE, "coarse solver not set");
     CK(cudaSetDevice(h->device));
+    h->rt.activate();
     if (stream != nullptr) {
         h->stream = (cudaStream_t)stream;
     } else {
@@ -1480,6 +1502,7 @@ static int check_cycle_args(amgb_hierarchy *h, int32_t cycle, int32_t cpl)
 {
     if (h == nullptr) return fail(AMGB_EINVAL, "null hierarchy");
     if (!h->finalized) return fail(AMGB_ESTATE, "hierarchy not finalized");
+    h->rt.activate();             // every solve / profile entry point passes through here
     if (cycle < 0 || cycle > 2) return fail(AMGB_EINVAL, "Unrecognized cycle type");
     if (cpl < 0) return fail(AMGB_EINVAL, "cycles_per_level < 0");
     return AMGB_OK;
@@ -1818,6 +1841,7 @@ extern "C" int amgb_operator_apply(amgb_operator *op, int32_t kind, const double
     if (op == nullptr) return fail(AMGB_EINVAL, "null operator");
     amgb_hierarchy *h = op->pool;
     CK(cudaSetDevice(h->device));
+    h->rt.activate();
     if (kind < 0 || kind > 4) return fail(AMGB_EINVAL, "unknown operator kind");
     if (kind == OP_GS) {
         if (wave < 0 || (size_t)wave + 1 >= op->waves.ptr.size()) return fail(AMGB_EINVAL, "wave index out of range");
