@@ -328,13 +328,28 @@ class MultilevelSolver:
         return LinearOperator(shape, matvec, dtype=dtype)
 
     def solve(self, b, x0=None, tol=1e-5, maxiter=100, cycle="V", accel=None, callback=None,
-              residuals=None, cycles_per_level=1, return_info=False):
-        """Execute multigrid cycling on the GPU (pyamg/multilevel.py:398-582; same arguments)."""
+              residuals=None, cycles_per_level=1, return_info=False, out=None):
+        """Execute multigrid cycling on the GPU (pyamg/multilevel.py:398-582; same arguments).
+
+        ``out`` (extension, optional): a C-contiguous float64 array of n entries that receives the solution
+        and is returned (reshaped like b) instead of a freshly allocated array -- with a page-locked buffer
+        (``pyamg_b200.pinned_empty``) this removes the page-fault cost of a new 100+ MB result per call."""
         b = np.asarray(b)
+        if out is not None:
+            if accel is not None or callback is not None:
+                raise ValueError("out= is supported for plain cycling only")
+            if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous
+                    and out.size == b.size):
+                raise ValueError("out must be a C-contiguous float64 array with as many entries as b")
         if x0 is None:
-            x = np.zeros_like(b)
+            # the engine starts from zero on the device (AMGB_FLAG_X0_ZERO): the host buffer is output only
+            x = out if out is not None else (np.empty_like(b, dtype=np.float64) if accel is None and callback is None
+                                             and not np.iscomplexobj(b) else np.zeros_like(b))
         else:
             x = np.array(x0)    # copy (:467)
+            if out is not None:
+                np.copyto(out.reshape(x.shape), x)
+                x = out
 
         A = self.levels[0].A
         cycle = str(cycle).upper()

@@ -323,3 +323,18 @@ def test_gpu_resident_pcg_matches_reference_golden(name, load_golden):
                              return_info=True)
         assert infoc == int(ex["info_cg"][0]) and len(seen) == len(ex["residuals_cg"]) - 1
         assert relerr(xc, ex["x_ref_cg"]) < 1e-11
+
+
+def test_out_buffer_and_pinned_result(load_golden):
+    """solve(out=...) writes into the caller's (page-locked) buffer and returns it; x0 semantics unchanged."""
+    ml, ex = load_golden("cfg3_rs_mcgs_poisson3d")
+    n = len(ex["b"])
+    out = pyamg_b200.pinned_empty(n)
+    out[:] = np.nan
+    x = ml.solve(ex["b"], tol=0, maxiter=len(ex["residuals"]) - 1, out=out)
+    assert np.shares_memory(x, out) and relerr(x, ex["x_ref"]) < TOL
+    x0 = ex["x0"].copy()
+    x = ml.solve(ex["b"], x0=x0, tol=1e-6, maxiter=50, out=out)
+    assert np.array_equal(x0, ex["x0"]) and relerr(x, ex["x_ref_tol"]) < TOL
+    with pytest.raises(ValueError):
+        ml.solve(ex["b"], out=np.zeros(n - 1))
