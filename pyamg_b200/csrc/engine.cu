@@ -25,6 +25,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 using namespace amgb;
@@ -158,6 +159,7 @@ static int g_tile_ctas[5] = {2, 2, 2, 2, 2};   // resident CTAs per SM of csr_ti
 static int g_tile_ctas_cap = 0;                  // AMGB_TILE_CTAS (0 = per-epilogue optimum)
 static int g_tile_T = 256, g_tile_rmax = 64, g_tile_warps = 8;
 static int g_tile_hints = 1;        // AMGB_NO_HINTS=1 disables the L2 eviction hints
+static int g_tile_pdl = 0;          // AMGB_TILE_PDL=1 (experimental): programmatic dependent launch of the tile kernel
 
 template <class C, int OP>
 static void tile_cfg_op(size_t smem_per_sm)
@@ -200,23 +202,25 @@ static void tile_configure(size_t smem_per_sm)
     g_tile_hints = !(nh && nh[0] == '1');
     const char *np = getenv("AMGB_NO_PDL");
     g_use_pdl = !(np && np[0] == '1');
+    const char *tp = getenv("AMGB_TILE_PDL");
+    g_tile_pdl = (tp && tp[0] == '1') ? 1 : 0;
 }
 
 // The launch helpers read the settings above; every hierarchy keeps the snapshot it was created (and its
 // tiles were built) under and re-activates it at each API entry, so hierarchies created under different
 // AMGB_* settings can coexist in one (single-threaded) process.
 struct TileRuntime {
-    int cfg, ctas[5], ctas_cap, T, rmax, warps, hints, pdl;
+    int cfg, ctas[5], ctas_cap, T, rmax, warps, hints, pdl, tile_pdl;
     void capture()
     {
         cfg = g_tile_cfg; ctas_cap = g_tile_ctas_cap; T = g_tile_T; rmax = g_tile_rmax; warps = g_tile_warps;
-        hints = g_tile_hints; pdl = g_use_pdl;
+        hints = g_tile_hints; pdl = g_use_pdl; tile_pdl = g_tile_pdl;
         for (int k = 0; k < 5; k++) ctas[k] = g_tile_ctas[k];
     }
     void activate() const
     {
         g_tile_cfg = cfg; g_tile_ctas_cap = ctas_cap; g_tile_T = T; g_tile_rmax = rmax; g_tile_warps = warps;
-        g_tile_hints = hints; g_use_pdl = pdl;
+        g_tile_hints = hints; g_use_pdl = pdl; g_tile_pdl = tile_pdl;
         for (int k = 0; k < 5; k++) g_tile_ctas[k] = ctas[k];
     }
 };
@@ -228,6 +232,24 @@ static int launch_tile_cfg(int G, const TileArgs &a, int grid, cudaStream_t s)
     constexpr size_t smem = tile_smem_bytes<C, OP>();
 #define AMGB_TILE_CASE(GG)                                                                               \
     case GG: {                                                                                           \
+        if constexpr (std::is_same<C, TileCfg6>::value) {                                                \
+            if (g_tile_pdl) {   /* opt-in: programmatic dependent launch, default geometry only */     \
+                static bool pdl_attr_done = false;                                                       \
+                if (!pdl_attr_done) {                                                                    \
+                    CK(cudaFuncSetAttribute(csr_tile_kernel<GG, OP, C, true>,                            \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+                    pdl_attr_done = true;                                                                \
+                }                                                                                        \
+                cudaLaunchConfig_t cfg = {};                                                             \
+                cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = smem; cfg.stream = s;          \
+                cudaLaunchAttribute at[1];                                                               \
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                           \
+                at[0].val.programmaticStreamSerializationAllowed = 1;                                    \
+                cfg.attrs = at; cfg.numAttrs = 1;                                                        \
+                CK(cudaLaunchKernelEx(&cfg, csr_tile_kernel<GG, OP, C, true>, a));                       \
+                break;                                                                                   \
+            }                                                                                            \
+        }                                                                                                \
         static bool attr_done = false;                                                                   \
         if (!attr_done) {                                                                                \
             CK(cudaFuncSetAttribute(csr_tile_kernel<GG, OP, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -581,6 +603,7 @@ struct amgb_hierarchy {
     bool use_tiles = true;
     bool use_permute = true;
     bool use_resident = false;     // AMGB_RESIDENT=1: experimental DSMEM-resident Gauss-Seidel applications
+    long long resident_max_rows = 65536;   // AMGB_RESIDENT_MAX_ROWS
 
     // coarse tail: levels >= tail_level run inside one cluster kernel (tail_kernel.cuh)
     int tail_level = 1 << 30;
@@ -816,6 +839,9 @@ struct amgb_hierarchy {
         if (!use_resident || s.kind != AMGB_SM_GAUSS_SEIDEL || !s.ws.contiguous) return AMGB_OK;
         const long long nw = (long long)s.ws.ptr.size() - 1;
         if (nw < 1 || L.A.n_rows < 1) return AMGB_OK;
+        // only where the dependent-wave latency, not the operator stream, is the cost: one cluster pulls
+        // the operator through 16 SMs, so bigger levels stay on the full-grid wave launches
+        if (L.A.n_rows > resident_max_rows) return AMGB_OK;
         // largest cluster the device co-schedules with the slice it then needs in shared memory
         for (int c = 16; c >= 2; c >>= 1) {
             int log2m = 5;
@@ -1302,6 +1328,7 @@ extern "C" int amgb_hierarchy_create(int device, amgb_hierarchy **out)
     h->use_tiles = !flag("AMGB_NO_TILES");
     h->use_permute = !flag("AMGB_NO_PERMUTE");
     h->use_resident = flag("AMGB_RESIDENT");
+    if (const char *v = getenv("AMGB_RESIDENT_MAX_ROWS")) h->resident_max_rows = atoll(v);
     *out = h;
     return AMGB_OK;
 }

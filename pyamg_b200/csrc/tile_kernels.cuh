@@ -145,14 +145,17 @@ __device__ __forceinline__ double ld_x_hint(const double *p, unsigned long long 
 
 // One lane: ask the TMA for tile t's segments.  Every source starts on a 16-byte boundary: entry ranges
 // are widened to multiples of 4 entries, vector ranges to multiples of 2 (the arrays are padded at upload).
-template <class C, int OP>
+// PART: bit 0 = arm the barrier for the whole tile and copy the immutable operator segments, bit 1 = copy the
+// vector segments (b / x_old).  The split lets a programmatically-launched kernel (PDL) fetch its first
+// operator tile while the previous launch is still writing the vectors.
+template <class C, int OP, int PART = 3>
 __device__ __forceinline__ void tile_issue(const TileArgs &a, int t, TileStageT<C, OP> &st, unsigned long long *bar,
                                            unsigned long long pol)
 {
     const TileDesc d0 = a.tiles[t], d1 = a.tiles[t + 1];
     const int len = d1.nz0 - d0.nz0;
     if (len > C::T) {              // long row: streamed from global memory, nothing to stage
-        mbar_expect_tx(bar, 0);
+        if (PART & 1) mbar_expect_tx(bar, 0);
         return;
     }
     constexpr bool kB = (OP == OP_RESID || OP == OP_JACOBI || OP == OP_GS);
@@ -163,26 +166,34 @@ __device__ __forceinline__ void tile_issue(const TileArgs &a, int t, TileStageT<
     const int rcnt = ((d1.row0 + 1 + 3) & ~3) - r4;
     const int v2 = d0.row0 & ~1;
     const int vcnt = ((d1.row0 + 1) & ~1) - v2;
-    mbar_expect_tx(bar, (unsigned)(cnt * 12 + rcnt * 4 + ((kB ? 1 : 0) + (kX ? 1 : 0)) * vcnt * 8));
-    if (cnt > 0) {
-        if (a.hints) {
-            bulk_g2s_hint(st.val, a.Ax + s4, (unsigned)cnt * 8u, bar, pol);
-            bulk_g2s_hint(st.col, a.Aj + s4, (unsigned)cnt * 4u, bar, pol);
-        } else {
-            bulk_g2s(st.val, a.Ax + s4, (unsigned)cnt * 8u, bar);
-            bulk_g2s(st.col, a.Aj + s4, (unsigned)cnt * 4u, bar);
+    if (PART & 1) {
+        mbar_expect_tx(bar, (unsigned)(cnt * 12 + rcnt * 4 + ((kB ? 1 : 0) + (kX ? 1 : 0)) * vcnt * 8));
+        if (cnt > 0) {
+            if (a.hints) {
+                bulk_g2s_hint(st.val, a.Ax + s4, (unsigned)cnt * 8u, bar, pol);
+                bulk_g2s_hint(st.col, a.Aj + s4, (unsigned)cnt * 4u, bar, pol);
+            } else {
+                bulk_g2s(st.val, a.Ax + s4, (unsigned)cnt * 8u, bar);
+                bulk_g2s(st.col, a.Aj + s4, (unsigned)cnt * 4u, bar);
+            }
         }
+        bulk_g2s(st.ptr, a.Ap + r4, (unsigned)rcnt * 4u, bar);
     }
-    bulk_g2s(st.ptr, a.Ap + r4, (unsigned)rcnt * 4u, bar);
-    if (kB && vcnt > 0) bulk_g2s(st.bseg, a.b + v2, (unsigned)vcnt * 8u, bar);
-    if (kX && vcnt > 0) bulk_g2s(st.xseg, a.x + v2, (unsigned)vcnt * 8u, bar);
+    if (PART & 2) {
+        if (kB && vcnt > 0) bulk_g2s(st.bseg, a.b + v2, (unsigned)vcnt * 8u, bar);
+        if (kX && vcnt > 0) bulk_g2s(st.xseg, a.x + v2, (unsigned)vcnt * 8u, bar);
+    }
 }
 
 // G lanes per row inside a tile (G = 1: thread per row -- 5/7-point stencils; larger G for the
 // denser coarse operators).  32/G rows are reduced per pass.
-template <int G, int OP, class C>
+// PDL = true (opt-in AMGB_TILE_PDL=1, launched with the programmatic-stream-serialization attribute): the
+// kernel may start while its predecessor still runs; it arms its barriers and fetches the operator segments
+// of its first tile(s), then waits for the predecessor before any vector (x, b, y, r) is touched.
+template <int G, int OP, class C, bool PDL = false>
 __global__ void __launch_bounds__(C::WARPS * 32) csr_tile_kernel(const TileArgs a)
 {
+    if (PDL) pdl_launch_dependents();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool kNeedDiag = (OP == OP_JACOBI || OP == OP_GS);
     constexpr int RPP = 32 / G;                       // rows per pass
@@ -206,17 +217,35 @@ __global__ void __launch_bounds__(C::WARPS * 32) csr_tile_kernel(const TileArgs 
     unsigned phase = 0;       // bit s = parity to wait for on stage s
     double r2 = 0.0;
 
-    if (lane == 0) {
+    // tiles whose operator segments are requested before the wait: the ring's prologue, or (single stage) tile t
+    constexpr int kPre = (STAGES > 1) ? STAGES - 1 : 1;
+    if (PDL) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < kPre; s++)
+                if (t + s * nwarps < a.tile_end)
+                    tile_issue<C, OP, 1>(a, t + s * nwarps, ws.st[s], &ws.bar[s], pol_first);
+        }
+        pdl_wait();               // every thread: the predecessor's vectors are complete and visible from here on
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < kPre; s++)
+                if (t + s * nwarps < a.tile_end)
+                    tile_issue<C, OP, 2>(a, t + s * nwarps, ws.st[s], &ws.bar[s], pol_first);
+        }
+    } else if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES - 1; s++)
             if (t + s * nwarps < a.tile_end) tile_issue<C, OP>(a, t + s * nwarps, ws.st[s], &ws.bar[s], pol_first);
     }
     int stage = 0;
+    bool requested = PDL && STAGES == 1;      // single stage + PDL: the first tile was requested above
     for (; t < a.tile_end; t += nwarps) {
         // keep the ring full: the stage consumed in the previous iteration is free again
         const int tn = t + (STAGES - 1) * nwarps;
         const int sn = (stage + STAGES - 1) % STAGES;
-        if (lane == 0 && tn < a.tile_end) tile_issue<C, OP>(a, tn, ws.st[sn], &ws.bar[sn], pol_first);
+        if (lane == 0 && tn < a.tile_end && !requested) tile_issue<C, OP>(a, tn, ws.st[sn], &ws.bar[sn], pol_first);
+        requested = false;
 
         const TileDesc d0 = a.tiles[t], d1 = a.tiles[t + 1];
         const int row0 = d0.row0, nrows = d1.row0 - d0.row0;

@@ -1,0 +1,26 @@
+#!/bin/bash
+# One gpurun call that validates and A/B-times every opt-in path left unmeasured at the end of round 1.
+#
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/r2_experiments.sh 256 > gpurun_out/r2_exp.log 2>&1'
+#
+# 1. parity of the default suite's newest test and of the experimental paths (fails loudly, keeps going);
+# 2. graphed V-cycle time + per-(level, op) GB/s of the 256^3 hierarchy under each setting -- the hierarchy is
+#    built once (tools/tune_tiles.py re-uploads per setting);
+# 3. a fresh launch list (ncu, bounded) for the default setting.
+G=${1:-256}
+mkdir -p gpurun_out
+echo "=== parity: newest default-suite test"
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "out_buffer" 2>&1 | tail -3
+echo "=== parity: experimental paths"
+AMGB_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_experimental.py -q -m gpu_experimental 2>&1 | tail -15
+echo "=== A/B (graphed cycle ms, small_levels ms, per-level GB/s)"
+S="AMGB_NO_PDL=0"                                              # baseline (default settings)
+S="$S;AMGB_TILE_PDL=1"                                         # tile kernels programmatically launched
+S="$S;AMGB_RESIDENT=1"                                         # levels <= 65536 rows: one cluster launch per smoother
+S="$S;AMGB_RESIDENT=1,AMGB_TILE_PDL=1"
+S="$S;AMGB_RESIDENT=1,AMGB_RESIDENT_MAX_ROWS=200000"           # + the 176 k-row level
+S="$S;AMGB_RESIDENT=1,AMGB_RESIDENT_MAX_ROWS=5000"             # only the smallest levels
+S="$S;AMGB_RESIDENT=1,AMGB_TILE_PDL=1,AMGB_TILE_MIN_NNZ=400000"
+timeout 1500 python tools/tune_tiles.py --grid $G --settings "$S" 2>&1 | grep -E "cycle_ms|Error|error" | cut -c1-600
+echo "=== bench line (default settings)"
+timeout 900 python bench.py --steps 10 --warmup 3 2>/dev/null | tail -1 | tee gpurun_out/r2_bench_default.json | cut -c1-400

@@ -38,6 +38,7 @@ if a.settings:      # "K=V,K=V;K=V" -> one dict of environment overrides per set
     settings = [dict(kv.split("=") for kv in s.split(",") if kv) for s in a.settings.split(";")]
 ALL_KEYS = sorted({k for st in settings for k in st})
 
+x_first = None
 for st in settings:
     for k in ALL_KEYS:
         os.environ.pop(k, None)
@@ -49,6 +50,9 @@ for st in settings:
     x.zero_()
     E.check(L.amgb_solve_device(h, P(b), P(x), 3, 0, 1, None))
     torch.cuda.synchronize()
+    if x_first is None:
+        x_first = x.clone()
+    dx = float((x - x_first).norm() / x_first.norm())     # same 3 cycles from zero under every setting
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     E.check(L.amgb_solve_device(h, P(b), P(x), 5, 0, 1, None))
@@ -64,4 +68,5 @@ for st in settings:
         v[0] += nbytes; v[1] += t
     line = {f"L{k[0]}:{OPS[k[1]].split('(')[0]}": round(v[0] / v[1] / 1e6) for k, v in sorted(g.items()) if k[0] <= 2}
     small = sum(v[1] for k, v in g.items() if k[0] >= 3) / 2
-    print(json.dumps({"setting": st, "cycle_ms": round(cyc_ms, 3), "small_levels_ms": round(small, 3), "GBps": line}), flush=True)
+    print(json.dumps({"setting": st, "cycle_ms": round(cyc_ms, 3), "small_levels_ms": round(small, 3),
+                      "relerr_vs_first_setting": dx, "GBps": line}), flush=True)
