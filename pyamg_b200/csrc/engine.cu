@@ -17,6 +17,7 @@
 #include "tile_kernels.cuh"
 #include "tail_kernel.cuh"
 #include "resident_kernel.cuh"
+#include "tile_flat_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -160,6 +161,7 @@ static int g_tile_ctas_cap = 0;                  // AMGB_TILE_CTAS (0 = per-epil
 static int g_tile_T = 256, g_tile_rmax = 64, g_tile_warps = 8;
 static int g_tile_hints = 1;        // AMGB_NO_HINTS=1 disables the L2 eviction hints
 static int g_tile_pdl = 0;          // AMGB_TILE_PDL=1 (experimental): programmatic dependent launch of the tile kernel
+static int g_tile_flat = 0;         // AMGB_TILE_FLAT=1 (experimental): flat-gather tile kernel (tile_flat_kernel.cuh)
 
 template <class C, int OP>
 static void tile_cfg_op(size_t smem_per_sm)
@@ -204,23 +206,25 @@ static void tile_configure(size_t smem_per_sm)
     g_use_pdl = !(np && np[0] == '1');
     const char *tp = getenv("AMGB_TILE_PDL");
     g_tile_pdl = (tp && tp[0] == '1') ? 1 : 0;
+    const char *tf = getenv("AMGB_TILE_FLAT");
+    g_tile_flat = (tf && tf[0] == '1' && g_tile_cfg == 6) ? 1 : 0;     // default geometry only
 }
 
 // The launch helpers read the settings above; every hierarchy keeps the snapshot it was created (and its
 // tiles were built) under and re-activates it at each API entry, so hierarchies created under different
 // AMGB_* settings can coexist in one (single-threaded) process.
 struct TileRuntime {
-    int cfg, ctas[5], ctas_cap, T, rmax, warps, hints, pdl, tile_pdl;
+    int cfg, ctas[5], ctas_cap, T, rmax, warps, hints, pdl, tile_pdl, tile_flat;
     void capture()
     {
         cfg = g_tile_cfg; ctas_cap = g_tile_ctas_cap; T = g_tile_T; rmax = g_tile_rmax; warps = g_tile_warps;
-        hints = g_tile_hints; pdl = g_use_pdl; tile_pdl = g_tile_pdl;
+        hints = g_tile_hints; pdl = g_use_pdl; tile_pdl = g_tile_pdl; tile_flat = g_tile_flat;
         for (int k = 0; k < 5; k++) ctas[k] = g_tile_ctas[k];
     }
     void activate() const
     {
         g_tile_cfg = cfg; g_tile_ctas_cap = ctas_cap; g_tile_T = T; g_tile_rmax = rmax; g_tile_warps = warps;
-        g_tile_hints = hints; g_use_pdl = pdl; g_tile_pdl = tile_pdl;
+        g_tile_hints = hints; g_use_pdl = pdl; g_tile_pdl = tile_pdl; g_tile_flat = tile_flat;
         for (int k = 0; k < 5; k++) g_tile_ctas[k] = ctas[k];
     }
 };
@@ -284,10 +288,46 @@ static int launch_tile_op(int G, const TileArgs &a, int grid, cudaStream_t s)
     }
 }
 
+// flat-gather variant (G == 0 in DevCsr::tile_G): default geometry, with or without programmatic launch
+template <int OP, bool PDL>
+static int launch_tile_flat_one(const TileArgs &a, int grid, cudaStream_t s)
+{
+    using C = TileCfg6;
+    constexpr size_t smem = tile_flat_smem_bytes<C, OP>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(csr_tile_flat_kernel<OP, C, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(C::WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = PDL ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, csr_tile_flat_kernel<OP, C, PDL>, a));
+    return AMGB_OK;
+}
+template <int OP>
+static int launch_tile_flat(const TileArgs &a, int grid, cudaStream_t s)
+{
+    return g_tile_pdl ? launch_tile_flat_one<OP, true>(a, grid, s) : launch_tile_flat_one<OP, false>(a, grid, s);
+}
+
 static int launch_tile(int op, int G, TileArgs a, int grid, cudaStream_t s)
 {
     if (a.tile_end <= a.tile_begin) return AMGB_OK;
     a.hints = g_tile_hints;
+    if (G == 0) {
+        switch (op) {
+        case OP_SPMV: return launch_tile_flat<OP_SPMV>(a, grid, s);
+        case OP_RESID: return launch_tile_flat<OP_RESID>(a, grid, s);
+        case OP_PADD: return launch_tile_flat<OP_PADD>(a, grid, s);
+        case OP_JACOBI: return launch_tile_flat<OP_JACOBI>(a, grid, s);
+        case OP_GS: return launch_tile_flat<OP_GS>(a, grid, s);
+        }
+        return fail(AMGB_EINVAL, "unknown tile op");
+    }
     switch (op) {
     case OP_SPMV: return launch_tile_op<OP_SPMV>(G, a, grid, s);
     case OP_RESID: return launch_tile_op<OP_RESID>(G, a, grid, s);
@@ -499,6 +539,18 @@ static void permute_csr(const HostCsr &A, const int *order, const int *colpos, H
     B.Ap[(size_t)A.n_rows] = (int)pos;
 }
 
+// the reference's sweeps let the LAST stored diagonal entry of a row win (relaxation.h:60-66); the flat-gather
+// kernel keeps one slot per row and therefore only takes matrices without such duplicates
+static bool has_duplicate_diagonal(const HostCsr &A)
+{
+    for (int i = 0; i < A.n_rows; i++) {
+        int cnt = 0;
+        for (int jj = A.Ap[(size_t)i]; jj < A.Ap[(size_t)i + 1]; jj++) cnt += (A.Aj[(size_t)jj] == i);
+        if (cnt > 1) return true;
+    }
+    return false;
+}
+
 static int pick_tile_G(long long nnz, long long n_rows)
 {
     const char *env = getenv("AMGB_TILE_G");
@@ -677,8 +729,9 @@ struct amgb_hierarchy {
         D.lanes = pick_lanes(D.nnz, D.n_rows);
         if (use_tiles) {
             D.tile_G = pick_tile_G(D.nnz, D.n_rows);
+            if (g_tile_flat && !has_duplicate_diagonal(H)) D.tile_G = 0;      // 0 = flat-gather kernel
             std::vector<TileDesc> tiles;
-            build_tiles(H, D.tile_G, breaks, tiles, tile_ptr);
+            build_tiles(H, D.tile_G ? D.tile_G : 32, breaks, tiles, tile_ptr);   // flat: no row-count rounding
             D.n_tiles = (int)tiles.size() - 1;
             RET(upload(&D.tiles, tiles.data(), (long long)tiles.size()));
         }

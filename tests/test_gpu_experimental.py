@@ -7,6 +7,8 @@ before enabling any of them by default:
 
   AMGB_RESIDENT=1        DSMEM-resident Gauss-Seidel smoother applications (csrc/resident_kernel.cuh);
                          AMGB_RESIDENT_MAX_ROWS (default 65536) bounds the levels it takes
+  AMGB_TILE_FLAT=1       flat-gather tile kernel (csrc/tile_flat_kernel.cuh): one gather round per tile at full
+                         warp width, products reduced per row out of shared memory
   AMGB_TILE_PDL=1        programmatic dependent launch of the TMA tile kernel: the first operator tile is
                          requested before griddepcontrol.wait (csrc/tile_kernels.cuh, PDL = true)
   DistributedSolver.capture_graph / halo='p2p' on NCCL (pyamg_b200/dist.py)
@@ -52,6 +54,11 @@ def test_resident_sweeps_on_a_mid_size_hierarchy(monkeypatch):
                                  {"AMGB_TILE_PDL": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_NO_PDL": "1"},
                                  {"AMGB_TILE_PDL": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_NO_HINTS": "1"},
                                  {"AMGB_TILE_PDL": "1"},
+                                 {"AMGB_TILE_FLAT": "1", "AMGB_TILE_MIN_NNZ": "0"},
+                                 {"AMGB_TILE_FLAT": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_NO_PERMUTE": "1"},
+                                 {"AMGB_TILE_FLAT": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_NO_HINTS": "1", "AMGB_NO_GRAPH": "1"},
+                                 {"AMGB_TILE_FLAT": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_PDL": "1"},
+                                 {"AMGB_TILE_FLAT": "1"},
                                  {"AMGB_RESIDENT": "1", "AMGB_RESIDENT_MAX_ROWS": "1000000", "AMGB_TILE_PDL": "1"}])
 @pytest.mark.parametrize("name", GOLDEN)
 def test_tile_kernel_programmatic_launch_matches_reference_golden(name, env, monkeypatch):
@@ -81,3 +88,24 @@ def test_tile_pdl_and_resident_on_a_mid_size_hierarchy(monkeypatch):
     b = np.random.default_rng(12).random(ml.levels[0].A.shape[0])
     cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A))
     assert relerr(ml.solve(b, tol=0, maxiter=3), cyc.solve(b, tol=0, maxiter=3)) < 1e-12
+
+
+def test_flat_tile_kernel_on_a_mid_size_hierarchy_and_host_abi(monkeypatch):
+    """Flat-gather tiles on operators with 7-60 entries per row (every epilogue), plus the smoother KATs
+    through the host ABI (which builds one-operator hierarchies with the same kernels)."""
+    import oracle
+    from pyamg_b200.classical import ruge_stuben_solver
+    from pyamg_b200.aggregation import smoothed_aggregation_solver
+    from pyamg_b200.gallery import poisson
+    monkeypatch.setenv("AMGB_TILE_FLAT", "1")
+    monkeypatch.setenv("AMGB_TILE_MIN_NNZ", "0")
+    sm = ("gauss_seidel_indexed", {"sweep": "symmetric"})
+    ml = ruge_stuben_solver(poisson((40, 40, 40)), presmoother=sm, postsmoother=sm)
+    b = np.random.default_rng(13).random(ml.levels[0].A.shape[0])
+    cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A))
+    assert relerr(ml.solve(b, tol=0, maxiter=3), cyc.solve(b, tol=0, maxiter=3)) < 1e-12
+    jac = ("jacobi", {"omega": 4.0 / 3.0, "iterations": 2})
+    ml = smoothed_aggregation_solver(poisson((300, 300)), presmoother=jac, postsmoother=jac)
+    b = np.random.default_rng(14).random(ml.levels[0].A.shape[0])
+    cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A))
+    assert relerr(ml.solve(b, tol=0, maxiter=3, cycle="W"), cyc.solve(b, tol=0, maxiter=3, cycle="W")) < 1e-12

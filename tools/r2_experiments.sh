@@ -21,6 +21,12 @@ S="$S;AMGB_RESIDENT=1,AMGB_TILE_PDL=1"
 S="$S;AMGB_RESIDENT=1,AMGB_RESIDENT_MAX_ROWS=200000"           # + the 176 k-row level
 S="$S;AMGB_RESIDENT=1,AMGB_RESIDENT_MAX_ROWS=5000"             # only the smallest levels
 S="$S;AMGB_RESIDENT=1,AMGB_TILE_PDL=1,AMGB_TILE_MIN_NNZ=400000"
+S="$S;AMGB_TILE_FLAT=1"                                        # flat-gather tile kernel on every tiled operator
+S="$S;AMGB_TILE_FLAT=1,AMGB_TILE_MIN_NNZ=300000"               # ... also on the 176 k-row level's waves
+S="$S;AMGB_TILE_FLAT=1,AMGB_TILE_PDL=1"
+S="$S;AMGB_TILE_FLAT=1,AMGB_TILE_PDL=1,AMGB_RESIDENT=1"
+S="$S;AMGB_TILE_FLAT=1,AMGB_TILE_CTAS=5"
+S="$S;AMGB_TILE_FLAT=1,AMGB_TILE_CTAS=7"
 timeout 1500 python tools/tune_tiles.py --grid $G --settings "$S" 2>&1 | grep -E "cycle_ms|Error|error" | cut -c1-600
 echo "=== bench line (default settings)"
 timeout 900 python bench.py --steps 10 --warmup 3 2>/dev/null | tail -1 | tee gpurun_out/r2_bench_default.json | cut -c1-400
