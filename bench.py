@@ -55,7 +55,9 @@ WORKLOAD = {"name": "cfg3"}      # set by --workload; the default is BASELINE.js
 
 def build_hierarchy(grid, stream=None, device=0):
     """cfg3 (default): poisson(grid) + RS hierarchy + multi-colour symmetric GS on every level (BASELINE
-    configs[2]).  cfg2: 2-D poisson(grid[:2]) + smoothed aggregation + weighted Jacobi (BASELINE configs[1])."""
+    configs[2]).  cfg2: 2-D poisson(grid[:2]) + smoothed aggregation + weighted Jacobi (BASELINE configs[1]).
+    cfg5: linear_elasticity(grid[:2]) BSR(2,2) + smoothed aggregation on the rigid-body modes + block Jacobi
+    (BASELINE configs[4])."""
     from pyamg_b200.gallery import poisson
     from pyamg_b200.classical import ruge_stuben_solver
     from pyamg_b200.aggregation import smoothed_aggregation_solver
@@ -66,6 +68,12 @@ def build_hierarchy(grid, stream=None, device=0):
         t1 = time.time()
         sm = ("jacobi", {"omega": 4.0 / 3.0})
         ml = smoothed_aggregation_solver(A, presmoother=sm, postsmoother=sm, device=device, stream=stream)
+    elif WORKLOAD["name"] == "cfg5":
+        from pyamg_b200.gallery import linear_elasticity
+        A, B = linear_elasticity(tuple(grid)[:2])
+        t1 = time.time()
+        ml = smoothed_aggregation_solver(A, B=B, presmoother="block_jacobi", postsmoother="block_jacobi",
+                                         device=device, stream=stream)
     else:
         A = poisson(grid)
         t1 = time.time()
@@ -193,6 +201,14 @@ def workload_config(grid, ml, ngpus):
                 "n": int(ml.levels[0].A.shape[0]), "nnz": int(ml.levels[0].A.nnz),
                 "sum_nnz_A": int(sum(lv.A.nnz for lv in ml.levels)),
                 "parallelism": "1 GPU" if ngpus == 1 else f"{ngpus} GPUs", "l2": "inputs larger than L2"}
+    if WORKLOAD["name"] == "cfg5":
+        return {"workload": f"gallery.linear_elasticity({tuple(grid)[:2]}) Q1 fp64 BSR(2,2)->(3,3), "
+                            f"smoothed_aggregation_solver(B = rigid-body modes) hierarchy ({len(ml.levels)} levels, "
+                            f"op-cx {ml.operator_complexity():.3f}), block-Jacobi pre+post, pinv coarse solve, "
+                            "V(1,1)-cycle + per-cycle residual check",
+                "n": int(ml.levels[0].A.shape[0]), "nnz": int(ml.levels[0].A.nnz),
+                "sum_nnz_A": int(sum(lv.A.nnz for lv in ml.levels)),
+                "parallelism": "1 GPU" if ngpus == 1 else f"{ngpus} GPUs", "l2": "L2-resident problem"}
     return {"workload": f"gallery.poisson({tuple(grid)}) 7-pt fp64 CSR, ruge_stuben_solver hierarchy "
                         f"({len(ml.levels)} levels, op-cx {ml.operator_complexity():.3f}), symmetric multi-colour "
                         "Gauss-Seidel pre+post (gauss_seidel_indexed over colour-sorted rows), pinv coarse solve, "
@@ -326,9 +342,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=256, help="grid points per dimension (3-D)")
     ap.add_argument("--cpu-sample", type=int, default=2, help="V-cycles timed for cpu_baseline")
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2"],
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5"],
                     help="cfg3 = BASELINE configs[2] (headline, default); cfg2 = configs[1]: 2-D Poisson, SA + Jacobi "
-                         "(use --grid 2000)")
+                         "(use --grid 2000); cfg5 = configs[4]: 2-D elasticity, SA + block Jacobi (use --grid 300)")
     args = ap.parse_args()
     WORKLOAD["name"] = args.workload
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -34,6 +34,8 @@ def lib():
         L.amgb_setup_standard_aggregation.argtypes = [i32, _I, _I, _I, _I]
         L.amgb_setup_gauss_seidel.restype = None
         L.amgb_setup_gauss_seidel.argtypes = [i32, _I, _I, _D, _D, _D, i32, i32]
+        L.amgb_setup_block_gauss_seidel.restype = None
+        L.amgb_setup_block_gauss_seidel.argtypes = [i32, i32, _I, _I, _D, _D, _D, _D, i32, i32]
         L.amgb_setup_coloring_is_valid.restype = i32
         L.amgb_setup_coloring_is_valid.argtypes = [i32, _I, _I, _I]
         _lib = L

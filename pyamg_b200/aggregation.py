@@ -1,17 +1,20 @@
-"""Smoothed-aggregation AMG setup on the host for SCALAR problems -- ``smoothed_aggregation_solver``.
+"""Smoothed-aggregation AMG setup on the host -- ``smoothed_aggregation_solver`` for scalar (CSR) and vector
+(BSR, several near-nullspace candidates) problems.
 
-Mirror of pyamg/aggregation/aggregation.py:26-431 for its default pipeline with one near-nullspace
-candidate: symmetric strength (theta = 0) -> standard aggregation -> candidates improved by 4 symmetric
-Gauss-Seidel sweeps on A B = 0 (finest level) -> tentative prolongator T by normalising B over every
-aggregate (``fit_candidates`` with K1 = K2 = 1) -> P = (I - omega/rho(D^-1 A) D^-1 A) T -> R = P^T ->
-A_c = R A P -> ``MultilevelSolver`` + ``change_smoothers``.  Native pieces: csrc/host_setup.cpp.
+Mirror of pyamg/aggregation/aggregation.py:26-431 for its default pipeline: symmetric strength (for BSR on the
+Frobenius norms of the blocks, strength.py:327-345) -> standard aggregation of the node graph -> candidates
+improved by 4 symmetric (block) Gauss-Seidel sweeps on A B = 0 (finest level) -> tentative prolongator T by
+orthonormalising the candidates over every aggregate (``fit_candidates``, tentative.py:11-152 /
+smoothed_aggregation.h:484-600: modified Gram-Schmidt, K1 unknowns per node x K2 candidates) ->
+P = (I - omega/rho(D^-1 A) D^-1 A) T -> R = P^T -> A_c = R A P -> ``MultilevelSolver`` + ``change_smoothers``.
+Native pieces: csrc/host_setup.cpp.
 
 Setup, i.e. NOT the accelerated path (see classical.py): it lets BASELINE configs[1] (Poisson 2000^2, SA +
-weighted Jacobi) be synthesised where the reference is not installed.  The spectral-radius estimate is a
-seeded Arnoldi here (the reference's is randomly started), so omega -- hence P -- agrees with a reference
-run only to the accuracy of that estimate unless the same ``rho`` values are injected (``rho=[...]``; what
-tests/test_setup.py does).  Block (BSR) problems, other strength/aggregation/smoothing choices:
-NotImplementedError.
+weighted Jacobi) and configs[4] (linear elasticity, BSR, block Jacobi) be synthesised where the reference is
+not installed.  The spectral-radius estimate is a seeded Arnoldi here (the reference's is randomly started), so
+omega -- hence P -- agrees with a reference run only to the accuracy of that estimate unless the same ``rho``
+values are injected (``rho=[...]``; what tests/test_setup.py does).  Other strength/aggregation/smoothing
+choices, nonsymmetric problems: NotImplementedError.
 """
 import numpy as np
 from scipy import sparse
@@ -26,10 +29,32 @@ __all__ = ["smoothed_aggregation_solver", "symmetric_strength_pattern", "standar
            "fit_candidates", "jacobi_prolongation_smoother"]
 
 
+def _bsr32(A):
+    A = A if (sparse.issparse(A) and A.format == "bsr") else sparse.bsr_array(A)
+    A = sparse.bsr_array((np.ascontiguousarray(A.data, dtype=np.float64), A.indices.astype(np.int32),
+                          A.indptr.astype(np.int32)), shape=A.shape, blocksize=A.blocksize)
+    return A
+
+
+def _is_block(A):
+    return sparse.issparse(A) and A.format == "bsr" and A.blocksize != (1, 1)
+
+
 def symmetric_strength_pattern(A, theta=0.0):
-    """CSR pattern (values 1) of the symmetric strength-of-connection graph of A, diagonal included."""
+    """CSR pattern (values 1) of the symmetric strength-of-connection graph of A, diagonal included.  BSR input:
+    the graph of the NODES, measured on the Frobenius norms of the blocks (strength.py:327-345)."""
     if theta < 0:
         raise ValueError("expected a positive theta")
+    if _is_block(A):
+        R, C = A.blocksize
+        if R != C:
+            raise ValueError("matrix must have square blocks")
+        shape = (A.shape[0] // R, A.shape[1] // C)
+        if theta == 0:
+            return sparse.csr_array((np.ones(len(A.indices)), A.indices.astype(np.int32), A.indptr.astype(np.int32)),
+                                    shape=shape)
+        norms = np.sqrt((A.data * A.data).reshape(-1, R * C).sum(axis=1))
+        A = sparse.csr_array((norms, A.indices, A.indptr), shape=shape)
     A = _csr32(A)
     n = A.shape[0]
     Sp = np.empty(n + 1, dtype=np.int32)
@@ -55,36 +80,99 @@ def standard_aggregation(C):
 
 
 def fit_candidates(AggOp, B, tol=1e-10):
-    """Tentative prolongator for ONE candidate: T[i, a] = B_i / ||B restricted to a||, coarse candidate
-    R_a = that norm (columns whose norm is below tol are zeroed)."""
-    B = np.asarray(B, dtype=np.float64).reshape(-1)
+    """Tentative prolongator T and coarse candidates R with T R = B on the aggregated nodes and orthonormal
+    columns per aggregate (tentative.py:11-152).  B is (K1 * n_nodes, K2): K1 unknowns per node, K2 candidates.
+    Per aggregate the K2 columns of the stacked candidate rows are orthonormalised by modified Gram-Schmidt in
+    column order; a column whose norm after orthogonalisation is not above tol x (its norm before) is zeroed
+    (smoothed_aggregation.h:516-600).  T is CSR for K1 = K2 = 1, else BSR with (K1, K2) blocks."""
+    B = np.asarray(B, dtype=np.float64)
+    if B.ndim == 1:
+        B = B.reshape(-1, 1)
     AggOp = _csr32(AggOp)
     n, na = AggOp.shape
-    if len(B) != n:
-        raise NotImplementedError("fit_candidates: one candidate and one unknown per node only")
-    rows = np.repeat(np.arange(n), np.diff(AggOp.indptr))
-    aid = AggOp.indices
-    norms = np.sqrt(np.bincount(aid, weights=B[rows] ** 2, minlength=na))
-    keep = norms > tol * norms          # the reference's threshold is relative to the column's own norm
-    scale = np.zeros(na)
-    scale[keep] = 1.0 / norms[keep]
-    R = np.where(keep, norms, 0.0).reshape(-1, 1)
-    T = sparse.csr_array((B[rows] * scale[aid], aid.copy(), AggOp.indptr.copy()), shape=(n, na))
-    return T, R
+    if B.shape[0] % n != 0:
+        raise ValueError(f"Dimensions of AggOp {AggOp.shape} and B {B.shape} are incompatible")
+    K1, K2 = B.shape[0] // n, B.shape[1]
+    member = np.diff(AggOp.indptr) > 0
+    nodes = np.nonzero(member)[0]
+    agg_of = AggOp.indices                                        # aggregate of nodes[k]
+    order = np.argsort(agg_of, kind="stable")                     # aggregate-major, nodes ascending inside
+    Q = B.reshape(n, K1, K2)[nodes[order]].copy()                 # (members, K1, K2)
+    gid = np.repeat(agg_of[order], K1)                            # aggregate of every stacked row
+    Qr = Q.reshape(-1, K2)                                        # view: stacked rows x candidates
+    R = np.zeros((na, K2, K2))
+    colsum = lambda w: np.bincount(gid, weights=w, minlength=na)
+    for bj in range(K2):
+        norm0 = np.sqrt(colsum(Qr[:, bj] * Qr[:, bj]))
+        for bi in range(bj):
+            d = colsum(Qr[:, bj] * Qr[:, bi])
+            Qr[:, bj] -= d[gid] * Qr[:, bi]
+            R[:, bi, bj] = d
+        norm1 = np.sqrt(colsum(Qr[:, bj] * Qr[:, bj]))
+        keep = norm1 > tol * norm0
+        scale = np.zeros(na)
+        scale[keep] = 1.0 / norm1[keep]
+        R[keep, bj, bj] = norm1[keep]
+        Qr[:, bj] *= scale[gid]
+    data = np.empty_like(Q)
+    data[order] = Q                                               # back to node order
+    indptr = np.concatenate([[0], np.cumsum(member)]).astype(np.int32)
+    if K1 == 1 and K2 == 1:
+        T = sparse.csr_array((data.reshape(-1), agg_of.copy(), indptr), shape=(n, na))
+    else:
+        T = sparse.bsr_array((data, agg_of.copy(), indptr), shape=(n * K1, na * K2), blocksize=(K1, K2))
+    return T, R.reshape(-1, K2)
 
 
 def jacobi_prolongation_smoother(S, T, omega=4.0 / 3.0, degree=1, rho=None):
-    """P = (I - omega/rho(D^-1 S) D^-1 S)^degree T   (diagonal weighting)."""
-    S = _csr32(S)
+    """P = (I - omega/rho(D^-1 S) D^-1 S)^degree T   (diagonal weighting, smooth.py 'diagonal'); block operators
+    keep their block structure."""
     D_inv = get_diagonal(S, inv=True)
-    D_inv_S = sparse.dia_array((D_inv, 0), shape=S.shape) @ S
+    if _is_block(S):
+        S = _bsr32(S)
+        Rb = S.blocksize[0]
+        rows = np.repeat(np.arange(S.shape[0] // Rb), np.diff(S.indptr))
+        scale = D_inv.reshape(-1, Rb)[rows]                        # (blocks, Rb): one factor per block row
+        D_inv_S = sparse.bsr_array((S.data * scale[:, :, None], S.indices, S.indptr), shape=S.shape,
+                                   blocksize=S.blocksize)
+    else:
+        S = _csr32(S)
+        D_inv_S = sparse.dia_array((D_inv, 0), shape=S.shape) @ S
     if rho is None:
         rho = approximate_spectral_radius(D_inv_S)
     D_inv_S = (omega / rho) * D_inv_S
     P = T
     for _ in range(degree):
         P = P - D_inv_S @ P
+    if sparse.issparse(T) and T.format == "bsr":
+        return _bsr32(P.tobsr(blocksize=T.blocksize))
     return _csr32(P)
+
+
+def _improve_candidates(A, B, fn, kw):
+    """B <- (relaxation on A x = 0 started from every column of B)  (aggregation.py:359-367)."""
+    if fn not in ("gauss_seidel", "block_gauss_seidel") or kw.get("sweep", "forward") not in ("symmetric", "forward"):
+        raise NotImplementedError("host SA setup improves candidates with (block_)gauss_seidel only")
+    its = int(kw.get("iterations", 1))
+    sym = 1 if kw.get("sweep", "forward") == "symmetric" else 0
+    B = np.array(B, dtype=np.float64, order="F")                   # columns contiguous
+    zero = np.zeros(A.shape[0])
+    bs = A.blocksize[0] if (fn == "block_gauss_seidel" and _is_block(A)) else 1
+    if bs == 1:
+        Ac = _csr32(A)
+        for k in range(B.shape[1]):
+            H.lib().amgb_setup_gauss_seidel(Ac.shape[0], H.ip(Ac.indptr), H.ip(Ac.indices), H.dp(Ac.data),
+                                            H.dp(B[:, k]), H.dp(zero), its, sym)
+    else:
+        Ab = _bsr32(A)
+        from .util import get_block_diag
+        Dinv = get_block_diag(Ab, blocksize=bs, inv_flag=True)
+        data = np.ascontiguousarray(Ab.data)
+        for k in range(B.shape[1]):
+            H.lib().amgb_setup_block_gauss_seidel(Ab.shape[0] // bs, bs, H.ip(Ab.indptr), H.ip(Ab.indices),
+                                                  H.dp(data.reshape(-1)), H.dp(Dinv.reshape(-1)), H.dp(B[:, k]),
+                                                  H.dp(zero), its, sym)
+    return np.ascontiguousarray(B)
 
 
 def smoothed_aggregation_solver(A, B=None, symmetry="hermitian", strength="symmetric", aggregate="standard",
@@ -108,25 +196,31 @@ def smoothed_aggregation_solver(A, B=None, symmetry="hermitian", strength="symme
             return [spec[min(i, 1)] for i in range(max_levels)]      # (first, rest) form of improve_candidates
         return [spec] * max_levels
 
-    if sparse.issparse(A) and A.format == "bsr" and A.blocksize != (1, 1):
-        raise NotImplementedError("host SA setup handles scalar problems (one unknown per node) only")
     if symmetry not in ("hermitian", "symmetric"):
         raise NotImplementedError("host SA setup: symmetric problems only")
-    A = _csr32(A)
+    A = _bsr32(A) if _is_block(A) else _csr32(A)
     if A.shape[0] != A.shape[1]:
         raise ValueError("expected square matrix")
-    B = np.ones(A.shape[0]) if B is None else np.asarray(B, dtype=np.float64).reshape(-1)
-    if len(B) != A.shape[0]:
-        raise NotImplementedError("host SA setup: one near-nullspace candidate only")
+    bs0 = A.blocksize[0] if _is_block(A) else 1
+    if B is None:
+        B = np.kron(np.ones((A.shape[0] // bs0, 1)), np.eye(bs0))      # aggregation.py:222-225
+    B = np.asarray(B, dtype=np.float64)
+    if B.ndim == 1:
+        B = B.reshape(-1, 1)
+    if B.shape[0] != A.shape[0]:
+        raise ValueError("The shape of near null-space modes B is incorrect")
     strength, aggregate, smooth = levelize(strength), levelize(aggregate), levelize(smooth)
     improve_candidates = levelize(improve_candidates)
     rho = list(rho) if rho is not None else []
 
+    def nodes_of(M):
+        return M.shape[0] // (M.blocksize[0] if _is_block(M) else 1)
+
     levels = [MultilevelSolver.Level()]
-    levels[-1].A, levels[-1].B = A, B.reshape(-1, 1)
-    while len(levels) < max_levels and levels[-1].A.shape[0] > max_coarse:
+    levels[-1].A, levels[-1].B = A, B
+    while len(levels) < max_levels and nodes_of(levels[-1].A) > max_coarse:
         k = len(levels) - 1
-        A, B = levels[-1].A, levels[-1].B.reshape(-1)
+        A, B = levels[-1].A, levels[-1].B
         fn, kw = unpack(strength[k])
         if fn != "symmetric" or set(kw) - {"theta"}:
             raise NotImplementedError("host SA setup offers strength=('symmetric', {'theta': t}) only")
@@ -137,13 +231,8 @@ def smoothed_aggregation_solver(A, B=None, symmetry="hermitian", strength="symme
         AggOp, Cnodes = standard_aggregation(C)
         fn, kw = unpack(improve_candidates[k])
         if fn is not None:
-            if fn not in ("gauss_seidel", "block_gauss_seidel") or kw.get("sweep", "forward") not in ("symmetric", "forward"):
-                raise NotImplementedError("host SA setup improves candidates with (block_)gauss_seidel only")
-            B = B.copy()
-            H.lib().amgb_setup_gauss_seidel(A.shape[0], H.ip(A.indptr), H.ip(A.indices), H.dp(A.data), H.dp(B),
-                                            H.dp(np.zeros(A.shape[0])), int(kw.get("iterations", 1)),
-                                            1 if kw.get("sweep", "forward") == "symmetric" else 0)
-            levels[-1].B = B.reshape(-1, 1)
+            B = _improve_candidates(A, B, fn, kw)
+            levels[-1].B = B
         T, Bc = fit_candidates(AggOp, B)
         fn, kw = unpack(smooth[k])
         if fn == "jacobi":
@@ -151,15 +240,21 @@ def smoothed_aggregation_solver(A, B=None, symmetry="hermitian", strength="symme
                 raise NotImplementedError("host SA setup: jacobi prolongation smoothing with omega/degree only")
             P = jacobi_prolongation_smoother(A, T, rho=rho[k] if k < len(rho) else None, **kw)
         elif fn is None:
-            P = _csr32(T)
+            P = _bsr32(T) if T.format == "bsr" else _csr32(T)
         else:
             raise NotImplementedError("host SA setup offers smooth=('jacobi', {...}) or None only")
-        R = _csr32(P.T.tocsr())
+        if P.format == "bsr":
+            R = _bsr32(P.T.tobsr(blocksize=P.blocksize[::-1]))
+            Ac = (R @ A @ P)
+            Ac = _bsr32(Ac.tobsr(blocksize=(P.blocksize[1], P.blocksize[1])))
+        else:
+            R = _csr32(P.T.tocsr())
+            Ac = _csr32(R @ A @ P)
         if keep:
             levels[-1].C, levels[-1].AggOp, levels[-1].Cnodes, levels[-1].T = C, AggOp, Cnodes, T
         levels[-1].P, levels[-1].R = P, R
         levels.append(MultilevelSolver.Level())
-        levels[-1].A = _csr32(R @ A @ P)
+        levels[-1].A = Ac
         levels[-1].B = Bc
     ml = MultilevelSolver(levels, **kwargs)
     change_smoothers(ml, presmoother, postsmoother)

@@ -449,6 +449,44 @@ void amgb_setup_gauss_seidel(int32_t n, const int32_t *Ap, const int32_t *Aj, co
     }
 }
 
+// Sequential BLOCK Gauss-Seidel sweeps on the host (candidate improvement for vector problems): block row i of
+// the BSR operator (blocks bs x bs, row-major) against x, then x_i = Dinv_i (b_i - sum_{j != i} A_ij x_j) with
+// the (pseudo-)inverted diagonal blocks supplied by the caller.  `symmetric` != 0: forward then backward.
+void amgb_setup_block_gauss_seidel(int32_t nb, int32_t bs, const int32_t *Ap, const int32_t *Aj, const double *Ax,
+                                   const double *Dinv, double *x, const double *b, int32_t iterations,
+                                   int32_t symmetric)
+{
+    const int64_t bb = (int64_t)bs * bs;
+    std::vector<double> rsum((size_t)bs);
+    auto sweep = [&](int32_t start, int32_t stop, int32_t step) {
+        for (int32_t i = start; i != stop; i += step) {
+            std::fill(rsum.begin(), rsum.end(), 0.0);
+            for (int32_t jj = Ap[i]; jj < Ap[i + 1]; jj++) {
+                const int32_t j = Aj[jj];
+                if (j == i) continue;
+                const double *blk = Ax + (int64_t)jj * bb;
+                const double *xj = x + (int64_t)j * bs;
+                for (int32_t r = 0; r < bs; r++) {
+                    double v = 0.0;
+                    for (int32_t c = 0; c < bs; c++) v += blk[(int64_t)r * bs + c] * xj[c];
+                    rsum[(size_t)r] += v;
+                }
+            }
+            for (int32_t r = 0; r < bs; r++) rsum[(size_t)r] = b[(int64_t)i * bs + r] - rsum[(size_t)r];
+            const double *di = Dinv + (int64_t)i * bb;
+            for (int32_t r = 0; r < bs; r++) {
+                double v = 0.0;
+                for (int32_t c = 0; c < bs; c++) v += di[(int64_t)r * bs + c] * rsum[(size_t)c];
+                x[(int64_t)i * bs + r] = v;
+            }
+        }
+    };
+    for (int32_t it = 0; it < iterations; it++) {
+        sweep(0, nb, 1);
+        if (symmetric) sweep(nb - 1, -1, -1);
+    }
+}
+
 // 1 if no stored off-diagonal entry joins two rows of equal colour (checks a colouring computed on a
 // pattern assumed symmetric), else 0.
 int32_t amgb_setup_coloring_is_valid(int32_t n, const int32_t *Ap, const int32_t *Aj, const int32_t *colors)

@@ -89,3 +89,69 @@ def diffusion_stencil_2d(epsilon=1.0, theta=0.0, type="FE"):
         Gyy = eps * CC + SS
         return np.array([[-Fxy / 4, -Exx, Fxy / 4], [-Gyy, 2 * Exx + 2 * Gyy, -Gyy], [Fxy / 4, -Exx, -Fxy / 4]])
     raise ValueError("type must be 'FE' or 'FD'")
+
+
+def _q1_plane_strain_stiffness(dx, dy, lame, mu):
+    """8x8 stiffness of one bilinear (Q1) rectangle dx x dy in plane strain, by 2x2 Gauss quadrature (exact for
+    this element).  Vertices counter-clockwise from the lower left; unknowns (u_x, u_y) per vertex."""
+    D = np.array([[lame + 2.0 * mu, lame, 0.0], [lame, lame + 2.0 * mu, 0.0], [0.0, 0.0, mu]])
+    sx = np.array([-1.0, 1.0, 1.0, -1.0])        # reference-square signs of the four vertices
+    sy = np.array([-1.0, -1.0, 1.0, 1.0])
+    g = 1.0 / np.sqrt(3.0)
+    K = np.zeros((8, 8))
+    for xi in (-g, g):
+        for eta in (-g, g):
+            dNdx = sx * (1.0 + sy * eta) / 4.0 * (2.0 / dx)
+            dNdy = sy * (1.0 + sx * xi) / 4.0 * (2.0 / dy)
+            Bm = np.zeros((3, 8))
+            Bm[0, 0::2] = dNdx
+            Bm[1, 1::2] = dNdy
+            Bm[2, 0::2] = dNdy
+            Bm[2, 1::2] = dNdx
+            K += Bm.T @ D @ Bm * (dx * dy / 4.0)
+    return K
+
+
+def linear_elasticity(grid, spacing=None, E=1e5, nu=0.3, format=None):
+    """2-D linear elasticity, Q1 elements on a regular grid with a clamped (Dirichlet) boundary:
+    (A, B) = BSR(2,2) stiffness matrix over the grid[0] x grid[1] interior vertices and the three rigid-body
+    modes (two translations, one rotation about the grid centre) as near-nullspace candidates.
+
+    Same problem as pyamg.gallery.linear_elasticity (gallery/elasticity.py:9-120; vertex k = iy*X + ix, unknowns
+    interleaved); the element matrix is integrated here by quadrature instead of the reference's closed form, so
+    entries agree to rounding (tests/test_setup.py).  The reference only accepts square grids (its index
+    arithmetic overruns otherwise); any X x Y grid is assembled here."""
+    if len(grid) != 2:
+        raise NotImplementedError(f"No support for grid={grid}")
+    X, Y = int(grid[0]), int(grid[1])
+    if X < 1 or Y < 1:
+        raise ValueError("invalid grid shape")
+    DX, DY = (1.0, 1.0) if spacing is None else (float(spacing[0]), float(spacing[1]))
+    lame = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu))
+    mu = E / (2.0 + 2.0 * nu)
+    K = _q1_plane_strain_stiffness(DX, DY, lame, mu)
+    # elements (ex, ey), 0 <= ex <= X, 0 <= ey <= Y, on the (X+2) x (Y+2) vertex grid; interior vertices only
+    ex, ey = np.meshgrid(np.arange(X + 1), np.arange(Y + 1), indexing="xy")
+    ex, ey = ex.ravel(), ey.ravel()
+    vx = np.stack([ex, ex + 1, ex + 1, ex], axis=1)          # vertex grid coordinates, counter-clockwise
+    vy = np.stack([ey, ey, ey + 1, ey + 1], axis=1)
+    inside = (vx >= 1) & (vx <= X) & (vy >= 1) & (vy <= Y)
+    vid = (vy - 1) * X + (vx - 1)                              # interior vertex number
+    dof = np.stack([2 * vid, 2 * vid + 1], axis=2).reshape(-1, 8)
+    ok = np.repeat(inside, 2, axis=1)
+    I = np.repeat(dof[:, :, None], 8, axis=2)
+    J = np.repeat(dof[:, None, :], 8, axis=1)
+    M = ok[:, :, None] & ok[:, None, :]
+    V = np.broadcast_to(K, I.shape)
+    n = 2 * X * Y
+    A = sparse.coo_array((V[M], (I[M], J[M])), shape=(n, n)).tocsr().tobsr(blocksize=(2, 2))
+    # rigid-body modes at the interior vertices; coordinates relative to the centre of the clamped plate
+    iy, ix = np.divmod(np.arange(X * Y), X)
+    px = (ix + 1 - (X + 1) / 2.0) * DX
+    py = (iy + 1 - (Y + 1) / 2.0) * DY
+    B = np.zeros((n, 3))
+    B[0::2, 0] = 1.0
+    B[1::2, 1] = 1.0
+    B[0::2, 2] = -py
+    B[1::2, 2] = px
+    return (A if format is None else A.asformat(format)), B

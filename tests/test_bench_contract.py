@@ -18,7 +18,8 @@ def _run(extra, env=None):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, **(env or {})))
 
 
-@pytest.mark.parametrize("extra", [["--grid", "12"], ["--grid", "40", "--workload", "cfg2"]])
+@pytest.mark.parametrize("extra", [["--grid", "12"], ["--grid", "40", "--workload", "cfg2"],
+                                   ["--grid", "20", "--workload", "cfg5"]])
 def test_reference_arm_prints_one_contract_line(extra):
     r = _run(extra)
     assert r.returncode == 0, r.stderr[-2000:]
