@@ -52,6 +52,7 @@ extern "C" {
 #define AMGB_CYCLE_V 0
 #define AMGB_CYCLE_W 1
 #define AMGB_CYCLE_F 2
+#define AMGB_CYCLE_AMLI 3   /* multilevel.py:631-657 (two A_c-orthogonalised coarse corrections per level) */
 
 typedef struct amgb_hierarchy amgb_hierarchy;
 

@@ -365,7 +365,7 @@ def cg(A, b, x0=None, tol=1e-5, maxiter=None, M=None, callback=None, residuals=N
 
 
 class Cycle:
-    """Restatement of MultilevelSolver.solve/__solve (pyamg/multilevel.py:398-662), V/W/F cycles,
+    """Restatement of MultilevelSolver.solve/__solve (pyamg/multilevel.py:398-662), V/W/F/AMLI cycles,
     'pinv' coarse solve (:717-721, GenericSolver.__call__ :797-816)."""
 
     def __init__(self, levels, coarse_pinv=None, kernels="oracle"):
@@ -436,6 +436,23 @@ class Cycle:
             self._solve(lvl + 1, coarse_x, coarse_b, cycle, cycles_per_level)
             for _ in range(cycles_per_level):
                 self._solve(lvl + 1, coarse_x, coarse_b, "V", 1)
+        elif cycle == "AMLI":
+            # multilevel.py:631-657: two A_c-orthogonalised coarse corrections; every inner solve starts from an
+            # all-ones guess and sees the coarse rhs as updated by the previous step
+            nAMLI = 2
+            Ac = self.levels[lvl + 1]["A"]
+            p = np.zeros((nAMLI, coarse_b.shape[0]))
+            for k in range(nAMLI):
+                p[k, :] = 1
+                self._solve(lvl + 1, p[k, :], coarse_b, cycle)
+                for j in range(k):
+                    beta = np.inner(p[j, :], matvec(Ac, p[k, :], self.kernels)) / \
+                        np.inner(p[j, :], matvec(Ac, p[j, :], self.kernels))
+                    p[k, :] -= beta * p[j, :]
+                Ap = matvec(Ac, p[k, :], self.kernels)
+                alpha = np.inner(p[k, :], coarse_b) / np.inner(p[k, :], Ap)
+                coarse_x += alpha * p[k, :]
+                coarse_b -= alpha * Ap
         else:
             raise TypeError(f"Unrecognized cycle type ({cycle})")
         x += matvec(L["P"], coarse_x, self.kernels)

@@ -230,6 +230,17 @@ __global__ void axpby_kernel(double a, const double *__restrict__ x, double b, d
     for (; i < n; i += stride) y[i] = a * x[i] + b * y[i];
 }
 
+// y += sign * (num / den) * x with the two scalars read from device memory (AMLI step sizes: no host round trip,
+// so the cycle stays capturable in a CUDA graph)
+__global__ void axpy_ratio_kernel(double *__restrict__ y, const double *__restrict__ x, const double *num,
+                                  const double *den, double sign, long long n)
+{
+    const double a = sign * (num[0] / den[0]);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) y[i] += a * x[i];
+}
+
 // out[slot] = sum(partials[0..m)) in a fixed order (single block) -> deterministic norms
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *partials, int m,
                                                                double *out)

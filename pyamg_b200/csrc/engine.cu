@@ -415,6 +415,9 @@ struct Level {
     bool has_pr = false;
     Smoother pre, post;
     double *x = nullptr, *x_home = nullptr, *xalt = nullptr, *b = nullptr, *r = nullptr;
+    // AMLI cycle (allocated on first use): the two search directions, A_c p, the accumulated coarse correction
+    // and four device scalars (<p0,b>, <p0,Ap0>, <p1,b> | <p0,Ap1'>, <p1,Ap1>)
+    double *amli_p[2] = {nullptr, nullptr}, *amli_Ap = nullptr, *amli_x = nullptr, *amli_s = nullptr;
 };
 
 static int validate_matrix(const amgb_matrix *M, const char *name)
@@ -643,9 +646,9 @@ struct amgb_hierarchy {
     double *sumsq_parts = nullptr;
     double *kry[4] = {nullptr, nullptr, nullptr, nullptr};   // Krylov work vectors (allocated on first use)
 
-    cudaGraphExec_t graph[3] = {nullptr, nullptr, nullptr};
-    int graph_cpl[3] = {0, 0, 0};
-    long long graph_nodes[3] = {0, 0, 0};
+    cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
+    int graph_cpl[4] = {0, 0, 0, 0};
+    long long graph_nodes[4] = {0, 0, 0, 0};
     bool profiling = false;
     int cur_level = 0;
     std::vector<ProfRec> prof;
@@ -669,7 +672,7 @@ struct amgb_hierarchy {
     bool recording = false;
     std::vector<TailStep> rec;
     double rec_bytes = 0.0;
-    struct TailProg { TailStep *dev = nullptr; int n = 0, cpl = -1, lvl = -1; double bytes = 0.0; } tail_prog[3];
+    struct TailProg { TailStep *dev = nullptr; int n = 0, cpl = -1, lvl = -1; double bytes = 0.0; } tail_prog[4];
 
     int record(int op, int G, int row0, int nrows, const int *rows, const DevCsr *M, const double *x,
                const double *b, double *y, double omega, double bytes, const double *dense = nullptr, int ncols = 0)
@@ -959,6 +962,12 @@ struct amgb_hierarchy {
         return launch_fill(x, n, 0.0, stream);
     }
 
+    int launch_fill_value(double *x, long long n, double v)
+    {
+        launches += (n > 0);
+        return launch_fill(x, n, v, stream);
+    }
+
     // MultilevelSolver.__solve (multilevel.py:584-662)
     int cycle(int lvl, int kind, int cpl)
     {
@@ -968,7 +977,7 @@ struct amgb_hierarchy {
         RET(smooth(L, L.pre));                                          // :610
         RET(spmv(OP_RESID, L.A, L.x, L.b, L.r));                        // :612
         RET(spmv(OP_SPMV, L.R, L.r, nullptr, C.b));                     // :614
-        if (lvl + 1 >= tail_level && !recording) RET(run_tail(lvl, kind, cpl));
+        if (lvl + 1 >= tail_level && !recording && kind != AMGB_CYCLE_AMLI) RET(run_tail(lvl, kind, cpl));
         else RET(descend(lvl, kind, cpl));
         cur_level = lvl;
         RET(spmv(OP_PADD, L.P, C.x, nullptr, L.x));                     // :660
@@ -991,6 +1000,7 @@ struct amgb_hierarchy {
     {
         Level &C = levels[(size_t)lvl + 1];
         if (lvl == (int)levels.size() - 2) return coarse_solve(C);      // :617-618
+        if (kind == AMGB_CYCLE_AMLI) return descend_amli(lvl, cpl);     // :631-657
         RET(launch_count_fill(C.x, C.A.n_rows));                        // :615
         if (kind == AMGB_CYCLE_V) {
             RET(cycle(lvl + 1, AMGB_CYCLE_V, 1));                       // :619-620
@@ -1004,6 +1014,79 @@ struct amgb_hierarchy {
             return fail(AMGB_EINVAL, "Unrecognized cycle type");        // :658 (TypeError)
         }
         return AMGB_OK;
+    }
+
+    // device dot product into a device scalar (two-stage, fixed grid: bit-reproducible)
+    int dot_to(const double *x, const double *y, long long n, double *out_dev)
+    {
+        dot_partials_kernel<<<kSumsqBlocks, 256, 0, stream>>>(x, y, n, sumsq_parts);
+        CK(cudaGetLastError());
+        reduce_partials_kernel<<<1, 1024, 0, stream>>>(sumsq_parts, kSumsqBlocks, out_dev);
+        CK(cudaGetLastError());
+        launches += 2;
+        return AMGB_OK;
+    }
+    int axpy_ratio(double *y, const double *x, const double *num, const double *den, double sign, long long n)
+    {
+        if (n <= 0) return AMGB_OK;
+        const long long grid = std::min<long long>((n + 255) / 256, (long long)g_num_sms * 16);
+        axpy_ratio_kernel<<<(unsigned)grid, 256, 0, stream>>>(y, x, num, den, sign, n);
+        CK(cudaGetLastError());
+        launches++;
+        return AMGB_OK;
+    }
+    int copy_vec(double *dst, const double *src, long long n)
+    {
+        CK(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+        launches++;
+        return AMGB_OK;
+    }
+
+    // buffers of the AMLI recursion on levels 1 .. L-2 (must exist before a graph capture starts)
+    int prepare_amli()
+    {
+        for (size_t l = 1; l + 1 < levels.size(); l++) {
+            Level &C = levels[l];
+            if (C.amli_s != nullptr) continue;
+            const long long n = C.A.n_rows;
+            RET(dalloc(&C.amli_p[0], n + 2));
+            RET(dalloc(&C.amli_p[1], n + 2));
+            RET(dalloc(&C.amli_Ap, n + 2));
+            RET(dalloc(&C.amli_x, n + 2));
+            RET(dalloc(&C.amli_s, 8));
+        }
+        return AMGB_OK;
+    }
+
+    // multilevel.py:631-657.  nAMLI = 2 corrections p_k = (one AMLI cycle on level lvl+1 from the all-ones guess,
+    // for the CURRENT coarse rhs), A_c-orthogonalised against the earlier one, each with the optimal step
+    // alpha_k = <p_k, b_c> / <p_k, A_c p_k>; the coarse rhs is updated in between.  <p_0, A_c p_0> is needed
+    // twice by the reference (step size, then the orthogonalisation coefficient): computed once here.
+    int descend_amli(int lvl, int cpl)
+    {
+        Level &C = levels[(size_t)lvl + 1];
+        const long long n = C.A.n_rows;
+        if (C.amli_s == nullptr) return fail(AMGB_ESTATE, "AMLI buffers not prepared");
+        double *s = C.amli_s;               // s[0] = <p0,b>, s[1] = <p0,Ap0>, s[2] = <p0,A p1'>, s[3] = <p1,b>, s[4] = <p1,Ap1>
+        RET(launch_count_fill(C.amli_x, n));                            // coarse_x = 0 (:615)
+        for (int k = 0; k < 2; k++) {
+            double *pk = C.amli_p[k];
+            RET(launch_fill_value(C.x, n, 1.0));                        // p[k, :] = 1 (:640)
+            RET(cycle(lvl + 1, AMGB_CYCLE_AMLI, cpl));                  // :641-642
+            cur_level = lvl + 1;
+            RET(copy_vec(pk, C.x, n));
+            if (k == 1) {                                               // :645-648
+                RET(spmv(OP_SPMV, C.A, pk, nullptr, C.amli_Ap));
+                RET(dot_to(C.amli_p[0], C.amli_Ap, n, s + 2));
+                RET(axpy_ratio(pk, C.amli_p[0], s + 2, s + 1, -1.0, n));
+            }
+            RET(spmv(OP_SPMV, C.A, pk, nullptr, C.amli_Ap));            // :651
+            RET(dot_to(pk, C.b, n, s + (k == 0 ? 0 : 3)));              // :652-653
+            RET(dot_to(pk, C.amli_Ap, n, s + (k == 0 ? 1 : 4)));
+            RET(axpy_ratio(C.amli_x, pk, s + (k == 0 ? 0 : 3), s + (k == 0 ? 1 : 4), 1.0, n));      // :656
+            RET(axpy_ratio(C.b, C.amli_Ap, s + (k == 0 ? 0 : 3), s + (k == 0 ? 1 : 4), -1.0, n));   // :659
+        }
+        return copy_vec(C.x, C.amli_x, n);                              // what the prolongation reads
     }
 
     // the same, for levels >= tail_level: recorded once, replayed by one cluster kernel
@@ -1073,7 +1156,8 @@ struct amgb_hierarchy {
         if (levels.size() == 1) {   // multilevel.py:559-561: x = coarse_solver(A, b)
             return coarse_solve(levels[0]);
         }
-        RET(prepare_tail(kind, cpl));
+        if (kind == AMGB_CYCLE_AMLI) RET(prepare_amli());
+        else RET(prepare_tail(kind, cpl));
         if (!use_graph) return cycle(0, kind, cpl);
         if (graph[kind] == nullptr || graph_cpl[kind] != cpl) {
             if (graph[kind] != nullptr) { cudaGraphExecDestroy(graph[kind]); graph[kind] = nullptr; }
@@ -1391,7 +1475,7 @@ extern "C" void amgb_hierarchy_destroy(amgb_hierarchy *h)
     if (h == nullptr) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (int k = 0; k < 3; k++)
+    for (int k = 0; k < 4; k++)
         if (h->graph[k]) cudaGraphExecDestroy(h->graph[k]);
     for (void *p : h->allocs) cudaFree(p);
     if (h->norm_host) cudaFreeHost(h->norm_host);
@@ -1583,7 +1667,7 @@ static int check_cycle_args(amgb_hierarchy *h, int32_t cycle, int32_t cpl)
     if (h == nullptr) return fail(AMGB_EINVAL, "null hierarchy");
     if (!h->finalized) return fail(AMGB_ESTATE, "hierarchy not finalized");
     h->rt.activate();             // every solve / profile entry point passes through here
-    if (cycle < 0 || cycle > 2) return fail(AMGB_EINVAL, "Unrecognized cycle type");
+    if (cycle < 0 || cycle > AMGB_CYCLE_AMLI) return fail(AMGB_EINVAL, "Unrecognized cycle type");
     if (cpl < 0) return fail(AMGB_EINVAL, "cycles_per_level < 0");
     return AMGB_OK;
 }

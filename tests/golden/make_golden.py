@@ -16,7 +16,7 @@ Run in the build container only (the GPU box has no /root/reference):
 Every fixture is one .npz written by pyamg_b200.hierarchy_io.save_hierarchy: the hierarchy the
 reference built (operators, smoother closures' parameters, cached coarse pinv) plus, as extra
 arrays, the rhs ``b``, the reference's ``x_ref = ml.solve(b, tol=0, maxiter=N)``, its residual
-history, W/F-cycle results, and single-sweep outputs of the reference's own relaxation routines and
+history, W/F/AMLI-cycle results, and single-sweep outputs of the reference's own relaxation routines and
 SciPy matvecs on level 0 (``k_*``).  Configs are the five BASELINE.json families at sizes the CPU
 suite runs in seconds.  rhs seed = 20260922.
 """
@@ -95,6 +95,9 @@ def emit(name, ml, extra_kw=None, ncyc=NCYC, cg_anyway=True):
     extra["residuals"] = np.array(res)
     extra["x_ref_W"] = ml.solve(b, tol=0, maxiter=2, cycle="W")
     extra["x_ref_F"] = ml.solve(b, tol=0, maxiter=2, cycle="F")
+    res = []
+    extra["x_ref_AMLI"] = ml.solve(b, tol=0, maxiter=3, cycle="AMLI", residuals=res)
+    extra["residuals_AMLI"] = np.array(res)
     x0 = rng.random(n)
     res = []
     xt, info = ml.solve(b, x0=x0, tol=1e-6, maxiter=50, residuals=res, return_info=True)

@@ -123,7 +123,8 @@ def test_single_level_hierarchy_is_a_coarse_solve():
     assert relerr(x, np.linalg.pinv(A.toarray()) @ b) < TOL
 
 
-def test_errors_mirror_the_reference(load_golden):
+def test_errors_mirror_the_reference(load_golden, monkeypatch):
+    monkeypatch.delenv("AMGB_EXPERIMENTAL", raising=False)     # AMLI is opt-in until validated on a B200
     ml, ex = load_golden("cfg1_rs_gs_poisson2d")
     with pytest.raises(TypeError):
         ml.solve(ex["b"], cycle="Q")                      # multilevel.py:658

@@ -121,6 +121,9 @@ def test_oracle_vcycle_matches_reference(name, load_golden):
     assert relerr(cyc.solve(ex["b"], tol=0, maxiter=2, cycle="W"), ex["x_ref_W"]) < TIGHT
     assert relerr(cyc.solve(ex["b"], tol=0, maxiter=2, cycle="F"), ex["x_ref_F"]) < TIGHT
     res = []
+    assert relerr(cyc.solve(ex["b"], tol=0, maxiter=3, cycle="AMLI", residuals=res), ex["x_ref_AMLI"]) < TIGHT
+    assert np.allclose(res, ex["residuals_AMLI"], rtol=1e-12, atol=0)
+    res = []
     x, info = cyc.solve(ex["b"], x0=ex["x0"], tol=1e-6, maxiter=50, residuals=res, return_info=True)
     assert info == int(ex["info_tol"][0])
     assert len(res) == len(ex["residuals_tol"])
