@@ -68,7 +68,12 @@ def lib():
     if not os.path.exists(path):
         raise EngineError("libpyamg_b200.so is missing: run `python -m pyamg_b200.build` "
                           "(there is no CPU fallback)")
-    L = ctypes.CDLL(path)
+    _lib = _bind(ctypes.CDLL(path))
+    return _lib
+
+
+def _bind(L):
+    """Declare the C signatures of include/pyamg_b200.h on a loaded library object."""
     L.amgb_last_error.restype = ctypes.c_char_p
     L.amgb_hierarchy_device_bytes.restype = ctypes.c_int64
     L.amgb_hierarchy_last_launches.restype = ctypes.c_int64
@@ -123,7 +128,6 @@ def lib():
     L.amgb_debug_build_tiles.argtypes = [i32, c_i32p, i32, ctypes.POINTER(ctypes.c_int64), i32, i32, i32, c_i32p,
                                          c_i32p, i32, c_i32p, c_i32p]
     L.amgb_wave_schedule.argtypes = [i32, c_i32p, c_i32p, c_i32p, i64, c_i32p, c_i32p]
-    _lib = L
     return L
 
 

@@ -48,15 +48,23 @@ struct CsrRowArgs {
 // streaming loads for the operator arrays: read once, keep them out of L1 so the x gathers own it
 __device__ __forceinline__ int ld_stream_i32(const int *p)
 {
+#ifdef AMGB_EMU      // host-side emulation build (tests/emu): same logic, plain load
+    return *p;
+#else
     int v;
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
+#endif
 }
 __device__ __forceinline__ double ld_stream_f64(const double *p)
 {
+#ifdef AMGB_EMU
+    return *p;
+#else
     double v;
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
+#endif
 }
 
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
@@ -64,11 +72,15 @@ __device__ __forceinline__ double ld_stream_f64(const double *p)
 // the predecessor produces before pdl_wait().  Without the attribute both are no-ops.
 __device__ __forceinline__ void pdl_launch_dependents()
 {
+#ifndef AMGB_EMU
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
 __device__ __forceinline__ void pdl_wait()
 {
+#ifndef AMGB_EMU
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 }
 
 template <int G>

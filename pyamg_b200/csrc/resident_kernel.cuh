@@ -37,19 +37,31 @@ constexpr int kResidentMaxLog2m = 14;      // 16384 doubles = 128 KB of shared m
 
 __device__ __forceinline__ unsigned dsmem_addr(const double *local, unsigned cta)
 {
+#ifdef AMGB_EMU
+    return ::emu::dsmem_addr(local, cta);
+#else
     unsigned r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"((unsigned)__cvta_generic_to_shared(local)), "r"(cta));
     return r;
+#endif
 }
 __device__ __forceinline__ double dsmem_ld(unsigned addr)
 {
+#ifdef AMGB_EMU
+    return *::emu::dsmem_ptr(addr);
+#else
     double v;
     asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
     return v;
+#endif
 }
 __device__ __forceinline__ void dsmem_st(unsigned addr, double v)
 {
+#ifdef AMGB_EMU
+    *::emu::dsmem_ptr(addr) = v;
+#else
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+#endif
 }
 
 template <int G>

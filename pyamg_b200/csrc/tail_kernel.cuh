@@ -40,19 +40,31 @@ constexpr int kTailThreads = 1024;
 
 __device__ __forceinline__ void cluster_barrier()
 {
+#ifdef AMGB_EMU
+    ::emu::cluster_barrier();
+#else
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
 }
 __device__ __forceinline__ unsigned cluster_rank()
 {
+#ifdef AMGB_EMU
+    return ::emu::cluster_ctarank();
+#else
     unsigned r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
+#endif
 }
 __device__ __forceinline__ unsigned cluster_size()
 {
+#ifdef AMGB_EMU
+    return ::emu::cluster_nctarank();
+#else
     unsigned r;
     asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
     return r;
+#endif
 }
 
 // SOLO = true: the step runs inside one CTA; vectors may be read through L1 (same-SM coherent).

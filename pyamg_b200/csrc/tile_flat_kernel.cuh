@@ -34,7 +34,9 @@ constexpr size_t tile_flat_smem_bytes() { return sizeof(TileFlatWarpSmemT<C, OP>
 
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
+#ifndef AMGB_EMU
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
 }
 
 // launch bounds: 6 CTAs of 8 warps per SM (the residency the tile kernels were tuned to) caps registers at 40
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, 6) csr_tile_flat_kernel(const T
 
     if (lane == 0) {
         mbar_init(&ws.bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbar_init();
     }
     __syncwarp();
     const unsigned long long pol_first = policy_evict_first();

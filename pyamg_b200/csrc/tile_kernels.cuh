@@ -81,15 +81,32 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
 {
+#ifdef AMGB_EMU
+    ::emu::mbar_init(bar, count);
+#else
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+#endif
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+#ifndef AMGB_EMU
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
 {
+#ifdef AMGB_EMU
+    ::emu::mbar_arrive_expect_tx(bar, bytes);
+#else
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
+#ifdef AMGB_EMU
+    ::emu::mbar_wait(bar, parity);
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -100,47 +117,75 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#endif
 }
 __device__ __forceinline__ unsigned long long policy_evict_first()
 {
+#ifdef AMGB_EMU
+    return 0ull;
+#else
     unsigned long long p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
+#endif
 }
 __device__ __forceinline__ unsigned long long policy_evict_last()
 {
+#ifdef AMGB_EMU
+    return 0ull;
+#else
     unsigned long long p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
+#endif
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA, SASS UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
 {
+#ifdef AMGB_EMU
+    ::emu::bulk_g2s(dst, src, bytes, bar);
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, unsigned bytes, unsigned long long *bar,
                                               unsigned long long policy)
 {
+#ifdef AMGB_EMU
+    (void)policy;
+    ::emu::bulk_g2s(dst, src, bytes, bar);
+#else
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
             "r"(smem_u32(dst)),
         "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
+#endif
 }
 __device__ __forceinline__ double ld_x_hint_nc(const double *p, unsigned long long policy)
 {
+#ifdef AMGB_EMU
+    (void)policy;
+    return *p;
+#else
     double v;
     asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
     return v;
+#endif
 }
 __device__ __forceinline__ double ld_x_hint(const double *p, unsigned long long policy)
 {
+#ifdef AMGB_EMU
+    (void)policy;
+    return *p;
+#else
     double v;
     asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy) : "memory");
     return v;
+#endif
 }
 
 // One lane: ask the TMA for tile t's segments.  Every source starts on a 16-byte boundary: entry ranges
@@ -205,7 +250,7 @@ __global__ void __launch_bounds__(C::WARPS * 32) csr_tile_kernel(const TileArgs 
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; s++) mbar_init(&ws.bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbar_init();
     }
     __syncwarp();
     const unsigned long long pol_first = policy_evict_first();

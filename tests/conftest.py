@@ -23,6 +23,20 @@ def pytest_configure(config):
                                        "(run explicitly with -m gpu_experimental; never part of -m gpu)")
 
 
+def _install_emulator():
+    """AMGB_TEST_EMU=1: run the `gpu` tests against tests/emu (the engine's kernel sources executed on host
+    fibers) instead of a B200.  Test infrastructure only -- the product never loads that library."""
+    import ctypes
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    from pyamg_b200 import _engine as E
+    E._lib = E._bind(ctypes.CDLL(build_emu.build()))
+
+
+if os.environ.get("AMGB_TEST_EMU") == "1":
+    _install_emulator()
+
+
 def golden_path(name):
     return os.path.join(GOLDEN_DIR, name + ".npz")
 
