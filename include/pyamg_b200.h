@@ -44,6 +44,14 @@ extern "C" {
 #define AMGB_SM_GAUSS_SEIDEL 2    /* relaxation.gauss_seidel / gauss_seidel_indexed: a row list
                                      executed in dependency waves == the sequential sweep       */
 #define AMGB_SM_BLOCK_JACOBI 3    /* relaxation.block_jacobi  (BSR + Dinv)                       */
+/* the cheap smoothers that share the SpMV / row-sweep core */
+#define AMGB_SM_POLYNOMIAL 4      /* relaxation.polynomial (relaxation.py:585-659): x += p(A)(b - A x), Horner;
+                                     what 'chebyshev' and 'richardson' resolve to (smoothing.py:611-647)      */
+#define AMGB_SM_JACOBI_INDEXED 5  /* relaxation.jacobi_indexed (relaxation.py:1081-1138 -> relaxation.h:382-427) */
+#define AMGB_SM_CF_JACOBI 6       /* relaxation.cf_jacobi (relaxation.py:1141-1203): C sweeps, then F sweeps     */
+#define AMGB_SM_FC_JACOBI 7       /* relaxation.fc_jacobi (relaxation.py:1206-1268): F sweeps, then C sweeps     */
+#define AMGB_SM_BLOCK_GAUSS_SEIDEL 8  /* relaxation.block_gauss_seidel (relaxation.py:502-582 ->
+                                     relaxation.h:1242-1298): block rows in dependency waves == the sequential sweep */
 
 #define AMGB_SWEEP_FORWARD 0
 #define AMGB_SWEEP_BACKWARD 1
@@ -79,7 +87,15 @@ typedef struct {
     const int32_t *indices;       /* Gauss-Seidel: explicit row list (gauss_seidel_indexed), or NULL
                                      for the natural order 0..n-1 (gauss_seidel) */
     int64_t n_indices;
-    const double *Dinv;           /* block Jacobi: (n/bs, bs, bs) row-major block-diagonal inverses */
+    const double *Dinv;           /* block Jacobi / block Gauss-Seidel: (n/bs, bs, bs) row-major block-diagonal inverses */
+    /* ---- fields below exist since amgb_version() >= 101; zero them for the kinds above ---- */
+    const int32_t *indices2;      /* CF/FC Jacobi: the F-points (indices = the C-points) */
+    int64_t n_indices2;
+    int32_t f_iterations;         /* CF/FC Jacobi: F sweeps per iteration */
+    int32_t c_iterations;         /* CF/FC Jacobi: C sweeps per iteration */
+    const double *coefficients;   /* polynomial: coefficients of p in DESCENDING order (relaxation.py:606-617) */
+    int32_t n_coefficients;
+    int32_t reserved_;
 } amgb_smoother;
 
 const char *amgb_last_error(void);
@@ -197,6 +213,22 @@ int amgb_host_block_jacobi(const int32_t *Ap, int Ap_size, const int32_t *Aj, in
                            double *temp, int temp_size, int32_t row_start, int32_t row_stop,
                            int32_t row_step, const double *omega, int omega_size,
                            int32_t blocksize);
+/* amg_core.jacobi_indexed (relaxation_bind.cpp:164-196 <- relaxation.h:382-427) */
+int amgb_host_jacobi_indexed(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                             const double *Ax, int Ax_size, double *x, int x_size,
+                             const double *b, int b_size, const int32_t *indices, int indices_size,
+                             const double *omega, int omega_size);
+/* amg_core.block_gauss_seidel (relaxation_bind.cpp:545-580 <- relaxation.h:1242-1298); only the full forward
+ * (0, nb, 1) and backward (nb-1, -1, -1) ranges the reference's Python layer passes (relaxation.py:561-582) */
+int amgb_host_block_gauss_seidel(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                                 const double *Ax, int Ax_size, double *x, int x_size,
+                                 const double *b, int b_size, const double *Tx, int Tx_size,
+                                 int32_t row_start, int32_t row_stop, int32_t row_step, int32_t blocksize);
+/* One application of ANY smoother descriptor to host vectors (x in place): what calling a level's
+ * presmoother(A, x, b) does in the reference (multilevel.py:610).  Runs the same wave schedules, tiles and
+ * kernels the cycle uses; the entry point behind the Python mirrors of relaxation.polynomial / cf_jacobi /
+ * fc_jacobi / jacobi_indexed / block_gauss_seidel. */
+int amgb_host_relax(const amgb_matrix *A, const amgb_smoother *sm, double *x, const double *b);
 /* scipy.sparse._sparsetools.csr_matvec / bsr_matvec as the cycle uses them (y = A x) */
 int amgb_host_matvec(const amgb_matrix *A, const double *x, double *y);
 

@@ -217,14 +217,89 @@ def gauss_seidel_indexed(A, x, b, indices, iterations=1, sweep="forward", kernel
                                               _dp(x), _dp(b), _ip(indices), *rs)
 
 
-def jacobi_indexed(A, x, b, indices, omega=1.0):
-    """pyamg/relaxation/relaxation.py:734-790 -> relaxation.h:382-427."""
+def jacobi_indexed(A, x, b, indices, iterations=1, omega=1.0, kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:1081-1138 -> relaxation.h:382-427."""
     A, x, b = make_system(A, x, b, formats=["csr"])
     _f64(A, x, b)
     indices = np.ascontiguousarray(indices, dtype=np.int32)
-    lib().oracle_jacobi_indexed(_ip(A.indptr), _ip(A.indices), _dp(A.data), _dp(x),
-                                A.shape[0], _dp(b), _ip(indices), len(indices),
-                                ctypes.c_double(float(omega)))
+    for _ in range(iterations):
+        if kernels == "ref":
+            lib("ref").ref_jacobi_indexed(_ip(A.indptr), A.shape[0], _ip(A.indices), _dp(A.data), len(A.data),
+                                          _dp(x), _dp(b), _ip(indices), len(indices), ctypes.c_double(float(omega)))
+        else:
+            lib().oracle_jacobi_indexed(_ip(A.indptr), _ip(A.indices), _dp(A.data), _dp(x),
+                                        A.shape[0], _dp(b), _ip(indices), len(indices),
+                                        ctypes.c_double(float(omega)))
+
+
+def cf_jacobi(A, x, b, Cpts, Fpts, iterations=1, f_iterations=1, c_iterations=1, omega=1.0, kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:1141-1203 (CSR branch): C sweeps, then F sweeps."""
+    for _ in range(iterations):
+        for _c in range(c_iterations):
+            jacobi_indexed(A, x, b, Cpts, omega=omega, kernels=kernels)
+        for _f in range(f_iterations):
+            jacobi_indexed(A, x, b, Fpts, omega=omega, kernels=kernels)
+
+
+def fc_jacobi(A, x, b, Cpts, Fpts, iterations=1, f_iterations=1, c_iterations=1, omega=1.0, kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:1206-1268 (CSR branch): F sweeps, then C sweeps."""
+    for _ in range(iterations):
+        for _f in range(f_iterations):
+            jacobi_indexed(A, x, b, Fpts, omega=omega, kernels=kernels)
+        for _c in range(c_iterations):
+            jacobi_indexed(A, x, b, Cpts, omega=omega, kernels=kernels)
+
+
+def polynomial(A, x, b, coefficients, iterations=1, kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:585-659: x += p(A)(b - A x) by Horner's rule; the matvecs are the
+    reference's SciPy calls restated (``matvec``)."""
+    A, x, b = make_system(A, x, b, formats=None)
+    _f64(A, x, b)
+    for _ in range(iterations):
+        if np.linalg.norm(x) == 0:                       # :646-649
+            residual = b
+        else:
+            residual = b - matvec(A, x, kernels)
+        h = coefficients[0] * residual                   # :651
+        for c in coefficients[1:]:                       # :653-654
+            h = c * residual + matvec(A, h, kernels)
+        x += h                                           # :656
+
+
+def block_gauss_seidel(A, x, b, iterations=1, sweep="forward", blocksize=1, Dinv=None, kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:502-582 -> relaxation.h:1242-1298 (Dinv must be given)."""
+    A, x, b = make_system(A, x, b, formats=["csr", "bsr"])
+    _f64(A, x, b)
+    A = A.tobsr(blocksize=(blocksize, blocksize))
+    if Dinv is None:
+        raise ValueError("oracle.block_gauss_seidel needs Dinv (setup-time quantity)")
+    if Dinv.shape[0] != A.shape[0] // blocksize:
+        raise ValueError("Dinv and A have incompatible dimensions")
+    if Dinv.shape[1] != blocksize or Dinv.shape[2] != blocksize:
+        raise ValueError("Dinv and blocksize are incompatible")
+    nb = len(x) // blocksize
+    if sweep == "forward":
+        rs = (0, nb, 1)
+    elif sweep == "backward":
+        rs = (nb - 1, -1, -1)
+    elif sweep == "symmetric":
+        for _ in range(iterations):
+            block_gauss_seidel(A, x, b, 1, "forward", blocksize, Dinv, kernels)
+            block_gauss_seidel(A, x, b, 1, "backward", blocksize, Dinv, kernels)
+        return
+    else:
+        raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+    if nb == 0:
+        return
+    data = np.ascontiguousarray(A.data).ravel()
+    dinv = np.ascontiguousarray(Dinv, dtype=np.float64).ravel()
+    for _ in range(iterations):
+        if kernels == "ref":
+            lib("ref").ref_block_gauss_seidel(_ip(A.indptr), nb, _ip(A.indices), _dp(data), len(A.indices),
+                                              _dp(x), _dp(b), _dp(dinv), *rs, blocksize)
+        else:
+            lib().oracle_block_gauss_seidel(_ip(A.indptr), _ip(A.indices), _dp(data), _dp(x), _dp(b),
+                                            _dp(dinv), *rs, blocksize)
 
 
 def block_jacobi(A, x, b, Dinv=None, blocksize=1, iterations=1, omega=1.0, kernels="oracle"):
@@ -261,6 +336,11 @@ _SMOOTHERS = {
     "gauss_seidel_indexed": gauss_seidel_indexed,
     "block_jacobi": block_jacobi,
     "sor": sor,
+    "polynomial": polynomial,
+    "jacobi_indexed": jacobi_indexed,
+    "cf_jacobi": cf_jacobi,
+    "fc_jacobi": fc_jacobi,
+    "block_gauss_seidel": block_gauss_seidel,
 }
 
 
@@ -283,6 +363,12 @@ def smoother_spec(sm):
         return (func.__name__, dict(sm.keywords))
     if getattr(sm, "__name__", "") == "none":
         return None
+    if getattr(sm, "__name__", "") in ("richardson", "chebyshev") and getattr(sm, "__closure__", None):
+        # smoothing.py:611-618 / :627-647: closures around relaxation.polynomial; parameters live in the cells
+        cv = {k: c.cell_contents for k, c in zip(sm.__code__.co_freevars, sm.__closure__)}
+        coef = cv["coefficients"] if "coefficients" in cv else [cv["omega"]]
+        return ("polynomial", {"coefficients": np.asarray(coef, dtype=np.float64),
+                               "iterations": int(cv.get("iterations", 1))})
     raise NotImplementedError(f"oracle: smoother {sm!r} is not introspectable")
 
 

@@ -68,4 +68,21 @@ void ref_block_jacobi(const int *Ap, int nb, const int *Aj, const double *Ax, in
                                       row_step, &omega, 1, bs);
 }
 
+// pyamg/amg_core/relaxation.h:382-427
+void ref_jacobi_indexed(const int *Ap, int n, const int *Aj, const double *Ax, int nnz, double *x,
+                        const double *b, const int *Id, int n_id, double omega)
+{
+    jacobi_indexed<int, double, double>(Ap, n + 1, Aj, nnz, Ax, nnz, x, n, b, n, Id, n_id, &omega, 1);
+}
+
+// pyamg/amg_core/relaxation.h:1242-1298
+void ref_block_gauss_seidel(const int *Ap, int nb, const int *Aj, const double *Ax, int nblk,
+                            double *x, const double *b, const double *Dinv, int row_start,
+                            int row_stop, int row_step, int bs)
+{
+    int n = nb * bs;
+    block_gauss_seidel<int, double, double>(Ap, nb + 1, Aj, nblk, Ax, nblk * bs * bs, x, n, b, n,
+                                            Dinv, nb * bs * bs, row_start, row_stop, row_step, bs);
+}
+
 }  // extern "C"

@@ -16,6 +16,7 @@ c_f64p = ctypes.POINTER(ctypes.c_double)
 
 OK, EINVAL, ECUDA, ENOTIMPL, ESTATE = 0, -1, -2, -3, -4
 SM_NONE, SM_JACOBI, SM_GAUSS_SEIDEL, SM_BLOCK_JACOBI = 0, 1, 2, 3
+SM_POLYNOMIAL, SM_JACOBI_INDEXED, SM_CF_JACOBI, SM_FC_JACOBI, SM_BLOCK_GAUSS_SEIDEL = 4, 5, 6, 7, 8
 SWEEPS = {"forward": 0, "backward": 1, "symmetric": 2}
 CYCLES = {"V": 0, "W": 1, "F": 2, "AMLI": 3}
 FLAG_X0_ZERO = 1
@@ -33,7 +34,10 @@ class Smoother(ctypes.Structure):
                 ("sweep", ctypes.c_int32), ("blocksize", ctypes.c_int32),
                 ("omega", ctypes.c_double),
                 ("indices", c_i32p), ("n_indices", ctypes.c_int64),
-                ("Dinv", c_f64p)]
+                ("Dinv", c_f64p),
+                ("indices2", c_i32p), ("n_indices2", ctypes.c_int64),
+                ("f_iterations", ctypes.c_int32), ("c_iterations", ctypes.c_int32),
+                ("coefficients", c_f64p), ("n_coefficients", ctypes.c_int32), ("reserved_", ctypes.c_int32)]
 
 
 class EngineError(RuntimeError):
@@ -53,6 +57,7 @@ SYMBOLS = [
     "amgb_host_jacobi", "amgb_host_gauss_seidel", "amgb_host_sor_gauss_seidel",
     "amgb_host_gauss_seidel_indexed",
     "amgb_host_bsr_jacobi", "amgb_host_block_jacobi", "amgb_host_matvec",
+    "amgb_host_jacobi_indexed", "amgb_host_block_gauss_seidel", "amgb_host_relax",
     "amgb_dev_csr_spmv", "amgb_dev_csr_residual", "amgb_dev_csr_spmv_add", "amgb_dev_csr_jacobi",
     "amgb_dev_csr_gs_wave", "amgb_dev_partials_len", "amgb_dev_dense_matvec", "amgb_dev_fill",
     "amgb_dev_gather", "amgb_wave_schedule", "amgb_debug_build_tiles",
@@ -116,6 +121,11 @@ def _bind(L):
     L.amgb_host_block_jacobi.argtypes = [c_i32p, ci, c_i32p, ci, c_f64p, ci, c_f64p, ci, c_f64p, ci,
                                          c_f64p, ci, c_f64p, ci, i32, i32, i32, c_f64p, ci, i32]
     L.amgb_host_matvec.argtypes = [ctypes.POINTER(Matrix), c_f64p, c_f64p]
+    L.amgb_host_jacobi_indexed.argtypes = [c_i32p, ci, c_i32p, ci, c_f64p, ci, c_f64p, ci, c_f64p, ci,
+                                           c_i32p, ci, c_f64p, ci]
+    L.amgb_host_block_gauss_seidel.argtypes = [c_i32p, ci, c_i32p, ci, c_f64p, ci, c_f64p, ci, c_f64p, ci,
+                                               c_f64p, ci, i32, i32, i32, i32]
+    L.amgb_host_relax.argtypes = [ctypes.POINTER(Matrix), ctypes.POINTER(Smoother), c_f64p, c_f64p]
     L.amgb_dev_csr_spmv.argtypes = [i32, vp, vp, vp, vp, vp, ci, vp]
     L.amgb_dev_csr_residual.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, ci, vp]
     L.amgb_dev_csr_spmv_add.argtypes = [i32, vp, vp, vp, vp, vp, ci, vp]

@@ -242,6 +242,14 @@ __global__ void axpby_kernel(double a, const double *__restrict__ x, double b, d
     for (; i < n; i += stride) y[i] = a * x[i] + b * y[i];
 }
 
+// y = a*x  (first Horner term of the polynomial smoother; never reads y, which may be uninitialised)
+__global__ void scale_kernel(double a, const double *__restrict__ x, double *__restrict__ y, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) y[i] = a * x[i];
+}
+
 // y += sign * (num / den) * x with the two scalars read from device memory (AMLI step sizes: no host round trip,
 // so the cycle stays capturable in a CUDA graph)
 __global__ void axpy_ratio_kernel(double *__restrict__ y, const double *__restrict__ x, const double *num,

@@ -57,7 +57,7 @@ static int fail(int code, const std::string &msg)
     } while (0)
 
 extern "C" const char *amgb_last_error(void) { return g_err.c_str(); }
-extern "C" int amgb_version(void) { return 100; }
+extern "C" int amgb_version(void) { return 101; }
 extern "C" int amgb_device_count(void)
 {
     int n = 0;
@@ -380,6 +380,10 @@ struct SmootherSpec {       // host copy of an amgb_smoother
     bool has_list = false;
     std::vector<int> list;
     std::vector<double> Dinv;
+    // SURVEY 8(f)-2 smoothers
+    std::vector<int> list2;          // CF/FC Jacobi: F-points (list = C-points)
+    int f_iterations = 1, c_iterations = 1;
+    std::vector<double> coef;        // polynomial, descending order
 };
 
 struct Smoother {
@@ -390,6 +394,11 @@ struct Smoother {
     double omega = 1.0;
     WaveSchedule ws;
     double *Dinv = nullptr;
+    // indexed Jacobi sweeps (jacobi_indexed: rows1; CF/FC Jacobi: rows1 = C-points, rows2 = F-points), level numbering
+    int *rows1 = nullptr, *rows2 = nullptr;
+    long long n_rows1 = 0, n_rows2 = 0;
+    int f_iterations = 1, c_iterations = 1;
+    std::vector<double> coef;        // polynomial coefficients (host: they become kernel arguments)
     // EXPERIMENTAL resident-vector cluster sweep (AMGB_RESIDENT=1): device copies of the schedule
     long long *res_wave_ptr = nullptr;
     int *res_seq = nullptr;
@@ -415,6 +424,7 @@ struct Level {
     bool has_pr = false;
     Smoother pre, post;
     double *x = nullptr, *x_home = nullptr, *xalt = nullptr, *b = nullptr, *r = nullptr;
+    double *poly[2] = {nullptr, nullptr};     // polynomial smoother: Horner accumulator h and A h
     // AMLI cycle (allocated on first use): the two search directions, A_c p, the accumulated coarse correction
     // and four device scalars (<p0,b>, <p0,Ap0>, <p1,b> | <p0,Ap1'>, <p1,Ap1>)
     double *amli_p[2] = {nullptr, nullptr}, *amli_Ap = nullptr, *amli_x = nullptr, *amli_s = nullptr;
@@ -863,9 +873,84 @@ struct amgb_hierarchy {
             return AMGB_OK;
         }
         case AMGB_SM_BLOCK_JACOBI: return block_jacobi(L, s);
+        case AMGB_SM_POLYNOMIAL: return polynomial(L, s);
+        case AMGB_SM_JACOBI_INDEXED:                                   // relaxation.py:1133-1138
+            for (int it = 0; it < s.iterations; it++) RET(jacobi_indexed(L, s.rows1, s.n_rows1, s.omega));
+            return AMGB_OK;
+        case AMGB_SM_CF_JACOBI:                                        // relaxation.py:1184-1189
+        case AMGB_SM_FC_JACOBI:                                        // relaxation.py:1249-1254
+            for (int it = 0; it < s.iterations; it++) {
+                if (s.kind == AMGB_SM_FC_JACOBI)
+                    for (int f = 0; f < s.f_iterations; f++) RET(jacobi_indexed(L, s.rows2, s.n_rows2, s.omega));
+                for (int c = 0; c < s.c_iterations; c++) RET(jacobi_indexed(L, s.rows1, s.n_rows1, s.omega));
+                if (s.kind == AMGB_SM_CF_JACOBI)
+                    for (int f = 0; f < s.f_iterations; f++) RET(jacobi_indexed(L, s.rows2, s.n_rows2, s.omega));
+            }
+            return AMGB_OK;
+        case AMGB_SM_BLOCK_GAUSS_SEIDEL: return block_gauss_seidel(L, s);
         }
         return fail(AMGB_ENOTIMPL, "smoother kind");
     }
+
+    // amg_core.jacobi_indexed (relaxation.h:382-427): temp = x, then the listed rows are relaxed from temp.
+    // The level's spare iterate buffer is temp; the rows kernel reads it and writes x (rows outside the list
+    // keep their values; a zero diagonal rewrites the old value).
+    int jacobi_indexed(Level &L, const int *rows, long long m, double omega)
+    {
+        if (recording) return fail(AMGB_ESTATE, "indexed Jacobi inside the cluster tail");
+        if (m <= 0) return AMGB_OK;
+        double *temp = (L.x == L.x_home) ? L.xalt : L.x_home;
+        RET(copy_vec(temp, L.x, L.A.n_rows));
+        launches++;
+        // bytes: the listed rows' entries are not known per list here; account the vector traffic + row list
+        RET(prof_begin(8, L.A.lanes, m, 0, 16.0 * L.A.n_rows + 28.0 * (double)m));
+        CsrRowArgs a;
+        a.n = (int)m; a.row0 = 0; a.rows = rows;
+        a.Ap = L.A.Ap; a.Aj = L.A.Aj; a.Ax = L.A.Ax;
+        a.x = temp; a.b = L.b; a.y = L.x; a.r = nullptr; a.omega = omega; a.partials = nullptr;
+        RET(launch_csr(OP_JACOBI, L.A.lanes, a, stream));
+        return prof_end();
+    }
+
+    // relaxation.polynomial (relaxation.py:646-659): per iteration r = b - A x, h = c_0 r,
+    // h = c_k r + A h (Horner), x += h.  L.r is free during smoothing (the cycle recomputes it afterwards).
+    int polynomial(Level &L, const Smoother &s)
+    {
+        if (recording) return fail(AMGB_ESTATE, "polynomial smoother inside the cluster tail");
+        if (s.coef.empty() || L.poly[0] == nullptr) return fail(AMGB_ESTATE, "polynomial smoother not prepared");
+        const long long n = L.A.n_rows;
+        for (int it = 0; it < s.iterations; it++) {
+            RET(spmv(OP_RESID, L.A, L.x, L.b, L.r));
+            double *h = L.poly[0], *Ah = L.poly[1];
+            RET(scale_to(h, s.coef[0], L.r, n));
+            for (size_t k = 1; k < s.coef.size(); k++) {
+                RET(spmv(OP_SPMV, L.A, h, nullptr, Ah));
+                RET(axpby(s.coef[k], L.r, 1.0, Ah, n));      // A h + c_k r
+                std::swap(h, Ah);
+            }
+            RET(axpby(1.0, h, 1.0, L.x, n));
+        }
+        return AMGB_OK;
+    }
+    int axpby(double a, const double *x, double b, double *y, long long n)
+    {
+        if (n <= 0) return AMGB_OK;
+        const long long grid = std::min<long long>((n + 255) / 256, (long long)g_num_sms * 16);
+        axpby_kernel<<<(unsigned)grid, 256, 0, stream>>>(a, x, b, y, n);
+        CK(cudaGetLastError());
+        launches++;
+        return AMGB_OK;
+    }
+    int scale_to(double *y, double a, const double *x, long long n)
+    {
+        if (n <= 0) return AMGB_OK;
+        const long long grid = std::min<long long>((n + 255) / 256, (long long)g_num_sms * 16);
+        scale_kernel<<<(unsigned)grid, 256, 0, stream>>>(a, x, y, n);
+        CK(cudaGetLastError());
+        launches++;
+        return AMGB_OK;
+    }
+    int block_gauss_seidel(Level &L, const Smoother &s);   // defined below (needs its kernel)
 
     // one launch = the whole smoother application (resident_kernel.cuh)
     int resident_apply(Level &L, const Smoother &s)
@@ -1301,6 +1386,110 @@ int amgb_hierarchy::block_jacobi(Level &L, const Smoother &s)
     return AMGB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// block Gauss-Seidel (relaxation.h:1242-1298) on the point-CSR expansion: the sequential sweep over block
+// rows is executed in dependency waves of the BLOCK graph (build_waves on the block pattern); inside a wave
+// one group of G lanes per block row sums the off-diagonal-block products with the CURRENT iterate and
+// writes x_I = Dinv_I (b_I - rsum) in place (no block of the wave reads another block of the same wave).
+// ------------------------------------------------------------------------------------------
+template <int G, int BS>
+__global__ void __launch_bounds__(kCsrThreads) block_gs_kernel(int nrows, const int *__restrict__ brows,
+                                                               const int *__restrict__ Ap, const int *__restrict__ Aj,
+                                                               const double *__restrict__ Ax, double *x,
+                                                               const double *__restrict__ b,
+                                                               const double *__restrict__ Dinv)
+{
+    const int lane = threadIdx.x & (G - 1);
+    const long long k = ((long long)blockIdx.x * kCsrThreads + threadIdx.x) / G;
+    const bool active = k < nrows;
+    const int I = active ? brows[k] : 0;
+    double rs[BS];
+#pragma unroll
+    for (int q = 0; q < BS; q++) {
+        double sum = 0.0;
+        if (active) {
+            const int row = I * BS + q;
+            const int s = Ap[row], e = Ap[row + 1];
+            for (int jj = s + lane; jj < e; jj += G) {
+                const int c = ld_stream_i32(Aj + jj);
+                const double v = ld_stream_f64(Ax + jj);
+                if (c / BS != I) sum += v * x[c];           // plain load: x is written by this launch
+            }
+        }
+        rs[q] = group_sum<G>(sum);
+    }
+    if (active && lane == 0) {
+        const size_t base = (size_t)I * BS;
+#pragma unroll
+        for (int q = 0; q < BS; q++) rs[q] = b[base + q] - rs[q];
+#pragma unroll
+        for (int q = 0; q < BS; q++) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < BS; c++) v += Dinv[base * BS + (size_t)q * BS + c] * rs[c];
+            x[base + q] = v;
+        }
+    }
+}
+
+template <int BS>
+static int launch_block_gs(int lanes, int nrows, const int *brows, const DevCsr &A, double *x, const double *b,
+                           const double *Dinv, cudaStream_t s)
+{
+    if (nrows <= 0) return AMGB_OK;
+    const dim3 g((unsigned)csr_grid(nrows, lanes)), t(kCsrThreads);
+    switch (lanes) {
+    case 1: block_gs_kernel<1, BS><<<g, t, 0, s>>>(nrows, brows, A.Ap, A.Aj, A.Ax, x, b, Dinv); break;
+    case 2: block_gs_kernel<2, BS><<<g, t, 0, s>>>(nrows, brows, A.Ap, A.Aj, A.Ax, x, b, Dinv); break;
+    case 4: block_gs_kernel<4, BS><<<g, t, 0, s>>>(nrows, brows, A.Ap, A.Aj, A.Ax, x, b, Dinv); break;
+    case 8: block_gs_kernel<8, BS><<<g, t, 0, s>>>(nrows, brows, A.Ap, A.Aj, A.Ax, x, b, Dinv); break;
+    case 16: block_gs_kernel<16, BS><<<g, t, 0, s>>>(nrows, brows, A.Ap, A.Aj, A.Ax, x, b, Dinv); break;
+    default: block_gs_kernel<32, BS><<<g, t, 0, s>>>(nrows, brows, A.Ap, A.Aj, A.Ax, x, b, Dinv); break;
+    }
+    CK(cudaGetLastError());
+    return AMGB_OK;
+}
+
+static int dispatch_block_gs(int bs, int lanes, int nrows, const int *brows, const DevCsr &A, double *x,
+                             const double *b, const double *Dinv, cudaStream_t s)
+{
+    switch (bs) {
+    case 1: return launch_block_gs<1>(lanes, nrows, brows, A, x, b, Dinv, s);
+    case 2: return launch_block_gs<2>(lanes, nrows, brows, A, x, b, Dinv, s);
+    case 3: return launch_block_gs<3>(lanes, nrows, brows, A, x, b, Dinv, s);
+    case 4: return launch_block_gs<4>(lanes, nrows, brows, A, x, b, Dinv, s);
+    case 5: return launch_block_gs<5>(lanes, nrows, brows, A, x, b, Dinv, s);
+    case 6: return launch_block_gs<6>(lanes, nrows, brows, A, x, b, Dinv, s);
+    case 7: return launch_block_gs<7>(lanes, nrows, brows, A, x, b, Dinv, s);
+    case 8: return launch_block_gs<8>(lanes, nrows, brows, A, x, b, Dinv, s);
+    }
+    return fail(AMGB_ENOTIMPL, "block_gauss_seidel: blocksize must be 1..8");
+}
+
+int amgb_hierarchy::block_gauss_seidel(Level &L, const Smoother &s)
+{
+    if (recording) return fail(AMGB_ESTATE, "block Gauss-Seidel inside the cluster tail");
+    const long long nw = (long long)s.ws.ptr.size() - 1;
+    auto wave = [&](long long w) -> int {
+        const int nr = (int)(s.ws.ptr[(size_t)w + 1] - s.ws.ptr[(size_t)w]);
+        if (nr <= 0) return AMGB_OK;
+        launches++;
+        RET(prof_begin(9, L.A.lanes, (long long)nr * s.bs, s.ws.nnz[(size_t)w],
+                       12.0 * s.ws.nnz[(size_t)w] + (4.0 + (28.0 + 8.0 * s.bs) * s.bs) * nr));
+        RET(dispatch_block_gs(s.bs, L.A.lanes, nr, s.ws.rows + s.ws.ptr[(size_t)w], L.A, L.x, L.b, s.Dinv, stream));
+        return prof_end();
+    };
+    for (int it = 0; it < s.iterations; it++) {                          // relaxation.py:561-582
+        if (s.sweep == AMGB_SWEEP_FORWARD || s.sweep == AMGB_SWEEP_SYMMETRIC)
+            for (long long w = 0; w < nw; w++) RET(wave(w));
+        if (s.sweep == AMGB_SWEEP_BACKWARD)
+            for (long long w = nw - 1; w >= 0; w--) RET(wave(w));
+        if (s.sweep == AMGB_SWEEP_SYMMETRIC)       // the middle wave relaxed twice in a row is idempotent: skipped
+            for (long long w = nw - 2; w >= 0; w--) RET(wave(w));
+    }
+    return AMGB_OK;
+}
+
 // smoother on the (possibly permuted) level operator.  `pos` maps original row ids to the level's
 // numbering (null = identity).  If `shared` is given the schedule is the level's own wave-major
 // layout (contiguous waves); otherwise waves are derived here and executed through a row list.
@@ -1340,6 +1529,46 @@ int amgb_hierarchy::make_smoother(const SmootherSpec &sp, const HostCsr &Aperm, 
                 s.ws.nnz[w] += Aperm.Ap[(size_t)rows[(size_t)k] + 1] - Aperm.Ap[(size_t)rows[(size_t)k]];
     } else if (sp.kind == AMGB_SM_BLOCK_JACOBI) {
         RET(upload(&s.Dinv, sp.Dinv.data(), (long long)sp.Dinv.size()));
+    } else if (sp.kind == AMGB_SM_POLYNOMIAL) {
+        s.coef = sp.coef;
+    } else if (sp.kind == AMGB_SM_JACOBI_INDEXED || sp.kind == AMGB_SM_CF_JACOBI || sp.kind == AMGB_SM_FC_JACOBI) {
+        s.f_iterations = sp.f_iterations;
+        s.c_iterations = sp.c_iterations;
+        std::vector<int> l1 = sp.list, l2 = sp.list2;
+        if (pos) {                                  // the level was put in wave-major order by its other smoother
+            for (int &v : l1) v = (*pos)[(size_t)v];
+            for (int &v : l2) v = (*pos)[(size_t)v];
+        }
+        RET(upload(&s.rows1, l1.data(), (long long)l1.size()));
+        RET(upload(&s.rows2, l2.data(), (long long)l2.size()));
+        s.n_rows1 = (long long)l1.size();
+        s.n_rows2 = (long long)l2.size();
+    } else if (sp.kind == AMGB_SM_BLOCK_GAUSS_SEIDEL) {
+        if (pos) return fail(AMGB_ESTATE, "block Gauss-Seidel on a permuted level");
+        RET(upload(&s.Dinv, sp.Dinv.data(), (long long)sp.Dinv.size()));
+        // block pattern of the point expansion: block row I references block column c / bs of every entry of its
+        // bs point rows (the rows of a BSR block row share one pattern; a CSR operator viewed block-wise may not)
+        const int bs = sp.bs, nb = Aperm.n_rows / bs;
+        HostCsr Bg;
+        Bg.n_rows = Bg.n_cols = nb;
+        Bg.Ap.assign((size_t)nb + 1, 0);
+        std::vector<int> mark((size_t)nb, -1);
+        for (int I = 0; I < nb; I++) {
+            for (int jj = Aperm.Ap[(size_t)I * bs]; jj < Aperm.Ap[(size_t)(I + 1) * bs]; jj++) {
+                const int J = Aperm.Aj[(size_t)jj] / bs;
+                if (J < nb && mark[(size_t)J] != I) { mark[(size_t)J] = I; Bg.Aj.push_back(J); }
+            }
+            Bg.Ap[(size_t)I + 1] = (int)Bg.Aj.size();
+        }
+        std::vector<int> rows;
+        build_waves(Bg, nullptr, nb, rows, s.ws.ptr);
+        RET(upload(&s.ws.rows, rows.data(), (long long)rows.size()));
+        s.ws.nnz.assign(s.ws.ptr.size() - 1, 0);
+        for (size_t w = 0; w + 1 < s.ws.ptr.size(); w++)
+            for (long long k = s.ws.ptr[w]; k < s.ws.ptr[w + 1]; k++) {
+                const size_t I = (size_t)rows[(size_t)k];
+                s.ws.nnz[w] += Aperm.Ap[(I + 1) * bs] - Aperm.Ap[I * bs];
+            }
     }
     return AMGB_OK;
 }
@@ -1369,6 +1598,7 @@ int amgb_hierarchy::finalize_levels()
         if (!H.has_pr || !use_permute) continue;
         // block smoothers address x in natural block numbering: such levels are never permuted
         if (H.pre.kind == AMGB_SM_BLOCK_JACOBI || H.post.kind == AMGB_SM_BLOCK_JACOBI) continue;
+        if (H.pre.kind == AMGB_SM_BLOCK_GAUSS_SEIDEL || H.post.kind == AMGB_SM_BLOCK_GAUSS_SEIDEL) continue;
         const SmootherSpec *src = nullptr;
         if (H.pre.kind == AMGB_SM_GAUSS_SEIDEL) { src = &H.pre; layout_src[(size_t)l] = 0; }
         else if (H.post.kind == AMGB_SM_GAUSS_SEIDEL) { src = &H.post; layout_src[(size_t)l] = 1; }
@@ -1511,6 +1741,38 @@ static int copy_smoother(const amgb_smoother *in, const HostCsr &A, SmootherSpec
         if (in->Dinv == nullptr) return fail(AMGB_EINVAL, "block_jacobi: Dinv required");
         s.Dinv.assign(in->Dinv, in->Dinv + (size_t)A.n_rows * s.bs);
         return AMGB_OK;
+    case AMGB_SM_BLOCK_GAUSS_SEIDEL:
+        if (s.sweep < 0 || s.sweep > 2)
+            return fail(AMGB_EINVAL, "valid sweep directions: \"forward\", \"backward\", and \"symmetric\"");
+        s.bs = in->blocksize;
+        if (s.bs < 1 || s.bs > 8 || A.n_rows % s.bs)
+            return fail(AMGB_ENOTIMPL, "block_gauss_seidel: blocksize must be 1..8 and divide n");
+        if (in->Dinv == nullptr) return fail(AMGB_EINVAL, "block_gauss_seidel: Dinv required");
+        s.Dinv.assign(in->Dinv, in->Dinv + (size_t)A.n_rows * s.bs);
+        return AMGB_OK;
+    case AMGB_SM_POLYNOMIAL:
+        if (in->coefficients == nullptr || in->n_coefficients < 1)
+            return fail(AMGB_EINVAL, "polynomial: at least one coefficient required");
+        s.coef.assign(in->coefficients, in->coefficients + in->n_coefficients);
+        return AMGB_OK;
+    case AMGB_SM_JACOBI_INDEXED:
+    case AMGB_SM_CF_JACOBI:
+    case AMGB_SM_FC_JACOBI:
+        if (in->n_indices < 0 || in->n_indices2 < 0 || (in->n_indices > 0 && in->indices == nullptr) ||
+            (in->n_indices2 > 0 && in->indices2 == nullptr))
+            return fail(AMGB_EINVAL, "indexed Jacobi: null row list");
+        s.list.assign(in->indices, in->indices + in->n_indices);
+        if (in->kind != AMGB_SM_JACOBI_INDEXED) {
+            s.list2.assign(in->indices2, in->indices2 + in->n_indices2);
+            s.f_iterations = in->f_iterations;
+            s.c_iterations = in->c_iterations;
+            if (s.f_iterations < 0 || s.c_iterations < 0) return fail(AMGB_EINVAL, "CF Jacobi: iterations < 0");
+        }
+        for (int v : s.list)
+            if (v < 0 || v >= A.n_rows) return fail(AMGB_EINVAL, "indexed Jacobi: row index out of range");
+        for (int v : s.list2)
+            if (v < 0 || v >= A.n_rows) return fail(AMGB_EINVAL, "indexed Jacobi: row index out of range");
+        return AMGB_OK;
     }
     return fail(AMGB_ENOTIMPL, "smoother kind outside the hot-path scope");
 }
@@ -1593,7 +1855,8 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
         int tl = nl;
         for (int l = nl - 1; l >= 1; l--) {
             const Level &L = h->levels[(size_t)l];
-            const bool blocky = L.has_pr && (L.pre.kind == AMGB_SM_BLOCK_JACOBI || L.post.kind == AMGB_SM_BLOCK_JACOBI);
+            // only the kinds the cluster interpreter knows (none, Jacobi, Gauss-Seidel) may run in the tail
+            const bool blocky = L.has_pr && (L.pre.kind > AMGB_SM_GAUSS_SEIDEL || L.post.kind > AMGB_SM_GAUSS_SEIDEL);
             if (L.A.nnz > h->tail_nnz_limit || blocky) break;
             tl = l;
         }
@@ -1633,6 +1896,10 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
         RET(h->dalloc(&L.b, n + 2));
         RET(h->dalloc(&L.r, n + 2));
         L.x = L.x_home;
+        if (L.has_pr && (L.pre.kind == AMGB_SM_POLYNOMIAL || L.post.kind == AMGB_SM_POLYNOMIAL)) {
+            RET(h->dalloc(&L.poly[0], n + 2));
+            RET(h->dalloc(&L.poly[1], n + 2));
+        }
     }
     h->n_partials = std::max<long long>(h->partials_len(h->levels[0].A), 1);
     RET(h->dalloc(&h->partials, h->n_partials));
@@ -2397,6 +2664,81 @@ extern "C" int amgb_host_block_jacobi(const int32_t *Ap, int Ap_size, const int3
     std::memcpy(temp, x, sizeof(double) * (size_t)n);           // relaxation.h:1043-1045
     CK(cudaMemcpy(x, dy, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
     return AMGB_OK;
+}
+
+extern "C" int amgb_host_relax(const amgb_matrix *A, const amgb_smoother *sm, double *x, const double *b)
+{
+    if (A == nullptr || sm == nullptr || x == nullptr || b == nullptr) return fail(AMGB_EINVAL, "null argument");
+    RET(validate_matrix(A, "A"));
+    const int n = A->n_rows;
+    if (n == 0) return AMGB_OK;
+    // a two-level hierarchy whose transfer operators are empty: level 0 carries the operator and the smoother
+    // through exactly the upload path of a real hierarchy (wave-major permutation, tiles, row lists)
+    amgb_hierarchy *h = nullptr;
+    RET(amgb_hierarchy_create(0, &h));
+    struct Guard { amgb_hierarchy *h; ~Guard() { amgb_hierarchy_destroy(h); } } guard{h};
+    std::vector<int32_t> p_ptr((size_t)n + 1, 0), one_ptr(2, 0);
+    amgb_matrix P = {n, 1, 1, 1, 0, p_ptr.data(), nullptr, nullptr};
+    amgb_matrix R = {1, n, 1, 1, 0, one_ptr.data(), nullptr, nullptr};
+    amgb_matrix C = {1, 1, 1, 1, 0, one_ptr.data(), nullptr, nullptr};
+    amgb_smoother none = {};
+    none.kind = AMGB_SM_NONE;
+    RET(amgb_hierarchy_add_level(h, A, &P, &R, sm, &none));
+    RET(amgb_hierarchy_add_level(h, &C, nullptr, nullptr, nullptr, nullptr));
+    RET(amgb_hierarchy_set_coarse_pinv(h, 1, nullptr, 1));
+    RET(amgb_hierarchy_finalize(h, nullptr));
+    h->rt.activate();
+    h->launches = 0;
+    RET(load_level0(h, b, x, cudaMemcpyHostToDevice));
+    Level &L0 = h->levels[0];
+    h->cur_level = 0;
+    RET(h->smooth(L0, L0.pre));
+    RET(store_level0(h, x, cudaMemcpyDeviceToHost));
+    CK(cudaStreamSynchronize(h->stream));
+    return AMGB_OK;
+}
+
+extern "C" int amgb_host_jacobi_indexed(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                                        const double *Ax, int Ax_size, double *x, int x_size, const double *b,
+                                        int b_size, const int32_t *indices, int indices_size, const double *omega,
+                                        int omega_size)
+{
+    RET(check_csr_host(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x_size, b_size, 1));
+    const int n = Ap_size - 1;
+    if (x_size != n || omega == nullptr || omega_size < 1) return fail(AMGB_EINVAL, "jacobi_indexed: bad vector sizes");
+    if (indices_size < 0 || (indices_size > 0 && indices == nullptr)) return fail(AMGB_EINVAL, "jacobi_indexed: null row list");
+    if (indices_size == 0 || n == 0) return AMGB_OK;
+    amgb_matrix A = {n, n, 1, 1, Aj_size, Ap, Aj, Ax};
+    amgb_smoother sm = {};
+    sm.kind = AMGB_SM_JACOBI_INDEXED;
+    sm.iterations = 1;
+    sm.omega = omega[0];
+    sm.indices = indices;
+    sm.n_indices = indices_size;
+    return amgb_host_relax(&A, &sm, x, b);
+}
+
+extern "C" int amgb_host_block_gauss_seidel(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
+                                            const double *Ax, int Ax_size, double *x, int x_size, const double *b,
+                                            int b_size, const double *Tx, int Tx_size, int32_t row_start,
+                                            int32_t row_stop, int32_t row_step, int32_t blocksize)
+{
+    if (blocksize < 1 || blocksize > 8) return fail(AMGB_ENOTIMPL, "block_gauss_seidel: blocksize must be 1..8");
+    RET(check_csr_host(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x_size, b_size, blocksize * blocksize));
+    const int nb = Ap_size - 1, n = nb * blocksize;
+    if (x_size != n || Tx == nullptr || (long long)Tx_size != (long long)n * blocksize)
+        return fail(AMGB_EINVAL, "block_gauss_seidel: bad vector sizes");
+    if (nb == 0) return AMGB_OK;
+    amgb_smoother sm = {};
+    sm.kind = AMGB_SM_BLOCK_GAUSS_SEIDEL;
+    sm.iterations = 1;
+    sm.blocksize = blocksize;
+    sm.Dinv = Tx;
+    if (row_start == 0 && row_stop == nb && row_step == 1) sm.sweep = AMGB_SWEEP_FORWARD;
+    else if (row_start == nb - 1 && row_stop == -1 && row_step == -1) sm.sweep = AMGB_SWEEP_BACKWARD;
+    else return fail(AMGB_ENOTIMPL, "block_gauss_seidel: only the full forward / backward block-row ranges");
+    amgb_matrix A = {n, n, blocksize, blocksize, Aj_size, Ap, Aj, Ax};
+    return amgb_host_relax(&A, &sm, x, b);
 }
 
 extern "C" int amgb_host_matvec(const amgb_matrix *A, const double *x, double *y)

@@ -18,7 +18,8 @@ from scipy import sparse
 from .multilevel import MultilevelSolver
 from .relaxation import relaxation
 
-_ARRAY_KW = ("indices", "Dinv")
+_ARRAY_KW = ("indices", "Dinv", "Cpts", "Fpts", "coefficients")
+_INT_KW = ("iterations", "blocksize", "f_iterations", "c_iterations")
 
 
 def _put_matrix(out, key, M):
@@ -43,7 +44,12 @@ def _put_smoother(out, key, sm):
         return None
     func = getattr(sm, "func", None)
     if func is None:
-        raise NotImplementedError(f"cannot serialise closure smoother {sm!r}")
+        from .relaxation.smoothing import polynomial_closure_parameters
+        poly = polynomial_closure_parameters(sm)          # 'richardson' / 'chebyshev' closures
+        if poly is None:
+            raise NotImplementedError(f"cannot serialise closure smoother {sm!r}")
+        out[f"{key}_coefficients"] = np.asarray(poly[0], dtype=np.float64)
+        return {"fn": "polynomial", "name": sm.__name__, "kw": {"iterations": int(poly[1])}, "closure": True}
     kw = {}
     for k, v in sm.keywords.items():
         if k in _ARRAY_KW:
@@ -52,7 +58,7 @@ def _put_smoother(out, key, sm):
             kw[k] = v
         elif np.isscalar(v) or (isinstance(v, np.ndarray) and v.size == 1):
             f = float(np.real(np.asarray(v).reshape(-1)[0]))
-            kw[k] = int(f) if k in ("iterations", "blocksize") else f
+            kw[k] = int(f) if k in _INT_KW else f
         else:
             raise NotImplementedError(f"smoother keyword {k}={v!r}")
     return {"fn": func.__name__, "name": getattr(sm, "__name__", func.__name__), "kw": kw}
@@ -68,6 +74,9 @@ def _get_smoother(z, key, d):
     for k in _ARRAY_KW:
         if f"{key}_{k}" in z:
             kw[k] = z[f"{key}_{k}"]
+    if d.get("closure"):
+        from .relaxation.smoothing import _polynomial_closure
+        return _polynomial_closure(d["name"], kw["coefficients"], kw.get("iterations", 1))
     sm = partial(fn, **kw)
     update_wrapper(sm, getattr(relaxation, d["name"], fn))
     return sm

@@ -16,7 +16,8 @@ from scipy import sparse
 
 from .. import _engine as E
 
-__all__ = ["make_system", "jacobi", "gauss_seidel", "gauss_seidel_indexed", "block_jacobi", "sor"]
+__all__ = ["make_system", "jacobi", "gauss_seidel", "gauss_seidel_indexed", "block_jacobi", "sor",
+           "polynomial", "jacobi_indexed", "cf_jacobi", "fc_jacobi", "block_gauss_seidel"]
 
 
 def make_system(A, x, b, formats=None):
@@ -203,3 +204,138 @@ def block_jacobi(A, x, b, Dinv=None, blocksize=1, iterations=1, omega=1.0):
         E.check(L.amgb_host_block_jacobi(E.i32p(Ap), len(Ap), E.i32p(Aj), len(Aj), E.f64p(Ax), len(Ax),
                                          E.f64p(x), n, E.f64p(b), n, E.f64p(Tx), len(Tx),
                                          E.f64p(temp), n, 0, nb, 1, E.f64p(om), 1, blocksize))
+
+
+# --------------------------------------------------------------------------------------------
+# the smoothers sharing the SpMV / row-sweep core.  All of them go through the generic
+# `amgb_host_relax` entry point (one smoother descriptor applied to host vectors by the cycle's own kernels).
+# --------------------------------------------------------------------------------------------
+def _relax(A, x, b, S, keep):
+    """Apply the engine smoother descriptor S once: HOST A, x (in place), b."""
+    E.require_gpu()
+    M = E.as_matrix(A, keep)
+    b = np.ascontiguousarray(b)
+    E.check(E.lib().amgb_host_relax(M, S, E.f64p(x), E.f64p(b)))
+
+
+def _descriptor():
+    S = E.Smoother()
+    S.kind, S.iterations, S.sweep, S.blocksize, S.omega = E.SM_NONE, 1, 0, 1, 1.0
+    S.indices, S.n_indices, S.Dinv = None, 0, None
+    S.indices2, S.n_indices2, S.f_iterations, S.c_iterations = None, 0, 1, 1
+    S.coefficients, S.n_coefficients, S.reserved_ = None, 0, 0
+    return S
+
+
+def polynomial(A, x, b, coefficients, iterations=1):
+    """x += p(A) (b - A x) with p given by its coefficients in descending order, evaluated by Horner's rule
+    (relaxation.py:585-659); what the 'richardson' and 'chebyshev' smoothers call."""
+    A, x, b = make_system(A, x, b, formats=None)
+    _fp64(A)
+    if A.shape[0] == 0 or iterations < 1:
+        return
+    coef = np.ascontiguousarray(np.real(np.asarray(coefficients)), dtype=np.float64).reshape(-1)
+    if coef.size < 1:
+        raise ValueError("polynomial smoother without coefficients")
+    S = _descriptor()
+    S.kind, S.iterations = E.SM_POLYNOMIAL, int(iterations)
+    S.coefficients, S.n_coefficients = E.f64p(coef), coef.size
+    _relax(A, x, b, S, [coef])
+
+
+def jacobi_indexed(A, x, b, indices, iterations=1, omega=1.0):
+    """Weighted Jacobi on the listed rows only (relaxation.py:1081-1138 -> relaxation.h:382-427): every listed
+    row is relaxed from the iterate as it was when the call started."""
+    A, x, b = make_system(A, x, b, formats=["csr", "bsr"])
+    _fp64(A)
+    indices = np.ascontiguousarray(np.asarray(indices, dtype="intc"), dtype=np.int32)
+    if A.format != "csr":
+        R, C = A.blocksize
+        if R != C:
+            raise ValueError("BSR blocks must be square")
+        if (R, C) != (1, 1):
+            raise NotImplementedError("bsr_jacobi_indexed (block rows) is not on the GPU hot path")
+        A = A.tocsr()
+    n = A.shape[0]
+    if n == 0 or len(indices) == 0:
+        return
+    E.require_gpu()
+    L = E.lib()
+    om = np.array([omega], dtype=np.float64)
+    b = np.ascontiguousarray(b)
+    Ap, Aj, Ax = _csr_args(A)
+    for _ in range(iterations):
+        E.check(L.amgb_host_jacobi_indexed(E.i32p(Ap), len(Ap), E.i32p(Aj), len(Aj), E.f64p(Ax), len(Ax),
+                                           E.f64p(x), n, E.f64p(b), n, E.i32p(indices), len(indices),
+                                           E.f64p(om), 1))
+
+
+def _cf(kind, A, x, b, Cpts, Fpts, iterations, f_iterations, c_iterations, omega):
+    A, x, b = make_system(A, x, b, formats=["csr", "bsr"])
+    _fp64(A)
+    if A.format != "csr":
+        R, C = A.blocksize
+        if R != C:
+            raise ValueError("BSR blocks must be square")
+        if (R, C) != (1, 1):
+            raise NotImplementedError("CF Jacobi on block rows (bsr_jacobi_indexed) is not on the GPU hot path")
+        A = A.tocsr()
+    Cpts = np.ascontiguousarray(np.asarray(Cpts), dtype=np.int32)
+    Fpts = np.ascontiguousarray(np.asarray(Fpts), dtype=np.int32)
+    if A.shape[0] == 0 or iterations < 1:
+        return
+    S = _descriptor()
+    S.kind, S.iterations, S.omega = kind, int(iterations), float(np.real(omega))
+    S.indices, S.n_indices = E.i32p(Cpts), len(Cpts)
+    S.indices2, S.n_indices2 = E.i32p(Fpts), len(Fpts)
+    S.f_iterations, S.c_iterations = int(f_iterations), int(c_iterations)
+    _relax(A, x, b, S, [Cpts, Fpts])
+
+
+def cf_jacobi(A, x, b, Cpts, Fpts, iterations=1, f_iterations=1, c_iterations=1, omega=1.0):
+    """CF Jacobi: per iteration c_iterations Jacobi sweeps over the C-points, then f_iterations over the
+    F-points (relaxation.py:1141-1203)."""
+    _cf(E.SM_CF_JACOBI, A, x, b, Cpts, Fpts, iterations, f_iterations, c_iterations, omega)
+
+
+def fc_jacobi(A, x, b, Cpts, Fpts, iterations=1, f_iterations=1, c_iterations=1, omega=1.0):
+    """FC Jacobi: F-point sweeps first, then C-point sweeps (relaxation.py:1206-1268)."""
+    _cf(E.SM_FC_JACOBI, A, x, b, Cpts, Fpts, iterations, f_iterations, c_iterations, omega)
+
+
+def block_gauss_seidel(A, x, b, iterations=1, sweep="forward", blocksize=1, Dinv=None):
+    """Block Gauss-Seidel, in place on x (relaxation.py:502-582 -> relaxation.h:1242-1298).  The sequential sweep
+    over block rows runs as dependency waves of the block graph, which reproduces it."""
+    A, x, b = make_system(A, x, b, formats=["csr", "bsr"])
+    _fp64(A)
+    A = A.tobsr(blocksize=(blocksize, blocksize))
+    if Dinv is None:
+        from ..util import get_block_diag
+        Dinv = get_block_diag(A, blocksize=blocksize, inv_flag=True)
+    elif Dinv.shape[0] != int(A.shape[0] / blocksize):
+        raise ValueError("Dinv and A have incompatible dimensions")
+    elif (Dinv.shape[1] != blocksize) or (Dinv.shape[2] != blocksize):
+        raise ValueError("Dinv and blocksize are incompatible")
+    nb = int(len(x) / blocksize)
+    if sweep == "forward":
+        rs = (0, nb, 1)
+    elif sweep == "backward":
+        rs = (nb - 1, -1, -1)
+    elif sweep == "symmetric":
+        for _ in range(iterations):
+            block_gauss_seidel(A, x, b, iterations=1, sweep="forward", blocksize=blocksize, Dinv=Dinv)
+            block_gauss_seidel(A, x, b, iterations=1, sweep="backward", blocksize=blocksize, Dinv=Dinv)
+        return
+    else:
+        raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+    if nb <= 0:
+        return
+    E.require_gpu()
+    L = E.lib()
+    n = A.shape[0]
+    b = np.ascontiguousarray(b)
+    Ap, Aj, Ax = _csr_args(A)
+    Tx = np.ascontiguousarray(Dinv, dtype=np.float64).reshape(-1)
+    for _ in range(iterations):
+        E.check(L.amgb_host_block_gauss_seidel(E.i32p(Ap), len(Ap), E.i32p(Aj), len(Aj), E.f64p(Ax), len(Ax),
+                                               E.f64p(x), n, E.f64p(b), n, E.f64p(Tx), len(Tx), *rs, blocksize))

@@ -20,12 +20,13 @@ import numpy as np
 from scipy import sparse
 
 from . import relaxation
+from .chebyshev import chebyshev_polynomial_coefficients
 from ..util import approximate_spectral_radius, get_block_diag, get_diagonal
 from .. import _engine as E
 
 DEFAULT_SWEEP = "forward"
 DEFAULT_NITER = 1
-SYMMETRIC_RELAXATION = ["jacobi", "block_jacobi", None]
+SYMMETRIC_RELAXATION = ["jacobi", "richardson", "block_jacobi", "jacobi_ne", "chebyshev", None]   # smoothing.py:49-50
 
 
 def _unpack_arg(v):
@@ -123,6 +124,127 @@ def setup_gauss_seidel_indexed(lvl, indices=None, iterations=DEFAULT_NITER, swee
     return smoother
 
 
+def _polynomial_closure(name, coefficients, iterations):
+    """The closure shape the reference stores for 'richardson' / 'chebyshev' (smoothing.py:611-618, :627-647):
+    a plain function named after the registry key whose cell variables hold the polynomial coefficients."""
+    coefficients = np.asarray(coefficients, dtype=np.float64)
+
+    def smoother(A, x, b):
+        relaxation.polynomial(A, x, b, coefficients=coefficients, iterations=iterations)
+    smoother.__name__ = name
+    smoother.__qualname__ = name
+    return smoother
+
+
+def setup_richardson(lvl, iterations=DEFAULT_NITER, omega=1.0):
+    """x += omega / rho(A) * (b - A x)  (smoothing.py:611-618)."""
+    omega = omega / approximate_spectral_radius(lvl.A)
+    return _polynomial_closure("richardson", [omega], iterations)
+
+
+def setup_chebyshev(lvl, lower_bound=1.0 / 30.0, upper_bound=1.1, degree=3, iterations=DEFAULT_NITER):
+    """Chebyshev polynomial smoother on [lower_bound, upper_bound] * rho(A)  (smoothing.py:627-647)."""
+    rho = approximate_spectral_radius(lvl.A)
+    a = rho * lower_bound
+    b = rho * upper_bound
+    coefficients = -chebyshev_polynomial_coefficients(a, b, degree)[:-1]      # drop the constant coefficient
+    return _polynomial_closure("chebyshev", coefficients, iterations)
+
+
+def _extract_splitting(lvl):
+    """F- and C-point lists from ``lvl.splitting`` (smoothing.py:55-72)."""
+    try:
+        splitting = lvl.splitting
+    except AttributeError as exc:
+        raise AttributeError("CF splitting is required in hierarchy.") from exc
+    if splitting.dtype != bool:
+        raise ValueError("CF splitting is required to be boolean.")
+    Fpts = np.where(np.logical_not(splitting))[0].astype(dtype=int)
+    Cpts = np.where(splitting)[0].astype(dtype=int)
+    return Fpts, Cpts
+
+
+def _setup_cf(fn, lvl, f_iterations, c_iterations, iterations, omega, withrho):
+    if withrho:
+        omega = omega / rho_D_inv_A(lvl.A)
+    Fpts, Cpts = _extract_splitting(lvl)
+    smoother = partial(fn, Cpts=Cpts, Fpts=Fpts, f_iterations=f_iterations, c_iterations=c_iterations,
+                       iterations=iterations, omega=omega)
+    update_wrapper(smoother, fn)
+    return smoother
+
+
+def setup_cf_jacobi(lvl, f_iterations=DEFAULT_NITER, c_iterations=DEFAULT_NITER, iterations=DEFAULT_NITER,
+                    omega=1.0, withrho=False):
+    """C-point Jacobi sweeps followed by F-point sweeps (smoothing.py:678-691)."""
+    return _setup_cf(relaxation.cf_jacobi, lvl, f_iterations, c_iterations, iterations, omega, withrho)
+
+
+def setup_fc_jacobi(lvl, f_iterations=DEFAULT_NITER, c_iterations=DEFAULT_NITER, iterations=DEFAULT_NITER,
+                    omega=1.0, withrho=False):
+    """F-point Jacobi sweeps followed by C-point sweeps (smoothing.py:694-707) -- AIR's post-smoother."""
+    return _setup_cf(relaxation.fc_jacobi, lvl, f_iterations, c_iterations, iterations, omega, withrho)
+
+
+def _setup_cf_block(fn_block_name, setup_point, lvl, f_iterations, c_iterations, iterations, omega, Dinv,
+                    blocksize, withrho):
+    if blocksize is None and Dinv is None:
+        if sparse.issparse(lvl.A) and lvl.A.format == "csr":
+            blocksize = 1
+        elif sparse.issparse(lvl.A) and lvl.A.format == "bsr":
+            blocksize = lvl.A.blocksize[0]
+    elif blocksize is None:
+        blocksize = Dinv.blocksize[1] if (sparse.issparse(Dinv) and Dinv.format == "bsr") else 1
+    if (lvl.A.shape[0] % blocksize) != 0:
+        raise ValueError("Blocksize does not divide size of matrix.")
+    if len(lvl.splitting) * blocksize != lvl.A.shape[0]:
+        raise ValueError("Blocksize not compatible with CF-splitting and matrix size.")
+    if blocksize != 1:
+        raise NotImplementedError(f"smoother '{fn_block_name}' with blocksize > 1 is not on the GPU hot path "
+                                  "(no CPU fallback)")
+    # blocksize 1: block Jacobi is point Jacobi; the reference forwards only iterations / omega / withrho
+    # (smoothing.py:735-739), the registry name stays the block one
+    smoother = setup_point(lvl, iterations=iterations, omega=omega, withrho=withrho)
+    smoother.__name__ = fn_block_name
+    return smoother
+
+
+def setup_cf_block_jacobi(lvl, f_iterations=DEFAULT_NITER, c_iterations=DEFAULT_NITER, iterations=DEFAULT_NITER,
+                          omega=1.0, Dinv=None, blocksize=None, withrho=False):
+    """smoothing.py:710-751 (blocksize 1 only: the scalar degenerate case)."""
+    return _setup_cf_block("cf_block_jacobi", setup_cf_jacobi, lvl, f_iterations, c_iterations, iterations,
+                           omega, Dinv, blocksize, withrho)
+
+
+def setup_fc_block_jacobi(lvl, f_iterations=DEFAULT_NITER, c_iterations=DEFAULT_NITER, iterations=DEFAULT_NITER,
+                          omega=1.0, Dinv=None, blocksize=None, withrho=False):
+    """smoothing.py:754-791 (blocksize 1 only)."""
+    return _setup_cf_block("fc_block_jacobi", setup_fc_jacobi, lvl, f_iterations, c_iterations, iterations,
+                           omega, Dinv, blocksize, withrho)
+
+
+def setup_block_gauss_seidel(lvl, iterations=DEFAULT_NITER, sweep=DEFAULT_SWEEP, Dinv=None, blocksize=None):
+    """Block Gauss-Seidel, the reference's default SA smoother (smoothing.py:582-608); blocksize 1 is plain
+    Gauss-Seidel under the block name."""
+    if blocksize is None and Dinv is None:
+        if sparse.issparse(lvl.A) and lvl.A.format == "csr":
+            blocksize = 1
+        elif sparse.issparse(lvl.A) and lvl.A.format == "bsr":
+            blocksize = lvl.A.blocksize[0]
+    elif blocksize is None:
+        blocksize = Dinv.shape[1]
+    if blocksize == 1:
+        smoother = setup_gauss_seidel(lvl, iterations=iterations, sweep=sweep)
+        update_wrapper(smoother, relaxation.block_gauss_seidel)
+        return smoother
+    if Dinv is None:
+        Dinv = get_block_diag(lvl.A, blocksize=blocksize, inv_flag=True)
+    smoother = partial(relaxation.block_gauss_seidel, iterations=iterations, Dinv=Dinv, blocksize=blocksize,
+                       sweep=sweep)
+    update_wrapper(smoother, relaxation.block_gauss_seidel)
+    return smoother
+
+
 def setup_none(lvl):
     def none(A, x, b):
         pass
@@ -136,13 +258,19 @@ _REGISTER = {
     "sor": setup_sor,
     "gauss_seidel_indexed": setup_gauss_seidel_indexed,
     "multicolor_gauss_seidel": setup_gauss_seidel_indexed,
+    "richardson": setup_richardson,
+    "chebyshev": setup_chebyshev,
+    "cf_jacobi": setup_cf_jacobi,
+    "fc_jacobi": setup_fc_jacobi,
+    "cf_block_jacobi": setup_cf_block_jacobi,
+    "fc_block_jacobi": setup_fc_block_jacobi,
+    "block_gauss_seidel": setup_block_gauss_seidel,
     "none": setup_none,
 }
 
 # in the reference's registry (smoothing.py:840-878) but outside the accelerated path
-_OUT_OF_SCOPE = ["schwarz", "strength_based_schwarz", "block_gauss_seidel", "richardson", "chebyshev",
-                 "jacobi_ne", "gauss_seidel_ne", "gauss_seidel_nr", "cf_jacobi", "fc_jacobi",
-                 "cf_block_jacobi", "fc_block_jacobi", "gmres", "cg", "cgne", "cgnr"]
+_OUT_OF_SCOPE = ["schwarz", "strength_based_schwarz", "jacobi_ne", "gauss_seidel_ne", "gauss_seidel_nr",
+                 "gmres", "cg", "cgne", "cgnr"]
 
 
 def _setup_call(fn):
@@ -224,13 +352,25 @@ def describe(sm, A, keep):
     S.indices, S.n_indices, S.Dinv = None, 0, None
     if sm is None:
         return S
+    S.indices2, S.n_indices2, S.f_iterations, S.c_iterations = None, 0, 1, 1
+    S.coefficients, S.n_coefficients, S.reserved_ = None, 0, 0
     func = getattr(sm, "func", None)
     if func is None:
         if getattr(sm, "__name__", None) == "none":
             return S
+        poly = polynomial_closure_parameters(sm)
+        if poly is not None:
+            coef = np.ascontiguousarray(poly[0], dtype=np.float64).reshape(-1)
+            if coef.size < 1:
+                raise ValueError("polynomial smoother without coefficients")
+            keep.append(coef)
+            S.kind, S.iterations = E.SM_POLYNOMIAL, int(poly[1])
+            S.coefficients, S.n_coefficients = E.f64p(coef), coef.size
+            return S
         raise NotImplementedError(
             f"smoother {getattr(sm, '__name__', sm)!r} is a closure the GPU engine cannot introspect; "
-            "supported: jacobi, gauss_seidel, gauss_seidel_indexed (multi-colour), block_jacobi, sor, None")
+            "supported: jacobi, gauss_seidel, gauss_seidel_indexed (multi-colour), block_jacobi, sor, richardson, "
+            "chebyshev, cf_jacobi, fc_jacobi, jacobi_indexed, block_gauss_seidel, None")
     name = func.__name__
     kw = dict(sm.keywords)
     S.iterations = int(kw.get("iterations", 1))
@@ -262,6 +402,69 @@ def describe(sm, A, keep):
         keep.append(Dinv)
         S.blocksize = bs
         S.Dinv = E.f64p(Dinv.reshape(-1))
+    elif name == "polynomial":
+        coef = np.ascontiguousarray(np.real(np.asarray(kw["coefficients"])), dtype=np.float64).reshape(-1)
+        if coef.size < 1:
+            raise ValueError("polynomial smoother without coefficients")
+        keep.append(coef)
+        S.kind = E.SM_POLYNOMIAL
+        S.coefficients, S.n_coefficients = E.f64p(coef), coef.size
+    elif name in ("jacobi_indexed", "cf_jacobi", "fc_jacobi"):
+        S.omega = float(np.real(kw.get("omega", 1.0)))
+        if name == "jacobi_indexed":
+            S.kind = E.SM_JACOBI_INDEXED
+            idx = np.ascontiguousarray(np.asarray(kw["indices"]), dtype=np.int32)
+        else:
+            S.kind = E.SM_CF_JACOBI if name == "cf_jacobi" else E.SM_FC_JACOBI
+            idx = np.ascontiguousarray(np.asarray(kw["Cpts"]), dtype=np.int32)
+            idx2 = np.ascontiguousarray(np.asarray(kw["Fpts"]), dtype=np.int32)
+            keep.append(idx2)
+            S.indices2, S.n_indices2 = E.i32p(idx2), len(idx2)
+            S.f_iterations = int(kw.get("f_iterations", 1))
+            S.c_iterations = int(kw.get("c_iterations", 1))
+            if getattr(A, "format", "csr") == "bsr" and A.blocksize != (1, 1):
+                raise NotImplementedError("CF Jacobi on a BSR operator (bsr_jacobi_indexed) is not on the GPU hot path")
+        keep.append(idx)
+        S.indices, S.n_indices = E.i32p(idx), len(idx)
+    elif name == "block_gauss_seidel":
+        S.kind = E.SM_BLOCK_GAUSS_SEIDEL
+        sweep = kw.get("sweep", "forward")
+        if sweep not in E.SWEEPS:
+            raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+        S.sweep = E.SWEEPS[sweep]
+        bs = int(kw.get("blocksize", 1))
+        Dinv = kw.get("Dinv", None)
+        if Dinv is None:
+            Dinv = get_block_diag(A, blocksize=bs, inv_flag=True)
+        Dinv = np.ascontiguousarray(Dinv, dtype=np.float64)
+        if Dinv.shape[0] != A.shape[0] // bs:
+            raise ValueError("Dinv and A have incompatible dimensions")
+        if Dinv.shape[1] != bs or Dinv.shape[2] != bs:
+            raise ValueError("Dinv and blocksize are incompatible")
+        keep.append(Dinv)
+        S.blocksize = bs
+        S.Dinv = E.f64p(Dinv.reshape(-1))
     else:
         raise NotImplementedError(f"smoother '{name}' is not on the GPU hot path (no CPU fallback)")
     return S
+
+
+def polynomial_closure_parameters(sm):
+    """(coefficients, iterations) of a 'richardson' / 'chebyshev' smoother closure, or None.
+
+    The reference keeps these smoothers' parameters in closure cells rather than ``partial`` keywords
+    (smoothing.py:611-618: ``omega``, ``iterations``; :627-647: ``coefficients``, ``iterations``); the cells are
+    read here, which is how a hierarchy built by the reference is adopted without re-running its setup."""
+    name = getattr(sm, "__name__", None)
+    code = getattr(sm, "__code__", None)
+    cells = getattr(sm, "__closure__", None)
+    if name not in ("richardson", "chebyshev") or code is None or cells is None:
+        return None
+    cv = {k: c.cell_contents for k, c in zip(code.co_freevars, cells)}
+    if "coefficients" in cv:
+        coef = cv["coefficients"]
+    elif "omega" in cv:
+        coef = [cv["omega"]]
+    else:
+        return None
+    return np.real(np.asarray(coef, dtype=np.float64)), int(cv.get("iterations", 1))

@@ -266,16 +266,31 @@ inline bool run_cluster(dim3 grid, dim3 block, size_t smem, unsigned first_block
     blockDim = block;
     size_t remaining = fibers.size();
     g.fibers_run += (long long)remaining;
+    // warp-granular round-robin: the lanes of one warp are cycled until none of them can move (all wait on a
+    // block / cluster barrier or an mbarrier, or are done), so a warp-level synchronisation costs 32 context
+    // switches, not one pass over every thread of the cluster
+    const size_t nfib = fibers.size();
     while (remaining > 0) {
         const unsigned long long before = g.progress;
         remaining = 0;
-        for (Fiber &f : fibers) {
-            if (f.done) continue;
-            g.cur = &f;
-            threadIdx = f.tid;
-            blockIdx = f.blk->bid;
-            emu_switch(&g.sched_sp, f.sp);
-            if (!f.done) remaining++;
+        for (size_t w0 = 0; w0 < nfib; w0 += 32) {
+            const size_t w1 = std::min(nfib, w0 + 32);      // warps: blocks are multiples of 32 threads (checked in execute)
+            size_t left;
+            unsigned long long p;
+            do {
+                p = g.progress;
+                left = 0;
+                for (size_t i = w0; i < w1; i++) {
+                    Fiber &f = fibers[i];
+                    if (f.done) continue;
+                    g.cur = &f;
+                    threadIdx = f.tid;
+                    blockIdx = f.blk->bid;
+                    emu_switch(&g.sched_sp, f.sp);
+                    if (!f.done) left++;
+                }
+            } while (left > 0 && g.progress != p);
+            remaining += left;
         }
         if (remaining > 0 && g.progress == before) {
             fprintf(stderr, "[cuda-emu] deadlock: %zu threads wait on a barrier nobody will release "
@@ -303,6 +318,7 @@ inline cudaError_t execute(dim3 grid, dim3 block, size_t smem, int cluster, Kern
     if (nblocks == 0 || block.x * block.y * block.z == 0 || block.x * block.y * block.z > 1024) return g.last_error = cudaErrorInvalidValue;
     if (cluster < 1 || nblocks % (unsigned)cluster) return g.last_error = cudaErrorInvalidValue;
     if (smem > 227 * 1024) return g.last_error = cudaErrorInvalidValue;
+    if (cluster > 1 && (block.x * block.y * block.z) % 32u) return g.last_error = cudaErrorInvalidValue;
     KernelCall *outer = g.call;
     g.call = call;
     g.launches++;

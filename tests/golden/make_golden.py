@@ -167,5 +167,41 @@ def main():
     emit("cfg6_rs_gsfwd_none_poisson3d", ml)
 
 
+def main_widening():
+    """SURVEY.md 8(f)-2 smoothers: polynomial (chebyshev / richardson), CF / FC Jacobi, AIR's hierarchy
+    (R != P^T, no pre-smoother, fc_jacobi post-smoother) and block Gauss-Seidel (the SA default)."""
+    from pyamg.gallery import advection_2d
+
+    # cfg7: SA + Chebyshev (degree 3) pre, two Richardson sweeps post -- closures, not partials
+    np.random.seed(SEED)
+    A = poisson((36, 36), format="csr")
+    ml = pyamg.smoothed_aggregation_solver(A, presmoother=("chebyshev", {"degree": 3, "iterations": 1}),
+                                           postsmoother=("richardson", {"iterations": 2}))
+    emit("cfg7_sa_cheby_richardson_poisson2d", ml)
+
+    # cfg8: RS + CF Jacobi pre / FC Jacobi post (two F sweeps), damped
+    np.random.seed(SEED)
+    A = poisson((11, 11, 11), format="csr")
+    ml = pyamg.ruge_stuben_solver(A, presmoother=("cf_jacobi", {"omega": 0.8, "f_iterations": 2}),
+                                  postsmoother=("fc_jacobi", {"omega": 0.8, "c_iterations": 2, "iterations": 2}))
+    emit("cfg8_rs_cfjacobi_poisson3d", ml)
+
+    # cfg9: AIR on 2-D upwind advection (nonsymmetric; R = approximate ideal restriction != P^T)
+    np.random.seed(SEED)
+    A, _rhs = advection_2d((30, 30), theta=np.pi / 5.0)
+    ml = pyamg.air_solver(A.tocsr())
+    emit("cfg9_air_fcjacobi_advection2d", ml, cg_anyway=False)
+
+    # cfg10: linear elasticity with the reference's DEFAULT SA smoothers (symmetric block Gauss-Seidel)
+    np.random.seed(SEED)
+    A, B = linear_elasticity((12, 12))
+    ml = pyamg.smoothed_aggregation_solver(A, B=B)
+    emit("cfg10_sa_bgs_elasticity", ml)
+
+
 if __name__ == "__main__":
-    main()
+    if "--widening" in sys.argv:
+        main_widening()
+    else:
+        main()
+        main_widening()

@@ -305,6 +305,8 @@ def test_gpu_resident_pcg_matches_reference_golden(name, load_golden):
     ml.solve(accel='cg'): same iteration count, info flag, residual history and iterate."""
     import warnings
     ml, ex = load_golden(name)
+    if "x_ref_cg" not in ex:
+        pytest.skip("no CG golden for this hierarchy (nonsymmetric operator)")
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")          # non-symmetric smoother pairs warn, exactly like the reference
         res = []

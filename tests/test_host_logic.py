@@ -11,7 +11,7 @@ import scipy.sparse as sp
 import pyamg_b200
 from pyamg_b200 import _engine as E
 from pyamg_b200.relaxation import smoothing, relaxation
-from conftest import GOLDEN, ROOT
+from conftest import GOLDEN, GOLDEN_ALL, ROOT
 from kats import poisson1d
 
 
@@ -85,7 +85,9 @@ def test_unsupported_smoothers_fail_loudly():
     with pytest.raises(NotImplementedError):
         smoothing.describe(richardson, poisson1d(3), [])
     with pytest.raises(NotImplementedError):
-        smoothing._setup_call("chebyshev")
+        smoothing._setup_call("schwarz")
+    with pytest.raises(NotImplementedError):
+        smoothing._setup_call("cgnr")
     with pytest.raises(ValueError):
         smoothing._setup_call("no_such_smoother")
     with pytest.raises(NotImplementedError):
@@ -127,7 +129,7 @@ def test_change_smoothers_grammar_and_symmetry_flag():
     assert ml.levels[0].presmoother.__name__ == "block_jacobi"
 
 
-@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("name", GOLDEN_ALL)
 def test_hierarchy_io_roundtrip_and_reports(name, load_golden, tmp_path):
     from pyamg_b200.hierarchy_io import save_hierarchy, load_hierarchy
     ml, ex = load_golden(name)
@@ -276,3 +278,43 @@ def test_from_pyamg_adopts_a_reference_style_solver_object(load_golden):
     # tuple form ('pinv', {...}) as the reference's coarse_grid_solver accepts it (multilevel.py:710-715)
     cs = pyamg_b200.coarse_grid_solver(("pinv", {"atol": 1e-12}))
     assert cs.name() == "('pinv', {'atol': 1e-12})"
+
+
+def test_widened_smoother_descriptors_are_parsed(load_golden):
+    """Closures of the reference's richardson / chebyshev (parameters in cell variables), cf/fc Jacobi partials and
+    block Gauss-Seidel partials -> engine descriptors."""
+    ml, _ = load_golden("cfg7_sa_cheby_richardson_poisson2d")
+    keep = []
+    S = smoothing.describe(ml.levels[0].presmoother, ml.levels[0].A, keep)
+    assert S.kind == E.SM_POLYNOMIAL and S.n_coefficients == 3 and S.iterations == 1
+    S = smoothing.describe(ml.levels[0].postsmoother, ml.levels[0].A, keep)
+    assert S.kind == E.SM_POLYNOMIAL and S.n_coefficients == 1 and S.iterations == 2
+    assert ml.levels[0].presmoother.__name__ == "chebyshev" and ml.levels[0].postsmoother.__name__ == "richardson"
+    ml, _ = load_golden("cfg8_rs_cfjacobi_poisson3d")
+    lvl = ml.levels[0]
+    S = smoothing.describe(lvl.presmoother, lvl.A, keep)
+    assert S.kind == E.SM_CF_JACOBI and S.f_iterations == 2 and S.c_iterations == 1 and S.omega == pytest.approx(0.8)
+    assert S.n_indices + S.n_indices2 == lvl.A.shape[0]
+    S = smoothing.describe(lvl.postsmoother, lvl.A, keep)
+    assert S.kind == E.SM_FC_JACOBI and S.c_iterations == 2 and S.iterations == 2
+    ml, _ = load_golden("cfg9_air_fcjacobi_advection2d")
+    assert smoothing.describe(ml.levels[0].presmoother, ml.levels[0].A, keep).kind == E.SM_NONE
+    assert smoothing.describe(ml.levels[0].postsmoother, ml.levels[0].A, keep).f_iterations == 2
+    ml, _ = load_golden("cfg10_sa_bgs_elasticity")
+    S = smoothing.describe(ml.levels[0].presmoother, ml.levels[0].A, keep)
+    assert S.kind == E.SM_BLOCK_GAUSS_SEIDEL and S.blocksize == 2 and S.sweep == E.SWEEPS["symmetric"]
+    assert smoothing.describe(ml.levels[1].presmoother, ml.levels[1].A, keep).blocksize == 3
+    # still outside the accelerated path: loud, never a CPU fallback
+    with pytest.raises(NotImplementedError):
+        smoothing._setup_call("schwarz")
+    with pytest.raises(NotImplementedError):
+        smoothing._setup_call("gauss_seidel_ne")
+
+
+def test_chebyshev_coefficients_reference_doctest():
+    """pyamg/relaxation/chebyshev.py:29-31."""
+    from pyamg_b200.relaxation.chebyshev import chebyshev_polynomial_coefficients
+    c = chebyshev_polynomial_coefficients(1.0, 2.0, 3)
+    assert np.allclose(c, [-0.32323232, 1.45454545, -2.12121212, 1.0], atol=5e-9)
+    with pytest.raises(ValueError):
+        chebyshev_polynomial_coefficients(2.0, 1.0, 3)

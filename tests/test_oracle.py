@@ -11,7 +11,7 @@ import pytest
 import scipy.sparse as sp
 
 import oracle
-from conftest import GOLDEN, relerr
+from conftest import GOLDEN_ALL as GOLDEN, relerr
 
 TIGHT = 1e-14   # oracle vs reference: same operations, same order
 
@@ -171,6 +171,8 @@ def test_oracle_pcg_matches_reference(name, load_golden):
     """ml.solve(accel='cg') = pyamg.krylov.cg preconditioned by one cycle (multilevel.py:479-508,
     krylov/_cg.py:97-196): V-cycle from x0 = 0 with tol 1e-10, and W-cycle from x0 with tol 1e-3."""
     ml, ex = load_golden(name)
+    if "x_ref_cg" not in ex:
+        pytest.skip("no CG golden for this hierarchy (nonsymmetric operator)")
     cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.P)
     res = []
     x, info = cyc.solve(ex["b"], tol=1e-10, maxiter=10, accel="cg", residuals=res, return_info=True)

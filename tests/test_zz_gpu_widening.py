@@ -1,0 +1,154 @@
+"""SURVEY.md 8(f)-2 widening: polynomial (chebyshev / richardson), indexed / CF / FC Jacobi, AIR hierarchies and
+block Gauss-Seidel on the engine, against the real reference's goldens (cfg7-10) and the oracle.
+
+This file sorts LAST on purpose: the kernels below were written after round 1's GPU budget was spent and have so
+far only run on tests/emu (the engine's kernel sources on host fibers: `AMGB_TEST_EMU=1 pytest -m gpu`); under
+`pytest -x` a failure here cannot hide the results of the B200-validated suites.
+
+Tolerance as everywhere: ||x_gpu - x_ref|| / ||x_ref|| < 1e-12 in fp64 (1e-11 for the Krylov-accelerated runs).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+import pyamg_b200
+from pyamg_b200.relaxation import relaxation as gpu_relax
+from pyamg_b200.relaxation import smoothing
+from conftest import GOLDEN_WIDENING, relerr
+import test_gpu_parity as T
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+# ------------------------------------------------------------------ the parity suite of the BASELINE goldens, re-run
+@pytest.mark.parametrize("name", GOLDEN_WIDENING)
+def test_vcycle_matches_reference_golden(name, load_golden):
+    T.test_vcycle_matches_reference_golden(name, load_golden)
+
+
+@pytest.mark.parametrize("name", GOLDEN_WIDENING)
+def test_w_and_f_cycles_match_reference_golden(name, load_golden):
+    T.test_w_and_f_cycles_match_reference_golden(name, load_golden)
+
+
+@pytest.mark.parametrize("name", GOLDEN_WIDENING)
+def test_tolerance_stop_and_x0_match_reference_golden(name, load_golden):
+    T.test_tolerance_stop_and_x0_match_reference_golden(name, load_golden)
+
+
+@pytest.mark.parametrize("name", GOLDEN_WIDENING)
+def test_vcycle_matches_oracle_on_fresh_rhs(name, load_golden):
+    T.test_vcycle_matches_oracle_on_fresh_rhs(name, load_golden)
+
+
+@pytest.mark.parametrize("env", [{"AMGB_NO_TILES": "1"}, {"AMGB_NO_PERMUTE": "1"}, {"AMGB_NO_GRAPH": "1"},
+                                 {"AMGB_TILE_MIN_NNZ": "0"}, {"AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_G": "4"},
+                                 {"AMGB_TAIL_NNZ": "600000"}, {"AMGB_NO_PDL": "1"}])
+@pytest.mark.parametrize("name", GOLDEN_WIDENING)
+def test_every_kernel_path_matches_reference_golden(name, env, monkeypatch):
+    T.test_every_kernel_path_matches_reference_golden(name, env, monkeypatch)
+
+
+@pytest.mark.parametrize("name", GOLDEN_WIDENING)
+def test_relaxation_kernels_and_matvecs_match_reference_golden(name, load_golden):
+    T.test_relaxation_kernels_match_reference_golden(name, load_golden)
+    T.test_matvecs_match_scipy_golden(name, load_golden)
+
+
+@pytest.mark.parametrize("name", GOLDEN_WIDENING)
+def test_gpu_resident_pcg_matches_reference_golden(name, load_golden):
+    T.test_gpu_resident_pcg_matches_reference_golden(name, load_golden)
+
+
+# ------------------------------------------------------------------ the smoother routines themselves vs the oracle
+def _system(n=23, seed=5, bs=1):
+    rng = np.random.default_rng(seed)
+    A = sp.random(n * bs, n * bs, density=0.2, random_state=np.random.RandomState(seed), format="csr")
+    A = (A + A.T + sp.eye(n * bs) * (4.0 + n * bs * 0.2)).tocsr()
+    A.sort_indices()
+    return A, rng.standard_normal(n * bs), rng.standard_normal(n * bs)
+
+
+def test_polynomial_matches_oracle():
+    A, x0, b = _system()
+    for coef, its in (([0.3], 1), ([0.01, -0.2, 0.7], 2), ([1e-3, 2e-2, -0.1, 0.4], 1)):
+        xg, xo = x0.copy(), x0.copy()
+        gpu_relax.polynomial(A, xg, b, coef, iterations=its)
+        oracle.polynomial(A, xo, b, coef, iterations=its)
+        assert relerr(xg, xo) < TOL
+    xg, xo = np.zeros_like(b), np.zeros_like(b)                      # the x = 0 shortcut of the reference (:646-649)
+    gpu_relax.polynomial(A, xg, b, [0.05, 0.5])
+    oracle.polynomial(A, xo, b, [0.05, 0.5])
+    assert relerr(xg, xo) < TOL
+
+
+def test_jacobi_indexed_and_cf_fc_jacobi_match_oracle():
+    A, x0, b = _system(n=31, seed=8)
+    n = A.shape[0]
+    rng = np.random.default_rng(3)
+    split = rng.random(n) < 0.4
+    C, F = np.where(split)[0], np.where(~split)[0]
+    for idx in (np.arange(n), C, F[::-1].copy(), np.array([2, 0]), np.array([5, 5, 7])):
+        xg, xo = x0.copy(), x0.copy()
+        gpu_relax.jacobi_indexed(A, xg, b, idx, iterations=2, omega=0.7)
+        oracle.jacobi_indexed(A, xo, b, idx, iterations=2, omega=0.7)
+        assert relerr(xg, xo) < TOL
+    for fn_g, fn_o in ((gpu_relax.cf_jacobi, oracle.cf_jacobi), (gpu_relax.fc_jacobi, oracle.fc_jacobi)):
+        for kw in ({}, {"iterations": 2, "f_iterations": 2, "c_iterations": 1, "omega": 0.6},
+                   {"f_iterations": 0, "c_iterations": 3, "omega": 1.1}):
+            xg, xo = x0.copy(), x0.copy()
+            fn_g(A, xg, b, C, F, **kw)
+            fn_o(A, xo, b, C, F, **kw)
+            assert relerr(xg, xo) < TOL
+    # the reference's doctest system (relaxation.py:1110-1118): rows outside the list are untouched
+    A4 = sp.csr_array(np.array([[4.0, -1, 0, 0], [-1, 4, -1, 0], [0, -1, 4, -1], [0, 0, -1, 4]]))
+    x, b4 = np.zeros(4), np.array([0.0, 1.0, 2.0, 3.0])
+    gpu_relax.jacobi_indexed(A4, x, b4, [2, 3])
+    assert np.array_equal(x[:2], [0.0, 0.0]) and relerr(x[2:], [0.5, 0.75]) < TOL
+
+
+@pytest.mark.parametrize("bs", [1, 2, 3, 4])
+def test_block_gauss_seidel_matches_oracle_and_compiled_reference(bs):
+    from pyamg_b200.util import get_block_diag
+    A, x0, b = _system(n=17, seed=20 + bs, bs=bs)
+    Ab = A.tobsr(blocksize=(bs, bs))
+    Dinv = get_block_diag(Ab, blocksize=bs, inv_flag=True)
+    for sweep, its in (("forward", 1), ("backward", 2), ("symmetric", 2)):
+        xg, xo = x0.copy(), x0.copy()
+        gpu_relax.block_gauss_seidel(Ab, xg, b, iterations=its, sweep=sweep, blocksize=bs, Dinv=Dinv)
+        oracle.block_gauss_seidel(Ab, xo, b, iterations=its, sweep=sweep, blocksize=bs, Dinv=Dinv,
+                                  kernels="ref" if oracle.have_ref() else "oracle")
+        assert relerr(xg, xo) < TOL
+    with pytest.raises(ValueError):
+        gpu_relax.block_gauss_seidel(Ab, x0.copy(), b, sweep="diagonal", blocksize=bs, Dinv=Dinv)
+
+
+def test_smoother_factory_builds_what_the_engine_runs():
+    """change_smoothers with the widened registry on hierarchies set up here (no reference needed): chebyshev +
+    richardson on SA, cf/fc Jacobi on RS (needs lvl.splitting), block Gauss-Seidel default on elasticity."""
+    from pyamg_b200.aggregation import smoothed_aggregation_solver
+    from pyamg_b200.classical import ruge_stuben_solver
+    from pyamg_b200.gallery import poisson, linear_elasticity
+    cases = []
+    np.random.seed(7)
+    cases.append(smoothed_aggregation_solver(poisson((30, 30)), presmoother=("chebyshev", {"degree": 4}),
+                                             postsmoother=("richardson", {"omega": 0.9, "iterations": 2})))
+    cases.append(ruge_stuben_solver(poisson((10, 10, 10)), presmoother=("cf_jacobi", {"omega": 0.7}),
+                                    postsmoother=("fc_jacobi", {"omega": 0.7, "f_iterations": 2})))
+    A, B = linear_elasticity((10, 10))
+    cases.append(smoothed_aggregation_solver(A, B=B, presmoother=("block_gauss_seidel", {"sweep": "symmetric"}),
+                                             postsmoother=("block_gauss_seidel", {"sweep": "symmetric"})))
+    for ml in cases:
+        n = ml.levels[0].A.shape[0]
+        b = np.random.default_rng(n).random(n)
+        cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A))
+        res = []
+        x = ml.solve(b, tol=0, maxiter=3, residuals=res)
+        assert relerr(x, cyc.solve(b, tol=0, maxiter=3)) < TOL
+        assert res[-1] < res[0]
+        assert relerr(ml.solve(b, tol=0, maxiter=2, cycle="W"), cyc.solve(b, tol=0, maxiter=2, cycle="W")) < TOL
+    assert cases[0].levels[0].presmoother.__name__ == "chebyshev"
+    assert cases[0].symmetric_smoothing is False and cases[1].symmetric_smoothing is False
+    assert cases[2].symmetric_smoothing is True
