@@ -355,15 +355,15 @@ class MultilevelSolver:
         A = self.levels[0].A
         cycle = str(cycle).upper()
 
-        if cycle == "AMLI" and os.environ.get("AMGB_EXPERIMENTAL") != "1":
-            # engine.cu descend_amli (multilevel.py:631-657) is written and its restatement in oracle/ is pinned
-            # bit-exactly against the reference, but it has not run on a B200 yet: opt-in until then
-            raise NotImplementedError("AMLI cycles: GPU path not validated yet (opt-in with AMGB_EXPERIMENTAL=1; "
-                                      "SURVEY.md 8(f)-2)")
         if cycle not in E.CYCLES:
             raise TypeError(f"Unrecognized cycle type ({cycle})")      # :658
+        # AMLI cycles require a hermitian matrix (multilevel.py:472-476)
+        if cycle == "AMLI" and hasattr(A, "symmetry") and A.symmetry != "hermitian":
+            raise ValueError("AMLI cycles require symmetry to be hermitian")
 
         if accel is not None:
+            if accel != "fgmres" and cycle == "AMLI":                  # multilevel.py:487-490
+                raise ValueError("AMLI cycles require acceleration (accel) to be fgmres, or no acceleration")
             # Check for symmetric smoothing scheme when using CG (multilevel.py:481-485)
             if (accel == "cg") and (not self.symmetric_smoothing):
                 warn("Incompatible non-symmetric multigrid preconditioner "

@@ -70,3 +70,30 @@ def relerr(a, b):
     b = np.asarray(b, dtype=float).ravel()
     nb = np.linalg.norm(b)
     return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
+
+
+def summation_order_sensitivity(ml, b, **solve_kw):
+    """How far the ORACLE's own result moves when every SpMV sums its row in the opposite order (a pure
+    rounding-level perturbation).  The engine's only arithmetic difference to the reference is the summation
+    order inside a row, so for ill-conditioned recurrences (AMLI's A-orthogonalised step sizes on nearly
+    collinear corrections) this is the honest yardstick; for V/W/F cycles it is ~1e-16."""
+    import numpy as np
+    import scipy.sparse as sp
+    import oracle
+    cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.P)
+    x = cyc.solve(b, **solve_kw)
+    orig = oracle.matvec
+
+    def reversed_rows(A, v, kernels="oracle"):
+        C = A.tocsr()
+        ip = C.indptr
+        idx = (np.concatenate([np.arange(ip[i + 1] - 1, ip[i] - 1, -1) for i in range(C.shape[0])])
+               if C.nnz else np.zeros(0, dtype=int))
+        return orig(sp.csr_array((C.data[idx], C.indices[idx], ip), shape=C.shape), v, kernels)
+
+    oracle.matvec = reversed_rows
+    try:
+        x2 = cyc.solve(b, **solve_kw)
+    finally:
+        oracle.matvec = orig
+    return relerr(x2, x)

@@ -7,7 +7,6 @@ before enabling any of them by default:
 
   AMGB_RESIDENT=1        DSMEM-resident Gauss-Seidel smoother applications (csrc/resident_kernel.cuh);
                          AMGB_RESIDENT_MAX_ROWS (default 65536) bounds the levels it takes
-  cycle='AMLI'           engine.cu descend_amli: device-scalar step sizes, graph-capturable (needs AMGB_EXPERIMENTAL=1)
   AMGB_TILE_FLAT=1       flat-gather tile kernel (csrc/tile_flat_kernel.cuh): one gather round per tile at full
                          warp width, products reduced per row out of shared memory
   AMGB_TILE_PDL=1        programmatic dependent launch of the TMA tile kernel: the first operator tile is
@@ -110,21 +109,3 @@ def test_flat_tile_kernel_on_a_mid_size_hierarchy_and_host_abi(monkeypatch):
     b = np.random.default_rng(14).random(ml.levels[0].A.shape[0])
     cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A))
     assert relerr(ml.solve(b, tol=0, maxiter=3, cycle="W"), cyc.solve(b, tol=0, maxiter=3, cycle="W")) < 1e-12
-
-
-@pytest.mark.parametrize("env", [{}, {"AMGB_NO_GRAPH": "1"}])
-@pytest.mark.parametrize("name", GOLDEN)
-def test_amli_cycle_matches_reference_golden(name, env, monkeypatch):
-    """cycle='AMLI' (multilevel.py:631-657): goldens from the real reference; the oracle restatement is
-    bit-identical to them on the CPU (tests/test_oracle.py)."""
-    from pyamg_b200.hierarchy_io import load_hierarchy
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    ml, ex = load_hierarchy(golden_path(name))
-    res = []
-    for _ in range(2):          # second call replays the captured graph
-        x = ml.solve(ex["b"], tol=0, maxiter=3, cycle="AMLI", residuals=res)
-        assert relerr(x, ex["x_ref_AMLI"]) < 1e-11
-        assert np.allclose(res, ex["residuals_AMLI"], rtol=1e-8)
-    # V-cycles afterwards are unaffected by the AMLI buffers / graph
-    assert relerr(ml.solve(ex["b"], tol=0, maxiter=len(ex["residuals"]) - 1), ex["x_ref"]) < 1e-12
