@@ -134,6 +134,7 @@ int amgb_solve(amgb_hierarchy *h, const double *b_host, double *x_host, double t
 /* amgb_solve with flags: AMGB_FLAG_X0_ZERO = the initial guess is zero, x_host is output only (saves the
  * host->device copy of x0; what aspreconditioner() and solve(x0=None) need). */
 #define AMGB_FLAG_X0_ZERO 1
+#define AMGB_FLAG_FLEXIBLE 2   /* amgb_solve_gmres: flexible GMRES (pyamg.krylov.fgmres) instead of pyamg.krylov.gmres */
 int amgb_solve_ex(amgb_hierarchy *h, const double *b_host, double *x_host, double tol, int32_t maxiter,
                   int32_t cycle, int32_t cycles_per_level, int32_t flags, double *residuals,
                   int32_t *n_residuals, int32_t *info);
@@ -144,6 +145,18 @@ int amgb_solve_ex(amgb_hierarchy *h, const double *b_host, double *x_host, doubl
  * k = maxiter reached, -1 = indefinite matrix / preconditioner detected (the reference's warning). */
 int amgb_solve_cg(amgb_hierarchy *h, const double *b_host, double *x_host, double tol, int32_t maxiter,
                   int32_t cycle, int32_t flags, double *residuals, int32_t *n_residuals, int32_t *info);
+
+/* MultilevelSolver.solve(accel='gmres' | 'fgmres') with every long vector resident in HBM: pyamg's Householder
+ * GMRES (pyamg/krylov/_gmres_householder.py:21-360 -- what pyamg.krylov.gmres resolves to; left-preconditioned,
+ * stops on the preconditioned residual against ||M b||) or, with AMGB_FLAG_FLEXIBLE, its flexible GMRES
+ * (pyamg/krylov/_fgmres.py:17-345; right-preconditioned), M = one multigrid cycle from x0 = 0.
+ * restart = 0: no restarts, at most `maxiter` inner iterations (maxiter <= 0: min(n, 40)); restart > 0: `maxiter`
+ * outer iterations of `restart` inner ones (:129-149).  residuals: caller-sized (max_residuals slots),
+ * *n_residuals = the number the method produced; *info: 0 converged, -1 stagnated (:339-346), else the number
+ * of inner iterations performed.  Needs n >= 2 (n == 1 is a closed form, :152-154). */
+int amgb_solve_gmres(amgb_hierarchy *h, const double *b_host, double *x_host, double tol, int32_t restart,
+                     int32_t maxiter, int32_t cycle, int32_t flags, double *residuals, int32_t max_residuals,
+                     int32_t *n_residuals, int32_t *info);
 
 /* The same on DEVICE vectors (no host copies): x_dev in/out, b_dev in. Runs exactly `ncycles`
  * cycles (tol = 0 semantics); if norms2_dev != NULL it receives ncycles+1 squared residual norms. */

@@ -20,6 +20,7 @@ SM_POLYNOMIAL, SM_JACOBI_INDEXED, SM_CF_JACOBI, SM_FC_JACOBI, SM_BLOCK_GAUSS_SEI
 SWEEPS = {"forward": 0, "backward": 1, "symmetric": 2}
 CYCLES = {"V": 0, "W": 1, "F": 2, "AMLI": 3}
 FLAG_X0_ZERO = 1
+FLAG_FLEXIBLE = 2
 
 
 class Matrix(ctypes.Structure):
@@ -51,6 +52,7 @@ SYMBOLS = [
     "amgb_last_error", "amgb_version", "amgb_device_count",
     "amgb_hierarchy_create", "amgb_hierarchy_destroy", "amgb_hierarchy_add_level",
     "amgb_hierarchy_set_coarse_pinv", "amgb_hierarchy_finalize", "amgb_solve", "amgb_solve_ex", "amgb_solve_cg",
+    "amgb_solve_gmres",
     "amgb_solve_device", "amgb_hierarchy_num_levels", "amgb_hierarchy_device_bytes",
     "amgb_hierarchy_last_launches", "amgb_profile_cycle", "amgb_host_alloc", "amgb_host_free",
     "amgb_operator_create", "amgb_operator_destroy", "amgb_operator_apply",
@@ -95,6 +97,7 @@ def _bind(L):
     L.amgb_solve.argtypes = [vp, vp, vp, f64, i32, i32, i32, c_f64p, c_i32p, c_i32p]
     L.amgb_solve_ex.argtypes = [vp, vp, vp, f64, i32, i32, i32, i32, c_f64p, c_i32p, c_i32p]
     L.amgb_solve_cg.argtypes = [vp, vp, vp, f64, i32, i32, i32, c_f64p, c_i32p, c_i32p]
+    L.amgb_solve_gmres.argtypes = [vp, vp, vp, f64, i32, i32, i32, i32, c_f64p, i32, c_i32p, c_i32p]
     L.amgb_solve_device.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     L.amgb_hierarchy_num_levels.argtypes = [vp]
     L.amgb_hierarchy_device_bytes.argtypes = [vp]

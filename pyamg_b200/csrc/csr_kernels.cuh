@@ -261,6 +261,82 @@ __global__ void axpy_ratio_kernel(double *__restrict__ y, const double *__restri
     for (; i < n; i += stride) y[i] += a * x[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Householder GMRES / flexible GMRES vector kernels (amgb_solve_gmres; pyamg/krylov/_gmres_householder.py,
+// _fgmres.py).  Vectors are in the ORIGINAL numbering: the reflectors single out leading entries.
+// ---------------------------------------------------------------------------------------------
+// v = (I - 2 w w^T) e_k = (-2 w_k) w + e_k                       (_gmres_householder.py:214-215)
+__global__ void hh_unit_reflect_kernel(double *__restrict__ v, const double *__restrict__ w, long long k, long long n)
+{
+    const double f = -2.0 * w[k];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        double t = f * w[i];
+        if (i == k) t = t + 1.0;
+        v[i] = t;
+    }
+}
+// w = [0 ... 0, v_k1 + alpha, v_{k1+1}, ..., v_{n-1}]               (:242-246; k1 = 0: :189-191).  w may alias v.
+__global__ void hh_make_w_kernel(double *w, const double *v, long long k1, double alpha, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        double t = (i < k1) ? 0.0 : v[i];
+        if (i == k1) t += alpha;
+        w[i] = t;
+    }
+}
+__global__ void div_kernel(double *__restrict__ y, double d, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) y[i] = y[i] / d;
+}
+__global__ void add_at_kernel(double *x, long long i, double v) { x[i] += v; }
+// partials[b] = sum of x_i^2 over i >= start of block b's grid-stride share   (norm of v[inner+1:], :239-240)
+__global__ void __launch_bounds__(256) sumsq_from_partials_kernel(const double *__restrict__ x, long long start,
+                                                                  long long n, double *__restrict__ partials)
+{
+    double t = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        if (i >= start) t += x[i] * x[i];
+    t = block_sum<256>(t);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+// stagnation test (:342-347): partials[b] = max |u_i / x_i| over x_i != 0 (-1 if the share has none)
+__global__ void __launch_bounds__(256) maxratio_partials_kernel(const double *__restrict__ u, const double *__restrict__ x,
+                                                                long long n, double *__restrict__ partials)
+{
+    __shared__ double s_max[8];
+    double t = -1.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        if (x[i] != 0.0) t = fmax(t, fabs(u[i] / x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) t = fmax(t, s_max[i]);
+        partials[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(1024) reduce_max_kernel(const double *partials, int m, double *out)
+{
+    __shared__ double s_max[32];
+    double t = -1.0;
+    for (int i = threadIdx.x; i < m; i += 1024) t = fmax(t, partials[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 32; i++) t = fmax(t, s_max[i]);
+        *out = t;
+    }
+}
+
 // out[slot] = sum(partials[0..m)) in a fixed order (single block) -> deterministic norms
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *partials, int m,
                                                                double *out)

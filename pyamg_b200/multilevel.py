@@ -314,6 +314,29 @@ class MultilevelSolver:
         xout = xh.reshape(b.shape)
         return (xout, info.value) if return_info else xout
 
+    def _solve_gmres_device(self, b, x0, tol, maxiter, cycle, residuals, return_info, flexible):
+        """solve(accel='gmres' | 'fgmres') on the GPU: pyamg's Householder GMRES / flexible GMRES
+        (pyamg/krylov/_gmres_householder.py, _fgmres.py) preconditioned by one cycle."""
+        b = np.asarray(b)
+        n = self.levels[0].A.shape[0]
+        if b.size != n or (x0 is not None and np.asarray(x0).size != n):
+            raise ValueError("b / x0 have invalid dimensions")
+        if maxiter is not None and maxiter > n:
+            warn("Setting maxiter to maximum allowed, n.")            # _gmres_householder.py:146-148
+        max_inner = min(n, 40) if maxiter is None else min(int(maxiter), n)
+        bh = np.ascontiguousarray(np.ravel(b), dtype=np.float64)
+        xh = np.zeros(n) if x0 is None else np.array(np.ravel(x0), dtype=np.float64)
+        res = np.empty(max_inner + 3, dtype=np.float64)
+        nres, info = ctypes.c_int32(0), ctypes.c_int32(0)
+        flags = (E.FLAG_X0_ZERO if x0 is None else 0) | (E.FLAG_FLEXIBLE if flexible else 0)
+        E.check(E.lib().amgb_solve_gmres(self.handle, bh.ctypes.data, xh.ctypes.data, float(tol), 0,
+                                         0 if maxiter is None else int(maxiter), E.CYCLES[cycle], flags,
+                                         E.f64p(res), len(res), ctypes.byref(nres), ctypes.byref(info)))
+        if residuals is not None:
+            residuals[:] = list(res[:min(nres.value, len(res))])
+        xout = xh.reshape(b.shape)
+        return (xout, info.value) if return_info else xout
+
     def psolve(self, b):
         """Legacy interface: one iteration (multilevel.py:339-353)."""
         return self.solve(b, maxiter=1)
@@ -373,6 +396,12 @@ class MultilevelSolver:
                 # pyamg.krylov.cg (what the reference resolves 'cg' to, multilevel.py:495-499) with every
                 # vector resident in HBM: amgb_solve_cg
                 return self._solve_cg_device(b, x0, tol, maxiter, cycle, residuals, return_info)
+            if accel in ("gmres", "fgmres") and callback is None and not np.iscomplexobj(b) \
+                    and self.levels[0].A.shape[0] > 1:
+                # pyamg.krylov.gmres (Householder) / pyamg.krylov.fgmres, what the reference resolves these
+                # strings to (multilevel.py:495-499), with every long vector resident in HBM: amgb_solve_gmres
+                return self._solve_gmres_device(b, x0, tol, maxiter, cycle, residuals, return_info,
+                                                flexible=(accel == "fgmres"))
             if accel == "cg":
                 accel = _cg_host           # same algorithm on the host (callback wants host iterates)
             elif isinstance(accel, str):

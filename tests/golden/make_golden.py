@@ -85,6 +85,33 @@ def kernel_goldens(ml, rng):
     return out
 
 
+KRYLOV_ONLY = False       # --krylov: rebuild the same hierarchies, write only the GMRES / FGMRES goldens
+
+
+def emit_krylov(name, ml, b, x0):
+    """Supplementary goldens tests/golden/krylov/<name>.npz: ml.solve(accel='gmres' | 'fgmres') of the real
+    reference (pyamg.krylov.gmres = Householder GMRES, left-preconditioned; pyamg.krylov.fgmres, right-
+    preconditioned) with the cycle as preconditioner."""
+    import warnings
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for tag, kw in (("gmres", dict(tol=1e-10, maxiter=12, accel="gmres")),
+                        ("gmresW", dict(x0=x0, tol=1e-3, maxiter=25, accel="gmres", cycle="W")),
+                        ("fgmres", dict(tol=1e-10, maxiter=12, accel="fgmres")),
+                        ("fgmresF", dict(x0=x0, tol=1e-4, maxiter=25, accel="fgmres", cycle="F")),
+                        ("fgmresAMLI", dict(tol=1e-8, maxiter=5, accel="fgmres", cycle="AMLI"))):
+            res = []
+            x, info = ml.solve(b, residuals=res, return_info=True, **kw)
+            out["x_ref_" + tag] = x
+            out["residuals_" + tag] = np.array(res)
+            out["info_" + tag] = np.array([info])
+    os.makedirs(os.path.join(HERE, "krylov"), exist_ok=True)
+    np.savez_compressed(os.path.join(HERE, "krylov", name + ".npz"), **out)
+    print(f"krylov/{name}: " + ", ".join(f"{t}: {len(out['residuals_' + t]) - 1} its info={int(out['info_' + t][0])}"
+                                       for t in ("gmres", "gmresW", "fgmres", "fgmresF", "fgmresAMLI")))
+
+
 def emit(name, ml, extra_kw=None, ncyc=NCYC, cg_anyway=True):
     rng = np.random.default_rng(SEED)
     n = ml.levels[0].A.shape[0]
@@ -93,6 +120,13 @@ def emit(name, ml, extra_kw=None, ncyc=NCYC, cg_anyway=True):
     res = []
     extra["x_ref"] = ml.solve(b, tol=0, maxiter=ncyc, residuals=res)   # also caches coarse pinv
     extra["residuals"] = np.array(res)
+    if KRYLOV_ONLY:
+        stored = np.load(os.path.join(HERE, name + ".npz"))
+        assert np.array_equal(stored["X_x_ref"], extra["x_ref"]), "rebuilt hierarchy differs from the stored golden"
+        rng2 = np.random.default_rng(SEED)
+        rng2.random(n)
+        emit_krylov(name, ml, b, stored["X_x0"])
+        return
     extra["x_ref_W"] = ml.solve(b, tol=0, maxiter=2, cycle="W")
     extra["x_ref_F"] = ml.solve(b, tol=0, maxiter=2, cycle="F")
     res = []
@@ -200,7 +234,11 @@ def main_widening():
 
 
 if __name__ == "__main__":
-    if "--widening" in sys.argv:
+    if "--krylov" in sys.argv:
+        KRYLOV_ONLY = True
+        main()
+        main_widening()
+    elif "--widening" in sys.argv:
         main_widening()
     else:
         main()

@@ -184,3 +184,32 @@ def test_oracle_pcg_matches_reference(name, load_golden):
                         return_info=True)
     assert info == int(ex["info_cgW"][0]) and len(res) == len(ex["residuals_cgW"])
     assert relerr(x, ex["x_ref_cgW"]) < TIGHT
+
+
+KRYLOV_RUNS = {"gmres": dict(tol=1e-10, maxiter=12, accel="gmres"),
+               "gmresW": dict(tol=1e-3, maxiter=25, accel="gmres", cycle="W"),
+               "fgmres": dict(tol=1e-10, maxiter=12, accel="fgmres"),
+               "fgmresF": dict(tol=1e-4, maxiter=25, accel="fgmres", cycle="F"),
+               "fgmresAMLI": dict(tol=1e-8, maxiter=5, accel="fgmres", cycle="AMLI")}
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_oracle_gmres_and_fgmres_match_reference(name, load_golden):
+    """ml.solve(accel='gmres' | 'fgmres') of the real reference (Householder GMRES, left-preconditioned; flexible
+    GMRES, right-preconditioned; krylov/_gmres_householder.py, _fgmres.py) vs oracle/krylov.py: same iteration
+    counts, info flags, residual histories and iterates (tests/golden/krylov/, made by make_golden.py --krylov)."""
+    import os
+    from conftest import GOLDEN_DIR
+    ml, ex = load_golden(name)
+    kg = np.load(os.path.join(GOLDEN_DIR, "krylov", name + ".npz"))
+    cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.P)
+    for tag, kw in KRYLOV_RUNS.items():
+        kw = dict(kw)
+        if tag in ("gmresW", "fgmresF"):
+            kw["x0"] = ex["x0"]
+        res = []
+        x, info = cyc.solve(ex["b"], residuals=res, return_info=True, **kw)
+        assert info == int(kg["info_" + tag][0]), tag
+        assert len(res) == len(kg["residuals_" + tag]), tag
+        assert np.allclose(res, kg["residuals_" + tag], rtol=1e-6, atol=1e-13 * res[0]), tag
+        assert relerr(x, kg["x_ref_" + tag]) < 1e-9, tag

@@ -174,3 +174,37 @@ def test_amli_cycle_matches_reference_golden(name, env, monkeypatch):
         assert np.allclose(res, ex["residuals_AMLI"], rtol=max(1e-8, 100 * tol))
     # V-cycles afterwards are unaffected by the AMLI buffers / graph
     assert relerr(ml.solve(ex["b"], tol=0, maxiter=len(ex["residuals"]) - 1), ex["x_ref"]) < 1e-12
+
+
+# ------------------------------------------------------------------ GPU-resident GMRES / FGMRES
+@pytest.mark.parametrize("name", GOLDEN_ALL)
+def test_gpu_resident_gmres_and_fgmres_match_reference_golden(name, load_golden):
+    """solve(accel='gmres' | 'fgmres') with every long vector in HBM (amgb_solve_gmres) against the real
+    reference's ml.solve(accel=...) (pyamg.krylov.gmres = Householder GMRES, left-preconditioned; fgmres,
+    right-preconditioned; V, W, F and AMLI cycles as preconditioner): same iteration count, info flag, residual
+    history and iterate.  Goldens: tests/golden/krylov/ (make_golden.py --krylov); the oracle restatement
+    (oracle/krylov.py) is pinned to the same files on the CPU."""
+    import os
+    import warnings
+    from conftest import GOLDEN_DIR
+    from test_oracle import KRYLOV_RUNS
+    ml, ex = load_golden(name)
+    kg = np.load(os.path.join(GOLDEN_DIR, "krylov", name + ".npz"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for tag, kw in KRYLOV_RUNS.items():
+            kw = dict(kw)
+            if tag in ("gmresW", "fgmresF"):
+                kw["x0"] = ex["x0"]
+            res = []
+            x, info = ml.solve(ex["b"], residuals=res, return_info=True, **kw)
+            assert info == int(kg["info_" + tag][0]), tag
+            assert len(res) == len(kg["residuals_" + tag]), tag
+            assert np.allclose(res, kg["residuals_" + tag], rtol=1e-5, atol=1e-12 * res[0]), tag
+            # yardstick: how far the REFERENCE algorithm's own iterate moves under a rounding-level change (every
+            # SpMV summing its rows backwards); 1e-15..1e-12 except with the AMLI cycle on elasticity (1e-9)
+            bound = max(1e-9, 20 * summation_order_sensitivity(ml, ex["b"], **kw))
+            assert relerr(x, kg["x_ref_" + tag]) < bound, tag
+    # misuse mirrors the reference: AMLI needs fgmres (multilevel.py:487-490)
+    with pytest.raises(ValueError):
+        ml.solve(ex["b"], accel="gmres", cycle="AMLI")
