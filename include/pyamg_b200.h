@@ -242,6 +242,14 @@ int amgb_host_block_gauss_seidel(const int32_t *Ap, int Ap_size, const int32_t *
  * kernels the cycle uses; the entry point behind the Python mirrors of relaxation.polynomial / cf_jacobi /
  * fc_jacobi / jacobi_indexed / block_gauss_seidel. */
 int amgb_host_relax(const amgb_matrix *A, const amgb_smoother *sm, double *x, const double *b);
+/* scipy.sparse._sparsetools.csr_matmat as the setup phase uses it for the Galerkin product `R @ A @ P`
+ * (pyamg/classical/classical.py:201, pyamg/aggregation/aggregation.py:425): C = A B with SciPy's results bit for
+ * bit -- same summation order per entry, same (reverse first-appearance) column order inside a row, exact zeros
+ * dropped.  CSR operands (block 1x1).  The three output arrays are malloc'ed by the library: release them with
+ * amgb_free.  Rows with more than 8192 products: AMGB_ENOTIMPL. */
+int amgb_host_csr_matmat(const amgb_matrix *A, const amgb_matrix *B, int32_t **Cp, int32_t **Cj, double **Cx,
+                         int64_t *nnz);
+void amgb_free(void *p);
 /* scipy.sparse._sparsetools.csr_matvec / bsr_matvec as the cycle uses them (y = A x) */
 int amgb_host_matvec(const amgb_matrix *A, const double *x, double *y);
 

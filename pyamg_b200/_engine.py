@@ -60,6 +60,7 @@ SYMBOLS = [
     "amgb_host_gauss_seidel_indexed",
     "amgb_host_bsr_jacobi", "amgb_host_block_jacobi", "amgb_host_matvec",
     "amgb_host_jacobi_indexed", "amgb_host_block_gauss_seidel", "amgb_host_relax",
+    "amgb_host_csr_matmat", "amgb_free",
     "amgb_dev_csr_spmv", "amgb_dev_csr_residual", "amgb_dev_csr_spmv_add", "amgb_dev_csr_jacobi",
     "amgb_dev_csr_gs_wave", "amgb_dev_partials_len", "amgb_dev_dense_matvec", "amgb_dev_fill",
     "amgb_dev_gather", "amgb_wave_schedule", "amgb_debug_build_tiles",
@@ -128,6 +129,10 @@ def _bind(L):
                                            c_i32p, ci, c_f64p, ci]
     L.amgb_host_block_gauss_seidel.argtypes = [c_i32p, ci, c_i32p, ci, c_f64p, ci, c_f64p, ci, c_f64p, ci,
                                                c_f64p, ci, i32, i32, i32, i32]
+    L.amgb_host_csr_matmat.argtypes = [ctypes.POINTER(Matrix), ctypes.POINTER(Matrix), ctypes.POINTER(c_i32p),
+                                       ctypes.POINTER(c_i32p), ctypes.POINTER(c_f64p), ctypes.POINTER(ctypes.c_int64)]
+    L.amgb_free.argtypes = [vp]
+    L.amgb_free.restype = None
     L.amgb_host_relax.argtypes = [ctypes.POINTER(Matrix), ctypes.POINTER(Smoother), c_f64p, c_f64p]
     L.amgb_dev_csr_spmv.argtypes = [i32, vp, vp, vp, vp, vp, ci, vp]
     L.amgb_dev_csr_residual.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, ci, vp]
@@ -211,3 +216,25 @@ def free_pinned(arr):
     ent = _PINNED.pop(id(arr), None)
     if ent is not None:
         lib().amgb_host_free(ent[0])
+
+
+def csr_matmat(A, B):
+    """C = A @ B on the GPU with SciPy's csr_matmat results bit for bit (amgb_host_csr_matmat): the Galerkin
+    product of the setup phase (pyamg/classical/classical.py:201).  Returns a scipy csr_array."""
+    from scipy import sparse
+    if A.shape[1] != B.shape[0]:
+        raise ValueError("dimension mismatch")
+    require_gpu()
+    keep = []
+    MA, MB = as_matrix(sparse.csr_array(A), keep), as_matrix(sparse.csr_array(B), keep)
+    Cp, Cj, Cx, nnz = c_i32p(), c_i32p(), c_f64p(), ctypes.c_int64(0)
+    check(lib().amgb_host_csr_matmat(MA, MB, ctypes.byref(Cp), ctypes.byref(Cj), ctypes.byref(Cx), ctypes.byref(nnz)))
+    try:
+        n, m = A.shape[0], nnz.value
+        indptr = np.ctypeslib.as_array(Cp, shape=(n + 1,)).copy()
+        indices = np.ctypeslib.as_array(Cj, shape=(max(m, 1),))[:m].copy()
+        data = np.ctypeslib.as_array(Cx, shape=(max(m, 1),))[:m].copy()
+    finally:
+        for p in (Cp, Cj, Cx):
+            lib().amgb_free(ctypes.cast(p, ctypes.c_void_p))
+    return sparse.csr_array((data, indices, indptr), shape=(A.shape[0], B.shape[1]))

@@ -23,7 +23,7 @@ from . import _host as H
 from .classical import _csr32
 from .multilevel import MultilevelSolver
 from .relaxation.smoothing import change_smoothers
-from .util import approximate_spectral_radius, get_diagonal
+from .util import approximate_spectral_radius, galerkin, get_diagonal
 
 __all__ = ["smoothed_aggregation_solver", "symmetric_strength_pattern", "standard_aggregation",
            "fit_candidates", "jacobi_prolongation_smoother"]
@@ -249,7 +249,7 @@ def smoothed_aggregation_solver(A, B=None, symmetry="hermitian", strength="symme
             Ac = _bsr32(Ac.tobsr(blocksize=(P.blocksize[1], P.blocksize[1])))
         else:
             R = _csr32(P.T.tocsr())
-            Ac = _csr32(R @ A @ P)
+            Ac = _csr32(galerkin(R, A, P) if (A.format == "csr" and R.format == "csr") else R @ A @ P)
         if keep:
             levels[-1].C, levels[-1].AggOp, levels[-1].Cnodes, levels[-1].T = C, AggOp, Cnodes, T
         levels[-1].P, levels[-1].R = P, R

@@ -14,6 +14,7 @@ from scipy import sparse
 
 from . import _host as H
 from .multilevel import MultilevelSolver
+from .util import galerkin
 from .relaxation.smoothing import change_smoothers
 
 __all__ = ["ruge_stuben_solver", "classical_strength_of_connection", "RS", "classical_interpolation"]
@@ -127,7 +128,7 @@ def ruge_stuben_solver(A, strength=("classical", {"theta": 0.25}), CF=("RS", {"s
         levels[-1].P = P
         levels[-1].R = R
         levels.append(MultilevelSolver.Level())
-        levels[-1].A = _csr32(R @ A @ P)                    # classical.py:201
+        levels[-1].A = _csr32(galerkin(R, A, P))            # classical.py:201 (AMGB_GPU_RAP=1: on the GPU)
     ml = MultilevelSolver(levels, **kwargs)
     change_smoothers(ml, presmoother, postsmoother)
     return ml

@@ -18,6 +18,7 @@
 #include "tail_kernel.cuh"
 #include "resident_kernel.cuh"
 #include "tile_flat_kernel.cuh"
+#include "spgemm.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -3045,6 +3046,115 @@ extern "C" int amgb_host_block_gauss_seidel(const int32_t *Ap, int Ap_size, cons
     else return fail(AMGB_ENOTIMPL, "block_gauss_seidel: only the full forward / backward block-row ranges");
     amgb_matrix A = {n, n, blocksize, blocksize, Aj_size, Ap, Aj, Ax};
     return amgb_host_relax(&A, &sm, x, b);
+}
+
+// ------------------------------------------------------------------------------------------
+// C = A B as scipy.sparse._sparsetools.csr_matmat computes it (spgemm.cuh): the Galerkin product of the setup phase
+// ------------------------------------------------------------------------------------------
+template <int CAP, int THREADS>
+static int launch_spgemm(SpgemmArgs a, cudaStream_t s)
+{
+    if (a.n_rows <= 0) return AMGB_OK;
+    constexpr size_t smem = spgemm_smem_bytes<CAP>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(spgemm_row_kernel<CAP, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    spgemm_row_kernel<CAP, THREADS><<<(unsigned)a.n_rows, THREADS, smem, s>>>(a);
+    CK(cudaGetLastError());
+    return AMGB_OK;
+}
+
+extern "C" void amgb_free(void *p) { free(p); }
+
+extern "C" int amgb_host_csr_matmat(const amgb_matrix *A, const amgb_matrix *B, int32_t **Cp_out, int32_t **Cj_out,
+                                    double **Cx_out, int64_t *nnz_out)
+{
+    if (Cp_out == nullptr || Cj_out == nullptr || Cx_out == nullptr || nnz_out == nullptr)
+        return fail(AMGB_EINVAL, "null output");
+    *Cp_out = nullptr; *Cj_out = nullptr; *Cx_out = nullptr; *nnz_out = 0;
+    RET(validate_matrix(A, "A"));
+    RET(validate_matrix(B, "B"));
+    if (A->block_r != 1 || A->block_c != 1 || B->block_r != 1 || B->block_c != 1)
+        return fail(AMGB_ENOTIMPL, "csr_matmat: CSR operands only (bsr_matmat is not on the GPU path)");
+    if (A->n_cols != B->n_rows) return fail(AMGB_EINVAL, "dimension mismatch");       // scipy: ValueError
+    const int n = A->n_rows;
+    for (int64_t k = 0; k < A->nnz_blocks; k++)
+        if (A->indices[k] < 0 || A->indices[k] >= A->n_cols) return fail(AMGB_EINVAL, "A: column index out of range");
+    for (int64_t k = 0; k < B->nnz_blocks; k++)
+        if (B->indices[k] < 0 || B->indices[k] >= B->n_cols) return fail(AMGB_EINVAL, "B: column index out of range");
+    // bins by the work of a row: products (and entries of A_i, which index the offset table)
+    std::vector<int> bins[3];
+    static const int kCap[3] = {256, 2048, 8192};
+    for (int i = 0; i < n; i++) {
+        long long prod = 0;
+        const int na = A->indptr[i + 1] - A->indptr[i];
+        if (na < 0) return fail(AMGB_EINVAL, "A: indptr not monotone");
+        for (int jj = A->indptr[i]; jj < A->indptr[i + 1]; jj++) {
+            const int j = A->indices[jj];
+            prod += B->indptr[j + 1] - B->indptr[j];
+        }
+        const long long need = std::max<long long>(prod, na);
+        int b = 0;
+        while (b < 3 && need > kCap[b]) b++;
+        if (b == 3) return fail(AMGB_ENOTIMPL, "csr_matmat: a row with more than 8192 products");
+        bins[b].push_back(i);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(AMGB_ECUDA, "no CUDA device");
+    Scratch sc;
+    SpgemmArgs a;
+    int *dAp, *dAj, *dBp, *dBj, *d_rows[3], *d_nnz, *dCp, *dCj;
+    double *dAx, *dBx, *dCx;
+    RET(sc.up(&dAp, A->indptr, (long long)n + 1)); RET(sc.up(&dAj, A->indices, A->nnz_blocks));
+    RET(sc.up(&dAx, A->data, A->nnz_blocks));
+    RET(sc.up(&dBp, B->indptr, (long long)B->n_rows + 1)); RET(sc.up(&dBj, B->indices, B->nnz_blocks));
+    RET(sc.up(&dBx, B->data, B->nnz_blocks));
+    for (int b = 0; b < 3; b++) RET(sc.up(&d_rows[b], bins[b].data(), (long long)bins[b].size()));
+    RET(sc.up(&d_nnz, (const int *)nullptr, (long long)n));
+    a.Ap = dAp; a.Aj = dAj; a.Ax = dAx; a.Bp = dBp; a.Bj = dBj; a.Bx = dBx;
+    a.row_nnz = d_nnz; a.Cp = nullptr; a.Cj = nullptr; a.Cx = nullptr;
+    auto pass = [&](int fill) -> int {
+        a.fill = fill;
+        a.rows = d_rows[0]; a.n_rows = (int)bins[0].size();
+        RET((launch_spgemm<256, 32>(a, 0)));
+        a.rows = d_rows[1]; a.n_rows = (int)bins[1].size();
+        RET((launch_spgemm<2048, 128>(a, 0)));
+        a.rows = d_rows[2]; a.n_rows = (int)bins[2].size();
+        RET((launch_spgemm<8192, 256>(a, 0)));
+        CK(cudaDeviceSynchronize());
+        return AMGB_OK;
+    };
+    RET(pass(0));
+    std::vector<int> row_nnz((size_t)n);
+    if (n > 0) CK(cudaMemcpy(row_nnz.data(), d_nnz, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+    int32_t *Cp = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n + 1));
+    if (Cp == nullptr) return fail(AMGB_ECUDA, "out of host memory");
+    long long run = 0;
+    Cp[0] = 0;
+    for (int i = 0; i < n; i++) {
+        run += row_nnz[(size_t)i];
+        if (run > 2147483647LL) { free(Cp); return fail(AMGB_EINVAL, "csr_matmat: nnz exceeds int32 (reference index type)"); }
+        Cp[i + 1] = (int32_t)run;
+    }
+    int32_t *Cj = (int32_t *)malloc(sizeof(int32_t) * (size_t)std::max<long long>(run, 1));
+    double *Cx = (double *)malloc(sizeof(double) * (size_t)std::max<long long>(run, 1));
+    struct OutGuard { int32_t *p, *j; double *x; bool keep; ~OutGuard() { if (!keep) { free(p); free(j); free(x); } } }
+        og{Cp, Cj, Cx, false};
+    if (Cj == nullptr || Cx == nullptr) return fail(AMGB_ECUDA, "out of host memory");
+    RET(sc.up(&dCp, (const int *)Cp, (long long)n + 1));
+    RET(sc.up(&dCj, (const int *)nullptr, run));
+    RET(sc.up(&dCx, (const double *)nullptr, run));
+    a.Cp = dCp; a.Cj = dCj; a.Cx = dCx;
+    RET(pass(1));
+    if (run > 0) {
+        CK(cudaMemcpy(Cj, dCj, sizeof(int32_t) * (size_t)run, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(Cx, dCx, sizeof(double) * (size_t)run, cudaMemcpyDeviceToHost));
+    }
+    og.keep = true;
+    *Cp_out = Cp; *Cj_out = Cj; *Cx_out = Cx; *nnz_out = run;
+    return AMGB_OK;
 }
 
 extern "C" int amgb_host_matvec(const amgb_matrix *A, const double *x, double *y)

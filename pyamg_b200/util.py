@@ -80,3 +80,21 @@ def approximate_spectral_radius(A, maxiter=15, restarts=5, seed=20260922):
         if m < maxiter:
             break
     return rho
+
+
+def galerkin(R, A, P, where=None):
+    """Coarse operator ``R @ A @ P`` (pyamg/classical/classical.py:201, aggregation/aggregation.py:425).
+
+    ``where='gpu'`` (or ``AMGB_GPU_RAP=1``) computes the two products with the engine's SpGEMM
+    (csrc/spgemm.cuh), which reproduces SciPy's ``csr_matmat`` bit for bit -- same values, same column order,
+    same dropped zeros -- so the hierarchy is identical either way; the default stays SciPy on the host until the
+    kernel has run on a B200.  CSR operands only."""
+    import os
+    if where is None:
+        where = "gpu" if os.environ.get("AMGB_GPU_RAP") == "1" else "host"
+    if where == "host":
+        return R @ A @ P
+    if where != "gpu":
+        raise ValueError("galerkin: where must be 'host' or 'gpu'")
+    from . import _engine as E
+    return E.csr_matmat(E.csr_matmat(sparse.csr_array(R), sparse.csr_array(A)), sparse.csr_array(P))

@@ -118,7 +118,7 @@ def build(force=False, verbose=False):
             with open(os.path.join(gdir, f), "w") as o:
                 o.write(transform(src, os.path.join(CSRC, f)))
     cmd = ["g++", "-x", "c++", "-std=c++17", "-O1", "-g", "-DAMGB_EMU", "-I", HERE, "-fPIC", "-shared",
-           "-fno-strict-aliasing", "-Wno-unknown-pragmas", "-Wno-attributes",
+           "-fno-strict-aliasing", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes",
            os.path.join(gdir, "engine.cu"), "-o", LIB]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)

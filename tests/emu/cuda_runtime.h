@@ -543,6 +543,10 @@ inline int __all_sync(unsigned m, int pred)
     const int n = std::min(32, emu::g.cur->blk->nthreads - (int)(emu::g.cur->tid.x & ~31u));
     return __ballot_sync(m, pred) == (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
 }
+inline double __dmul_rn(double a, double b) { return a * b; }      // the host build has no FMA contraction (-ffp-contract=off)
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, 8); return r; }
+inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }

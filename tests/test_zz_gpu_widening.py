@@ -208,3 +208,54 @@ def test_gpu_resident_gmres_and_fgmres_match_reference_golden(name, load_golden)
     # misuse mirrors the reference: AMLI needs fgmres (multilevel.py:487-490)
     with pytest.raises(ValueError):
         ml.solve(ex["b"], accel="gmres", cycle="AMLI")
+
+
+# ------------------------------------------------------------------ Galerkin product on the GPU
+def _bitwise_equal(C, D):
+    C, D = sp.csr_array(C), sp.csr_array(D)
+    return (C.shape == D.shape and np.array_equal(C.indptr, D.indptr) and np.array_equal(C.indices, D.indices)
+            and np.array_equal(C.data.view(np.int64), D.data.view(np.int64)))
+
+
+def test_spgemm_equals_scipy_csr_matmat_bit_for_bit():
+    """amgb_host_csr_matmat vs SciPy's csr_matmat (what `R @ A @ P` runs, classical.py:201): identical indptr,
+    identical column ORDER inside every row (reverse first appearance), identical value bits (same summation order,
+    no FMA), exact zeros dropped; unsorted operands, empty rows / columns, rectangular shapes, all three row bins."""
+    from pyamg_b200 import _engine as E
+    for (m, k, n, d, seed) in [(30, 40, 25, 0.1, 1), (50, 50, 50, 0.3, 2), (7, 3, 9, 0.9, 3), (200, 150, 180, 0.05, 4),
+                               (12, 60, 100, 0.9, 5)]:
+        A = sp.csr_array(sp.random(m, k, density=d, random_state=np.random.RandomState(seed), format="csr"))
+        B = sp.csr_array(sp.random(k, n, density=d, random_state=np.random.RandomState(seed + 50), format="csr"))
+        A.data = np.round(A.data * 8) / 8 - 0.5            # exact cancellations: csr_matmat drops the zeros
+        B.data = np.round(B.data * 8) / 8 - 0.5
+        assert _bitwise_equal(A @ B, E.csr_matmat(A, B))
+        C = A @ B                                          # a SciPy product has unsorted column indices
+        assert _bitwise_equal(C.T.tocsr() @ C, E.csr_matmat(C.T.tocsr(), C))
+        assert _bitwise_equal(C @ sp.csr_array((n, 4)), E.csr_matmat(C, sp.csr_array((n, 4))))   # empty operand
+    with pytest.raises(ValueError):
+        E.csr_matmat(sp.eye(3, format="csr"), sp.eye(4, format="csr"))
+    dense = sp.csr_array(np.ones((2, 100))), sp.csr_array(np.ones((100, 100)))
+    with pytest.raises(NotImplementedError):               # 10 000 products in one row: outside the supported bins
+        E.csr_matmat(*dense)
+
+
+@pytest.mark.parametrize("name", ["cfg1_rs_gs_poisson2d", "cfg3_rs_mcgs_poisson3d", "cfg9_air_fcjacobi_advection2d"])
+def test_galerkin_product_reproduces_the_reference_hierarchy(name, load_golden):
+    """(R A) P on the GPU == the coarse operators the REAL reference stored in the golden hierarchies, bit for bit
+    (classical RS, and AIR where R != P^T)."""
+    from pyamg_b200.util import galerkin
+    ml, _ = load_golden(name)
+    for lvl, nxt in zip(ml.levels[:-1], ml.levels[1:]):
+        assert _bitwise_equal(galerkin(lvl.R, lvl.A, lvl.P, where="gpu"), nxt.A)
+
+
+def test_host_setup_with_gpu_galerkin_builds_the_same_hierarchy(monkeypatch):
+    from pyamg_b200.classical import ruge_stuben_solver
+    from pyamg_b200.gallery import poisson
+    A = poisson((14, 14, 14))
+    ref = ruge_stuben_solver(A)
+    monkeypatch.setenv("AMGB_GPU_RAP", "1")
+    gpu = ruge_stuben_solver(A)
+    assert len(ref.levels) == len(gpu.levels)
+    for a, b in zip(ref.levels, gpu.levels):
+        assert _bitwise_equal(a.A, b.A)
