@@ -24,6 +24,8 @@
 //     from uninitialised device memory shows up in the parity tests;
 //   * stream capture records closures with by-value arguments, graph launch replays them (what baking
 //     pointers into a CUDA graph means); everything else runs synchronously in stream order;
+//   * AMGB_EMU_ORDER=reverse visits warps and lanes in the opposite order: results that change with it depend on
+//     the interleaving between synchronisation points, i.e. the kernel has a race (or an order-dependent reduction);
 //   * a launch in which no fiber can make progress is reported as cudaErrorLaunchFailure ("deadlock").
 #pragma once
 #ifndef AMGB_EMU
@@ -169,6 +171,7 @@ struct State {
     std::map<uintptr_t, size_t> allocs;       // device allocations: base -> bytes
     std::vector<unsigned char *> stacks;      // fiber stacks (reused across launches)
     bool tma_lazy = false;
+    bool reverse = false;                     // AMGB_EMU_ORDER=reverse
     struct PendingCopy { unsigned long long *bar; void *dst; const void *src; unsigned bytes; };
     std::vector<PendingCopy> pending;
     long long launches = 0, fibers_run = 0;
@@ -274,14 +277,19 @@ inline bool run_cluster(dim3 grid, dim3 block, size_t smem, unsigned first_block
     while (remaining > 0) {
         const unsigned long long before = g.progress;
         remaining = 0;
-        for (size_t w0 = 0; w0 < nfib; w0 += 32) {
+        const size_t nwarp_all = (nfib + 31) / 32;
+        for (size_t wi = 0; wi < nwarp_all; wi++) {
+            // AMGB_EMU_ORDER=reverse: warps and lanes are visited in the opposite order -- a correct kernel (no
+            // dependence on the interleaving between synchronisation points) gives bit-identical results
+            const size_t w0 = (g.reverse ? (nwarp_all - 1 - wi) : wi) * 32;
             const size_t w1 = std::min(nfib, w0 + 32);      // warps: blocks are multiples of 32 threads (checked in execute)
             size_t left;
             unsigned long long p;
             do {
                 p = g.progress;
                 left = 0;
-                for (size_t i = w0; i < w1; i++) {
+                for (size_t ii = w0; ii < w1; ii++) {
+                    const size_t i = g.reverse ? (w1 - 1 - (ii - w0)) : ii;
                     Fiber &f = fibers[i];
                     if (f.done) continue;
                     g.cur = &f;
@@ -580,6 +588,8 @@ inline cudaError_t cudaGetDeviceCount(int *n)
     if (!(t && t[0] == '1')) { *n = 0; return cudaErrorNoDevice; }     // never a silent CPU path
     const char *lz = getenv("AMGB_EMU_TMA");
     emu::g.tma_lazy = lz && strcmp(lz, "lazy") == 0;
+    const char *ord = getenv("AMGB_EMU_ORDER");
+    emu::g.reverse = ord && strcmp(ord, "reverse") == 0;
     *n = 1;
     return cudaSuccess;
 }

@@ -69,3 +69,27 @@ def test_tile_kernels_everywhere_with_lazy_tma_completion():
          "vcycle_matches_reference_golden or relaxation_kernels or w_and_f")
     _run({"AMGB_EMU_TMA": "lazy", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_CFG": "1"}, "vcycle_matches_reference_golden",
          files=("tests/test_gpu_parity.py",))
+
+
+def test_results_do_not_depend_on_thread_interleaving(tmp_path):
+    """The emulator runs the lanes of a warp one after the other between synchronisation points; visiting warps and
+    lanes in the opposite order (AMGB_EMU_ORDER=reverse) must not change a single bit of V/W cycles, GMRES or CG --
+    with the lanes-per-row kernels and with the TMA tile kernels on every operator.  A kernel with a race (e.g. an
+    in-place Gauss-Seidel wave that read a row of its own wave) would differ."""
+    import numpy as np
+    names = ["cfg3_rs_mcgs_poisson3d", "cfg5_sa_bjacobi_elasticity", "cfg9_air_fcjacobi_advection2d",
+             "cfg10_sa_bgs_elasticity"]
+    probe = os.path.join(ROOT, "tests", "emu", "order_probe.py")
+    for extra in ({}, {"AMGB_TILE_MIN_NNZ": "0"}):
+        dumps = []
+        for order in ("forward", "reverse"):
+            env = dict(os.environ)
+            env.update(extra)
+            env.update({"AMGB_TEST_EMU": "1", "AMGB_EMU_ORDER": order})
+            path = str(tmp_path / f"{order}{len(extra)}.npz")
+            r = subprocess.run([sys.executable, probe, path, *names], cwd=ROOT, env=env, capture_output=True,
+                               text=True, timeout=900)
+            assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+            dumps.append(np.load(path))
+        for n in names:
+            assert np.array_equal(dumps[0][n].view(np.int64), dumps[1][n].view(np.int64)), (n, extra)
