@@ -11,6 +11,10 @@ G=${1:-256}
 mkdir -p gpurun_out
 echo "=== parity: newest default-suite test"
 timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "out_buffer" 2>&1 | tail -3
+echo "=== parity: SURVEY 8(f) widening (smoothers, AMLI, GMRES/FGMRES, GPU Galerkin) -- first hardware run"
+timeout 1500 python -m pytest tests/test_zz_gpu_widening.py -q -m gpu 2>&1 | tail -8
+echo "=== timing: widening rows"
+timeout 1200 python tools/time_widening.py --grid 128 2>&1 | tail -14 | tee gpurun_out/r2_widening.jsonl
 echo "=== parity: experimental paths"
 AMGB_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_experimental.py -q -m gpu_experimental 2>&1 | tail -15
 echo "=== A/B (graphed cycle ms, small_levels ms, per-level GB/s)"
