@@ -242,6 +242,18 @@ int amgb_host_block_gauss_seidel(const int32_t *Ap, int Ap_size, const int32_t *
  * kernels the cycle uses; the entry point behind the Python mirrors of relaxation.polynomial / cf_jacobi /
  * fc_jacobi / jacobi_indexed / block_gauss_seidel. */
 int amgb_host_relax(const amgb_matrix *A, const amgb_smoother *sm, double *x, const double *b);
+/* GPU-resident Arnoldi rounds for the spectral-radius estimates of the smoother setup (pyamg/util/linalg.py:255-383
+ * approximate_spectral_radius -> _approximate_eigenvalues :90-252): the operator x -> diag(row_scale) (A x)
+ * (row_scale may be NULL) is uploaded once; amgb_arnoldi_run does a whole round of modified-Gram-Schmidt Arnoldi
+ * on the device and returns the (maxiter+1) x maxiter Hessenberg matrix (row-major) and the number of valid steps;
+ * the host picks the restart vector from H's eigen-decomposition and hands its coefficients in the (still resident)
+ * basis to amgb_arnoldi_combine; the next run with v0_host == NULL starts from it. */
+typedef struct amgb_arnoldi amgb_arnoldi;
+int amgb_arnoldi_create(int device, const amgb_matrix *A, const double *row_scale, int32_t maxiter, amgb_arnoldi **out);
+int amgb_arnoldi_run(amgb_arnoldi *a, const double *v0_host, double breakdown, double *H_host, int32_t *m_done);
+int amgb_arnoldi_combine(amgb_arnoldi *a, const double *coef, int32_t m);
+void amgb_arnoldi_destroy(amgb_arnoldi *a);
+
 /* scipy.sparse._sparsetools.csr_matmat as the setup phase uses it for the Galerkin product `R @ A @ P`
  * (pyamg/classical/classical.py:201, pyamg/aggregation/aggregation.py:425): C = A B with SciPy's results bit for
  * bit -- same summation order per entry, same (reverse first-appearance) column order inside a row, exact zeros

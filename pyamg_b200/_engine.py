@@ -61,6 +61,7 @@ SYMBOLS = [
     "amgb_host_bsr_jacobi", "amgb_host_block_jacobi", "amgb_host_matvec",
     "amgb_host_jacobi_indexed", "amgb_host_block_gauss_seidel", "amgb_host_relax",
     "amgb_host_csr_matmat", "amgb_free",
+    "amgb_arnoldi_create", "amgb_arnoldi_run", "amgb_arnoldi_combine", "amgb_arnoldi_destroy",
     "amgb_dev_csr_spmv", "amgb_dev_csr_residual", "amgb_dev_csr_spmv_add", "amgb_dev_csr_jacobi",
     "amgb_dev_csr_gs_wave", "amgb_dev_partials_len", "amgb_dev_dense_matvec", "amgb_dev_fill",
     "amgb_dev_gather", "amgb_wave_schedule", "amgb_debug_build_tiles",
@@ -131,6 +132,11 @@ def _bind(L):
                                                c_f64p, ci, i32, i32, i32, i32]
     L.amgb_host_csr_matmat.argtypes = [ctypes.POINTER(Matrix), ctypes.POINTER(Matrix), ctypes.POINTER(c_i32p),
                                        ctypes.POINTER(c_i32p), ctypes.POINTER(c_f64p), ctypes.POINTER(ctypes.c_int64)]
+    L.amgb_arnoldi_create.argtypes = [ctypes.c_int, ctypes.POINTER(Matrix), c_f64p, i32, ctypes.POINTER(vp)]
+    L.amgb_arnoldi_run.argtypes = [vp, c_f64p, f64, c_f64p, c_i32p]
+    L.amgb_arnoldi_combine.argtypes = [vp, c_f64p, i32]
+    L.amgb_arnoldi_destroy.argtypes = [vp]
+    L.amgb_arnoldi_destroy.restype = None
     L.amgb_free.argtypes = [vp]
     L.amgb_free.restype = None
     L.amgb_host_relax.argtypes = [ctypes.POINTER(Matrix), ctypes.POINTER(Smoother), c_f64p, c_f64p]

@@ -337,6 +337,24 @@ __global__ void __launch_bounds__(1024) reduce_max_kernel(const double *partials
     }
 }
 
+// Arnoldi pieces (amgb_arnoldi_run): everything between two host reads stays on the device
+__global__ void sqrt_scalar_kernel(double *p) { *p = sqrt(*p); }
+// y = x / *den   (next Krylov basis vector: w / ||w|| with the norm in a device scalar)
+__global__ void div_dev_kernel(double *__restrict__ y, const double *__restrict__ x, const double *den, long long n)
+{
+    const double d = den[0];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) y[i] = x[i] / d;
+}
+// y *= s (elementwise): the operator diag(s) A of rho(D^-1 A) without forming the scaled matrix
+__global__ void mul_kernel(double *__restrict__ y, const double *__restrict__ s, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) y[i] = y[i] * s[i];
+}
+
 // out[slot] = sum(partials[0..m)) in a fixed order (single block) -> deterministic norms
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *partials, int m,
                                                                double *out)

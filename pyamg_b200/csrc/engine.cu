@@ -2594,6 +2594,146 @@ extern "C" int amgb_operator_apply(amgb_operator *op, int32_t kind, const double
     return AMGB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// C ABI (1c): GPU-resident Arnoldi rounds for the spectral-radius estimates of the smoother setup
+// (pyamg/util/linalg.py:255-383 approximate_spectral_radius -> _approximate_eigenvalues :90-252:
+// rho(D^-1 A) for Jacobi's omega, smoothing.py:372-400, rho(A) for Richardson / Chebyshev, :611-647).
+// The operator x -> diag(row_scale) (A x) is uploaded once; one call runs a whole round of modified-Gram-Schmidt
+// Arnoldi without a host round trip (inner products stay in device scalars: dot_to + axpy_ratio_kernel), the small
+// Hessenberg matrix goes to the host, whose eigen-decomposition (LAPACK through SciPy, as in the reference)
+// picks the restart vector as a combination of the basis that is still resident.
+// ------------------------------------------------------------------------------------------
+struct amgb_arnoldi {
+    amgb_hierarchy *pool = nullptr;
+    DevCsr M;
+    int maxiter = 0;
+    long long n = 0, npad = 0;
+    double *V = nullptr, *w = nullptr, *scale = nullptr, *dH = nullptr, *one = nullptr;
+    bool have_start = false;
+    double *v(int j) const { return V + (size_t)j * npad; }
+};
+
+extern "C" int amgb_arnoldi_create(int device, const amgb_matrix *A, const double *row_scale, int32_t maxiter,
+                                   amgb_arnoldi **out)
+{
+    if (out == nullptr) return fail(AMGB_EINVAL, "out is null");
+    *out = nullptr;
+    if (maxiter < 1) return fail(AMGB_EINVAL, "maxiter < 1");
+    amgb_hierarchy *pool = nullptr;
+    RET(amgb_hierarchy_create(device, &pool));
+    std::unique_ptr<amgb_arnoldi> a(new amgb_arnoldi());
+    a->pool = pool;
+    auto bail = [&](int rc) { amgb_hierarchy_destroy(pool); return rc; };
+    HostCsr H;
+    int rc = to_host_csr(A, H, "A");
+    if (rc == AMGB_OK && H.n_rows != H.n_cols) rc = fail(AMGB_EINVAL, "expected square matrix");   // linalg.py:150-151
+    if (rc != AMGB_OK) return bail(rc);
+    if (cudaStreamCreateWithFlags(&pool->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(AMGB_ECUDA, "stream"));
+    pool->own_stream = true;
+    a->n = H.n_rows;
+    a->npad = ((a->n + 2 + 31) / 32) * 32;
+    a->maxiter = (int)std::min<long long>(maxiter, std::max<long long>(a->n, 1));
+    rc = pool->upload_csr(H, a->M);
+    if (rc == AMGB_OK) rc = pool->dalloc(&a->V, (long long)(a->maxiter + 1) * a->npad);
+    if (rc == AMGB_OK) rc = pool->dalloc(&a->w, a->npad);
+    if (rc == AMGB_OK) rc = pool->dalloc(&a->dH, (long long)(a->maxiter + 1) * a->maxiter);
+    if (rc == AMGB_OK) rc = pool->dalloc(&a->one, 8);
+    if (rc == AMGB_OK) rc = pool->dalloc(&pool->sumsq_parts, kSumsqBlocks);
+    if (rc == AMGB_OK && row_scale != nullptr) rc = pool->upload(&a->scale, row_scale, a->n, 2);
+    if (rc != AMGB_OK) return bail(rc);
+    const double init[2] = {1.0, 0.0};
+    if (cudaMemcpy(a->one, init, sizeof init, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(a->V, 0, sizeof(double) * (size_t)(a->maxiter + 1) * (size_t)a->npad) != cudaSuccess ||
+        cudaMemset(a->w, 0, sizeof(double) * (size_t)a->npad) != cudaSuccess ||
+        cudaHostAlloc((void **)&pool->norm_host, sizeof(double) * 2, cudaHostAllocDefault) != cudaSuccess)
+        return bail(fail(AMGB_ECUDA, "arnoldi: device initialisation"));
+    *out = a.release();
+    return AMGB_OK;
+}
+
+extern "C" void amgb_arnoldi_destroy(amgb_arnoldi *a)
+{
+    if (a == nullptr) return;
+    amgb_hierarchy_destroy(a->pool);
+    delete a;
+}
+
+// One round: V[0] = v0 / ||v0|| (v0 from the host, or -- v0_host == NULL -- the vector left by amgb_arnoldi_combine),
+// then maxiter steps  w = diag(s) A V[j];  H[i][j] = <V[i], w>, w -= H[i][j] V[i] (i <= j);  H[j+1][j] = ||w||;
+// V[j+1] = w / H[j+1][j].  H: (maxiter+1) x maxiter row-major on the host.  *m_done = number of valid steps: the
+// first j with H[j+1][j] < breakdown * max(1, max |H[:j+1,:j+1]|) ends the round at m = j + 1 (later columns are
+// then meaningless); 0 if the start vector is zero.
+extern "C" int amgb_arnoldi_run(amgb_arnoldi *a, const double *v0_host, double breakdown, double *H_host, int32_t *m_done)
+{
+    if (a == nullptr || H_host == nullptr || m_done == nullptr) return fail(AMGB_EINVAL, "null argument");
+    amgb_hierarchy *h = a->pool;
+    CK(cudaSetDevice(h->device));
+    h->rt.activate();
+    cudaStream_t s = h->stream;
+    const long long n = a->n;
+    const int mi = a->maxiter;
+    *m_done = 0;
+    if (v0_host != nullptr) CK(cudaMemcpyAsync(a->v(0), v0_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+    else if (!a->have_start) return fail(AMGB_ESTATE, "arnoldi: no start vector (call amgb_arnoldi_combine or pass v0)");
+    a->have_start = false;
+    double *scal = a->one + 1;
+    RET(h->dot_to(a->v(0), a->v(0), n, scal));
+    CK(cudaMemcpyAsync(h->norm_host, scal, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (!(h->norm_host[0] > 0.0)) {
+        std::fill(H_host, H_host + (size_t)(mi + 1) * mi, 0.0);
+        return AMGB_OK;
+    }
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)g_num_sms * 16);
+    div_kernel<<<grid, 256, 0, s>>>(a->v(0), std::sqrt(h->norm_host[0]), n);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(a->dH, 0, sizeof(double) * (size_t)(mi + 1) * (size_t)mi, s));
+    for (int j = 0; j < mi; j++) {
+        RET(h->spmv(OP_SPMV, a->M, a->v(j), nullptr, a->w));
+        if (a->scale != nullptr) {
+            mul_kernel<<<grid, 256, 0, s>>>(a->w, a->scale, n);
+            CK(cudaGetLastError());
+        }
+        for (int i = 0; i <= j; i++) {
+            double *hij = a->dH + (size_t)i * mi + j;
+            RET(h->dot_to(a->v(i), a->w, n, hij));
+            RET(h->axpy_ratio(a->w, a->v(i), hij, a->one, -1.0, n));
+        }
+        double *hn = a->dH + (size_t)(j + 1) * mi + j;
+        RET(h->dot_to(a->w, a->w, n, hn));
+        sqrt_scalar_kernel<<<1, 1, 0, s>>>(hn);
+        CK(cudaGetLastError());
+        div_dev_kernel<<<grid, 256, 0, s>>>(a->v(j + 1), a->w, hn, n);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(H_host, a->dH, sizeof(double) * (size_t)(mi + 1) * (size_t)mi, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int m = mi;
+    double hmax = 0.0;
+    for (int j = 0; j < mi; j++) {
+        for (int i = 0; i <= j; i++) hmax = std::max(hmax, std::fabs(H_host[(size_t)i * mi + j]));
+        for (int jj = 0; jj < j; jj++) hmax = std::max(hmax, std::fabs(H_host[(size_t)j * mi + jj]));
+        if (!(H_host[(size_t)(j + 1) * mi + j] >= breakdown * std::max(1.0, hmax))) { m = j + 1; break; }
+    }
+    *m_done = m;
+    return AMGB_OK;
+}
+
+// next start vector = sum_k coef[k] V[k], k < m (the dominant Ritz vector: linalg.py:369-371)
+extern "C" int amgb_arnoldi_combine(amgb_arnoldi *a, const double *coef, int32_t m)
+{
+    if (a == nullptr || coef == nullptr) return fail(AMGB_EINVAL, "null argument");
+    if (m < 1 || m > a->maxiter) return fail(AMGB_EINVAL, "arnoldi: m out of range");
+    amgb_hierarchy *h = a->pool;
+    CK(cudaSetDevice(h->device));
+    h->rt.activate();
+    RET(h->scale_to(a->w, coef[0], a->v(0), a->n));
+    for (int k = 1; k < m; k++) RET(h->axpby(coef[k], a->v(k), 1.0, a->w, a->n));
+    RET(h->copy_vec(a->v(0), a->w, a->n));
+    a->have_start = true;
+    return AMGB_OK;
+}
+
 // HOST helper (no CUDA): the tile list the engine would build for a CSR row-pointer array under the
 // geometry (T entries, RMAX rows per tile) with G lanes per row and optional row breaks (e.g. wave
 // boundaries, n_breaks+1 ascending entries starting at 0).  row0/nz0 receive n_tiles+1 descriptors (sentinel

@@ -38,9 +38,14 @@ def _unpack_arg(v):
 def rho_D_inv_A(A):
     """(approx.) spectral radius of D^-1 A, cached on the matrix (smoothing.py:372-400)."""
     if not hasattr(A, "rho_D_inv"):
+        import os
         D_inv = get_diagonal(A, inv=True)
-        D_inv_A = sparse.dia_array((D_inv, 0), shape=(len(D_inv), len(D_inv))) @ sparse.csr_array(A)
-        A.rho_D_inv = approximate_spectral_radius(D_inv_A)
+        if os.environ.get("AMGB_GPU_RHO") == "1" and A.format == "csr":
+            # Arnoldi rounds on the device, D^-1 applied as a row scaling (no scaled copy of A is formed)
+            A.rho_D_inv = approximate_spectral_radius(A, row_scale=D_inv, where="gpu")
+        else:
+            D_inv_A = sparse.dia_array((D_inv, 0), shape=(len(D_inv), len(D_inv))) @ sparse.csr_array(A)
+            A.rho_D_inv = approximate_spectral_radius(D_inv_A, where="host")
     return A.rho_D_inv
 
 

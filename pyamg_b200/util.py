@@ -41,11 +41,58 @@ def get_block_diag(A, blocksize, inv_flag=True):
     return np.ascontiguousarray(block_diag)
 
 
-def approximate_spectral_radius(A, maxiter=15, restarts=5, seed=20260922):
+def _gpu_rho_enabled(where):
+    import os
+    if where is None:
+        where = "gpu" if os.environ.get("AMGB_GPU_RHO") == "1" else "host"
+    if where not in ("host", "gpu"):
+        raise ValueError("where must be 'host' or 'gpu'")
+    return where == "gpu"
+
+
+def _approximate_spectral_radius_gpu(A, row_scale, v0, maxiter, restarts):
+    """The rounds below on the device (amgb_arnoldi_*): the operator is uploaded once, every round
+    of modified-Gram-Schmidt Arnoldi runs without a host round trip, only the small Hessenberg matrix comes back for
+    the eigen-decomposition that picks the restart vector (a combination of the resident basis)."""
+    import ctypes
+    from . import _engine as E
+    E.require_gpu()
+    L = E.lib()
+    keep = []
+    M = E.as_matrix(sparse.csr_array(A), keep)
+    sc = None if row_scale is None else np.ascontiguousarray(row_scale, dtype=np.float64)
+    hdl = ctypes.c_void_p()
+    E.check(L.amgb_arnoldi_create(0, M, None if sc is None else E.f64p(sc), int(maxiter), ctypes.byref(hdl)))
+    try:
+        H = np.zeros((maxiter + 1, maxiter))
+        m = ctypes.c_int32(0)
+        rho = 0.0
+        start = np.ascontiguousarray(v0, dtype=np.float64)
+        for _ in range(restarts + 1):
+            E.check(L.amgb_arnoldi_run(hdl, None if start is None else E.f64p(start), 1e-12, E.f64p(H.reshape(-1)),
+                                       ctypes.byref(m)))
+            if m.value == 0:
+                break
+            ev, evec = np.linalg.eig(H[:m.value, :m.value])
+            k = int(np.argmax(np.abs(ev)))
+            rho = float(np.abs(ev[k]))
+            coef = np.ascontiguousarray(np.real(evec[:, k]), dtype=np.float64)
+            E.check(L.amgb_arnoldi_combine(hdl, E.f64p(coef), m.value))
+            start = None
+            if m.value < maxiter:
+                break
+        return rho
+    finally:
+        L.amgb_arnoldi_destroy(hdl)
+
+
+def approximate_spectral_radius(A, maxiter=15, restarts=5, seed=20260922, row_scale=None, where=None):
     """Largest |Ritz value| of a restarted Arnoldi process started from a seeded random vector.
 
-    Same estimator family as the reference (Arnoldi, 15 steps, 5 restarts); the start vector is
-    seeded here, so the value is reproducible (the reference's is not: SURVEY.md hazard 2).
+    Same estimator family as the reference (Arnoldi, 15 steps, 5 restarts; pyamg/util/linalg.py:255-383); the start
+    vector is seeded here, so the value is reproducible (the reference's is not: SURVEY.md hazard 2).
+    ``row_scale``: estimate rho(diag(row_scale) A) without forming the scaled matrix.  ``where='gpu'`` (or
+    ``AMGB_GPU_RHO=1``) runs the Arnoldi rounds on the device -- same algorithm, values equal to rounding.
     """
     A = sparse.csr_array(A) if not sparse.issparse(A) else A
     n = A.shape[0]
@@ -54,6 +101,10 @@ def approximate_spectral_radius(A, maxiter=15, restarts=5, seed=20260922):
     rng = np.random.default_rng(seed)
     v0 = rng.random(n)
     maxiter = int(min(maxiter, n))
+    if _gpu_rho_enabled(where):
+        return _approximate_spectral_radius_gpu(A, row_scale, v0, maxiter, restarts)
+    if row_scale is not None:
+        A = sparse.dia_array((np.asarray(row_scale), 0), shape=(n, n)) @ sparse.csr_array(A)
     rho = 0.0
     for _ in range(restarts + 1):
         V = np.zeros((maxiter + 1, n))

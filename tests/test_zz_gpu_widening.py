@@ -259,3 +259,35 @@ def test_host_setup_with_gpu_galerkin_builds_the_same_hierarchy(monkeypatch):
     assert len(ref.levels) == len(gpu.levels)
     for a, b in zip(ref.levels, gpu.levels):
         assert _bitwise_equal(a.A, b.A)
+
+
+# ------------------------------------------------------------------ spectral-radius estimates on the GPU (8(f)-4)
+def test_gpu_arnoldi_matches_the_host_estimator():
+    """amgb_arnoldi_* (restarted modified-Gram-Schmidt Arnoldi with the basis resident in HBM) vs the host
+    estimator of pyamg_b200.util (same algorithm as the reference's approximate_spectral_radius,
+    pyamg/util/linalg.py:255-383): rho(A) and rho(D^-1 A) equal to rounding, incl. an exhausted Krylov space."""
+    from pyamg_b200.gallery import poisson, stencil_grid, diffusion_stencil_2d
+    from pyamg_b200.util import approximate_spectral_radius, get_diagonal
+    for A in (poisson((20, 20)), stencil_grid(diffusion_stencil_2d(0.001, np.pi / 6, "FE"), (24, 24)), poisson((7,)),
+              poisson((6, 6, 6))):
+        A = sp.csr_array(A)
+        D = get_diagonal(A, inv=True)
+        for scale in (None, D):
+            rh = approximate_spectral_radius(A, row_scale=scale, where="host")
+            rg = approximate_spectral_radius(A, row_scale=scale, where="gpu")
+            assert abs(rh - rg) <= 1e-11 * rh
+    assert approximate_spectral_radius(poisson((20, 20)), where="gpu") == pytest.approx(8.0, rel=1e-2)
+
+
+def test_sa_setup_with_gpu_spectral_radius_builds_the_same_hierarchy(monkeypatch):
+    """Jacobi's omega and the prolongation smoother's rho from the device estimate: operators equal to 1e-12."""
+    from pyamg_b200.aggregation import smoothed_aggregation_solver
+    from pyamg_b200.gallery import poisson
+    sm = ("jacobi", {"omega": 4.0 / 3.0})
+    ref = smoothed_aggregation_solver(poisson((24, 24)), presmoother=sm, postsmoother=sm)
+    monkeypatch.setenv("AMGB_GPU_RHO", "1")
+    gpu = smoothed_aggregation_solver(poisson((24, 24)), presmoother=sm, postsmoother=sm)
+    assert len(ref.levels) == len(gpu.levels)
+    for a, b in zip(ref.levels[:-1], gpu.levels[:-1]):
+        assert a.presmoother.keywords["omega"] == pytest.approx(b.presmoother.keywords["omega"], rel=1e-12)
+        assert abs(a.P - b.P).max() <= 1e-12 * abs(a.P).max()
