@@ -4,6 +4,7 @@
 
   * Galerkin product R A P: GPU SpGEMM (amgb_host_csr_matmat, host buffers in/out) vs SciPy on the host, bitwise
     comparison of the results included;
+  * rho(D^-1 A): restarted Arnoldi on the host vs amgb_arnoldi_* (basis resident in HBM);
   * smoothers: V-cycles/s of the same RS hierarchy with multi-colour GS, Chebyshev(3), CF-Jacobi;
   * Krylov: solve(accel='cg' | 'gmres' | 'fgmres') to 1e-8, iterations and wall time.
 """
@@ -45,6 +46,18 @@ def main():
         print(json.dumps({"item": "galerkin", "level": l, "n": Al.shape[0], "nnz_A": int(Al.nnz), "nnz_C": int(Cs.nnz),
                           "scipy_s": round(t_host, 3), "gpu_e2e_s": round(t_gpu, 3), "bitwise_equal": bool(same)}),
               flush=True)
+    # ---- spectral-radius estimate rho(D^-1 A): host Arnoldi vs resident-basis Arnoldi on the device
+    from pyamg_b200.util import approximate_spectral_radius, get_diagonal
+    A0 = sp.csr_array(ml.levels[0].A)
+    D = get_diagonal(A0, inv=True)
+    t0 = time.perf_counter()
+    rh = approximate_spectral_radius(A0, row_scale=D, where="host")
+    t_host = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    rg = approximate_spectral_radius(A0, row_scale=D, where="gpu")
+    t_gpu = time.perf_counter() - t0
+    print(json.dumps({"item": "rho_Dinv_A", "n": A0.shape[0], "host_s": round(t_host, 3), "gpu_e2e_s": round(t_gpu, 3),
+                      "rel_diff": float(abs(rh - rg) / rh)}), flush=True)
     # ---- smoothers
     n = A.shape[0]
     b = np.random.default_rng(20260922).random(n)
