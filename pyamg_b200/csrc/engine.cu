@@ -2072,408 +2072,7 @@ extern "C" int amgb_solve_device(amgb_hierarchy *h, const double *b_dev, double 
     return AMGB_OK;
 }
 
-// ------------------------------------------------------------------------------------------
-// GPU-resident preconditioned CG: ml.solve(accel='cg') with every vector in HBM.
-// Restates pyamg/krylov/_cg.py:97-196 (criteria 'rr': stop when ||r|| < tol ||b||; r recomputed from
-// b - A x every 8th step, updated by r -= alpha A p otherwise; aborts on p'Ap < 0 or r'z < 0) with
-// M = one multigrid cycle from x0 = 0 (MultilevelSolver.aspreconditioner, multilevel.py:355-396).
-// r lives in the level-0 rhs buffer (the cycle never writes it), z is the cycle's level-0 iterate.
-// Dot products are two-stage with a fixed grid (bit-reproducible); their values are read on the host
-// once per iteration -- two tiny synchronisations against a ~10 ms cycle.
-// ------------------------------------------------------------------------------------------
-static int dev_dot(amgb_hierarchy *h, const double *x, const double *y, long long n, double *out_host)
-{
-    dot_partials_kernel<<<sumsq_blocks(), 256, 0, h->stream>>>(x, y, n, h->sumsq_parts);
-    CK(cudaGetLastError());
-    reduce_partials_kernel<<<1, 1024, 0, h->stream>>>(h->sumsq_parts, sumsq_blocks(), h->norms2);
-    CK(cudaGetLastError());
-    h->launches += 2;
-    CK(cudaMemcpyAsync(h->norm_host, h->norms2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    *out_host = h->norm_host[0];
-    return AMGB_OK;
-}
-
-static int dev_axpby(amgb_hierarchy *h, double a, const double *x, double b, double *y, long long n)
-{
-    if (n <= 0) return AMGB_OK;
-    const long long grid = std::min<long long>((n + 255) / 256, (long long)g_num_sms * 16);
-    axpby_kernel<<<(unsigned)grid, 256, 0, h->stream>>>(a, x, b, y, n);
-    CK(cudaGetLastError());
-    h->launches++;
-    return AMGB_OK;
-}
-
-extern "C" int amgb_solve_cg(amgb_hierarchy *h, const double *b_host, double *x_host, double tol, int32_t maxiter,
-                             int32_t cycle, int32_t flags, double *residuals, int32_t *n_residuals, int32_t *info)
-{
-    RET(check_cycle_args(h, cycle, 1));
-    if (b_host == nullptr || x_host == nullptr) return fail(AMGB_EINVAL, "null host vector");
-    if (maxiter < 1) return fail(AMGB_EINVAL, "Number of iterations must be positive");    // _cg.py:95-96
-    CK(cudaSetDevice(h->device));
-    Level &L0 = h->levels[0];
-    const long long n = L0.A.n_rows;
-    cudaStream_t s = h->stream;
-    h->launches = 0;
-    if (h->kry[0] == nullptr)
-        for (int k = 0; k < 4; k++) RET(h->dalloc(&h->kry[k], n + 2));
-    double *xk = h->kry[0], *p = h->kry[1], *Ap = h->kry[2], *bk = h->kry[3];
-    double *r = L0.b;                                     // CG residual = rhs of the preconditioner
-    // b -> bk, x0 -> xk (level-0 numbering)
-    RET(load_level0(h, b_host, (flags & AMGB_FLAG_X0_ZERO) ? nullptr : x_host, cudaMemcpyHostToDevice));
-    CK(cudaMemcpyAsync(bk, L0.b, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(xk, L0.x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
-    auto precond = [&]() -> int {                         // z = M r: one cycle from zero on (L0.x, L0.b = r)
-        L0.x = L0.x_home;
-        RET(h->launch_count_fill(L0.x, n));
-        return h->one_iteration(cycle, 1);
-    };
-    double normb2 = 0, rz = 0, rr = 0, pAp = 0;
-    RET(dev_dot(h, bk, bk, n, &normb2));
-    double normb = std::sqrt(normb2);
-    if (normb == 0.0) normb = 1.0;
-    RET(h->spmv(OP_RESID, L0.A, xk, bk, r));              // r = b - A x        (:99)
-    RET(precond());                                       // z = M r            (:100)
-    CK(cudaMemcpyAsync(p, L0.x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));   // p = z (:101)
-    RET(dev_dot(h, r, L0.x, n, &rz));                     // rz = <r, z>        (:102)
-    RET(dev_dot(h, r, r, n, &rr));
-    std::vector<double> res;
-    res.push_back(std::sqrt(rr));                         // residuals[:] = [normr] (:104-106)
-    const double rtol = tol * normb;                      // criteria 'rr'      (:114-115)
-    int it = 0, status = -2;
-    if (res.back() < rtol) status = 0;                    // :133-134
-    while (status == -2) {
-        RET(h->spmv(OP_SPMV, L0.A, p, nullptr, Ap));      // Ap = A p           (:142)
-        const double rz_old = rz;
-        RET(dev_dot(h, Ap, p, n, &pAp));                  // curvature of A     (:145-148)
-        if (pAp < 0.0) { status = -1; break; }
-        const double alpha = rz / pAp;                    // :150
-        RET(dev_axpby(h, alpha, p, 1.0, xk, n));          // x += alpha p       (:151)
-        if ((it % 8) != 0 && it > 0) {
-            RET(dev_axpby(h, -alpha, Ap, 1.0, r, n));     // r -= alpha Ap      (:153-154)
-        } else {
-            RET(h->spmv(OP_RESID, L0.A, xk, bk, r));      // r = b - A x        (:155-156)
-        }
-        RET(precond());                                   // z = M r            (:158)
-        RET(dev_dot(h, r, L0.x, n, &rz));                 // :159
-        if (rz < 0.0) { status = -1; break; }             // curvature of M     (:161-163)
-        const double beta = rz / rz_old;                  // :165
-        RET(dev_axpby(h, 1.0, L0.x, beta, p, n));         // p = beta p + z     (:166-167)
-        it++;
-        RET(dev_dot(h, r, r, n, &rr));
-        res.push_back(std::sqrt(rr));                     // :171-174
-        if (res.back() < rtol) { status = 0; break; }     // :190-191
-        if (it == maxiter) { status = it; break; }        // :193-194
-    }
-    // x out (original numbering)
-    CK(cudaMemcpyAsync(L0.x_home, xk, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
-    L0.x = L0.x_home;
-    RET(store_level0(h, x_host, cudaMemcpyDeviceToHost));
-    CK(cudaStreamSynchronize(s));
-    if (residuals != nullptr)
-        for (size_t k = 0; k < res.size() && k < (size_t)maxiter + 1; k++) residuals[k] = res[k];
-    if (n_residuals != nullptr) *n_residuals = (int32_t)res.size();
-    if (info != nullptr) *info = status;
-    h->last_launches = h->launches;
-    return AMGB_OK;
-}
-
-// ------------------------------------------------------------------------------------------
-// GPU-resident Householder GMRES and flexible GMRES: ml.solve(accel='gmres' | 'fgmres') with
-// every long vector in HBM.  Restates pyamg/krylov/_gmres_householder.py:21-360 (what pyamg.krylov.gmres resolves
-// to, LEFT preconditioning, stop on the preconditioned residual vs ||M b||) and pyamg/krylov/_fgmres.py:17-345
-// (RIGHT preconditioning, the preconditioned directions are stored) with the native helpers of
-// pyamg/amg_core/krylov.h (apply_householders :37-62, householder_hornerscheme :106-135, apply_givens :158-187);
-// M = one multigrid cycle from a zero guess (aspreconditioner, multilevel.py:355-396).
-// The reflectors single out the LEADING entries of the vectors, so the Krylov vectors live in the ORIGINAL
-// numbering; they are gathered into the level-0 (wave-major) numbering around the SpMV + cycle.  The small
-// Hessenberg / Givens / back-substitution work stays on the host (<= 41 x 41); per inner iteration the host reads
-// max_inner + 1 leading entries of v and two scalars.
-// ------------------------------------------------------------------------------------------
-namespace {
-struct Gmres {
-    amgb_hierarchy *h;
-    long long n, npad;
-    int cycle;
-    cudaStream_t s;
-    Level &L0;
-    Gmres(amgb_hierarchy *h_, int cyc) : h(h_), n(h_->levels[0].A.n_rows), npad(((h_->levels[0].A.n_rows + 2 + 31) / 32) * 32),
-                                         cycle(cyc), s(h_->stream), L0(h_->levels[0]) {}
-    double *W(int j) const { return h->gm_W + (size_t)j * npad; }
-    double *Z(int j) const { return h->gm_Z + (size_t)j * npad; }
-    int grid() const { return (int)std::min<long long>((n + 255) / 256, (long long)g_num_sms * 16); }
-
-    int to_level(const double *src, double *dst)      // original numbering -> level-0 numbering
-    {
-        if (h->order0 == nullptr) return h->copy_vec(dst, src, n);
-        return h->gather(src, h->order0, dst, n);
-    }
-    int from_level(const double *src, double *dst)
-    {
-        if (h->pos0 == nullptr) return h->copy_vec(dst, src, n);
-        return h->gather(src, h->pos0, dst, n);
-    }
-    int precond()                                      // L0.x <- M L0.b : one cycle from zero
-    {
-        L0.x = L0.x_home;
-        RET(h->launch_count_fill(L0.x, n));
-        return h->one_iteration(cycle, 1);
-    }
-    int read(const double *dev, double *host, int count)
-    {
-        CK(cudaMemcpyAsync(h->norm_host, dev, sizeof(double) * (size_t)std::min(count, 2), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        for (int k = 0; k < std::min(count, 2); k++) host[k] = h->norm_host[k];
-        return AMGB_OK;
-    }
-    int dot(const double *x, const double *y, double *out)
-    {
-        RET(h->dot_to(x, y, n, h->gm_s));
-        return read(h->gm_s, out, 1);
-    }
-    int sumsq_from(const double *x, long long start, double *out)
-    {
-        sumsq_from_partials_kernel<<<sumsq_blocks(), 256, 0, s>>>(x, start, n, h->sumsq_parts);
-        CK(cudaGetLastError());
-        reduce_partials_kernel<<<1, 1024, 0, s>>>(h->sumsq_parts, sumsq_blocks(), h->gm_s);
-        CK(cudaGetLastError());
-        h->launches += 2;
-        return read(h->gm_s, out, 1);
-    }
-    // z <- (I - 2 w w^T) z with the inner product kept on the device (krylov.h:48-56: alpha = <w, z>; alpha *= -2)
-    int reflect(const double *w, double *z)
-    {
-        RET(h->dot_to(w, z, n, h->gm_s));
-        return h->axpy_ratio(z, w, h->gm_s, h->gm_s + 3, -2.0, n);       // gm_s[3] == 1.0
-    }
-    int make_w(double *w, const double *v, long long k1, double alpha)
-    {
-        hh_make_w_kernel<<<grid(), 256, 0, s>>>(w, v, k1, alpha, n);
-        CK(cudaGetLastError());
-        h->launches++;
-        double nn = 0.0;
-        RET(dot(w, w, &nn));
-        div_kernel<<<grid(), 256, 0, s>>>(w, std::sqrt(nn), n);
-        CK(cudaGetLastError());
-        h->launches++;
-        return AMGB_OK;
-    }
-};
-
-// LAPACK dlartg (what scipy's get_lapack_funcs(['lartg']) calls): c, s, r with [c s; -s c] [f; g] = [r; 0]
-void lartg(double f, double g, double *c, double *sn, double *r)
-{
-    if (g == 0.0) { *c = 1.0; *sn = 0.0; *r = f; return; }
-    if (f == 0.0) { *c = 0.0; *sn = std::copysign(1.0, g); *r = std::fabs(g); return; }
-    const double d = std::sqrt(f * f + g * g);
-    *c = std::fabs(f) / d;
-    *r = std::copysign(d, f);
-    *sn = g / *r;
-}
-}  // namespace
-
-extern "C" int amgb_solve_gmres(amgb_hierarchy *h, const double *b_host, double *x_host, double tol, int32_t restart,
-                                int32_t maxiter, int32_t cycle, int32_t flags, double *residuals,
-                                int32_t max_residuals, int32_t *n_residuals, int32_t *info)
-{
-    RET(check_cycle_args(h, cycle, 1));
-    if (b_host == nullptr || x_host == nullptr) return fail(AMGB_EINVAL, "null host vector");
-    if (restart < 0) return fail(AMGB_EINVAL, "restart < 0");
-    CK(cudaSetDevice(h->device));
-    Gmres G(h, cycle);
-    const long long n = G.n;
-    if (n < 2) return fail(AMGB_EINVAL, "gmres: n < 2 is the caller's closed form (b / A[0,0])");
-    const bool flex = (flags & AMGB_FLAG_FLEXIBLE) != 0;
-    // _gmres_householder.py:129-149
-    long long max_outer, max_inner;
-    if (restart > 0) {
-        max_outer = maxiter > 0 ? maxiter : 1;
-        max_inner = std::min<long long>(restart, n);
-    } else {
-        max_outer = 1;
-        max_inner = maxiter > 0 ? std::min<long long>(maxiter, n) : std::min<long long>(n, 40);
-    }
-    const int mi = (int)max_inner;
-    cudaStream_t s = h->stream;
-    h->launches = 0;
-    if (h->gm_W == nullptr || h->gm_inner < mi || (flex && !h->gm_flex)) {
-        // (re)allocation: earlier, smaller buffers stay in the pool until the hierarchy is destroyed
-        RET(h->dalloc(&h->gm_W, (long long)(mi + 1) * G.npad));
-        if (flex) RET(h->dalloc(&h->gm_Z, (long long)mi * G.npad));
-        if (h->gm_s == nullptr) {
-            for (int k = 0; k < 4; k++) RET(h->dalloc(&h->gm_vec[k], G.npad));
-            for (int k = 0; k < 3; k++) RET(h->dalloc(&h->gm_lvl[k], G.npad));
-            RET(h->dalloc(&h->gm_s, 8));
-            const double init[4] = {0.0, 0.0, 0.0, 1.0};
-            CK(cudaMemcpy(h->gm_s, init, sizeof init, cudaMemcpyHostToDevice));
-        }
-        h->gm_inner = mi;
-        h->gm_flex = h->gm_flex || flex;
-    }
-    if (cycle == AMGB_CYCLE_AMLI) RET(h->prepare_amli());
-    double *v = h->gm_vec[0], *xk = h->gm_vec[1], *bk = h->gm_vec[2], *upd = h->gm_vec[3];
-    double *b_lvl = h->gm_lvl[0], *lin = h->gm_lvl[1], *lout = h->gm_lvl[2];
-    Level &L0 = G.L0;
-    const size_t vbytes = sizeof(double) * (size_t)n;
-    CK(cudaMemcpyAsync(bk, b_host, vbytes, cudaMemcpyHostToDevice, s));
-    if (flags & AMGB_FLAG_X0_ZERO) RET(h->launch_count_fill(xk, n));
-    else CK(cudaMemcpyAsync(xk, x_host, vbytes, cudaMemcpyHostToDevice, s));
-    RET(G.to_level(bk, b_lvl));
-
-    // r = b - A x (then r = M r for the left-preconditioned method) -> the first reflector's storage W(0)
-    auto residual_to_w0 = [&]() -> int {
-        RET(G.to_level(xk, lin));
-        if (flex) {
-            RET(h->spmv(OP_RESID, L0.A, lin, b_lvl, lout));
-            return G.from_level(lout, G.W(0));
-        }
-        RET(h->spmv(OP_RESID, L0.A, lin, b_lvl, L0.b));
-        RET(G.precond());
-        return G.from_level(L0.x, G.W(0));
-    };
-    std::vector<double> res;
-    double t = 0.0, normr = 0.0;
-    RET(residual_to_w0());
-    RET(G.dot(G.W(0), G.W(0), &t));
-    normr = std::sqrt(t);
-    res.push_back(normr);                                                   // :165-167
-    double scale = 1.0;                                                     // :169-174 / _fgmres.py:171-174
-    RET(G.dot(bk, bk, &t));
-    if (t != 0.0) {
-        if (flex) {
-            scale = std::sqrt(t);
-        } else {
-            RET(h->copy_vec(L0.b, b_lvl, n));
-            RET(G.precond());
-            RET(G.from_level(L0.x, v));
-            RET(G.dot(v, v, &t));
-            scale = std::sqrt(t);
-        }
-    }
-    int status = -2, niter = 0;
-    if (normr < tol * scale) status = 0;                                    // :177-178
-    const int m2 = (int)std::min<long long>(n, (long long)mi + 1);          // leading entries of v the host needs
-    std::vector<double> H((size_t)mi * mi), Q((size_t)4 * mi), g((size_t)mi + 1), hv((size_t)m2), y((size_t)mi);
-    double *hv_pinned = nullptr;
-    CK(cudaHostAlloc((void **)&hv_pinned, sizeof(double) * (size_t)m2, cudaHostAllocDefault));
-    struct PinGuard { double *p; ~PinGuard() { if (p) cudaFreeHost(p); } } pin_guard{hv_pinned};
-
-    for (long long outer = 0; outer < max_outer && status == -2; outer++) {
-        // first reflector from r: w = r; w[0] += sign(r[0]) ||r||; w /= ||w||          (:186-192)
-        double r0 = 0.0;
-        RET(G.read(G.W(0), &r0, 1));
-        const double beta = (r0 == 0.0 ? 1.0 : r0 / std::fabs(r0)) * normr;
-        RET(G.make_w(G.W(0), G.W(0), 0, beta));
-        CK(cudaMemsetAsync(G.W(1), 0, sizeof(double) * (size_t)mi * (size_t)G.npad, s));   // W = zeros (:203)
-        std::fill(H.begin(), H.end(), 0.0);
-        std::fill(Q.begin(), Q.end(), 0.0);
-        std::fill(g.begin(), g.end(), 0.0);
-        g[0] = -beta;                                                        // :208-209
-        int inner = 0;
-        for (inner = 0; inner < mi; inner++) {
-            hh_unit_reflect_kernel<<<G.grid(), 256, 0, s>>>(v, G.W(inner), inner, n);      // :214-215
-            CK(cudaGetLastError());
-            h->launches++;
-            for (int j = inner - 1; j >= 0; j--) RET(G.reflect(G.W(j), v));                 // :219
-            if (flex) {                                                      // _fgmres.py:221-230
-                RET(G.to_level(v, L0.b));
-                RET(G.precond());
-                RET(G.from_level(L0.x, G.Z(inner)));
-                RET(h->spmv(OP_SPMV, L0.A, L0.x, nullptr, lout));
-                RET(G.from_level(lout, v));
-            } else {                                                         // :222-225
-                RET(G.to_level(v, lin));
-                RET(h->spmv(OP_SPMV, L0.A, lin, nullptr, L0.b));
-                RET(G.precond());
-                RET(G.from_level(L0.x, v));
-            }
-            for (int j = 0; j <= inner; j++) RET(G.reflect(G.W(j), v));                     // :235
-            CK(cudaMemcpyAsync(hv_pinned, v, sizeof(double) * (size_t)m2, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            for (int k = 0; k < m2; k++) hv[(size_t)k] = hv_pinned[k];
-            if (inner != n - 1) {                                            // :244-263
-                double alpha = 0.0;
-                RET(G.sumsq_from(v, inner + 1, &alpha));
-                alpha = std::sqrt(alpha);
-                if (alpha != 0.0) {
-                    const double v0 = hv[(size_t)inner + 1];
-                    alpha = (v0 == 0.0 ? 1.0 : v0 / std::fabs(v0)) * alpha;
-                    if (inner < mi - 1) RET(G.make_w(G.W(inner + 1), v, inner + 1, alpha));
-                    hv[(size_t)inner + 1] = -alpha;
-                    for (int k = inner + 2; k < m2; k++) hv[(size_t)k] = 0.0;
-                }
-            }
-            for (int rot = 0; rot < inner; rot++) {                          // apply_givens (krylov.h:171-186)
-                const double xt = hv[(size_t)rot];
-                hv[(size_t)rot] = Q[(size_t)4 * rot] * xt + Q[(size_t)4 * rot + 1] * hv[(size_t)rot + 1];
-                hv[(size_t)rot + 1] = Q[(size_t)4 * rot + 2] * xt + Q[(size_t)4 * rot + 3] * hv[(size_t)rot + 1];
-            }
-            if (inner != n - 1 && hv[(size_t)inner + 1] != 0.0) {            // :276-291
-                double c, sn, rr;
-                lartg(hv[(size_t)inner], hv[(size_t)inner + 1], &c, &sn, &rr);
-                double *q = &Q[(size_t)4 * inner];
-                q[0] = c; q[1] = sn; q[2] = -sn; q[3] = c;
-                const double g0 = g[(size_t)inner], g1 = g[(size_t)inner + 1];
-                g[(size_t)inner] = c * g0 + sn * g1;
-                g[(size_t)inner + 1] = -sn * g0 + c * g1;
-                hv[(size_t)inner] = c * hv[(size_t)inner] + sn * hv[(size_t)inner + 1];
-                hv[(size_t)inner + 1] = 0.0;
-            }
-            for (int k = 0; k < mi; k++) H[(size_t)k * mi + inner] = hv[(size_t)k];         // H[:, inner] (:295)
-            if (!flex) niter++;                                              // :297
-            if (inner < mi - 1) {                                            // :301-305
-                normr = std::fabs(g[(size_t)inner + 1]);
-                if (normr < tol * scale) break;                              // (fgmres: before niter += 1)
-                res.push_back(normr);
-            }
-            if (flex) niter++;                                               // _fgmres.py:306
-        }
-        if (inner == mi) inner = mi - 1;                                     // Python's loop variable after a full loop
-        const int k = inner + 1;
-        for (int i = k - 1; i >= 0; i--) {                                   // solve H[0:k,0:k] y = g[0:k] (upper triangular)
-            double acc = g[(size_t)i];
-            for (int j = i + 1; j < k; j++) acc -= H[(size_t)i * mi + j] * y[(size_t)j];
-            y[(size_t)i] = acc / H[(size_t)i * mi + i];
-        }
-        if (flex) {                                                          // update = Z[:, 0:k] y (_fgmres.py:321)
-            RET(h->scale_to(upd, y[0], G.Z(0), n));
-            for (int j = 1; j < k; j++) RET(h->axpby(y[(size_t)j], G.Z(j), 1.0, upd, n));
-        } else {                                                             // householder_hornerscheme (:321-322)
-            RET(h->launch_count_fill(upd, n));
-            for (int j = k - 1; j >= 0; j--) {
-                add_at_kernel<<<1, 1, 0, s>>>(upd, j, y[(size_t)j]);
-                CK(cudaGetLastError());
-                h->launches++;
-                RET(G.reflect(G.W(j), upd));
-            }
-        }
-        RET(h->axpby(1.0, upd, 1.0, xk, n));                                 // x = x + update (:324)
-        RET(residual_to_w0());                                               // :325-328
-        RET(G.dot(G.W(0), G.W(0), &t));
-        normr = std::sqrt(t);
-        res.push_back(normr);                                                // :335-336
-        maxratio_partials_kernel<<<sumsq_blocks(), 256, 0, s>>>(upd, xk, n, h->sumsq_parts);   // :339-346
-        CK(cudaGetLastError());
-        reduce_max_kernel<<<1, 1024, 0, s>>>(h->sumsq_parts, sumsq_blocks(), h->gm_s + 1);
-        CK(cudaGetLastError());
-        h->launches += 2;
-        double change = 0.0;
-        RET(G.read(h->gm_s + 1, &change, 1));
-        if (change >= 0.0 && change < 1e-12) { status = -1; break; }
-        if (normr < tol * scale) { status = 0; break; }                     // :349-350
-    }
-    if (status == -2) status = niter;                                        // :354
-    CK(cudaMemcpyAsync(x_host, xk, vbytes, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    L0.x = L0.x_home;
-    const int nres = (int)std::min<size_t>(res.size(), (size_t)std::max(max_residuals, 0));
-    if (residuals != nullptr)
-        for (int k = 0; k < nres; k++) residuals[k] = res[(size_t)k];
-    if (n_residuals != nullptr) *n_residuals = (int32_t)res.size();
-    if (info != nullptr) *info = status;
-    h->last_launches = h->launches;
-    return AMGB_OK;
-}
+#include "abi_krylov.cuh"      // amgb_solve_cg, amgb_solve_gmres
 
 // One un-graphed cycle with a CUDA-event pair around every operator launch of the cycle.
 // rec[k*6 + {0..5}] = level, op (0 spmv/R, 1 residual, 2 prolong+add, 3 jacobi, 4 gs wave, 5 block jacobi,
@@ -2510,807 +2109,5 @@ extern "C" int amgb_profile_cycle(amgb_hierarchy *h, int32_t cycle, double *rec,
     return AMGB_OK;
 }
 
-// ------------------------------------------------------------------------------------------
-// C ABI (1b): one resident operator with the tile kernels -- the building block of the multi-GPU layer
-// (pyamg_b200/dist.py) and of Krylov-style callers that keep their vectors on the device.
-// ------------------------------------------------------------------------------------------
-struct amgb_operator {
-    amgb_hierarchy *pool = nullptr;      // owns the device allocations
-    DevCsr M;
-    WaveSchedule waves;                  // optional contiguous wave ranges (Gauss-Seidel)
-    double *partials = nullptr;
-};
-
-extern "C" int amgb_operator_create(int device, const amgb_matrix *Min, const int64_t *wave_ptr, int32_t n_waves,
-                                    void *stream, amgb_operator **out)
-{
-    if (out == nullptr) return fail(AMGB_EINVAL, "out is null");
-    *out = nullptr;
-    amgb_hierarchy *pool = nullptr;
-    RET(amgb_hierarchy_create(device, &pool));
-    std::unique_ptr<amgb_operator> op(new amgb_operator());
-    op->pool = pool;
-    auto bail = [&](int rc) { amgb_hierarchy_destroy(pool); return rc; };
-    HostCsr H;
-    int rc = to_host_csr(Min, H, "M");
-    if (rc != AMGB_OK) return bail(rc);
-    if (stream != nullptr) pool->stream = (cudaStream_t)stream;
-    else {
-        if (cudaStreamCreateWithFlags(&pool->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(AMGB_ECUDA, "stream"));
-        pool->own_stream = true;
-    }
-    if (wave_ptr != nullptr && n_waves > 0) {
-        WaveSchedule &W = op->waves;
-        W.ptr.assign(wave_ptr, wave_ptr + n_waves + 1);
-        if (W.ptr.front() != 0 || W.ptr.back() > H.n_rows) return bail(fail(AMGB_EINVAL, "wave_ptr out of range"));
-        for (int w = 0; w < n_waves; w++)
-            if (W.ptr[(size_t)w + 1] < W.ptr[(size_t)w]) return bail(fail(AMGB_EINVAL, "wave_ptr not monotone"));
-        W.contiguous = true;
-        W.nnz.assign((size_t)n_waves, 0);
-        for (int w = 0; w < n_waves; w++)
-            W.nnz[(size_t)w] = H.Ap[(size_t)W.ptr[(size_t)w + 1]] - H.Ap[(size_t)W.ptr[(size_t)w]];
-        std::vector<long long> breaks(W.ptr);
-        if (breaks.back() != H.n_rows) breaks.push_back(H.n_rows);
-        rc = pool->upload_csr(H, op->M, &breaks, &W.tile_ptr);
-        if (!pool->use_tiles) W.tile_ptr.clear();
-    } else {
-        rc = pool->upload_csr(H, op->M);
-    }
-    if (rc != AMGB_OK) return bail(rc);
-    rc = pool->dalloc(&op->partials, std::max<long long>(pool->partials_len(op->M), 1));
-    if (rc != AMGB_OK) return bail(rc);
-    *out = op.release();
-    return AMGB_OK;
-}
-
-extern "C" void amgb_operator_destroy(amgb_operator *op)
-{
-    if (op == nullptr) return;
-    amgb_hierarchy_destroy(op->pool);
-    delete op;
-}
-
-// kind: 0 y = M x | 1 y = b - M x (norm2_out, if given, receives |y|^2) | 2 y += M x |
-//       3 y = jacobi(x; b, omega), r (optional) = b - M x | 4 Gauss-Seidel on wave `wave` of y (= x) in place.
-// All pointers are DEVICE pointers; x must have M.n_cols entries (+2 readable doubles of padding).
-extern "C" int amgb_operator_apply(amgb_operator *op, int32_t kind, const double *x, const double *b, double *y,
-                                   double *r, double omega, double *norm2_out, int32_t wave)
-{
-    if (op == nullptr) return fail(AMGB_EINVAL, "null operator");
-    amgb_hierarchy *h = op->pool;
-    CK(cudaSetDevice(h->device));
-    h->rt.activate();
-    if (kind < 0 || kind > 4) return fail(AMGB_EINVAL, "unknown operator kind");
-    if (kind == OP_GS) {
-        if (wave < 0 || (size_t)wave + 1 >= op->waves.ptr.size()) return fail(AMGB_EINVAL, "wave index out of range");
-        return h->gs_wave(op->M, op->waves, wave, y, b, omega);
-    }
-    double *parts = (norm2_out != nullptr && (kind == OP_RESID || kind == OP_JACOBI)) ? op->partials : nullptr;
-    RET(h->spmv(kind, op->M, x, b, y, omega, r, parts));
-    if (parts != nullptr) {
-        reduce_partials_kernel<<<1, 1024, 0, h->stream>>>(parts, (int)h->partials_used(op->M, kind), norm2_out);
-        CK(cudaGetLastError());
-    }
-    return AMGB_OK;
-}
-
-// ------------------------------------------------------------------------------------------
-// C ABI (1c): GPU-resident Arnoldi rounds for the spectral-radius estimates of the smoother setup
-// (pyamg/util/linalg.py:255-383 approximate_spectral_radius -> _approximate_eigenvalues :90-252:
-// rho(D^-1 A) for Jacobi's omega, smoothing.py:372-400, rho(A) for Richardson / Chebyshev, :611-647).
-// The operator x -> diag(row_scale) (A x) is uploaded once; one call runs a whole round of modified-Gram-Schmidt
-// Arnoldi without a host round trip (inner products stay in device scalars: dot_to + axpy_ratio_kernel), the small
-// Hessenberg matrix goes to the host, whose eigen-decomposition (LAPACK through SciPy, as in the reference)
-// picks the restart vector as a combination of the basis that is still resident.
-// ------------------------------------------------------------------------------------------
-struct amgb_arnoldi {
-    amgb_hierarchy *pool = nullptr;
-    DevCsr M;
-    int maxiter = 0;
-    long long n = 0, npad = 0;
-    double *V = nullptr, *w = nullptr, *scale = nullptr, *dH = nullptr, *one = nullptr;
-    bool have_start = false;
-    double *v(int j) const { return V + (size_t)j * npad; }
-};
-
-extern "C" int amgb_arnoldi_create(int device, const amgb_matrix *A, const double *row_scale, int32_t maxiter,
-                                   amgb_arnoldi **out)
-{
-    if (out == nullptr) return fail(AMGB_EINVAL, "out is null");
-    *out = nullptr;
-    if (maxiter < 1) return fail(AMGB_EINVAL, "maxiter < 1");
-    amgb_hierarchy *pool = nullptr;
-    RET(amgb_hierarchy_create(device, &pool));
-    std::unique_ptr<amgb_arnoldi> a(new amgb_arnoldi());
-    a->pool = pool;
-    auto bail = [&](int rc) { amgb_hierarchy_destroy(pool); return rc; };
-    HostCsr H;
-    int rc = to_host_csr(A, H, "A");
-    if (rc == AMGB_OK && H.n_rows != H.n_cols) rc = fail(AMGB_EINVAL, "expected square matrix");   // linalg.py:150-151
-    if (rc != AMGB_OK) return bail(rc);
-    if (cudaStreamCreateWithFlags(&pool->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(AMGB_ECUDA, "stream"));
-    pool->own_stream = true;
-    a->n = H.n_rows;
-    a->npad = ((a->n + 2 + 31) / 32) * 32;
-    a->maxiter = (int)std::min<long long>(maxiter, std::max<long long>(a->n, 1));
-    rc = pool->upload_csr(H, a->M);
-    if (rc == AMGB_OK) rc = pool->dalloc(&a->V, (long long)(a->maxiter + 1) * a->npad);
-    if (rc == AMGB_OK) rc = pool->dalloc(&a->w, a->npad);
-    if (rc == AMGB_OK) rc = pool->dalloc(&a->dH, (long long)(a->maxiter + 1) * a->maxiter);
-    if (rc == AMGB_OK) rc = pool->dalloc(&a->one, 8);
-    if (rc == AMGB_OK) rc = pool->dalloc(&pool->sumsq_parts, kSumsqBlocks);
-    if (rc == AMGB_OK && row_scale != nullptr) rc = pool->upload(&a->scale, row_scale, a->n, 2);
-    if (rc != AMGB_OK) return bail(rc);
-    const double init[2] = {1.0, 0.0};
-    if (cudaMemcpy(a->one, init, sizeof init, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemset(a->V, 0, sizeof(double) * (size_t)(a->maxiter + 1) * (size_t)a->npad) != cudaSuccess ||
-        cudaMemset(a->w, 0, sizeof(double) * (size_t)a->npad) != cudaSuccess ||
-        cudaHostAlloc((void **)&pool->norm_host, sizeof(double) * 2, cudaHostAllocDefault) != cudaSuccess)
-        return bail(fail(AMGB_ECUDA, "arnoldi: device initialisation"));
-    *out = a.release();
-    return AMGB_OK;
-}
-
-extern "C" void amgb_arnoldi_destroy(amgb_arnoldi *a)
-{
-    if (a == nullptr) return;
-    amgb_hierarchy_destroy(a->pool);
-    delete a;
-}
-
-// One round: V[0] = v0 / ||v0|| (v0 from the host, or -- v0_host == NULL -- the vector left by amgb_arnoldi_combine),
-// then maxiter steps  w = diag(s) A V[j];  H[i][j] = <V[i], w>, w -= H[i][j] V[i] (i <= j);  H[j+1][j] = ||w||;
-// V[j+1] = w / H[j+1][j].  H: (maxiter+1) x maxiter row-major on the host.  *m_done = number of valid steps: the
-// first j with H[j+1][j] < breakdown * max(1, max |H[:j+1,:j+1]|) ends the round at m = j + 1 (later columns are
-// then meaningless); 0 if the start vector is zero.
-extern "C" int amgb_arnoldi_run(amgb_arnoldi *a, const double *v0_host, double breakdown, double *H_host, int32_t *m_done)
-{
-    if (a == nullptr || H_host == nullptr || m_done == nullptr) return fail(AMGB_EINVAL, "null argument");
-    amgb_hierarchy *h = a->pool;
-    CK(cudaSetDevice(h->device));
-    h->rt.activate();
-    cudaStream_t s = h->stream;
-    const long long n = a->n;
-    const int mi = a->maxiter;
-    *m_done = 0;
-    if (v0_host != nullptr) CK(cudaMemcpyAsync(a->v(0), v0_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
-    else if (!a->have_start) return fail(AMGB_ESTATE, "arnoldi: no start vector (call amgb_arnoldi_combine or pass v0)");
-    a->have_start = false;
-    double *scal = a->one + 1;
-    RET(h->dot_to(a->v(0), a->v(0), n, scal));
-    CK(cudaMemcpyAsync(h->norm_host, scal, sizeof(double), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    if (!(h->norm_host[0] > 0.0)) {
-        std::fill(H_host, H_host + (size_t)(mi + 1) * mi, 0.0);
-        return AMGB_OK;
-    }
-    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)g_num_sms * 16);
-    div_kernel<<<grid, 256, 0, s>>>(a->v(0), std::sqrt(h->norm_host[0]), n);
-    CK(cudaGetLastError());
-    CK(cudaMemsetAsync(a->dH, 0, sizeof(double) * (size_t)(mi + 1) * (size_t)mi, s));
-    for (int j = 0; j < mi; j++) {
-        RET(h->spmv(OP_SPMV, a->M, a->v(j), nullptr, a->w));
-        if (a->scale != nullptr) {
-            mul_kernel<<<grid, 256, 0, s>>>(a->w, a->scale, n);
-            CK(cudaGetLastError());
-        }
-        for (int i = 0; i <= j; i++) {
-            double *hij = a->dH + (size_t)i * mi + j;
-            RET(h->dot_to(a->v(i), a->w, n, hij));
-            RET(h->axpy_ratio(a->w, a->v(i), hij, a->one, -1.0, n));
-        }
-        double *hn = a->dH + (size_t)(j + 1) * mi + j;
-        RET(h->dot_to(a->w, a->w, n, hn));
-        sqrt_scalar_kernel<<<1, 1, 0, s>>>(hn);
-        CK(cudaGetLastError());
-        div_dev_kernel<<<grid, 256, 0, s>>>(a->v(j + 1), a->w, hn, n);
-        CK(cudaGetLastError());
-    }
-    CK(cudaMemcpyAsync(H_host, a->dH, sizeof(double) * (size_t)(mi + 1) * (size_t)mi, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    int m = mi;
-    double hmax = 0.0;
-    for (int j = 0; j < mi; j++) {
-        for (int i = 0; i <= j; i++) hmax = std::max(hmax, std::fabs(H_host[(size_t)i * mi + j]));
-        for (int jj = 0; jj < j; jj++) hmax = std::max(hmax, std::fabs(H_host[(size_t)j * mi + jj]));
-        if (!(H_host[(size_t)(j + 1) * mi + j] >= breakdown * std::max(1.0, hmax))) { m = j + 1; break; }
-    }
-    *m_done = m;
-    return AMGB_OK;
-}
-
-// next start vector = sum_k coef[k] V[k], k < m (the dominant Ritz vector: linalg.py:369-371)
-extern "C" int amgb_arnoldi_combine(amgb_arnoldi *a, const double *coef, int32_t m)
-{
-    if (a == nullptr || coef == nullptr) return fail(AMGB_EINVAL, "null argument");
-    if (m < 1 || m > a->maxiter) return fail(AMGB_EINVAL, "arnoldi: m out of range");
-    amgb_hierarchy *h = a->pool;
-    CK(cudaSetDevice(h->device));
-    h->rt.activate();
-    RET(h->scale_to(a->w, coef[0], a->v(0), a->n));
-    for (int k = 1; k < m; k++) RET(h->axpby(coef[k], a->v(k), 1.0, a->w, a->n));
-    RET(h->copy_vec(a->v(0), a->w, a->n));
-    a->have_start = true;
-    return AMGB_OK;
-}
-
-// HOST helper (no CUDA): the tile list the engine would build for a CSR row-pointer array under the
-// geometry (T entries, RMAX rows per tile) with G lanes per row and optional row breaks (e.g. wave
-// boundaries, n_breaks+1 ascending entries starting at 0).  row0/nz0 receive n_tiles+1 descriptors (sentinel
-// last, capacity `cap`), tile_ptr (if non-null, n_breaks+1 entries) the tile range of every break range.
-// Exposed so the tiling invariants can be tested without a GPU.
-extern "C" int amgb_debug_build_tiles(int32_t n, const int32_t *Ap, int32_t G, const int64_t *breaks,
-                                      int32_t n_breaks, int32_t T, int32_t RMAX, int32_t *row0, int32_t *nz0,
-                                      int32_t cap, int32_t *tile_ptr, int32_t *n_tiles)
-{
-    if (Ap == nullptr || row0 == nullptr || nz0 == nullptr || n_tiles == nullptr || n < 0)
-        return fail(AMGB_EINVAL, "build_tiles: bad arguments");
-    if (G < 1 || G > 32 || (G & (G - 1)) || T < 1 || RMAX < 1) return fail(AMGB_EINVAL, "build_tiles: bad geometry");
-    HostCsr H;
-    H.n_rows = H.n_cols = n;
-    H.Ap.assign(Ap, Ap + n + 1);
-    const int saveT = g_tile_T, saveR = g_tile_rmax;
-    g_tile_T = T;
-    g_tile_rmax = RMAX;
-    std::vector<TileDesc> tiles;
-    std::vector<int> tp;
-    std::vector<long long> br;
-    if (breaks != nullptr) br.assign(breaks, breaks + n_breaks + 1);
-    build_tiles(H, G, breaks ? &br : nullptr, tiles, breaks ? &tp : nullptr);
-    g_tile_T = saveT;
-    g_tile_rmax = saveR;
-    if ((int)tiles.size() > cap) return fail(AMGB_EINVAL, "build_tiles: output capacity too small");
-    for (size_t t = 0; t < tiles.size(); t++) { row0[t] = tiles[t].row0; nz0[t] = tiles[t].nz0; }
-    if (tile_ptr != nullptr && breaks != nullptr)
-        for (size_t w = 0; w < tp.size(); w++) tile_ptr[w] = tp[w];
-    *n_tiles = (int32_t)tiles.size() - 1;
-    return AMGB_OK;
-}
-
-// Dependency waves of a sequential sweep (host only, no CUDA): wave_of[k] (1-based) for list position k.
-// The multi-GPU layer uses it to give every rank the same global wave structure.
-extern "C" int amgb_wave_schedule(int32_t n, const int32_t *Ap, const int32_t *Aj, const int32_t *list, int64_t m,
-                                  int32_t *wave_of, int32_t *n_waves)
-{
-    if (Ap == nullptr || wave_of == nullptr || n < 0 || m < 0) return fail(AMGB_EINVAL, "wave_schedule: bad arguments");
-    std::vector<int> wwave((size_t)n, 0), rwave((size_t)n, 0);
-    int maxw = 0;
-    for (int64_t k = 0; k < m; k++) {
-        const int i = list ? list[k] : (int)k;
-        if (i < 0 || i >= n) return fail(AMGB_EINVAL, "wave_schedule: row index out of range");
-        int wv = std::max(rwave[(size_t)i], wwave[(size_t)i]);
-        for (int jj = Ap[i]; jj < Ap[i + 1]; jj++) {
-            const int j = Aj[jj];
-            if (j != i && j >= 0 && j < n) wv = std::max(wv, wwave[(size_t)j]);
-        }
-        wv += 1;
-        wave_of[k] = wv;
-        wwave[(size_t)i] = wv;
-        for (int jj = Ap[i]; jj < Ap[i + 1]; jj++) {
-            const int j = Aj[jj];
-            if (j != i && j >= 0 && j < n) rwave[(size_t)j] = std::max(rwave[(size_t)j], wv);
-        }
-        maxw = std::max(maxw, wv);
-    }
-    if (n_waves) *n_waves = maxw;
-    return AMGB_OK;
-}
-
-// ------------------------------------------------------------------------------------------
-// C ABI (3): device kernels
-// ------------------------------------------------------------------------------------------
-static int resolve_lanes(int lanes, int32_t n_rows, const int32_t *Ap, cudaStream_t s, int *out)
-{
-    if (lanes == 0) {
-        int nnz = 0;
-        if (n_rows > 0) {
-            CK(cudaMemcpyAsync(&nnz, Ap + n_rows, sizeof(int), cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-        }
-        lanes = pick_lanes(nnz, n_rows);
-    }
-    if (lanes < 1 || lanes > 32 || (lanes & (lanes - 1))) return fail(AMGB_EINVAL, "lanes must be a power of two in 1..32");
-    *out = lanes;
-    return AMGB_OK;
-}
-
-extern "C" int64_t amgb_dev_partials_len(int32_t n_rows, int lanes)
-{
-    if (lanes <= 0) lanes = 32;
-    return csr_grid(n_rows, lanes) + 1;
-}
-
-static CsrRowArgs mk_args(int n, int row0, const int *rows, const int *Ap, const int *Aj, const double *Ax,
-                          const double *x, const double *b, double *y, double *r, double omega, double *parts)
-{
-    CsrRowArgs a;
-    a.n = n; a.row0 = row0; a.rows = rows; a.Ap = Ap; a.Aj = Aj; a.Ax = Ax;
-    a.x = x; a.b = b; a.y = y; a.r = r; a.omega = omega; a.partials = parts;
-    return a;
-}
-
-extern "C" int amgb_dev_csr_spmv(int32_t n_rows, const int32_t *Ap, const int32_t *Aj, const double *Ax,
-                                 const double *x, double *y, int lanes, void *stream)
-{
-    cudaStream_t s = (cudaStream_t)stream;
-    RET(resolve_lanes(lanes, n_rows, Ap, s, &lanes));
-    return launch_csr(OP_SPMV, lanes, mk_args(n_rows, 0, nullptr, Ap, Aj, Ax, x, nullptr, y, nullptr, 0.0, nullptr), s);
-}
-
-extern "C" int amgb_dev_csr_residual(int32_t n_rows, const int32_t *Ap, const int32_t *Aj, const double *Ax,
-                                     const double *x, const double *b, double *r, double *partials,
-                                     double *norm2_out, int lanes, void *stream)
-{
-    cudaStream_t s = (cudaStream_t)stream;
-    RET(resolve_lanes(lanes, n_rows, Ap, s, &lanes));
-    if ((partials == nullptr) != (norm2_out == nullptr))
-        return fail(AMGB_EINVAL, "partials and norm2_out must be given together");
-    RET(launch_csr(OP_RESID, lanes, mk_args(n_rows, 0, nullptr, Ap, Aj, Ax, x, b, r, nullptr, 0.0, partials), s));
-    if (partials != nullptr) {
-        reduce_partials_kernel<<<1, 1024, 0, s>>>(partials, (int)csr_grid(n_rows, lanes), norm2_out);
-        CK(cudaGetLastError());
-    }
-    return AMGB_OK;
-}
-
-extern "C" int amgb_dev_csr_spmv_add(int32_t n_rows, const int32_t *Ap, const int32_t *Aj, const double *Ax,
-                                     const double *xc, double *x, int lanes, void *stream)
-{
-    cudaStream_t s = (cudaStream_t)stream;
-    RET(resolve_lanes(lanes, n_rows, Ap, s, &lanes));
-    return launch_csr(OP_PADD, lanes, mk_args(n_rows, 0, nullptr, Ap, Aj, Ax, xc, nullptr, x, nullptr, 0.0, nullptr), s);
-}
-
-extern "C" int amgb_dev_csr_jacobi(int32_t n_rows, const int32_t *Ap, const int32_t *Aj, const double *Ax,
-                                   const double *x_in, const double *b, double *x_out, double *r_out,
-                                   double omega, int lanes, void *stream)
-{
-    cudaStream_t s = (cudaStream_t)stream;
-    if (x_in == x_out) return fail(AMGB_EINVAL, "jacobi: x_in and x_out must differ");
-    RET(resolve_lanes(lanes, n_rows, Ap, s, &lanes));
-    return launch_csr(OP_JACOBI, lanes, mk_args(n_rows, 0, nullptr, Ap, Aj, Ax, x_in, b, x_out, r_out, omega, nullptr), s);
-}
-
-extern "C" int amgb_dev_csr_gs_wave(int32_t n, int32_t row0, const int32_t *rows, const int32_t *Ap,
-                                    const int32_t *Aj, const double *Ax, double *x, const double *b,
-                                    double omega, int lanes, void *stream)
-{
-    cudaStream_t s = (cudaStream_t)stream;
-    if (lanes == 0) lanes = 8;
-    if (lanes < 1 || lanes > 32 || (lanes & (lanes - 1))) return fail(AMGB_EINVAL, "lanes must be a power of two in 1..32");
-    return launch_csr(OP_GS, lanes, mk_args(n, row0, rows, Ap, Aj, Ax, x, b, x, nullptr, omega, nullptr), s);
-}
-
-extern "C" int amgb_dev_dense_matvec(int32_t m, int32_t n, const double *M, const double *x, double *y,
-                                     void *stream)
-{
-    if (m <= 0) return AMGB_OK;
-    dense_matvec_kernel<<<(m + 3) / 4, 128, 0, (cudaStream_t)stream>>>(m, n, M, x, y);
-    CK(cudaGetLastError());
-    return AMGB_OK;
-}
-
-extern "C" int amgb_dev_gather(const double *in, const int32_t *idx, double *out, int64_t n, void *stream)
-{
-    if (n <= 0) return AMGB_OK;
-    const long long grid = std::min<long long>((n + 255) / 256, (long long)148 * 16);
-    gather_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(in, idx, out, n);
-    CK(cudaGetLastError());
-    return AMGB_OK;
-}
-
-extern "C" int amgb_dev_fill(double *x, int64_t n, double v, void *stream)
-{
-    return launch_fill(x, n, v, (cudaStream_t)stream);
-}
-
-// ------------------------------------------------------------------------------------------
-// C ABI (2): reference-FFI-shaped host entry points.  Upload, run the same kernels, download.
-// ------------------------------------------------------------------------------------------
-namespace {
-struct Scratch {   // RAII device scratch for the host-shaped calls
-    std::vector<void *> ptrs;
-    ~Scratch() { for (void *p : ptrs) cudaFree(p); }
-    template <typename T>
-    int up(T **d, const T *h, long long n)
-    {
-        void *q = nullptr;
-        CK(cudaMalloc(&q, (size_t)std::max<long long>(n, 1) * sizeof(T)));
-        ptrs.push_back(q);
-        if (n > 0 && h != nullptr) CK(cudaMemcpy(q, h, (size_t)n * sizeof(T), cudaMemcpyHostToDevice));
-        *d = (T *)q;
-        return AMGB_OK;
-    }
-};
-
-int check_csr_host(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size, const double *Ax,
-                   int Ax_size, int x_size, int b_size, int vals_per_entry)
-{
-    if (Ap == nullptr || Ap_size < 1) return fail(AMGB_EINVAL, "Ap missing");
-    if (Aj_size > 0 && (Aj == nullptr || Ax == nullptr)) return fail(AMGB_EINVAL, "Aj/Ax missing");
-    if ((long long)Aj_size * vals_per_entry != (long long)Ax_size) return fail(AMGB_EINVAL, "Aj/Ax size mismatch");
-    if (Ap[Ap_size - 1] != Aj_size) return fail(AMGB_EINVAL, "Ap[-1] != len(Aj)");
-    if (x_size != b_size) return fail(AMGB_EINVAL, "x and b sizes differ");
-    return AMGB_OK;
-}
-
-// rows visited by `for (i = start; i != stop; i += step)`
-int range_rows(int start, int stop, int step, int n, std::vector<int> &rows)
-{
-    rows.clear();
-    if (step == 0) return fail(AMGB_EINVAL, "row_step == 0");
-    if ((stop - start) % step != 0) return fail(AMGB_EINVAL, "row range never terminates");
-    if ((stop - start) / step < 0) return fail(AMGB_EINVAL, "row range never terminates");
-    for (int i = start; i != stop; i += step) {
-        if (i < 0 || i >= n) return fail(AMGB_EINVAL, "row index out of range");
-        rows.push_back(i);
-    }
-    return AMGB_OK;
-}
-}  // namespace
-
-extern "C" int amgb_host_jacobi(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
-                                const double *Ax, int Ax_size, double *x, int x_size, const double *b,
-                                int b_size, double *temp, int temp_size, int32_t row_start,
-                                int32_t row_stop, int32_t row_step, const double *omega, int omega_size)
-{
-    RET(check_csr_host(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x_size, b_size, 1));
-    const int n = Ap_size - 1;
-    if (x_size != n || temp_size < n || omega == nullptr || omega_size < 1)
-        return fail(AMGB_EINVAL, "jacobi: bad vector sizes");
-    std::vector<int> rows;
-    RET(range_rows(row_start, row_stop, row_step, n, rows));
-    if (rows.empty()) return AMGB_OK;
-    Scratch sc;
-    int *dAp, *dAj, *drows;
-    double *dAx, *dx, *db, *dy;
-    RET(sc.up(&dAp, Ap, Ap_size)); RET(sc.up(&dAj, Aj, Aj_size)); RET(sc.up(&dAx, Ax, Ax_size));
-    RET(sc.up(&dx, (const double *)x, n)); RET(sc.up(&db, b, n)); RET(sc.up(&dy, (const double *)x, n));
-    RET(sc.up(&drows, rows.data(), (long long)rows.size()));
-    const int lanes = pick_lanes(Aj_size, n);
-    RET(launch_csr(OP_JACOBI, lanes, mk_args((int)rows.size(), 0, drows, dAp, dAj, dAx, dx, db, dy, nullptr, omega[0], nullptr), 0));
-    CK(cudaDeviceSynchronize());
-    for (int i : rows) temp[i] = x[i];                      // relaxation.h:325-327
-    CK(cudaMemcpy(x, dy, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
-    return AMGB_OK;
-}
-
-static int host_gs_common(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size, const double *Ax,
-                          int Ax_size, double *x, int x_size, const double *b, int b_size,
-                          const std::vector<int> &list, double omega = 1.0)
-{
-    RET(check_csr_host(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x_size, b_size, 1));
-    const int n = Ap_size - 1;
-    if (x_size != n) return fail(AMGB_EINVAL, "gauss_seidel: bad vector sizes");
-    if (list.empty()) return AMGB_OK;
-    HostCsr H;
-    H.n_rows = H.n_cols = n;
-    H.Ap.assign(Ap, Ap + Ap_size);
-    H.Aj.assign(Aj, Aj + Aj_size);
-    for (int c : H.Aj) if (c < 0 || c >= n) return fail(AMGB_EINVAL, "column index out of range");
-    std::vector<int> rows;
-    std::vector<long long> ptr;
-    build_waves(H, list.data(), (long long)list.size(), rows, ptr);
-    Scratch sc;
-    int *dAp, *dAj, *drows;
-    double *dAx, *dx, *db;
-    RET(sc.up(&dAp, Ap, Ap_size)); RET(sc.up(&dAj, Aj, Aj_size)); RET(sc.up(&dAx, Ax, Ax_size));
-    RET(sc.up(&dx, (const double *)x, n)); RET(sc.up(&db, b, n));
-    RET(sc.up(&drows, rows.data(), (long long)rows.size()));
-    const int lanes = pick_lanes(Aj_size, n);
-    for (size_t w = 0; w + 1 < ptr.size(); w++)
-        RET(launch_csr(OP_GS, lanes, mk_args((int)(ptr[w + 1] - ptr[w]), 0, drows + ptr[w], dAp, dAj, dAx, dx, db, dx, nullptr, omega, nullptr), 0));
-    CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(x, dx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
-    return AMGB_OK;
-}
-
-extern "C" int amgb_host_gauss_seidel(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
-                                      const double *Ax, int Ax_size, double *x, int x_size, const double *b,
-                                      int b_size, int32_t row_start, int32_t row_stop, int32_t row_step)
-{
-    if (Ap == nullptr || Ap_size < 1) return fail(AMGB_EINVAL, "Ap missing");
-    std::vector<int> list;
-    RET(range_rows(row_start, row_stop, row_step, Ap_size - 1, list));
-    return host_gs_common(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x, x_size, b, b_size, list);
-}
-
-extern "C" int amgb_host_sor_gauss_seidel(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
-                                          const double *Ax, int Ax_size, double *x, int x_size, const double *b,
-                                          int b_size, int32_t row_start, int32_t row_stop, int32_t row_step,
-                                          double omega)
-{
-    if (Ap == nullptr || Ap_size < 1) return fail(AMGB_EINVAL, "Ap missing");
-    std::vector<int> list;
-    RET(range_rows(row_start, row_stop, row_step, Ap_size - 1, list));
-    return host_gs_common(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x, x_size, b, b_size, list, omega);
-}
-
-extern "C" int amgb_host_gauss_seidel_indexed(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
-                                              const double *Ax, int Ax_size, double *x, int x_size,
-                                              const double *b, int b_size, const int32_t *Id, int Id_size,
-                                              int32_t row_start, int32_t row_stop, int32_t row_step)
-{
-    if (Ap == nullptr || Ap_size < 1) return fail(AMGB_EINVAL, "Ap missing");
-    std::vector<int> pos, list;
-    RET(range_rows(row_start, row_stop, row_step, Id_size, pos));
-    for (int k : pos) {
-        if (Id[k] < 0 || Id[k] >= Ap_size - 1) return fail(AMGB_EINVAL, "row index out of range");
-        list.push_back(Id[k]);
-    }
-    return host_gs_common(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x, x_size, b, b_size, list);
-}
-
-extern "C" int amgb_host_bsr_jacobi(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
-                                    const double *Ax, int Ax_size, double *x, int x_size, const double *b,
-                                    int b_size, double *temp, int temp_size, int32_t row_start,
-                                    int32_t row_stop, int32_t row_step, int32_t blocksize,
-                                    const double *omega, int omega_size)
-{
-    if (blocksize < 1) return fail(AMGB_EINVAL, "blocksize < 1");
-    RET(check_csr_host(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x_size, b_size, blocksize * blocksize));
-    const int nb = Ap_size - 1, n = nb * blocksize;
-    if (x_size != n || temp_size < n || omega == nullptr || omega_size < 1)
-        return fail(AMGB_EINVAL, "bsr_jacobi: bad vector sizes");
-    std::vector<int> brows;
-    RET(range_rows(row_start, row_stop, row_step, nb, brows));
-    if (brows.empty()) return AMGB_OK;
-    amgb_matrix M;
-    M.n_rows = M.n_cols = n; M.block_r = M.block_c = blocksize; M.nnz_blocks = Aj_size;
-    M.indptr = Ap; M.indices = Aj; M.data = Ax;
-    HostCsr H;
-    RET(to_host_csr(&M, H, "A"));
-    std::vector<int> rows;
-    for (int I : brows) for (int k = 0; k < blocksize; k++) rows.push_back(I * blocksize + k);
-    Scratch sc;
-    int *dAp, *dAj, *drows;
-    double *dAx, *dx, *db, *dy;
-    RET(sc.up(&dAp, H.Ap.data(), (long long)H.Ap.size())); RET(sc.up(&dAj, H.Aj.data(), (long long)H.Aj.size()));
-    RET(sc.up(&dAx, H.Ax.data(), (long long)H.Ax.size()));
-    RET(sc.up(&dx, (const double *)x, n)); RET(sc.up(&db, b, n)); RET(sc.up(&dy, (const double *)x, n));
-    RET(sc.up(&drows, rows.data(), (long long)rows.size()));
-    const int lanes = pick_lanes((long long)H.Aj.size(), n);
-    RET(launch_csr(OP_JACOBI, lanes, mk_args((int)rows.size(), 0, drows, dAp, dAj, dAx, dx, db, dy, nullptr, omega[0], nullptr), 0));
-    CK(cudaDeviceSynchronize());
-    for (int i = 0; i < (int)rows.size(); i++) temp[i] = x[i];   // relaxation.h:506-508
-    CK(cudaMemcpy(x, dy, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
-    return AMGB_OK;
-}
-
-extern "C" int amgb_host_block_jacobi(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
-                                      const double *Ax, int Ax_size, double *x, int x_size, const double *b,
-                                      int b_size, const double *Tx, int Tx_size, double *temp, int temp_size,
-                                      int32_t row_start, int32_t row_stop, int32_t row_step,
-                                      const double *omega, int omega_size, int32_t blocksize)
-{
-    if (blocksize < 1 || blocksize > 8) return fail(AMGB_ENOTIMPL, "block_jacobi: blocksize must be 1..8");
-    RET(check_csr_host(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x_size, b_size, blocksize * blocksize));
-    const int nb = Ap_size - 1, n = nb * blocksize;
-    if (x_size != n || temp_size < n || omega == nullptr || omega_size < 1 || Tx == nullptr ||
-        Tx_size != nb * blocksize * blocksize)
-        return fail(AMGB_EINVAL, "block_jacobi: bad vector sizes");
-    if (!(row_start == 0 && row_stop == nb && row_step == 1))
-        return fail(AMGB_ENOTIMPL, "block_jacobi: only the full forward range (what relaxation.py:483-484 passes)");
-    if (nb == 0) return AMGB_OK;
-    amgb_matrix M;
-    M.n_rows = M.n_cols = n; M.block_r = M.block_c = blocksize; M.nnz_blocks = Aj_size;
-    M.indptr = Ap; M.indices = Aj; M.data = Ax;
-    HostCsr H;
-    RET(to_host_csr(&M, H, "A"));
-    Scratch sc;
-    DevCsr D;
-    double *dx, *db, *dy, *dD;
-    RET(sc.up(&D.Ap, H.Ap.data(), (long long)H.Ap.size())); RET(sc.up(&D.Aj, H.Aj.data(), (long long)H.Aj.size()));
-    RET(sc.up(&D.Ax, H.Ax.data(), (long long)H.Ax.size()));
-    RET(sc.up(&dx, (const double *)x, n)); RET(sc.up(&db, b, n)); RET(sc.up(&dy, (const double *)x, n));
-    RET(sc.up(&dD, Tx, Tx_size));
-    D.n_rows = D.n_cols = n;
-    const int lanes = pick_lanes((long long)H.Aj.size(), n);
-    RET(dispatch_block_jacobi(blocksize, lanes, nb, D, dx, db, dD, dy, omega[0], 0));
-    CK(cudaDeviceSynchronize());
-    std::memcpy(temp, x, sizeof(double) * (size_t)n);           // relaxation.h:1043-1045
-    CK(cudaMemcpy(x, dy, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
-    return AMGB_OK;
-}
-
-extern "C" int amgb_host_relax(const amgb_matrix *A, const amgb_smoother *sm, double *x, const double *b)
-{
-    if (A == nullptr || sm == nullptr || x == nullptr || b == nullptr) return fail(AMGB_EINVAL, "null argument");
-    RET(validate_matrix(A, "A"));
-    const int n = A->n_rows;
-    if (n == 0) return AMGB_OK;
-    // a two-level hierarchy whose transfer operators are empty: level 0 carries the operator and the smoother
-    // through exactly the upload path of a real hierarchy (wave-major permutation, tiles, row lists)
-    amgb_hierarchy *h = nullptr;
-    RET(amgb_hierarchy_create(0, &h));
-    struct Guard { amgb_hierarchy *h; ~Guard() { amgb_hierarchy_destroy(h); } } guard{h};
-    std::vector<int32_t> p_ptr((size_t)n + 1, 0), one_ptr(2, 0);
-    amgb_matrix P = {n, 1, 1, 1, 0, p_ptr.data(), nullptr, nullptr};
-    amgb_matrix R = {1, n, 1, 1, 0, one_ptr.data(), nullptr, nullptr};
-    amgb_matrix C = {1, 1, 1, 1, 0, one_ptr.data(), nullptr, nullptr};
-    amgb_smoother none = {};
-    none.kind = AMGB_SM_NONE;
-    RET(amgb_hierarchy_add_level(h, A, &P, &R, sm, &none));
-    RET(amgb_hierarchy_add_level(h, &C, nullptr, nullptr, nullptr, nullptr));
-    RET(amgb_hierarchy_set_coarse_pinv(h, 1, nullptr, 1));
-    RET(amgb_hierarchy_finalize(h, nullptr));
-    h->rt.activate();
-    h->launches = 0;
-    RET(load_level0(h, b, x, cudaMemcpyHostToDevice));
-    Level &L0 = h->levels[0];
-    h->cur_level = 0;
-    RET(h->smooth(L0, L0.pre));
-    RET(store_level0(h, x, cudaMemcpyDeviceToHost));
-    CK(cudaStreamSynchronize(h->stream));
-    return AMGB_OK;
-}
-
-extern "C" int amgb_host_jacobi_indexed(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
-                                        const double *Ax, int Ax_size, double *x, int x_size, const double *b,
-                                        int b_size, const int32_t *indices, int indices_size, const double *omega,
-                                        int omega_size)
-{
-    RET(check_csr_host(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x_size, b_size, 1));
-    const int n = Ap_size - 1;
-    if (x_size != n || omega == nullptr || omega_size < 1) return fail(AMGB_EINVAL, "jacobi_indexed: bad vector sizes");
-    if (indices_size < 0 || (indices_size > 0 && indices == nullptr)) return fail(AMGB_EINVAL, "jacobi_indexed: null row list");
-    if (indices_size == 0 || n == 0) return AMGB_OK;
-    amgb_matrix A = {n, n, 1, 1, Aj_size, Ap, Aj, Ax};
-    amgb_smoother sm = {};
-    sm.kind = AMGB_SM_JACOBI_INDEXED;
-    sm.iterations = 1;
-    sm.omega = omega[0];
-    sm.indices = indices;
-    sm.n_indices = indices_size;
-    return amgb_host_relax(&A, &sm, x, b);
-}
-
-extern "C" int amgb_host_block_gauss_seidel(const int32_t *Ap, int Ap_size, const int32_t *Aj, int Aj_size,
-                                            const double *Ax, int Ax_size, double *x, int x_size, const double *b,
-                                            int b_size, const double *Tx, int Tx_size, int32_t row_start,
-                                            int32_t row_stop, int32_t row_step, int32_t blocksize)
-{
-    if (blocksize < 1 || blocksize > 8) return fail(AMGB_ENOTIMPL, "block_gauss_seidel: blocksize must be 1..8");
-    RET(check_csr_host(Ap, Ap_size, Aj, Aj_size, Ax, Ax_size, x_size, b_size, blocksize * blocksize));
-    const int nb = Ap_size - 1, n = nb * blocksize;
-    if (x_size != n || Tx == nullptr || (long long)Tx_size != (long long)n * blocksize)
-        return fail(AMGB_EINVAL, "block_gauss_seidel: bad vector sizes");
-    if (nb == 0) return AMGB_OK;
-    amgb_smoother sm = {};
-    sm.kind = AMGB_SM_BLOCK_GAUSS_SEIDEL;
-    sm.iterations = 1;
-    sm.blocksize = blocksize;
-    sm.Dinv = Tx;
-    if (row_start == 0 && row_stop == nb && row_step == 1) sm.sweep = AMGB_SWEEP_FORWARD;
-    else if (row_start == nb - 1 && row_stop == -1 && row_step == -1) sm.sweep = AMGB_SWEEP_BACKWARD;
-    else return fail(AMGB_ENOTIMPL, "block_gauss_seidel: only the full forward / backward block-row ranges");
-    amgb_matrix A = {n, n, blocksize, blocksize, Aj_size, Ap, Aj, Ax};
-    return amgb_host_relax(&A, &sm, x, b);
-}
-
-// ------------------------------------------------------------------------------------------
-// C = A B as scipy.sparse._sparsetools.csr_matmat computes it (spgemm.cuh): the Galerkin product of the setup phase
-// ------------------------------------------------------------------------------------------
-template <int CAP, int THREADS>
-static int launch_spgemm(SpgemmArgs a, cudaStream_t s)
-{
-    if (a.n_rows <= 0) return AMGB_OK;
-    constexpr size_t smem = spgemm_smem_bytes<CAP>();
-    static bool attr_done = false;
-    if (!attr_done) {
-        CK(cudaFuncSetAttribute(spgemm_row_kernel<CAP, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    spgemm_row_kernel<CAP, THREADS><<<(unsigned)a.n_rows, THREADS, smem, s>>>(a);
-    CK(cudaGetLastError());
-    return AMGB_OK;
-}
-
-extern "C" void amgb_free(void *p) { free(p); }
-
-extern "C" int amgb_host_csr_matmat(const amgb_matrix *A, const amgb_matrix *B, int32_t **Cp_out, int32_t **Cj_out,
-                                    double **Cx_out, int64_t *nnz_out)
-{
-    if (Cp_out == nullptr || Cj_out == nullptr || Cx_out == nullptr || nnz_out == nullptr)
-        return fail(AMGB_EINVAL, "null output");
-    *Cp_out = nullptr; *Cj_out = nullptr; *Cx_out = nullptr; *nnz_out = 0;
-    RET(validate_matrix(A, "A"));
-    RET(validate_matrix(B, "B"));
-    if (A->block_r != 1 || A->block_c != 1 || B->block_r != 1 || B->block_c != 1)
-        return fail(AMGB_ENOTIMPL, "csr_matmat: CSR operands only (bsr_matmat is not on the GPU path)");
-    if (A->n_cols != B->n_rows) return fail(AMGB_EINVAL, "dimension mismatch");       // scipy: ValueError
-    const int n = A->n_rows;
-    for (int64_t k = 0; k < A->nnz_blocks; k++)
-        if (A->indices[k] < 0 || A->indices[k] >= A->n_cols) return fail(AMGB_EINVAL, "A: column index out of range");
-    for (int64_t k = 0; k < B->nnz_blocks; k++)
-        if (B->indices[k] < 0 || B->indices[k] >= B->n_cols) return fail(AMGB_EINVAL, "B: column index out of range");
-    // bins by the work of a row: products (and entries of A_i, which index the offset table)
-    std::vector<int> bins[3];
-    static const int kCap[3] = {256, 2048, 8192};
-    for (int i = 0; i < n; i++) {
-        long long prod = 0;
-        const int na = A->indptr[i + 1] - A->indptr[i];
-        if (na < 0) return fail(AMGB_EINVAL, "A: indptr not monotone");
-        for (int jj = A->indptr[i]; jj < A->indptr[i + 1]; jj++) {
-            const int j = A->indices[jj];
-            prod += B->indptr[j + 1] - B->indptr[j];
-        }
-        const long long need = std::max<long long>(prod, na);
-        int b = 0;
-        while (b < 3 && need > kCap[b]) b++;
-        if (b == 3) return fail(AMGB_ENOTIMPL, "csr_matmat: a row with more than 8192 products");
-        bins[b].push_back(i);
-    }
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(AMGB_ECUDA, "no CUDA device");
-    Scratch sc;
-    SpgemmArgs a;
-    int *dAp, *dAj, *dBp, *dBj, *d_rows[3], *d_nnz, *dCp, *dCj;
-    double *dAx, *dBx, *dCx;
-    RET(sc.up(&dAp, A->indptr, (long long)n + 1)); RET(sc.up(&dAj, A->indices, A->nnz_blocks));
-    RET(sc.up(&dAx, A->data, A->nnz_blocks));
-    RET(sc.up(&dBp, B->indptr, (long long)B->n_rows + 1)); RET(sc.up(&dBj, B->indices, B->nnz_blocks));
-    RET(sc.up(&dBx, B->data, B->nnz_blocks));
-    for (int b = 0; b < 3; b++) RET(sc.up(&d_rows[b], bins[b].data(), (long long)bins[b].size()));
-    RET(sc.up(&d_nnz, (const int *)nullptr, (long long)n));
-    a.Ap = dAp; a.Aj = dAj; a.Ax = dAx; a.Bp = dBp; a.Bj = dBj; a.Bx = dBx;
-    a.row_nnz = d_nnz; a.Cp = nullptr; a.Cj = nullptr; a.Cx = nullptr;
-    auto pass = [&](int fill) -> int {
-        a.fill = fill;
-        a.rows = d_rows[0]; a.n_rows = (int)bins[0].size();
-        RET((launch_spgemm<256, 32>(a, 0)));
-        a.rows = d_rows[1]; a.n_rows = (int)bins[1].size();
-        RET((launch_spgemm<2048, 128>(a, 0)));
-        a.rows = d_rows[2]; a.n_rows = (int)bins[2].size();
-        RET((launch_spgemm<8192, 256>(a, 0)));
-        CK(cudaDeviceSynchronize());
-        return AMGB_OK;
-    };
-    RET(pass(0));
-    std::vector<int> row_nnz((size_t)n);
-    if (n > 0) CK(cudaMemcpy(row_nnz.data(), d_nnz, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
-    int32_t *Cp = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n + 1));
-    if (Cp == nullptr) return fail(AMGB_ECUDA, "out of host memory");
-    long long run = 0;
-    Cp[0] = 0;
-    for (int i = 0; i < n; i++) {
-        run += row_nnz[(size_t)i];
-        if (run > 2147483647LL) { free(Cp); return fail(AMGB_EINVAL, "csr_matmat: nnz exceeds int32 (reference index type)"); }
-        Cp[i + 1] = (int32_t)run;
-    }
-    int32_t *Cj = (int32_t *)malloc(sizeof(int32_t) * (size_t)std::max<long long>(run, 1));
-    double *Cx = (double *)malloc(sizeof(double) * (size_t)std::max<long long>(run, 1));
-    struct OutGuard { int32_t *p, *j; double *x; bool keep; ~OutGuard() { if (!keep) { free(p); free(j); free(x); } } }
-        og{Cp, Cj, Cx, false};
-    if (Cj == nullptr || Cx == nullptr) return fail(AMGB_ECUDA, "out of host memory");
-    RET(sc.up(&dCp, (const int *)Cp, (long long)n + 1));
-    RET(sc.up(&dCj, (const int *)nullptr, run));
-    RET(sc.up(&dCx, (const double *)nullptr, run));
-    a.Cp = dCp; a.Cj = dCj; a.Cx = dCx;
-    RET(pass(1));
-    if (run > 0) {
-        CK(cudaMemcpy(Cj, dCj, sizeof(int32_t) * (size_t)run, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(Cx, dCx, sizeof(double) * (size_t)run, cudaMemcpyDeviceToHost));
-    }
-    og.keep = true;
-    *Cp_out = Cp; *Cj_out = Cj; *Cx_out = Cx; *nnz_out = run;
-    return AMGB_OK;
-}
-
-extern "C" int amgb_host_matvec(const amgb_matrix *A, const double *x, double *y)
-{
-    HostCsr H;
-    RET(to_host_csr(A, H, "A"));
-    if (x == nullptr || y == nullptr) return fail(AMGB_EINVAL, "null vector");
-    Scratch sc;
-    int *dAp, *dAj;
-    double *dAx, *dx, *dy;
-    RET(sc.up(&dAp, H.Ap.data(), (long long)H.Ap.size())); RET(sc.up(&dAj, H.Aj.data(), (long long)H.Aj.size()));
-    RET(sc.up(&dAx, H.Ax.data(), (long long)H.Ax.size()));
-    RET(sc.up(&dx, x, H.n_cols)); RET(sc.up(&dy, (const double *)nullptr, H.n_rows));
-    const int lanes = pick_lanes((long long)H.Aj.size(), H.n_rows);
-    RET(launch_csr(OP_SPMV, lanes, mk_args(H.n_rows, 0, nullptr, dAp, dAj, dAx, dx, nullptr, dy, nullptr, 0.0, nullptr), 0));
-    CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(y, dy, sizeof(double) * (size_t)H.n_rows, cudaMemcpyDeviceToHost));
-    return AMGB_OK;
-}
+#include "abi_operator.cuh"    // amgb_operator_*, amgb_arnoldi_*, amgb_debug_*, amgb_dev_*
+#include "abi_host.cuh"        // amgb_host_*, amgb_host_relax, amgb_host_csr_matmat
