@@ -56,7 +56,8 @@ WORKLOAD = {"name": "cfg3"}      # set by --workload; the default is BASELINE.js
 def build_hierarchy(grid, stream=None, device=0):
     """cfg3 (default): poisson(grid) + RS hierarchy + multi-colour symmetric GS on every level (BASELINE
     configs[2]).  cfg2: 2-D poisson(grid[:2]) + smoothed aggregation + weighted Jacobi (BASELINE configs[1]).
-    cfg5: linear_elasticity(grid[:2]) BSR(2,2) + smoothed aggregation on the rigid-body modes + block Jacobi
+    cfg4: stencil_grid(rotated anisotropic diffusion, grid[:2]) + smoothed aggregation + weighted Jacobi (BASELINE
+    configs[3], the multi-GPU configuration).  cfg5: linear_elasticity(grid[:2]) BSR(2,2) + smoothed aggregation on the rigid-body modes + block Jacobi
     (BASELINE configs[4])."""
     from pyamg_b200.gallery import poisson
     from pyamg_b200.classical import ruge_stuben_solver
@@ -65,6 +66,16 @@ def build_hierarchy(grid, stream=None, device=0):
     np.random.seed(SEED)
     if WORKLOAD["name"] == "cfg2":
         A = poisson(tuple(grid)[:2])
+        t1 = time.time()
+        sm = ("jacobi", {"omega": 4.0 / 3.0})
+        ml = smoothed_aggregation_solver(A, presmoother=sm, postsmoother=sm, device=device, stream=stream)
+    elif WORKLOAD["name"] == "cfg4":
+        # BASELINE configs[3]: anisotropic rotated diffusion (eps = 0.001, theta = pi/6, FE stencil), SA + Jacobi -- the
+        # row-partitioned multi-GPU configuration.  Strength of connection is the SA default ('symmetric'), which
+        # the host setup offers; SURVEY.md 8(d)-4: with it the stand-alone V-cycle does not converge on this
+        # operator (the reference needs strength='evolution' for that) -- throughput is unaffected.
+        from pyamg_b200.gallery import stencil_grid, diffusion_stencil_2d
+        A = stencil_grid(diffusion_stencil_2d(epsilon=0.001, theta=np.pi / 6, type="FE"), tuple(grid)[:2], format="csr")
         t1 = time.time()
         sm = ("jacobi", {"omega": 4.0 / 3.0})
         ml = smoothed_aggregation_solver(A, presmoother=sm, postsmoother=sm, device=device, stream=stream)
@@ -198,6 +209,14 @@ def workload_config(grid, ml, ngpus):
         return {"workload": f"gallery.poisson({tuple(grid)[:2]}) 5-pt fp64 CSR, smoothed_aggregation_solver hierarchy "
                             f"({len(ml.levels)} levels, op-cx {ml.operator_complexity():.3f}), weighted Jacobi omega=4/3 "
                             "pre+post, pinv coarse solve, V(1,1)-cycle + per-cycle residual check",
+                "n": int(ml.levels[0].A.shape[0]), "nnz": int(ml.levels[0].A.nnz),
+                "sum_nnz_A": int(sum(lv.A.nnz for lv in ml.levels)),
+                "parallelism": "1 GPU" if ngpus == 1 else f"{ngpus} GPUs", "l2": "inputs larger than L2"}
+    if WORKLOAD["name"] == "cfg4":
+        return {"workload": f"gallery.stencil_grid(diffusion_stencil_2d(eps=0.001, theta=pi/6, 'FE'), {tuple(grid)[:2]}) "
+                            f"9-pt fp64 CSR, smoothed_aggregation_solver hierarchy (symmetric strength; {len(ml.levels)} "
+                            f"levels, op-cx {ml.operator_complexity():.3f}), weighted Jacobi omega=4/3 pre+post, pinv "
+                            "coarse solve, V(1,1)-cycle + per-cycle residual check",
                 "n": int(ml.levels[0].A.shape[0]), "nnz": int(ml.levels[0].A.nnz),
                 "sum_nnz_A": int(sum(lv.A.nnz for lv in ml.levels)),
                 "parallelism": "1 GPU" if ngpus == 1 else f"{ngpus} GPUs", "l2": "inputs larger than L2"}
@@ -342,9 +361,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=256, help="grid points per dimension (3-D)")
     ap.add_argument("--cpu-sample", type=int, default=2, help="V-cycles timed for cpu_baseline")
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5"],
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg4", "cfg5"],
                     help="cfg3 = BASELINE configs[2] (headline, default); cfg2 = configs[1]: 2-D Poisson, SA + Jacobi "
-                         "(use --grid 2000); cfg5 = configs[4]: 2-D elasticity, SA + block Jacobi (use --grid 300)")
+                         "(use --grid 2000); cfg4 = configs[3]: anisotropic diffusion, SA + Jacobi, the multi-GPU "
+                         "configuration (use --grid 4096); cfg5 = configs[4]: 2-D elasticity, SA + block Jacobi (use --grid 300)")
     args = ap.parse_args()
     WORKLOAD["name"] = args.workload
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -38,6 +38,8 @@ def lib():
         L.amgb_setup_block_gauss_seidel.argtypes = [i32, i32, _I, _I, _D, _D, _D, _D, i32, i32]
         L.amgb_setup_coloring_is_valid.restype = i32
         L.amgb_setup_coloring_is_valid.argtypes = [i32, _I, _I, _I]
+        L.amgb_setup_arnoldi_round.restype = i32
+        L.amgb_setup_arnoldi_round.argtypes = [i32, _I, _I, _D, _D, _D, i32, f64, _D]
         _lib = L
     return _lib
 

@@ -499,4 +499,68 @@ int32_t amgb_setup_coloring_is_valid(int32_t n, const int32_t *Ap, const int32_t
     return 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// One round of modified-Gram-Schmidt Arnoldi on the host, multi-threaded (the spectral-radius estimates of the
+// smoother setup: pyamg/util/linalg.py:90-252 _approximate_eigenvalues, non-symmetric branch :214-229).  Same
+// contract as the device version amgb_arnoldi_run (csrc/abi_operator.cuh): V is (maxiter+1) x n row-major with the
+// (unnormalised) start vector in row 0, the operator is x -> diag(row_scale) (A x) (row_scale may be NULL), H is
+// (maxiter+1) x maxiter row-major; returns the number of valid steps m (0 for a zero start vector; a step whose
+// new norm is below breakdown * max(1, max |H[:j+1,:j+1]|) ends the round at m = j + 1).
+// Inner products are summed over fixed 8192-entry chunks whose partial sums are added in chunk order: the result
+// does not depend on the number of threads.
+// ---------------------------------------------------------------------------------------------
+static double chunked_dot(const double *x, const double *y, int64_t n)
+{
+    const int64_t C = 8192, nch = (n + C - 1) / C;
+    std::vector<double> part((size_t)std::max<int64_t>(nch, 1), 0.0);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < nch; c++) {
+        const int64_t i0 = c * C, i1 = std::min(n, i0 + C);
+        double s = 0.0;
+        for (int64_t i = i0; i < i1; i++) s += x[i] * y[i];
+        part[(size_t)c] = s;
+    }
+    double t = 0.0;
+    for (int64_t c = 0; c < nch; c++) t += part[(size_t)c];
+    return t;
+}
+
+int32_t amgb_setup_arnoldi_round(int32_t n, const int32_t *Ap, const int32_t *Aj, const double *Ax,
+                                 const double *row_scale, double *V, int32_t maxiter, double breakdown, double *H)
+{
+    const int64_t N = n;
+    for (int64_t k = 0; k < (int64_t)(maxiter + 1) * maxiter; k++) H[k] = 0.0;
+    double *v0 = V;
+    const double nv = std::sqrt(chunked_dot(v0, v0, N));
+    if (!(nv > 0.0)) return 0;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; i++) v0[i] /= nv;
+    double hmax = 0.0;
+    for (int32_t j = 0; j < maxiter; j++) {
+        const double *vj = V + (size_t)j * N;
+        double *w = V + (size_t)(j + 1) * N;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < N; i++) {
+            double sum = 0.0;
+            for (int32_t jj = Ap[i]; jj < Ap[i + 1]; jj++) sum += Ax[jj] * vj[Aj[jj]];
+            w[i] = row_scale ? row_scale[i] * sum : sum;
+        }
+        for (int32_t i = 0; i <= j; i++) {
+            const double *vi = V + (size_t)i * N;
+            const double h = chunked_dot(vi, w, N);
+            H[(size_t)i * maxiter + j] = h;
+#pragma omp parallel for schedule(static)
+            for (int64_t k = 0; k < N; k++) w[k] -= h * vi[k];
+        }
+        const double hn = std::sqrt(chunked_dot(w, w, N));
+        H[(size_t)(j + 1) * maxiter + j] = hn;
+        for (int32_t i = 0; i <= j; i++) hmax = std::max(hmax, std::fabs(H[(size_t)i * maxiter + j]));
+        for (int32_t jj = 0; jj < j; jj++) hmax = std::max(hmax, std::fabs(H[(size_t)j * maxiter + jj]));
+        if (!(hn >= breakdown * std::max(1.0, hmax))) return j + 1;
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < N; k++) w[k] /= hn;
+    }
+    return maxiter;
+}
+
 }  // extern "C"

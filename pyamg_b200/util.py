@@ -50,7 +50,15 @@ def _gpu_rho_enabled(where):
     return where == "gpu"
 
 
-def _approximate_spectral_radius_gpu(A, row_scale, v0, maxiter, restarts):
+def _ritz_converged(H, ev, evec, k, m, tol):
+    """linalg.py:351-365: |H[m, m-1] * (last component of the dominant Ritz vector)| / |ritz value| < tol."""
+    if m >= H.shape[1] + 1 or abs(ev[k]) == 0.0:
+        return False
+    error = H[m, m - 1] * evec[-1, k]
+    return bool(np.abs(error) / np.abs(ev[k]) < tol)
+
+
+def _approximate_spectral_radius_gpu(A, row_scale, v0, maxiter, restarts, tol):
     """The rounds below on the device (amgb_arnoldi_*): the operator is uploaded once, every round
     of modified-Gram-Schmidt Arnoldi runs without a host round trip, only the small Hessenberg matrix comes back for
     the eigen-decomposition that picks the restart vector (a combination of the resident basis)."""
@@ -76,21 +84,51 @@ def _approximate_spectral_radius_gpu(A, row_scale, v0, maxiter, restarts):
             ev, evec = np.linalg.eig(H[:m.value, :m.value])
             k = int(np.argmax(np.abs(ev)))
             rho = float(np.abs(ev[k]))
+            if _ritz_converged(H, ev, evec, k, m.value, tol) or m.value < maxiter:
+                break
             coef = np.ascontiguousarray(np.real(evec[:, k]), dtype=np.float64)
             E.check(L.amgb_arnoldi_combine(hdl, E.f64p(coef), m.value))
             start = None
-            if m.value < maxiter:
-                break
         return rho
     finally:
         L.amgb_arnoldi_destroy(hdl)
 
 
-def approximate_spectral_radius(A, maxiter=15, restarts=5, seed=20260922, row_scale=None, where=None):
+def _approximate_spectral_radius_host_native(A, row_scale, v0, maxiter, restarts, tol):
+    """The same rounds with the multi-threaded host kernel (csrc/host_setup.cpp amgb_setup_arnoldi_round): the
+    NumPy loop below spends its time in ~700 single-threaded vector passes per estimate, which dominates the SA
+    setups of the large benchmark inputs."""
+    from . import _host as Hh
+    A = sparse.csr_array(A)
+    n = A.shape[0]
+    Ap = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    Aj = np.ascontiguousarray(A.indices, dtype=np.int32)
+    Ax = np.ascontiguousarray(A.data, dtype=np.float64)
+    sc = None if row_scale is None else np.ascontiguousarray(row_scale, dtype=np.float64)
+    V = np.zeros((maxiter + 1, n))
+    H = np.zeros((maxiter + 1, maxiter))
+    V[0] = v0
+    rho = 0.0
+    for _ in range(restarts + 1):
+        m = Hh.lib().amgb_setup_arnoldi_round(n, Hh.ip(Ap), Hh.ip(Aj), Hh.dp(Ax), None if sc is None else Hh.dp(sc),
+                                              Hh.dp(V.reshape(-1)), maxiter, 1e-12, Hh.dp(H.reshape(-1)))
+        if m == 0:
+            break
+        ev, evec = np.linalg.eig(H[:m, :m])
+        k = int(np.argmax(np.abs(ev)))
+        rho = float(np.abs(ev[k]))
+        if _ritz_converged(H, ev, evec, k, m, tol) or m < maxiter:
+            break
+        V[0] = np.real(evec[:, k]) @ V[:m]                  # restart from the dominant Ritz vector
+    return rho
+
+
+def approximate_spectral_radius(A, maxiter=15, restarts=5, seed=20260922, row_scale=None, where=None, tol=0.01):
     """Largest |Ritz value| of a restarted Arnoldi process started from a seeded random vector.
 
-    Same estimator family as the reference (Arnoldi, 15 steps, 5 restarts; pyamg/util/linalg.py:255-383); the start
-    vector is seeded here, so the value is reproducible (the reference's is not: SURVEY.md hazard 2).
+    Same estimator as the reference (Arnoldi, 15 steps, up to 5 restarts, stop once the dominant Ritz pair's
+    residual estimate is below ``tol`` = 0.01 relative; pyamg/util/linalg.py:255-383); the start vector is seeded
+    here, so the value is reproducible (the reference's is not: SURVEY.md hazard 2).
     ``row_scale``: estimate rho(diag(row_scale) A) without forming the scaled matrix.  ``where='gpu'`` (or
     ``AMGB_GPU_RHO=1``) runs the Arnoldi rounds on the device -- same algorithm, values equal to rounding.
     """
@@ -102,7 +140,9 @@ def approximate_spectral_radius(A, maxiter=15, restarts=5, seed=20260922, row_sc
     v0 = rng.random(n)
     maxiter = int(min(maxiter, n))
     if _gpu_rho_enabled(where):
-        return _approximate_spectral_radius_gpu(A, row_scale, v0, maxiter, restarts)
+        return _approximate_spectral_radius_gpu(A, row_scale, v0, maxiter, restarts, tol)
+    if sparse.issparse(A) and A.format in ("csr", "bsr") and n >= 4096:
+        return _approximate_spectral_radius_host_native(A, row_scale, v0, maxiter, restarts, tol)
     if row_scale is not None:
         A = sparse.dia_array((np.asarray(row_scale), 0), shape=(n, n)) @ sparse.csr_array(A)
     rho = 0.0
@@ -127,9 +167,9 @@ def approximate_spectral_radius(A, maxiter=15, restarts=5, seed=20260922, row_sc
         ev, evec = np.linalg.eig(H[:m, :m])
         k = int(np.argmax(np.abs(ev)))
         rho = float(np.abs(ev[k]))
-        v0 = np.real(V[:m].T @ evec[:, k])   # restart from the dominant Ritz vector
-        if m < maxiter:
+        if _ritz_converged(H, ev, evec, k, m, tol) or m < maxiter:
             break
+        v0 = np.real(V[:m].T @ evec[:, k])   # restart from the dominant Ritz vector
     return rho
 
 

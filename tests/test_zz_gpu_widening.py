@@ -291,3 +291,49 @@ def test_sa_setup_with_gpu_spectral_radius_builds_the_same_hierarchy(monkeypatch
     for a, b in zip(ref.levels[:-1], gpu.levels[:-1]):
         assert a.presmoother.keywords["omega"] == pytest.approx(b.presmoother.keywords["omega"], rel=1e-12)
         assert abs(a.P - b.P).max() <= 1e-12 * abs(a.P).max()
+
+
+# ------------------------------------------------------------------ misuse of the new entry points fails loudly
+def test_new_entry_points_reject_bad_arguments():
+    import ctypes
+    from pyamg_b200 import _engine as E
+    L = E.lib()
+    A = sp.csr_array(np.array([[4.0, -1.0], [-1.0, 4.0]]))
+    keep = []
+    M = E.as_matrix(A, keep)
+    x, b = np.zeros(2), np.ones(2)
+    S = gpu_relax._descriptor()
+    S.kind = 99                                                    # unknown smoother kind
+    assert L.amgb_host_relax(M, S, E.f64p(x), E.f64p(b)) == E.ENOTIMPL
+    S.kind, S.n_coefficients = E.SM_POLYNOMIAL, 0                  # polynomial without coefficients
+    assert L.amgb_host_relax(M, S, E.f64p(x), E.f64p(b)) == E.EINVAL
+    S = gpu_relax._descriptor()
+    idx = np.array([0, 5], dtype=np.int32)                          # row index outside the matrix
+    S.kind, S.indices, S.n_indices = E.SM_JACOBI_INDEXED, E.i32p(idx), 2
+    assert L.amgb_host_relax(M, S, E.f64p(x), E.f64p(b)) == E.EINVAL
+    S = gpu_relax._descriptor()
+    S.kind, S.blocksize = E.SM_BLOCK_GAUSS_SEIDEL, 2                # block Gauss-Seidel without Dinv
+    assert L.amgb_host_relax(M, S, E.f64p(x), E.f64p(b)) == E.EINVAL
+    assert L.amgb_host_relax(None, S, E.f64p(x), E.f64p(b)) == E.EINVAL
+    # Arnoldi: run before any start vector, combination outside the basis
+    h = ctypes.c_void_p()
+    E.check(L.amgb_arnoldi_create(0, M, None, 5, ctypes.byref(h)))
+    H = np.zeros(3 * 2)
+    m = ctypes.c_int32(0)
+    assert L.amgb_arnoldi_run(h, None, 1e-12, E.f64p(H), ctypes.byref(m)) == E.ESTATE
+    coef = np.ones(4)
+    assert L.amgb_arnoldi_combine(h, E.f64p(coef), 4) == E.EINVAL
+    L.amgb_arnoldi_destroy(h)
+    # GMRES on a one-unknown system is the caller's closed form; the Python mirror handles it on the host
+    lvl = pyamg_b200.MultilevelSolver.Level()
+    lvl.A = sp.csr_array(np.array([[2.0]]))
+    ml1 = pyamg_b200.MultilevelSolver([lvl])
+    assert ml1.solve(np.array([4.0]), maxiter=1, tol=0)[0] == pytest.approx(2.0)
+    # cycle / accelerator combinations the reference rejects (multilevel.py:487-490)
+    from pyamg_b200.classical import ruge_stuben_solver
+    from pyamg_b200.gallery import poisson
+    ml = ruge_stuben_solver(poisson((8, 8)))
+    with pytest.raises(ValueError):
+        ml.solve(np.ones(64), cycle="AMLI", accel="gmres")
+    with pytest.raises(TypeError):
+        ml.solve(np.ones(64), cycle="Z", accel="fgmres")
