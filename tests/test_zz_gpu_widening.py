@@ -276,7 +276,7 @@ def test_gpu_arnoldi_matches_the_host_estimator():
             rh = approximate_spectral_radius(A, row_scale=scale, where="host")
             rg = approximate_spectral_radius(A, row_scale=scale, where="gpu")
             assert abs(rh - rg) <= 1e-11 * rh
-    assert approximate_spectral_radius(poisson((20, 20)), where="gpu") == pytest.approx(8.0, rel=1e-2)
+    assert approximate_spectral_radius(poisson((20, 20)), where="gpu") == pytest.approx(7.955, rel=2e-2)   # lambda_max of the 20 x 20 5-point Laplacian; the estimator stops at 1 % (tol)
 
 
 def test_sa_setup_with_gpu_spectral_radius_builds_the_same_hierarchy(monkeypatch):
