@@ -10,9 +10,10 @@ from . import relaxation
 from .relaxation.smoothing import change_smoothers
 from ._engine import pinned_empty, EngineError
 from . import gallery
+from . import krylov
 from .classical import ruge_stuben_solver
 from .aggregation import smoothed_aggregation_solver
 
 __version__ = "0.1.0"
 __all__ = ["MultilevelSolver", "coarse_grid_solver", "relaxation", "change_smoothers",
-           "pinned_empty", "EngineError", "gallery", "ruge_stuben_solver", "smoothed_aggregation_solver"]
+           "pinned_empty", "EngineError", "gallery", "krylov", "ruge_stuben_solver", "smoothed_aggregation_solver"]

@@ -349,7 +349,9 @@ class MultilevelSolver:
         def matvec(b):
             return self.solve(b, maxiter=1, cycle=cycle, tol=1e-12)
 
-        return LinearOperator(shape, matvec, dtype=dtype)
+        M = LinearOperator(shape, matvec, dtype=dtype)
+        M._amgb_solver, M._amgb_cycle = self, str(cycle).upper()     # lets pyamg_b200.krylov keep the solve resident
+        return M
 
     def solve(self, b, x0=None, tol=1e-5, maxiter=100, cycle="V", accel=None, callback=None,
               residuals=None, cycles_per_level=1, return_info=False, out=None):

@@ -339,3 +339,31 @@ def test_new_entry_points_reject_bad_arguments():
         ml.solve(np.ones(64), cycle="AMLI", accel="gmres")
     with pytest.raises(TypeError):
         ml.solve(np.ones(64), cycle="Z", accel="fgmres")
+
+
+def test_krylov_module_keeps_the_preconditioned_solve_resident(load_golden):
+    """pyamg.krylov-style calls `gmres(A, b, M=ml.aspreconditioner())`: with a pyamg_b200 preconditioner they run
+    resident and equal ml.solve(accel=...); other operators / preconditioners are refused loudly."""
+    import os
+    import warnings
+    from conftest import GOLDEN_DIR
+    from pyamg_b200 import krylov
+    ml, ex = load_golden("cfg3_rs_mcgs_poisson3d")
+    kg = np.load(os.path.join(GOLDEN_DIR, "krylov", "cfg3_rs_mcgs_poisson3d.npz"))
+    A = ml.levels[0].A
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = []
+        x, info = krylov.gmres(A, ex["b"], tol=1e-10, maxiter=12, M=ml.aspreconditioner("V"), residuals=res)
+        assert info == int(kg["info_gmres"][0]) and len(res) == len(kg["residuals_gmres"])
+        assert relerr(x, kg["x_ref_gmres"]) < 1e-9
+        x, info = krylov.fgmres(A.copy(), ex["b"], x0=ex["x0"], tol=1e-4, maxiter=25, M=ml.aspreconditioner("F"))
+        assert relerr(x, kg["x_ref_fgmresF"]) < 1e-9
+        x, info = krylov.cg(A, ex["b"], tol=1e-10, maxiter=10, M=ml.aspreconditioner())
+        assert relerr(x, ex["x_ref_cg"]) < 1e-11
+    with pytest.raises(NotImplementedError):
+        krylov.gmres(A, ex["b"], M=None)
+    with pytest.raises(NotImplementedError):
+        krylov.gmres(2.0 * A, ex["b"], M=ml.aspreconditioner())
+    with pytest.raises(NotImplementedError):
+        krylov.cg(A, ex["b"], M=ml.aspreconditioner(), callback=lambda xk: None)
