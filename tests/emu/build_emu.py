@@ -92,22 +92,34 @@ def transform(text, origin):
 
 def _digest():
     h = hashlib.sha256()
-    for d in (CSRC, HERE):
-        for f in sorted(os.listdir(d)):
-            p = os.path.join(d, f)
-            if os.path.isfile(p) and f.endswith((".cu", ".cuh", ".h", ".py")):
-                h.update(f.encode())
-                h.update(open(p, "rb").read())
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    files += [os.path.join(HERE, "cuda_runtime.h"), os.path.join(HERE, "build_emu.py")]
+    for p in files:
+        h.update(os.path.basename(p).encode())
+        h.update(open(p, "rb").read())
     h.update(open(os.path.join(ROOT, "include", "pyamg_b200.h"), "rb").read())
     return h.hexdigest()
 
 
 def build(force=False, verbose=False):
     """Returns the path of the emulation library (rebuilt when any source changed)."""
+    import fcntl
     stamp = LIB + ".sha256"
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+
+    def fresh():
+        return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig
+    if not force and fresh():
         return LIB
+    os.makedirs(GEN, exist_ok=True)
+    with open(os.path.join(GEN, ".lock"), "w") as lock:       # several ranks / test processes may get here at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and fresh():
+            return LIB
+        return _build_locked(dig, stamp, verbose)
+
+
+def _build_locked(dig, stamp, verbose):
     gdir = os.path.join(GEN, "pyamg_b200", "csrc")
     os.makedirs(gdir, exist_ok=True)
     os.makedirs(os.path.join(GEN, "include"), exist_ok=True)
@@ -119,10 +131,11 @@ def build(force=False, verbose=False):
                 o.write(transform(src, os.path.join(CSRC, f)))
     cmd = ["g++", "-x", "c++", "-std=c++17", "-O1", "-g", "-DAMGB_EMU", "-I", HERE, "-fPIC", "-shared",
            "-fno-strict-aliasing", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes",
-           os.path.join(gdir, "engine.cu"), "-o", LIB]
+           os.path.join(gdir, "engine.cu"), "-o", LIB + ".tmp"]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
+    os.replace(LIB + ".tmp", LIB)              # atomic: a process that already mapped the old library keeps it
     with open(stamp, "w") as o:
         o.write(dig)
     return LIB

@@ -618,6 +618,16 @@ inline cudaError_t cudaMalloc(void **p, size_t bytes)
     return cudaSuccess;
 }
 template <class T> inline cudaError_t cudaMalloc(T **p, size_t bytes) { return cudaMalloc((void **)p, bytes); }
+// memory the "device" did not allocate itself (torch CPU tensors standing in for CUDA tensors in the distributed
+// emulator test) is announced here so that the TMA source check knows it
+extern "C" __attribute__((visibility("default"))) void amgb_emu_register_allocation(void *p, size_t bytes)
+{
+    emu::g.allocs[(uintptr_t)p] = bytes;
+}
+extern "C" __attribute__((visibility("default"))) void amgb_emu_unregister_allocation(void *p)
+{
+    emu::g.allocs.erase((uintptr_t)p);
+}
 inline cudaError_t cudaFree(void *p)
 {
     if (p == nullptr) return cudaSuccess;
