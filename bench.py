@@ -350,7 +350,7 @@ def run_distributed(args, grid, ml, local, rank, world, tstream):
 
 
 OPS = {0: "spmv(restrict)", 1: "residual", 2: "prolong+add", 3: "jacobi", 4: "gs_wave", 5: "block_jacobi",
-       6: "coarse_tail(cluster kernel)", 7: "resident_gs(cluster, DSMEM)"}
+       6: "coarse_tail(cluster kernel)", 7: "resident_gs(cluster, DSMEM)", 8: "jacobi_indexed", 9: "block_gs_wave"}
 
 
 def main():

@@ -237,7 +237,8 @@ class MultilevelSolver:
         """Time every operator launch of one (un-graphed) cycle with CUDA events.
 
         Returns a float array (n, 6): level, op (0 spmv/restrict, 1 residual, 2 prolong+add, 3 jacobi,
-        4 gs wave, 5 block jacobi), rows, nnz, algorithmic bytes, milliseconds."""
+        4 gs wave, 5 block jacobi, 6 cluster tail, 7 resident GS, 8 indexed Jacobi, 9 block GS wave), rows, nnz,
+        algorithmic bytes, milliseconds."""
         rec = np.empty(max_records * 6, dtype=np.float64)
         nrec = ctypes.c_int32(0)
         E.check(E.lib().amgb_profile_cycle(self.handle, E.CYCLES[str(cycle).upper()], E.f64p(rec),
