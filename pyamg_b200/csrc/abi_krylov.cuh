@@ -228,9 +228,11 @@ extern "C" int amgb_solve_gmres(amgb_hierarchy *h, const double *b_host, double 
     cudaStream_t s = h->stream;
     h->launches = 0;
     if (h->gm_W == nullptr || h->gm_inner < mi || (flex && !h->gm_flex)) {
-        // (re)allocation: earlier, smaller buffers stay in the pool until the hierarchy is destroyed
+        CK(cudaStreamSynchronize(s));                    // nothing in flight may still use the buffers being replaced
+        h->dfree(h->gm_W);
+        h->dfree(h->gm_Z);
         RET(h->dalloc(&h->gm_W, (long long)(mi + 1) * G.npad));
-        if (flex) RET(h->dalloc(&h->gm_Z, (long long)mi * G.npad));
+        if (flex || h->gm_flex) RET(h->dalloc(&h->gm_Z, (long long)mi * G.npad));
         if (h->gm_s == nullptr) {
             for (int k = 0; k < 4; k++) RET(h->dalloc(&h->gm_vec[k], G.npad));
             for (int k = 0; k < 3; k++) RET(h->dalloc(&h->gm_lvl[k], G.npad));

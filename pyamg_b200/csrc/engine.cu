@@ -730,6 +730,17 @@ struct amgb_hierarchy {
         return AMGB_OK;
     }
 
+    // give a buffer of this pool back before the hierarchy dies (re-sized Krylov work space)
+    template <typename T>
+    void dfree(T *&p)
+    {
+        if (p == nullptr) return;
+        auto it = std::find(allocs.begin(), allocs.end(), (void *)p);
+        if (it != allocs.end()) allocs.erase(it);
+        cudaFree((void *)p);
+        p = nullptr;
+    }
+
     // `pad` extra elements are allocated (and zeroed) past the payload: the TMA reads whole 16-byte groups
     template <typename T>
     int upload(T **p, const T *src, long long count, int pad = 0)
