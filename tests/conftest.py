@@ -29,6 +29,7 @@ GOLDEN_WIDENING = [g for g in GOLDEN_ALL if _cfg_number(g) > 6]
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "timeout(seconds): pytest-timeout's per-test limit (a no-op without the plugin)")
     config.addinivalue_line("markers", "gpu_experimental: opt-in code paths not yet validated on hardware "
                                        "(run explicitly with -m gpu_experimental; never part of -m gpu)")
 

@@ -18,7 +18,8 @@ from pyamg_b200.relaxation import smoothing
 from conftest import GOLDEN_ALL, GOLDEN_WIDENING, golden_path, relerr, summation_order_sensitivity
 import test_gpu_parity as T
 
-pytestmark = pytest.mark.gpu
+# first hardware run of these kernels: a hang must not take the whole GPU tier down with it (pytest-timeout)
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 TOL = 1e-12
 
 
