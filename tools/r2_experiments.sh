@@ -34,3 +34,11 @@ S="$S;AMGB_TILE_FLAT=1,AMGB_TILE_CTAS=7"
 timeout 1500 python tools/tune_tiles.py --grid $G --settings "$S" 2>&1 | grep -E "cycle_ms|Error|error" | cut -c1-600
 echo "=== bench line (default settings)"
 timeout 900 python bench.py --steps 10 --warmup 3 2>/dev/null | tail -1 | tee gpurun_out/r2_bench_default.json | cut -c1-400
+echo "=== ncu: launch list of the widened rows + one full capture of the Galerkin SpGEMM and of a block-GS wave"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_widening_launches.csv \
+    python tools/time_widening.py --grid 48 > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:spgemm_row_kernel -c 3 \
+    -o gpurun_out/r2_spgemm python tools/time_widening.py --grid 64 > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:block_gs_kernel -c 2 \
+    -o gpurun_out/r2_block_gs python -m pytest tests/test_zz_gpu_widening.py -q -m gpu -k "vcycle_matches_reference_golden and cfg10" > /dev/null 2>&1
+
