@@ -408,7 +408,21 @@ class MultilevelSolver:
             if accel == "cg":
                 accel = _cg_host           # same algorithm on the host (callback wants host iterates)
             elif isinstance(accel, str):
-                accel = getattr(sla, accel)
+                # the reference looks the name up in pyamg.krylov first, then in scipy.sparse.linalg
+                # (multilevel.py:495-499); its host solvers are used when the reference is importable, with the GPU
+                # cycle as M (one host <-> device round trip per application)
+                try:
+                    from pyamg import krylov as ref_krylov
+                except ImportError:
+                    ref_krylov = None
+                if ref_krylov is not None and hasattr(ref_krylov, accel):
+                    accel = getattr(ref_krylov, accel)
+                elif hasattr(sla, accel):
+                    accel = getattr(sla, accel)
+                else:
+                    raise NotImplementedError(f"accel='{accel}': GPU-resident accelerators are 'cg', 'gmres' and "
+                                              "'fgmres'; other names need pyamg.krylov or scipy.sparse.linalg to "
+                                              "provide a host solver of that name")
             M = self.aspreconditioner(cycle=cycle)
             try:  # PyAMG style interface which has a residuals parameter (multilevel.py:503-508)
                 x, info = accel(A, b, x0=x0, tol=tol, maxiter=maxiter, M=M, callback=callback,
