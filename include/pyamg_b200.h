@@ -158,6 +158,12 @@ int amgb_solve_gmres(amgb_hierarchy *h, const double *b_host, double *x_host, do
                      int32_t maxiter, int32_t cycle, int32_t flags, double *residuals, int32_t max_residuals,
                      int32_t *n_residuals, int32_t *info);
 
+/* MultilevelSolver.solve(accel='bicgstab') resident in HBM: pyamg's right-preconditioned BiCGStab
+ * (pyamg/krylov/_bicgstab.py:10-200, criteria 'rr') with M = one multigrid cycle from x0 = 0.  residuals:
+ * maxiter+1 slots; *info: 0 converged, else maxiter.  Needs n >= 2. */
+int amgb_solve_bicgstab(amgb_hierarchy *h, const double *b_host, double *x_host, double tol, int32_t maxiter,
+                        int32_t cycle, int32_t flags, double *residuals, int32_t *n_residuals, int32_t *info);
+
 /* The same on DEVICE vectors (no host copies): x_dev in/out, b_dev in. Runs exactly `ncycles`
  * cycles (tol = 0 semantics); if norms2_dev != NULL it receives ncycles+1 squared residual norms. */
 int amgb_solve_device(amgb_hierarchy *h, const double *b_dev, double *x_dev, int32_t ncycles,

@@ -482,8 +482,16 @@ class Cycle:
                              matvec=lambda v: matvec(A0, v, self.kernels), callback=callback, residuals=residuals)
             x = x.reshape(np.shape(b))
             return (x, info) if return_info else x
+        if accel == "bicgstab":            # pyamg.krylov.bicgstab: oracle/krylov.py
+            from .krylov import bicgstab as _bicgstab
+            A0 = self.levels[0]["A"]
+            x, info = _bicgstab(A0, b, x0=x0, tol=tol, maxiter=maxiter,
+                                M=lambda r: self.solve(r, maxiter=1, cycle=cycle, tol=1e-12),
+                                matvec=lambda v: matvec(A0, v, self.kernels), callback=callback, residuals=residuals)
+            x = x.reshape(np.shape(b))
+            return (x, info) if return_info else x
         if accel is not None:
-            raise NotImplementedError("oracle: accel other than 'cg', 'gmres', 'fgmres'")
+            raise NotImplementedError("oracle: accel other than 'cg', 'gmres', 'fgmres', 'bicgstab'")
         x = np.zeros_like(b) if x0 is None else np.array(x0)
         A = self.levels[0]["A"]
         cycle = str(cycle).upper()

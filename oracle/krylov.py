@@ -203,3 +203,61 @@ def gmres(A, b, x0=None, tol=1e-5, restart=None, maxiter=None, M=None, callback=
             return x, 0
 
     return x, niter
+
+
+def bicgstab(A, b, x0=None, tol=1e-5, maxiter=None, M=None, callback=None, residuals=None, matvec=None):
+    """pyamg/krylov/_bicgstab.py:10-200 (criteria 'rr'): right-preconditioned BiCGStab, statement by statement."""
+    if matvec is None:
+        def matvec(v):
+            return A @ v
+    if M is None:
+        def M(v):
+            return v.copy()
+    b = np.ravel(np.asarray(b, dtype=np.float64))
+    n = len(b)
+    x = np.zeros(n) if x0 is None else np.array(np.ravel(x0), dtype=np.float64)
+    if maxiter is None:
+        maxiter = len(x) + 5
+    elif maxiter < 1:
+        raise ValueError("Number of iterations must be positive")
+    r = b - matvec(x)
+    normr = _norm(r)
+    if residuals is not None:
+        residuals[:] = [normr]
+    normb = _norm(b)
+    if normb == 0.0:
+        normb = 1.0
+    rtol = tol * normb
+    if normr < rtol:
+        return x, 0
+    if n == 1:
+        entry = np.ravel(matvec(np.array([1.0])))
+        return b / entry, 0
+    rstar = r.copy()
+    p = r.copy()
+    rrstarOld = np.inner(rstar.conjugate(), r)
+    it = 0
+    while True:
+        Mp = M(p)
+        AMp = matvec(Mp)
+        alpha = rrstarOld / np.inner(rstar.conjugate(), AMp)
+        s = r - alpha * AMp
+        Ms = M(s)
+        AMs = matvec(Ms)
+        omega = np.inner(AMs.conjugate(), s) / np.inner(AMs.conjugate(), AMs)
+        x = x + alpha * Mp + omega * Ms
+        r = s - omega * AMs
+        rrstarNew = np.inner(rstar.conjugate(), r)
+        beta = (rrstarNew / rrstarOld) * (alpha / omega)
+        rrstarOld = rrstarNew
+        p = r + beta * (p - omega * AMp)
+        it += 1
+        normr = _norm(r)
+        if residuals is not None:
+            residuals.append(normr)
+        if callback is not None:
+            callback(x)
+        if normr < rtol:
+            return x, 0
+        if it == maxiter:
+            return x, it

@@ -52,7 +52,7 @@ SYMBOLS = [
     "amgb_last_error", "amgb_version", "amgb_device_count",
     "amgb_hierarchy_create", "amgb_hierarchy_destroy", "amgb_hierarchy_add_level",
     "amgb_hierarchy_set_coarse_pinv", "amgb_hierarchy_finalize", "amgb_solve", "amgb_solve_ex", "amgb_solve_cg",
-    "amgb_solve_gmres",
+    "amgb_solve_gmres", "amgb_solve_bicgstab",
     "amgb_solve_device", "amgb_hierarchy_num_levels", "amgb_hierarchy_device_bytes",
     "amgb_hierarchy_last_launches", "amgb_profile_cycle", "amgb_host_alloc", "amgb_host_free",
     "amgb_operator_create", "amgb_operator_destroy", "amgb_operator_apply",
@@ -99,6 +99,7 @@ def _bind(L):
     L.amgb_solve.argtypes = [vp, vp, vp, f64, i32, i32, i32, c_f64p, c_i32p, c_i32p]
     L.amgb_solve_ex.argtypes = [vp, vp, vp, f64, i32, i32, i32, i32, c_f64p, c_i32p, c_i32p]
     L.amgb_solve_cg.argtypes = [vp, vp, vp, f64, i32, i32, i32, c_f64p, c_i32p, c_i32p]
+    L.amgb_solve_bicgstab.argtypes = [vp, vp, vp, f64, i32, i32, i32, c_f64p, c_i32p, c_i32p]
     L.amgb_solve_gmres.argtypes = [vp, vp, vp, f64, i32, i32, i32, i32, c_f64p, i32, c_i32p, c_i32p]
     L.amgb_solve_device.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     L.amgb_hierarchy_num_levels.argtypes = [vp]

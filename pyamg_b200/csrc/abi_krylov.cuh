@@ -407,3 +407,92 @@ extern "C" int amgb_solve_gmres(amgb_hierarchy *h, const double *b_host, double 
     h->last_launches = h->launches;
     return AMGB_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// GPU-resident right-preconditioned BiCGStab: ml.solve(accel='bicgstab') with every vector in HBM.
+// Restates pyamg/krylov/_bicgstab.py:10-200 (criteria 'rr') with M = one multigrid cycle from x0 = 0.  Like CG the
+// method is invariant under the level-0 row permutation, so all vectors live in the level numbering; the
+// preconditioned directions M p and M s are read straight out of the cycle's iterate buffer.
+// ------------------------------------------------------------------------------------------
+extern "C" int amgb_solve_bicgstab(amgb_hierarchy *h, const double *b_host, double *x_host, double tol, int32_t maxiter,
+                                   int32_t cycle, int32_t flags, double *residuals, int32_t *n_residuals, int32_t *info)
+{
+    RET(check_cycle_args(h, cycle, 1));
+    if (b_host == nullptr || x_host == nullptr) return fail(AMGB_EINVAL, "null host vector");
+    if (maxiter < 1) return fail(AMGB_EINVAL, "Number of iterations must be positive");    // _bicgstab.py:92-93
+    CK(cudaSetDevice(h->device));
+    Level &L0 = h->levels[0];
+    const long long n = L0.A.n_rows;
+    if (n < 2) return fail(AMGB_EINVAL, "bicgstab: n < 2 is the caller's closed form (b / A[0,0])");
+    cudaStream_t s = h->stream;
+    h->launches = 0;
+    if (h->kry[0] == nullptr)
+        for (int k = 0; k < 4; k++) RET(h->dalloc(&h->kry[k], n + 2));
+    if (h->kry2[0] == nullptr)
+        for (int k = 0; k < 4; k++) RET(h->dalloc(&h->kry2[k], n + 2));
+    double *xk = h->kry[0], *p = h->kry[1], *AMp = h->kry[2], *bk = h->kry[3];
+    double *r = h->kry2[0], *rstar = h->kry2[1], *sv = h->kry2[2], *AMs = h->kry2[3];
+    const size_t vbytes = sizeof(double) * (size_t)n;
+    RET(load_level0(h, b_host, (flags & AMGB_FLAG_X0_ZERO) ? nullptr : x_host, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(bk, L0.b, vbytes, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(xk, L0.x, vbytes, cudaMemcpyDeviceToDevice, s));
+    auto precond_of = [&](const double *v) -> int {        // L0.x <- M v
+        CK(cudaMemcpyAsync(L0.b, v, vbytes, cudaMemcpyDeviceToDevice, s));
+        L0.x = L0.x_home;
+        RET(h->launch_count_fill(L0.x, n));
+        return h->one_iteration(cycle, 1);
+    };
+    double t = 0, rrstar_old = 0, rrstar_new = 0, d1 = 0, d2 = 0;
+    RET(h->spmv(OP_RESID, L0.A, xk, bk, r));                          // r = b - A x             (:96)
+    RET(dev_dot(h, r, r, n, &t));
+    std::vector<double> res;
+    res.push_back(std::sqrt(t));                                      // :97-100
+    RET(dev_dot(h, bk, bk, n, &t));
+    double normb = std::sqrt(t);
+    if (normb == 0.0) normb = 1.0;                                    // :103-106
+    const double rtol = tol * normb;                                  // criteria 'rr' (:109-110)
+    int it = 0, status = -2;
+    if (res.back() < rtol) status = 0;                                // :122-123
+    if (status == -2) {
+        CK(cudaMemcpyAsync(rstar, r, vbytes, cudaMemcpyDeviceToDevice, s));   // :131-132
+        CK(cudaMemcpyAsync(p, r, vbytes, cudaMemcpyDeviceToDevice, s));
+        RET(dev_dot(h, rstar, r, n, &rrstar_old));                    // :134
+    }
+    while (status == -2) {
+        RET(precond_of(p));                                           // Mp = M p                (:140)
+        RET(h->spmv(OP_SPMV, L0.A, L0.x, nullptr, AMp));              // AMp = A Mp              (:141)
+        RET(dev_dot(h, rstar, AMp, n, &d1));
+        const double alpha = rrstar_old / d1;                         // :144
+        RET(dev_axpby(h, alpha, L0.x, 1.0, xk, n));                   // x += alpha Mp           (:155, first term)
+        CK(cudaMemcpyAsync(sv, r, vbytes, cudaMemcpyDeviceToDevice, s));
+        RET(dev_axpby(h, -alpha, AMp, 1.0, sv, n));                   // s = r - alpha AMp       (:147)
+        RET(precond_of(sv));                                          // Ms = M s                (:148)
+        RET(h->spmv(OP_SPMV, L0.A, L0.x, nullptr, AMs));              // AMs = A Ms              (:149)
+        RET(dev_dot(h, AMs, sv, n, &d1));
+        RET(dev_dot(h, AMs, AMs, n, &d2));
+        const double omega = d1 / d2;                                 // :152
+        RET(dev_axpby(h, omega, L0.x, 1.0, xk, n));                   // x += omega Ms           (:155, second term)
+        CK(cudaMemcpyAsync(r, sv, vbytes, cudaMemcpyDeviceToDevice, s));
+        RET(dev_axpby(h, -omega, AMs, 1.0, r, n));                    // r = s - omega AMs       (:158)
+        RET(dev_dot(h, rstar, r, n, &rrstar_new));                    // :161
+        const double beta = (rrstar_new / rrstar_old) * (alpha / omega);      // :162
+        rrstar_old = rrstar_new;
+        RET(dev_axpby(h, -omega, AMp, 1.0, p, n));                    // p - omega AMp
+        RET(dev_axpby(h, 1.0, r, beta, p, n));                        // p = r + beta (p - omega AMp)   (:166)
+        it++;
+        RET(dev_dot(h, r, r, n, &t));
+        res.push_back(std::sqrt(t));                                  // :170-173
+        if (res.back() < rtol) { status = 0; break; }                 // :184-185
+        if (it == maxiter) { status = it; break; }                    // :187-188
+    }
+    CK(cudaMemcpyAsync(L0.x_home, xk, vbytes, cudaMemcpyDeviceToDevice, s));
+    L0.x = L0.x_home;
+    RET(store_level0(h, x_host, cudaMemcpyDeviceToHost));
+    CK(cudaStreamSynchronize(s));
+    if (residuals != nullptr)
+        for (size_t k = 0; k < res.size() && k < (size_t)maxiter + 1; k++) residuals[k] = res[k];
+    if (n_residuals != nullptr) *n_residuals = (int32_t)res.size();
+    if (info != nullptr) *info = status;
+    h->last_launches = h->launches;
+    return AMGB_OK;
+}

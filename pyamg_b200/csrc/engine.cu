@@ -659,6 +659,7 @@ struct amgb_hierarchy {
     double *norm_host = nullptr;  // pinned scalar for the tol test
     double *sumsq_parts = nullptr;
     double *kry[4] = {nullptr, nullptr, nullptr, nullptr};   // Krylov work vectors (allocated on first use)
+    double *kry2[4] = {nullptr, nullptr, nullptr, nullptr};  // BiCGStab's additional four
     // Householder GMRES / FGMRES (amgb_solve_gmres): reflectors W, preconditioned directions Z (flexible), work
     // vectors in the original numbering (v, x, b, update) and in level-0 numbering (b, SpMV in/out), device scalars
     double *gm_W = nullptr, *gm_Z = nullptr, *gm_vec[4] = {nullptr, nullptr, nullptr, nullptr};

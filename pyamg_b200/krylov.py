@@ -13,7 +13,7 @@ SciPy's / the reference's host solvers accept the same ``M`` unchanged.
 """
 import numpy as np
 
-__all__ = ["cg", "gmres", "fgmres"]
+__all__ = ["cg", "gmres", "fgmres", "bicgstab"]
 
 
 def _resident(A, M, name):
@@ -64,3 +64,10 @@ def gmres(A, b, x0=None, tol=1e-5, restart=None, maxiter=None, M=None, callback=
 def fgmres(A, b, x0=None, tol=1e-5, restart=None, maxiter=None, M=None, callback=None, residuals=None, **kwargs):
     """pyamg.krylov.fgmres (krylov/_fgmres.py:17-345) with the cycle ``M``, resident."""
     return _run("fgmres", A, b, x0, tol, maxiter, M, callback, residuals, restart)
+
+
+def bicgstab(A, b, x0=None, tol=1e-5, criteria="rr", maxiter=None, M=None, callback=None, residuals=None):
+    """pyamg.krylov.bicgstab (krylov/_bicgstab.py:10-200) with the cycle ``M``, resident (criteria 'rr' only)."""
+    if criteria != "rr":
+        raise NotImplementedError("pyamg_b200.krylov.bicgstab: stopping criteria 'rr' only")
+    return _run("bicgstab", A, b, x0, tol, maxiter, M, callback, residuals)

@@ -291,23 +291,25 @@ class MultilevelSolver:
         smoothing.rebuild_smoother(self.levels[0])
         self._invalidate()
 
-    def _solve_cg_device(self, b, x0, tol, maxiter, cycle, residuals, return_info):
-        """solve(accel='cg') on the GPU: pyamg's CG (pyamg/krylov/_cg.py) preconditioned by one cycle."""
+    def _solve_cg_device(self, b, x0, tol, maxiter, cycle, residuals, return_info, method="cg"):
+        """solve(accel='cg' | 'bicgstab') on the GPU: pyamg's CG (pyamg/krylov/_cg.py) or BiCGStab (_bicgstab.py)
+        preconditioned by one cycle."""
         b = np.asarray(b)
         n = self.levels[0].A.shape[0]
         if b.size != n or (x0 is not None and np.asarray(x0).size != n):
             raise ValueError("b / x0 have invalid dimensions")
         if maxiter is None:
-            maxiter = int(1.3 * n) + 2                        # _cg.py:92-93
+            maxiter = int(1.3 * n) + 2 if method == "cg" else n + 5     # _cg.py:92-93, _bicgstab.py:90-91
         elif maxiter < 1:
             raise ValueError("Number of iterations must be positive")
         bh = np.ascontiguousarray(np.ravel(b), dtype=np.float64)
         xh = np.zeros(n) if x0 is None else np.array(np.ravel(x0), dtype=np.float64)
         res = np.empty(int(maxiter) + 1, dtype=np.float64)
         nres, info = ctypes.c_int32(0), ctypes.c_int32(0)
-        E.check(E.lib().amgb_solve_cg(self.handle, bh.ctypes.data, xh.ctypes.data, float(tol), int(maxiter),
-                                      E.CYCLES[cycle], E.FLAG_X0_ZERO if x0 is None else 0, E.f64p(res),
-                                      ctypes.byref(nres), ctypes.byref(info)))
+        fn = E.lib().amgb_solve_cg if method == "cg" else E.lib().amgb_solve_bicgstab
+        E.check(fn(self.handle, bh.ctypes.data, xh.ctypes.data, float(tol), int(maxiter),
+                   E.CYCLES[cycle], E.FLAG_X0_ZERO if x0 is None else 0, E.f64p(res),
+                   ctypes.byref(nres), ctypes.byref(info)))
         if info.value == -1:
             warn("\nIndefinite matrix or preconditioner detected in CG, aborting\n")
         if residuals is not None:
@@ -399,6 +401,10 @@ class MultilevelSolver:
                 # pyamg.krylov.cg (what the reference resolves 'cg' to, multilevel.py:495-499) with every
                 # vector resident in HBM: amgb_solve_cg
                 return self._solve_cg_device(b, x0, tol, maxiter, cycle, residuals, return_info)
+            if accel == "bicgstab" and callback is None and not np.iscomplexobj(b) \
+                    and self.levels[0].A.shape[0] > 1:
+                # pyamg.krylov.bicgstab (right-preconditioned, criteria 'rr') resident: amgb_solve_bicgstab
+                return self._solve_cg_device(b, x0, tol, maxiter, cycle, residuals, return_info, method="bicgstab")
             if accel in ("gmres", "fgmres") and callback is None and not np.iscomplexobj(b) \
                     and self.levels[0].A.shape[0] > 1:
                 # pyamg.krylov.gmres (Householder) / pyamg.krylov.fgmres, what the reference resolves these

@@ -100,7 +100,9 @@ def emit_krylov(name, ml, b, x0):
                         ("gmresW", dict(x0=x0, tol=1e-3, maxiter=25, accel="gmres", cycle="W")),
                         ("fgmres", dict(tol=1e-10, maxiter=12, accel="fgmres")),
                         ("fgmresF", dict(x0=x0, tol=1e-4, maxiter=25, accel="fgmres", cycle="F")),
-                        ("fgmresAMLI", dict(tol=1e-8, maxiter=5, accel="fgmres", cycle="AMLI"))):
+                        ("fgmresAMLI", dict(tol=1e-8, maxiter=5, accel="fgmres", cycle="AMLI")),
+                        ("bicgstab", dict(tol=1e-10, maxiter=8, accel="bicgstab")),
+                        ("bicgstabW", dict(x0=x0, tol=1e-4, maxiter=20, accel="bicgstab", cycle="W"))):
             res = []
             x, info = ml.solve(b, residuals=res, return_info=True, **kw)
             out["x_ref_" + tag] = x
@@ -109,7 +111,7 @@ def emit_krylov(name, ml, b, x0):
     os.makedirs(os.path.join(HERE, "krylov"), exist_ok=True)
     np.savez_compressed(os.path.join(HERE, "krylov", name + ".npz"), **out)
     print(f"krylov/{name}: " + ", ".join(f"{t}: {len(out['residuals_' + t]) - 1} its info={int(out['info_' + t][0])}"
-                                       for t in ("gmres", "gmresW", "fgmres", "fgmresF", "fgmresAMLI")))
+                                       for t in ("gmres", "gmresW", "fgmres", "fgmresF", "fgmresAMLI", "bicgstab", "bicgstabW")))
 
 
 def emit(name, ml, extra_kw=None, ncyc=NCYC, cg_anyway=True):

@@ -190,7 +190,9 @@ KRYLOV_RUNS = {"gmres": dict(tol=1e-10, maxiter=12, accel="gmres"),
                "gmresW": dict(tol=1e-3, maxiter=25, accel="gmres", cycle="W"),
                "fgmres": dict(tol=1e-10, maxiter=12, accel="fgmres"),
                "fgmresF": dict(tol=1e-4, maxiter=25, accel="fgmres", cycle="F"),
-               "fgmresAMLI": dict(tol=1e-8, maxiter=5, accel="fgmres", cycle="AMLI")}
+               "fgmresAMLI": dict(tol=1e-8, maxiter=5, accel="fgmres", cycle="AMLI"),
+               "bicgstab": dict(tol=1e-10, maxiter=8, accel="bicgstab"),
+               "bicgstabW": dict(tol=1e-4, maxiter=20, accel="bicgstab", cycle="W")}
 
 
 @pytest.mark.parametrize("name", GOLDEN)
@@ -205,7 +207,7 @@ def test_oracle_gmres_and_fgmres_match_reference(name, load_golden):
     cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.P)
     for tag, kw in KRYLOV_RUNS.items():
         kw = dict(kw)
-        if tag in ("gmresW", "fgmresF"):
+        if tag in ("gmresW", "fgmresF", "bicgstabW"):
             kw["x0"] = ex["x0"]
         res = []
         x, info = cyc.solve(ex["b"], residuals=res, return_info=True, **kw)

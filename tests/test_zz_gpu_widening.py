@@ -195,7 +195,7 @@ def test_gpu_resident_gmres_and_fgmres_match_reference_golden(name, load_golden)
         warnings.simplefilter("ignore")
         for tag, kw in KRYLOV_RUNS.items():
             kw = dict(kw)
-            if tag in ("gmresW", "fgmresF"):
+            if tag in ("gmresW", "fgmresF", "bicgstabW"):
                 kw["x0"] = ex["x0"]
             res = []
             x, info = ml.solve(ex["b"], residuals=res, return_info=True, **kw)
@@ -362,6 +362,8 @@ def test_krylov_module_keeps_the_preconditioned_solve_resident(load_golden):
         assert relerr(x, kg["x_ref_fgmresF"]) < 1e-9
         x, info = krylov.cg(A, ex["b"], tol=1e-10, maxiter=10, M=ml.aspreconditioner())
         assert relerr(x, ex["x_ref_cg"]) < 1e-11
+        x, info = krylov.bicgstab(A, ex["b"], tol=1e-10, maxiter=8, M=ml.aspreconditioner())
+        assert info == int(kg["info_bicgstab"][0]) and relerr(x, kg["x_ref_bicgstab"]) < 1e-9
     with pytest.raises(NotImplementedError):
         krylov.gmres(A, ex["b"], M=None)
     with pytest.raises(NotImplementedError):
