@@ -119,6 +119,12 @@ int amgb_hierarchy_add_level(amgb_hierarchy *h, const amgb_matrix *A, const amgb
 int amgb_hierarchy_set_coarse_pinv(amgb_hierarchy *h, int32_t n, const double *pinv,
                                    int32_t coarse_is_zero);
 
+/* Coarsest-level solver = relaxation (multilevel.py:764-781: coarse_solver='gauss_seidel' | 'jacobi' | 'sor' |
+ * 'block_jacobi' | 'block_gauss_seidel' | 'richardson' | 'chebyshev', default 10 iterations): x = 0, then the
+ * smoother `sm` applied once (its `iterations` sweeps).  Call after the last amgb_hierarchy_add_level instead of
+ * amgb_hierarchy_set_coarse_pinv. */
+int amgb_hierarchy_set_coarse_relaxation(amgb_hierarchy *h, const amgb_smoother *sm);
+
 /* Allocate work vectors, build wave schedules, capture CUDA graphs.  stream == NULL -> the
  * engine's own stream; otherwise every launch goes to the caller's stream (a cudaStream_t). */
 int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream);

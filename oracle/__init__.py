@@ -383,6 +383,10 @@ def hierarchy_spec(ml):
             d["pre"] = smoother_spec(getattr(lvl, "presmoother", None))
             d["post"] = smoother_spec(getattr(lvl, "postsmoother", None))
         levels.append(d)
+    # a relaxation method as the coarsest-level solver (multilevel.py:764-781): recorded on the last level
+    cs = getattr(ml, "coarse_solver", None)
+    if getattr(cs, "relaxation", None) is not None and levels:
+        levels[-1]["coarse_relax"] = smoother_spec(cs.smoother(levels[-1]["A"]))
     return levels
 
 
@@ -462,6 +466,11 @@ class Cycle:
     def coarse_solve(self, A, b):
         if A.nnz == 0:
             return np.zeros(b.shape)
+        relax = self.levels[-1].get("coarse_relax")
+        if relax is not None:                      # multilevel.py:773-779: x = 0; relax(A, x, b)
+            x = np.zeros_like(b)
+            _smooth(relax, A, x, np.ascontiguousarray(b), self.kernels)
+            return x
         if self.coarse_pinv is None:
             self.coarse_pinv = pinv(A.toarray())
         return np.dot(self.coarse_pinv, b)

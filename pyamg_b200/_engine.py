@@ -51,7 +51,7 @@ _lib = None
 SYMBOLS = [
     "amgb_last_error", "amgb_version", "amgb_device_count",
     "amgb_hierarchy_create", "amgb_hierarchy_destroy", "amgb_hierarchy_add_level",
-    "amgb_hierarchy_set_coarse_pinv", "amgb_hierarchy_finalize", "amgb_solve", "amgb_solve_ex", "amgb_solve_cg",
+    "amgb_hierarchy_set_coarse_pinv", "amgb_hierarchy_set_coarse_relaxation", "amgb_hierarchy_finalize", "amgb_solve", "amgb_solve_ex", "amgb_solve_cg",
     "amgb_solve_gmres", "amgb_solve_bicgstab",
     "amgb_solve_device", "amgb_hierarchy_num_levels", "amgb_hierarchy_device_bytes",
     "amgb_hierarchy_last_launches", "amgb_profile_cycle", "amgb_host_alloc", "amgb_host_free",
@@ -95,6 +95,7 @@ def _bind(L):
                                            ctypes.POINTER(Matrix), ctypes.POINTER(Smoother),
                                            ctypes.POINTER(Smoother)]
     L.amgb_hierarchy_set_coarse_pinv.argtypes = [vp, i32, c_f64p, i32]
+    L.amgb_hierarchy_set_coarse_relaxation.argtypes = [vp, ctypes.POINTER(Smoother)]
     L.amgb_hierarchy_finalize.argtypes = [vp, vp]
     L.amgb_solve.argtypes = [vp, vp, vp, f64, i32, i32, i32, c_f64p, c_i32p, c_i32p]
     L.amgb_solve_ex.argtypes = [vp, vp, vp, f64, i32, i32, i32, i32, c_f64p, c_i32p, c_i32p]

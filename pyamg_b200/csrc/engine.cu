@@ -647,6 +647,10 @@ struct amgb_hierarchy {
     int coarse_n = 0;
     bool coarse_zero = false;
     bool have_coarse = false;
+    // relaxation as the coarse solver (multilevel.py:764-781): x = 0, then `iterations` sweeps of a smoother
+    bool coarse_relax = false;
+    SmootherSpec coarse_spec;
+    Smoother coarse_sm;
 
     // level-0 wave-major permutation (device): order0[new] = old, pos0[old] = new; null = identity
     int *order0 = nullptr, *pos0 = nullptr;
@@ -1050,6 +1054,20 @@ struct amgb_hierarchy {
     int coarse_solve(Level &Lc)
     {
         if (coarse_zero) return launch_count_fill(Lc.x, Lc.A.n_rows);
+        if (coarse_relax) {                                             // :773-779
+            Lc.x = Lc.x_home;
+            RET(launch_count_fill(Lc.x, Lc.A.n_rows));
+            RET(smooth(Lc, coarse_sm));
+            if (Lc.x != Lc.x_home) {                                    // odd number of Jacobi ping-pongs
+                if (recording) {
+                    RET(record(T_COPY, 1, 0, Lc.A.n_rows, nullptr, nullptr, Lc.x, nullptr, Lc.x_home, 0.0, 16.0 * Lc.A.n_rows));
+                } else {
+                    RET(copy_vec(Lc.x_home, Lc.x, Lc.A.n_rows));
+                }
+                std::swap(Lc.x, Lc.xalt);
+            }
+            return AMGB_OK;
+        }
         const int n = coarse_n;
         if (recording)
             return record(T_DENSE, 32, 0, n, nullptr, nullptr, Lc.b, nullptr, Lc.x, 0.0, 8.0 * n * n + 16.0 * n,
@@ -1681,6 +1699,7 @@ int amgb_hierarchy::finalize_levels()
             RET(make_smoother(H.pre, *Ause, pv, sh_pre, L.pre));
             RET(make_smoother(H.post, *Ause, pv, sh_post, L.post));
         }
+        if (!H.has_pr && coarse_relax) RET(make_smoother(coarse_spec, *Ause, nullptr, nullptr, coarse_sm));
         if (l == 0 && permuted) {
             RET(upload(&order0, order[0].data(), (long long)order[0].size()));
             RET(upload(&pos0, pos[0].data(), (long long)pos[0].size()));
@@ -1844,6 +1863,21 @@ extern "C" int amgb_hierarchy_set_coarse_pinv(amgb_hierarchy *h, int32_t n, cons
     return AMGB_OK;
 }
 
+extern "C" int amgb_hierarchy_set_coarse_relaxation(amgb_hierarchy *h, const amgb_smoother *sm)
+{
+    if (h == nullptr || sm == nullptr) return fail(AMGB_EINVAL, "null argument");
+    if (h->finalized) return fail(AMGB_ESTATE, "hierarchy already finalized");
+    if (h->host.empty()) return fail(AMGB_ESTATE, "no levels");
+    if (h->host.back().has_pr) return fail(AMGB_ESTATE, "the coarsest level must be added first (without P/R)");
+    if (sm->kind == AMGB_SM_NONE) return fail(AMGB_EINVAL, "coarse relaxation: a smoother kind is required");
+    RET(copy_smoother(sm, h->host.back().A, h->coarse_spec));
+    h->coarse_relax = true;
+    h->coarse_zero = false;
+    h->coarse_n = h->host.back().A.n_rows;
+    h->have_coarse = true;
+    return AMGB_OK;
+}
+
 extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
 {
     if (h == nullptr) return fail(AMGB_EINVAL, "null hierarchy");
@@ -1879,7 +1913,8 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
             const Level &L = h->levels[(size_t)l];
             // only the kinds the cluster interpreter knows (none, Jacobi, Gauss-Seidel) may run in the tail
             const bool blocky = L.has_pr && (L.pre.kind > AMGB_SM_GAUSS_SEIDEL || L.post.kind > AMGB_SM_GAUSS_SEIDEL);
-            if (L.A.nnz > h->tail_nnz_limit || blocky) break;
+            const bool coarse_blocky = !L.has_pr && h->coarse_relax && h->coarse_sm.kind > AMGB_SM_GAUSS_SEIDEL;
+            if (L.A.nnz > h->tail_nnz_limit || blocky || coarse_blocky) break;
             tl = l;
         }
         if (!(nt && nt[0] == '1') && tl < nl) {
@@ -1909,7 +1944,8 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
             fprintf(stderr, "[amgb] levels=%d tail_level=%d cluster=%d tile_cfg=%d ctas/sm=%d hints=%d\n", nl,
                     h->tail_level < nl ? h->tail_level : -1, h->tail_csize, g_tile_cfg, g_tile_ctas[OP_GS], g_tile_hints);
     }
-    if (!h->coarse_zero) RET(h->upload(&h->coarse_pinv, h->coarse_host.data(), (long long)h->coarse_host.size()));
+    if (!h->coarse_zero && !h->coarse_relax)
+        RET(h->upload(&h->coarse_pinv, h->coarse_host.data(), (long long)h->coarse_host.size()));
     h->coarse_host.clear();
     for (Level &L : h->levels) {
         const long long n = L.A.n_rows;
@@ -1918,7 +1954,8 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
         RET(h->dalloc(&L.b, n + 2));
         RET(h->dalloc(&L.r, n + 2));
         L.x = L.x_home;
-        if (L.has_pr && (L.pre.kind == AMGB_SM_POLYNOMIAL || L.post.kind == AMGB_SM_POLYNOMIAL)) {
+        if ((L.has_pr && (L.pre.kind == AMGB_SM_POLYNOMIAL || L.post.kind == AMGB_SM_POLYNOMIAL)) ||
+            (!L.has_pr && h->coarse_relax && h->coarse_sm.kind == AMGB_SM_POLYNOMIAL)) {
             RET(h->dalloc(&L.poly[0], n + 2));
             RET(h->dalloc(&L.poly[1], n + 2));
         }

@@ -94,8 +94,8 @@ def save_hierarchy(path, ml, extra=None, compressed=True):
             m["pre"] = _put_smoother(out, f"L{k}_pre", getattr(lvl, "presmoother", None))
             m["post"] = _put_smoother(out, f"L{k}_post", getattr(lvl, "postsmoother", None))
         meta["levels"].append(m)
-    name = ml.coarse_solver.name() if hasattr(ml.coarse_solver, "name") else "'pinv'"
-    meta["coarse_solver"] = name
+    from .multilevel import coarse_solver_spec
+    meta["coarse_solver"] = repr(coarse_solver_spec(ml.coarse_solver))     # name or (name, kwargs)
     meta["symmetric_smoothing"] = bool(getattr(ml, "symmetric_smoothing", False))
     cached = getattr(ml.coarse_solver, "P", None)
     if cached is not None:

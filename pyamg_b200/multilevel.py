@@ -31,13 +31,48 @@ from .relaxation import smoothing
 __all__ = ["MultilevelSolver", "coarse_grid_solver"]
 
 
+def coarse_solver_spec(cs):
+    """The ``coarse_solver=`` argument a coarse solver object was built from: ``name`` or ``(name, kwargs)``.
+
+    The reference's ``GenericSolver.name()`` returns only the method name (multilevel.py:820-823); its keyword
+    arguments -- e.g. the sweep count of a relaxation coarse solver -- live in the closure of the ``solve`` function
+    its ``__call__`` uses (:700-790).  They are read from there, so that a reference-built hierarchy is adopted with
+    the coarse solver it really has."""
+    import ast
+    own = getattr(cs, "spec", None)
+    if own is not None:
+        return own
+    name = cs.name() if hasattr(cs, "name") else "'pinv'"
+    try:
+        name = ast.literal_eval(name)
+    except (ValueError, SyntaxError) as exc:
+        raise NotImplementedError(f"coarse solver {name} is not on the GPU hot path") from exc
+    kwargs = {}
+    try:
+        call = type(cs).__call__
+        cells = dict(zip(call.__code__.co_freevars, [c.cell_contents for c in call.__closure__ or ()]))
+        solve = cells.get("solve")
+        if solve is not None and solve.__closure__:
+            kwargs = dict(zip(solve.__code__.co_freevars, [c.cell_contents for c in solve.__closure__])).get("kwargs", {})
+    except (AttributeError, TypeError, ValueError):
+        kwargs = {}
+    if isinstance(name, tuple):
+        return name
+    return (name, dict(kwargs)) if kwargs else name
+
+
+# relaxation methods usable as the coarsest-level solver (multilevel.py:764-766) that the engine runs
+_RELAXATION_COARSE = ("gauss_seidel", "jacobi", "block_gauss_seidel", "block_jacobi", "richardson", "sor", "chebyshev")
+
+
 def coarse_grid_solver(solver):
     """Coarse-level solver descriptor (pyamg/multilevel.py:665-826).
 
     The engine applies the coarsest solve as a dense matrix-vector product with a matrix computed
     once on the CPU: the pseudo-inverse for 'pinv'/'pinv2' (what the reference caches, :717-721),
     the plain inverse for the direct methods 'lu'/'cholesky'/'splu' (same solve, different
-    rounding).  Iterative / relaxation coarse solvers are outside the accelerated path.
+    rounding).  Relaxation methods (:764-781: x = 0, then `iterations` sweeps, default 10) run as the engine's
+    smoother kernels on the coarsest level.  Krylov coarse solvers are outside the accelerated path.
     """
     def unpack_arg(v):
         if isinstance(v, tuple):
@@ -54,14 +89,32 @@ def coarse_grid_solver(solver):
     elif name is None:
         def dense(A):
             return np.zeros(A.shape)
+    elif name in _RELAXATION_COARSE:
+        dense = None                                  # x = 0, then `iterations` (default 10) sweeps on the GPU
+        kwargs = dict(kwargs)
+        kwargs.setdefault("iterations", 10)           # multilevel.py:768-769
     elif isinstance(name, str) or callable(name):
         raise NotImplementedError(f"coarse solver {name!r} is not on the GPU hot path; use 'pinv' "
-                                  "(the reference's default), 'lu', 'cholesky', 'splu' or None")
+                                  "(the reference's default), 'lu', 'cholesky', 'splu', a relaxation method "
+                                  f"({', '.join(_RELAXATION_COARSE)}) or None")
     else:
         raise ValueError(f"unknown solver: {name}")
 
+    relax_spec = (name, kwargs) if dense is None else None
+    relax_name = name                                 # (`name` itself is shadowed inside the class body below)
+
     class GenericSolver:
-        """Holds the cached dense operator; applied on the GPU by the cycle engine."""
+        """Holds the cached dense operator (or the relaxation descriptor); applied on the GPU by the cycle engine."""
+        relaxation = relax_spec
+        spec = solver                                 # what this object was built from (see coarse_solver_spec)
+        if relax_spec is not None:
+            P = None                                  # no dense operator: the solve is `iterations` GPU sweeps
+
+        def smoother(self, A):
+            """The closure the reference builds for a relaxation coarse solver (multilevel.py:773-776)."""
+            lvl = MultilevelSolver.Level()
+            lvl.A = A
+            return smoothing._setup_call(relax_name)(lvl, **kwargs)
 
         def dense_operator(self, A):
             if not hasattr(self, "P"):
@@ -163,12 +216,7 @@ class MultilevelSolver:
     def from_pyamg(cls, ml, device=0, stream=None):
         """Adopt a hierarchy built by the reference (any ``pyamg`` constructor): same Level
         objects, same smoother closures, same coarse solver kind (and its cached pinv if any)."""
-        name = ml.coarse_solver.name() if hasattr(ml.coarse_solver, "name") else "'pinv'"
-        try:
-            import ast
-            spec = ast.literal_eval(name)
-        except (ValueError, SyntaxError) as exc:
-            raise NotImplementedError(f"coarse solver {name} is not on the GPU hot path") from exc
+        spec = coarse_solver_spec(ml.coarse_solver)
         new = cls(list(ml.levels), coarse_solver=spec, device=device, stream=stream)
         new.symmetric_smoothing = getattr(ml, "symmetric_smoothing", False)
         cached = getattr(ml.coarse_solver, "P", None)
@@ -214,6 +262,10 @@ class MultilevelSolver:
             Ac = self.levels[-1].A
             if Ac.nnz == 0:     # GenericSolver.__call__, multilevel.py:801-803
                 E.check(L.amgb_hierarchy_set_coarse_pinv(h, Ac.shape[0], None, 1))
+            elif getattr(self.coarse_solver, "relaxation", None) is not None:
+                keep = []
+                S = smoothing.describe(self.coarse_solver.smoother(Ac), Ac, keep)
+                E.check(L.amgb_hierarchy_set_coarse_relaxation(h, ctypes.byref(S)))
             else:
                 Pd = self.coarse_solver.dense_operator(Ac)
                 E.check(L.amgb_hierarchy_set_coarse_pinv(h, Ac.shape[0], E.f64p(Pd.reshape(-1)), 0))

@@ -85,6 +85,7 @@ def kernel_goldens(ml, rng):
     return out
 
 
+ONLY = None               # --only <name>: write just this configuration's files
 KRYLOV_ONLY = False       # --krylov: rebuild the same hierarchies, write only the GMRES / FGMRES goldens
 
 
@@ -115,6 +116,8 @@ def emit_krylov(name, ml, b, x0):
 
 
 def emit(name, ml, extra_kw=None, ncyc=NCYC, cg_anyway=True):
+    if ONLY is not None and name != ONLY:
+        return
     rng = np.random.default_rng(SEED)
     n = ml.levels[0].A.shape[0]
     b = rng.random(n)
@@ -228,6 +231,13 @@ def main_widening():
     ml = pyamg.air_solver(A.tocsr())
     emit("cfg9_air_fcjacobi_advection2d", ml, cg_anyway=False)
 
+    # cfg11: relaxation as the coarsest-level solver (multilevel.py:764-781): 4 symmetric Gauss-Seidel sweeps on a
+    # 57-unknown coarsest level instead of the pseudo-inverse
+    np.random.seed(SEED)
+    A = poisson((30, 30), format="csr")
+    ml = pyamg.ruge_stuben_solver(A, max_coarse=60, coarse_solver=("gauss_seidel", {"iterations": 4, "sweep": "symmetric"}))
+    emit("cfg11_rs_gs_coarse_relaxation", ml)
+
     # cfg10: linear elasticity with the reference's DEFAULT SA smoothers (symmetric block Gauss-Seidel)
     np.random.seed(SEED)
     A, B = linear_elasticity((12, 12))
@@ -236,6 +246,8 @@ def main_widening():
 
 
 if __name__ == "__main__":
+    if "--only" in sys.argv:
+        ONLY = sys.argv[sys.argv.index("--only") + 1]
     if "--krylov" in sys.argv:
         KRYLOV_ONLY = True
         main()

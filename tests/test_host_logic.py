@@ -318,3 +318,21 @@ def test_chebyshev_coefficients_reference_doctest():
     assert np.allclose(c, [-0.32323232, 1.45454545, -2.12121212, 1.0], atol=5e-9)
     with pytest.raises(ValueError):
         chebyshev_polynomial_coefficients(2.0, 1.0, 3)
+
+
+def test_coarse_solver_spec_roundtrip(load_golden, tmp_path):
+    """Relaxation coarse solvers keep their keyword arguments through save / load (the reference's name() drops
+    them: multilevel.py:820-823) and show up in the engine descriptor."""
+    from pyamg_b200.hierarchy_io import save_hierarchy, load_hierarchy
+    from pyamg_b200.multilevel import coarse_solver_spec
+    ml, ex = load_golden("cfg11_rs_gs_coarse_relaxation")
+    assert coarse_solver_spec(ml.coarse_solver) == ("gauss_seidel", {"iterations": 4, "sweep": "symmetric"})
+    assert ml.coarse_solver.relaxation == ("gauss_seidel", {"iterations": 4, "sweep": "symmetric"})
+    p = str(tmp_path / "h.npz")
+    save_hierarchy(p, ml)
+    ml2, _ = load_hierarchy(p)
+    assert coarse_solver_spec(ml2.coarse_solver) == coarse_solver_spec(ml.coarse_solver)
+    S = smoothing.describe(ml.coarse_solver.smoother(ml.levels[-1].A), ml.levels[-1].A, [])
+    assert S.kind == E.SM_GAUSS_SEIDEL and S.iterations == 4 and S.sweep == E.SWEEPS["symmetric"]
+    assert pyamg_b200.coarse_grid_solver("jacobi").relaxation == ("jacobi", {"iterations": 10})   # default: 10 sweeps
+    assert coarse_solver_spec(pyamg_b200.coarse_grid_solver("pinv")) == "pinv"

@@ -370,3 +370,34 @@ def test_krylov_module_keeps_the_preconditioned_solve_resident(load_golden):
         krylov.gmres(2.0 * A, ex["b"], M=ml.aspreconditioner())
     with pytest.raises(NotImplementedError):
         krylov.cg(A, ex["b"], M=ml.aspreconditioner(), callback=lambda xk: None)
+
+
+# ------------------------------------------------------------------ relaxation as the coarsest-level solver
+@pytest.mark.parametrize("coarse", [("jacobi", {"iterations": 5, "omega": 0.8, "withrho": False}),
+                                    ("sor", {"omega": 1.2, "iterations": 3, "sweep": "backward"}),
+                                    ("chebyshev", {"degree": 2, "iterations": 2}),
+                                    "gauss_seidel"])
+def test_relaxation_coarse_solvers_match_oracle(coarse):
+    """coarse_solver=<relaxation method> (multilevel.py:764-781: x = 0, then `iterations` sweeps, default 10)."""
+    from pyamg_b200.classical import ruge_stuben_solver
+    from pyamg_b200.gallery import poisson
+    np.random.seed(3)
+    ml = ruge_stuben_solver(poisson((24, 24)), max_coarse=40, coarse_solver=coarse)
+    assert ml.levels[-1].A.shape[0] > 10
+    b = np.random.default_rng(4).random(ml.levels[0].A.shape[0])
+    cyc = oracle.Cycle(oracle.hierarchy_spec(ml))
+    for cycle in ("V", "W"):
+        assert relerr(ml.solve(b, tol=0, maxiter=3, cycle=cycle), cyc.solve(b, tol=0, maxiter=3, cycle=cycle)) < TOL
+    with pytest.raises(NotImplementedError):
+        pyamg_b200.coarse_grid_solver("cg")
+
+
+def test_block_relaxation_coarse_solver_on_elasticity():
+    from pyamg_b200.aggregation import smoothed_aggregation_solver
+    from pyamg_b200.gallery import linear_elasticity
+    A, B = linear_elasticity((12, 12))
+    ml = smoothed_aggregation_solver(A, B=B, max_coarse=30, max_levels=2,
+                                     coarse_solver=("block_gauss_seidel", {"sweep": "symmetric", "iterations": 6}))
+    b = np.random.default_rng(5).random(A.shape[0])
+    cyc = oracle.Cycle(oracle.hierarchy_spec(ml))
+    assert relerr(ml.solve(b, tol=0, maxiter=3), cyc.solve(b, tol=0, maxiter=3)) < TOL
