@@ -300,6 +300,17 @@ int64_t amgb_dev_partials_len(int32_t n_rows, int lanes);
 int amgb_dev_dense_matvec(int32_t m, int32_t n, const double *M, const double *x, double *y,
                           void *stream);
 int amgb_dev_fill(double *x, int64_t n, double v, void *stream);
+/* out_dev[0] = <x, y> (x == y: squared 2-norm) by the engine's deterministic two-stage reduction (the `norm2` of
+ * SURVEY.md 8(b)); scratch = amgb_dev_reduce_len() doubles of device memory. */
+int64_t amgb_dev_reduce_len(void);
+int amgb_dev_dot(const double *x, const double *y, int64_t n, double *scratch, double *out_dev, void *stream);
+/* y = a x + b y */
+int amgb_dev_axpby(double a, const double *x, double b, double *y, int64_t n, void *stream);
+/* bsr_block_jacobi of SURVEY.md 8(b) on the point-CSR expansion of the BSR operator (Ap has n_block_rows*bs + 1
+ * entries), Dinv (n_block_rows, bs, bs) row-major, bs <= 8, x_out != x_in. */
+int amgb_dev_block_jacobi(int32_t n_block_rows, int32_t bs, const int32_t *Ap, const int32_t *Aj, const double *Ax,
+                          const double *x_in, const double *b, const double *Dinv, double *x_out, double omega,
+                          int lanes, void *stream);
 /* out[i] = in[idx[i]] (halo packing, permuted layouts) */
 int amgb_dev_gather(const double *in, const int32_t *idx, double *out, int64_t n, void *stream);
 /* HOST helper (no CUDA): the TMA tile list for a CSR row-pointer array under geometry (T, RMAX), G lanes per

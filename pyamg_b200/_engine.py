@@ -64,7 +64,8 @@ SYMBOLS = [
     "amgb_arnoldi_create", "amgb_arnoldi_run", "amgb_arnoldi_combine", "amgb_arnoldi_destroy",
     "amgb_dev_csr_spmv", "amgb_dev_csr_residual", "amgb_dev_csr_spmv_add", "amgb_dev_csr_jacobi",
     "amgb_dev_csr_gs_wave", "amgb_dev_partials_len", "amgb_dev_dense_matvec", "amgb_dev_fill",
-    "amgb_dev_gather", "amgb_wave_schedule", "amgb_debug_build_tiles",
+    "amgb_dev_gather", "amgb_dev_reduce_len", "amgb_dev_dot", "amgb_dev_axpby", "amgb_dev_block_jacobi",
+    "amgb_wave_schedule", "amgb_debug_build_tiles",
 ]
 
 
@@ -151,6 +152,11 @@ def _bind(L):
     L.amgb_dev_dense_matvec.argtypes = [i32, i32, vp, vp, vp, vp]
     L.amgb_dev_fill.argtypes = [vp, i64, f64, vp]
     L.amgb_dev_gather.argtypes = [vp, vp, vp, i64, vp]
+    L.amgb_dev_reduce_len.restype = ctypes.c_int64
+    L.amgb_dev_reduce_len.argtypes = []
+    L.amgb_dev_dot.argtypes = [vp, vp, i64, vp, vp, vp]
+    L.amgb_dev_axpby.argtypes = [f64, vp, f64, vp, i64, vp]
+    L.amgb_dev_block_jacobi.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, f64, ci, vp]
     L.amgb_debug_build_tiles.argtypes = [i32, c_i32p, i32, ctypes.POINTER(ctypes.c_int64), i32, i32, i32, c_i32p,
                                          c_i32p, i32, c_i32p, c_i32p]
     L.amgb_wave_schedule.argtypes = [i32, c_i32p, c_i32p, c_i32p, i64, c_i32p, c_i32p]

@@ -396,3 +396,44 @@ extern "C" int amgb_dev_fill(double *x, int64_t n, double v, void *stream)
 {
     return launch_fill(x, n, v, (cudaStream_t)stream);
 }
+
+// out_dev[0] = <x, y> (x == y: the squared 2-norm) with the engine's deterministic two-stage reduction;
+// scratch: amgb_dev_reduce_len() doubles of device memory
+extern "C" int64_t amgb_dev_reduce_len(void) { return kSumsqBlocks; }
+
+extern "C" int amgb_dev_dot(const double *x, const double *y, int64_t n, double *scratch, double *out_dev, void *stream)
+{
+    if (x == nullptr || y == nullptr || scratch == nullptr || out_dev == nullptr) return fail(AMGB_EINVAL, "null pointer");
+    if (n < 0) return fail(AMGB_EINVAL, "n < 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    dot_partials_kernel<<<sumsq_blocks(), 256, 0, s>>>(x, y, n, scratch);
+    CK(cudaGetLastError());
+    reduce_partials_kernel<<<1, 1024, 0, s>>>(scratch, sumsq_blocks(), out_dev);
+    CK(cudaGetLastError());
+    return AMGB_OK;
+}
+
+// y = a x + b y
+extern "C" int amgb_dev_axpby(double a, const double *x, double b, double *y, int64_t n, void *stream)
+{
+    if (n <= 0) return AMGB_OK;
+    if (x == nullptr || y == nullptr) return fail(AMGB_EINVAL, "null pointer");
+    const long long grid = std::min<long long>((n + 255) / 256, (long long)g_num_sms * 16);
+    axpby_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a, x, b, y, n);
+    CK(cudaGetLastError());
+    return AMGB_OK;
+}
+
+// block Jacobi sweep on the point-CSR expansion of a BSR operator (what the engine uploads): n_block_rows block rows
+// of size bs, Dinv (n_block_rows, bs, bs) row-major, x_out != x_in
+extern "C" int amgb_dev_block_jacobi(int32_t n_block_rows, int32_t bs, const int32_t *Ap, const int32_t *Aj,
+                                     const double *Ax, const double *x_in, const double *b, const double *Dinv,
+                                     double *x_out, double omega, int lanes, void *stream)
+{
+    if (x_in == x_out) return fail(AMGB_EINVAL, "block_jacobi: x_in and x_out must differ");
+    if (lanes == 0) lanes = 8;
+    if (lanes < 1 || lanes > 32 || (lanes & (lanes - 1))) return fail(AMGB_EINVAL, "lanes must be a power of two in 1..32");
+    DevCsr A;
+    A.Ap = const_cast<int *>(Ap); A.Aj = const_cast<int *>(Aj); A.Ax = const_cast<double *>(Ax);
+    return dispatch_block_jacobi(bs, lanes, n_block_rows, A, x_in, b, Dinv, x_out, omega, (cudaStream_t)stream);
+}

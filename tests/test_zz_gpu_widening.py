@@ -401,3 +401,115 @@ def test_block_relaxation_coarse_solver_on_elasticity():
     b = np.random.default_rng(5).random(A.shape[0])
     cyc = oracle.Cycle(oracle.hierarchy_spec(ml))
     assert relerr(ml.solve(b, tol=0, maxiter=3), cyc.solve(b, tol=0, maxiter=3)) < TOL
+
+
+# ------------------------------------------------------------------ the device-pointer entry points (C ABI group 3)
+class _DevMem:
+    """Device arrays for the amgb_dev_* calls: torch CUDA tensors on a GPU, NumPy arrays on the kernel emulator."""
+
+    def __init__(self):
+        import os
+        self.emu = os.environ.get("AMGB_TEST_EMU") == "1"
+        if not self.emu:
+            import torch
+            self.torch = torch
+
+    def up(self, a):
+        a = np.ascontiguousarray(a)
+        if self.emu:
+            return a.copy()
+        return self.torch.from_numpy(a.copy()).cuda()
+
+    def ptr(self, d):
+        import ctypes
+        return ctypes.c_void_p(d.ctypes.data if self.emu else d.data_ptr())
+
+    def get(self, d):
+        if self.emu:
+            return d.copy()
+        self.torch.cuda.synchronize()
+        return d.cpu().numpy()
+
+
+def test_device_pointer_entry_points():
+    """csr_spmv, csr_residual(+norm), csr_spmv_add, fused Jacobi(+residual), GS wave, dense matvec,
+    fill, gather, norm2 / dot, axpby, block Jacobi -- each against NumPy / the oracle on device-resident arrays."""
+    from pyamg_b200 import _engine as E
+    from pyamg_b200.util import get_block_diag
+    L, D = E.lib(), _DevMem()
+    A, x0, b = _system(n=40, seed=31)
+    n = A.shape[0]
+    Ap, Aj, Ax = (D.up(A.indptr.astype(np.int32)), D.up(A.indices.astype(np.int32)), D.up(A.data))
+    dx, db = D.up(x0), D.up(b)
+    dy, dr = D.up(np.zeros(n)), D.up(np.zeros(n))
+    P = D.ptr
+    for lanes in (0, 4, 32):
+        E.check(L.amgb_dev_csr_spmv(n, P(Ap), P(Aj), P(Ax), P(dx), P(dy), lanes, None))
+        assert relerr(D.get(dy), A @ x0) < TOL
+        parts, nrm = D.up(np.zeros(int(L.amgb_dev_partials_len(n, lanes)))), D.up(np.zeros(1))
+        E.check(L.amgb_dev_csr_residual(n, P(Ap), P(Aj), P(Ax), P(dx), P(db), P(dr), P(parts), P(nrm), lanes, None))
+        r = b - A @ x0
+        assert relerr(D.get(dr), r) < TOL and D.get(nrm)[0] == pytest.approx(r @ r, rel=1e-13)
+        dacc = D.up(b)
+        E.check(L.amgb_dev_csr_spmv_add(n, P(Ap), P(Aj), P(Ax), P(dx), P(dacc), lanes, None))
+        assert relerr(D.get(dacc), b + A @ x0) < TOL
+        xo = x0.copy()
+        oracle.jacobi(A, xo, b, omega=0.7)
+        E.check(L.amgb_dev_csr_jacobi(n, P(Ap), P(Aj), P(Ax), P(dx), P(db), P(dy), P(dr), 0.7, lanes, None))
+        assert relerr(D.get(dy), xo) < TOL and relerr(D.get(dr), r) < TOL      # r: residual of the INPUT iterate
+    # one Gauss-Seidel "wave" over an independent set (rows 0, 1, ... with no mutual coupling are not guaranteed here:
+    # use a single row list of one row at a time == the sequential sweep)
+    xg, xo = D.up(x0), x0.copy()
+    oracle.gauss_seidel(A, xo, b, sweep="forward")
+    for i in range(n):
+        E.check(L.amgb_dev_csr_gs_wave(1, i, None, P(Ap), P(Aj), P(Ax), P(xg), P(db), 1.0, 4, None))
+    assert relerr(D.get(xg), xo) < TOL
+    rows = D.up(np.array([5, 3], dtype=np.int32))                              # explicit (independent) row list
+    xg, xo = D.up(x0), x0.copy()
+    Aloc = A.tolil(); Aloc[5, 3] = 0; Aloc[3, 5] = 0; Aloc = sp.csr_array(Aloc.tocsr()); Aloc.eliminate_zeros()
+    Bp, Bj, Bx = D.up(Aloc.indptr.astype(np.int32)), D.up(Aloc.indices.astype(np.int32)), D.up(Aloc.data)
+    oracle.gauss_seidel_indexed(Aloc, xo, b, np.array([5, 3], dtype=np.int32))
+    E.check(L.amgb_dev_csr_gs_wave(2, 0, P(rows), P(Bp), P(Bj), P(Bx), P(xg), P(db), 1.0, 8, None))
+    assert relerr(D.get(xg), xo) < TOL
+    # dense matvec, fill, gather
+    M = np.random.default_rng(2).standard_normal((7, n))
+    dM, d7 = D.up(M), D.up(np.zeros(7))
+    E.check(L.amgb_dev_dense_matvec(7, n, P(dM), P(dx), P(d7), None))
+    assert relerr(D.get(d7), M @ x0) < TOL
+    E.check(L.amgb_dev_fill(P(dy), n, 2.5, None))
+    assert np.array_equal(D.get(dy), np.full(n, 2.5))
+    idx = np.random.default_rng(3).permutation(n).astype(np.int32)
+    didx = D.up(idx)
+    E.check(L.amgb_dev_gather(P(dx), P(didx), P(dy), n, None))
+    assert np.array_equal(D.get(dy), x0[idx])
+    # norm2 / dot, axpby
+    scratch, out = D.up(np.zeros(int(L.amgb_dev_reduce_len()))), D.up(np.zeros(1))
+    E.check(L.amgb_dev_dot(P(dx), P(db), n, P(scratch), P(out), None))
+    assert D.get(out)[0] == pytest.approx(x0 @ b, rel=1e-13)
+    E.check(L.amgb_dev_dot(P(dx), P(dx), n, P(scratch), P(out), None))
+    assert D.get(out)[0] == pytest.approx(x0 @ x0, rel=1e-13)
+    dz = D.up(b)
+    E.check(L.amgb_dev_axpby(0.3, P(dx), -1.5, P(dz), n, None))
+    assert relerr(D.get(dz), 0.3 * x0 - 1.5 * b) < TOL
+    # block Jacobi on the point expansion of a BSR(3,3) operator
+    Ab3, xb, bb = _system(n=12, seed=33, bs=3)
+    Ab = Ab3.tobsr(blocksize=(3, 3))
+    Dinv = get_block_diag(Ab, blocksize=3, inv_flag=True)
+    Ac = sp.csr_array(Ab.tocsr())
+    keep = []
+    Mx = E.as_matrix(Ab, keep)                    # the engine's expansion keeps the BSR storage order: rebuild it here
+    exp_ptr, exp_j, exp_x = [0], [], []
+    for I in range(Ab.shape[0] // 3):
+        for rr in range(3):
+            for jj in range(Ab.indptr[I], Ab.indptr[I + 1]):
+                for cc in range(3):
+                    exp_j.append(Ab.indices[jj] * 3 + cc)
+                    exp_x.append(Ab.data[jj, rr, cc])
+            exp_ptr.append(len(exp_j))
+    Ep, Ej, Ex = D.up(np.array(exp_ptr, np.int32)), D.up(np.array(exp_j, np.int32)), D.up(np.array(exp_x))
+    dxb, dbb, dyb, dD = D.up(xb), D.up(bb), D.up(np.zeros_like(xb)), D.up(Dinv.reshape(-1))
+    xo = xb.copy()
+    oracle.block_jacobi(Ab, xo, bb, Dinv=Dinv, blocksize=3, omega=0.9)
+    E.check(L.amgb_dev_block_jacobi(Ab.shape[0] // 3, 3, P(Ep), P(Ej), P(Ex), P(dxb), P(dbb), P(dD), P(dyb), 0.9, 4, None))
+    assert relerr(D.get(dyb), xo) < TOL
+    assert L.amgb_dev_block_jacobi(4, 3, P(Ep), P(Ej), P(Ex), P(dxb), P(dbb), P(dD), P(dxb), 0.9, 4, None) == E.EINVAL
