@@ -124,3 +124,11 @@ def test_distributed_cycle_on_the_emulator(name, world, n_dist, halo, tmp_path, 
     assert relerr(got["x"], x) < 1e-12
     assert np.allclose(got["res"], res, rtol=1e-9)
     assert got["launches"][0] > 0
+
+
+def test_persistent_grids_of_other_sizes():
+    """The tile kernels run a persistent grid of (SM count x resident CTAs) blocks with a static tile -> warp map:
+    with one emulated SM every warp walks many tiles, with 13 most warps get none -- same results either way."""
+    for sms in ("1", "13"):
+        _run({"AMGB_EMU_SMS": sms, "AMGB_TILE_MIN_NNZ": "0"},
+             "vcycle_matches_reference_golden or relaxation_kernels", files=("tests/test_gpu_parity.py",))
