@@ -402,6 +402,7 @@ struct Smoother {
     int *rows1 = nullptr, *rows2 = nullptr;
     long long n_rows1 = 0, n_rows2 = 0;
     int f_iterations = 1, c_iterations = 1;
+    bool cf_contig = false;          // CF/FC Jacobi on a level stored C|F: ws.ptr = {0, nC, n} (+ tile ranges)
     std::vector<double> coef;        // polynomial coefficients (host: they become kernel arguments)
     // EXPERIMENTAL resident-vector cluster sweep (AMGB_RESIDENT=1): device copies of the schedule
     long long *res_wave_ptr = nullptr;
@@ -682,6 +683,7 @@ struct amgb_hierarchy {
     bool use_graph = true;
     bool use_tiles = true;
     bool use_permute = true;
+    bool use_cf_layout = true;     // AMGB_NO_CF_LAYOUT=1: CF / FC Jacobi through row lists on the natural numbering
     bool use_resident = false;     // AMGB_RESIDENT=1: experimental DSMEM-resident Gauss-Seidel applications
     long long resident_max_rows = 65536;   // AMGB_RESIDENT_MAX_ROWS
 
@@ -907,15 +909,49 @@ struct amgb_hierarchy {
         case AMGB_SM_FC_JACOBI:                                        // relaxation.py:1249-1254
             for (int it = 0; it < s.iterations; it++) {
                 if (s.kind == AMGB_SM_FC_JACOBI)
-                    for (int f = 0; f < s.f_iterations; f++) RET(jacobi_indexed(L, s.rows2, s.n_rows2, s.omega));
-                for (int c = 0; c < s.c_iterations; c++) RET(jacobi_indexed(L, s.rows1, s.n_rows1, s.omega));
+                    for (int f = 0; f < s.f_iterations; f++) RET(cf_sweep(L, s, 1));
+                for (int c = 0; c < s.c_iterations; c++) RET(cf_sweep(L, s, 0));
                 if (s.kind == AMGB_SM_CF_JACOBI)
-                    for (int f = 0; f < s.f_iterations; f++) RET(jacobi_indexed(L, s.rows2, s.n_rows2, s.omega));
+                    for (int f = 0; f < s.f_iterations; f++) RET(cf_sweep(L, s, 1));
             }
             return AMGB_OK;
         case AMGB_SM_BLOCK_GAUSS_SEIDEL: return block_gauss_seidel(L, s);
         }
         return fail(AMGB_ENOTIMPL, "smoother kind");
+    }
+
+    // one Jacobi sweep over the C-points (which = 0) or the F-points (1) of a CF / FC Jacobi smoother
+    int cf_sweep(Level &L, const Smoother &s, int which)
+    {
+        if (!s.cf_contig)
+            return which == 0 ? jacobi_indexed(L, s.rows1, s.n_rows1, s.omega) : jacobi_indexed(L, s.rows2, s.n_rows2, s.omega);
+        // C|F layout: the set is the contiguous row range [ptr[which], ptr[which+1]).  The sweep reads the iterate
+        // in place and writes the range's new values to the spare buffer (rows of the range read each other's OLD
+        // values, relaxation.h:394-399), then only that range is copied back -- no snapshot of the whole vector.
+        if (recording) return fail(AMGB_ESTATE, "CF Jacobi inside the cluster tail");
+        const long long r0 = s.ws.ptr[(size_t)which], nrow = s.ws.ptr[(size_t)which + 1] - r0;
+        if (nrow <= 0) return AMGB_OK;
+        double *temp = (L.x == L.x_home) ? L.xalt : L.x_home;
+        const long long nnzw = s.ws.nnz[(size_t)which];
+        launches++;
+        RET(prof_begin(8, L.A.tiles ? L.A.tile_G : L.A.lanes, nrow, nnzw, 12.0 * nnzw + 4.0 * (nrow + 1) + 40.0 * nrow));
+        if (L.A.tiles != nullptr && !s.ws.tile_ptr.empty() && nnzw >= tile_min_nnz) {
+            TileArgs a;
+            a.tiles = L.A.tiles; a.tile_begin = s.ws.tile_ptr[(size_t)which]; a.tile_end = s.ws.tile_ptr[(size_t)which + 1];
+            a.Ap = L.A.Ap; a.Aj = L.A.Aj; a.Ax = L.A.Ax; a.x = L.x; a.b = L.b; a.y = temp; a.r = nullptr; a.omega = s.omega;
+            a.partials = nullptr;
+            RET(launch_tile(OP_JACOBI, L.A.tile_G, a, tile_grid(OP_JACOBI, a.tile_end - a.tile_begin), stream));
+        } else {
+            CsrRowArgs a;
+            a.n = (int)nrow; a.row0 = (int)r0; a.rows = nullptr;
+            a.Ap = L.A.Ap; a.Aj = L.A.Aj; a.Ax = L.A.Ax;
+            a.x = L.x; a.b = L.b; a.y = temp; a.r = nullptr; a.omega = s.omega; a.partials = nullptr;
+            RET(launch_csr(OP_JACOBI, L.A.lanes, a, stream));
+        }
+        RET(prof_end());
+        CK(cudaMemcpyAsync(L.x + r0, temp + r0, sizeof(double) * (size_t)nrow, cudaMemcpyDeviceToDevice, stream));
+        launches++;
+        return AMGB_OK;
     }
 
     // amg_core.jacobi_indexed (relaxation.h:382-427): temp = x, then the listed rows are relaxed from temp.
@@ -1574,6 +1610,10 @@ int amgb_hierarchy::make_smoother(const SmootherSpec &sp, const HostCsr &Aperm, 
     } else if (sp.kind == AMGB_SM_JACOBI_INDEXED || sp.kind == AMGB_SM_CF_JACOBI || sp.kind == AMGB_SM_FC_JACOBI) {
         s.f_iterations = sp.f_iterations;
         s.c_iterations = sp.c_iterations;
+        if (shared != nullptr) {                    // the level is stored C-points first, F-points behind them
+            s.ws = *shared;
+            s.cf_contig = true;
+        }
         std::vector<int> l1 = sp.list, l2 = sp.list2;
         if (pos) {                                  // the level was put in wave-major order by its other smoother
             for (int &v : l1) v = (*pos)[(size_t)v];
@@ -1642,7 +1682,27 @@ int amgb_hierarchy::finalize_levels()
         const SmootherSpec *src = nullptr;
         if (H.pre.kind == AMGB_SM_GAUSS_SEIDEL) { src = &H.pre; layout_src[(size_t)l] = 0; }
         else if (H.post.kind == AMGB_SM_GAUSS_SEIDEL) { src = &H.post; layout_src[(size_t)l] = 1; }
-        if (src == nullptr) continue;
+        if (src == nullptr) {
+            // CF / FC Jacobi (AIR's smoother): put the C-points first and the F-points behind them, so that a sweep
+            // over either set is a contiguous row range streamed by the tile kernel instead of a row-list gather
+            auto is_cf = [](int k) { return k == AMGB_SM_CF_JACOBI || k == AMGB_SM_FC_JACOBI; };
+            const SmootherSpec *cf = is_cf(H.pre.kind) ? &H.pre : (is_cf(H.post.kind) ? &H.post : nullptr);
+            if (cf == nullptr || !use_cf_layout || cf->list.empty() || cf->list2.empty()) continue;
+            std::vector<int> both(cf->list);
+            both.insert(both.end(), cf->list2.begin(), cf->list2.end());
+            if (!is_permutation(both, H.A.n_rows)) continue;
+            WaveSchedule &W = layout[(size_t)l];
+            W.ptr = {0, (long long)cf->list.size(), (long long)H.A.n_rows};
+            W.contiguous = true;
+            W.nnz.assign(2, 0);
+            for (size_t k = 0; k < both.size(); k++)
+                W.nnz[k < cf->list.size() ? 0 : 1] += H.A.Ap[(size_t)both[k] + 1] - H.A.Ap[(size_t)both[k]];
+            order[(size_t)l] = both;
+            pos[(size_t)l].resize(both.size());
+            for (size_t i = 0; i < both.size(); i++) pos[(size_t)l][(size_t)both[i]] = (int)i;
+            layout_src[(size_t)l] = is_cf(H.pre.kind) ? 2 : 3;          // 2 / 3 = C|F layout taken from pre / post
+            continue;
+        }
         if (src->has_list && !is_permutation(src->list, H.A.n_rows)) { layout_src[(size_t)l] = -1; continue; }
         std::vector<int> rows;
         WaveSchedule &W = layout[(size_t)l];
@@ -1696,6 +1756,15 @@ int amgb_hierarchy::finalize_levels()
             const WaveSchedule *sh_post = (permuted && (layout_src[(size_t)l] == 1 || same_lists)) ? &W : nullptr;
             if (H.pre.kind != AMGB_SM_GAUSS_SEIDEL) sh_pre = nullptr;
             if (H.post.kind != AMGB_SM_GAUSS_SEIDEL) sh_post = nullptr;
+            if (layout_src[(size_t)l] >= 2) sh_pre = sh_post = nullptr;   // (decided just below for the C|F layout)
+            if (permuted && layout_src[(size_t)l] >= 2) {                // C|F layout: smoothers with the layout's lists
+                const SmootherSpec &ref = (layout_src[(size_t)l] == 2) ? H.pre : H.post;
+                auto same_cf = [&](const SmootherSpec &q) {
+                    return (q.kind == AMGB_SM_CF_JACOBI || q.kind == AMGB_SM_FC_JACOBI) && q.list == ref.list && q.list2 == ref.list2;
+                };
+                sh_pre = same_cf(H.pre) ? &W : nullptr;
+                sh_post = same_cf(H.post) ? &W : nullptr;
+            }
             RET(make_smoother(H.pre, *Ause, pv, sh_pre, L.pre));
             RET(make_smoother(H.post, *Ause, pv, sh_post, L.post));
         }
@@ -1735,6 +1804,7 @@ extern "C" int amgb_hierarchy_create(int device, amgb_hierarchy **out)
     h->use_graph = !flag("AMGB_NO_GRAPH");
     h->use_tiles = !flag("AMGB_NO_TILES");
     h->use_permute = !flag("AMGB_NO_PERMUTE");
+    h->use_cf_layout = !flag("AMGB_NO_CF_LAYOUT");
     h->use_resident = flag("AMGB_RESIDENT");
     if (const char *v = getenv("AMGB_RESIDENT_MAX_ROWS")) h->resident_max_rows = atoll(v);
     *out = h;

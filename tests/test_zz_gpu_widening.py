@@ -46,7 +46,7 @@ def test_vcycle_matches_oracle_on_fresh_rhs(name, load_golden):
 
 @pytest.mark.parametrize("env", [{"AMGB_NO_TILES": "1"}, {"AMGB_NO_PERMUTE": "1"}, {"AMGB_NO_GRAPH": "1"},
                                  {"AMGB_TILE_MIN_NNZ": "0"}, {"AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_G": "4"},
-                                 {"AMGB_TAIL_NNZ": "600000"}, {"AMGB_NO_PDL": "1"}])
+                                 {"AMGB_TAIL_NNZ": "600000"}, {"AMGB_NO_PDL": "1"}, {"AMGB_NO_CF_LAYOUT": "1"}])
 @pytest.mark.parametrize("name", GOLDEN_WIDENING)
 def test_every_kernel_path_matches_reference_golden(name, env, monkeypatch):
     T.test_every_kernel_path_matches_reference_golden(name, env, monkeypatch)
