@@ -24,7 +24,7 @@
 //     from uninitialised device memory shows up in the parity tests;
 //   * stream capture records closures with by-value arguments, graph launch replays them (what baking
 //     pointers into a CUDA graph means); everything else runs synchronously in stream order;
-//   * AMGB_EMU_ORDER=reverse visits warps and lanes in the opposite order: results that change with it depend on
+//   * AMGB_EMU_ORDER=reverse (or random:<seed>) visits warps and lanes in the opposite (a pseudo-random) order: results that change with it depend on
 //     the interleaving between synchronisation points, i.e. the kernel has a race (or an order-dependent reduction);
 //   * a launch in which no fiber can make progress is reported as cudaErrorLaunchFailure ("deadlock").
 #pragma once
@@ -172,6 +172,9 @@ struct State {
     std::vector<unsigned char *> stacks;      // fiber stacks (reused across launches)
     bool tma_lazy = false;
     bool reverse = false;                     // AMGB_EMU_ORDER=reverse
+    bool shuffle = false;                     // AMGB_EMU_ORDER=random:<seed>
+    unsigned long long rng = 1;
+    size_t rot = 0;
     struct PendingCopy { unsigned long long *bar; void *dst; const void *src; unsigned bytes; };
     std::vector<PendingCopy> pending;
     long long launches = 0, fibers_run = 0;
@@ -281,7 +284,15 @@ inline bool run_cluster(dim3 grid, dim3 block, size_t smem, unsigned first_block
         for (size_t wi = 0; wi < nwarp_all; wi++) {
             // AMGB_EMU_ORDER=reverse: warps and lanes are visited in the opposite order -- a correct kernel (no
             // dependence on the interleaving between synchronisation points) gives bit-identical results
-            const size_t w0 = (g.reverse ? (nwarp_all - 1 - wi) : wi) * 32;
+            size_t wsel = g.reverse ? (nwarp_all - 1 - wi) : wi;
+            if (g.shuffle) {                       // AMGB_EMU_ORDER=random:<seed>: a rotated warp order every pass,
+                if (wi == 0) {                     // a rotated + strided lane order every warp visit
+                    g.rng = g.rng * 6364136223846793005ull + 1442695040888963407ull;
+                    g.rot = (size_t)(g.rng >> 33);
+                }
+                wsel = (wi + g.rot) % nwarp_all;
+            }
+            const size_t w0 = wsel * 32;
             const size_t w1 = std::min(nfib, w0 + 32);      // warps: blocks are multiples of 32 threads (checked in execute)
             size_t left;
             unsigned long long p;
@@ -289,7 +300,8 @@ inline bool run_cluster(dim3 grid, dim3 block, size_t smem, unsigned first_block
                 p = g.progress;
                 left = 0;
                 for (size_t ii = w0; ii < w1; ii++) {
-                    const size_t i = g.reverse ? (w1 - 1 - (ii - w0)) : ii;
+                    size_t i = g.reverse ? (w1 - 1 - (ii - w0)) : ii;
+                    if (g.shuffle && w1 - w0 == 32) i = w0 + ((ii - w0) * 13 + g.rot + wsel) % 32;   // 13 is coprime to 32
                     Fiber &f = fibers[i];
                     if (f.done) continue;
                     g.cur = &f;
@@ -590,6 +602,8 @@ inline cudaError_t cudaGetDeviceCount(int *n)
     emu::g.tma_lazy = lz && strcmp(lz, "lazy") == 0;
     const char *ord = getenv("AMGB_EMU_ORDER");
     emu::g.reverse = ord && strcmp(ord, "reverse") == 0;
+    emu::g.shuffle = ord && strncmp(ord, "random", 6) == 0;
+    if (emu::g.shuffle && ord[6] == ':') emu::g.rng = strtoull(ord + 7, nullptr, 10) * 2654435761ull + 1;
     *n = 1;
     return cudaSuccess;
 }

@@ -73,7 +73,7 @@ def test_tile_kernels_everywhere_with_lazy_tma_completion():
 
 def test_results_do_not_depend_on_thread_interleaving(tmp_path):
     """The emulator runs the lanes of a warp one after the other between synchronisation points; visiting warps and
-    lanes in the opposite order (AMGB_EMU_ORDER=reverse) must not change a single bit of V/W cycles, GMRES or CG --
+    lanes in the opposite order or a pseudo-random one (AMGB_EMU_ORDER=reverse | random:<seed>) must not change a single bit of V/W cycles, GMRES or CG --
     with the lanes-per-row kernels and with the TMA tile kernels on every operator.  A kernel with a race (e.g. an
     in-place Gauss-Seidel wave that read a row of its own wave) would differ."""
     import numpy as np
@@ -82,7 +82,7 @@ def test_results_do_not_depend_on_thread_interleaving(tmp_path):
     probe = os.path.join(ROOT, "tests", "emu", "order_probe.py")
     for extra in ({}, {"AMGB_TILE_MIN_NNZ": "0"}):
         dumps = []
-        for order in ("forward", "reverse"):
+        for order in ("forward", "reverse", "random:20260922"):
             env = dict(os.environ)
             env.update(extra)
             env.update({"AMGB_TEST_EMU": "1", "AMGB_EMU_ORDER": order})
@@ -92,7 +92,8 @@ def test_results_do_not_depend_on_thread_interleaving(tmp_path):
             assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
             dumps.append(np.load(path))
         for n in names:
-            assert np.array_equal(dumps[0][n].view(np.int64), dumps[1][n].view(np.int64)), (n, extra)
+            for other in dumps[1:]:
+                assert np.array_equal(dumps[0][n].view(np.int64), other[n].view(np.int64)), (n, extra)
 
 
 @pytest.mark.parametrize("name,world,n_dist,halo", [("cfg3_rs_mcgs_poisson3d", 2, 2, "allgather"),
