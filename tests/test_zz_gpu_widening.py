@@ -513,3 +513,65 @@ def test_device_pointer_entry_points():
     E.check(L.amgb_dev_block_jacobi(Ab.shape[0] // 3, 3, P(Ep), P(Ej), P(Ex), P(dxb), P(dbb), P(dD), P(dyb), 0.9, 4, None))
     assert relerr(D.get(dyb), xo) < TOL
     assert L.amgb_dev_block_jacobi(4, 3, P(Ep), P(Ej), P(Ex), P(dxb), P(dbb), P(dD), P(dxb), 0.9, 4, None) == E.EINVAL
+
+
+# ------------------------------------------------------------------ randomised hierarchies
+@pytest.mark.parametrize("case", range(6))
+def test_random_two_level_hierarchies_with_long_rows_and_quirks(case, monkeypatch):
+    """Seeded random operators built to hit the corners of the tile builder and the kernels: rows longer than a tile
+    (230-700 entries; geometries T = 224 and 512), empty-ish and short rows, a zero diagonal, unsorted column indices,
+    random P (R = P^T), random pre/post smoothers incl. the wave-major and C|F layouts -- two V-cycles against the
+    oracle through the lanes-per-row kernels, the TMA tile kernels on every operator, a second tile geometry and
+    the un-permuted layout."""
+    from pyamg_b200.relaxation.smoothing import change_smoothers
+    rng = np.random.default_rng(1000 + case)
+    n, nc = int(rng.integers(300, 1200)), int(rng.integers(20, 90))
+    A = sp.random(n, n, density=float(rng.choice([0.02, 0.1, 0.4])),
+                  random_state=np.random.RandomState(int(rng.integers(1 << 30))), format="lil")
+    for i in rng.choice(n, size=max(1, n // 40), replace=False):
+        cols = rng.choice(n, size=min(n, int(rng.integers(230, 700))), replace=False)
+        A[i, cols] = rng.standard_normal(len(cols))
+    A = sp.csr_array(A.tocsr())
+    A = (A + A.T).tocsr()
+    A = (A + sp.diags_array(np.asarray(np.abs(A).sum(axis=1)).ravel() + 1.0)).tocsr()
+    if case % 2:
+        A = A.tolil()
+        A[3, 3] = 0.0
+        A = sp.csr_array(A.tocsr())
+        A.eliminate_zeros()
+    A = sp.csr_array(A)
+    A.sort_indices()
+    for i in range(0, n, 7):                                       # unsorted indices, as RS coarse levels have
+        s, e = A.indptr[i], A.indptr[i + 1]
+        perm = rng.permutation(e - s)
+        A.indices[s:e], A.data[s:e] = A.indices[s:e][perm], A.data[s:e][perm]
+    P = sp.random(n, nc, density=min(1.0, 3.0 / nc), random_state=np.random.RandomState(int(rng.integers(1 << 30))),
+                  format="csr")
+    P = sp.csr_array(P + sp.csr_array((np.ones(n), (np.arange(n), np.arange(n) % nc)), shape=(n, nc)))
+
+    def i32(M):
+        M = sp.csr_array(M)
+        M.indptr, M.indices = M.indptr.astype(np.int32), M.indices.astype(np.int32)
+        return M
+    R = i32(P.T.tocsr())
+    A, P = i32(A), i32(P)
+    Ac = i32(R @ A @ P)
+    l0, l1 = pyamg_b200.MultilevelSolver.Level(), pyamg_b200.MultilevelSolver.Level()
+    l0.A, l0.P, l0.R, l1.A = A, P, R, Ac
+    l0.splitting = rng.random(n) < 0.5
+    ml = pyamg_b200.MultilevelSolver([l0, l1])
+    choices = [("jacobi", {"omega": 0.6, "withrho": False, "iterations": int(rng.integers(1, 4))}),
+               ("gauss_seidel", {"sweep": str(rng.choice(["forward", "backward", "symmetric"]))}),
+               ("gauss_seidel_indexed", {"sweep": "symmetric"}), ("sor", {"omega": 1.3, "sweep": "forward"}),
+               ("cf_jacobi", {"omega": 0.5, "f_iterations": 2}), ("fc_jacobi", {"omega": 0.5}), None]
+    change_smoothers(ml, choices[int(rng.integers(len(choices)))], choices[int(rng.integers(len(choices)))])
+    b = rng.standard_normal(n)
+    xo = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(Ac)).solve(b, tol=0, maxiter=2)
+    for env in ({}, {"AMGB_TILE_MIN_NNZ": "0"}, {"AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_CFG": "0"},
+                {"AMGB_NO_PERMUTE": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_G": "8"}):
+        for k in ("AMGB_TILE_MIN_NNZ", "AMGB_TILE_CFG", "AMGB_NO_PERMUTE", "AMGB_TILE_G"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ml._invalidate()
+        assert relerr(ml.solve(b, tol=0, maxiter=2), xo) < 1e-12, env
