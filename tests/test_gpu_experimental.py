@@ -109,3 +109,15 @@ def test_flat_tile_kernel_on_a_mid_size_hierarchy_and_host_abi(monkeypatch):
     b = np.random.default_rng(14).random(ml.levels[0].A.shape[0])
     cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A))
     assert relerr(ml.solve(b, tol=0, maxiter=3, cycle="W"), cyc.solve(b, tol=0, maxiter=3, cycle="W")) < 1e-12
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_experimental_kernels_on_random_hierarchies(case, monkeypatch):
+    """The seeded random two-level hierarchies of tests/test_zz_gpu_widening.py (rows longer than a tile, zero
+    diagonal, unsorted indices, random smoothers / layouts) through the opt-in kernel variants."""
+    from test_zz_gpu_widening import random_hierarchy_check
+    random_hierarchy_check(case, monkeypatch, (
+        {"AMGB_TILE_FLAT": "1", "AMGB_TILE_MIN_NNZ": "0"},
+        {"AMGB_RESIDENT": "1", "AMGB_RESIDENT_MAX_ROWS": "100000"},
+        {"AMGB_TILE_PDL": "1", "AMGB_TILE_MIN_NNZ": "0"},
+        {"AMGB_TILE_FLAT": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_RESIDENT": "1", "AMGB_TILE_PDL": "1"}))

@@ -516,8 +516,18 @@ def test_device_pointer_entry_points():
 
 
 # ------------------------------------------------------------------ randomised hierarchies
+_FUZZ_ENVS = ({}, {"AMGB_TILE_MIN_NNZ": "0"}, {"AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_CFG": "0"},
+              {"AMGB_NO_PERMUTE": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_G": "8"})
+_FUZZ_KEYS = ("AMGB_TILE_MIN_NNZ", "AMGB_TILE_CFG", "AMGB_NO_PERMUTE", "AMGB_TILE_G", "AMGB_TILE_FLAT", "AMGB_RESIDENT",
+              "AMGB_RESIDENT_MAX_ROWS", "AMGB_TILE_PDL")
+
+
 @pytest.mark.parametrize("case", range(6))
 def test_random_two_level_hierarchies_with_long_rows_and_quirks(case, monkeypatch):
+    random_hierarchy_check(case, monkeypatch, _FUZZ_ENVS)
+
+
+def random_hierarchy_check(case, monkeypatch, envs):
     """Seeded random operators built to hit the corners of the tile builder and the kernels: rows longer than a tile
     (230-700 entries; geometries T = 224 and 512), empty-ish and short rows, a zero diagonal, unsorted column indices,
     random P (R = P^T), random pre/post smoothers incl. the wave-major and C|F layouts -- two V-cycles against the
@@ -567,9 +577,8 @@ def test_random_two_level_hierarchies_with_long_rows_and_quirks(case, monkeypatc
     change_smoothers(ml, choices[int(rng.integers(len(choices)))], choices[int(rng.integers(len(choices)))])
     b = rng.standard_normal(n)
     xo = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(Ac)).solve(b, tol=0, maxiter=2)
-    for env in ({}, {"AMGB_TILE_MIN_NNZ": "0"}, {"AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_CFG": "0"},
-                {"AMGB_NO_PERMUTE": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_G": "8"}):
-        for k in ("AMGB_TILE_MIN_NNZ", "AMGB_TILE_CFG", "AMGB_NO_PERMUTE", "AMGB_TILE_G"):
+    for env in envs:
+        for k in _FUZZ_KEYS:
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
