@@ -213,8 +213,11 @@ def build_plan(ml, world, rank, n_dist=None, dist_nnz=20_000_000, halo="allgathe
         D.post = smoothing.describe(getattr(lvl, "postsmoother", None), lvl.A, keep)
         D._keep = keep
         for S in (D.pre, D.post):
-            if S.kind == E.SM_BLOCK_JACOBI:
-                raise NotImplementedError("block Jacobi on a partitioned level")
+            if S.kind not in (E.SM_NONE, E.SM_JACOBI, E.SM_GAUSS_SEIDEL, E.SM_POLYNOMIAL):
+                raise NotImplementedError("partitioned levels run Jacobi, Gauss-Seidel (global waves) and polynomial "
+                                          f"smoothers; smoother kind {S.kind} needs the single-GPU engine")
+            if S.kind == E.SM_POLYNOMIAL:      # the coefficient array must outlive the descriptor
+                S._coef = np.ctypeslib.as_array(S.coefficients, shape=(S.n_coefficients,)).copy()
         # global dependency waves of the (pre) Gauss-Seidel sweep decide the local storage order
         D.wave_ptr = None
         gs = D.pre if D.pre.kind == E.SM_GAUSS_SEIDEL else (D.post if D.post.kind == E.SM_GAUSS_SEIDEL else None)
@@ -292,6 +295,7 @@ class DistributedSolver:
             L.send_idx = be.index(D.send_idx)
             L.send = be.vector(max(sp.maxB, int(sp.send_off[-1])))
             L.x, L.xalt, L.b, L.r = (be.vector(sp.n_ext) for _ in range(4))
+            L.poly = be.vector(sp.n_ext) if E.SM_POLYNOMIAL in (D.pre.kind, D.post.kind) else None
             self.lv.append(L)
         # replicated remainder: an ordinary engine hierarchy on every rank
         self.sub = backend.sub_solver(MultilevelSolver, ml, self.n_dist)
@@ -322,6 +326,24 @@ class DistributedSolver:
                 be.apply(L.A, OP_JACOBI, L.x, L.b, L.xalt, omega=S.omega)
                 L.x, L.xalt = L.xalt, L.x
             return
+        if S.kind == E.SM_POLYNOMIAL:
+            # relaxation.polynomial (relaxation.py:646-659): r = b - A x; h = c_0 r; h = c_k r + A h; x += h.
+            # Every SpMV of a partitioned vector is preceded by its halo exchange.
+            coef = S._coef
+            for _ in range(S.iterations):
+                self.halo(L, L.x)
+                be.apply(L.A, OP_RESID, L.x, L.b, L.r)
+                h, Ah = L.xalt, L.poly
+                be.scale_to(h, float(coef[0]), L.r)
+                for c in coef[1:]:
+                    self.halo(L, h)
+                    be.apply(L.A, OP_SPMV, h, None, Ah)
+                    be.axpby(float(c), L.r, 1.0, Ah)
+                    h, Ah = Ah, h
+                be.axpby(1.0, h, 1.0, L.x)
+            return
+        if S.kind != E.SM_GAUSS_SEIDEL:
+            raise NotImplementedError(f"smoother kind {S.kind} on a partitioned level")
         nw = L.D.n_waves
         om = 1.0 if S.sweep == E.SWEEPS["symmetric"] else S.omega
         for _ in range(S.iterations):
@@ -463,6 +485,12 @@ class GpuBackend:
 
     def copy_scalar(self, src, dst, slot):
         dst[slot:slot + 1].copy_(src[:1])
+
+    def scale_to(self, dst, a, src):                # dst = a * src (owned part and halo region alike)
+        self.torch.mul(src, a, out=dst)
+
+    def axpby(self, a, x, b, y):                    # y = a x + b y
+        y.mul_(b).add_(x, alpha=a)
 
     # operators
     def operator(self, M, wave_ptr):

@@ -40,6 +40,13 @@ class NumpyBackend:
     def copy_scalar(self, src, dst, slot):
         dst[slot] = src[0]
 
+    def scale_to(self, dst, a, src):
+        dst[:] = a * src
+
+    def axpby(self, a, x, b, y):
+        y *= b
+        y += a * x
+
     def operator(self, M, wave_ptr):
         return (sp.csr_array(M), None if wave_ptr is None else np.asarray(wave_ptr))
 

@@ -40,6 +40,7 @@ def _run(name, world, n_dist, tmp_path, halo="allgather"):
     ("cfg4_sa_jacobi_aniso2d", 2, 3, "allgather"),   # 2 Jacobi sweeps pre (ping-pong), three partitioned levels
     ("cfg3_rs_mcgs_poisson3d", 4, 2, "p2p"),         # neighbour send/recv halo plan, 4 ranks
     ("cfg4_sa_jacobi_aniso2d", 3, 3, "p2p"),
+    ("cfg7_sa_cheby_richardson_poisson2d", 2, 2, "allgather"),   # polynomial smoothers: a halo exchange per Horner SpMV
 ])
 def test_distributed_vcycle_matches_sequential_oracle(name, world, n_dist, halo, tmp_path, load_golden):
     ml, ex = load_golden(name)
