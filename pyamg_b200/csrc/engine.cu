@@ -2140,7 +2140,16 @@ extern "C" int amgb_solve_ex(amgb_hierarchy *h, const double *b_host, double *x_
         normb = std::sqrt(h->norm_host[0]);
         if (normb == 0.0) normb = 1.0;
     }
-    RET(h->residual_norm2(0));                                     // :545
+    if (flags & AMGB_FLAG_X0_ZERO) {
+        // x0 = 0: the initial residual b - A 0 is b itself (:545) -- one pass over b instead of one over A
+        sumsq_partials_kernel<<<sumsq_blocks(), 256, 0, s>>>(L0.b, L0.A.n_rows, h->sumsq_parts);
+        CK(cudaGetLastError());
+        reduce_partials_kernel<<<1, 1024, 0, s>>>(h->sumsq_parts, sumsq_blocks(), h->norms2);
+        CK(cudaGetLastError());
+        h->launches += 2;
+    } else {
+        RET(h->residual_norm2(0));                                 // :545
+    }
     int it = 0, conv = -1;
     while (true) {
         RET(h->one_iteration(cycle, cycles_per_level));            // :559-563
