@@ -157,6 +157,11 @@ def jacobi(A, x, b, iterations=1, omega=1.0, kernels="oracle"):
 def gauss_seidel(A, x, b, iterations=1, sweep="forward", omega=1.0, kernels="oracle"):
     """pyamg/relaxation/relaxation.py:265-346 (CSR path; 'symmetric' = fwd then bwd WITHOUT omega,
     :326-330; omega != 1 -> sor_gauss_seidel :335-338)."""
+    if sparse.issparse(A) and A.format == "bsr":
+        # relaxation.py:343-346: the BSR branch calls bsr_gauss_seidel, which has no omega -- SOR on a BSR operator
+        # (every smoothed-aggregation coarse level is BSR, blocksize 1 for scalar problems) is plain Gauss-Seidel;
+        # point-wise BSR Gauss-Seidel equals the sweep on the CSR expansion (test_relaxation.py:224-249)
+        omega = 1.0
     A, x, b = make_system(A, x, b, formats=["csr"])
     _f64(A, x, b)
     n = A.shape[0]

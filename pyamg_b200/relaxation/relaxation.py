@@ -112,6 +112,7 @@ def gauss_seidel(A, x, b, iterations=1, sweep="forward", omega=1.0):
         if R != C:
             raise ValueError("BSR blocks must be square")
         A = A.tocsr()
+        omega = 1.0      # reference quirk: the BSR branch (bsr_gauss_seidel, relaxation.py:343-346) has no omega
     n = A.shape[0]
     if sweep == "forward":
         rs = (0, n, 1)

@@ -389,6 +389,10 @@ def describe(sm, A, keep):
             raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
         S.sweep = E.SWEEPS[sweep]
         S.omega = float(np.real(kw.get("omega", 1.0))) if name != "gauss_seidel_indexed" else 1.0
+        if getattr(A, "format", None) == "bsr":
+            # reference quirk: on a BSR operator gauss_seidel / sor call bsr_gauss_seidel, which has no omega
+            # (relaxation.py:343-346) -- every SA coarse level is BSR, so 'sor' there is plain Gauss-Seidel
+            S.omega = 1.0
         if name == "gauss_seidel_indexed":
             idx = np.ascontiguousarray(np.asarray(kw["indices"], dtype="intc"), dtype=np.int32)
             keep.append(idx)

@@ -238,6 +238,14 @@ def main_widening():
     ml = pyamg.ruge_stuben_solver(A, max_coarse=60, coarse_solver=("gauss_seidel", {"iterations": 4, "sweep": "symmetric"}))
     emit("cfg11_rs_gs_coarse_relaxation", ml)
 
+    # cfg12: SOR on a smoothed-aggregation hierarchy: level 0 is CSR (in-sweep omega, sor_gauss_seidel), the coarse
+    # levels are BSR(1,1) where the reference's gauss_seidel ignores omega (relaxation.py:343-346)
+    np.random.seed(SEED)
+    A = poisson((28, 28), format="csr")
+    ml = pyamg.smoothed_aggregation_solver(A, presmoother=("sor", {"omega": 1.2, "sweep": "forward"}),
+                                           postsmoother=("sor", {"omega": 1.2, "sweep": "backward", "iterations": 2}))
+    emit("cfg12_sa_sor_poisson2d", ml)
+
     # cfg10: linear elasticity with the reference's DEFAULT SA smoothers (symmetric block Gauss-Seidel)
     np.random.seed(SEED)
     A, B = linear_elasticity((12, 12))

@@ -117,7 +117,8 @@ def test_oracle_vcycle_matches_reference(name, load_golden):
     res = []
     x = cyc.solve(ex["b"], tol=0, maxiter=len(ex["residuals"]) - 1, residuals=res)
     assert relerr(x, ex["x_ref"]) < TIGHT
-    assert np.allclose(res, ex["residuals"], rtol=1e-12, atol=0)
+    # residual norms: b - A x cancels ~4 digits by the last cycle, so iterates equal to 2e-16 give norms equal to 1e-11
+    assert np.allclose(res, ex["residuals"], rtol=1e-10, atol=0)
     assert relerr(cyc.solve(ex["b"], tol=0, maxiter=2, cycle="W"), ex["x_ref_W"]) < TIGHT
     assert relerr(cyc.solve(ex["b"], tol=0, maxiter=2, cycle="F"), ex["x_ref_F"]) < TIGHT
     res = []

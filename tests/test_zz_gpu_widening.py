@@ -584,3 +584,50 @@ def random_hierarchy_check(case, monkeypatch, envs):
             monkeypatch.setenv(k, v)
         ml._invalidate()
         assert relerr(ml.solve(b, tol=0, maxiter=2), xo) < 1e-12, env
+
+
+# ------------------------------------------------------------------ adoption of real reference solvers (needs pyamg)
+@pytest.mark.parametrize("family", ["rs_default", "rs_cljp_direct_jacobi", "sa_default", "sa_elasticity_default",
+                                    "sa_energy_chebyshev", "rootnode", "pairwise", "adaptive_sa", "air",
+                                    "sa_sor_none_lu", "rs_coarse_gauss_seidel", "sa_richardson_splu"])
+def test_from_pyamg_adopts_every_solver_family(family):
+    """MultilevelSolver.from_pyamg on hierarchies the REAL reference builds (skipped where pyamg is not importable,
+    i.e. on the GPU box; in the build container: PYTHONPATH=<reference build> AMGB_TEST_EMU=1 pytest -m gpu -k adopts):
+    three V-cycles and two W-cycles equal the reference's own ml.solve to 1e-12 -- classical RS (RS / CLJP
+    splittings, direct interpolation), SA with default block Gauss-Seidel (scalar and elasticity), energy-minimising
+    SA + Chebyshev, root-node, pairwise, adaptive SA, AIR, SOR on BSR coarse levels (omega ignored there, as in the
+    reference), None smoothers, lu / splu / relaxation coarse solvers."""
+    pyamg = pytest.importorskip("pyamg")
+    import warnings
+    from pyamg.gallery import poisson, linear_elasticity, advection_2d, stencil_grid
+    from pyamg.gallery.diffusion import diffusion_stencil_2d
+    A2, A3 = poisson((24, 24), format="csr"), poisson((9, 9, 9), format="csr")
+    build = {
+        "rs_default": lambda: pyamg.ruge_stuben_solver(A2),
+        "rs_cljp_direct_jacobi": lambda: pyamg.ruge_stuben_solver(
+            A2, CF="CLJP", interpolation="direct", presmoother=("jacobi", {"omega": 0.8}), postsmoother=("jacobi", {"omega": 0.8})),
+        "sa_default": lambda: pyamg.smoothed_aggregation_solver(A3),
+        "sa_elasticity_default": lambda: pyamg.smoothed_aggregation_solver(*[linear_elasticity((10, 10))[k] for k in (0,)],
+                                                                        B=linear_elasticity((10, 10))[1]),
+        "sa_energy_chebyshev": lambda: pyamg.smoothed_aggregation_solver(
+            stencil_grid(diffusion_stencil_2d(0.01, np.pi / 4, "FD"), (24, 24), format="csr"), smooth="energy",
+            presmoother=("chebyshev", {"degree": 2}), postsmoother=("chebyshev", {"degree": 2})),
+        "rootnode": lambda: pyamg.rootnode_solver(A2),
+        "pairwise": lambda: pyamg.pairwise_solver(A2),
+        "adaptive_sa": lambda: pyamg.aggregation.adaptive_sa_solver(A2, num_candidates=1)[0],
+        "air": lambda: pyamg.air_solver(advection_2d((20, 20))[0].tocsr()),
+        "sa_sor_none_lu": lambda: pyamg.smoothed_aggregation_solver(A2, presmoother=("sor", {"omega": 1.2}),
+                                                                   postsmoother=None, coarse_solver="lu"),
+        "rs_coarse_gauss_seidel": lambda: pyamg.ruge_stuben_solver(A2, max_coarse=50,
+                                                                   coarse_solver=("gauss_seidel", {"iterations": 3})),
+        "sa_richardson_splu": lambda: pyamg.smoothed_aggregation_solver(A2, presmoother="richardson",
+                                                                       postsmoother="richardson", coarse_solver="splu"),
+    }
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np.random.seed(1)
+        ref = build[family]()
+        b = np.random.default_rng(2).random(ref.levels[0].A.shape[0])
+        gpu = pyamg_b200.MultilevelSolver.from_pyamg(ref)
+        assert relerr(gpu.solve(b, tol=0, maxiter=3), ref.solve(b, tol=0, maxiter=3)) < TOL
+        assert relerr(gpu.solve(b, tol=0, maxiter=2, cycle="W"), ref.solve(b, tol=0, maxiter=2, cycle="W")) < TOL
