@@ -631,3 +631,36 @@ def test_from_pyamg_adopts_every_solver_family(family):
         gpu = pyamg_b200.MultilevelSolver.from_pyamg(ref)
         assert relerr(gpu.solve(b, tol=0, maxiter=3), ref.solve(b, tol=0, maxiter=3)) < TOL
         assert relerr(gpu.solve(b, tol=0, maxiter=2, cycle="W"), ref.solve(b, tol=0, maxiter=2, cycle="W")) < TOL
+
+
+@pytest.mark.parametrize("family", ["rs", "sa_elasticity", "air", "rootnode"])
+def test_adopted_hierarchies_all_solve_variants_match_the_reference(family):
+    """On hierarchies adopted from the real reference (needs pyamg: build container only): CG / GMRES / FGMRES /
+    BiCGStab acceleration, FGMRES + AMLI, tolerance stop from x0, AMLI and F(cycles_per_level=2) cycles -- same
+    iterates, iteration counts and info flags as the reference's own ml.solve."""
+    pyamg = pytest.importorskip("pyamg")
+    import warnings
+    from pyamg.gallery import poisson, linear_elasticity, advection_2d
+    A2 = poisson((20, 20), format="csr")
+    build = {"rs": lambda: pyamg.ruge_stuben_solver(A2),
+             "sa_elasticity": lambda: pyamg.smoothed_aggregation_solver(linear_elasticity((8, 8))[0], B=linear_elasticity((8, 8))[1]),
+             "air": lambda: pyamg.air_solver(advection_2d((16, 16))[0].tocsr()),
+             "rootnode": lambda: pyamg.rootnode_solver(A2)}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np.random.seed(1)
+        ref = build[family]()
+        gpu = pyamg_b200.MultilevelSolver.from_pyamg(ref)
+        n = ref.levels[0].A.shape[0]
+        b, x0 = np.random.default_rng(2).random(n), np.random.default_rng(3).random(n)
+        for kw in (dict(accel="cg", tol=1e-8, maxiter=8), dict(accel="gmres", tol=1e-8, maxiter=8),
+                   dict(accel="fgmres", tol=1e-8, maxiter=8, cycle="W"), dict(accel="bicgstab", tol=1e-8, maxiter=8),
+                   dict(accel="fgmres", cycle="AMLI", tol=1e-6, maxiter=4), dict(tol=1e-6, maxiter=30, x0=x0),
+                   dict(cycle="AMLI", tol=0, maxiter=2), dict(cycle="F", tol=0, maxiter=2, cycles_per_level=2)):
+            if family == "air" and kw.get("accel") == "cg":
+                continue                                  # nonsymmetric operator
+            rr, rg = [], []
+            xr, ir = ref.solve(b, residuals=rr, return_info=True, **kw)
+            xg, ig = gpu.solve(b, residuals=rg, return_info=True, **kw)
+            assert (ir, len(rr)) == (ig, len(rg)), kw
+            assert relerr(xg, xr) < 1e-9, kw
