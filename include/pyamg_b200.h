@@ -52,6 +52,10 @@ extern "C" {
 #define AMGB_SM_FC_JACOBI 7       /* relaxation.fc_jacobi (relaxation.py:1206-1268): F sweeps, then C sweeps     */
 #define AMGB_SM_BLOCK_GAUSS_SEIDEL 8  /* relaxation.block_gauss_seidel (relaxation.py:502-582 ->
                                      relaxation.h:1242-1298): block rows in dependency waves == the sequential sweep */
+#define AMGB_SM_CF_BLOCK_JACOBI 9 /* relaxation.cf_block_jacobi (relaxation.py:1271-1339 -> block_jacobi_indexed,
+                                     relaxation.h:1113-1172): indices / indices2 list BLOCK rows (C / F), Dinv as for
+                                     block Jacobi; AIR's smoother for block systems */
+#define AMGB_SM_FC_BLOCK_JACOBI 10 /* relaxation.fc_block_jacobi (relaxation.py:1342-1412) */
 
 #define AMGB_SWEEP_FORWARD 0
 #define AMGB_SWEEP_BACKWARD 1

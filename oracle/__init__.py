@@ -255,6 +255,44 @@ def fc_jacobi(A, x, b, Cpts, Fpts, iterations=1, f_iterations=1, c_iterations=1,
             jacobi_indexed(A, x, b, Cpts, omega=omega, kernels=kernels)
 
 
+def _block_jacobi_indexed(A, x, b, Dinv, indices, blocksize, omega, kernels):
+    nb = A.shape[0] // blocksize
+    data = np.ascontiguousarray(A.data).ravel()
+    dinv = np.ascontiguousarray(Dinv, dtype=np.float64).ravel()
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    om = ctypes.c_double(float(omega))
+    if kernels == "ref":
+        lib("ref").ref_block_jacobi_indexed(_ip(A.indptr), nb, _ip(A.indices), _dp(data), len(A.indices), _dp(x), _dp(b),
+                                            _dp(dinv), _ip(indices), len(indices), om, blocksize)
+    else:
+        lib().oracle_block_jacobi_indexed(_ip(A.indptr), _ip(A.indices), _dp(data), _dp(x), A.shape[0], _dp(b),
+                                          _dp(dinv), _ip(indices), len(indices), om, blocksize)
+
+
+def _cf_block_jacobi(order, A, x, b, Cpts, Fpts, Dinv, blocksize, iterations, f_iterations, c_iterations, omega, kernels):
+    A, x, b = make_system(A, x, b, formats=["csr", "bsr"])
+    _f64(A, x, b)
+    A = A.tobsr(blocksize=(blocksize, blocksize))
+    if Dinv is None:
+        raise ValueError("oracle: block CF Jacobi needs Dinv (setup-time quantity)")
+    for _ in range(iterations):
+        for pts, reps in ((Cpts, c_iterations), (Fpts, f_iterations)) if order == "cf" else ((Fpts, f_iterations), (Cpts, c_iterations)):
+            for _r in range(reps):
+                _block_jacobi_indexed(A, x, b, Dinv, pts, blocksize, omega, kernels)
+
+
+def cf_block_jacobi(A, x, b, Cpts, Fpts, Dinv=None, blocksize=1, iterations=1, f_iterations=1, c_iterations=1,
+                    omega=1.0, kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:1271-1339."""
+    _cf_block_jacobi("cf", A, x, b, Cpts, Fpts, Dinv, blocksize, iterations, f_iterations, c_iterations, omega, kernels)
+
+
+def fc_block_jacobi(A, x, b, Cpts, Fpts, Dinv=None, blocksize=1, iterations=1, f_iterations=1, c_iterations=1,
+                    omega=1.0, kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:1342-1412."""
+    _cf_block_jacobi("fc", A, x, b, Cpts, Fpts, Dinv, blocksize, iterations, f_iterations, c_iterations, omega, kernels)
+
+
 def polynomial(A, x, b, coefficients, iterations=1, kernels="oracle"):
     """pyamg/relaxation/relaxation.py:585-659: x += p(A)(b - A x) by Horner's rule; the matvecs are the
     reference's SciPy calls restated (``matvec``)."""
@@ -346,6 +384,8 @@ _SMOOTHERS = {
     "cf_jacobi": cf_jacobi,
     "fc_jacobi": fc_jacobi,
     "block_gauss_seidel": block_gauss_seidel,
+    "cf_block_jacobi": cf_block_jacobi,
+    "fc_block_jacobi": fc_block_jacobi,
 }
 
 

@@ -85,4 +85,13 @@ void ref_block_gauss_seidel(const int *Ap, int nb, const int *Aj, const double *
                                             Dinv, nb * bs * bs, row_start, row_stop, row_step, bs);
 }
 
+// pyamg/amg_core/relaxation.h:1113-1172
+void ref_block_jacobi_indexed(const int *Ap, int nb, const int *Aj, const double *Ax, int nblk, double *x,
+                              const double *b, const double *Dinv, const int *Id, int n_id, double omega, int bs)
+{
+    int n = nb * bs;
+    block_jacobi_indexed<int, double, double>(Ap, nb + 1, Aj, nblk, Ax, nblk * bs * bs, x, n, b, n,
+                                              Dinv, nb * bs * bs, Id, n_id, &omega, 1, bs);
+}
+
 }  // extern "C"

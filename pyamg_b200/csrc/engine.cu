@@ -916,6 +916,16 @@ struct amgb_hierarchy {
             }
             return AMGB_OK;
         case AMGB_SM_BLOCK_GAUSS_SEIDEL: return block_gauss_seidel(L, s);
+        case AMGB_SM_CF_BLOCK_JACOBI:                                  // relaxation.py:1328-1339
+        case AMGB_SM_FC_BLOCK_JACOBI:                                  // relaxation.py:1401-1412
+            for (int it = 0; it < s.iterations; it++) {
+                if (s.kind == AMGB_SM_FC_BLOCK_JACOBI)
+                    for (int f = 0; f < s.f_iterations; f++) RET(block_jacobi_indexed(L, s, s.rows2, s.n_rows2));
+                for (int c = 0; c < s.c_iterations; c++) RET(block_jacobi_indexed(L, s, s.rows1, s.n_rows1));
+                if (s.kind == AMGB_SM_CF_BLOCK_JACOBI)
+                    for (int f = 0; f < s.f_iterations; f++) RET(block_jacobi_indexed(L, s, s.rows2, s.n_rows2));
+            }
+            return AMGB_OK;
         }
         return fail(AMGB_ENOTIMPL, "smoother kind");
     }
@@ -1013,6 +1023,7 @@ struct amgb_hierarchy {
         return AMGB_OK;
     }
     int block_gauss_seidel(Level &L, const Smoother &s);   // defined below (needs its kernel)
+    int block_jacobi_indexed(Level &L, const Smoother &s, const int *brows, long long m);
 
     // one launch = the whole smoother application (resident_kernel.cuh)
     int resident_apply(Level &L, const Smoother &s)
@@ -1542,6 +1553,88 @@ static int dispatch_block_gs(int bs, int lanes, int nrows, const int *brows, con
     return fail(AMGB_ENOTIMPL, "block_gauss_seidel: blocksize must be 1..8");
 }
 
+// indexed block Jacobi (relaxation.h:1113-1172): the listed block rows are relaxed from the snapshot `xold`
+template <int G, int BS>
+__global__ void __launch_bounds__(kCsrThreads) block_jacobi_indexed_kernel(int nrows, const int *__restrict__ brows,
+                                                                           const int *__restrict__ Ap, const int *__restrict__ Aj,
+                                                                           const double *__restrict__ Ax,
+                                                                           const double *__restrict__ xold,
+                                                                           const double *__restrict__ b,
+                                                                           const double *__restrict__ Dinv,
+                                                                           double *__restrict__ x, double omega)
+{
+    const int lane = threadIdx.x & (G - 1);
+    const long long k = ((long long)blockIdx.x * kCsrThreads + threadIdx.x) / G;
+    const bool active = k < nrows;
+    const int I = active ? brows[k] : 0;
+    double rs[BS];
+#pragma unroll
+    for (int q = 0; q < BS; q++) {
+        double sum = 0.0;
+        if (active) {
+            const int row = I * BS + q;
+            const int s = Ap[row], e = Ap[row + 1];
+            for (int jj = s + lane; jj < e; jj += G) {
+                const int c = ld_stream_i32(Aj + jj);
+                const double v = ld_stream_f64(Ax + jj);
+                if (c / BS != I) sum += v * __ldg(xold + c);
+            }
+        }
+        rs[q] = group_sum<G>(sum);
+    }
+    if (active && lane == 0) {
+        const size_t base = (size_t)I * BS;
+#pragma unroll
+        for (int q = 0; q < BS; q++) rs[q] = b[base + q] - rs[q];
+#pragma unroll
+        for (int q = 0; q < BS; q++) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < BS; c++) v += Dinv[base * BS + (size_t)q * BS + c] * rs[c];
+            x[base + q] = (1.0 - omega) * xold[base + q] + omega * v;
+        }
+    }
+}
+
+template <int BS>
+static int launch_block_jacobi_indexed(int lanes, int nrows, const int *brows, const DevCsr &A, const double *xold,
+                                       const double *b, const double *Dinv, double *x, double omega, cudaStream_t s)
+{
+    if (nrows <= 0) return AMGB_OK;
+    const dim3 g((unsigned)csr_grid(nrows, lanes)), t(kCsrThreads);
+    switch (lanes) {
+    case 1: block_jacobi_indexed_kernel<1, BS><<<g, t, 0, s>>>(nrows, brows, A.Ap, A.Aj, A.Ax, xold, b, Dinv, x, omega); break;
+    case 2: block_jacobi_indexed_kernel<2, BS><<<g, t, 0, s>>>(nrows, brows, A.Ap, A.Aj, A.Ax, xold, b, Dinv, x, omega); break;
+    case 4: block_jacobi_indexed_kernel<4, BS><<<g, t, 0, s>>>(nrows, brows, A.Ap, A.Aj, A.Ax, xold, b, Dinv, x, omega); break;
+    case 8: block_jacobi_indexed_kernel<8, BS><<<g, t, 0, s>>>(nrows, brows, A.Ap, A.Aj, A.Ax, xold, b, Dinv, x, omega); break;
+    case 16: block_jacobi_indexed_kernel<16, BS><<<g, t, 0, s>>>(nrows, brows, A.Ap, A.Aj, A.Ax, xold, b, Dinv, x, omega); break;
+    default: block_jacobi_indexed_kernel<32, BS><<<g, t, 0, s>>>(nrows, brows, A.Ap, A.Aj, A.Ax, xold, b, Dinv, x, omega); break;
+    }
+    CK(cudaGetLastError());
+    return AMGB_OK;
+}
+
+int amgb_hierarchy::block_jacobi_indexed(Level &L, const Smoother &s, const int *brows, long long m)
+{
+    if (recording) return fail(AMGB_ESTATE, "indexed block Jacobi inside the cluster tail");
+    if (m <= 0) return AMGB_OK;
+    double *temp = (L.x == L.x_home) ? L.xalt : L.x_home;
+    RET(copy_vec(temp, L.x, L.A.n_rows));
+    launches++;
+    RET(prof_begin(8, L.A.lanes, m * s.bs, 0, 16.0 * L.A.n_rows + (4.0 + (24.0 + 8.0 * s.bs) * s.bs) * (double)m));
+    switch (s.bs) {
+    case 2: RET(launch_block_jacobi_indexed<2>(L.A.lanes, (int)m, brows, L.A, temp, L.b, s.Dinv, L.x, s.omega, stream)); break;
+    case 3: RET(launch_block_jacobi_indexed<3>(L.A.lanes, (int)m, brows, L.A, temp, L.b, s.Dinv, L.x, s.omega, stream)); break;
+    case 4: RET(launch_block_jacobi_indexed<4>(L.A.lanes, (int)m, brows, L.A, temp, L.b, s.Dinv, L.x, s.omega, stream)); break;
+    case 5: RET(launch_block_jacobi_indexed<5>(L.A.lanes, (int)m, brows, L.A, temp, L.b, s.Dinv, L.x, s.omega, stream)); break;
+    case 6: RET(launch_block_jacobi_indexed<6>(L.A.lanes, (int)m, brows, L.A, temp, L.b, s.Dinv, L.x, s.omega, stream)); break;
+    case 7: RET(launch_block_jacobi_indexed<7>(L.A.lanes, (int)m, brows, L.A, temp, L.b, s.Dinv, L.x, s.omega, stream)); break;
+    case 8: RET(launch_block_jacobi_indexed<8>(L.A.lanes, (int)m, brows, L.A, temp, L.b, s.Dinv, L.x, s.omega, stream)); break;
+    default: RET(launch_block_jacobi_indexed<1>(L.A.lanes, (int)m, brows, L.A, temp, L.b, s.Dinv, L.x, s.omega, stream)); break;
+    }
+    return prof_end();
+}
+
 int amgb_hierarchy::block_gauss_seidel(Level &L, const Smoother &s)
 {
     if (recording) return fail(AMGB_ESTATE, "block Gauss-Seidel inside the cluster tail");
@@ -1623,6 +1716,15 @@ int amgb_hierarchy::make_smoother(const SmootherSpec &sp, const HostCsr &Aperm, 
         RET(upload(&s.rows2, l2.data(), (long long)l2.size()));
         s.n_rows1 = (long long)l1.size();
         s.n_rows2 = (long long)l2.size();
+    } else if (sp.kind == AMGB_SM_CF_BLOCK_JACOBI || sp.kind == AMGB_SM_FC_BLOCK_JACOBI) {
+        if (pos) return fail(AMGB_ESTATE, "block CF Jacobi on a permuted level");
+        s.f_iterations = sp.f_iterations;
+        s.c_iterations = sp.c_iterations;
+        RET(upload(&s.Dinv, sp.Dinv.data(), (long long)sp.Dinv.size()));
+        RET(upload(&s.rows1, sp.list.data(), (long long)sp.list.size()));
+        RET(upload(&s.rows2, sp.list2.data(), (long long)sp.list2.size()));
+        s.n_rows1 = (long long)sp.list.size();
+        s.n_rows2 = (long long)sp.list2.size();
     } else if (sp.kind == AMGB_SM_BLOCK_GAUSS_SEIDEL) {
         if (pos) return fail(AMGB_ESTATE, "block Gauss-Seidel on a permuted level");
         RET(upload(&s.Dinv, sp.Dinv.data(), (long long)sp.Dinv.size()));
@@ -1679,6 +1781,7 @@ int amgb_hierarchy::finalize_levels()
         // block smoothers address x in natural block numbering: such levels are never permuted
         if (H.pre.kind == AMGB_SM_BLOCK_JACOBI || H.post.kind == AMGB_SM_BLOCK_JACOBI) continue;
         if (H.pre.kind == AMGB_SM_BLOCK_GAUSS_SEIDEL || H.post.kind == AMGB_SM_BLOCK_GAUSS_SEIDEL) continue;
+        if (H.pre.kind >= AMGB_SM_CF_BLOCK_JACOBI || H.post.kind >= AMGB_SM_CF_BLOCK_JACOBI) continue;
         const SmootherSpec *src = nullptr;
         if (H.pre.kind == AMGB_SM_GAUSS_SEIDEL) { src = &H.pre; layout_src[(size_t)l] = 0; }
         else if (H.post.kind == AMGB_SM_GAUSS_SEIDEL) { src = &H.post; layout_src[(size_t)l] = 1; }
@@ -1861,6 +1964,28 @@ static int copy_smoother(const amgb_smoother *in, const HostCsr &A, SmootherSpec
         if (in->Dinv == nullptr) return fail(AMGB_EINVAL, "block_gauss_seidel: Dinv required");
         s.Dinv.assign(in->Dinv, in->Dinv + (size_t)A.n_rows * s.bs);
         return AMGB_OK;
+    case AMGB_SM_CF_BLOCK_JACOBI:
+    case AMGB_SM_FC_BLOCK_JACOBI: {
+        s.bs = in->blocksize;
+        if (s.bs < 1 || s.bs > 8 || A.n_rows % s.bs)
+            return fail(AMGB_ENOTIMPL, "cf_block_jacobi: blocksize must be 1..8 and divide n");
+        if (in->Dinv == nullptr) return fail(AMGB_EINVAL, "cf_block_jacobi: Dinv required");
+        if (in->n_indices < 0 || in->n_indices2 < 0 || (in->n_indices > 0 && in->indices == nullptr) ||
+            (in->n_indices2 > 0 && in->indices2 == nullptr))
+            return fail(AMGB_EINVAL, "cf_block_jacobi: null block-row list");
+        s.Dinv.assign(in->Dinv, in->Dinv + (size_t)A.n_rows * s.bs);
+        s.list.assign(in->indices, in->indices + in->n_indices);
+        s.list2.assign(in->indices2, in->indices2 + in->n_indices2);
+        s.f_iterations = in->f_iterations;
+        s.c_iterations = in->c_iterations;
+        if (s.f_iterations < 0 || s.c_iterations < 0) return fail(AMGB_EINVAL, "cf_block_jacobi: iterations < 0");
+        const int nb = A.n_rows / s.bs;
+        for (int v : s.list)
+            if (v < 0 || v >= nb) return fail(AMGB_EINVAL, "cf_block_jacobi: block-row index out of range");
+        for (int v : s.list2)
+            if (v < 0 || v >= nb) return fail(AMGB_EINVAL, "cf_block_jacobi: block-row index out of range");
+        return AMGB_OK;
+    }
     case AMGB_SM_POLYNOMIAL:
         if (in->coefficients == nullptr || in->n_coefficients < 1)
             return fail(AMGB_EINVAL, "polynomial: at least one coefficient required");

@@ -17,7 +17,8 @@ from scipy import sparse
 from .. import _engine as E
 
 __all__ = ["make_system", "jacobi", "gauss_seidel", "gauss_seidel_indexed", "block_jacobi", "sor",
-           "polynomial", "jacobi_indexed", "cf_jacobi", "fc_jacobi", "block_gauss_seidel"]
+           "polynomial", "jacobi_indexed", "cf_jacobi", "fc_jacobi", "block_gauss_seidel", "cf_block_jacobi",
+           "fc_block_jacobi"]
 
 
 def make_system(A, x, b, formats=None):
@@ -340,3 +341,41 @@ def block_gauss_seidel(A, x, b, iterations=1, sweep="forward", blocksize=1, Dinv
     for _ in range(iterations):
         E.check(L.amgb_host_block_gauss_seidel(E.i32p(Ap), len(Ap), E.i32p(Aj), len(Aj), E.f64p(Ax), len(Ax),
                                                E.f64p(x), n, E.f64p(b), n, E.f64p(Tx), len(Tx), *rs, blocksize))
+
+
+def _cf_block(kind, A, x, b, Cpts, Fpts, Dinv, blocksize, iterations, f_iterations, c_iterations, omega):
+    A, x, b = make_system(A, x, b, formats=["csr", "bsr"])
+    _fp64(A)
+    A = A.tobsr(blocksize=(blocksize, blocksize))
+    if Dinv is None:
+        from ..util import get_block_diag
+        Dinv = get_block_diag(A, blocksize=blocksize, inv_flag=True)
+    elif Dinv.shape[0] != int(A.shape[0] / blocksize):
+        raise ValueError("Dinv and A have incompatible dimensions")
+    elif (Dinv.shape[1] != blocksize) or (Dinv.shape[2] != blocksize):
+        raise ValueError("Dinv and blocksize are incompatible")
+    Cpts = np.ascontiguousarray(np.asarray(Cpts), dtype=np.int32)
+    Fpts = np.ascontiguousarray(np.asarray(Fpts), dtype=np.int32)
+    if A.shape[0] == 0 or iterations < 1:
+        return
+    Tx = np.ascontiguousarray(Dinv, dtype=np.float64).reshape(-1)
+    S = _descriptor()
+    S.kind, S.iterations, S.omega, S.blocksize = kind, int(iterations), float(np.real(omega)), int(blocksize)
+    S.Dinv = E.f64p(Tx)
+    S.indices, S.n_indices = E.i32p(Cpts), len(Cpts)
+    S.indices2, S.n_indices2 = E.i32p(Fpts), len(Fpts)
+    S.f_iterations, S.c_iterations = int(f_iterations), int(c_iterations)
+    _relax(A, x, b, S, [Cpts, Fpts, Tx])
+
+
+def cf_block_jacobi(A, x, b, Cpts, Fpts, Dinv=None, blocksize=1, iterations=1, f_iterations=1, c_iterations=1,
+                    omega=1.0):
+    """CF block Jacobi: block rows listed in Cpts, then those in Fpts, each relaxed from a snapshot of the iterate
+    (relaxation.py:1271-1339 -> block_jacobi_indexed, relaxation.h:1113-1172)."""
+    _cf_block(E.SM_CF_BLOCK_JACOBI, A, x, b, Cpts, Fpts, Dinv, blocksize, iterations, f_iterations, c_iterations, omega)
+
+
+def fc_block_jacobi(A, x, b, Cpts, Fpts, Dinv=None, blocksize=1, iterations=1, f_iterations=1, c_iterations=1,
+                    omega=1.0):
+    """FC block Jacobi (relaxation.py:1342-1412): F block rows first, then C."""
+    _cf_block(E.SM_FC_BLOCK_JACOBI, A, x, b, Cpts, Fpts, Dinv, blocksize, iterations, f_iterations, c_iterations, omega)

@@ -205,8 +205,16 @@ def _setup_cf_block(fn_block_name, setup_point, lvl, f_iterations, c_iterations,
     if len(lvl.splitting) * blocksize != lvl.A.shape[0]:
         raise ValueError("Blocksize not compatible with CF-splitting and matrix size.")
     if blocksize != 1:
-        raise NotImplementedError(f"smoother '{fn_block_name}' with blocksize > 1 is not on the GPU hot path "
-                                  "(no CPU fallback)")
+        Fpts, Cpts = _extract_splitting(lvl)
+        if Dinv is None:
+            Dinv = get_block_diag(lvl.A, blocksize=blocksize, inv_flag=True)
+        if withrho:
+            omega = omega / rho_block_D_inv_A(lvl.A, Dinv)
+        fn = getattr(relaxation, fn_block_name)
+        smoother = partial(fn, Cpts=Cpts, Fpts=Fpts, f_iterations=f_iterations, c_iterations=c_iterations,
+                           iterations=iterations, omega=omega, Dinv=Dinv, blocksize=blocksize)     # smoothing.py:741-751
+        update_wrapper(smoother, fn)
+        return smoother
     # blocksize 1: block Jacobi is point Jacobi; the reference forwards only iterations / omega / withrho
     # (smoothing.py:735-739), the registry name stays the block one
     smoother = setup_point(lvl, iterations=iterations, omega=omega, withrho=withrho)
@@ -216,14 +224,14 @@ def _setup_cf_block(fn_block_name, setup_point, lvl, f_iterations, c_iterations,
 
 def setup_cf_block_jacobi(lvl, f_iterations=DEFAULT_NITER, c_iterations=DEFAULT_NITER, iterations=DEFAULT_NITER,
                           omega=1.0, Dinv=None, blocksize=None, withrho=False):
-    """smoothing.py:710-751 (blocksize 1 only: the scalar degenerate case)."""
+    """smoothing.py:710-751."""
     return _setup_cf_block("cf_block_jacobi", setup_cf_jacobi, lvl, f_iterations, c_iterations, iterations,
                            omega, Dinv, blocksize, withrho)
 
 
 def setup_fc_block_jacobi(lvl, f_iterations=DEFAULT_NITER, c_iterations=DEFAULT_NITER, iterations=DEFAULT_NITER,
                           omega=1.0, Dinv=None, blocksize=None, withrho=False):
-    """smoothing.py:754-791 (blocksize 1 only)."""
+    """smoothing.py:754-791."""
     return _setup_cf_block("fc_block_jacobi", setup_fc_jacobi, lvl, f_iterations, c_iterations, iterations,
                            omega, Dinv, blocksize, withrho)
 
@@ -435,6 +443,23 @@ def describe(sm, A, keep):
                 raise NotImplementedError("CF Jacobi on a BSR operator (bsr_jacobi_indexed) is not on the GPU hot path")
         keep.append(idx)
         S.indices, S.n_indices = E.i32p(idx), len(idx)
+    elif name in ("cf_block_jacobi", "fc_block_jacobi"):
+        S.kind = E.SM_CF_BLOCK_JACOBI if name == "cf_block_jacobi" else E.SM_FC_BLOCK_JACOBI
+        S.omega = float(np.real(kw.get("omega", 1.0)))
+        bs = int(kw.get("blocksize", 1))
+        Dinv = kw.get("Dinv", None)
+        if Dinv is None:
+            Dinv = get_block_diag(A, blocksize=bs, inv_flag=True)
+        Dinv = np.ascontiguousarray(Dinv, dtype=np.float64)
+        if Dinv.shape != (A.shape[0] // bs, bs, bs):
+            raise ValueError("Dinv and A have incompatible dimensions")
+        idx = np.ascontiguousarray(np.asarray(kw["Cpts"]), dtype=np.int32)
+        idx2 = np.ascontiguousarray(np.asarray(kw["Fpts"]), dtype=np.int32)
+        keep += [Dinv, idx, idx2]
+        S.blocksize, S.Dinv = bs, E.f64p(Dinv.reshape(-1))
+        S.indices, S.n_indices = E.i32p(idx), len(idx)
+        S.indices2, S.n_indices2 = E.i32p(idx2), len(idx2)
+        S.f_iterations, S.c_iterations = int(kw.get("f_iterations", 1)), int(kw.get("c_iterations", 1))
     elif name == "block_gauss_seidel":
         S.kind = E.SM_BLOCK_GAUSS_SEIDEL
         sweep = kw.get("sweep", "forward")

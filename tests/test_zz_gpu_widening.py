@@ -664,3 +664,59 @@ def test_adopted_hierarchies_all_solve_variants_match_the_reference(family):
             xg, ig = gpu.solve(b, residuals=rg, return_info=True, **kw)
             assert (ir, len(rr)) == (ig, len(rg)), kw
             assert relerr(xg, xr) < 1e-9, kw
+
+
+# ------------------------------------------------------------------ CF / FC block Jacobi (AIR on block systems)
+@pytest.mark.parametrize("bs", [2, 3])
+def test_cf_fc_block_jacobi_match_oracle_and_compiled_reference(bs):
+    """relaxation.cf_block_jacobi / fc_block_jacobi (relaxation.py:1271-1412 -> block_jacobi_indexed,
+    relaxation.h:1113-1172): listed block rows relaxed from a snapshot, C then F or F then C."""
+    from pyamg_b200.util import get_block_diag
+    rng = np.random.default_rng(40 + bs)
+    nb = 15
+    n = nb * bs
+    A = sp.random(n, n, density=0.3, random_state=np.random.RandomState(bs), format="csr")
+    A = (A + A.T + sp.eye(n) * 8).tobsr(blocksize=(bs, bs))
+    Dinv = get_block_diag(A, blocksize=bs, inv_flag=True)
+    split = rng.random(nb) < 0.5
+    C, F = np.where(split)[0], np.where(~split)[0]
+    x0, b = rng.standard_normal(n), rng.standard_normal(n)
+    kern = "ref" if oracle.have_ref() else "oracle"
+    for fg, fo in ((gpu_relax.cf_block_jacobi, oracle.cf_block_jacobi), (gpu_relax.fc_block_jacobi, oracle.fc_block_jacobi)):
+        for kw in ({}, {"iterations": 2, "f_iterations": 2, "c_iterations": 0, "omega": 0.7}):
+            xg, xo = x0.copy(), x0.copy()
+            fg(A, xg, b, C, F, Dinv=Dinv, blocksize=bs, **kw)
+            fo(A, xo, b, C, F, Dinv=Dinv, blocksize=bs, kernels=kern, **kw)
+            assert relerr(xg, xo) < TOL
+
+
+def test_block_cf_jacobi_in_a_cycle_and_through_hierarchy_io(tmp_path):
+    """A two-level block hierarchy with fc_block_jacobi (what air_solver installs on BSR operators): engine vs oracle,
+    also after a save / load round trip of the descriptor (Cpts, Fpts, Dinv, blocksize)."""
+    from pyamg_b200.hierarchy_io import save_hierarchy, load_hierarchy
+    from pyamg_b200.relaxation.smoothing import change_smoothers
+    rng = np.random.default_rng(77)
+    bs, nb, ncb = 2, 30, 9
+    n, nc = nb * bs, ncb * bs
+    A = sp.random(n, n, density=0.15, random_state=np.random.RandomState(5), format="csr")
+    A = sp.bsr_array((A + A.T + sp.eye(n) * 6).tobsr(blocksize=(bs, bs)))
+    P = sp.bsr_array(sp.kron(sp.csr_array((np.ones(nb), (np.arange(nb), np.arange(nb) % ncb)), shape=(nb, ncb)),
+                             np.eye(bs)).tobsr(blocksize=(bs, bs)))
+    R = sp.bsr_array(P.T.tobsr(blocksize=(bs, bs)))
+    def i32(M):
+        M.indptr, M.indices = M.indptr.astype(np.int32), M.indices.astype(np.int32)
+        return M
+    l0, l1 = pyamg_b200.MultilevelSolver.Level(), pyamg_b200.MultilevelSolver.Level()
+    l0.A, l0.P, l0.R = i32(A), i32(P), i32(R)
+    l1.A = i32(sp.bsr_array((R @ A @ P).tobsr(blocksize=(bs, bs))))
+    l0.splitting = rng.random(nb) < 0.4
+    ml = pyamg_b200.MultilevelSolver([l0, l1])
+    change_smoothers(ml, ("cf_block_jacobi", {"omega": 0.8}), ("fc_block_jacobi", {"omega": 0.8, "f_iterations": 2}))
+    b = rng.standard_normal(n)
+    xo = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(l1.A)).solve(b, tol=0, maxiter=3)
+    assert relerr(ml.solve(b, tol=0, maxiter=3), xo) < TOL
+    p = str(tmp_path / "h.npz")
+    save_hierarchy(p, ml)
+    ml2, _ = load_hierarchy(p)
+    assert ml2.levels[0].postsmoother.__name__ == "fc_block_jacobi"
+    assert relerr(ml2.solve(b, tol=0, maxiter=3), xo) < TOL
