@@ -56,6 +56,14 @@ extern "C" {
                                      relaxation.h:1113-1172): indices / indices2 list BLOCK rows (C / F), Dinv as for
                                      block Jacobi; AIR's smoother for block systems */
 #define AMGB_SM_FC_BLOCK_JACOBI 10 /* relaxation.fc_block_jacobi (relaxation.py:1342-1412) */
+/* normal-equation smoothers (Kaczmarz family): the descriptor's Dinv is an n-vector -- 1 / diag(A A^H) for the NE
+ * kinds, 1 / diag(A^H A) for NR (util.get_diagonal(norm_eq = 2 | 1), relaxation.py:798, :881, :969); the engine
+ * keeps its own column-sorted copies of A and A^T for them (the reference sorts the operator in place there) */
+#define AMGB_SM_JACOBI_NE 11        /* relaxation.jacobi_ne (relaxation.py:734-812 -> relaxation.h:579-606) */
+#define AMGB_SM_GAUSS_SEIDEL_NE 12  /* relaxation.gauss_seidel_ne (relaxation.py:815-901 -> relaxation.h:633-657):
+                                       row projections in dependency waves of the A A^T conflict graph */
+#define AMGB_SM_GAUSS_SEIDEL_NR 13  /* relaxation.gauss_seidel_nr (relaxation.py:904-999 -> relaxation.h:684-713):
+                                       column projections on the residual, waves of the A^T A conflict graph */
 
 #define AMGB_SWEEP_FORWARD 0
 #define AMGB_SWEEP_BACKWARD 1

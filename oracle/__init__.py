@@ -293,6 +293,103 @@ def fc_block_jacobi(A, x, b, Cpts, Fpts, Dinv=None, blocksize=1, iterations=1, f
     _cf_block_jacobi("fc", A, x, b, Cpts, Fpts, Dinv, blocksize, iterations, f_iterations, c_iterations, omega, kernels)
 
 
+def get_diagonal(A, norm_eq=False, inv=False):
+    """pyamg/util/utils.py:530-600: diag(A), diag(A^H A) (norm_eq=1) or diag(A A^H) (norm_eq=2); sorts A IN PLACE."""
+    A.sort_indices()
+    if norm_eq == 1:
+        At = A.T
+        D = (At.multiply(At.conjugate())) @ np.ones((At.shape[0],))
+    elif norm_eq == 2:
+        D = (A.multiply(A.conjugate())) @ np.ones((A.shape[0],))
+    else:
+        D = A.diagonal()
+    if inv:
+        Dinv = np.zeros_like(D)
+        mask = D != 0.0
+        Dinv[mask] = 1.0 / D[mask]
+        return Dinv
+    return D
+
+
+def jacobi_ne(A, x, b, iterations=1, omega=1.0, kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:734-812 -> relaxation.h:579-606."""
+    A, x, b = make_system(A, x, b, formats=["csr"])
+    _f64(A, x, b)
+    n = A.shape[0]
+    temp = np.zeros_like(x)
+    Dinv = get_diagonal(A, norm_eq=2, inv=True)
+    for _ in range(iterations):
+        delta = np.ascontiguousarray(np.ravel(b - matvec(A, x, kernels)) * np.ravel(Dinv))
+        if kernels == "ref":
+            lib("ref").ref_jacobi_ne(_ip(A.indptr), n, _ip(A.indices), _dp(A.data), len(A.data), _dp(x), _dp(b),
+                                     _dp(delta), _dp(temp), ctypes.c_double(float(omega)))
+        else:
+            lib().oracle_jacobi_ne(_ip(A.indptr), _ip(A.indices), _dp(A.data), _dp(x), _dp(delta), _dp(temp), n,
+                                   ctypes.c_double(float(omega)))
+
+
+def gauss_seidel_ne(A, x, b, iterations=1, sweep="forward", omega=1.0, Dinv=None, kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:815-901 -> relaxation.h:633-657."""
+    A, x, b = make_system(A, x, b, formats=["csr"])
+    _f64(A, x, b)
+    n = A.shape[0]
+    if Dinv is None:
+        Dinv = np.ravel(get_diagonal(A, norm_eq=2, inv=True))
+    if sweep == "forward":
+        rs = (0, n, 1)
+    elif sweep == "backward":
+        rs = (n - 1, -1, -1)
+    elif sweep == "symmetric":
+        for _ in range(iterations):
+            gauss_seidel_ne(A, x, b, 1, "forward", omega, Dinv, kernels)
+            gauss_seidel_ne(A, x, b, 1, "backward", omega, Dinv, kernels)
+        return
+    else:
+        raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+    Dinv = np.ascontiguousarray(Dinv, dtype=np.float64)
+    for _ in range(iterations):
+        if kernels == "ref":
+            lib("ref").ref_gauss_seidel_ne(_ip(A.indptr), n, _ip(A.indices), _dp(A.data), len(A.data), _dp(x), _dp(b),
+                                           *rs, _dp(Dinv), ctypes.c_double(float(omega)))
+        else:
+            lib().oracle_gauss_seidel_ne(_ip(A.indptr), _ip(A.indices), _dp(A.data), _dp(x), _dp(b), *rs, _dp(Dinv),
+                                         ctypes.c_double(float(omega)))
+
+
+def gauss_seidel_nr(A, x, b, iterations=1, sweep="forward", omega=1.0, Dinv=None, kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:904-999 -> relaxation.h:684-713 (A in CSC)."""
+    if not (sparse.issparse(A) and A.format == "csc"):
+        A = sparse.csc_array(A)
+    A.indptr, A.indices = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    if not isinstance(x, np.ndarray) or not isinstance(b, np.ndarray):
+        raise ValueError("expected numpy arrays")
+    x, b = np.ravel(x), np.ravel(b)
+    n = A.shape[0]
+    if Dinv is None:
+        Dinv = np.ravel(get_diagonal(A, norm_eq=1, inv=True))
+    if sweep == "forward":
+        cs = (0, n, 1)
+    elif sweep == "backward":
+        cs = (n - 1, -1, -1)
+    elif sweep == "symmetric":
+        for _ in range(iterations):
+            gauss_seidel_nr(A, x, b, 1, "forward", omega, Dinv, kernels)
+            gauss_seidel_nr(A, x, b, 1, "backward", omega, Dinv, kernels)
+        return
+    else:
+        raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+    Dinv = np.ascontiguousarray(Dinv, dtype=np.float64)
+    r = np.ascontiguousarray(b - A @ x)
+    data = np.ascontiguousarray(A.data, dtype=np.float64)
+    for _ in range(iterations):
+        if kernels == "ref":
+            lib("ref").ref_gauss_seidel_nr(_ip(A.indptr), n, _ip(A.indices), _dp(data), len(data), _dp(x), _dp(r),
+                                           *cs, _dp(Dinv), ctypes.c_double(float(omega)))
+        else:
+            lib().oracle_gauss_seidel_nr(_ip(A.indptr), _ip(A.indices), _dp(data), _dp(x), _dp(r), *cs, _dp(Dinv),
+                                         ctypes.c_double(float(omega)))
+
+
 def polynomial(A, x, b, coefficients, iterations=1, kernels="oracle"):
     """pyamg/relaxation/relaxation.py:585-659: x += p(A)(b - A x) by Horner's rule; the matvecs are the
     reference's SciPy calls restated (``matvec``)."""
@@ -386,6 +483,9 @@ _SMOOTHERS = {
     "block_gauss_seidel": block_gauss_seidel,
     "cf_block_jacobi": cf_block_jacobi,
     "fc_block_jacobi": fc_block_jacobi,
+    "jacobi_ne": jacobi_ne,
+    "gauss_seidel_ne": gauss_seidel_ne,
+    "gauss_seidel_nr": gauss_seidel_nr,
 }
 
 
@@ -414,6 +514,15 @@ def smoother_spec(sm):
         coef = cv["coefficients"] if "coefficients" in cv else [cv["omega"]]
         return ("polynomial", {"coefficients": np.asarray(coef, dtype=np.float64),
                                "iterations": int(cv.get("iterations", 1))})
+    if getattr(sm, "__name__", "") in ("jacobi_ne", "gauss_seidel_ne", "gauss_seidel_nr") and getattr(sm, "__closure__", None):
+        # smoothing.py:641-675: closures around relaxation.<name>(lvl.Acsr | lvl.Acsc, x, b, ...); the operator they
+        # relax with is the level's own A in another format, so only the scalar parameters are taken from the cells
+        own = getattr(sm, "_ne_parameters", None)          # closures built by pyamg_b200 carry them as an attribute
+        if own is not None:
+            return (sm.__name__, dict(own))
+        cv = {k: c.cell_contents for k, c in zip(sm.__code__.co_freevars, sm.__closure__)}
+        kw = {k: cv[k] for k in ("iterations", "sweep", "omega") if k in cv}
+        return (sm.__name__, kw)
     raise NotImplementedError(f"oracle: smoother {sm!r} is not introspectable")
 
 
@@ -442,6 +551,11 @@ def _smooth(spec, A, x, b, kernels):
     fn = _SMOOTHERS.get(name)
     if fn is None:
         raise NotImplementedError(f"oracle: smoother '{name}' out of hot-path scope")
+    if name in ("jacobi_ne", "gauss_seidel_ne"):
+        A = sparse.csr_array(A).copy()             # lvl.Acsr: a CSR view the reference sorts in place, not lvl.A
+        A.indptr, A.indices = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    elif name == "gauss_seidel_nr":
+        A = sparse.csc_array(sparse.csr_array(A))   # lvl.Acsc
     fn(A, x, b, kernels=kernels, **kw)
 
 

@@ -94,4 +94,27 @@ void ref_block_jacobi_indexed(const int *Ap, int nb, const int *Aj, const double
                                               Dinv, nb * bs * bs, Id, n_id, &omega, 1, bs);
 }
 
+// pyamg/amg_core/relaxation.h:579-606
+void ref_jacobi_ne(const int *Ap, int n, const int *Aj, const double *Ax, int nnz, double *x, const double *b,
+                   const double *delta, double *temp, double omega)
+{
+    jacobi_ne<int, double, double>(Ap, n + 1, Aj, nnz, Ax, nnz, x, n, b, n, delta, n, temp, n, 0, n, 1, &omega, 1);
+}
+
+// pyamg/amg_core/relaxation.h:633-657
+void ref_gauss_seidel_ne(const int *Ap, int n, const int *Aj, const double *Ax, int nnz, double *x, const double *b,
+                         int row_start, int row_stop, int row_step, const double *Dinv, double omega)
+{
+    gauss_seidel_ne<int, double, double>(Ap, n + 1, Aj, nnz, Ax, nnz, x, n, b, n, row_start, row_stop, row_step,
+                                         Dinv, n, omega);
+}
+
+// pyamg/amg_core/relaxation.h:684-713
+void ref_gauss_seidel_nr(const int *Ap, int n, const int *Aj, const double *Ax, int nnz, double *x, double *z,
+                         int col_start, int col_stop, int col_step, const double *Dinv, double omega)
+{
+    gauss_seidel_nr<int, double, double>(Ap, n + 1, Aj, nnz, Ax, nnz, x, n, z, n, col_start, col_stop, col_step,
+                                         Dinv, n, omega);
+}
+
 }  // extern "C"

@@ -337,6 +337,44 @@ __global__ void __launch_bounds__(1024) reduce_max_kernel(const double *partials
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Kaczmarz-type sweeps (gauss_seidel_ne / gauss_seidel_nr, relaxation.h:633-657, :684-713): G lanes per row of M
+// (= A for NE, = A^T for NR); the rows of one launch share no column (conflict waves), so the scatter updates of
+// different rows never touch the same entry of v.
+//   NE: delta = (b_i - sum_j m_ij v_j) * Dinv_i * omega ;  v_j += m_ij * delta            (v = x)
+//   NR: delta = (sum_j m_ij v_j) * (Dinv_i * omega)     ;  x_i += delta ; v_j -= delta * m_ij   (v = r)
+// ---------------------------------------------------------------------------------------------
+template <int G, bool NR>
+__global__ void __launch_bounds__(kCsrThreads) kaczmarz_kernel(int nrows, const int *__restrict__ rows,
+                                                               const int *__restrict__ Mp, const int *__restrict__ Mj,
+                                                               const double *__restrict__ Mx, double *v,
+                                                               const double *__restrict__ b,
+                                                               const double *__restrict__ Dinv, double omega, double *xout)
+{
+    const int lane = threadIdx.x & (G - 1);
+    const long long k = ((long long)blockIdx.x * kCsrThreads + threadIdx.x) / G;
+    const bool active = k < nrows;
+    int row = 0, start = 0, end = 0;
+    if (active) {
+        row = rows[k];
+        start = Mp[row];
+        end = Mp[row + 1];
+    }
+    double sum = 0.0;
+    for (int jj = start + lane; jj < end; jj += G) sum += Mx[jj] * v[Mj[jj]];
+    sum = group_sum<G>(sum);                       // every lane of the group holds the row's inner product
+    if (!active) return;                           // (after the shuffles: inactive groups took part in them)
+    double delta;
+    if (NR) {
+        delta = sum * (Dinv[row] * omega);
+        if (lane == 0) xout[row] += delta;
+        for (int jj = start + lane; jj < end; jj += G) v[Mj[jj]] -= delta * Mx[jj];
+    } else {
+        delta = (b[row] - sum) * Dinv[row] * omega;
+        for (int jj = start + lane; jj < end; jj += G) v[Mj[jj]] += Mx[jj] * delta;
+    }
+}
+
 // Arnoldi pieces (amgb_arnoldi_run): everything between two host reads stays on the device
 __global__ void sqrt_scalar_kernel(double *p) { *p = sqrt(*p); }
 // y = x / *den   (next Krylov basis vector: w / ||w|| with the norm in a device scalar)

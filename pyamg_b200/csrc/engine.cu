@@ -403,6 +403,9 @@ struct Smoother {
     long long n_rows1 = 0, n_rows2 = 0;
     int f_iterations = 1, c_iterations = 1;
     bool cf_contig = false;          // CF/FC Jacobi on a level stored C|F: ws.ptr = {0, nC, n} (+ tile ranges)
+    // normal-equation smoothers: column-sorted copies of A (ne_A) and A^T (ne_At; omega-scaled for jacobi_ne),
+    // inverse diagonal of A A^H or A^H A in Dinv, conflict waves of the sweep operator in ws (row lists)
+    DevCsr ne_A, ne_At;
     std::vector<double> coef;        // polynomial coefficients (host: they become kernel arguments)
     // EXPERIMENTAL resident-vector cluster sweep (AMGB_RESIDENT=1): device copies of the schedule
     long long *res_wave_ptr = nullptr;
@@ -916,6 +919,9 @@ struct amgb_hierarchy {
             }
             return AMGB_OK;
         case AMGB_SM_BLOCK_GAUSS_SEIDEL: return block_gauss_seidel(L, s);
+        case AMGB_SM_JACOBI_NE:
+        case AMGB_SM_GAUSS_SEIDEL_NE:
+        case AMGB_SM_GAUSS_SEIDEL_NR: return normal_equations(L, s);
         case AMGB_SM_CF_BLOCK_JACOBI:                                  // relaxation.py:1328-1339
         case AMGB_SM_FC_BLOCK_JACOBI:                                  // relaxation.py:1401-1412
             for (int it = 0; it < s.iterations; it++) {
@@ -1022,6 +1028,7 @@ struct amgb_hierarchy {
         launches++;
         return AMGB_OK;
     }
+    int normal_equations(Level &L, const Smoother &s);     // jacobi_ne / gauss_seidel_ne / gauss_seidel_nr
     int block_gauss_seidel(Level &L, const Smoother &s);   // defined below (needs its kernel)
     int block_jacobi_indexed(Level &L, const Smoother &s, const int *brows, long long m);
 
@@ -1635,6 +1642,129 @@ int amgb_hierarchy::block_jacobi_indexed(Level &L, const Smoother &s, const int 
     return prof_end();
 }
 
+// ------------------------------------------------------------------------------------------
+// normal-equation smoothers
+// ------------------------------------------------------------------------------------------
+static void sort_rows_by_column(HostCsr &A)       // what scipy's sort_indices does (util.get_diagonal sorts in place)
+{
+    std::vector<std::pair<int, double>> row;
+    for (int i = 0; i < A.n_rows; i++) {
+        const int s = A.Ap[(size_t)i], e = A.Ap[(size_t)i + 1];
+        row.resize((size_t)(e - s));
+        for (int jj = s; jj < e; jj++) row[(size_t)(jj - s)] = {A.Aj[(size_t)jj], A.Ax[(size_t)jj]};
+        std::stable_sort(row.begin(), row.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.first < b.first; });
+        for (int jj = s; jj < e; jj++) { A.Aj[(size_t)jj] = row[(size_t)(jj - s)].first; A.Ax[(size_t)jj] = row[(size_t)(jj - s)].second; }
+    }
+}
+
+static void transpose_csr(const HostCsr &A, HostCsr &T)     // rows of T = columns of A, entries by ascending row of A
+{
+    T.n_rows = A.n_cols; T.n_cols = A.n_rows;
+    T.Ap.assign((size_t)A.n_cols + 1, 0);
+    T.Aj.resize(A.Aj.size());
+    T.Ax.resize(A.Ax.size());
+    for (int c : A.Aj) T.Ap[(size_t)c + 1]++;
+    for (int c = 0; c < A.n_cols; c++) T.Ap[(size_t)c + 1] += T.Ap[(size_t)c];
+    std::vector<int> cur(T.Ap.begin(), T.Ap.end() - 1);
+    for (int i = 0; i < A.n_rows; i++)
+        for (int jj = A.Ap[(size_t)i]; jj < A.Ap[(size_t)i + 1]; jj++) {
+            const int p = cur[(size_t)A.Aj[(size_t)jj]]++;
+            T.Aj[(size_t)p] = i;
+            T.Ax[(size_t)p] = A.Ax[(size_t)jj];
+        }
+}
+
+// sequential sweep over the rows 0..n-1 of M, each reading AND writing the vector entries of its columns: row i goes
+// to wave 1 + (latest wave that touched any of its columns); waves in order == the sequential sweep, in reverse
+// order == the backward sweep
+static bool build_conflict_waves(const HostCsr &M, std::vector<int> &rows_sorted, std::vector<long long> &ptr)
+{
+    std::vector<int> last((size_t)M.n_cols, 0), w((size_t)M.n_rows);
+    std::vector<int> seen((size_t)M.n_cols, -1);
+    int maxw = 0;
+    for (int i = 0; i < M.n_rows; i++) {
+        int wv = 0;
+        for (int jj = M.Ap[(size_t)i]; jj < M.Ap[(size_t)i + 1]; jj++) {
+            const int c = M.Aj[(size_t)jj];
+            if (seen[(size_t)c] == i) return false;            // duplicate column in a row: lanes would collide
+            seen[(size_t)c] = i;
+            wv = std::max(wv, last[(size_t)c]);
+        }
+        wv += 1;
+        w[(size_t)i] = wv;
+        for (int jj = M.Ap[(size_t)i]; jj < M.Ap[(size_t)i + 1]; jj++) last[(size_t)M.Aj[(size_t)jj]] = wv;
+        maxw = std::max(maxw, wv);
+    }
+    ptr.assign((size_t)maxw + 1, 0);
+    for (int i = 0; i < M.n_rows; i++) ptr[(size_t)w[(size_t)i]]++;
+    for (int q = 0; q < maxw; q++) ptr[(size_t)q + 1] += ptr[(size_t)q];
+    rows_sorted.resize((size_t)M.n_rows);
+    std::vector<long long> cur(ptr.begin(), ptr.end() - 1);
+    for (int i = 0; i < M.n_rows; i++) rows_sorted[(size_t)cur[(size_t)w[(size_t)i] - 1]++] = i;
+    return true;
+}
+
+template <bool NR>
+static int launch_kaczmarz(int lanes, int nrows, const int *rows, const DevCsr &M, double *v, const double *b,
+                           const double *Dinv, double omega, double *xout, cudaStream_t s)
+{
+    if (nrows <= 0) return AMGB_OK;
+    const dim3 g((unsigned)csr_grid(nrows, lanes)), t(kCsrThreads);
+    switch (lanes) {
+    case 1: kaczmarz_kernel<1, NR><<<g, t, 0, s>>>(nrows, rows, M.Ap, M.Aj, M.Ax, v, b, Dinv, omega, xout); break;
+    case 2: kaczmarz_kernel<2, NR><<<g, t, 0, s>>>(nrows, rows, M.Ap, M.Aj, M.Ax, v, b, Dinv, omega, xout); break;
+    case 4: kaczmarz_kernel<4, NR><<<g, t, 0, s>>>(nrows, rows, M.Ap, M.Aj, M.Ax, v, b, Dinv, omega, xout); break;
+    case 8: kaczmarz_kernel<8, NR><<<g, t, 0, s>>>(nrows, rows, M.Ap, M.Aj, M.Ax, v, b, Dinv, omega, xout); break;
+    case 16: kaczmarz_kernel<16, NR><<<g, t, 0, s>>>(nrows, rows, M.Ap, M.Aj, M.Ax, v, b, Dinv, omega, xout); break;
+    default: kaczmarz_kernel<32, NR><<<g, t, 0, s>>>(nrows, rows, M.Ap, M.Aj, M.Ax, v, b, Dinv, omega, xout); break;
+    }
+    CK(cudaGetLastError());
+    return AMGB_OK;
+}
+
+int amgb_hierarchy::normal_equations(Level &L, const Smoother &s)
+{
+    if (recording) return fail(AMGB_ESTATE, "normal-equation smoother inside the cluster tail");
+    const long long n = L.A.n_rows;
+    if (s.kind == AMGB_SM_JACOBI_NE) {                                   // relaxation.py:806-812
+        double *temp = (L.x == L.x_home) ? L.xalt : L.x_home;
+        const long long grid = std::min<long long>((n + 255) / 256, (long long)g_num_sms * 16);
+        for (int it = 0; it < s.iterations; it++) {
+            RET(spmv(OP_RESID, s.ne_A, L.x, L.b, L.r));                  // b - A x
+            mul_kernel<<<(unsigned)grid, 256, 0, stream>>>(L.r, s.Dinv, n);      // delta = (b - A x) * Dinv
+            CK(cudaGetLastError());
+            launches++;
+            RET(spmv(OP_SPMV, s.ne_At, L.r, nullptr, temp));             // temp = (omega A^H) delta   (relaxation.h:592-600)
+            RET(axpby(1.0, temp, 1.0, L.x, n));                          // x += temp                  (:602-603)
+        }
+        return AMGB_OK;
+    }
+    const bool nr = s.kind == AMGB_SM_GAUSS_SEIDEL_NR;
+    const DevCsr &M = nr ? s.ne_At : s.ne_A;
+    const long long nw = (long long)s.ws.ptr.size() - 1;
+    auto sweep = [&](bool forward) -> int {
+        for (long long q = 0; q < nw; q++) {
+            const long long w = forward ? q : nw - 1 - q;
+            const int nrow = (int)(s.ws.ptr[(size_t)w + 1] - s.ws.ptr[(size_t)w]);
+            launches++;
+            if (nr) RET(launch_kaczmarz<true>(M.lanes, nrow, s.ws.rows + s.ws.ptr[(size_t)w], M, L.r, nullptr, s.Dinv, s.omega, L.x, stream));
+            else RET(launch_kaczmarz<false>(M.lanes, nrow, s.ws.rows + s.ws.ptr[(size_t)w], M, L.x, L.b, s.Dinv, s.omega, nullptr, stream));
+        }
+        return AMGB_OK;
+    };
+    auto residual = [&]() -> int { return nr ? spmv(OP_RESID, s.ne_A, L.x, L.b, L.r) : AMGB_OK; };   // relaxation.py:992
+    if (s.sweep == AMGB_SWEEP_SYMMETRIC) {                               // :883-889 / :971-977: fwd call, then bwd call
+        for (int it = 0; it < s.iterations; it++) {
+            RET(residual()); RET(sweep(true));
+            RET(residual()); RET(sweep(false));
+        }
+        return AMGB_OK;
+    }
+    RET(residual());                                                     // once per call, kept up to date by the sweeps
+    for (int it = 0; it < s.iterations; it++) RET(sweep(s.sweep == AMGB_SWEEP_FORWARD));
+    return AMGB_OK;
+}
+
 int amgb_hierarchy::block_gauss_seidel(Level &L, const Smoother &s)
 {
     if (recording) return fail(AMGB_ESTATE, "block Gauss-Seidel inside the cluster tail");
@@ -1716,6 +1846,22 @@ int amgb_hierarchy::make_smoother(const SmootherSpec &sp, const HostCsr &Aperm, 
         RET(upload(&s.rows2, l2.data(), (long long)l2.size()));
         s.n_rows1 = (long long)l1.size();
         s.n_rows2 = (long long)l2.size();
+    } else if (sp.kind == AMGB_SM_JACOBI_NE || sp.kind == AMGB_SM_GAUSS_SEIDEL_NE || sp.kind == AMGB_SM_GAUSS_SEIDEL_NR) {
+        if (pos) return fail(AMGB_ESTATE, "normal-equation smoother on a permuted level");
+        RET(upload(&s.Dinv, sp.Dinv.data(), (long long)sp.Dinv.size(), 2));
+        HostCsr As = Aperm, At;
+        sort_rows_by_column(As);
+        transpose_csr(As, At);
+        if (sp.kind == AMGB_SM_JACOBI_NE)
+            for (double &v : At.Ax) v = sp.omega * v;                    // omega2 * conjugate(Ax[j])   (relaxation.h:598)
+        if (sp.kind != AMGB_SM_GAUSS_SEIDEL_NE || true) RET(upload_csr(As, s.ne_A));
+        if (sp.kind != AMGB_SM_GAUSS_SEIDEL_NE) RET(upload_csr(At, s.ne_At));
+        if (sp.kind != AMGB_SM_JACOBI_NE) {
+            std::vector<int> rows;
+            if (!build_conflict_waves(sp.kind == AMGB_SM_GAUSS_SEIDEL_NR ? At : As, rows, s.ws.ptr))
+                return fail(AMGB_ENOTIMPL, "gauss_seidel_ne / _nr: duplicate column entries inside a row");
+            RET(upload(&s.ws.rows, rows.data(), (long long)rows.size()));
+        }
     } else if (sp.kind == AMGB_SM_CF_BLOCK_JACOBI || sp.kind == AMGB_SM_FC_BLOCK_JACOBI) {
         if (pos) return fail(AMGB_ESTATE, "block CF Jacobi on a permuted level");
         s.f_iterations = sp.f_iterations;
@@ -1963,6 +2109,14 @@ static int copy_smoother(const amgb_smoother *in, const HostCsr &A, SmootherSpec
             return fail(AMGB_ENOTIMPL, "block_gauss_seidel: blocksize must be 1..8 and divide n");
         if (in->Dinv == nullptr) return fail(AMGB_EINVAL, "block_gauss_seidel: Dinv required");
         s.Dinv.assign(in->Dinv, in->Dinv + (size_t)A.n_rows * s.bs);
+        return AMGB_OK;
+    case AMGB_SM_JACOBI_NE:
+    case AMGB_SM_GAUSS_SEIDEL_NE:
+    case AMGB_SM_GAUSS_SEIDEL_NR:
+        if (s.sweep < 0 || s.sweep > 2)
+            return fail(AMGB_EINVAL, "valid sweep directions: \"forward\", \"backward\", and \"symmetric\"");
+        if (in->Dinv == nullptr) return fail(AMGB_EINVAL, "normal-equation smoother: Dinv (n-vector) required");
+        s.Dinv.assign(in->Dinv, in->Dinv + (size_t)A.n_rows);
         return AMGB_OK;
     case AMGB_SM_CF_BLOCK_JACOBI:
     case AMGB_SM_FC_BLOCK_JACOBI: {

@@ -44,7 +44,11 @@ def _put_smoother(out, key, sm):
         return None
     func = getattr(sm, "func", None)
     if func is None:
-        from .relaxation.smoothing import polynomial_closure_parameters
+        from .relaxation.smoothing import polynomial_closure_parameters, normal_equation_closure_parameters
+        ne = normal_equation_closure_parameters(sm)       # 'jacobi_ne' / 'gauss_seidel_ne' / 'gauss_seidel_nr' closures
+        if ne is not None:
+            kw = {k: (int(v) if k == "iterations" else (v if isinstance(v, str) else float(np.real(v)))) for k, v in ne[1].items()}
+            return {"fn": ne[0], "name": ne[0], "kw": kw, "closure": "ne"}
         poly = polynomial_closure_parameters(sm)          # 'richardson' / 'chebyshev' closures
         if poly is None:
             raise NotImplementedError(f"cannot serialise closure smoother {sm!r}")
@@ -64,7 +68,10 @@ def _put_smoother(out, key, sm):
     return {"fn": func.__name__, "name": getattr(sm, "__name__", func.__name__), "kw": kw}
 
 
-def _get_smoother(z, key, d):
+def _get_smoother(z, key, d, lvl=None):
+    if d is not None and d.get("closure") == "ne":
+        from .relaxation.smoothing import _ne_closure
+        return _ne_closure(d["name"], lvl, **d["kw"])
     if d is None:
         def none(A, x, b):
             pass
@@ -120,8 +127,8 @@ def load_hierarchy(path, device=0, stream=None):
         if "P" in m:
             lvl.P = _get_matrix(z, f"L{k}_P", m["P"])
             lvl.R = _get_matrix(z, f"L{k}_R", m["R"])
-            lvl.presmoother = _get_smoother(z, f"L{k}_pre", m["pre"])
-            lvl.postsmoother = _get_smoother(z, f"L{k}_post", m["post"])
+            lvl.presmoother = _get_smoother(z, f"L{k}_pre", m["pre"], lvl)
+            lvl.postsmoother = _get_smoother(z, f"L{k}_post", m["post"], lvl)
         levels.append(lvl)
     ml = MultilevelSolver(levels, coarse_solver=ast.literal_eval(meta["coarse_solver"]),
                           device=device, stream=stream)

@@ -18,7 +18,7 @@ from .. import _engine as E
 
 __all__ = ["make_system", "jacobi", "gauss_seidel", "gauss_seidel_indexed", "block_jacobi", "sor",
            "polynomial", "jacobi_indexed", "cf_jacobi", "fc_jacobi", "block_gauss_seidel", "cf_block_jacobi",
-           "fc_block_jacobi"]
+           "fc_block_jacobi", "jacobi_ne", "gauss_seidel_ne", "gauss_seidel_nr"]
 
 
 def make_system(A, x, b, formats=None):
@@ -379,3 +379,41 @@ def fc_block_jacobi(A, x, b, Cpts, Fpts, Dinv=None, blocksize=1, iterations=1, f
                     omega=1.0):
     """FC block Jacobi (relaxation.py:1342-1412): F block rows first, then C."""
     _cf_block(E.SM_FC_BLOCK_JACOBI, A, x, b, Cpts, Fpts, Dinv, blocksize, iterations, f_iterations, c_iterations, omega)
+
+
+def _normal_equations(kind, norm_eq, A, x, b, iterations, sweep, omega, Dinv):
+    if not isinstance(x, np.ndarray):
+        raise ValueError("expected numpy array for argument x")
+    A, x, b = make_system(sparse.csr_array(A) if not (sparse.issparse(A) and A.format in ("csr", "bsr")) else A, x, b,
+                          formats=["csr"])
+    _fp64(A)
+    if sweep not in E.SWEEPS:
+        raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+    if A.shape[0] == 0 or iterations < 1:
+        return
+    if Dinv is None:
+        from ..util import get_diagonal
+        Dinv = get_diagonal(A, norm_eq=norm_eq, inv=True)
+    Dinv = np.ascontiguousarray(np.ravel(Dinv), dtype=np.float64)
+    S = _descriptor()
+    S.kind, S.iterations, S.omega, S.sweep = kind, int(iterations), float(np.real(omega)), E.SWEEPS[sweep]
+    S.Dinv = E.f64p(Dinv)
+    _relax(A, x, b, S, [Dinv])
+
+
+def jacobi_ne(A, x, b, iterations=1, omega=1.0):
+    """Jacobi on A A^H y = b, x = A^H y (relaxation.py:734-812 -> relaxation.h:579-606):
+    x += omega A^H (diag(A A^H)^-1 (b - A x))."""
+    _normal_equations(E.SM_JACOBI_NE, 2, A, x, b, iterations, "forward", omega, None)
+
+
+def gauss_seidel_ne(A, x, b, iterations=1, sweep="forward", omega=1.0, Dinv=None):
+    """Gauss-Seidel on A A^H y = b (Kaczmarz row projections; relaxation.py:815-901 -> relaxation.h:633-657).  The
+    sequential sweep runs as dependency waves of the rows' column-conflict graph, which reproduces it."""
+    _normal_equations(E.SM_GAUSS_SEIDEL_NE, 2, A, x, b, iterations, sweep, omega, Dinv)
+
+
+def gauss_seidel_nr(A, x, b, iterations=1, sweep="forward", omega=1.0, Dinv=None):
+    """Gauss-Seidel on A^H A x = A^H b (column projections on the residual; relaxation.py:904-999 ->
+    relaxation.h:684-713)."""
+    _normal_equations(E.SM_GAUSS_SEIDEL_NR, 1, A, x, b, iterations, sweep, omega, Dinv)

@@ -258,6 +258,52 @@ def setup_block_gauss_seidel(lvl, iterations=DEFAULT_NITER, sweep=DEFAULT_SWEEP,
     return smoother
 
 
+def _ne_closure(name, lvl, **params):
+    """The closure shape the reference stores for the normal-equation smoothers (smoothing.py:641-675): a plain function
+    named after the registry key; cell variables hold the level and the scalar parameters."""
+    fn = getattr(relaxation, name)
+
+    def smoother(A, x, b):
+        fn(lvl.A, x, b, **params)
+    smoother.__name__ = name
+    smoother.__qualname__ = name
+    smoother._ne_parameters = dict(params)
+    return smoother
+
+
+def setup_jacobi_ne(lvl, iterations=DEFAULT_NITER, omega=1.0, withrho=True):
+    """Jacobi on the normal equations A A^H y = b (smoothing.py:641-651)."""
+    if withrho:
+        omega = omega / rho_D_inv_A(lvl.A) ** 2
+    return _ne_closure("jacobi_ne", lvl, iterations=iterations, omega=omega)
+
+
+def setup_gauss_seidel_ne(lvl, iterations=DEFAULT_NITER, sweep=DEFAULT_SWEEP, omega=1.0):
+    """Gauss-Seidel on A A^H y = b (Kaczmarz; smoothing.py:654-663)."""
+    return _ne_closure("gauss_seidel_ne", lvl, iterations=iterations, sweep=sweep, omega=omega)
+
+
+def setup_gauss_seidel_nr(lvl, iterations=DEFAULT_NITER, sweep=DEFAULT_SWEEP, omega=1.0):
+    """Gauss-Seidel on A^H A x = A^H b (smoothing.py:666-675)."""
+    return _ne_closure("gauss_seidel_nr", lvl, iterations=iterations, sweep=sweep, omega=omega)
+
+
+def normal_equation_closure_parameters(sm):
+    """(name, {iterations, sweep, omega}) of a jacobi_ne / gauss_seidel_ne / gauss_seidel_nr smoother closure -- the
+    reference's (parameters in cell variables, smoothing.py:641-675) or the ones built above -- else None."""
+    name = getattr(sm, "__name__", None)
+    if name not in ("jacobi_ne", "gauss_seidel_ne", "gauss_seidel_nr"):
+        return None
+    own = getattr(sm, "_ne_parameters", None)
+    if own is not None:
+        return name, dict(own)
+    code, cells = getattr(sm, "__code__", None), getattr(sm, "__closure__", None)
+    if code is None or cells is None:
+        return None
+    cv = {k: c.cell_contents for k, c in zip(code.co_freevars, cells)}
+    return name, {k: cv[k] for k in ("iterations", "sweep", "omega") if k in cv}
+
+
 def setup_none(lvl):
     def none(A, x, b):
         pass
@@ -278,12 +324,14 @@ _REGISTER = {
     "cf_block_jacobi": setup_cf_block_jacobi,
     "fc_block_jacobi": setup_fc_block_jacobi,
     "block_gauss_seidel": setup_block_gauss_seidel,
+    "jacobi_ne": setup_jacobi_ne,
+    "gauss_seidel_ne": setup_gauss_seidel_ne,
+    "gauss_seidel_nr": setup_gauss_seidel_nr,
     "none": setup_none,
 }
 
 # in the reference's registry (smoothing.py:840-878) but outside the accelerated path
-_OUT_OF_SCOPE = ["schwarz", "strength_based_schwarz", "jacobi_ne", "gauss_seidel_ne", "gauss_seidel_nr",
-                 "gmres", "cg", "cgne", "cgnr"]
+_OUT_OF_SCOPE = ["schwarz", "strength_based_schwarz", "gmres", "cg", "cgne", "cgnr"]
 
 
 def _setup_call(fn):
@@ -379,6 +427,23 @@ def describe(sm, A, keep):
             keep.append(coef)
             S.kind, S.iterations = E.SM_POLYNOMIAL, int(poly[1])
             S.coefficients, S.n_coefficients = E.f64p(coef), coef.size
+            return S
+        ne = normal_equation_closure_parameters(sm)
+        if ne is not None:
+            name, kw = ne
+            if getattr(A, "format", "csr") == "bsr" and A.blocksize != (1, 1):
+                raise NotImplementedError("normal-equation smoothers on a block operator are not on the GPU hot path")
+            S.kind = {"jacobi_ne": E.SM_JACOBI_NE, "gauss_seidel_ne": E.SM_GAUSS_SEIDEL_NE,
+                      "gauss_seidel_nr": E.SM_GAUSS_SEIDEL_NR}[name]
+            S.iterations = int(kw.get("iterations", 1))
+            S.omega = float(np.real(kw.get("omega", 1.0)))
+            sweep = kw.get("sweep", "forward")
+            if sweep not in E.SWEEPS:
+                raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+            S.sweep = E.SWEEPS[sweep]
+            Dinv = np.ascontiguousarray(get_diagonal(A, norm_eq=1 if name == "gauss_seidel_nr" else 2, inv=True))
+            keep.append(Dinv)
+            S.Dinv = E.f64p(Dinv)
             return S
         raise NotImplementedError(
             f"smoother {getattr(sm, '__name__', sm)!r} is a closure the GPU engine cannot introspect; "

@@ -12,9 +12,17 @@ import numpy as np
 from scipy import sparse
 
 
-def get_diagonal(A, inv=False):
-    """diag(A) (or its entry-wise inverse with 0 where the diagonal is 0)."""
-    D = np.asarray(sparse.csr_array(A).diagonal(), dtype=np.float64)
+def get_diagonal(A, norm_eq=False, inv=False):
+    """diag(A), diag(A^H A) (``norm_eq=1``) or diag(A A^H) (``norm_eq=2``), or its entry-wise inverse with 0 where
+    the diagonal is 0 (pyamg/util/utils.py:530-600; the sums run over column-sorted rows, as there)."""
+    if norm_eq in (1, 2):
+        M = sparse.csr_array(A).copy()
+        M.sort_indices()
+        if norm_eq == 1:
+            M = M.T
+        D = np.asarray((M.multiply(M.conjugate())) @ np.ones((M.shape[0],)), dtype=np.float64)
+    else:
+        D = np.asarray(sparse.csr_array(A).diagonal(), dtype=np.float64)
     if inv:
         Dinv = np.zeros_like(D)
         mask = D != 0.0

@@ -246,6 +246,23 @@ def main_widening():
                                            postsmoother=("sor", {"omega": 1.2, "sweep": "backward", "iterations": 2}))
     emit("cfg12_sa_sor_poisson2d", ml)
 
+    # cfg13: normal-equation smoothers (closures; parameters in cell variables): Gauss-Seidel NR pre, Gauss-Seidel NE
+    # post on a nonsymmetric operator (upwind advection + diffusion)
+    np.random.seed(SEED)
+    Adv = advection_2d((22, 22), theta=np.pi / 7.0)[0]
+    m = int(round(np.sqrt(Adv.shape[0])))
+    A = (Adv + 0.3 * poisson((m, m))).tocsr()
+    ml = pyamg.ruge_stuben_solver(A, presmoother=("gauss_seidel_nr", {"sweep": "symmetric"}),
+                                  postsmoother=("gauss_seidel_ne", {"sweep": "backward", "omega": 0.9, "iterations": 2}))
+    emit("cfg13_rs_gsnr_gsne_advdiff2d", ml, cg_anyway=False)
+
+    # cfg14: Jacobi NE (omega / rho(D^-1 A)^2 computed by the reference, read back from the closure) on SA
+    np.random.seed(SEED)
+    A = poisson((26, 26), format="csr")
+    ml = pyamg.smoothed_aggregation_solver(A, presmoother=("jacobi_ne", {"omega": 4.0 / 3.0}),
+                                           postsmoother=("jacobi_ne", {"omega": 4.0 / 3.0, "iterations": 2}))
+    emit("cfg14_sa_jacobine_poisson2d", ml)
+
     # cfg10: linear elasticity with the reference's DEFAULT SA smoothers (symmetric block Gauss-Seidel)
     np.random.seed(SEED)
     A, B = linear_elasticity((12, 12))

@@ -308,7 +308,7 @@ def test_widened_smoother_descriptors_are_parsed(load_golden):
     with pytest.raises(NotImplementedError):
         smoothing._setup_call("schwarz")
     with pytest.raises(NotImplementedError):
-        smoothing._setup_call("gauss_seidel_ne")
+        smoothing._setup_call("cgne")
 
 
 def test_chebyshev_coefficients_reference_doctest():
@@ -336,3 +336,22 @@ def test_coarse_solver_spec_roundtrip(load_golden, tmp_path):
     assert S.kind == E.SM_GAUSS_SEIDEL and S.iterations == 4 and S.sweep == E.SWEEPS["symmetric"]
     assert pyamg_b200.coarse_grid_solver("jacobi").relaxation == ("jacobi", {"iterations": 10})   # default: 10 sweeps
     assert coarse_solver_spec(pyamg_b200.coarse_grid_solver("pinv")) == "pinv"
+
+
+def test_normal_equation_closures_are_parsed(load_golden):
+    """The reference keeps jacobi_ne / gauss_seidel_ne / gauss_seidel_nr parameters in closure cells
+    (smoothing.py:641-675): they survive adoption, save / load and reach the engine descriptor with Dinv = the inverse
+    diagonal of A A^H (NE) or A^H A (NR)."""
+    from pyamg_b200.util import get_diagonal
+    ml, _ = load_golden("cfg13_rs_gsnr_gsne_advdiff2d")
+    lvl = ml.levels[0]
+    keep = []
+    S = smoothing.describe(lvl.presmoother, lvl.A, keep)
+    assert S.kind == E.SM_GAUSS_SEIDEL_NR and S.sweep == E.SWEEPS["symmetric"] and S.iterations == 1
+    assert np.allclose(np.ctypeslib.as_array(S.Dinv, shape=(lvl.A.shape[0],)), 1.0 / (lvl.A.multiply(lvl.A)).sum(axis=0))
+    S = smoothing.describe(lvl.postsmoother, lvl.A, keep)
+    assert S.kind == E.SM_GAUSS_SEIDEL_NE and S.iterations == 2 and S.omega == pytest.approx(0.9)
+    assert np.allclose(get_diagonal(lvl.A, norm_eq=2), np.asarray((lvl.A.multiply(lvl.A)).sum(axis=1)).ravel())
+    ml, _ = load_golden("cfg14_sa_jacobine_poisson2d")
+    S = smoothing.describe(ml.levels[0].postsmoother, ml.levels[0].A, keep)
+    assert S.kind == E.SM_JACOBI_NE and S.iterations == 2 and 0 < S.omega < 4.0 / 3.0

@@ -720,3 +720,41 @@ def test_block_cf_jacobi_in_a_cycle_and_through_hierarchy_io(tmp_path):
     ml2, _ = load_hierarchy(p)
     assert ml2.levels[0].postsmoother.__name__ == "fc_block_jacobi"
     assert relerr(ml2.solve(b, tol=0, maxiter=3), xo) < TOL
+
+
+# ------------------------------------------------------------------ normal-equation smoothers (Kaczmarz family)
+def test_normal_equation_smoothers_match_oracle_and_compiled_reference():
+    """relaxation.jacobi_ne / gauss_seidel_ne / gauss_seidel_nr (relaxation.py:734-999 -> relaxation.h:579-713): the
+    row / column projections run as conflict waves (rows of a wave share no column), which reproduces the sequential
+    sweep; forward, backward, symmetric, several iterations, omega != 1."""
+    rng = np.random.default_rng(0)
+    n = 60
+    A = sp.random(n, n, density=0.15, random_state=np.random.RandomState(1), format="csr")
+    A = sp.csr_array(A + sp.eye(n) * 3)
+    A.indptr, A.indices = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    x0, b = rng.standard_normal(n), rng.standard_normal(n)
+    kern = "ref" if oracle.have_ref() else "oracle"
+    for name, kw in (("jacobi_ne", dict(iterations=2, omega=0.3)),
+                     ("gauss_seidel_ne", dict(sweep="symmetric", iterations=2, omega=0.9)),
+                     ("gauss_seidel_ne", dict(sweep="backward")),
+                     ("gauss_seidel_nr", dict(sweep="forward", iterations=2, omega=1.1)),
+                     ("gauss_seidel_nr", dict(sweep="symmetric")),
+                     ("gauss_seidel_nr", dict(sweep="backward", iterations=3))):
+        xo, xg = x0.copy(), x0.copy()
+        getattr(oracle, name)(sp.csc_array(A) if name.endswith("nr") else A.copy(), xo, b, kernels=kern, **kw)
+        getattr(gpu_relax, name)(A.copy(), xg, b, **kw)
+        assert relerr(xg, xo) < TOL, (name, kw)
+    with pytest.raises(ValueError):
+        gpu_relax.gauss_seidel_ne(A, x0.copy(), b, sweep="diagonal")
+
+
+def test_normal_equation_smoothers_from_the_factory():
+    from pyamg_b200.classical import ruge_stuben_solver
+    from pyamg_b200.gallery import poisson
+    np.random.seed(11)
+    ml = ruge_stuben_solver(poisson((18, 18)), presmoother=("gauss_seidel_nr", {"sweep": "symmetric"}),
+                            postsmoother=("jacobi_ne", {"omega": 1.0, "iterations": 2}))
+    b = np.random.default_rng(12).random(ml.levels[0].A.shape[0])
+    cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A))
+    assert relerr(ml.solve(b, tol=0, maxiter=3), cyc.solve(b, tol=0, maxiter=3)) < TOL
+    assert ml.levels[0].presmoother.__name__ == "gauss_seidel_nr"

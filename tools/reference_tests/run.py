@@ -11,8 +11,8 @@ with two pytest plugins from this directory:
                           test_aggregation.py, test_air.py, test_rootnode.py -- setup on the reference, every fp64 solve
                           on the engine (the kernel emulator when no GPU is present: AMGB_TEST_EMU=1 is set by the plugins)
 Round-1 result on the emulator: test_relaxation.py 31 of 41 (the 10 others are float32 / complex / block-row
-jacobi_indexed cases, which fail loudly by design); solver tests 53 of 61 with 231 solves on the engine (the 8 others:
-Krylov coarse solvers, schwarz and gauss_seidel_nr smoothers -- NotImplementedError by design).
+jacobi_indexed cases, which fail loudly by design); solver tests 55 of 61 with 233 solves on the engine (the 6 others:
+Krylov coarse solvers and the schwarz smoother -- NotImplementedError by design).
 """
 import os
 import shutil
