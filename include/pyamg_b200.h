@@ -64,6 +64,10 @@ extern "C" {
                                        row projections in dependency waves of the A A^T conflict graph */
 #define AMGB_SM_GAUSS_SEIDEL_NR 13  /* relaxation.gauss_seidel_nr (relaxation.py:904-999 -> relaxation.h:684-713):
                                        column projections on the residual, waves of the A^T A conflict graph */
+#define AMGB_SM_SCHWARZ 14          /* relaxation.schwarz (relaxation.py:157-262 -> overlapping_schwarz_csr,
+                                       relaxation.h:818-880): multiplicative overlapping Schwarz.  indices = the
+                                       subdomains' row lists back to back, indices2 = their n_sub + 1 offsets, Dinv =
+                                       the (pseudo-)inverses of the subdomain blocks, row-major, back to back */
 
 #define AMGB_SWEEP_FORWARD 0
 #define AMGB_SWEEP_BACKWARD 1

@@ -390,6 +390,69 @@ def gauss_seidel_nr(A, x, b, iterations=1, sweep="forward", omega=1.0, Dinv=None
                                          ctypes.c_double(float(omega)))
 
 
+def schwarz_parameters(A, subdomain=None, subdomain_ptr=None, inv_subblock=None, inv_subblock_ptr=None):
+    """pyamg/relaxation/relaxation.py:1002-1078: default subdomains = the rows' sparsity patterns; every subdomain
+    block A[sub][:, sub] (amg_core.extract_subblocks, relaxation.h:905-960) is pseudo-inverted with LAPACK gelss."""
+    from scipy.linalg import get_lapack_funcs
+    if hasattr(A, "schwarz_parameters"):
+        if subdomain is None or subdomain_ptr is None or (np.array_equal(A.schwarz_parameters[0], subdomain)
+                                                          and np.array_equal(A.schwarz_parameters[1], subdomain_ptr)):
+            return A.schwarz_parameters
+    if subdomain is None or subdomain_ptr is None:
+        subdomain_ptr = A.indptr.copy()
+        subdomain = A.indices.copy()
+    if inv_subblock is None or inv_subblock_ptr is None:
+        inv_subblock_ptr = np.zeros(subdomain_ptr.shape, dtype=A.indices.dtype)
+        blocksize = subdomain_ptr[1:] - subdomain_ptr[:-1]
+        inv_subblock_ptr[1:] = np.cumsum(blocksize * blocksize)
+        inv_subblock = np.zeros((inv_subblock_ptr[-1],), dtype=A.dtype)
+        cond = 1e6 * np.finfo(np.double).eps                # util/params.py set_tol('d')
+        gelss, = get_lapack_funcs(["gelss"], (np.ones((1,), dtype=A.dtype),))
+        Acsr = sparse.csr_array(A)
+        for i in range(subdomain_ptr.shape[0] - 1):
+            m = blocksize[i]
+            sub = subdomain[subdomain_ptr[i]:subdomain_ptr[i + 1]]
+            block = np.array(Acsr[sub][:, sub].toarray(), order="C")
+            out = gelss(block, np.eye(m, m, dtype=A.dtype), cond=cond, overwrite_a=True, overwrite_b=True)
+            inv_subblock[inv_subblock_ptr[i]:inv_subblock_ptr[i + 1]] = np.ravel(out[1])
+    A.schwarz_parameters = (subdomain, subdomain_ptr, inv_subblock, inv_subblock_ptr)
+    return A.schwarz_parameters
+
+
+def schwarz(A, x, b, iterations=1, subdomain=None, subdomain_ptr=None, inv_subblock=None, inv_subblock_ptr=None,
+            sweep="forward", kernels="oracle"):
+    """pyamg/relaxation/relaxation.py:157-262 -> overlapping_schwarz_csr (relaxation.h:818-880)."""
+    A, x, b = make_system(A, x, b, formats=["csr"])
+    _f64(A, x, b)
+    A.sort_indices()
+    subdomain, subdomain_ptr, inv_subblock, inv_subblock_ptr = schwarz_parameters(A, subdomain, subdomain_ptr,
+                                                                                  inv_subblock, inv_subblock_ptr)
+    nsub = subdomain_ptr.shape[0] - 1
+    if sweep == "forward":
+        rs = (0, nsub, 1)
+    elif sweep == "backward":
+        rs = (nsub - 1, -1, -1)
+    elif sweep == "symmetric":
+        for _ in range(iterations):
+            schwarz(A, x, b, 1, subdomain, subdomain_ptr, inv_subblock, inv_subblock_ptr, "forward", kernels)
+            schwarz(A, x, b, 1, subdomain, subdomain_ptr, inv_subblock, inv_subblock_ptr, "backward", kernels)
+        return
+    else:
+        raise ValueError("valid sweep directions: 'forward', 'backward', and 'symmetric'")
+    Sj = np.ascontiguousarray(subdomain, dtype=np.int32)
+    Sp = np.ascontiguousarray(subdomain_ptr, dtype=np.int32)
+    Tx = np.ascontiguousarray(inv_subblock, dtype=np.float64)
+    Tp = np.ascontiguousarray(inv_subblock_ptr, dtype=np.int32)
+    n = A.shape[0]
+    for _ in range(iterations):
+        if kernels == "ref":
+            lib("ref").ref_overlapping_schwarz_csr(_ip(A.indptr), n, _ip(A.indices), _dp(A.data), len(A.data), _dp(x), _dp(b),
+                                                   _dp(Tx), len(Tx), _ip(Tp), _ip(Sj), len(Sj), _ip(Sp), nsub, *rs)
+        else:
+            lib().oracle_overlapping_schwarz_csr(_ip(A.indptr), _ip(A.indices), _dp(A.data), _dp(x), _dp(b), _dp(Tx),
+                                                 _ip(Tp), _ip(Sj), _ip(Sp), n, *rs)
+
+
 def polynomial(A, x, b, coefficients, iterations=1, kernels="oracle"):
     """pyamg/relaxation/relaxation.py:585-659: x += p(A)(b - A x) by Horner's rule; the matvecs are the
     reference's SciPy calls restated (``matvec``)."""
@@ -486,6 +549,7 @@ _SMOOTHERS = {
     "jacobi_ne": jacobi_ne,
     "gauss_seidel_ne": gauss_seidel_ne,
     "gauss_seidel_nr": gauss_seidel_nr,
+    "schwarz": schwarz,
 }
 
 
@@ -514,6 +578,18 @@ def smoother_spec(sm):
         coef = cv["coefficients"] if "coefficients" in cv else [cv["omega"]]
         return ("polynomial", {"coefficients": np.asarray(coef, dtype=np.float64),
                                "iterations": int(cv.get("iterations", 1))})
+    if getattr(sm, "__name__", "") == "schwarz" and getattr(sm, "__closure__", None):
+        # smoothing.py:509-526: closure around relaxation.schwarz(lvl.Acsr, ...) with the subdomains and their block
+        # inverses (computed once at setup) in the cells
+        own = getattr(sm, "_schwarz_parameters", None)
+        cv = own if own is not None else {k: c.cell_contents for k, c in zip(sm.__code__.co_freevars, sm.__closure__)}
+        return ("schwarz", {k: cv[k] for k in ("iterations", "subdomain", "subdomain_ptr", "inv_subblock",
+                                               "inv_subblock_ptr", "sweep")})
+    if getattr(sm, "__name__", "") == "strength_based_schwarz" and getattr(sm, "__closure__", None):
+        # smoothing.py:529-548: subdomains = rows of the strength matrix in the cells; the block inverses are rebuilt
+        # from lvl.Acsr on every application (inv_subblock=None below does the same)
+        cv = {k: c.cell_contents for k, c in zip(sm.__code__.co_freevars, sm.__closure__)}
+        return ("schwarz", {k: cv[k] for k in ("iterations", "subdomain", "subdomain_ptr", "sweep")})
     if getattr(sm, "__name__", "") in ("jacobi_ne", "gauss_seidel_ne", "gauss_seidel_nr") and getattr(sm, "__closure__", None):
         # smoothing.py:641-675: closures around relaxation.<name>(lvl.Acsr | lvl.Acsc, x, b, ...); the operator they
         # relax with is the level's own A in another format, so only the scalar parameters are taken from the cells
@@ -551,7 +627,7 @@ def _smooth(spec, A, x, b, kernels):
     fn = _SMOOTHERS.get(name)
     if fn is None:
         raise NotImplementedError(f"oracle: smoother '{name}' out of hot-path scope")
-    if name in ("jacobi_ne", "gauss_seidel_ne"):
+    if name in ("jacobi_ne", "gauss_seidel_ne", "schwarz"):
         A = sparse.csr_array(A).copy()             # lvl.Acsr: a CSR view the reference sorts in place, not lvl.A
         A.indptr, A.indices = A.indptr.astype(np.int32), A.indices.astype(np.int32)
     elif name == "gauss_seidel_nr":

@@ -117,4 +117,13 @@ void ref_gauss_seidel_nr(const int *Ap, int n, const int *Aj, const double *Ax, 
                                          Dinv, n, omega);
 }
 
+// pyamg/amg_core/relaxation.h:818-880
+void ref_overlapping_schwarz_csr(const int *Ap, int n, const int *Aj, const double *Ax, int nnz, double *x,
+                                 const double *b, const double *Tx, int tx_size, const int *Tp, const int *Sj,
+                                 int sj_size, const int *Sp, int nsub, int row_start, int row_stop, int row_step)
+{
+    overlapping_schwarz_csr<int, double, double>(Ap, n + 1, Aj, nnz, Ax, nnz, x, n, b, n, Tx, tx_size, Tp, nsub + 1,
+                                                 Sj, sj_size, Sp, nsub + 1, nsub, n, row_start, row_stop, row_step);
+}
+
 }  // extern "C"

@@ -18,7 +18,7 @@ OK, EINVAL, ECUDA, ENOTIMPL, ESTATE = 0, -1, -2, -3, -4
 SM_NONE, SM_JACOBI, SM_GAUSS_SEIDEL, SM_BLOCK_JACOBI = 0, 1, 2, 3
 SM_POLYNOMIAL, SM_JACOBI_INDEXED, SM_CF_JACOBI, SM_FC_JACOBI, SM_BLOCK_GAUSS_SEIDEL = 4, 5, 6, 7, 8
 SM_CF_BLOCK_JACOBI, SM_FC_BLOCK_JACOBI = 9, 10
-SM_JACOBI_NE, SM_GAUSS_SEIDEL_NE, SM_GAUSS_SEIDEL_NR = 11, 12, 13
+SM_JACOBI_NE, SM_GAUSS_SEIDEL_NE, SM_GAUSS_SEIDEL_NR, SM_SCHWARZ = 11, 12, 13, 14
 SWEEPS = {"forward": 0, "backward": 1, "symmetric": 2}
 CYCLES = {"V": 0, "W": 1, "F": 2, "AMLI": 3}
 FLAG_X0_ZERO = 1

@@ -375,6 +375,53 @@ __global__ void __launch_bounds__(kCsrThreads) kaczmarz_kernel(int nrows, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// multiplicative overlapping Schwarz (relaxation.h:818-880): one warp per subdomain of the launch (subdomains of a
+// wave neither read nor write each other's entries).  Every lane forms whole local rows sequentially -- rsum_q =
+// (-sum a x) + b, then (T rsum)_q with T the block's stored (pseudo-)inverse -- in the reference's own order, so the
+// arithmetic is the sequential code's, bit for bit; all reads of x precede the updates (two warp barriers).
+// Shared memory: 2 * max_m doubles per warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSchwarzWarps = 4;
+__global__ void __launch_bounds__(kSchwarzWarps * 32) schwarz_kernel(int ndom, const int *__restrict__ doms,
+                                                                    const int *__restrict__ Sp, const int *__restrict__ Sj,
+                                                                    const long long *__restrict__ Tp,
+                                                                    const double *__restrict__ Tx,
+                                                                    const int *__restrict__ Ap, const int *__restrict__ Aj,
+                                                                    const double *__restrict__ Ax, double *x,
+                                                                    const double *__restrict__ b, int max_m)
+{
+    extern __shared__ __align__(16) unsigned char schwarz_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *rsum = reinterpret_cast<double *>(schwarz_smem) + (size_t)warp * 2 * max_m;
+    double *upd = rsum + max_m;
+    const int k = blockIdx.x * kSchwarzWarps + warp;
+    const bool active = k < ndom;             // whole warps are active or not: the warp barriers below stay converged
+    int s0 = 0, m = 0;
+    long long t0 = 0;
+    if (active) {
+        const int d = doms[k];
+        s0 = Sp[d];
+        m = Sp[d + 1] - s0;
+        t0 = Tp[d];
+    }
+    for (int q = lane; q < m; q += 32) {
+        const int row = Sj[s0 + q];
+        double r = 0.0;
+        for (int jj = Ap[row]; jj < Ap[row + 1]; jj++) r -= Ax[jj] * x[Aj[jj]];
+        rsum[q] = r + b[row];
+    }
+    __syncwarp();
+    for (int q = lane; q < m; q += 32) {
+        double u = 0.0;
+        const double *Trow = Tx + t0 + (long long)q * m;
+        for (int c = 0; c < m; c++) u += Trow[c] * rsum[c];
+        upd[q] = u;
+    }
+    __syncwarp();
+    for (int q = lane; q < m; q += 32) x[Sj[s0 + q]] += upd[q];
+}
+
 // Arnoldi pieces (amgb_arnoldi_run): everything between two host reads stays on the device
 __global__ void sqrt_scalar_kernel(double *p) { *p = sqrt(*p); }
 // y = x / *den   (next Krylov basis vector: w / ||w|| with the norm in a device scalar)

@@ -406,6 +406,10 @@ struct Smoother {
     // normal-equation smoothers: column-sorted copies of A (ne_A) and A^T (ne_At; omega-scaled for jacobi_ne),
     // inverse diagonal of A A^H or A^H A in Dinv, conflict waves of the sweep operator in ws (row lists)
     DevCsr ne_A, ne_At;
+    // Schwarz: subdomain row lists (sz_Sj / sz_Sp), block inverses (Dinv) with offsets sz_Tp, largest subdomain
+    int *sz_Sj = nullptr, *sz_Sp = nullptr;
+    long long *sz_Tp = nullptr;
+    int sz_max_m = 0;
     std::vector<double> coef;        // polynomial coefficients (host: they become kernel arguments)
     // EXPERIMENTAL resident-vector cluster sweep (AMGB_RESIDENT=1): device copies of the schedule
     long long *res_wave_ptr = nullptr;
@@ -922,6 +926,7 @@ struct amgb_hierarchy {
         case AMGB_SM_JACOBI_NE:
         case AMGB_SM_GAUSS_SEIDEL_NE:
         case AMGB_SM_GAUSS_SEIDEL_NR: return normal_equations(L, s);
+        case AMGB_SM_SCHWARZ: return schwarz(L, s);
         case AMGB_SM_CF_BLOCK_JACOBI:                                  // relaxation.py:1328-1339
         case AMGB_SM_FC_BLOCK_JACOBI:                                  // relaxation.py:1401-1412
             for (int it = 0; it < s.iterations; it++) {
@@ -1029,6 +1034,7 @@ struct amgb_hierarchy {
         return AMGB_OK;
     }
     int normal_equations(Level &L, const Smoother &s);     // jacobi_ne / gauss_seidel_ne / gauss_seidel_nr
+    int schwarz(Level &L, const Smoother &s);
     int block_gauss_seidel(Level &L, const Smoother &s);   // defined below (needs its kernel)
     int block_jacobi_indexed(Level &L, const Smoother &s, const int *brows, long long m);
 
@@ -1765,6 +1771,66 @@ int amgb_hierarchy::normal_equations(Level &L, const Smoother &s)
     return AMGB_OK;
 }
 
+// multiplicative Schwarz: subdomain k reads x on the columns of its rows and writes x on its rows; it goes to wave
+// 1 + (latest wave that wrote anything it reads, or read / wrote anything it writes)
+static void build_schwarz_waves(const HostCsr &A, const std::vector<int> &Sj, const std::vector<int> &Sp,
+                                std::vector<int> &doms_sorted, std::vector<long long> &ptr)
+{
+    const int nd = (int)Sp.size() - 1;
+    std::vector<int> wwave((size_t)A.n_rows, 0), rwave((size_t)A.n_rows, 0), w((size_t)std::max(nd, 1));
+    int maxw = 0;
+    for (int k = 0; k < nd; k++) {
+        int wv = 0;
+        for (int q = Sp[(size_t)k]; q < Sp[(size_t)k + 1]; q++) {
+            const int row = Sj[(size_t)q];
+            wv = std::max(wv, std::max(rwave[(size_t)row], wwave[(size_t)row]));
+            for (int jj = A.Ap[(size_t)row]; jj < A.Ap[(size_t)row + 1]; jj++) wv = std::max(wv, wwave[(size_t)A.Aj[(size_t)jj]]);
+        }
+        wv += 1;
+        w[(size_t)k] = wv;
+        for (int q = Sp[(size_t)k]; q < Sp[(size_t)k + 1]; q++) {
+            const int row = Sj[(size_t)q];
+            wwave[(size_t)row] = wv;
+            for (int jj = A.Ap[(size_t)row]; jj < A.Ap[(size_t)row + 1]; jj++) {
+                int &rw = rwave[(size_t)A.Aj[(size_t)jj]];
+                rw = std::max(rw, wv);
+            }
+        }
+        maxw = std::max(maxw, wv);
+    }
+    ptr.assign((size_t)maxw + 1, 0);
+    for (int k = 0; k < nd; k++) ptr[(size_t)w[(size_t)k]]++;
+    for (int q = 0; q < maxw; q++) ptr[(size_t)q + 1] += ptr[(size_t)q];
+    doms_sorted.resize((size_t)nd);
+    std::vector<long long> cur(ptr.begin(), ptr.end() - 1);
+    for (int k = 0; k < nd; k++) doms_sorted[(size_t)cur[(size_t)w[(size_t)k] - 1]++] = k;
+}
+
+int amgb_hierarchy::schwarz(Level &L, const Smoother &s)
+{
+    if (recording) return fail(AMGB_ESTATE, "Schwarz smoother inside the cluster tail");
+    const long long nw = (long long)s.ws.ptr.size() - 1;
+    const size_t smem = (size_t)kSchwarzWarps * 2 * (size_t)std::max(s.sz_max_m, 1) * sizeof(double);
+    auto sweep = [&](bool forward) -> int {
+        for (long long q = 0; q < nw; q++) {
+            const long long w = forward ? q : nw - 1 - q;
+            const int nd = (int)(s.ws.ptr[(size_t)w + 1] - s.ws.ptr[(size_t)w]);
+            if (nd <= 0) continue;
+            schwarz_kernel<<<(unsigned)((nd + kSchwarzWarps - 1) / kSchwarzWarps), kSchwarzWarps * 32, smem, stream>>>(
+                nd, s.ws.rows + s.ws.ptr[(size_t)w], s.sz_Sp, s.sz_Sj, s.sz_Tp, s.Dinv, s.ne_A.Ap, s.ne_A.Aj, s.ne_A.Ax, L.x, L.b,
+                std::max(s.sz_max_m, 1));
+            CK(cudaGetLastError());
+            launches++;
+        }
+        return AMGB_OK;
+    };
+    for (int it = 0; it < s.iterations; it++) {                            // relaxation.py:241-262
+        if (s.sweep == AMGB_SWEEP_FORWARD || s.sweep == AMGB_SWEEP_SYMMETRIC) RET(sweep(true));
+        if (s.sweep == AMGB_SWEEP_BACKWARD || s.sweep == AMGB_SWEEP_SYMMETRIC) RET(sweep(false));
+    }
+    return AMGB_OK;
+}
+
 int amgb_hierarchy::block_gauss_seidel(Level &L, const Smoother &s)
 {
     if (recording) return fail(AMGB_ESTATE, "block Gauss-Seidel inside the cluster tail");
@@ -1862,6 +1928,32 @@ int amgb_hierarchy::make_smoother(const SmootherSpec &sp, const HostCsr &Aperm, 
                 return fail(AMGB_ENOTIMPL, "gauss_seidel_ne / _nr: duplicate column entries inside a row");
             RET(upload(&s.ws.rows, rows.data(), (long long)rows.size()));
         }
+    } else if (sp.kind == AMGB_SM_SCHWARZ) {
+        if (pos) return fail(AMGB_ESTATE, "Schwarz smoother on a permuted level");
+        HostCsr As = Aperm;
+        sort_rows_by_column(As);                                  // relaxation.py:228 (A.sort_indices())
+        RET(upload_csr(As, s.ne_A));
+        const std::vector<int> &Sj = sp.list, &Sp = sp.list2;
+        const int nd = (int)Sp.size() - 1;
+        std::vector<long long> Tp((size_t)nd + 1, 0);
+        int max_m = 0;
+        for (int k = 0; k < nd; k++) {
+            const long long m = Sp[(size_t)k + 1] - Sp[(size_t)k];
+            Tp[(size_t)k + 1] = Tp[(size_t)k] + m * m;
+            max_m = std::max<int>(max_m, (int)m);
+        }
+        if ((long long)sp.Dinv.size() != Tp[(size_t)nd]) return fail(AMGB_EINVAL, "schwarz: inv_subblock size != sum of subdomain sizes squared");
+        if ((size_t)kSchwarzWarps * 2 * (size_t)max_m * sizeof(double) > 200 * 1024) return fail(AMGB_ENOTIMPL, "schwarz: subdomain too large");
+        s.sz_max_m = max_m;
+        RET(upload(&s.sz_Sj, Sj.data(), (long long)Sj.size()));
+        RET(upload(&s.sz_Sp, Sp.data(), (long long)Sp.size()));
+        RET(upload(&s.sz_Tp, Tp.data(), (long long)Tp.size()));
+        RET(upload(&s.Dinv, sp.Dinv.data(), (long long)sp.Dinv.size()));
+        std::vector<int> doms;
+        build_schwarz_waves(As, Sj, Sp, doms, s.ws.ptr);
+        RET(upload(&s.ws.rows, doms.data(), (long long)doms.size()));
+        const size_t smem = (size_t)kSchwarzWarps * 2 * (size_t)std::max(max_m, 1) * sizeof(double);
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(schwarz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else if (sp.kind == AMGB_SM_CF_BLOCK_JACOBI || sp.kind == AMGB_SM_FC_BLOCK_JACOBI) {
         if (pos) return fail(AMGB_ESTATE, "block CF Jacobi on a permuted level");
         s.f_iterations = sp.f_iterations;
@@ -2118,6 +2210,34 @@ static int copy_smoother(const amgb_smoother *in, const HostCsr &A, SmootherSpec
         if (in->Dinv == nullptr) return fail(AMGB_EINVAL, "normal-equation smoother: Dinv (n-vector) required");
         s.Dinv.assign(in->Dinv, in->Dinv + (size_t)A.n_rows);
         return AMGB_OK;
+    case AMGB_SM_SCHWARZ: {
+        if (s.sweep < 0 || s.sweep > 2)
+            return fail(AMGB_EINVAL, "valid sweep directions: 'forward', 'backward', and 'symmetric'");
+        if (in->indices2 == nullptr || in->n_indices2 < 1 || (in->n_indices > 0 && in->indices == nullptr))
+            return fail(AMGB_EINVAL, "schwarz: subdomain / subdomain_ptr required");
+        s.list.assign(in->indices, in->indices + in->n_indices);
+        s.list2.assign(in->indices2, in->indices2 + in->n_indices2);
+        if (s.list2.front() != 0 || s.list2.back() != (int)s.list.size()) return fail(AMGB_EINVAL, "schwarz: subdomain_ptr inconsistent");
+        long long tsize = 0;
+        for (size_t k = 0; k + 1 < s.list2.size(); k++) {
+            const long long m = s.list2[k + 1] - s.list2[k];
+            if (m < 0) return fail(AMGB_EINVAL, "schwarz: subdomain_ptr not monotone");
+            tsize += m * m;
+        }
+        for (int v : s.list)
+            if (v < 0 || v >= A.n_rows) return fail(AMGB_EINVAL, "schwarz: row index out of range");
+        {   // a row listed twice in ONE subdomain would be updated by two lanes at once
+            std::vector<int> seen((size_t)A.n_rows, -1);
+            for (size_t k = 0; k + 1 < s.list2.size(); k++)
+                for (int q = s.list2[k]; q < s.list2[k + 1]; q++) {
+                    if (seen[(size_t)s.list[(size_t)q]] == (int)k) return fail(AMGB_ENOTIMPL, "schwarz: a subdomain lists a row twice");
+                    seen[(size_t)s.list[(size_t)q]] = (int)k;
+                }
+        }
+        if (in->Dinv == nullptr && tsize > 0) return fail(AMGB_EINVAL, "schwarz: inv_subblock required");
+        s.Dinv.assign(in->Dinv, in->Dinv + tsize);
+        return AMGB_OK;
+    }
     case AMGB_SM_CF_BLOCK_JACOBI:
     case AMGB_SM_FC_BLOCK_JACOBI: {
         s.bs = in->blocksize;

@@ -20,6 +20,7 @@ from .relaxation import relaxation
 
 _ARRAY_KW = ("indices", "Dinv", "Cpts", "Fpts", "coefficients")
 _INT_KW = ("iterations", "blocksize", "f_iterations", "c_iterations")
+_SCHWARZ_ARRAYS = ("subdomain", "subdomain_ptr", "inv_subblock", "inv_subblock_ptr")
 
 
 def _put_matrix(out, key, M):
@@ -39,7 +40,7 @@ def _get_matrix(z, key, m):
     return sparse.csr_array(arrs, shape=tuple(m["shape"]))
 
 
-def _put_smoother(out, key, sm):
+def _put_smoother(out, key, sm, A=None):
     if sm is None or (getattr(sm, "func", None) is None and getattr(sm, "__name__", "") == "none"):
         return None
     func = getattr(sm, "func", None)
@@ -49,6 +50,13 @@ def _put_smoother(out, key, sm):
         if ne is not None:
             kw = {k: (int(v) if k == "iterations" else (v if isinstance(v, str) else float(np.real(v)))) for k, v in ne[1].items()}
             return {"fn": ne[0], "name": ne[0], "kw": kw, "closure": "ne"}
+        from .relaxation.smoothing import schwarz_closure_parameters
+        sz = schwarz_closure_parameters(sm, A)            # 'schwarz' / 'strength_based_schwarz' closures
+        if sz is not None:
+            for k in _SCHWARZ_ARRAYS:
+                out[f"{key}_{k}"] = np.asarray(sz[k])
+            return {"fn": "schwarz", "name": "schwarz", "closure": "schwarz",
+                    "kw": {"iterations": int(sz["iterations"]), "sweep": sz["sweep"]}}
         poly = polynomial_closure_parameters(sm)          # 'richardson' / 'chebyshev' closures
         if poly is None:
             raise NotImplementedError(f"cannot serialise closure smoother {sm!r}")
@@ -72,6 +80,9 @@ def _get_smoother(z, key, d, lvl=None):
     if d is not None and d.get("closure") == "ne":
         from .relaxation.smoothing import _ne_closure
         return _ne_closure(d["name"], lvl, **d["kw"])
+    if d is not None and d.get("closure") == "schwarz":
+        from .relaxation.smoothing import setup_schwarz
+        return setup_schwarz(lvl, **d["kw"], **{k: z[f"{key}_{k}"] for k in _SCHWARZ_ARRAYS})
     if d is None:
         def none(A, x, b):
             pass
@@ -98,8 +109,8 @@ def save_hierarchy(path, ml, extra=None, compressed=True):
             R = lvl.R if hasattr(lvl, "R") else lvl.P.T.conjugate()
             m["P"] = _put_matrix(out, f"L{k}_P", lvl.P)
             m["R"] = _put_matrix(out, f"L{k}_R", R)
-            m["pre"] = _put_smoother(out, f"L{k}_pre", getattr(lvl, "presmoother", None))
-            m["post"] = _put_smoother(out, f"L{k}_post", getattr(lvl, "postsmoother", None))
+            m["pre"] = _put_smoother(out, f"L{k}_pre", getattr(lvl, "presmoother", None), lvl.A)
+            m["post"] = _put_smoother(out, f"L{k}_post", getattr(lvl, "postsmoother", None), lvl.A)
         meta["levels"].append(m)
     from .multilevel import coarse_solver_spec
     meta["coarse_solver"] = repr(coarse_solver_spec(ml.coarse_solver))     # name or (name, kwargs)

@@ -417,3 +417,75 @@ def gauss_seidel_nr(A, x, b, iterations=1, sweep="forward", omega=1.0, Dinv=None
     """Gauss-Seidel on A^H A x = A^H b (column projections on the residual; relaxation.py:904-999 ->
     relaxation.h:684-713)."""
     _normal_equations(E.SM_GAUSS_SEIDEL_NR, 1, A, x, b, iterations, sweep, omega, Dinv)
+
+
+# --------------------------------------------------------------------------------------------
+# overlapping multiplicative Schwarz
+# --------------------------------------------------------------------------------------------
+def schwarz_parameters(A, subdomain=None, subdomain_ptr=None, inv_subblock=None, inv_subblock_ptr=None):
+    """Subdomains and the (pseudo-)inverses of their diagonal blocks (relaxation.py:1002-1078).  HOST setup, cached
+    on the matrix like the reference does: by default subdomain i is the sparsity pattern of row i; block i is
+    A[sub_i][:, sub_i] (what amg_core.extract_subblocks gathers, relaxation.h:905-960) and its inverse the LAPACK
+    gelss minimum-norm solve against the identity with rcond = 1e6 eps."""
+    cached = getattr(A, "schwarz_parameters", None)
+    if cached is not None:
+        # the reference returns the cached set when no subdomains are named or the named ones are the cached ones
+        if subdomain is None or subdomain_ptr is None or \
+                (np.array_equal(cached[0], subdomain) and np.array_equal(cached[1], subdomain_ptr)):
+            return cached
+    if subdomain is None or subdomain_ptr is None:
+        subdomain_ptr, subdomain = A.indptr.copy(), A.indices.copy()
+    if inv_subblock is None or inv_subblock_ptr is None:
+        from scipy.linalg import get_lapack_funcs
+        sizes = np.diff(subdomain_ptr)
+        inv_subblock_ptr = np.zeros(subdomain_ptr.shape, dtype=A.indices.dtype)
+        np.cumsum(sizes * sizes, out=inv_subblock_ptr[1:])
+        inv_subblock = np.zeros(int(inv_subblock_ptr[-1]), dtype=A.dtype)
+        gelss, = get_lapack_funcs(["gelss"], (np.ones(1, dtype=A.dtype),))
+        rcond = 1e6 * np.finfo(np.float64).eps
+        Ap, Aj, Ax = A.indptr, A.indices, A.data
+        where = np.full(A.shape[1], -1, dtype=np.int64)         # column -> local index inside the current subdomain
+        for d, m in enumerate(sizes):
+            rows = subdomain[subdomain_ptr[d]:subdomain_ptr[d + 1]]
+            where[rows] = np.arange(m)
+            block = np.zeros((m, m), dtype=A.dtype)
+            for local, row in enumerate(rows):
+                cols = Aj[Ap[row]:Ap[row + 1]]
+                hit = where[cols] >= 0
+                np.add.at(block[local], where[cols[hit]], Ax[Ap[row]:Ap[row + 1]][hit])
+            where[rows] = -1
+            sol = gelss(block, np.eye(m, dtype=A.dtype), cond=rcond, overwrite_a=True, overwrite_b=True)[1]
+            inv_subblock[inv_subblock_ptr[d]:inv_subblock_ptr[d + 1]] = sol.reshape(-1)
+    A.schwarz_parameters = (subdomain, subdomain_ptr, inv_subblock, inv_subblock_ptr)
+    return A.schwarz_parameters
+
+
+def schwarz(A, x, b, iterations=1, subdomain=None, subdomain_ptr=None, inv_subblock=None, inv_subblock_ptr=None,
+            sweep="forward"):
+    """Overlapping multiplicative Schwarz (relaxation.py:157-262 -> overlapping_schwarz_csr, relaxation.h:818-880):
+    subdomain after subdomain, x[sub] += inv(A[sub, sub]) (b - A x)[sub].  On the device the subdomains run in
+    dependency waves that reproduce the sequential order bit for bit."""
+    A, x, b = make_system(A, x, b, formats=["csr"])
+    _fp64(A)
+    A.sort_indices()
+    if sweep not in E.SWEEPS:
+        raise ValueError("valid sweep directions: 'forward', 'backward', and 'symmetric'")
+    subdomain, subdomain_ptr, inv_subblock, inv_subblock_ptr = schwarz_parameters(
+        A, subdomain, subdomain_ptr, inv_subblock, inv_subblock_ptr)
+    if A.shape[0] == 0 or iterations < 1:
+        return
+    S = _descriptor()
+    keep = []
+    _fill_schwarz(S, keep, subdomain, subdomain_ptr, inv_subblock, iterations, sweep)
+    _relax(A, x, b, S, keep)
+
+
+def _fill_schwarz(S, keep, subdomain, subdomain_ptr, inv_subblock, iterations, sweep):
+    Sj = np.ascontiguousarray(subdomain, dtype=np.int32)
+    Sp = np.ascontiguousarray(subdomain_ptr, dtype=np.int32)
+    T = np.ascontiguousarray(np.real(inv_subblock), dtype=np.float64)
+    keep += [Sj, Sp, T]
+    S.kind, S.iterations, S.sweep = E.SM_SCHWARZ, int(iterations), E.SWEEPS[sweep]
+    S.indices, S.n_indices = E.i32p(Sj), len(Sj)
+    S.indices2, S.n_indices2 = E.i32p(Sp), len(Sp)
+    S.Dinv = E.f64p(T)

@@ -304,6 +304,63 @@ def normal_equation_closure_parameters(sm):
     return name, {k: cv[k] for k in ("iterations", "sweep", "omega") if k in cv}
 
 
+def _level_csr(lvl):
+    """The level operator as sorted CSR, kept on the level as ``Acsr`` (matrix_asformat, smoothing.py:441-491)."""
+    if not hasattr(lvl, "Acsr"):
+        lvl.Acsr = lvl.A if lvl.A.format == "csr" else lvl.A.tocsr()
+    lvl.Acsr.sort_indices()
+    return lvl.Acsr
+
+
+def setup_schwarz(lvl, iterations=DEFAULT_NITER, subdomain=None, subdomain_ptr=None, inv_subblock=None,
+                  inv_subblock_ptr=None, sweep=DEFAULT_SWEEP):
+    """Overlapping multiplicative Schwarz (smoothing.py:509-526): subdomains and block inverses once, at setup."""
+    A = _level_csr(lvl)
+    params = dict(zip(("subdomain", "subdomain_ptr", "inv_subblock", "inv_subblock_ptr"),
+                      relaxation.schwarz_parameters(A, subdomain, subdomain_ptr, inv_subblock, inv_subblock_ptr)))
+    params.update(iterations=iterations, sweep=sweep)
+
+    def smoother(A_, x, b):
+        relaxation.schwarz(lvl.Acsr, x, b, **params)
+    smoother.__name__ = smoother.__qualname__ = "schwarz"
+    smoother._schwarz_parameters = params
+    return smoother
+
+
+def setup_strength_based_schwarz(lvl, iterations=DEFAULT_NITER, sweep=DEFAULT_SWEEP):
+    """Schwarz whose subdomains are the rows of the strength matrix C (smoothing.py:529-548).  The reference
+    rebuilds the block inverses on every application; they depend on A and C only, so they are built once here."""
+    C = (lvl.C if hasattr(lvl, "C") else lvl.A).tocsr()
+    C.sort_indices()
+    return setup_schwarz(lvl, iterations=iterations, subdomain=C.indices.copy(), subdomain_ptr=C.indptr.copy(),
+                         sweep=sweep)
+
+
+def schwarz_closure_parameters(sm, A):
+    """The parameters of a schwarz / strength_based_schwarz smoother closure -- the reference's (cell variables,
+    smoothing.py:509-548) or the ones built above -- as a dict, else None.  A is the level operator (the
+    strength-based closure of the reference carries the subdomains only; the inverses are built from A here)."""
+    name = getattr(sm, "__name__", None)
+    if name not in ("schwarz", "strength_based_schwarz"):
+        return None
+    own = getattr(sm, "_schwarz_parameters", None)
+    if own is not None:
+        return dict(own)
+    code, cells = getattr(sm, "__code__", None), getattr(sm, "__closure__", None)
+    if code is None or cells is None:
+        return None
+    cv = {k: c.cell_contents for k, c in zip(code.co_freevars, cells)}
+    if name == "strength_based_schwarz":
+        Acsr = sparse.csr_array(A)
+        Acsr.sort_indices()
+        cv["subdomain"], cv["subdomain_ptr"], cv["inv_subblock"], cv["inv_subblock_ptr"] = \
+            relaxation.schwarz_parameters(Acsr, cv["subdomain"], cv["subdomain_ptr"])
+    keys = ("iterations", "subdomain", "subdomain_ptr", "inv_subblock", "inv_subblock_ptr", "sweep")
+    if any(k not in cv for k in keys):
+        return None
+    return {k: cv[k] for k in keys}
+
+
 def setup_none(lvl):
     def none(A, x, b):
         pass
@@ -327,11 +384,13 @@ _REGISTER = {
     "jacobi_ne": setup_jacobi_ne,
     "gauss_seidel_ne": setup_gauss_seidel_ne,
     "gauss_seidel_nr": setup_gauss_seidel_nr,
+    "schwarz": setup_schwarz,
+    "strength_based_schwarz": setup_strength_based_schwarz,
     "none": setup_none,
 }
 
 # in the reference's registry (smoothing.py:840-878) but outside the accelerated path
-_OUT_OF_SCOPE = ["schwarz", "strength_based_schwarz", "gmres", "cg", "cgne", "cgnr"]
+_OUT_OF_SCOPE = ["gmres", "cg", "cgne", "cgnr"]
 
 
 def _setup_call(fn):
@@ -444,6 +503,13 @@ def describe(sm, A, keep):
             Dinv = np.ascontiguousarray(get_diagonal(A, norm_eq=1 if name == "gauss_seidel_nr" else 2, inv=True))
             keep.append(Dinv)
             S.Dinv = E.f64p(Dinv)
+            return S
+        sz = schwarz_closure_parameters(sm, A)
+        if sz is not None:
+            if sz["sweep"] not in E.SWEEPS:
+                raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+            relaxation._fill_schwarz(S, keep, sz["subdomain"], sz["subdomain_ptr"], sz["inv_subblock"],
+                                     sz["iterations"], sz["sweep"])
             return S
         raise NotImplementedError(
             f"smoother {getattr(sm, '__name__', sm)!r} is a closure the GPU engine cannot introspect; "

@@ -45,6 +45,7 @@
 #include <map>
 #include <memory>
 #include <tuple>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -350,9 +351,30 @@ inline cudaError_t execute(dim3 grid, dim3 block, size_t smem, int cluster, Kern
     return ok ? cudaSuccess : (g.last_error = cudaErrorLaunchFailure);
 }
 
+// dynamic shared memory above 48 KB needs cudaFuncSetAttribute(kernel, MaxDynamicSharedMemorySize, >= bytes) first,
+// as on the device (static shared memory is small in every kernel here: checked with cuobjdump --dump-resource-usage)
+inline std::unordered_map<const void *, size_t> &smem_optin()
+{
+    static std::unordered_map<const void *, size_t> m;
+    return m;
+}
+inline bool smem_allowed(const void *kernel, size_t smem)
+{
+    if (smem <= 48 * 1024) return true;
+    auto it = smem_optin().find(kernel);
+    if (it != smem_optin().end() && it->second >= smem) return true;
+    fprintf(stderr, "[cuda-emu] launch with %zu bytes of dynamic shared memory without the opt-in attribute\n", smem);
+    return false;
+}
+inline bool grid_allowed(dim3 grid)
+{
+    return grid.x <= 2147483647u && grid.y <= 65535u && grid.z <= 65535u;
+}
+
 template <class... P, class... A>
 inline cudaError_t launch(dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster, void (*kernel)(P...), A &&...args)
 {
+    if (!smem_allowed(reinterpret_cast<const void *>(kernel), smem) || !grid_allowed(grid)) return g.last_error = cudaErrorInvalidValue;
     auto call = std::make_shared<KernelCallT<P...>>(kernel, std::forward<A>(args)...);
     if (s != nullptr && s->capturing) {
         s->cap->nodes.push_back([=]() { execute(grid, block, smem, cluster, call.get()); });
@@ -726,7 +748,14 @@ inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b)
     return cudaSuccess;
 }
 
-template <class F> inline cudaError_t cudaFuncSetAttribute(F *, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F *f, cudaFuncAttribute a, int v)
+{
+    if (a == cudaFuncAttributeMaxDynamicSharedMemorySize) {
+        if (v < 0 || v > 227 * 1024) return emu::g.last_error = cudaErrorInvalidValue;
+        emu::smem_optin()[reinterpret_cast<const void *>(f)] = (size_t)v;
+    }
+    return cudaSuccess;
+}
 template <class F>
 inline cudaError_t cudaOccupancyMaxActiveClusters(int *n, F *, const cudaLaunchConfig_t *cfg)
 {

@@ -263,6 +263,27 @@ def main_widening():
                                            postsmoother=("jacobi_ne", {"omega": 4.0 / 3.0, "iterations": 2}))
     emit("cfg14_sa_jacobine_poisson2d", ml)
 
+    # cfg15: overlapping Schwarz with the default subdomains (the rows' sparsity patterns); subdomains and block
+    # inverses live in the closure's cells
+    np.random.seed(SEED)
+    A = stencil_grid(diffusion_stencil_2d(epsilon=0.05, theta=np.pi / 5.0, type="FE"), (18, 18), format="csr")
+    ml = pyamg.smoothed_aggregation_solver(A, strength=("symmetric", {"theta": 0.1}),
+                                           presmoother=("schwarz", {"sweep": "symmetric"}),
+                                           postsmoother=("schwarz", {"sweep": "backward", "iterations": 2}),
+                                           max_coarse=20)
+    emit("cfg15_sa_schwarz_aniso2d", ml)
+
+    # cfg16: strength-based Schwarz (subdomains = rows of the strength matrix, which keep=True leaves on the levels;
+    # the reference rebuilds the block inverses on every application).  Pre and post share the subdomains: with
+    # NumPy 2 the reference's parameter cache (relaxation.py:1036-1041) cannot compare two different sets.
+    np.random.seed(SEED)
+    A = A.copy()                                    # cfg15 left its parameter cache on the matrix object
+    ml = pyamg.smoothed_aggregation_solver(A, strength=("symmetric", {"theta": 0.1}),
+                                           presmoother=("strength_based_schwarz", {"sweep": "forward"}),
+                                           postsmoother=("strength_based_schwarz", {"sweep": "backward", "iterations": 2}),
+                                           max_coarse=20, keep=True)
+    emit("cfg16_sa_strength_schwarz_aniso2d", ml)
+
     # cfg10: linear elasticity with the reference's DEFAULT SA smoothers (symmetric block Gauss-Seidel)
     np.random.seed(SEED)
     A, B = linear_elasticity((12, 12))

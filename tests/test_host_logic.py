@@ -85,8 +85,6 @@ def test_unsupported_smoothers_fail_loudly():
     with pytest.raises(NotImplementedError):
         smoothing.describe(richardson, poisson1d(3), [])
     with pytest.raises(NotImplementedError):
-        smoothing._setup_call("schwarz")
-    with pytest.raises(NotImplementedError):
         smoothing._setup_call("cgnr")
     with pytest.raises(ValueError):
         smoothing._setup_call("no_such_smoother")
@@ -306,8 +304,6 @@ def test_widened_smoother_descriptors_are_parsed(load_golden):
     assert smoothing.describe(ml.levels[1].presmoother, ml.levels[1].A, keep).blocksize == 3
     # still outside the accelerated path: loud, never a CPU fallback
     with pytest.raises(NotImplementedError):
-        smoothing._setup_call("schwarz")
-    with pytest.raises(NotImplementedError):
         smoothing._setup_call("cgne")
 
 
@@ -355,3 +351,48 @@ def test_normal_equation_closures_are_parsed(load_golden):
     ml, _ = load_golden("cfg14_sa_jacobine_poisson2d")
     S = smoothing.describe(ml.levels[0].postsmoother, ml.levels[0].A, keep)
     assert S.kind == E.SM_JACOBI_NE and S.iterations == 2 and 0 < S.omega < 4.0 / 3.0
+
+
+def test_schwarz_closures_and_parameters(load_golden, tmp_path):
+    """The reference keeps the Schwarz subdomains and block inverses in closure cells (smoothing.py:509-548): they
+    reach the engine descriptor (indices = rows, indices2 = offsets, Dinv = inverses) and survive save / load;
+    schwarz_parameters restates relaxation.py:1002-1078 incl. its cache-on-the-matrix rules."""
+    import oracle
+    from pyamg_b200.hierarchy_io import save_hierarchy, load_hierarchy
+    from pyamg_b200.relaxation import relaxation
+    ml, _ = load_golden("cfg15_sa_schwarz_aniso2d")
+    lvl = ml.levels[0]
+    keep = []
+    S = smoothing.describe(lvl.presmoother, lvl.A, keep)
+    assert S.kind == E.SM_SCHWARZ and S.sweep == E.SWEEPS["symmetric"] and S.iterations == 1
+    assert S.n_indices2 == lvl.A.shape[0] + 1 and S.n_indices == lvl.A.nnz          # default: the sparsity patterns
+    S2 = smoothing.describe(lvl.postsmoother, lvl.A, keep)
+    assert S2.kind == E.SM_SCHWARZ and S2.sweep == E.SWEEPS["backward"] and S2.iterations == 2
+    sb, _ = load_golden("cfg16_sa_strength_schwarz_aniso2d")
+    S3 = smoothing.describe(sb.levels[0].postsmoother, sb.levels[0].A, keep)
+    assert S3.kind == E.SM_SCHWARZ and S3.iterations == 2
+    assert S3.n_indices2 == S.n_indices2 and S3.n_indices < S.n_indices             # strength pattern: fewer entries
+    p = str(tmp_path / "h.npz")
+    save_hierarchy(p, ml)
+    ml2, _ = load_hierarchy(p)
+    a, b = lvl.postsmoother._schwarz_parameters, ml2.levels[0].postsmoother._schwarz_parameters
+    assert all(np.array_equal(a[k], b[k]) for k in ("subdomain", "subdomain_ptr", "inv_subblock", "inv_subblock_ptr"))
+    # parameters: product == oracle == dense inverse of the blocks
+    A = sp.csr_array(lvl.A).copy()
+    A.sort_indices()
+    mine = relaxation.schwarz_parameters(A)
+    theirs = oracle.schwarz_parameters(sp.csr_array(lvl.A).copy())
+    assert all(np.array_equal(u, v) for u, v in zip(mine, theirs))
+    d = 17
+    rows = mine[0][mine[1][d]:mine[1][d + 1]]
+    blk = A.toarray()[np.ix_(rows, rows)]
+    assert np.allclose(mine[2][mine[3][d]:mine[3][d + 1]].reshape(len(rows), -1) @ blk, np.eye(len(rows)), atol=1e-10)
+    # cache rules: no subdomains named -> the cached set; other subdomains -> rebuilt and re-cached
+    assert relaxation.schwarz_parameters(A) is mine
+    sub, ptr = np.arange(A.shape[0], dtype=np.int32), np.arange(0, A.shape[0] + 1, 2, dtype=np.int32)
+    other = relaxation.schwarz_parameters(A, sub, ptr)
+    assert other is not mine and relaxation.schwarz_parameters(A) is other
+    # singular block: pseudo-inverse (gelss with rcond = 1e6 eps), not an exception
+    Z = sp.csr_array(np.array([[1.0, 1.0], [1.0, 1.0]]))
+    T = relaxation.schwarz_parameters(Z, np.array([0, 1], dtype=np.int32), np.array([0, 2], dtype=np.int32))[2]
+    assert np.allclose(T.reshape(2, 2), np.full((2, 2), 0.25))

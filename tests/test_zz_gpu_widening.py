@@ -589,7 +589,8 @@ def random_hierarchy_check(case, monkeypatch, envs):
 # ------------------------------------------------------------------ adoption of real reference solvers (needs pyamg)
 @pytest.mark.parametrize("family", ["rs_default", "rs_cljp_direct_jacobi", "sa_default", "sa_elasticity_default",
                                     "sa_energy_chebyshev", "rootnode", "pairwise", "adaptive_sa", "air",
-                                    "sa_sor_none_lu", "rs_coarse_gauss_seidel", "sa_richardson_splu"])
+                                    "sa_sor_none_lu", "rs_coarse_gauss_seidel", "sa_richardson_splu", "sa_schwarz",
+                                    "sa_strength_schwarz"])
 def test_from_pyamg_adopts_every_solver_family(family):
     """MultilevelSolver.from_pyamg on hierarchies the REAL reference builds (skipped where pyamg is not importable,
     i.e. on the GPU box; in the build container: PYTHONPATH=<reference build> AMGB_TEST_EMU=1 pytest -m gpu -k adopts):
@@ -622,6 +623,10 @@ def test_from_pyamg_adopts_every_solver_family(family):
                                                                    coarse_solver=("gauss_seidel", {"iterations": 3})),
         "sa_richardson_splu": lambda: pyamg.smoothed_aggregation_solver(A2, presmoother="richardson",
                                                                        postsmoother="richardson", coarse_solver="splu"),
+        "sa_schwarz": lambda: pyamg.smoothed_aggregation_solver(A2.copy(), presmoother="schwarz", postsmoother="schwarz"),
+        "sa_strength_schwarz": lambda: pyamg.smoothed_aggregation_solver(
+            A2.copy(), strength=("symmetric", {"theta": 0.3}), keep=True, presmoother="strength_based_schwarz",
+            postsmoother=("strength_based_schwarz", {"sweep": "forward"})),
     }
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -758,3 +763,65 @@ def test_normal_equation_smoothers_from_the_factory():
     cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A))
     assert relerr(ml.solve(b, tol=0, maxiter=3), cyc.solve(b, tol=0, maxiter=3)) < TOL
     assert ml.levels[0].presmoother.__name__ == "gauss_seidel_nr"
+
+
+# ------------------------------------------------------------------ overlapping multiplicative Schwarz
+def _cover(n, rng, max_m):
+    """A random overlapping cover of range(n): subdomains of 1..max_m distinct rows, every row in at least one."""
+    subs = [rng.choice(n, size=int(rng.integers(1, max_m + 1)), replace=False) for _ in range(n // 3)]
+    missing = np.setdiff1d(np.arange(n), np.concatenate(subs))
+    subs += [missing[k:k + 3] for k in range(0, len(missing), 3)]
+    ptr = np.zeros(len(subs) + 1, dtype=np.int32)
+    ptr[1:] = np.cumsum([len(u) for u in subs])
+    return np.concatenate(subs).astype(np.int32), ptr
+
+
+def test_schwarz_matches_oracle_and_compiled_reference():
+    """relaxation.schwarz (relaxation.py:157-262 -> overlapping_schwarz_csr, relaxation.h:818-880): subdomains that
+    touch (a row of one is a row or a column neighbour of the other) keep their sequential order, the others share a
+    wave -- bit for bit the sequential sweep.  Default subdomains (sparsity patterns), random overlapping covers with
+    subdomains of 1 row and of more rows than a warp has lanes, the three sweeps, several iterations."""
+    from pyamg_b200.gallery import poisson
+    rng = np.random.default_rng(3)
+    kern = "ref" if oracle.have_ref() else "oracle"
+    cases = []
+    for A in (poisson((9, 8), format="csr"), poisson((4, 5, 3), format="csr"),
+              sp.random(70, 70, density=0.08, random_state=np.random.RandomState(5), format="csr") + 4 * sp.eye(70)):
+        A = sp.csr_array(A)
+        A.sort_indices()
+        A.indptr, A.indices = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+        cases.append((A, None, None))
+        cases.append((A, *_cover(A.shape[0], rng, 6)))
+    cases.append((cases[-1][0], *_cover(70, rng, 45)))
+    for A, sub, ptr in cases:
+        n = A.shape[0]
+        x0, b = rng.standard_normal(n), rng.standard_normal(n)
+        for kw in (dict(), dict(sweep="backward", iterations=2), dict(sweep="symmetric", iterations=2)):
+            xo, xg = x0.copy(), x0.copy()
+            oracle.schwarz(A.copy(), xo, b, subdomain=sub, subdomain_ptr=ptr, kernels=kern, **kw)
+            gpu_relax.schwarz(A.copy(), xg, b, subdomain=sub, subdomain_ptr=ptr, **kw)
+            assert relerr(xg, xo) < TOL, (n, kw)            # (bit-equal without FMA contraction: the emulator)
+    with pytest.raises(ValueError):
+        gpu_relax.schwarz(A, x0.copy(), b, sweep="diagonal")
+    with pytest.raises(NotImplementedError):          # a row twice in one subdomain: two lanes would update it at once
+        gpu_relax.schwarz(A.copy(), x0.copy(), b, subdomain=np.array([0, 1, 0], dtype=np.int32),
+                          subdomain_ptr=np.array([0, 3], dtype=np.int32))
+
+
+def test_schwarz_smoothers_from_the_factory():
+    """('schwarz', ...) and ('strength_based_schwarz', ...) through the setup registry (smoothing.py:509-548) on an SA
+    hierarchy whose coarse levels are BSR."""
+    from pyamg_b200.aggregation import smoothed_aggregation_solver
+    from pyamg_b200.gallery import poisson
+    np.random.seed(13)
+    ml = smoothed_aggregation_solver(poisson((16, 16), format="csr"), max_coarse=15,
+                                     presmoother=("schwarz", {"sweep": "forward", "iterations": 2}),
+                                     postsmoother=("strength_based_schwarz", {"sweep": "symmetric"}))
+    assert len(ml.levels) >= 3 and ml.levels[0].presmoother.__name__ == "schwarz"
+    b = np.random.default_rng(14).random(ml.levels[0].A.shape[0])
+    cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A))
+    for cycle in ("V", "W"):
+        assert relerr(ml.solve(b, tol=0, maxiter=3, cycle=cycle), cyc.solve(b, tol=0, maxiter=3, cycle=cycle)) < TOL
+    res = []
+    ml.solve(b, tol=1e-8, residuals=res)
+    assert res[-1] < 1e-8 * np.linalg.norm(b) and len(res) < 20

@@ -8,7 +8,8 @@ import conftest as _amgb_conftest   # installs the emulator as the engine
 import pyamg.relaxation.relaxation as R
 import pyamg_b200.relaxation.relaxation as G
 NAMES = ["jacobi", "gauss_seidel", "sor", "gauss_seidel_indexed", "block_jacobi", "block_gauss_seidel", "polynomial",
-         "jacobi_indexed", "cf_jacobi", "fc_jacobi", "cf_block_jacobi", "fc_block_jacobi"]
+         "jacobi_indexed", "cf_jacobi", "fc_jacobi", "cf_block_jacobi", "fc_block_jacobi", "jacobi_ne", "gauss_seidel_ne",
+         "gauss_seidel_nr", "schwarz"]
 for n in NAMES:
     setattr(R, n, getattr(G, n))
 import pyamg.relaxation as RP

@@ -83,6 +83,26 @@ def main():
         ml.solve(b, tol=1e-8, maxiter=30, accel=accel, residuals=res)
         print(json.dumps({"item": "solve_1e-8", "accel": accel, "iterations": len(res) - 1,
                           "seconds": round(time.perf_counter() - t0, 4)}), flush=True)
+    # ---- smoothers whose waves come from conflict graphs (Kaczmarz, Schwarz): smaller problem, the Schwarz setup
+    #      inverts one dense block per row on the host (as the reference does)
+    gs = min(g, 48)
+    ml = ruge_stuben_solver(poisson((gs, gs, gs)))
+    b = np.random.default_rng(20260923).random(ml.levels[0].A.shape[0])
+    for label, sm in (("gauss_seidel", ("gauss_seidel", {"sweep": "symmetric"})),
+                      ("gauss_seidel_ne", ("gauss_seidel_ne", {"sweep": "symmetric"})),
+                      ("gauss_seidel_nr", ("gauss_seidel_nr", {"sweep": "symmetric"})),
+                      ("schwarz", ("schwarz", {"sweep": "symmetric"}))):
+        t0 = time.perf_counter()
+        change_smoothers(ml, sm, sm)
+        ml.solve(b, tol=0, maxiter=2)
+        t_setup = time.perf_counter() - t0
+        res = []
+        t0 = time.perf_counter()
+        ml.solve(b, tol=0, maxiter=10, residuals=res)
+        dt = time.perf_counter() - t0
+        print(json.dumps({"item": "cycles_small", "grid": gs, "smoother": label, "setup_and_upload_s": round(t_setup, 2),
+                          "e2e_cycles_per_s": round(10 / dt, 1),
+                          "residual_drop_per_cycle": round(float((res[-1] / res[0]) ** 0.1), 4)}), flush=True)
 
 
 if __name__ == "__main__":
