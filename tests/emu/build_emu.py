@@ -20,7 +20,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "pyamg_b200", "csrc")
 GEN = os.path.join(HERE, "_gen")
-LIB = os.path.join(GEN, "libpyamg_b200_emu.so")
+# AMGB_EMU_SANITIZE=1: a second library built with AddressSanitizer (device allocations are host heap blocks, so an
+# out-of-bounds global-memory access in a kernel is reported).  Run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+# and ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0.
+SANITIZE = os.environ.get("AMGB_EMU_SANITIZE") == "1"
+LIB = os.path.join(GEN, "libpyamg_b200_emu_asan.so" if SANITIZE else "libpyamg_b200_emu.so")
 
 
 def _match_back_template(s, i):
@@ -132,6 +136,8 @@ def _build_locked(dig, stamp, verbose):
     cmd = ["g++", "-x", "c++", "-std=c++17", "-O1", "-g", "-DAMGB_EMU", "-I", HERE, "-fPIC", "-shared",
            "-fno-strict-aliasing", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes",
            os.path.join(gdir, "engine.cu"), "-o", LIB + ".tmp"]
+    if SANITIZE:
+        cmd[5:5] = ["-fsanitize=address", "-fno-omit-frame-pointer"]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)

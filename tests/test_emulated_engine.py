@@ -134,3 +134,17 @@ def test_persistent_grids_of_other_sizes():
     for sms in ("1", "13"):
         _run({"AMGB_EMU_SMS": sms, "AMGB_TILE_MIN_NNZ": "0"},
              "vcycle_matches_reference_golden or relaxation_kernels", files=("tests/test_gpu_parity.py",))
+
+
+@pytest.mark.skipif(os.environ.get("AMGB_TEST_ASAN") != "1", reason="opt-in (AMGB_TEST_ASAN=1): builds a second emulator library")
+def test_gpu_subset_under_address_sanitizer():
+    """The emulation library built with -fsanitize=address (AMGB_EMU_SANITIZE=1): device allocations are host heap
+    blocks, so a kernel that reads or writes global memory out of bounds is reported.  The whole gpu suite runs the
+    same way:
+        LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 \
+        AMGB_EMU_SANITIZE=1 AMGB_TEST_EMU=1 python -m pytest tests -m gpu -q"""
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not installed")
+    _run({"LD_PRELOAD": asan, "ASAN_OPTIONS": "detect_leaks=0:detect_stack_use_after_return=0", "AMGB_EMU_SANITIZE": "1"},
+         SUBSET + " or schwarz or normal_equation or spgemm", timeout=1800)

@@ -10,9 +10,10 @@ with two pytest plugins from this directory:
                           complex / f32 problems stay on the reference): test_multilevel.py, test_classical.py,
                           test_aggregation.py, test_air.py, test_rootnode.py -- setup on the reference, every fp64 solve
                           on the engine (the kernel emulator when no GPU is present: AMGB_TEST_EMU=1 is set by the plugins)
-Round-1 result on the emulator: test_relaxation.py 31 of 41 (the 10 others are float32 / complex / block-row
-jacobi_indexed cases, which fail loudly by design); solver tests 55 of 61 with 233 solves on the engine (the 6 others:
-Krylov coarse solvers and the schwarz smoother -- NotImplementedError by design).
+Round-1 result on the emulator: test_relaxation.py 24 of 41 with every relaxation function replaced, the
+normal-equation and Schwarz ones included (every real fp64 case passes; the 17 others are complex-valued (15),
+float32 (1) and block-row jacobi_indexed (1) cases, which fail loudly by design); solver tests 57 of 61 with the
+solves on the engine (the 4 others: Krylov coarse solvers -- NotImplementedError by design).
 """
 import os
 import shutil
