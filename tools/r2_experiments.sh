@@ -14,7 +14,7 @@ timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "out_buffer" 
 echo "=== parity: SURVEY 8(f) widening (smoothers, AMLI, GMRES/FGMRES, GPU Galerkin) -- first hardware run"
 timeout 1500 python -m pytest tests/test_zz_gpu_widening.py -q -m gpu 2>&1 | tail -8
 echo "=== timing: widening rows"
-timeout 1200 python tools/time_widening.py --grid 128 2>&1 | tail -14 | tee gpurun_out/r2_widening.jsonl
+timeout 1500 python tools/time_widening.py --grid 128 2>&1 | tail -20 | tee gpurun_out/r2_widening.jsonl
 echo "=== parity: experimental paths"
 AMGB_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_experimental.py -q -m gpu_experimental 2>&1 | tail -15
 echo "=== A/B (graphed cycle ms, small_levels ms, per-level GB/s)"
@@ -39,6 +39,8 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python tools/time_widening.py --grid 48 > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:spgemm_row_kernel -c 3 \
     -o gpurun_out/r2_spgemm python tools/time_widening.py --grid 64 > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:schwarz_kernel|kaczmarz_kernel" -c 4 \
+    -o gpurun_out/r2_conflict_waves python -m pytest tests/test_zz_gpu_widening.py -q -m gpu -k "vcycle_matches_reference_golden and (cfg13 or cfg15)" > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:block_gs_kernel -c 2 \
     -o gpurun_out/r2_block_gs python -m pytest tests/test_zz_gpu_widening.py -q -m gpu -k "vcycle_matches_reference_golden and cfg10" > /dev/null 2>&1
 
