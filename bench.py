@@ -141,67 +141,67 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_cycles_per_s(ml, b, ncyc, kernels):
-    """The reference's CPU path (compiled relaxation.h + SciPy matvec, or the C port) on this host.
-    Returns (V-cycles/s, seconds, x after ncyc cycles) -- x doubles as a full-size parity check."""
-    import oracle
-    cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A),
-                       kernels=kernels)
-    t0 = time.perf_counter()
-    x = cyc.solve(b, tol=0, maxiter=ncyc)
-    dt = time.perf_counter() - t0
-    return ncyc / dt, dt, x
+def reference_solver(ml):
+    """The reference's CPU implementation of the path for hierarchy `ml`: (callable cycles(b, k) -> x after k
+    V-cycles from x0 = 0 incl. the per-cycle residual checks, kind, description).
 
-
-def run_reference(args, grid):
-    """--impl reference: the reference's own CPU implementation of the path, rank 0 only."""
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
+    With oracle/_ref/site present (the unmodified reference, compiled in place by oracle/build.py; it travels to
+    the GPU box) this is the REAL ``pyamg.MultilevelSolver.solve`` (multilevel.py:398-582) on the same operators
+    and smoother parameters (oracle/reference_adapter.py); otherwise the oracle's restatement of ``__solve`` driving
+    the compiled ``relaxation.h`` (oracle/_ref/libamg_ref.so) or, last, the C port."""
     import oracle
-    ml = build_hierarchy(grid)
-    n = ml.levels[0].A.shape[0]
-    b = np.random.default_rng(SEED).random(n)
+    try:
+        from oracle.reference_adapter import to_reference
+        ref = to_reference(ml)
+        return (lambda b, k: ref.solve(b, tol=0, maxiter=k)), "reference", \
+            "pyamg.MultilevelSolver.solve of the unmodified reference (oracle/_ref/site), amg_core + SciPy matvec"
+    except ImportError:
+        pass
     kernels = "ref" if oracle.have_ref() else "oracle"
     cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A),
                        kernels=kernels)
-    x = np.zeros(n)
-    for _ in range(args.warmup):
-        x = cyc.solve(b, x0=x, tol=0, maxiter=1)
+    return (lambda b, k: cyc.solve(b, tol=0, maxiter=k)), ("reference" if kernels == "ref" else "port"), \
+        ("compiled reference relaxation.h + SciPy matvec under the oracle's __solve restatement" if kernels == "ref"
+         else "oracle C port")
+
+
+def cpu_cycles_per_s(ml, b, ncyc):
+    """The reference's CPU path on this host: (V-cycles/s, seconds, x after ncyc cycles, kind, description) -- x
+    doubles as a full-size parity check."""
+    cycles, kind, desc = reference_solver(ml)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        x = cyc.solve(b, x0=x, tol=0, maxiter=1)
+    x = cycles(b, ncyc)
+    dt = time.perf_counter() - t0
+    return ncyc / dt, dt, x, kind, desc
+
+
+def run_reference(args, grid):
+    """--impl reference: the reference's own CPU implementation of the path, rank 0 only.  One call
+    ``solve(b, tol=0, maxiter=steps)`` is timed: `steps` V-cycles, each followed by the residual check, exactly
+    the reference's iteration (plus the one initial residual of the call)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    ml = build_hierarchy(grid)
+    n = ml.levels[0].A.shape[0]
+    b = np.random.default_rng(SEED).random(n)
+    cycles, kind, desc = reference_solver(ml)
+    if args.warmup > 0:
+        cycles(b, args.warmup)
+    t0 = time.perf_counter()
+    cycles(b, args.steps)
     dt = time.perf_counter() - t0
     v = args.steps / dt
-    kind = "reference" if kernels == "ref" else "port"
     print(json.dumps({
         "impl": "reference", "metric": "V-cycles/sec", "value": v, "unit": "V-cycles/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(grid, ml, 1),
         "cpu_baseline": {"value": v, "unit": "V-cycles/s", "cores": 1, "kind": kind,
-                         "sample": f"{args.steps} x (1 V-cycle + residual check) on the full hierarchy; "
-                                   f"host has {os.cpu_count()} cores, the reference path is single-threaded"},
+                         "sample": f"one solve(b, tol=0, maxiter={args.steps}) = {args.steps} x (V-cycle + residual "
+                                   f"check) on the full hierarchy; {desc}; host has {os.cpu_count()} cores, the "
+                                   "reference path is single-threaded (GIL held, no OpenMP)"},
         "e2e": {"value": v, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
-
-
-def ncu_traffic(ml, dk):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_ncu_tile_kernels.csv: dram__bytes_read.sum + dram__bytes_write.sum), or None when the
-    capture does not cover this kernel / problem size."""
-    try:
-        lvl, op = dk
-        if ml.levels[0].A.shape[0] != 256 ** 3 or op != 4 or lvl not in (0, 1):
-            return None
-        tag = "tile<G=1 OP=4>" if lvl == 0 else "tile<G=2 OP=4>"
-        vals = []
-        for ln in open(os.path.join(ROOT, "profiles", "r01_ncu_tile_kernels.csv")):
-            f = ln.strip().split(",")
-            if f[0] == tag:
-                vals.append(float(f[2]) * 1e9 + float(f[3]) * 1e6)
-        return float(np.mean(vals)) if vals else None
-    except Exception:
-        return None
 
 
 def workload_config(grid, ml, ngpus):
@@ -350,57 +350,46 @@ def run_distributed(args, grid, ml, local, rank, world, tstream):
 
 
 OPS = {0: "spmv(restrict)", 1: "residual", 2: "prolong+add", 3: "jacobi", 4: "gs_wave", 5: "block_jacobi",
-       6: "coarse_tail(cluster kernel)", 7: "resident_gs(cluster, DSMEM)", 8: "jacobi_indexed", 9: "block_gs_wave"}
+       6: "coarse_tail(cluster kernel)", 7: "resident_gs(cluster, DSMEM)", 8: "jacobi_indexed", 9: "block_gs_wave",
+       10: "coarse_part(persistent grid kernel)"}
+DEFAULT_GRID = {"cfg3": 256, "cfg2": 2000, "cfg4": 4096, "cfg5": 300}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--grid", type=int, default=256, help="grid points per dimension (3-D)")
-    ap.add_argument("--cpu-sample", type=int, default=2, help="V-cycles timed for cpu_baseline")
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg4", "cfg5"],
-                    help="cfg3 = BASELINE configs[2] (headline, default); cfg2 = configs[1]: 2-D Poisson, SA + Jacobi "
-                         "(use --grid 2000); cfg4 = configs[3]: anisotropic diffusion, SA + Jacobi, the multi-GPU "
-                         "configuration (use --grid 4096); cfg5 = configs[4]: 2-D elasticity, SA + block Jacobi (use --grid 300)")
-    args = ap.parse_args()
-    WORKLOAD["name"] = args.workload
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    grid = (args.grid,) * 3
+def so_sha():
+    try:
+        return open(os.path.join(ROOT, "pyamg_b200", "libpyamg_b200.so.sha256")).read().split()[0][:16]
+    except Exception:
+        return None
 
-    if args.impl == "reference":
-        run_reference(args, grid)
-        return
 
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of kernel `kernel_key` from the committed
+    `ncu --set full` capture profiles/r02_ncu_traffic.json -- used only when that capture was taken from THIS build
+    of the library (the capture records the .so's sha256); None otherwise."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        if d.get("so_sha16") != so_sha():
+            return None
+        return d["kernels"].get(kernel_key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def measure_config(name, grid, args, local, tstream, steps, warmup, cpu_sample, headline):
+    """Everything bench.py reports for ONE workload on one GPU: device-resident V-cycles/s, e2e through the C ABI
+    with host buffers, per-kernel roofline table, the reference's CPU path beside it and full-size parity."""
     import torch
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        # NCCL prints its version banner on stdout when NCCL_DEBUG is set: keep stdout to the one JSON line
-        os.environ.pop("NCCL_DEBUG", None)
-        if os.environ.get("AMGB_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = os.environ["AMGB_NCCL_DEBUG"]
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from pyamg_b200 import _engine as E
-
-    # a non-default torch stream: the engine launches on it, torch CUDA events time it
-    tstream = torch.cuda.Stream(device=local)
-    torch.cuda.set_stream(tstream)
+    WORKLOAD["name"] = name
     stream = tstream.cuda_stream
-    assert stream != 0
+    t_setup = time.time()
     ml = build_hierarchy(grid, stream=stream, device=local)
+    t_setup = time.time() - t_setup
     n = ml.levels[0].A.shape[0]
-    if world > 1:
-        run_distributed(args, grid, ml, local, rank, world, tstream)
-        return
     t0 = time.time()
     dev_bytes = ml.upload()
-    log(f"upload + wave scheduling {time.time() - t0:.1f}s, {dev_bytes / 1e9:.2f} GB in HBM")
+    t_upload = time.time() - t0
+    log(f"[{name}] upload + wave scheduling {t_upload:.1f}s, {dev_bytes / 1e9:.2f} GB in HBM")
     L, h = E.lib(), ml.handle
     b_host = E.pinned_empty(n)
     x_host = E.pinned_empty(n)
@@ -408,32 +397,25 @@ def main():
     dev = torch.device("cuda", local)
     b = torch.from_numpy(b_host).to(dev)
     x = torch.zeros(n, dtype=torch.float64, device=dev)
-    norms = torch.zeros(args.steps + args.warmup + 2, dtype=torch.float64, device=dev)
+    norms = torch.zeros(steps + warmup + 2, dtype=torch.float64, device=dev)
     P = lambda t: ctypes.c_void_p(t.data_ptr())
 
     def cycles(k):
         E.check(L.amgb_solve_device(h, P(b), P(x), k, 0, 1, P(norms)))
 
     # ---- device-resident throughput -------------------------------------------------------
-    cycles(args.warmup)
+    cycles(warmup)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    cycles(args.steps)
+    cycles(steps)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = ml.last_launches()
-    res = np.sqrt(norms[:args.steps + 1].cpu().numpy())
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        dist.barrier()
+    res = np.sqrt(norms[:steps + 1].cpu().numpy())
 
     # ---- end to end through the C ABI with host buffers (one cycle per call) ---------------
     nres, info = ctypes.c_int32(0), ctypes.c_int32(0)
@@ -448,20 +430,11 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
     clocks = sampler.summary()
-
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-        return
 
     # ---- per-kernel roofline: CUDA events around every launch of one cycle ----------------
     peak, peak_src = peak_hbm()
@@ -473,81 +446,187 @@ def main():
         g[0] += nbytes; g[1] += t; g[2] += 1
     total_ms = sum(g[1] for g in groups.values())
     table = sorted(((k, g) for k, g in groups.items()), key=lambda kv: -kv[1][1])
-    kernels = [{"level": k[0], "op": OPS[k[1]], "launches_per_cycle": g[2] // 3, "ms_per_cycle": round(g[1] / 3, 4),
-                "share": round(g[1] / total_ms, 3), "GBps": round(g[0] / g[1] / 1e6, 1),
-                "frac": round(g[0] / g[1] / 1e6 / peak, 3)} for k, g in table[:8]]
+    kernels = [{"level": k[0], "op": OPS.get(k[1], str(k[1])), "launches_per_cycle": g[2] // 3,
+                "ms_per_cycle": round(g[1] / 3, 4), "share": round(g[1] / total_ms, 3),
+                "GBps": round(g[0] / g[1] / 1e6, 1), "frac": round(g[0] / g[1] / 1e6 / peak, 3)} for k, g in table[:10]]
     (dk, dg) = table[0]
+    key = f"{name}:L{dk[0]}:{OPS.get(dk[1], str(dk[1])).split('(')[0]}"
     roofline = {"bound": "hbm", "achieved": dg[0] / dg[1] / 1e6, "peak": peak, "unit": "GB/s",
-                "frac": dg[0] / dg[1] / 1e6 / peak, "traffic": ncu_traffic(ml, dk),
-                "kernel": f"level {dk[0]} {OPS[dk[1]]} (csr_tile_kernel: TMA-staged CSR, wave-major rows)", "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                "bytes_per_launch": dg[0] / dg[2], "ms_per_launch": dg[1] / dg[2]}
+                "frac": dg[0] / dg[1] / 1e6 / peak, "traffic": ncu_traffic(key),
+                "kernel": f"level {dk[0]} {OPS.get(dk[1], str(dk[1]))}", "kernel_key": key,
+                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                "bytes_per_launch": dg[0] / dg[2], "ms_per_launch": dg[1] / dg[2], "share_of_cycle": dg[1] / total_ms}
+    # whole-cycle figure: algorithmic bytes of every launch of the cycle / graphed cycle time
+    cyc_bytes = sum(g[0] for g in groups.values()) / 3
+    cycle_roof = {"algorithmic_GB_per_cycle": cyc_bytes / 1e9, "GBps": cyc_bytes / (ms / steps) / 1e6,
+                  "frac": cyc_bytes / (ms / steps) / 1e6 / peak}
+    small_ms = sum(g[1] for k, g in groups.items() if k[0] >= 3) / 3
 
-    # ---- fine-level kernels in isolation (metric: fine-level SpMV GB/s vs roofline) --------
-    # level-0 operator in natural order through the resident-operator C API (TMA tile kernels)
+    out = {"value": steps / (ms * 1e-3), "unit": "V-cycles/s", "ms_per_step": ms / steps, "steps": steps,
+           "config": workload_config(grid, ml, 1), "roofline": roofline, "cycle_roofline": cycle_roof,
+           "e2e": {"value": steps / e2e_dt, "unit": "V-cycles/s", "h2d_bytes_per_step": 8 * n,
+                   "d2h_bytes_per_step": 8 * n + 16,
+                   "path": "C ABI amgb_solve_ex(b_host, x_host, maxiter=1, X0_ZERO) per step (the aspreconditioner "
+                           "pattern: rhs in, one cycle from zero + stop-test norms, iterate out), pinned host buffers"},
+           "gpu_launches": int(launches), "clocks": clocks, "kernels": kernels,
+           "levels_ge3_ms_per_cycle": round(small_ms, 4),
+           "residual_reduction_per_cycle": float((res[-1] / res[0]) ** (1.0 / max(len(res) - 1, 1))),
+           "hbm_bytes": int(dev_bytes), "host_setup_s": round(t_setup, 1), "upload_s": round(t_upload, 1)}
+
+    # ---- fine-level kernels in isolation (metric: fine-level SpMV GB/s vs roofline), checked at size ----
+    import oracle
     A0 = ml.levels[0].A
-    keep = []
-    A0c = E.as_matrix(A0, keep)
-    op0 = ctypes.c_void_p()
-    E.check(L.amgb_operator_create(local, ctypes.byref(A0c), None, 0, ctypes.c_void_p(stream), ctypes.byref(op0)))
-    xin = torch.zeros(n + 2, dtype=torch.float64, device=dev)
-    xin[:n] = b
-    bb = torch.zeros(n + 2, dtype=torch.float64, device=dev)
-    bb[:n] = torch.flip(b, dims=[0])
-    y, r = torch.empty(n + 2, dtype=torch.float64, device=dev), torch.empty(n + 2, dtype=torch.float64, device=dev)
+    if getattr(A0, "format", "csr") == "csr":
+        keep = []
+        A0c = E.as_matrix(A0, keep)
+        op0 = ctypes.c_void_p()
+        E.check(L.amgb_operator_create(local, ctypes.byref(A0c), None, 0, ctypes.c_void_p(stream), ctypes.byref(op0)))
+        xin = torch.zeros(n + 2, dtype=torch.float64, device=dev)
+        xin[:n] = b
+        bb = torch.zeros(n + 2, dtype=torch.float64, device=dev)
+        bb[:n] = torch.flip(b, dims=[0])
+        y, r = torch.empty(n + 2, dtype=torch.float64, device=dev), torch.empty(n + 2, dtype=torch.float64, device=dev)
 
-    def tkern(fn, reps=10):
-        for _ in range(3):
-            fn()
-        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        c.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(c) / reps
+        def tkern(fn, reps=10):
+            for _ in range(3):
+                fn()
+            a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            c.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(c) / reps
 
-    nnz0 = A0.nnz
-    t_spmv = tkern(lambda: E.check(L.amgb_operator_apply(op0, 0, P(xin), None, P(y), None, 0.0, None, -1)))
-    t_jac = tkern(lambda: E.check(L.amgb_operator_apply(op0, 3, P(xin), P(bb), P(y), P(r), 0.8, None, -1)))
-    L.amgb_operator_destroy(op0)
-    by_spmv = 12 * nnz0 + 4 * (n + 1) + 16 * n
-    by_jac = 12 * nnz0 + 4 * (n + 1) + 32 * n
-    fine = {"kernel": "csr_tile_kernel (TMA-staged), level-0 operator, natural order",
+        nnz0 = A0.nnz
+        omega = 0.8
+        t_spmv = tkern(lambda: E.check(L.amgb_operator_apply(op0, 0, P(xin), None, P(y), None, 0.0, None, -1)))
+        y_spmv = y[:n].cpu().numpy()
+        t_jac = tkern(lambda: E.check(L.amgb_operator_apply(op0, 3, P(xin), P(bb), P(y), P(r), omega, None, -1)))
+        y_jac, r_jac = y[:n].cpu().numpy(), r[:n].cpu().numpy()
+        L.amgb_operator_destroy(op0)
+        # parity of these launches AT SIZE against the reference's own kernels (amg_core.jacobi relaxation.h:309-346
+        # compiled in place, SciPy csr_matvec): one Jacobi sweep, the residual by-product, the SpMV
+        kern = "ref" if oracle.have_ref() else "oracle"
+        xh, bh = b_host.copy(), b_host[::-1].copy()
+        y_ref = oracle.matvec(A0, xh, kernels=kern)
+        r_ref = bh - y_ref
+        xj = xh.copy()
+        oracle.jacobi(A0, xj, bh, iterations=1, omega=omega, kernels=kern)
+        rel = lambda a_, b_: float(np.linalg.norm(a_ - b_) / np.linalg.norm(b_))
+        by_spmv = 12 * nnz0 + 4 * (n + 1) + 16 * n
+        by_jac = 12 * nnz0 + 4 * (n + 1) + 32 * n
+        out["fine_level"] = {
+            "kernel": "csr_tile_kernel (TMA-staged), level-0 operator, natural order",
             "spmv_ms": t_spmv, "spmv_GBps": by_spmv / t_spmv / 1e6, "spmv_frac": by_spmv / t_spmv / 1e6 / peak,
             "jacobi_residual_fused_ms": t_jac, "jacobi_residual_fused_GBps": by_jac / t_jac / 1e6,
-            "jacobi_residual_fused_frac": by_jac / t_jac / 1e6 / peak,
-            "jacobi_residual_fused_alg_bytes": by_jac}
+            "jacobi_residual_fused_frac": by_jac / t_jac / 1e6 / peak, "jacobi_residual_fused_alg_bytes": by_jac,
+            "parity": {"spmv": rel(y_spmv, y_ref), "jacobi_x": rel(y_jac, xj), "jacobi_residual": rel(r_jac, r_ref),
+                       "against": "amg_core.jacobi (reference relaxation.h compiled in place) + SciPy csr_matvec"
+                                  if kern == "ref" else "oracle C port", "bar": 1e-12}}
+        log(f"[{name}] fine level: SpMV {out['fine_level']['spmv_frac']:.3f}, fused Jacobi+residual "
+            f"{out['fine_level']['jacobi_residual_fused_frac']:.3f} of peak; parity {out['fine_level']['parity']}")
+        del xin, bb, y, r
 
-    # ---- CPU baseline: the reference's path on this box's host cores (bounded sample) ------
-    import oracle
-    kern = "ref" if oracle.have_ref() else "oracle"
-    cpu_v, cpu_dt, x_cpu = cpu_cycles_per_s(ml, b_host.copy(), args.cpu_sample, kern)
-    x_gpu = ml.solve(b_host, tol=0, maxiter=args.cpu_sample)
+    # ---- CPU baseline: the reference's path on this box's host cores (bounded sample) + full-size parity ------
+    cpu_v, cpu_dt, x_cpu, kind, desc = cpu_cycles_per_s(ml, b_host.copy(), cpu_sample)
+    x_gpu = ml.solve(b_host, tol=0, maxiter=cpu_sample)
     parity = float(np.linalg.norm(x_gpu - x_cpu) / np.linalg.norm(x_cpu))
-    log(f"full-size parity after {args.cpu_sample} V-cycles: |x_gpu - x_cpu|/|x_cpu| = {parity:.3e}")
-    cpu = {"value": cpu_v, "unit": "V-cycles/s", "cores": 1, "kind": "reference" if kern == "ref" else "port",
-           "sample": f"{args.cpu_sample} V-cycles (+ residual checks) on the same hierarchy and rhs, {cpu_dt:.1f}s; "
-                     f"compiled reference relaxation.h + SciPy matvec, single-threaded by construction; "
-                     f"host has {os.cpu_count()} cores"}
+    log(f"[{name}] full-size parity after {cpu_sample} V-cycles: |x_gpu - x_cpu|/|x_cpu| = {parity:.3e}; "
+        f"{out['value']:.1f} V-cycles/s, e2e {out['e2e']['value']:.1f}, cpu {cpu_v:.3f}")
+    out["cpu_baseline"] = {"value": cpu_v, "unit": "V-cycles/s", "cores": 1, "kind": kind,
+                           "sample": f"one solve(b, tol=0, maxiter={cpu_sample}) on the same hierarchy and rhs, "
+                                     f"{cpu_dt:.1f}s; {desc}; single-threaded by construction; host has "
+                                     f"{os.cpu_count()} cores"}
+    out["parity_full_size"] = {"rel_err_vs_cpu_reference": parity, "cycles": cpu_sample, "bar": 1e-12}
+    E.free_pinned(b_host)
+    E.free_pinned(x_host)
+    ml._invalidate()
+    del b, x, norms
+    torch.cuda.empty_cache()
+    return out
 
-    value = world * args.steps / (ms * 1e-3)
-    out = {
-        "metric": "V-cycles/sec", "value": value, "unit": "V-cycles/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(grid, ml, world),
-        "roofline": roofline, "cpu_baseline": cpu,
-        "e2e": {"value": world * args.steps / e2e_dt, "unit": "V-cycles/s", "h2d_bytes_per_step": 8 * n,
-                "d2h_bytes_per_step": 8 * n + 16,
-                "path": "C ABI amgb_solve_ex(b_host, x_host, maxiter=1, X0_ZERO) per step (the aspreconditioner "
-                        "pattern: rhs in, one cycle from zero + stop-test norms, iterate out), pinned host buffers"},
-        "gpu_launches": int(launches), "clocks": clocks, "fine_level": fine, "kernels": kernels,
-        "residual_reduction_per_cycle": float((res[-1] / res[0]) ** (1.0 / max(len(res) - 1, 1))),
-        "hbm_bytes": int(dev_bytes),
-        "parity_full_size": {"rel_err_vs_cpu_reference": parity, "cycles": args.cpu_sample, "bar": 1e-12},
-    }
-    print(json.dumps(out), flush=True)
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=None, help="grid points per dimension (default: the BASELINE size "
+                    "of the workload: cfg3 256, cfg2 2000, cfg4 4096, cfg5 300)")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="V-cycles timed for cpu_baseline")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg4", "cfg5"],
+                    help="cfg3 = BASELINE configs[2] (headline, default); cfg2 = configs[1]: 2-D Poisson 2000^2, SA + "
+                         "Jacobi; cfg4 = configs[3]: anisotropic diffusion 4096^2, SA + Jacobi, the multi-GPU "
+                         "configuration; cfg5 = configs[4]: 2-D elasticity 300^2, SA + block Jacobi")
+    ap.add_argument("--configs", default="cfg2,cfg5,cfg4",
+                    help="N=1 only: the other BASELINE GPU configurations measured after the headline and reported "
+                         "under 'configs' (value, e2e, roofline, cpu_baseline, parity_full_size each); '' = none")
+    ap.add_argument("--configs-budget-s", type=float, default=480.0,
+                    help="a configuration of --configs is skipped once this much wall time has been spent on them")
+    args = ap.parse_args()
+    WORKLOAD["name"] = args.workload
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    g = args.grid if args.grid is not None else DEFAULT_GRID[args.workload]
+    grid = (g,) * 3
+
+    if args.impl == "reference":
+        run_reference(args, grid)
+        return
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
     if world > 1:
-        dist.barrier()
+        import torch.distributed as dist
+        # NCCL's INFO lines would land on stdout, which carries exactly one JSON line: send them to stderr instead
+        # (the driver's rank check reads the NCCL log; nothing is suppressed)
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # a non-default torch stream: the engine launches on it, torch CUDA events time it
+    tstream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(tstream)
+    assert tstream.cuda_stream != 0
+    if world > 1:
+        ml = build_hierarchy(grid, stream=tstream.cuda_stream, device=local)
+        run_distributed(args, grid, ml, local, rank, world, tstream)
+        return
+
+    head = measure_config(args.workload, grid, args, local, tstream, args.steps, args.warmup, args.cpu_sample, True)
+    out = {"metric": "V-cycles/sec", "value": head["value"], "unit": "V-cycles/s", "n_gpus": 1, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+    for k in ("config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "fine_level", "kernels",
+              "cycle_roofline", "levels_ge3_ms_per_cycle", "residual_reduction_per_cycle", "hbm_bytes",
+              "parity_full_size", "host_setup_s", "upload_s"):
+        if k in head:
+            out[k] = head[k]
+    out["so_sha16"] = so_sha()
+
+    # ---- the other BASELINE GPU configurations, same measurements, bounded wall time ----------------------
+    extra, t_extra = {}, time.time()
+    for name in [c for c in args.configs.split(",") if c and c != args.workload]:
+        if time.time() - t_extra > args.configs_budget_s:
+            extra[name] = {"skipped": f"--configs-budget-s {args.configs_budget_s:.0f} s spent on the earlier ones"}
+            continue
+        try:
+            gg = (DEFAULT_GRID[name],) * 3
+            r = measure_config(name, gg, args, local, tstream, max(args.steps, 20), 3,
+                               1 if name == "cfg4" else 2, False)
+            r.pop("steps", None)
+            extra[name] = r
+        except Exception as exc:                                   # noqa: BLE001 - the headline must still be printed
+            extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            log(f"[{name}] failed: {exc}")
+    if extra:
+        out["configs"] = extra
+    WORKLOAD["name"] = args.workload
+    print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":

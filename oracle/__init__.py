@@ -588,6 +588,10 @@ def smoother_spec(sm):
     if getattr(sm, "__name__", "") == "strength_based_schwarz" and getattr(sm, "__closure__", None):
         # smoothing.py:529-548: subdomains = rows of the strength matrix in the cells; the block inverses are rebuilt
         # from lvl.Acsr on every application (inv_subblock=None below does the same)
+        own = getattr(sm, "_schwarz_parameters", None)      # closures built by pyamg_b200 carry them as an attribute
+        if own is not None:
+            return ("schwarz", {k: own[k] for k in ("iterations", "subdomain", "subdomain_ptr", "inv_subblock",
+                                                    "inv_subblock_ptr", "sweep")})
         cv = {k: c.cell_contents for k, c in zip(sm.__code__.co_freevars, sm.__closure__)}
         return ("schwarz", {k: cv[k] for k in ("iterations", "subdomain", "subdomain_ptr", "sweep")})
     if getattr(sm, "__name__", "") in ("jacobi_ne", "gauss_seidel_ne", "gauss_seidel_nr") and getattr(sm, "__closure__", None):

@@ -51,5 +51,74 @@ def build_oracle(force=False, verbose=False):
     return out
 
 
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The WHOLE reference package, importable (SURVEY 8(c) recipe): test infrastructure and the `--impl reference` arm.
+# ---------------------------------------------------------------------------------------------------------------
+REF_PKG = "/root/reference/pyamg"
+REF_SITE = os.path.join(HERE, "_ref", "site")          # git-ignored, NOT gpurun-ignored: travels to the GPU box
+_EXT = ["air", "evolution_strength", "graph", "krylov", "linalg", "relaxation", "ruge_stuben", "smoothed_aggregation"]
+
+
+def reference_site():
+    """Path to put on sys.path so that `import pyamg` is the unmodified reference (None if it was never built)."""
+    return REF_SITE if os.path.exists(os.path.join(REF_SITE, "pyamg", "__init__.py")) else None
+
+
+def build_reference_package(force=False, verbose=False, jobs=8):
+    """Install the unmodified reference into oracle/_ref/site: the package tree is copied there as an INSTALL (the
+    directory is git-ignored; nothing of it enters this repo's history) and its eight checked-in pybind11 binding
+    units are compiled in place with the flags of the reference's meson.build:4,7 -- meson itself is not in this
+    image.  A dist-info stub answers pyamg/__init__.py:12-13's importlib.metadata.version call."""
+    import shutil
+    import sysconfig
+    if not os.path.isdir(REF_PKG):
+        return reference_site()
+    suffix = sysconfig.get_config_var("EXT_SUFFIX")
+    dst = os.path.join(REF_SITE, "pyamg")
+    done = all(os.path.exists(os.path.join(dst, "amg_core", h + suffix)) for h in _EXT)
+    if done and not force:
+        return REF_SITE
+    if os.path.isdir(REF_SITE):
+        shutil.rmtree(REF_SITE)
+    os.makedirs(REF_SITE)
+    shutil.copytree(REF_PKG, dst, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+    inc = subprocess.check_output(["python3", "-m", "pybind11", "--includes"], text=True).split()
+    core = os.path.join(dst, "amg_core")
+    procs = []
+    for h in _EXT:
+        cmd = ["g++", "-O2", "-std=c++11", "-ftemplate-depth=2048", "-shared", "-fPIC", "-fvisibility=hidden",
+               *inc, h + "_bind.cpp", "-o", h + suffix]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append(subprocess.Popen(cmd, cwd=core))
+        if len(procs) >= jobs:
+            for p in procs:
+                assert p.wait() == 0
+            procs = []
+    for p in procs:
+        assert p.wait() == 0
+    info = os.path.join(REF_SITE, "pyamg-0.0.0.dist-info")
+    os.makedirs(info, exist_ok=True)
+    with open(os.path.join(info, "METADATA"), "w") as f:
+        f.write("Metadata-Version: 2.1\nName: pyamg\nVersion: 0.0.0+oracle\n")
+    return REF_SITE
+
+
+def import_reference():
+    """`import pyamg` = the unmodified reference from oracle/_ref/site (raises ImportError when it was never built).
+    Only tests/, smoke() and bench.py's reference / cpu_baseline legs may call this."""
+    import sys
+    site = reference_site()
+    if site is None:
+        raise ImportError("oracle/_ref/site is absent: run oracle/build.py where /root/reference exists")
+    if site not in sys.path:
+        sys.path.insert(0, site)
+    import pyamg
+    return pyamg
+
+
 if __name__ == "__main__":
     print(build_oracle(force=True, verbose=True))
+    print(build_reference_package(force=True, verbose=True))

@@ -128,6 +128,7 @@ def jacobi_prolongation_smoother(S, T, omega=4.0 / 3.0, degree=1, rho=None):
     """P = (I - omega/rho(D^-1 S) D^-1 S)^degree T   (diagonal weighting, smooth.py 'diagonal'); block operators
     keep their block structure."""
     D_inv = get_diagonal(S, inv=True)
+    S_given = S
     if _is_block(S):
         S = _bsr32(S)
         Rb = S.blocksize[0]
@@ -139,7 +140,12 @@ def jacobi_prolongation_smoother(S, T, omega=4.0 / 3.0, degree=1, rho=None):
         S = _csr32(S)
         D_inv_S = sparse.dia_array((D_inv, 0), shape=S.shape) @ S
     if rho is None:
-        rho = approximate_spectral_radius(D_inv_S)
+        if not _is_block(S):
+            # the same seeded estimate setup_jacobi asks for later: computed once, cached on the operator
+            from .relaxation.smoothing import rho_D_inv_A
+            rho = rho_D_inv_A(S_given) if sparse.issparse(S_given) and S_given.format == "csr" else rho_D_inv_A(S)
+        else:
+            rho = approximate_spectral_radius(D_inv_S)
     D_inv_S = (omega / rho) * D_inv_S
     P = T
     for _ in range(degree):
@@ -175,17 +181,25 @@ def _improve_candidates(A, B, fn, kw):
     return np.ascontiguousarray(B)
 
 
-def smoothed_aggregation_solver(A, B=None, symmetry="hermitian", strength="symmetric", aggregate="standard",
+def smoothed_aggregation_solver(A, B=None, BH=None, symmetry="hermitian", strength="symmetric", aggregate="standard",
                                 smooth=("jacobi", {"omega": 4.0 / 3.0}),
-                                presmoother=("jacobi", {"omega": 4.0 / 3.0}),
-                                postsmoother=("jacobi", {"omega": 4.0 / 3.0}),
+                                presmoother=("block_gauss_seidel", {"sweep": "symmetric"}),
+                                postsmoother=("block_gauss_seidel", {"sweep": "symmetric"}),
                                 improve_candidates=(("block_gauss_seidel", {"sweep": "symmetric", "iterations": 4}),
                                                     None),
-                                max_levels=10, max_coarse=10, keep=False, rho=None, **kwargs):
-    """Create a multilevel solver using classical-style smoothed aggregation -- the reference's signature
-    (aggregation.py:26-40) for scalar problems; the default smoothers are weighted Jacobi here because the
-    reference's default (lexicographic block Gauss-Seidel) is not a throughput smoother on a GPU (it is
-    supported by the engine, as dependency waves, when requested)."""
+                                max_levels=10, max_coarse=10, diagonal_dominance=False, keep=False, rho=None,
+                                **kwargs):
+    """Create a multilevel solver using classical-style smoothed aggregation -- the reference's signature and
+    defaults (aggregation.py:26-40), symmetric block Gauss-Seidel smoothing included (the engine runs it as
+    dependency waves of the block graph).  ``BH`` (left near-nullspace of nonsymmetric problems) and
+    ``diagonal_dominance`` belong to setup variants the host setup does not offer: they raise instead of being
+    ignored.  ``rho``: optional list of known spectral radii rho(D^-1 A) per level (skips the estimates)."""
+    if BH is not None:
+        raise NotImplementedError("host SA setup: BH (nonsymmetric problems) -- build with the reference and adopt "
+                                  "the hierarchy with MultilevelSolver.from_pyamg")
+    if diagonal_dominance:
+        raise NotImplementedError("host SA setup: diagonal_dominance -- build with the reference and adopt the "
+                                  "hierarchy with MultilevelSolver.from_pyamg")
     def unpack(v):
         return (v[0], v[1]) if isinstance(v, tuple) else (v, {})
 

@@ -16,6 +16,7 @@
 #include "csr_kernels.cuh"
 #include "tile_kernels.cuh"
 #include "tail_kernel.cuh"
+#include "grid_kernel.cuh"
 #include "resident_kernel.cuh"
 #include "tile_flat_kernel.cuh"
 #include "spgemm.cuh"
@@ -697,6 +698,10 @@ struct amgb_hierarchy {
     // coarse tail: levels >= tail_level run inside one cluster kernel (tail_kernel.cuh)
     int tail_level = 1 << 30;
     int tail_csize = 1;
+    // grid mode (grid_kernel.cuh): the same recorded program walked by one cooperatively launched CTA per SM
+    bool tail_grid = false;
+    int grid_ctas = 0;
+    GridSync *grid_sync = nullptr;
     // AMGB_TAIL_NNZ: levels with at most this many entries run in the cluster tail kernel.  Default 0 = off:
     // with programmatic dependent launch the per-wave launches of a CUDA graph pipeline better (measured
     // 9.8 ms vs 10.3 ms per 256^3 cycle, profiles/r01_tune_small_levels.txt); the tail remains selectable.
@@ -713,11 +718,12 @@ struct amgb_hierarchy {
     {
         TailStep st;
         // small steps run on CTA 0 alone (no cluster barrier); the bound is on the bytes one SM must pull
-        const bool solo = tail_csize > 1 && bytes <= tail_solo_bytes;
+        const int nctas = tail_grid ? grid_ctas : tail_csize;
+        const bool solo = nctas > 1 && bytes <= tail_solo_bytes;
         if (op <= T_GS && nrows > 0) {
             // one pass over the step's rows: as many lanes per row as the cluster can spare, but no more
             // than the row length warrants (G from pick_lanes is the smallest power of two >= mean length)
-            const int nthreads = (solo ? 1 : tail_csize) * kTailThreads;
+            const int nthreads = (solo ? 1 : nctas) * kTailThreads;
             int fill = 1;
             while (fill < 32 && (long long)fill * 2 * nrows <= nthreads) fill <<= 1;
             G = std::max(1, std::min(G, fill));
@@ -1309,6 +1315,22 @@ struct amgb_hierarchy {
         if (tp.n == 0) return AMGB_OK;
         launches++;
         cur_level = lvl + 1;
+        if (tail_grid) {
+            RET(prof_begin(10, grid_ctas, tp.n, 0, tp.bytes));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)grid_ctas);
+            cfg.blockDim = dim3(kGridThreads);
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeCooperative;
+            at[0].val.cooperative = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            const TailStep *prog = tp.dev;
+            int nsteps = tp.n;
+            GridSync *gs = grid_sync;
+            CK(cudaLaunchKernelEx(&cfg, coarse_grid_kernel, prog, nsteps, gs));
+            return prof_end();
+        }
         RET(prof_begin(6, tail_csize, tp.n, 0, tp.bytes));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)tail_csize);
@@ -2370,6 +2392,9 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
     }
     {   // coarse tail: the deepest run of levels whose operators are all small and block-smoother free
         const char *nt = getenv("AMGB_NO_TAIL");
+        const char *tg = getenv("AMGB_TAIL_GRID");
+        h->tail_grid = tg && tg[0] == '1';
+        if (h->tail_grid) h->tail_nnz_limit = 12000000;          // levels up to ~12 M entries (L2-resident waves)
         const char *tn = getenv("AMGB_TAIL_NNZ");
         if (tn && atoll(tn) >= 0) h->tail_nnz_limit = atoll(tn);
         const char *sb = getenv("AMGB_TAIL_SOLO_BYTES");
@@ -2386,7 +2411,18 @@ extern "C" int amgb_hierarchy_finalize(amgb_hierarchy *h, void *stream)
             if (L.A.nnz > h->tail_nnz_limit || blocky || coarse_blocky) break;
             tl = l;
         }
-        if (!(nt && nt[0] == '1') && tl < nl) {
+        if (!(nt && nt[0] == '1') && tl < nl && h->tail_grid) {
+            // one CTA per SM, all co-resident (cooperative launch): never more CTAs than the device can hold at once
+            int per_sm = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_grid_kernel, kGridThreads, 0));
+            if (per_sm < 1) return fail(AMGB_ECUDA, "coarse_grid_kernel does not fit an SM");
+            h->grid_ctas = g_num_sms;
+            const char *gc = getenv("AMGB_GRID_CTAS");
+            if (gc && atoi(gc) >= 1) h->grid_ctas = std::min(atoi(gc), g_num_sms);
+            RET(h->dalloc(&h->grid_sync, 1));
+            CK(cudaMemset(h->grid_sync, 0, sizeof(GridSync)));
+            h->tail_level = tl;
+        } else if (!(nt && nt[0] == '1') && tl < nl) {
             CK(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             const char *cs = getenv("AMGB_TAIL_CLUSTER");
             int want = cs ? atoi(cs) : 16;

@@ -366,7 +366,7 @@ class MultilevelSolver:
             warn("\nIndefinite matrix or preconditioner detected in CG, aborting\n")
         if residuals is not None:
             residuals[:] = list(res[:nres.value])
-        xout = xh.reshape(b.shape)
+        xout = xh.ravel()          # the reference's Krylov solvers hand back the ravelled iterate
         return (xout, info.value) if return_info else xout
 
     def _solve_gmres_device(self, b, x0, tol, maxiter, cycle, residuals, return_info, flexible):
@@ -389,7 +389,7 @@ class MultilevelSolver:
                                          E.f64p(res), len(res), ctypes.byref(nres), ctypes.byref(info)))
         if residuals is not None:
             residuals[:] = list(res[:min(nres.value, len(res))])
-        xout = xh.reshape(b.shape)
+        xout = xh.ravel()          # the reference's Krylov solvers hand back the ravelled iterate
         return (xout, info.value) if return_info else xout
 
     def psolve(self, b):
@@ -558,7 +558,7 @@ class MultilevelSolver:
                     status = it
                     break
 
-        xout = xh.reshape(out_shape)
+        xout = xh.ravel()          # b and x are ravelled before cycling (multilevel.py:553-554): (n,) out, even for (n,1) in
         if return_info:
             return xout, status
         return xout

@@ -332,8 +332,12 @@ def setup_strength_based_schwarz(lvl, iterations=DEFAULT_NITER, sweep=DEFAULT_SW
     rebuilds the block inverses on every application; they depend on A and C only, so they are built once here."""
     C = (lvl.C if hasattr(lvl, "C") else lvl.A).tocsr()
     C.sort_indices()
-    return setup_schwarz(lvl, iterations=iterations, subdomain=C.indices.copy(), subdomain_ptr=C.indptr.copy(),
-                         sweep=sweep)
+    smoother = setup_schwarz(lvl, iterations=iterations, subdomain=C.indices.copy(), subdomain_ptr=C.indptr.copy(),
+                             sweep=sweep)
+    # the registry key of THIS smoother (rebuild_smoother / hierarchy_io look it up by name and must re-derive the
+    # subdomains from lvl.C, not fall back to A's sparsity pattern)
+    smoother.__name__ = smoother.__qualname__ = "strength_based_schwarz"
+    return smoother
 
 
 def schwarz_closure_parameters(sm, A):
@@ -409,9 +413,15 @@ def _is_symmetric_pair(fn1, kw1, fn2, kw2):
     """Truth table of smoothing.py:226-262."""
     if kw1.get("iterations", DEFAULT_NITER) != kw2.get("iterations", DEFAULT_NITER):
         return False
+    if (fn1, fn2) in (("cf_jacobi", "fc_jacobi"), ("fc_jacobi", "cf_jacobi"),
+                      ("cf_block_jacobi", "fc_block_jacobi"), ("fc_block_jacobi", "cf_block_jacobi")):
+        return (kw1.get("f_iterations", DEFAULT_NITER) == kw2.get("f_iterations", DEFAULT_NITER)
+                and kw1.get("c_iterations", DEFAULT_NITER) == kw2.get("c_iterations", DEFAULT_NITER))
     if fn1 != fn2:
         return False
     if fn1 not in SYMMETRIC_RELAXATION:
+        if fn1.startswith(("cf_", "fc_")):
+            return False
         s1 = kw1.get("sweep", DEFAULT_SWEEP)
         s2 = kw2.get("sweep", DEFAULT_SWEEP)
         if (s1, s2) not in [("forward", "backward"), ("backward", "forward"), ("symmetric", "symmetric")]:

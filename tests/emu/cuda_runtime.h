@@ -83,13 +83,14 @@ enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureM
                              cudaStreamCaptureModeRelaxed = 2 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8,
                          cudaFuncAttributeNonPortableClusterSizeAllowed = 11 };
-enum cudaLaunchAttributeID { cudaLaunchAttributeClusterDimension = 4,
+enum cudaLaunchAttributeID { cudaLaunchAttributeCooperative = 2, cudaLaunchAttributeClusterDimension = 4,
                              cudaLaunchAttributeProgrammaticStreamSerialization = 6 };
 constexpr unsigned cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0;
 
 struct cudaLaunchAttributeValue {
     struct { unsigned x, y, z; } clusterDim;
     int programmaticStreamSerializationAllowed;
+    int cooperative;
 };
 struct cudaLaunchAttribute { cudaLaunchAttributeID id; cudaLaunchAttributeValue val; };
 
@@ -420,6 +421,15 @@ inline void cluster_barrier()
     Cluster &c = *g.cur->blk->cl;
     if (++c.arrived >= c.alive) { c.arrived = 0; c.gen++; g.progress++; }
     else { const unsigned gen = c.gen; while (c.gen == gen) yield(); }
+}
+// grid barrier of a cooperatively launched kernel (csrc/grid_kernel.cuh): arrive on a monotone counter in global
+// memory, then wait until it reaches `target`; the arrival counts as progress for the deadlock detector
+inline void grid_arrive_wait(unsigned long long *count, unsigned long long target)
+{
+    require_device_code("grid barrier");
+    (*count)++;
+    g.progress++;
+    while (*count < target) yield();
 }
 inline unsigned cluster_ctarank() { return (unsigned)g.cur->blk->rank; }
 inline unsigned cluster_nctarank() { return (unsigned)g.cur->blk->cl->nctas; }
@@ -757,6 +767,12 @@ template <class F> inline cudaError_t cudaFuncSetAttribute(F *f, cudaFuncAttribu
     return cudaSuccess;
 }
 template <class F>
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F *, int threads, size_t smem)
+{
+    *n = (threads <= 1024 && smem <= 227 * 1024) ? std::max(1, 2048 / std::max(threads, 1)) : 0;
+    return cudaSuccess;
+}
+template <class F>
 inline cudaError_t cudaOccupancyMaxActiveClusters(int *n, F *, const cudaLaunchConfig_t *cfg)
 {
     const size_t per_sm = 227 * 1024;
@@ -767,7 +783,17 @@ template <class... P, class... A>
 inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t *cfg, void (*kernel)(P...), A &&...args)
 {
     int cluster = 1;
-    for (unsigned k = 0; k < cfg->numAttrs; k++)
+    for (unsigned k = 0; k < cfg->numAttrs; k++) {
         if (cfg->attrs[k].id == cudaLaunchAttributeClusterDimension) cluster = (int)cfg->attrs[k].val.clusterDim.x;
+        // a cooperative grid: every block is resident at once (the device guarantees it or refuses the launch; one
+        // block per SM is the rule the engine follows) -- scheduled here like one big cluster
+        if (cfg->attrs[k].id == cudaLaunchAttributeCooperative && cfg->attrs[k].val.cooperative) {
+            cudaDeviceProp pr;
+            cudaGetDeviceProperties(&pr, 0);
+            const unsigned nb = cfg->gridDim.x * cfg->gridDim.y * cfg->gridDim.z;
+            if ((int)nb > pr.multiProcessorCount) return emu::g.last_error = cudaErrorInvalidValue;
+            cluster = (int)nb;
+        }
+    }
     return emu::launch(cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, cfg->stream, cluster, kernel, std::forward<A>(args)...);
 }

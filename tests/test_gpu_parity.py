@@ -61,7 +61,7 @@ def test_vcycle_matches_oracle_on_fresh_rhs(name, load_golden):
     cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.P)
     xo = cyc.solve(b, tol=0, maxiter=4)
     xg = ml.solve(b, tol=0, maxiter=4)
-    assert xg.shape == (n, 1)
+    assert xg.shape == (n,)          # the reference ravels b and x (multilevel.py:553-554) and returns (n,)
     assert relerr(xg, xo) < TOL
 
 
@@ -72,7 +72,16 @@ def test_vcycle_matches_oracle_on_fresh_rhs(name, load_golden):
                                  {"AMGB_TILE_CFG": "4", "AMGB_NO_HINTS": "1"}, {"AMGB_NO_TAIL": "1"},
                                  {"AMGB_TAIL_NNZ": "600000"}, {"AMGB_TAIL_NNZ": "600000", "AMGB_TAIL_CLUSTER": "1"},
                                  {"AMGB_TAIL_NNZ": "600000", "AMGB_TAIL_CLUSTER": "4"}, {"AMGB_NO_PDL": "1"},
-                                 {"AMGB_NO_TAIL": "1", "AMGB_NO_TILES": "1"}, {"AMGB_TAIL_NNZ": "600000", "AMGB_TAIL_SOLO_BYTES": "0"}])
+                                 {"AMGB_NO_TAIL": "1", "AMGB_NO_TILES": "1"}, {"AMGB_TAIL_NNZ": "600000", "AMGB_TAIL_SOLO_BYTES": "0"},
+                                 # the persistent grid kernel for the coarse part (grid_kernel.cuh), incl. no solo steps
+                                 # and every step solo; the TMA tile kernels forced onto the small golden operators
+                                 {"AMGB_TAIL_GRID": "1"}, {"AMGB_TAIL_GRID": "1", "AMGB_TAIL_SOLO_BYTES": "0"},
+                                 {"AMGB_TAIL_GRID": "1", "AMGB_TAIL_SOLO_BYTES": "1e12"},
+                                 {"AMGB_TAIL_GRID": "1", "AMGB_TAIL_NNZ": "3000", "AMGB_TILE_MIN_NNZ": "0"},
+                                 {"AMGB_NO_TAIL": "1", "AMGB_TILE_MIN_NNZ": "0"},
+                                 {"AMGB_NO_TAIL": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_G": "2"},
+                                 {"AMGB_NO_TAIL": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_G": "8", "AMGB_TILE_CFG": "4"},
+                                 {"AMGB_NO_TAIL": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_CFG": "1"}])
 @pytest.mark.parametrize("name", GOLDEN)
 def test_every_kernel_path_matches_reference_golden(name, env, monkeypatch):
     """The lanes-per-row kernels, the un-permuted layout, the un-graphed cycle, forced lane-group widths
