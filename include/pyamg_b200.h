@@ -339,6 +339,26 @@ int amgb_debug_build_tiles(int32_t n, const int32_t *Ap, int32_t G, const int64_
 int amgb_wave_schedule(int32_t n, const int32_t *Ap, const int32_t *Aj, const int32_t *list, int64_t m,
                        int32_t *wave_of, int32_t *n_waves);
 
+/* ---- (4) multi-GPU halo exchange over NVLink peer memory (the reference has no distributed
+ *      path; this replaces the host-issued ncclAllGather per operator application of round 1) -----------------
+ * One process per GPU.  amgb_comm_create allocates this rank's IPC block (flags + double-buffered staging for
+ * `cap_doubles` halo entries) and returns 64 opaque handle bytes; the ranks exchange the handles (any transport:
+ * torch.distributed all_gather) and amgb_comm_connect maps the blocks of the ranks in nbr_mask (bit q = rank q
+ * is a halo neighbour at some level; the masks must be symmetric).  amgb_comm_exchange is ONE kernel on the
+ * communicator's stream: packed boundary entries of v are stored straight into the neighbours' staging buffers,
+ * a flag per source rank is released system-wide, the kernel waits for its own sources and unpacks into the halo
+ * region of v ([owned (n_own) | from rank 0 | from rank 1 | ...]).  Graph-capturable (no host work, no NCCL). */
+typedef struct amgb_comm amgb_comm;
+int amgb_comm_create(int device, int world, int rank, int64_t cap_doubles, void *stream, amgb_comm **out,
+                     unsigned char *handle64);
+int amgb_comm_connect(amgb_comm *c, const unsigned char *handles /* world x 64 bytes */, uint32_t nbr_mask);
+/* send_idx: DEVICE array of local indices packed per destination rank; send_off: HOST, world + 1 offsets into it;
+ * peer_off: HOST, world entries: where this rank's block starts in destination q's halo region; recv_total:
+ * entries this rank receives. */
+int amgb_comm_exchange(amgb_comm *c, double *v, int64_t n_own, const int32_t *send_idx, const int64_t *send_off,
+                       const int64_t *peer_off, int64_t recv_total);
+void amgb_comm_destroy(amgb_comm *c);
+
 #ifdef __cplusplus
 }
 #endif

@@ -162,6 +162,11 @@ def _bind(L):
     L.amgb_debug_build_tiles.argtypes = [i32, c_i32p, i32, ctypes.POINTER(ctypes.c_int64), i32, i32, i32, c_i32p,
                                          c_i32p, i32, c_i32p, c_i32p]
     L.amgb_wave_schedule.argtypes = [i32, c_i32p, c_i32p, c_i32p, i64, c_i32p, c_i32p]
+    L.amgb_comm_create.argtypes = [ci, ci, ci, i64, vp, ctypes.POINTER(vp), ctypes.c_char_p]
+    L.amgb_comm_connect.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint32]
+    L.amgb_comm_exchange.argtypes = [vp, vp, i64, vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), i64]
+    L.amgb_comm_destroy.argtypes = [vp]
+    L.amgb_comm_destroy.restype = None
     return L
 
 

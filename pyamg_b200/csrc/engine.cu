@@ -2674,3 +2674,4 @@ extern "C" int amgb_profile_cycle(amgb_hierarchy *h, int32_t cycle, double *rec,
 
 #include "abi_operator.cuh"    // amgb_operator_*, amgb_arnoldi_*, amgb_debug_*, amgb_dev_*
 #include "abi_host.cuh"        // amgb_host_*, amgb_host_relax, amgb_host_csr_matmat
+#include "abi_comm.cuh"        // amgb_comm_*: halo exchange over NVLink peer memory (multi-GPU)

@@ -191,9 +191,11 @@ def build_plan(ml, world, rank, n_dist=None, dist_nnz=20_000_000, halo="allgathe
             bounds.append(coarse_bounds_from_splitting(sp, bounds[l - 1]))
         else:
             bounds.append(block_bounds(ml.levels[l].A.shape[0], world))
-    if halo not in ("allgather", "p2p"):
-        raise ValueError("halo must be 'allgather' or 'p2p'")
-    spaces = [_Space(ml.levels[l].A.shape[0], bounds[l], rank, mode=halo) for l in range(n_dist)]
+    if halo not in ("allgather", "p2p", "peer"):
+        raise ValueError("halo must be 'allgather', 'p2p' or 'peer'")
+    # 'peer' (stores into the neighbours' memory over NVLink, amgb_comm_*) shares the neighbour layout of 'p2p'
+    spaces = [_Space(ml.levels[l].A.shape[0], bounds[l], rank, mode="p2p" if halo == "peer" else halo)
+              for l in range(n_dist)]
     for l in range(n_dist):
         lvl = ml.levels[l]
         spaces[l].add_reader(lvl.A, bounds[l])                         # smoother / residual gather x_l
@@ -297,6 +299,22 @@ class DistributedSolver:
             L.x, L.xalt, L.b, L.r = (be.vector(sp.n_ext) for _ in range(4))
             L.poly = be.vector(sp.n_ext) if E.SM_POLYNOMIAL in (D.pre.kind, D.post.kind) else None
             self.lv.append(L)
+        if halo == "peer" and be.world > 1:
+            # one communicator for all levels: neighbour set = union over the levels (symmetric by construction: q
+            # sends to p exactly when p receives from q), staging sized for the largest halo
+            mask, cap = 0, 1
+            for L in self.lv:
+                sp = L.sp
+                cap = max(cap, int(sp.recv_off[-1]))
+                for q in range(be.world):
+                    if sp.send_off[q + 1] > sp.send_off[q] or sp.recv_off[q + 1] > sp.recv_off[q]:
+                        mask |= 1 << q
+            recv_offs = be.allgather_object([np.asarray(L.sp.recv_off, dtype=np.int64) for L in self.lv])
+            for l, L in enumerate(self.lv):
+                # where MY block starts inside rank q's halo region of level l
+                L.peer_off = np.array([int(recv_offs[q][l][be.rank]) for q in range(be.world)], dtype=np.int64)
+                L.send_off = np.ascontiguousarray(L.sp.send_off, dtype=np.int64)
+            be.comm_setup(cap, mask)
         # replicated remainder: an ordinary engine hierarchy on every rank
         self.sub = backend.sub_solver(MultilevelSolver, ml, self.n_dist)
         nrep = ml.levels[self.n_dist].A.shape[0]
@@ -308,6 +326,9 @@ class DistributedSolver:
     def halo(self, L, v):
         """All-gather the boundary entries of partitioned vector v into its halo region."""
         if self.be.world == 1:
+            return
+        if self.halo_mode == "peer":      # ONE kernel: pack + stores into the neighbours' staging + flags + unpack
+            self.be.exchange_peer(v, L.sp.n_own, L.send_idx, L.send_off, L.peer_off, int(L.sp.recv_off[-1]))
             return
         self.be.gather(v, L.send_idx, L.send, len(L.D.send_idx))
         if self.halo_mode == "p2p":
@@ -547,6 +568,32 @@ class GpuBackend:
             import torch.distributed as dist
             dist.all_reduce(v[:v.numel() - 2], group=self.group)
 
+    def allgather_object(self, obj):
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, obj, group=self.group)
+        return parts
+
+    def comm_setup(self, cap, nbr_mask):
+        """Peer-memory communicator (csrc/abi_comm.cuh): every rank exports one IPC block, the 64-byte handles
+        travel through the process group once, neighbours map each other's blocks."""
+        import torch.distributed as dist
+        handle = ctypes.create_string_buffer(64)
+        c = ctypes.c_void_p()
+        E.check(self.L.amgb_comm_create(self.dev_index, self.world, self.rank, int(cap),
+                                        ctypes.c_void_p(self.stream.cuda_stream), ctypes.byref(c), handle))
+        self._comm = c
+        handles = self.allgather_object(bytes(handle.raw))
+        E.check(self.L.amgb_comm_connect(c, b"".join(handles), int(nbr_mask)))
+        dist.barrier(group=self.group)
+
+    def exchange_peer(self, v, n_own, send_idx, send_off, peer_off, recv_total):
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        E.check(self.L.amgb_comm_exchange(self._comm, ctypes.c_void_p(v.data_ptr()), int(n_own),
+                                          ctypes.c_void_p(send_idx.data_ptr()), send_off.ctypes.data_as(i64p),
+                                          peer_off.ctypes.data_as(i64p), int(recv_total)))
+        self.kernel_launches += 1
+
     def allgather_host(self, own):
         """Concatenation of every rank's owned block (host array) -- result path, not timed."""
         if self.world == 1:
@@ -574,3 +621,6 @@ class GpuBackend:
         for h in self._ops:
             self.L.amgb_operator_destroy(h)
         self._ops = []
+        if getattr(self, "_comm", None) is not None:
+            self.L.amgb_comm_destroy(self._comm)
+            self._comm = None

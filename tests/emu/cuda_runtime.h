@@ -32,6 +32,7 @@
 #error "tests/emu/cuda_runtime.h is only for the -DAMGB_EMU host build of the engine"
 #endif
 
+#include <sched.h>
 #include <sys/mman.h>
 
 #include <algorithm>
@@ -431,6 +432,17 @@ inline void grid_arrive_wait(unsigned long long *count, unsigned long long targe
     g.progress++;
     while (*count < target) yield();
 }
+// a spin on memory another PROCESS writes (csrc/abi_comm.cuh: peers' flags in a shared-memory block): give the
+// processor away, count it as progress (the deadlock detector only knows this process), let the other fibers run
+inline void external_wait()
+{
+    require_device_code("external wait");
+    sched_yield();
+    g.progress++;
+    yield();
+}
+inline void register_allocation(void *p, size_t bytes) { g.allocs[(uintptr_t)p] = bytes; }
+inline void unregister_allocation(void *p) { g.allocs.erase((uintptr_t)p); }
 inline unsigned cluster_ctarank() { return (unsigned)g.cur->blk->rank; }
 inline unsigned cluster_nctarank() { return (unsigned)g.cur->blk->cl->nctas; }
 
@@ -609,6 +621,7 @@ template <class T> inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; 
 template <class T> inline T atomicCAS(T *p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
+inline void __threadfence_system() { __sync_synchronize(); }
 
 // ------------------------------------------------------------------------------------------------
 // runtime API (the subset the engine uses)
