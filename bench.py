@@ -238,46 +238,63 @@ def workload_config(grid, ml, ngpus):
             "l2": "inputs larger than L2 (level-0 operator 1.4 GB); no flush needed"}
 
 
-def run_distributed(args, grid, ml, local, rank, world, tstream):
-    """N > 1: strong scaling of the SAME problem -- levels with > 20 M stored entries row-partitioned
-    across the ranks (NCCL all-gather of halo entries before every operator application, all-reduce for
-    the restriction onto the replicated coarse part), pyamg_b200/dist.py."""
+def dist_measure(name, grid, args, local, rank, world, steps, warmup, dist_nnz):
+    """One workload on `world` GPUs (strong scaling of the SAME problem): the levels with more than `dist_nnz` stored
+    entries row-partitioned in contiguous slabs, the rest replicated (pyamg_b200/dist.py).  Halo exchange: one kernel
+    per exchange that stores the boundary entries straight into the neighbours' memory over NVLink
+    (csrc/abi_comm.cuh; AMGB_DIST_HALO=allgather|p2p selects the NCCL paths of round 1); restriction onto the
+    replicated part and the stop-test norm are NCCL all-reduces; the whole cycle is ONE CUDA graph per rank.
+    Returns rank 0's result dict (None on the other ranks)."""
     import torch
     import torch.distributed as dist
-    from pyamg_b200.dist import DistributedSolver, GpuBackend
+    from pyamg_b200.dist import DistributedSolver, GpuBackend, OP_GS, OP_JACOBI
+    WORKLOAD["name"] = name
     dev = torch.device("cuda", local)
+    tstream = torch.cuda.current_stream(dev)
+    t0 = time.time()
+    ml = build_hierarchy(grid, stream=tstream.cuda_stream, device=local)
+    t_setup = time.time() - t0
     n = ml.levels[0].A.shape[0]
     t0 = time.time()
     be = GpuBackend(device=local, rank=rank, world=world)
-    halo = os.environ.get("AMGB_DIST_HALO", "allgather")       # 'p2p': neighbour send/recv (experimental on GPU)
-    ds = DistributedSolver(ml, be, halo=halo)
-    log(f"halo exchange: {halo}; partitioned levels {ds.n_dist} of {len(ml.levels)}; halo entries/rank {[int(L.sp.maxB) for L in ds.lv]}; "
-        f"plan + upload {time.time() - t0:.1f}s")
+    halo = os.environ.get("AMGB_DIST_HALO", "peer")
+    ds = DistributedSolver(ml, be, halo=halo, dist_nnz=dist_nnz)
+    log(f"[{name}] halo exchange: {halo}; partitioned levels {ds.n_dist} of {len(ml.levels)}; halo entries received/rank "
+        f"{[int(L.sp.recv_off[-1]) if halo != 'allgather' else int(L.sp.maxB) for L in ds.lv]}; plan + upload {time.time() - t0:.1f}s")
     b_host = np.random.default_rng(SEED).random(n)
     ds.load(b_host)
-    norms = be.vector(args.steps + args.warmup + 2)
-    ds.cycles(args.warmup)
+    norms = be.vector(steps + warmup + 2)
+    ds.cycles(max(warmup, 2))
     torch.cuda.synchronize()
-    if os.environ.get("AMGB_DIST_GRAPH") == "1":                # experimental: whole distributed cycle as one graph
+    graphed = False
+    if os.environ.get("AMGB_DIST_GRAPH", "1") == "1":            # the whole distributed cycle as one graph per rank
         try:
             ds.capture_graph()
             ds.cycles(1)
             torch.cuda.synchronize()
-            log("distributed cycle captured into a CUDA graph")
+            graphed = True
         except Exception as exc:                                # noqa: BLE001 - fall back to host-driven launches
             ds._graph = None
-            log(f"graph capture unavailable ({type(exc).__name__}: {exc}); running host-driven")
+            log(f"[{name}] graph capture unavailable ({type(exc).__name__}: {exc}); running host-driven")
+    ok = torch.tensor([1 if graphed else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)                   # every rank replays a graph, or none does
+    if int(ok.item()) == 0:
+        ds._graph, graphed = None, False
+    ds.load(b_host)
     dist.barrier()
+    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = be.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ds.cycles(args.steps, norms=norms)
+    ds.cycles(steps, norms=norms)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = be.kernel_launches - l0
+    if graphed:
+        launches += steps * getattr(ds, "graph_launches", 0)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
@@ -299,54 +316,107 @@ def run_distributed(args, grid, ml, local, rank, world, tstream):
         e2e_step()
     dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
     e2e_dt = time.perf_counter() - t0
     t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_dt = float(t.item())
     clocks = sampler.summary()
-    # roofline of the local level-0 Gauss-Seidel wave kernel (same kernel as N=1, on this rank's slab)
+    # roofline of the local level-0 smoother kernel (same kernel as N=1, on this rank's slab)
     peak, peak_src = peak_hbm()
-    from pyamg_b200.dist import OP_GS
     D0 = L0.D
-    w = int(np.argmax(np.diff(D0.wave_ptr)))
-    rows_w = int(D0.wave_ptr[w + 1] - D0.wave_ptr[w])
-    nnz_w = int(D0.A.indptr[D0.wave_ptr[w + 1]] - D0.A.indptr[D0.wave_ptr[w]])
+    if D0.wave_ptr is not None:
+        w = int(np.argmax(np.diff(D0.wave_ptr)))
+        rows_w = int(D0.wave_ptr[w + 1] - D0.wave_ptr[w])
+        nnz_w = int(D0.A.indptr[D0.wave_ptr[w + 1]] - D0.A.indptr[D0.wave_ptr[w]])
+        fn = lambda: be.apply(L0.A, OP_GS, L0.x, L0.b, L0.x, omega=1.0, wave=w)
+        kbytes, kname = 12.0 * nnz_w + 36.0 * rows_w, "level 0 gs_wave on this rank's slab (csr_tile_kernel)"
+    else:
+        fn = lambda: be.apply(L0.A, OP_JACOBI, L0.x, L0.b, L0.xalt, omega=1.0)
+        kbytes = 12.0 * D0.A.nnz + 4.0 * (D0.A.shape[0] + 1) + 24.0 * D0.A.shape[0]
+        kname = "level 0 jacobi on this rank's slab (csr_tile_kernel)"
     for _ in range(3):
-        be.apply(L0.A, OP_GS, L0.x, L0.b, L0.x, omega=1.0, wave=w)
+        fn()
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a0.record()
     for _ in range(10):
-        be.apply(L0.A, OP_GS, L0.x, L0.b, L0.x, omega=1.0, wave=w)
+        fn()
     a1.record()
     torch.cuda.synchronize()
     kms = a0.elapsed_time(a1) / 10
-    kbytes = 12.0 * nnz_w + 36.0 * rows_w
-    res = np.sqrt(norms[:args.steps + 1].cpu().numpy())
+    res = np.sqrt(norms[:steps + 1].cpu().numpy())
+    # parity against the single-GPU engine on the same hierarchy and rhs: two cycles from zero on both
+    ncyc = 2
+    ds.load(b_host)
+    ds.cycles(ncyc)
+    x_dist = ds.gather_x()
+    parity = None
+    if rank == 0:
+        x_one = ml.solve(b_host, tol=0, maxiter=ncyc)
+        parity = float(np.linalg.norm(x_dist - x_one) / np.linalg.norm(x_one))
+        ml._invalidate()
+        log(f"[{name}] {world} GPUs: {steps / (ms * 1e-3):.1f} V-cycles/s ({ms / steps:.3f} ms/cycle, "
+            f"{'one CUDA graph per rank' if graphed else 'host-driven launches'}), e2e {steps / e2e_dt:.1f}; "
+            f"|x_{world}gpu - x_1gpu|/|x_1gpu| after {ncyc} cycles = {parity:.2e}")
+    dist.barrier()
+    out = None
     if rank == 0:
         cfg = workload_config(grid, ml, world)
-        cfg["parallelism"] = (f"{world} GPUs: levels 0..{ds.n_dist - 1} row-partitioned (contiguous slabs), NCCL "
-                              "all-gather of halo x before every operator application, all-reduce for the "
-                              "restriction; coarser levels replicated on every rank")
-        print(json.dumps({
-            "metric": "V-cycles/sec", "value": args.steps / (ms * 1e-3), "unit": "V-cycles/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "roofline": {"bound": "hbm", "achieved": kbytes / kms / 1e6, "peak": peak, "unit": "GB/s",
-                         "frac": kbytes / kms / 1e6 / peak, "traffic": None,
-                         "kernel": "level 0 gs_wave on this rank's slab (csr_tile_kernel)",
-                         "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"},
-            "cpu_baseline": None,
-            "e2e": {"value": args.steps / e2e_dt, "unit": "V-cycles/s", "h2d_bytes_per_step": 8 * n,
-                    "d2h_bytes_per_step": 8 * n + 8 * world,
-                    "path": "per rank: pinned rhs slab H2D, one distributed V-cycle + stop-test norm, owned x D2H"},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "residual_reduction_per_cycle": float((res[-1] / res[0]) ** (1.0 / max(len(res) - 1, 1))),
-            "halo_entries_per_rank": [int(L.sp.maxB) for L in ds.lv],
-        }), flush=True)
-    dist.barrier()
+        cfg["parallelism"] = (f"{world} GPUs: levels 0..{ds.n_dist - 1} row-partitioned (contiguous slabs), halo x entries "
+                              + ("stored into the neighbours' memory over NVLink by one kernel per exchange"
+                                 if halo == "peer" else f"exchanged with NCCL ({halo})")
+                              + " before every operator application, NCCL all-reduce for the restriction onto the "
+                              "replicated coarser levels (run redundantly on every rank)")
+        out = {"value": steps / (ms * 1e-3), "unit": "V-cycles/s", "ms_per_step": ms / steps, "config": cfg,
+               "roofline": {"bound": "hbm", "achieved": kbytes / kms / 1e6, "peak": peak, "unit": "GB/s",
+                            "frac": kbytes / kms / 1e6 / peak, "traffic": None, "kernel": kname,
+                            "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"},
+               "e2e": {"value": steps / e2e_dt, "unit": "V-cycles/s", "h2d_bytes_per_step": 8 * n,
+                       "d2h_bytes_per_step": 8 * n + 8 * world,
+                       "path": "per rank: pinned rhs slab H2D, one distributed V-cycle + stop-test norm, owned x D2H"},
+               "gpu_launches": int(launches), "clocks": clocks, "cuda_graph": graphed, "halo": halo,
+               "residual_reduction_per_cycle": float((res[-1] / res[0]) ** (1.0 / max(len(res) - 1, 1))),
+               "halo_entries_per_rank": [int(L.sp.recv_off[-1]) if halo != "allgather" else int(L.sp.maxB) for L in ds.lv],
+               "exchanges_per_cycle": int(getattr(ds, "exchanges_per_cycle", 0)),
+               "parity_vs_n1": {"rel_err": parity, "cycles": ncyc, "bar": 1e-12,
+                                "against": "the single-GPU engine on rank 0, same hierarchy and rhs"},
+               "host_setup_s": round(t_setup, 1)}
     be.close()
+    del ds, be
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_distributed(args, grid, local, rank, world):
+    """N > 1: the headline workload partitioned over the ranks, then (inside the same line, under `configs`) BASELINE
+    configs[3] -- the multi-GPU configuration north_star names: anisotropic diffusion 4096^2, SA + Jacobi, one halo
+    exchange per sweep."""
+    import torch.distributed as dist
+    head = dist_measure(args.workload, grid, args, local, rank, world, args.steps, args.warmup, 20_000_000)
+    extra = {}
+    for name in [c for c in args.configs.split(",") if c == "cfg4" and c != args.workload]:
+        try:
+            r = dist_measure(name, (DEFAULT_GRID[name],) * 3, args, local, rank, world, max(args.steps, 20), 3, 2_000_000)
+            if r is not None:
+                extra[name] = r
+        except Exception as exc:                                   # noqa: BLE001 - the headline must still be printed
+            if rank == 0:
+                extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            log(f"[{name}] failed: {exc}")
+    if rank == 0:
+        out = {"metric": "V-cycles/sec", "value": head["value"], "unit": "V-cycles/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "cpu_baseline": None}
+        for k, v in head.items():
+            if k not in out:
+                out[k] = v
+        if extra:
+            out["configs"] = extra
+        out["so_sha16"] = so_sha()
+        WORKLOAD["name"] = args.workload
+        print(json.dumps(out), flush=True)
+    dist.barrier()
 
 
 OPS = {0: "spmv(restrict)", 1: "residual", 2: "prolong+add", 3: "jacobi", 4: "gs_wave", 5: "block_jacobi",
@@ -593,8 +663,7 @@ def main():
     torch.cuda.set_stream(tstream)
     assert tstream.cuda_stream != 0
     if world > 1:
-        ml = build_hierarchy(grid, stream=tstream.cuda_stream, device=local)
-        run_distributed(args, grid, ml, local, rank, world, tstream)
+        run_distributed(args, grid, local, rank, world)
         return
 
     head = measure_config(args.workload, grid, args, local, tstream, args.steps, args.warmup, args.cpu_sample, True)

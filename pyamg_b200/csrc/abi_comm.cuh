@@ -193,6 +193,9 @@ extern "C" int amgb_comm_create(int device, int world, int rank, int64_t cap_dou
     c->peer[rank] = c->base;
     const char *g = getenv("AMGB_COMM_CTAS");
     if (g && atoi(g) >= 1) c->grid = std::min(atoi(g), 64);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->grid = std::max(1, std::min(c->grid, prop.multiProcessorCount));     // cooperative: every CTA resident
     CK(cudaDeviceSynchronize());
     *out = c;
     return AMGB_OK;

@@ -15,6 +15,10 @@
 #include "../../include/pyamg_b200.h"
 #include "csr_kernels.cuh"
 #include "tile_kernels.cuh"
+#ifndef AMGB_EMU
+#include <cuda_profiler_api.h>
+#endif
+#include <array>
 #include "tail_kernel.cuh"
 #include "grid_kernel.cuh"
 #include "resident_kernel.cuh"
@@ -793,8 +797,57 @@ struct amgb_hierarchy {
     }
 
     // ---- per-launch timing (profile mode only; never inside a graph capture) ----
+    // AMGB_NCU_SELECT="level:op:count,...": the next `count` launches of (level, op) of an UN-GRAPHED cycle are
+    // bracketed by cudaProfilerStart/Stop, so `ncu --profile-from-start off` captures exactly the launches asked
+    // for (one per kernel family and level) instead of the ~1000 launches of a cycle.  Profiling aid only.
+    std::vector<std::array<long long, 3>> ncu_select;
+    bool ncu_select_read = false, ncu_open = false;
+    void ncu_gate_begin(int op)
+    {
+#ifndef AMGB_EMU
+        if (!ncu_select_read) {
+            ncu_select_read = true;
+            const char *e = getenv("AMGB_NCU_SELECT");
+            if (e != nullptr) {
+                std::string str(e);
+                size_t pos = 0;
+                while (pos < str.size()) {
+                    size_t end = str.find(',', pos);
+                    if (end == std::string::npos) end = str.size();
+                    long long l = 0, o = 0, c = 0;
+                    if (sscanf(str.substr(pos, end - pos).c_str(), "%lld:%lld:%lld", &l, &o, &c) == 3)
+                        ncu_select.push_back({l, o, c});
+                    pos = end + 1;
+                }
+            }
+        }
+        if (ncu_select.empty() || recording) return;
+        for (auto &sel : ncu_select)
+            if (sel[0] == cur_level && sel[1] == op && sel[2] > 0) {
+                sel[2]--;
+                cudaStreamSynchronize(stream);
+                cudaProfilerStart();
+                ncu_open = true;
+                return;
+            }
+#else
+        (void)op;
+#endif
+    }
+    void ncu_gate_end()
+    {
+#ifndef AMGB_EMU
+        if (ncu_open) {
+            cudaStreamSynchronize(stream);
+            cudaProfilerStop();
+            ncu_open = false;
+        }
+#endif
+    }
+
     int prof_begin(int op, int lanes, long long rows, long long nnz, double bytes)
     {
+        if (use_graph == false) ncu_gate_begin(op);
         if (!profiling) return AMGB_OK;
         ProfRec r;
         r.level = cur_level; r.op = op; r.lanes = lanes; r.rows = rows; r.nnz = nnz; r.bytes = bytes;
@@ -806,6 +859,7 @@ struct amgb_hierarchy {
     }
     int prof_end()
     {
+        ncu_gate_end();
         if (!profiling) return AMGB_OK;
         CK(cudaEventRecord(prof.back().e1, stream));
         return AMGB_OK;

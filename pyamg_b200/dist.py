@@ -314,6 +314,7 @@ class DistributedSolver:
                 # where MY block starts inside rank q's halo region of level l
                 L.peer_off = np.array([int(recv_offs[q][l][be.rank]) for q in range(be.world)], dtype=np.int64)
                 L.send_off = np.ascontiguousarray(L.sp.send_off, dtype=np.int64)
+            cap = max(be.allgather_object(int(cap)))           # ONE staging size: peers address each other's buffers
             be.comm_setup(cap, mask)
         # replicated remainder: an ordinary engine hierarchy on every rank
         self.sub = backend.sub_solver(MultilevelSolver, ml, self.n_dist)
@@ -327,6 +328,7 @@ class DistributedSolver:
         """All-gather the boundary entries of partitioned vector v into its halo region."""
         if self.be.world == 1:
             return
+        self.n_exchanges = getattr(self, "n_exchanges", 0) + 1
         if self.halo_mode == "peer":      # ONE kernel: pack + stores into the neighbours' staging + flags + unpack
             self.be.exchange_peer(v, L.sp.n_own, L.send_idx, L.send_off, L.peer_off, int(L.sp.recv_off[-1]))
             return
@@ -434,9 +436,9 @@ class DistributedSolver:
                 self.be.copy_scalar(self.residual_norm(), norms, it)
 
     def capture_graph(self):
-        """EXPERIMENTAL (off by default; not yet validated on hardware): capture one distributed V-cycle --
-        engine kernels, NCCL collectives and the replicated sub-hierarchy's own graph -- into a CUDA graph on
-        the backend's stream, so the ~500 host-issued launches per cycle become one replay.  Requires warmed-up
+        """Capture one distributed V-cycle -- engine kernels, peer-memory halo exchanges (amgb_comm_exchange), the
+        all-reduce of the restriction and the replicated sub-hierarchy's own graph -- into a CUDA graph on the
+        backend's stream, so the ~500 host-issued launches per cycle become one replay.  Requires warmed-up
         cycles (all engine graphs instantiated) and an even number of Jacobi ping-pongs per level."""
         torch = getattr(self.be, "torch", None)
         if torch is None:
@@ -445,11 +447,16 @@ class DistributedSolver:
             swaps = sum(S.iterations for S in (L.D.pre, L.D.post) if S.kind == E.SM_JACOBI)
             if swaps % 2:
                 raise NotImplementedError("odd number of Jacobi sweeps per cycle: buffers would alternate")
+        x0 = getattr(self, "n_exchanges", 0)
         self.cycle(0)                                  # make sure every lazily built piece exists
+        self.exchanges_per_cycle = getattr(self, "n_exchanges", 0) - x0
         torch.cuda.synchronize()
+        l0 = self.be.kernel_launches
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=self.be.stream):
+        # thread-local capture mode: NCCL's watchdog thread keeps querying its events while this thread captures
+        with torch.cuda.graph(g, stream=self.be.stream, capture_error_mode="thread_local"):
             self.cycle(0)
+        self.graph_launches = self.be.kernel_launches - l0      # kernels one replay launches
         self._graph = g
         return g
 

@@ -38,9 +38,9 @@ def _unpack_arg(v):
 def rho_D_inv_A(A):
     """(approx.) spectral radius of D^-1 A, cached on the matrix (smoothing.py:372-400)."""
     if not hasattr(A, "rho_D_inv"):
-        import os
+        from ..util import gpu_rho_default
         D_inv = get_diagonal(A, inv=True)
-        if os.environ.get("AMGB_GPU_RHO") == "1" and A.format == "csr":
+        if A.format == "csr" and gpu_rho_default(A.shape[0]):
             # Arnoldi rounds on the device, D^-1 applied as a row scaling (no scaled copy of A is formed)
             A.rho_D_inv = approximate_spectral_radius(A, row_scale=D_inv, where="gpu")
         else:

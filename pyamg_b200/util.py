@@ -49,10 +49,30 @@ def get_block_diag(A, blocksize, inv_flag=True):
     return np.ascontiguousarray(block_diag)
 
 
-def _gpu_rho_enabled(where):
+GPU_RHO_MIN_ROWS = 200_000
+
+
+def gpu_rho_default(n):
+    """Where the spectral-radius estimates run when the caller does not say: on the device for operators with at
+    least GPU_RHO_MIN_ROWS rows when a CUDA device is visible (measured on a B200, profiles/r02_widening.jsonl:
+    rho(D^-1 A) of the 2.1 M-row level-0 operator 0.17 s resident on the GPU vs 35 s on the host; values equal to
+    3e-16), on the host otherwise.  AMGB_GPU_RHO=1 / 0 forces either."""
     import os
+    env = os.environ.get("AMGB_GPU_RHO")
+    if env in ("0", "1"):
+        return env == "1"
+    if n < GPU_RHO_MIN_ROWS:
+        return False
+    try:
+        from . import _engine as E
+        return E.lib().amgb_device_count() >= 1
+    except Exception:                    # noqa: BLE001 - no library / no device: the host estimator
+        return False
+
+
+def _gpu_rho_enabled(where, n=0):
     if where is None:
-        where = "gpu" if os.environ.get("AMGB_GPU_RHO") == "1" else "host"
+        where = "gpu" if gpu_rho_default(n) else "host"
     if where not in ("host", "gpu"):
         raise ValueError("where must be 'host' or 'gpu'")
     return where == "gpu"
@@ -78,7 +98,8 @@ def _approximate_spectral_radius_gpu(A, row_scale, v0, maxiter, restarts, tol):
     M = E.as_matrix(sparse.csr_array(A), keep)
     sc = None if row_scale is None else np.ascontiguousarray(row_scale, dtype=np.float64)
     hdl = ctypes.c_void_p()
-    E.check(L.amgb_arnoldi_create(0, M, None if sc is None else E.f64p(sc), int(maxiter), ctypes.byref(hdl)))
+    import os
+    E.check(L.amgb_arnoldi_create(int(os.environ.get("LOCAL_RANK", "0")), M, None if sc is None else E.f64p(sc), int(maxiter), ctypes.byref(hdl)))
     try:
         H = np.zeros((maxiter + 1, maxiter))
         m = ctypes.c_int32(0)
@@ -147,7 +168,7 @@ def approximate_spectral_radius(A, maxiter=15, restarts=5, seed=20260922, row_sc
     rng = np.random.default_rng(seed)
     v0 = rng.random(n)
     maxiter = int(min(maxiter, n))
-    if _gpu_rho_enabled(where):
+    if _gpu_rho_enabled(where, n) and sparse.issparse(A) and A.format == "csr":
         return _approximate_spectral_radius_gpu(A, row_scale, v0, maxiter, restarts, tol)
     if sparse.issparse(A) and A.format in ("csr", "bsr") and n >= 4096:
         return _approximate_spectral_radius_host_native(A, row_scale, v0, maxiter, restarts, tol)

@@ -18,6 +18,10 @@ from pyamg_b200.dist import DistributedSolver, GpuBackend   # noqa: E402
 from pyamg_b200.hierarchy_io import load_hierarchy          # noqa: E402
 
 
+HALO = sys.argv[1] if len(sys.argv) > 1 else "peer"          # peer | allgather | p2p
+GRAPH = len(sys.argv) > 2 and sys.argv[2] == "graph"
+
+
 def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -37,9 +41,13 @@ def main():
             ml, ex = load_hierarchy(os.path.join(ROOT, "tests", "golden", name + ".npz"))
             b = ex["b"]
         be = GpuBackend(device=local, rank=rank, world=world)
-        ds = DistributedSolver(ml, be, n_dist=n_dist)
+        ds = DistributedSolver(ml, be, n_dist=n_dist, halo=HALO)
         ds.load(b)
         norms = be.vector(4)
+        if GRAPH:                      # the whole distributed cycle replayed as one CUDA graph per rank
+            ds.cycles(1)
+            ds.capture_graph()
+            ds.load(b)
         ds.cycles(3, norms=norms)
         x = ds.gather_x()
         if rank == 0:
@@ -50,7 +58,7 @@ def main():
             rr = np.sqrt(norms[:4].cpu().numpy())
             good = err < 1e-12 and np.allclose(rr, res, rtol=1e-9)
             ok &= bool(good)
-            print(f"[dist-gpu] world={world} {name} n_dist={n_dist}: relerr={err:.2e} "
+            print(f"[dist-gpu] world={world} halo={HALO}{' graph' if GRAPH else ''} {name} n_dist={n_dist}: relerr={err:.2e} "
                   f"halo={[int(L.sp.maxB) for L in ds.lv]} {'OK' if good else 'FAIL'}", flush=True)
         be.close()
         dist.barrier()

@@ -182,6 +182,7 @@ struct State {
     std::vector<PendingCopy> pending;
     long long launches = 0, fibers_run = 0;
     int device_set = 0;
+    bool ext_wait = false;       // some fiber polls memory another process writes (emu::external_wait)
 };
 inline State g;
 
@@ -280,8 +281,11 @@ inline bool run_cluster(dim3 grid, dim3 block, size_t smem, unsigned first_block
     // block / cluster barrier or an mbarrier, or are done), so a warp-level synchronisation costs 32 context
     // switches, not one pass over every thread of the cluster
     const size_t nfib = fibers.size();
+    double ext_since = 0.0;
+    auto now_s = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     while (remaining > 0) {
         const unsigned long long before = g.progress;
+        g.ext_wait = false;
         remaining = 0;
         const size_t nwarp_all = (nfib + 31) / 32;
         for (size_t wi = 0; wi < nwarp_all; wi++) {
@@ -316,6 +320,20 @@ inline bool run_cluster(dim3 grid, dim3 block, size_t smem, unsigned first_block
             } while (left > 0 && g.progress != p);
             remaining += left;
         }
+        if (remaining > 0 && g.progress == before && g.ext_wait) {
+            // every runnable fiber waits for another PROCESS (peer flags in shared memory): not a deadlock of this
+            // kernel -- give the processor away and look again (bounded: a lost peer fails the launch after 120 s)
+            g.ext_wait = false;
+            if (ext_since == 0.0) ext_since = now_s();
+            if (now_s() - ext_since > 120.0) {
+                fprintf(stderr, "[cuda-emu] timeout: waited 120 s for another process\n");
+                g.cur = nullptr;
+                return false;
+            }
+            sched_yield();
+            continue;
+        }
+        if (g.progress != before) ext_since = 0.0;
         if (remaining > 0 && g.progress == before) {
             fprintf(stderr, "[cuda-emu] deadlock: %zu threads wait on a barrier nobody will release "
                             "(block %u of %u, %d threads per block)\n", remaining, first_block, grid.x * grid.y * grid.z, nthreads);
@@ -437,8 +455,7 @@ inline void grid_arrive_wait(unsigned long long *count, unsigned long long targe
 inline void external_wait()
 {
     require_device_code("external wait");
-    sched_yield();
-    g.progress++;
+    g.ext_wait = true;           // not progress of THIS process: the scheduler moves on to the other warps
     yield();
 }
 inline void register_allocation(void *p, size_t bytes) { g.allocs[(uintptr_t)p] = bytes; }

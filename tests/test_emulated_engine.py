@@ -98,6 +98,10 @@ def test_results_do_not_depend_on_thread_interleaving(tmp_path):
 
 @pytest.mark.parametrize("name,world,n_dist,halo", [("cfg3_rs_mcgs_poisson3d", 2, 2, "allgather"),
                                                     ("cfg4_sa_jacobi_aniso2d", 3, 2, "p2p"),
+                                                    # halo exchange as ONE kernel storing into the neighbours' memory
+                                                    # (amgb_comm_*; POSIX shared memory stands in for CUDA IPC)
+                                                    ("cfg3_rs_mcgs_poisson3d", 2, 2, "peer"),
+                                                    ("cfg4_sa_jacobi_aniso2d", 3, 2, "peer"),
                                                     ("cfg7_sa_cheby_richardson_poisson2d", 2, 2, "allgather")])
 def test_distributed_cycle_on_the_emulator(name, world, n_dist, halo, tmp_path, load_golden):
     """The multi-GPU layer end to end at world_size 2 / 3: DistributedSolver + GpuBackend code paths with the
