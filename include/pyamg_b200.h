@@ -290,6 +290,11 @@ void amgb_arnoldi_destroy(amgb_arnoldi *a);
 int amgb_host_csr_matmat(const amgb_matrix *A, const amgb_matrix *B, int32_t **Cp, int32_t **Cj, double **Cx,
                          int64_t *nnz);
 void amgb_free(void *p);
+/* pyamg.graph.vertex_coloring(G, 'MIS') (pyamg/graph.py:84-126 -> amg_core vertex_coloring_mis, graph.h:218-235)
+ * computed on the device: same colours vertex by vertex (structurally symmetric pattern; the diagonal is ignored).
+ * rounds (nullable): wavefront rounds used. */
+int amgb_host_vertex_coloring_mis(int32_t n, const int32_t *Ap, const int32_t *Aj, int32_t *colors,
+                                  int32_t *n_colors, int32_t *rounds);
 /* scipy.sparse._sparsetools.csr_matvec / bsr_matvec as the cycle uses them (y = A x) */
 int amgb_host_matvec(const amgb_matrix *A, const double *x, double *y);
 

@@ -68,6 +68,8 @@ SYMBOLS = [
     "amgb_dev_csr_gs_wave", "amgb_dev_partials_len", "amgb_dev_dense_matvec", "amgb_dev_fill",
     "amgb_dev_gather", "amgb_dev_reduce_len", "amgb_dev_dot", "amgb_dev_axpby", "amgb_dev_block_jacobi",
     "amgb_wave_schedule", "amgb_debug_build_tiles",
+    "amgb_host_vertex_coloring_mis",
+    "amgb_comm_create", "amgb_comm_connect", "amgb_comm_exchange", "amgb_comm_destroy",
 ]
 
 
@@ -162,6 +164,7 @@ def _bind(L):
     L.amgb_debug_build_tiles.argtypes = [i32, c_i32p, i32, ctypes.POINTER(ctypes.c_int64), i32, i32, i32, c_i32p,
                                          c_i32p, i32, c_i32p, c_i32p]
     L.amgb_wave_schedule.argtypes = [i32, c_i32p, c_i32p, c_i32p, i64, c_i32p, c_i32p]
+    L.amgb_host_vertex_coloring_mis.argtypes = [i32, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p]
     L.amgb_comm_create.argtypes = [ci, ci, ci, i64, vp, ctypes.POINTER(vp), ctypes.c_char_p]
     L.amgb_comm_connect.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint32]
     L.amgb_comm_exchange.argtypes = [vp, vp, i64, vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), i64]

@@ -412,3 +412,60 @@ extern "C" int amgb_host_matvec(const amgb_matrix *A, const double *x, double *y
     CK(cudaMemcpy(y, dy, sizeof(double) * (size_t)H.n_rows, cudaMemcpyDeviceToHost));
     return AMGB_OK;
 }
+
+
+// ---- device vertex colouring ----------------------------------------------------------------
+// The reference's 'MIS' colouring (pyamg/graph.py:84-126 -> amg_core vertex_coloring_mis, graph.h:218-235) of the
+// graph of a structurally symmetric CSR pattern, computed on the device as a wavefront of first-fit decisions
+// (coloring.cuh).  Host arrays in, host colours out.  rounds_out (nullable): rounds the wavefront needed.
+// More than 256 colours: AMGB_ENOTIMPL (callers fall back to the host routine).
+extern "C" int amgb_host_vertex_coloring_mis(int32_t n, const int32_t *Ap, const int32_t *Aj, int32_t *colors,
+                                             int32_t *n_colors, int32_t *rounds_out)
+{
+    if (n < 0 || Ap == nullptr || colors == nullptr || n_colors == nullptr) return fail(AMGB_EINVAL, "null pointer");
+    *n_colors = 0;
+    if (rounds_out) *rounds_out = 0;
+    if (n == 0) return AMGB_OK;
+    const long long nnz = Ap[n];
+    if (nnz < 0 || (nnz > 0 && Aj == nullptr)) return fail(AMGB_EINVAL, "Aj missing");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(AMGB_ECUDA, "no CUDA device");
+    Scratch sc;
+    int *dAp, *dAj, *dcol, *dflag;
+    unsigned long long *drem;
+    RET(sc.up(&dAp, Ap, (long long)n + 1));
+    RET(sc.up(&dAj, Aj, nnz));
+    RET(sc.up(&dcol, (const int *)nullptr, (long long)n));
+    RET(sc.up(&dflag, (const int *)nullptr, 1));
+    RET(sc.up(&drem, (const unsigned long long *)nullptr, 1));
+    CK(cudaMemset(dcol, 0xFF, sizeof(int) * (size_t)n));             // -1: uncoloured
+    CK(cudaMemset(dflag, 0, sizeof(int)));
+    cudaDeviceProp prop;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaGetDeviceProperties(&prop, dev));
+    const int grid = (int)std::min<long long>(((long long)n + 255) / 256, (long long)prop.multiProcessorCount * 8);
+    int rounds = 0;
+    const int kBatch = 8;                                            // rounds between two looks at the counter
+    for (;;) {
+        unsigned long long rem = 0;
+        for (int b = 0; b < kBatch; b++) {
+            CK(cudaMemsetAsync(drem, 0, sizeof(unsigned long long), 0));
+            amgb::mis_color_round_kernel<<<grid, 256>>>(n, dAp, dAj, dcol, drem, dflag);
+            CK(cudaGetLastError());
+            rounds++;
+        }
+        CK(cudaMemcpy(&rem, drem, sizeof rem, cudaMemcpyDeviceToHost));
+        if (rem == 0) break;
+        if (rounds > 4 * n + 64) return fail(AMGB_ESTATE, "vertex colouring did not terminate (pattern not symmetric?)");
+    }
+    int over = 0;
+    CK(cudaMemcpy(&over, dflag, sizeof over, cudaMemcpyDeviceToHost));
+    if (over) return fail(AMGB_ENOTIMPL, "vertex colouring needs more than 256 colours");
+    CK(cudaMemcpy(colors, dcol, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+    int k = 0;
+    for (int i = 0; i < n; i++) k = std::max(k, colors[i] + 1);
+    *n_colors = k;
+    if (rounds_out) *rounds_out = rounds;
+    return AMGB_OK;
+}

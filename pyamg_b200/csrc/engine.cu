@@ -21,6 +21,7 @@
 #include <array>
 #include "tail_kernel.cuh"
 #include "grid_kernel.cuh"
+#include "coloring.cuh"
 #include "resident_kernel.cuh"
 #include "tile_flat_kernel.cuh"
 #include "spgemm.cuh"

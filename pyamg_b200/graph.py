@@ -1,7 +1,7 @@
 """Graph helpers used at smoother-setup time (host): vertex colouring for multi-colour GS.
 
-Plays the role of pyamg.graph.vertex_coloring (pyamg/graph.py:84-126); built in are first-fit greedy
-colourings in natural, smallest-last (Matula-Beck; fewest colours on the dense coarse operators, the
+Plays the role of pyamg.graph.vertex_coloring (pyamg/graph.py:84-126); built in are the reference's 'MIS' colouring
+(= first-fit greedy in natural order, see below), first-fit in smallest-last (Matula-Beck; fewest colours on the dense coarse operators, the
 smoother factory's default) and largest-degree-first order -- all red-black on 5/7-point stencils.  Any colouring --
 including the reference's 'MIS' one -- gives a valid multi-colour sweep: the engine derives the
 dependency waves from the row list itself (csrc/engine.cu build_waves), so a colouring only
@@ -13,9 +13,56 @@ from scipy import sparse
 from . import _host as H
 
 
-def vertex_coloring(G, method="greedy"):
-    """Colours (int32 array, starting at 0) such that no edge of G joins equal colours."""
-    orders = {"greedy": 0, "natural": 0, "smallest_last": 1, "SL": 1, "LDF": 2}
+GPU_COLORING_MIN_ROWS = 200_000
+
+
+def _device_coloring_wanted(n, where):
+    import os
+    if where is not None:
+        if where not in ("host", "gpu"):
+            raise ValueError("where must be 'host' or 'gpu'")
+        return where == "gpu"
+    env = os.environ.get("AMGB_GPU_COLORING")
+    if env in ("0", "1"):
+        return env == "1"
+    if n < GPU_COLORING_MIN_ROWS:
+        return False
+    try:
+        from . import _engine as E
+        return E.lib().amgb_device_count() >= 1
+    except Exception:                    # noqa: BLE001 - no library / no device: the host routine
+        return False
+
+
+def _mis_coloring_device(G):
+    """The 'MIS' colouring on the device (csrc/coloring.cuh: wavefront of first-fit decisions, colours identical to
+    the sequential reference vertex by vertex).  Returns None when it needs more than 256 colours."""
+    import ctypes
+    from . import _engine as E
+    n = G.shape[0]
+    Ap = np.ascontiguousarray(G.indptr, dtype=np.int32)
+    Aj = np.ascontiguousarray(G.indices, dtype=np.int32)
+    colors = np.empty(n, dtype=np.int32)
+    k, rounds = ctypes.c_int32(0), ctypes.c_int32(0)
+    try:
+        E.check(E.lib().amgb_host_vertex_coloring_mis(n, E.i32p(Ap), E.i32p(Aj), E.i32p(colors), ctypes.byref(k),
+                                                      ctypes.byref(rounds)))
+    except NotImplementedError:
+        return None
+    return colors
+
+
+def vertex_coloring(G, method="greedy", where=None):
+    """Colours (int32 array, starting at 0) such that no edge of G joins equal colours.
+
+    ``where='gpu'`` (default for 'MIS' / natural-order greedy on graphs with at least GPU_COLORING_MIN_ROWS vertices
+    when a CUDA device is visible; AMGB_GPU_COLORING=0/1 forces either) computes the colouring on the device."""
+    # 'MIS' (pyamg.graph.vertex_coloring's default, amg_core/graph.h:218-235): colour k is the lexicographically first
+    # maximal independent set of what colours 0..k-1 left over (maximal_independent_set_serial walks the vertices in
+    # index order, graph.h:128-199).  Vertex i misses set k exactly when a SMALLER-index neighbour is in it, so i gets
+    # the smallest colour no smaller-index neighbour holds: natural-order first fit.  Same colours vertex by vertex
+    # (tests/test_setup.py::test_mis_colouring_is_the_reference's, against the real reference).
+    orders = {"greedy": 0, "natural": 0, "MIS": 0, "smallest_last": 1, "SL": 1, "LDF": 2}
     if method not in orders:
         raise NotImplementedError(f"colouring method {method!r}: built in are 'greedy' (natural-order first "
                                   "fit), 'smallest_last', 'LDF'; or pass the row list from "
@@ -32,6 +79,12 @@ def vertex_coloring(G, method="greedy"):
         H.lib().amgb_setup_greedy_coloring_ordered(n, H.ip(Ap), H.ip(Aj), orders[method], H.ip(colors))
         return colors, bool(H.lib().amgb_setup_coloring_is_valid(n, H.ip(Ap), H.ip(Aj), H.ip(colors)))
 
+    if orders[method] == 0 and _device_coloring_wanted(n, where):
+        Ap = np.ascontiguousarray(G.indptr, dtype=np.int32)
+        Aj = np.ascontiguousarray(G.indices, dtype=np.int32)
+        colors = _mis_coloring_device(G)
+        if colors is not None and H.lib().amgb_setup_coloring_is_valid(n, H.ip(Ap), H.ip(Aj), H.ip(colors)):
+            return colors          # (an invalid result means a structurally non-symmetric pattern: host path below)
     colors, ok = run(G)
     if not ok:     # structurally non-symmetric operator: colour the symmetrised pattern instead
         colors, ok = run((abs(G) + abs(G).T).tocsr())

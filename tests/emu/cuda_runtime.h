@@ -683,6 +683,7 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
     return cudaSuccess;
 }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 
 inline cudaError_t cudaMalloc(void **p, size_t bytes)
 {

@@ -196,3 +196,20 @@ def test_vector_sa_setup_reproduces_reference_elasticity_hierarchy(load_golden):
     # default candidates of a block problem: one constant per unknown of a node
     ml3 = smoothed_aggregation_solver(A, max_coarse=20)
     assert ml3.levels[0].B.shape == (392, 2) and ml3.levels[1].A.blocksize == (2, 2)
+
+
+def test_mis_colouring_is_the_references():
+    """pyamg.graph.vertex_coloring(G, 'MIS') (amg_core/graph.h:218-235: repeated lexicographically-first maximal
+    independent sets) equals natural-order first fit vertex by vertex -- checked against the REAL reference (installed
+    by oracle/build.py into oracle/_ref/site) on every level of two Ruge-Stuben hierarchies and a random graph."""
+    pyamg = pytest.importorskip("pyamg")
+    import scipy.sparse as sp
+    from pyamg.graph import vertex_coloring as reference_coloring
+    from pyamg_b200.graph import vertex_coloring
+    graphs = []
+    for A in (pyamg.gallery.poisson((30, 30), format="csr"), pyamg.gallery.poisson((12, 12, 12), format="csr")):
+        graphs += [lvl.A for lvl in pyamg.ruge_stuben_solver(A, max_coarse=10).levels]
+    R = sp.random(300, 300, 0.03, random_state=1)
+    graphs.append((R + R.T).tocsr())
+    for G in graphs:
+        assert np.array_equal(reference_coloring(G, "MIS"), vertex_coloring(G, "MIS"))
