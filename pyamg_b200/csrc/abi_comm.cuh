@@ -21,8 +21,8 @@
 // still unpacks staging[k & 1], and cannot start exchange k+2 before this rank has signalled k+1 -- which the stream
 // orders after the unpack of k.  Flags are monotone, so "flag >= k" is the whole protocol.
 //
-// Launch: all CTAs must be co-resident (CTAs that have pushed wait for peers while the last one signals), so the
-// kernel is launched cooperatively (the driver checks residency) with a small grid; every spin traps after a bounded
+// Launch: all CTAs must be co-resident (CTAs that have pushed wait for peers while the last one signals): a small
+// grid (16 CTAs by default) ordered after the previous kernel by the stream / graph; every spin traps after a bounded
 // number of polls instead of hanging the device when a peer died.
 #pragma once
 #include <cstring>
@@ -143,6 +143,7 @@ struct amgb_comm {
     unsigned long long *seq = nullptr;
     unsigned *done = nullptr, *fin = nullptr;
     int grid = 16;
+    int coop = 0;
     long long exchanges = 0;
 #ifdef AMGB_EMU
     char shm_name[64] = {};
@@ -191,6 +192,8 @@ extern "C" int amgb_comm_create(int device, int world, int rank, int64_t cap_dou
     c->done = (unsigned *)((unsigned char *)ctrl + 64);
     c->fin = (unsigned *)((unsigned char *)ctrl + 128);
     c->peer[rank] = c->base;
+    const char *cp = getenv("AMGB_COMM_COOP");
+    c->coop = (cp && cp[0] == '1') ? 1 : 0;
     const char *g = getenv("AMGB_COMM_CTAS");
     if (g && atoi(g) >= 1) c->grid = std::min(atoi(g), 64);
     cudaDeviceProp prop;
@@ -267,10 +270,19 @@ extern "C" int amgb_comm_exchange(amgb_comm *c, double *v, int64_t n_own, const 
     cfg.gridDim = dim3((unsigned)c->grid);
     cfg.blockDim = dim3(kCommThreads);
     cfg.stream = c->stream;
+    // All CTAs must be resident at once (CTAs that have pushed wait for peers while the last one signals).  The grid is
+    // at most 64 CTAs of 256 threads on a 148-SM device and the stream / graph orders it after the previous kernel, so
+    // that holds by construction; AMGB_COMM_COOP=1 additionally asks the driver to verify it (cooperative launch).
+    // The emulator always co-schedules the blocks of this kernel.
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.attrs = at;
+#ifdef AMGB_EMU
+    cfg.numAttrs = 1;
+#else
+    cfg.numAttrs = c->coop ? 1 : 0;
+#endif
     CK(cudaLaunchKernelEx(&cfg, halo_exchange_kernel, a));
     c->exchanges++;
     return AMGB_OK;

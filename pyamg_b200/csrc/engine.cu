@@ -171,10 +171,16 @@ static int g_tile_ctas_cap = 0;                  // AMGB_TILE_CTAS (0 = per-epil
 static int g_tile_T = 256, g_tile_rmax = 64, g_tile_warps = 8;
 static int g_tile_hints = 1;        // AMGB_NO_HINTS=1 disables the L2 eviction hints
 static int g_tile_pdl = 0;          // AMGB_TILE_PDL=1 (experimental): programmatic dependent launch of the tile kernel
-static int g_tile_flat = 0;         // AMGB_TILE_FLAT=1 (experimental): flat-gather tile kernel (tile_flat_kernel.cuh)
+static int g_tile_flat = 0;         // AMGB_TILE_FLAT=1 (experimental): flat-gather tile kernel (tile_flat_kernel.cuh); 2: only R (all levels) and P (levels >= 1)
+// second geometry for the denser operators of a hierarchy (mean row length above g_dense_avg): AMGB_TILE_DENSE_CFG=7
+static int g_dense_cfg = 0;
+static double g_dense_avg = 12.0;
+static int g_dense_ctas[5] = {2, 2, 2, 2, 2};
+static int g_dense_T = 352, g_dense_rmax = 64;
+static double g_lane_entries = 12.0;   // AMGB_TILE_LANE_ENTRIES: lanes per row G doubles while mean row length > this * G
 
 template <class C, int OP>
-static void tile_cfg_op(size_t smem_per_sm)
+static void tile_cfg_op(size_t smem_per_sm, int *ctas = nullptr)
 {
     int c = std::max(1, (int)(smem_per_sm / (tile_smem_bytes<C, OP>() + 1024)));
     c = std::min(c, 2048 / (C::WARPS * 32));
@@ -182,7 +188,7 @@ static void tile_cfg_op(size_t smem_per_sm)
     // gather latency, but the shared memory they pin shrinks L1 -- the sweet spot depends on the stage size
     static const int kBest[5] = {6, 7, 6, 5, 6};   // SpMV, residual, prolong+add, Jacobi, Gauss-Seidel
     const int cap = g_tile_ctas_cap > 0 ? g_tile_ctas_cap : kBest[OP];
-    g_tile_ctas[OP] = std::max(1, std::min(c, cap));
+    (ctas ? ctas : g_tile_ctas)[OP] = std::max(1, std::min(c, cap));
 }
 
 template <class C>
@@ -217,7 +223,21 @@ static void tile_configure(size_t smem_per_sm)
     const char *tp = getenv("AMGB_TILE_PDL");
     g_tile_pdl = (tp && tp[0] == '1') ? 1 : 0;
     const char *tf = getenv("AMGB_TILE_FLAT");
-    g_tile_flat = (tf && tf[0] == '1' && g_tile_cfg == 6) ? 1 : 0;     // default geometry only
+    g_tile_flat = (tf && (tf[0] == '1' || tf[0] == '2') && g_tile_cfg == 6) ? (tf[0] - '0') : 0;     // default geometry only
+    const char *dc = getenv("AMGB_TILE_DENSE_CFG");
+    g_dense_cfg = (dc && atoi(dc) == 7) ? 7 : 0;
+    if (g_dense_cfg == 7) {
+        g_dense_T = TileCfg7::T; g_dense_rmax = TileCfg7::RMAX;
+        tile_cfg_op<TileCfg7, OP_SPMV>(smem_per_sm, g_dense_ctas);
+        tile_cfg_op<TileCfg7, OP_RESID>(smem_per_sm, g_dense_ctas);
+        tile_cfg_op<TileCfg7, OP_PADD>(smem_per_sm, g_dense_ctas);
+        tile_cfg_op<TileCfg7, OP_JACOBI>(smem_per_sm, g_dense_ctas);
+        tile_cfg_op<TileCfg7, OP_GS>(smem_per_sm, g_dense_ctas);
+    }
+    const char *da = getenv("AMGB_TILE_DENSE_AVG");
+    g_dense_avg = (da && atof(da) > 0) ? atof(da) : 12.0;
+    const char *le = getenv("AMGB_TILE_LANE_ENTRIES");
+    g_lane_entries = (le && atof(le) >= 1.0) ? atof(le) : 12.0;
 }
 
 // The launch helpers read the settings above; every hierarchy keeps the snapshot it was created (and its
@@ -225,14 +245,20 @@ static void tile_configure(size_t smem_per_sm)
 // AMGB_* settings can coexist in one (single-threaded) process.
 struct TileRuntime {
     int cfg, ctas[5], ctas_cap, T, rmax, warps, hints, pdl, tile_pdl, tile_flat;
+    int dense_cfg, dense_ctas[5];
+    double dense_avg, lane_entries;
     void capture()
     {
+        dense_cfg = g_dense_cfg; dense_avg = g_dense_avg; lane_entries = g_lane_entries;
+        for (int k = 0; k < 5; k++) dense_ctas[k] = g_dense_ctas[k];
         cfg = g_tile_cfg; ctas_cap = g_tile_ctas_cap; T = g_tile_T; rmax = g_tile_rmax; warps = g_tile_warps;
         hints = g_tile_hints; pdl = g_use_pdl; tile_pdl = g_tile_pdl; tile_flat = g_tile_flat;
         for (int k = 0; k < 5; k++) ctas[k] = g_tile_ctas[k];
     }
     void activate() const
     {
+        g_dense_cfg = dense_cfg; g_dense_avg = dense_avg; g_lane_entries = lane_entries;
+        for (int k = 0; k < 5; k++) g_dense_ctas[k] = dense_ctas[k];
         g_tile_cfg = cfg; g_tile_ctas_cap = ctas_cap; g_tile_T = T; g_tile_rmax = rmax; g_tile_warps = warps;
         g_tile_hints = hints; g_use_pdl = pdl; g_tile_pdl = tile_pdl; g_tile_flat = tile_flat;
         for (int k = 0; k < 5; k++) g_tile_ctas[k] = ctas[k];
@@ -288,8 +314,9 @@ static int launch_tile_cfg(int G, const TileArgs &a, int grid, cudaStream_t s)
 }
 
 template <int OP>
-static int launch_tile_op(int G, const TileArgs &a, int grid, cudaStream_t s)
+static int launch_tile_op(int G, const TileArgs &a, int grid, cudaStream_t s, int cfg)
 {
+    if (cfg == 7) return launch_tile_cfg<OP, TileCfg7>(G, a, grid, s);
     switch (g_tile_cfg) {
     case 0: return launch_tile_cfg<OP, TileCfg0>(G, a, grid, s);
     case 1: return launch_tile_cfg<OP, TileCfg1>(G, a, grid, s);
@@ -324,7 +351,7 @@ static int launch_tile_flat(const TileArgs &a, int grid, cudaStream_t s)
     return g_tile_pdl ? launch_tile_flat_one<OP, true>(a, grid, s) : launch_tile_flat_one<OP, false>(a, grid, s);
 }
 
-static int launch_tile(int op, int G, TileArgs a, int grid, cudaStream_t s)
+static int launch_tile(int op, int G, TileArgs a, int grid, cudaStream_t s, int cfg = 0)
 {
     if (a.tile_end <= a.tile_begin) return AMGB_OK;
     a.hints = g_tile_hints;
@@ -339,18 +366,18 @@ static int launch_tile(int op, int G, TileArgs a, int grid, cudaStream_t s)
         return fail(AMGB_EINVAL, "unknown tile op");
     }
     switch (op) {
-    case OP_SPMV: return launch_tile_op<OP_SPMV>(G, a, grid, s);
-    case OP_RESID: return launch_tile_op<OP_RESID>(G, a, grid, s);
-    case OP_PADD: return launch_tile_op<OP_PADD>(G, a, grid, s);
-    case OP_JACOBI: return launch_tile_op<OP_JACOBI>(G, a, grid, s);
-    case OP_GS: return launch_tile_op<OP_GS>(G, a, grid, s);
+    case OP_SPMV: return launch_tile_op<OP_SPMV>(G, a, grid, s, cfg);
+    case OP_RESID: return launch_tile_op<OP_RESID>(G, a, grid, s, cfg);
+    case OP_PADD: return launch_tile_op<OP_PADD>(G, a, grid, s, cfg);
+    case OP_JACOBI: return launch_tile_op<OP_JACOBI>(G, a, grid, s, cfg);
+    case OP_GS: return launch_tile_op<OP_GS>(G, a, grid, s, cfg);
     }
     return fail(AMGB_EINVAL, "unknown tile op");
 }
 
-static inline int tile_grid(int op, int ntiles)
+static inline int tile_grid(int op, int ntiles, int cfg = 0)
 {
-    const int full = g_num_sms * g_tile_ctas[op];
+    const int full = g_num_sms * (cfg == 7 ? g_dense_ctas[op] : g_tile_ctas[op]);
     const int need = (ntiles + g_tile_warps - 1) / g_tile_warps;
     return std::max(1, std::min(full, need));
 }
@@ -374,6 +401,7 @@ struct DevCsr {
     TileDesc *tiles = nullptr;   // n_tiles + 1
     int n_tiles = 0;
     int tile_G = 1;
+    int tile_cfg = 0;            // 7: built for (and launched with) the dense geometry TileCfg7; 0: the hierarchy's default
 };
 
 struct WaveSchedule {       // a sequential sweep over a row list, regrouped into dependency waves
@@ -592,7 +620,7 @@ static int pick_tile_G(long long nnz, long long n_rows)
     if (n_rows <= 0) return 1;
     const double avg = (double)nnz / (double)n_rows;
     int g = 1;
-    while (g < 32 && avg > 12.0 * g) g <<= 1;     // ~6-12 stored entries per lane
+    while (g < 32 && avg > g_lane_entries * g) g <<= 1;     // ~6-12 stored entries per lane (default)
     return g;
 }
 
@@ -600,8 +628,10 @@ static int pick_tile_G(long long nnz, long long n_rows)
 // (sorted, e.g. Gauss-Seidel wave boundaries); a row longer than T is a tile of its own.
 // Row counts are rounded down to a multiple of the rows reduced per pass (32/G) where possible.
 static void build_tiles(const HostCsr &A, int G, const std::vector<long long> *breaks,
-                        std::vector<TileDesc> &tiles, std::vector<int> *tile_ptr)
+                        std::vector<TileDesc> &tiles, std::vector<int> *tile_ptr, int T = 0, int rmax = 0)
 {
+    if (T <= 0) T = g_tile_T;
+    if (rmax <= 0) rmax = g_tile_rmax;
     const int n = A.n_rows, rpp = 32 / G;
     tiles.clear();
     size_t bi = 1;                       // next break to honour: (*breaks)[bi]
@@ -616,9 +646,9 @@ static void build_tiles(const HostCsr &A, int G, const std::vector<long long> *b
         }
         int e = r;
         long long nz = 0;
-        while (e < limit && e - r < g_tile_rmax) {
+        while (e < limit && e - r < rmax) {
             const long long len = A.Ap[(size_t)e + 1] - A.Ap[(size_t)e];
-            if (nz + len > g_tile_T) break;
+            if (nz + len > T) break;
             nz += len;
             e++;
         }
@@ -776,8 +806,9 @@ struct amgb_hierarchy {
         return AMGB_OK;
     }
 
+    // role: 0 = a level operator A, 1 = prolongation P, 2 = restriction R (flat-gather mode 2 picks by it)
     int upload_csr(const HostCsr &H, DevCsr &D, const std::vector<long long> *breaks = nullptr,
-                   std::vector<int> *tile_ptr = nullptr)
+                   std::vector<int> *tile_ptr = nullptr, int role = 0, int level = 0)
     {
         D.n_rows = H.n_rows;
         D.n_cols = H.n_cols;
@@ -788,9 +819,13 @@ struct amgb_hierarchy {
         D.lanes = pick_lanes(D.nnz, D.n_rows);
         if (use_tiles) {
             D.tile_G = pick_tile_G(D.nnz, D.n_rows);
-            if (g_tile_flat && !has_duplicate_diagonal(H)) D.tile_G = 0;      // 0 = flat-gather kernel
+            const bool flat_here = g_tile_flat == 1 || (g_tile_flat == 2 && (role == 2 || (role == 1 && level >= 1)));
+            if (flat_here && !has_duplicate_diagonal(H)) D.tile_G = 0;      // 0 = flat-gather kernel
+            const double avg = D.n_rows > 0 ? (double)D.nnz / (double)D.n_rows : 0.0;
+            D.tile_cfg = (g_dense_cfg == 7 && D.tile_G != 0 && avg > g_dense_avg) ? 7 : 0;
             std::vector<TileDesc> tiles;
-            build_tiles(H, D.tile_G ? D.tile_G : 32, breaks, tiles, tile_ptr);   // flat: no row-count rounding
+            build_tiles(H, D.tile_G ? D.tile_G : 32, breaks, tiles, tile_ptr,       // flat: no row-count rounding
+                        D.tile_cfg == 7 ? g_dense_T : 0, D.tile_cfg == 7 ? g_dense_rmax : 0);
             D.n_tiles = (int)tiles.size() - 1;
             RET(upload(&D.tiles, tiles.data(), (long long)tiles.size()));
         }
@@ -885,8 +920,8 @@ struct amgb_hierarchy {
             a.tiles = M.tiles; a.tile_begin = 0; a.tile_end = M.n_tiles;
             a.Ap = M.Ap; a.Aj = M.Aj; a.Ax = M.Ax; a.x = x; a.b = b; a.y = y; a.r = r; a.omega = omega;
             a.partials = parts;
-            const int grid = parts ? tile_grid(op, 1 << 30) : tile_grid(op, M.n_tiles);   // fixed grid when reducing
-            RET(launch_tile(op, M.tile_G, a, grid, stream));
+            const int grid = parts ? tile_grid(op, 1 << 30, M.tile_cfg) : tile_grid(op, M.n_tiles, M.tile_cfg);   // fixed grid when reducing
+            RET(launch_tile(op, M.tile_G, a, grid, stream, M.tile_cfg));
         } else {
             CsrRowArgs a;
             a.n = M.n_rows; a.row0 = 0; a.rows = nullptr;
@@ -899,12 +934,13 @@ struct amgb_hierarchy {
 
     long long partials_used(const DevCsr &M, int op) const   // slots the kernel of `op` actually writes
     {
-        return M.tiles ? (long long)g_num_sms * g_tile_ctas[op] : csr_grid(M.n_rows, M.lanes);
+        return M.tiles ? (long long)g_num_sms * (M.tile_cfg == 7 ? g_dense_ctas[op] : g_tile_ctas[op]) : csr_grid(M.n_rows, M.lanes);
     }
     long long partials_len(const DevCsr &M) const
     {
         // residual / Jacobi partial sums: one slot per CTA of the (fixed) persistent grid
-        return M.tiles ? (long long)g_num_sms * std::max(g_tile_ctas[OP_RESID], g_tile_ctas[OP_JACOBI])
+        return M.tiles ? (long long)g_num_sms * std::max(std::max(g_tile_ctas[OP_RESID], g_tile_ctas[OP_JACOBI]),
+                                                         std::max(g_dense_ctas[OP_RESID], g_dense_ctas[OP_JACOBI]))
                        : csr_grid(M.n_rows, M.lanes);
     }
 
@@ -925,7 +961,7 @@ struct amgb_hierarchy {
             a.tiles = A.tiles; a.tile_begin = ws.tile_ptr[(size_t)w]; a.tile_end = ws.tile_ptr[(size_t)w + 1];
             a.Ap = A.Ap; a.Aj = A.Aj; a.Ax = A.Ax; a.x = x; a.b = b; a.y = x; a.r = nullptr; a.omega = omega;
             a.partials = nullptr;
-            RET(launch_tile(OP_GS, A.tile_G, a, tile_grid(OP_GS, a.tile_end - a.tile_begin), stream));
+            RET(launch_tile(OP_GS, A.tile_G, a, tile_grid(OP_GS, a.tile_end - a.tile_begin, A.tile_cfg), stream, A.tile_cfg));
         } else {
             CsrRowArgs a;
             a.n = nrow;
@@ -1022,7 +1058,7 @@ struct amgb_hierarchy {
             a.tiles = L.A.tiles; a.tile_begin = s.ws.tile_ptr[(size_t)which]; a.tile_end = s.ws.tile_ptr[(size_t)which + 1];
             a.Ap = L.A.Ap; a.Aj = L.A.Aj; a.Ax = L.A.Ax; a.x = L.x; a.b = L.b; a.y = temp; a.r = nullptr; a.omega = s.omega;
             a.partials = nullptr;
-            RET(launch_tile(OP_JACOBI, L.A.tile_G, a, tile_grid(OP_JACOBI, a.tile_end - a.tile_begin), stream));
+            RET(launch_tile(OP_JACOBI, L.A.tile_G, a, tile_grid(OP_JACOBI, a.tile_end - a.tile_begin, L.A.tile_cfg), stream, L.A.tile_cfg));
         } else {
             CsrRowArgs a;
             a.n = (int)nrow; a.row0 = (int)r0; a.rows = nullptr;
@@ -1421,6 +1457,12 @@ struct amgb_hierarchy {
         if (kind == AMGB_CYCLE_AMLI) RET(prepare_amli());
         else RET(prepare_tail(kind, cpl));
         if (!use_graph) return cycle(0, kind, cpl);
+        {   // the caller is capturing this stream into ITS OWN graph (the multi-GPU layer captures the whole distributed
+            // cycle): an executable graph cannot be launched into a capturing stream -- issue the launch sequence itself
+            cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st == cudaStreamCaptureStatusActive)
+                return cycle(0, kind, cpl);
+        }
         if (graph[kind] == nullptr || graph_cpl[kind] != cpl) {
             if (graph[kind] != nullptr) { cudaGraphExecDestroy(graph[kind]); graph[kind] = nullptr; }
             const long long before = launches;
@@ -2163,10 +2205,10 @@ int amgb_hierarchy::finalize_levels()
         }
         if (H.has_pr) {
             HostCsr T;
-            if (ord || psn) { permute_csr(H.P, ord, psn, T); RET(upload_csr(T, L.P)); }
-            else RET(upload_csr(H.P, L.P));
-            if (ordn || ps) { permute_csr(H.R, ordn, ps, T); RET(upload_csr(T, L.R)); }
-            else RET(upload_csr(H.R, L.R));
+            if (ord || psn) { permute_csr(H.P, ord, psn, T); RET(upload_csr(T, L.P, nullptr, nullptr, 1, l)); }
+            else RET(upload_csr(H.P, L.P, nullptr, nullptr, 1, l));
+            if (ordn || ps) { permute_csr(H.R, ordn, ps, T); RET(upload_csr(T, L.R, nullptr, nullptr, 2, l)); }
+            else RET(upload_csr(H.R, L.R, nullptr, nullptr, 2, l));
             const std::vector<int> *pv = permuted ? &pos[(size_t)l] : nullptr;
             const bool same_lists = H.pre.kind == AMGB_SM_GAUSS_SEIDEL && H.post.kind == AMGB_SM_GAUSS_SEIDEL &&
                                     H.pre.has_list == H.post.has_list && H.pre.list == H.post.list;

@@ -55,6 +55,9 @@ using TileCfg0 = TileCfg<512, 128, 2, 8>;
 using TileCfg1 = TileCfg<256, 64, 2, 8>;
 using TileCfg4 = TileCfg<256, 64, 1, 8>;     // single stage, ~48 warps/SM: cross-warp overlap only
 using TileCfg6 = TileCfg<224, 64, 1, 8>;     // 32 seven-point rows per tile; 7-8 CTAs/SM = 56-64 warps/SM
+using TileCfg7 = TileCfg<352, 64, 1, 8>;     // denser coarse operators (~19-36 entries per row): 16 rows of 19 entries
+                                             // fill both passes of a G = 2 warp (224 entries hold 11 such rows: 69 % of
+                                             // the lanes, ncu profiles/r02_ncu_kernels.csv: 17.5 threads per instruction)
 
 // the b / x_old slices are staged only for the epilogues that read them: shared memory is what limits
 // the number of resident warps, and resident warps are what hides the gather latency

@@ -744,6 +744,12 @@ inline cudaError_t cudaStreamSynchronize(cudaStream_t s)
 {
     return (s != nullptr && s->capturing) ? cudaErrorStreamCaptureInvalidated : cudaSuccess;   // illegal during capture
 }
+enum cudaStreamCaptureStatus { cudaStreamCaptureStatusNone = 0, cudaStreamCaptureStatusActive = 1 };
+inline cudaError_t cudaStreamIsCapturing(cudaStream_t s, cudaStreamCaptureStatus *st)
+{
+    *st = (s != nullptr && s->capturing) ? cudaStreamCaptureStatusActive : cudaStreamCaptureStatusNone;
+    return cudaSuccess;
+}
 inline cudaError_t cudaStreamBeginCapture(cudaStream_t s, cudaStreamCaptureMode)
 {
     if (s == nullptr || s->capturing) return cudaErrorInvalidValue;

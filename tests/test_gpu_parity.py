@@ -81,7 +81,13 @@ def test_vcycle_matches_oracle_on_fresh_rhs(name, load_golden):
                                  {"AMGB_NO_TAIL": "1", "AMGB_TILE_MIN_NNZ": "0"},
                                  {"AMGB_NO_TAIL": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_G": "2"},
                                  {"AMGB_NO_TAIL": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_G": "8", "AMGB_TILE_CFG": "4"},
-                                 {"AMGB_NO_TAIL": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_CFG": "1"}])
+                                 {"AMGB_NO_TAIL": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_CFG": "1"},
+                                 # second tile geometry for the denser operators, flat gathers for R / coarse P only,
+                                 # other lanes-per-row rules
+                                 {"AMGB_NO_TAIL": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_DENSE_CFG": "7", "AMGB_TILE_DENSE_AVG": "4"},
+                                 {"AMGB_NO_TAIL": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_DENSE_CFG": "7", "AMGB_TILE_LANE_ENTRIES": "3"},
+                                 {"AMGB_NO_TAIL": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_FLAT": "2"},
+                                 {"AMGB_NO_TAIL": "1", "AMGB_TILE_MIN_NNZ": "0", "AMGB_TILE_FLAT": "2", "AMGB_TILE_DENSE_CFG": "7"}])
 @pytest.mark.parametrize("name", GOLDEN)
 def test_every_kernel_path_matches_reference_golden(name, env, monkeypatch):
     """The lanes-per-row kernels, the un-permuted layout, the un-graphed cycle, forced lane-group widths

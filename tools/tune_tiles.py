@@ -67,6 +67,7 @@ for st in settings:
         v = g.setdefault(k, [0.0, 0.0])
         v[0] += nbytes; v[1] += t
     line = {f"L{k[0]}:{OPS[k[1]].split('(')[0]}": round(v[0] / v[1] / 1e6) for k, v in sorted(g.items()) if k[0] <= 2}
+    ms = {f"L{k[0]}:{OPS[k[1]].split('(')[0]}": round(v[1] / 2, 3) for k, v in sorted(g.items()) if k[0] <= 2}
     small = sum(v[1] for k, v in g.items() if k[0] >= 3) / 2
     print(json.dumps({"setting": st, "cycle_ms": round(cyc_ms, 3), "small_levels_ms": round(small, 3),
-                      "relerr_vs_first_setting": dx, "GBps": line}), flush=True)
+                      "relerr_vs_first_setting": dx, "GBps": line, "ms": ms}), flush=True)
