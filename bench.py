@@ -346,6 +346,36 @@ def dist_measure(name, grid, args, local, rank, world, steps, warmup, dist_nnz):
     torch.cuda.synchronize()
     kms = a0.elapsed_time(a1) / 10
     res = np.sqrt(norms[:steps + 1].cpu().numpy())
+
+    # ---- where the cycle's time goes: exchanges, local wave kernels, the replicated coarse part, the all-reduce ----
+    def timed(fn, reps):
+        for _ in range(2):
+            fn()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        c0.record()
+        for _ in range(reps):
+            fn()
+        c1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([c0.elapsed_time(c1) / reps * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return round(float(tt.item()), 2)
+
+    parts = {"exchange_us": [timed(lambda L=L: ds.halo(L, L.x), 30) for L in ds.lv],
+             "allreduce_restriction_us": timed(lambda: be.allreduce(ds.bc_rep), 20),
+             "replicated_coarse_cycle_us": timed(lambda: ds.sub.cycle_device(ds.bc_rep, ds.xc_rep), 10),
+             "largest_local_wave_us": []}
+    for L in ds.lv:
+        D = L.D
+        if D.wave_ptr is not None:
+            wl = int(np.argmax(np.diff(D.wave_ptr)))
+            parts["largest_local_wave_us"].append(
+                timed(lambda L=L, wl=wl: be.apply(L.A, OP_GS, L.x, L.b, L.x, omega=1.0, wave=wl), 20))
+        else:
+            parts["largest_local_wave_us"].append(
+                timed(lambda L=L: be.apply(L.A, OP_JACOBI, L.x, L.b, L.xalt, omega=1.0), 20))
+    log(f"[{name}] time model (us, host-driven launches, max over ranks): {parts}")
     # parity against the single-GPU engine on the same hierarchy and rhs: two cycles from zero on both
     ncyc = 2
     ds.load(b_host)
@@ -378,7 +408,7 @@ def dist_measure(name, grid, args, local, rank, world, steps, warmup, dist_nnz):
                "gpu_launches": int(launches), "clocks": clocks, "cuda_graph": graphed, "halo": halo,
                "residual_reduction_per_cycle": float((res[-1] / res[0]) ** (1.0 / max(len(res) - 1, 1))),
                "halo_entries_per_rank": [int(L.sp.recv_off[-1]) if halo != "allgather" else int(L.sp.maxB) for L in ds.lv],
-               "exchanges_per_cycle": int(getattr(ds, "exchanges_per_cycle", 0)),
+               "exchanges_per_cycle": int(getattr(ds, "exchanges_per_cycle", 0)), "time_model_us": parts,
                "parity_vs_n1": {"rel_err": parity, "cycles": ncyc, "bar": 1e-12,
                                 "against": "the single-GPU engine on rank 0, same hierarchy and rhs"},
                "host_setup_s": round(t_setup, 1)}
@@ -645,9 +675,13 @@ def main():
         run_reference(args, grid)
         return
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        # torchrun pins every rank to one OpenMP thread; the host-side setup (colouring, wave schedules, strength /
+        # interpolation passes of csrc/host_setup.cpp) is multi-threaded: give each rank its share of the cores
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     import torch
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:

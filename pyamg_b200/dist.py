@@ -297,6 +297,7 @@ class DistributedSolver:
             L.send_idx = be.index(D.send_idx)
             L.send = be.vector(max(sp.maxB, int(sp.send_off[-1])))
             L.x, L.xalt, L.b, L.r = (be.vector(sp.n_ext) for _ in range(4))
+            L.x_home = L.x
             L.poly = be.vector(sp.n_ext) if E.SM_POLYNOMIAL in (D.pre.kind, D.post.kind) else None
             self.lv.append(L)
         if halo == "peer" and be.world > 1:
@@ -403,6 +404,9 @@ class DistributedSolver:
             self.sub.cycle_device(self.bc_rep, self.xc_rep)
             be.apply(L.P, OP_PADD, self.xc_rep, None, L.x)
         self.smooth(L, D.post)
+        if L.x is not L.x_home:        # odd number of Jacobi ping-pongs: bring the iterate home (a replayed graph
+            self.be.copy_owned(L.x_home, L.x, L.sp.n_own)          # has its buffer addresses baked in)
+            L.x, L.xalt = L.x_home, L.x
 
     # -- public -------------------------------------------------------------------------------------
     def load(self, b_global, x0_global=None):
@@ -439,14 +443,10 @@ class DistributedSolver:
         """Capture one distributed V-cycle -- engine kernels, peer-memory halo exchanges (amgb_comm_exchange), the
         all-reduce of the restriction and the replicated sub-hierarchy's own graph -- into a CUDA graph on the
         backend's stream, so the ~500 host-issued launches per cycle become one replay.  Requires warmed-up
-        cycles (all engine graphs instantiated) and an even number of Jacobi ping-pongs per level."""
+        cycles (all engine graphs instantiated)."""
         torch = getattr(self.be, "torch", None)
         if torch is None:
             raise NotImplementedError("graph capture needs the GPU backend")
-        for L in self.lv:
-            swaps = sum(S.iterations for S in (L.D.pre, L.D.post) if S.kind == E.SM_JACOBI)
-            if swaps % 2:
-                raise NotImplementedError("odd number of Jacobi sweeps per cycle: buffers would alternate")
         x0 = getattr(self, "n_exchanges", 0)
         self.cycle(0)                                  # make sure every lazily built piece exists
         self.exchanges_per_cycle = getattr(self, "n_exchanges", 0) - x0
@@ -513,6 +513,9 @@ class GpuBackend:
 
     def copy_scalar(self, src, dst, slot):
         dst[slot:slot + 1].copy_(src[:1])
+
+    def copy_owned(self, dst, src, n):
+        dst[:n].copy_(src[:n])
 
     def scale_to(self, dst, a, src):                # dst = a * src (owned part and halo region alike)
         self.torch.mul(src, a, out=dst)

@@ -40,6 +40,9 @@ class NumpyBackend:
     def copy_scalar(self, src, dst, slot):
         dst[slot] = src[0]
 
+    def copy_owned(self, dst, src, n):
+        dst[:n] = src[:n]
+
     def scale_to(self, dst, a, src):
         dst[:] = a * src
 
