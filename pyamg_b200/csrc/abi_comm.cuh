@@ -22,7 +22,7 @@
 // orders after the unpack of k.  Flags are monotone, so "flag >= k" is the whole protocol.
 //
 // Launch: all CTAs must be co-resident (CTAs that have pushed wait for peers while the last one signals): a small
-// grid (16 CTAs by default) ordered after the previous kernel by the stream / graph; every spin traps after a bounded
+// grid (64 CTAs by default) ordered after the previous kernel by the stream / graph; every spin traps after a bounded
 // number of polls instead of hanging the device when a peer died.
 #pragma once
 #include <cstring>
@@ -83,12 +83,33 @@ __global__ void __launch_bounds__(kCommThreads) halo_exchange_kernel(const ExchA
     const long long boff = (long long)(k & 1ull) * a.cap;
     const long long gtid = (long long)blockIdx.x * kCommThreads + threadIdx.x;
     const long long gsz = (long long)gridDim.x * kCommThreads;
-    // 1. push
-    for (long long i = gtid; i < a.send_total; i += gsz) {
-        int q = 0;
+    // 1. push: four independent index -> value -> remote-store chains per thread and trip (the chain is two dependent
+    //    loads of ~1 us each; a 256^2-plane halo is 65 536 entries per neighbour)
+    constexpr int U = 4;
+    for (long long i0 = gtid; i0 < a.send_total; i0 += gsz * U) {
+        int idx[U];
+        double val[U];
 #pragma unroll
-        for (int t = 1; t < kCommMaxWorld; t++) q += (t < a.world && i >= a.send_begin[t]) ? 1 : 0;
-        a.stage_peer[q][boff + a.dst_off[q] + (i - a.send_begin[q])] = a.v_src[a.send_idx[i]];
+        for (int u = 0; u < U; u++) {
+            const long long i = i0 + (long long)u * gsz;
+            idx[u] = i < a.send_total ? __ldg(a.send_idx + i) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) val[u] = idx[u] >= 0 ? a.v_src[idx[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long long i = i0 + (long long)u * gsz;
+            if (idx[u] < 0) continue;
+            int q = 0;
+#pragma unroll
+            for (int t = 1; t < kCommMaxWorld; t++) q += (t < a.world && i >= a.send_begin[t]) ? 1 : 0;
+            double *dst = a.stage_peer[0];
+            long long off = a.dst_off[0], beg = a.send_begin[0];
+#pragma unroll
+            for (int t = 1; t < kCommMaxWorld; t++)
+                if (q == t) { dst = a.stage_peer[t]; off = a.dst_off[t]; beg = a.send_begin[t]; }
+            dst[boff + off + (i - beg)] = val[u];
+        }
     }
     // 2. signal (last CTA)
     __syncthreads();
@@ -115,7 +136,19 @@ __global__ void __launch_bounds__(kCommThreads) halo_exchange_kernel(const ExchA
     }
     __syncthreads();
     // 4. unpack (staging is written by peers over NVLink: read it from L2, never from a stale L1 line)
-    for (long long i = gtid; i < a.recv_total; i += gsz) a.v_halo[i] = __ldcg(a.stage_local + boff + i);
+    for (long long i0 = gtid; i0 < a.recv_total; i0 += gsz * U) {
+        double val[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long long i = i0 + (long long)u * gsz;
+            val[u] = i < a.recv_total ? __ldcg(a.stage_local + boff + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long long i = i0 + (long long)u * gsz;
+            if (i < a.recv_total) a.v_halo[i] = val[u];
+        }
+    }
     // 5. the last CTA to finish closes the exchange
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -142,7 +175,7 @@ struct amgb_comm {
     unsigned nbr_mask = 0;
     unsigned long long *seq = nullptr;
     unsigned *done = nullptr, *fin = nullptr;
-    int grid = 16;
+    int grid = 64;
     int coop = 0;
     long long exchanges = 0;
 #ifdef AMGB_EMU
