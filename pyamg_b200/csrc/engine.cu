@@ -223,9 +223,14 @@ static void tile_configure(size_t smem_per_sm)
     const char *tp = getenv("AMGB_TILE_PDL");
     g_tile_pdl = (tp && tp[0] == '1') ? 1 : 0;
     const char *tf = getenv("AMGB_TILE_FLAT");
-    g_tile_flat = (tf && (tf[0] == '1' || tf[0] == '2') && g_tile_cfg == 6) ? (tf[0] - '0') : 0;     // default geometry only
+    // defaults measured on the 256^3 hierarchy (profiles/r02_tune_tiles.jsonl): flat gathers for the restrictions and
+    // the coarse prolongations (mode 2: R 3.5 -> 4.3, 1.6 -> 2.8, 1.6 -> 2.2 TB/s on levels 0 / 1 / 2) and the second,
+    // larger tile geometry for operators with more than ~12 entries per row (level-1 GS waves 3.0 -> 3.2 TB/s):
+    // 9.51 -> 9.07 ms per cycle.  AMGB_TILE_FLAT=0 / AMGB_TILE_DENSE_CFG=0 switch them off.
+    const int flat_mode = tf ? ((tf[0] == '1' || tf[0] == '2') ? (tf[0] - '0') : 0) : 2;
+    g_tile_flat = (g_tile_cfg == 6) ? flat_mode : 0;     // default geometry only
     const char *dc = getenv("AMGB_TILE_DENSE_CFG");
-    g_dense_cfg = (dc && atoi(dc) == 7) ? 7 : 0;
+    g_dense_cfg = dc ? ((atoi(dc) == 7) ? 7 : 0) : 7;
     if (g_dense_cfg == 7) {
         g_dense_T = TileCfg7::T; g_dense_rmax = TileCfg7::RMAX;
         tile_cfg_op<TileCfg7, OP_SPMV>(smem_per_sm, g_dense_ctas);

@@ -25,13 +25,11 @@ def _device_coloring_wanted(n, where):
     env = os.environ.get("AMGB_GPU_COLORING")
     if env in ("0", "1"):
         return env == "1"
-    if n < GPU_COLORING_MIN_ROWS:
-        return False
-    try:
-        from . import _engine as E
-        return E.lib().amgb_device_count() >= 1
-    except Exception:                    # noqa: BLE001 - no library / no device: the host routine
-        return False
+    # default: the host routine.  Measured on a B200 box (profiles/r02_widening.jsonl): the multi-threaded host first
+    # fit colours the 2.1 M-row / 14.6 M-entry level in 0.031 s, the device wavefront needs 0.033 s end to end (graph
+    # upload included) and 0.30 s on the 1 M-row / 19.6 M-entry level with its longer dependency chains -- identical
+    # colours, no gain: the colouring stays on the host unless asked for (where='gpu', AMGB_GPU_COLORING=1).
+    return False
 
 
 def _mis_coloring_device(G):
@@ -55,8 +53,8 @@ def _mis_coloring_device(G):
 def vertex_coloring(G, method="greedy", where=None):
     """Colours (int32 array, starting at 0) such that no edge of G joins equal colours.
 
-    ``where='gpu'`` (default for 'MIS' / natural-order greedy on graphs with at least GPU_COLORING_MIN_ROWS vertices
-    when a CUDA device is visible; AMGB_GPU_COLORING=0/1 forces either) computes the colouring on the device."""
+    ``where='gpu'`` (or AMGB_GPU_COLORING=1) computes the 'MIS' / natural-order greedy colouring on the device: same
+    colours vertex by vertex; the host routine is the default because it is as fast (see _device_coloring_wanted)."""
     # 'MIS' (pyamg.graph.vertex_coloring's default, amg_core/graph.h:218-235): colour k is the lexicographically first
     # maximal independent set of what colours 0..k-1 left over (maximal_independent_set_serial walks the vertices in
     # index order, graph.h:128-199).  Vertex i misses set k exactly when a SMALLER-index neighbour is in it, so i gets
