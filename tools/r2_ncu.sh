@@ -21,7 +21,7 @@ step "dominant kernel (level-1 GS wave): --set full with source"
 AMGB_NCU_SELECT="1:4:1" timeout 300 $NCU --set full --import-source on --profile-from-start off -o $O/l1_gs_full python tools/ncu_targets.py cycle > $O/l1_gs_full.log 2>&1
 step "block Jacobi (cfg5), Jacobi cycle (cfg2)"
 AMGB_NCU_SELECT="0:5:1,1:5:1,0:1:1,0:0:1,0:2:1" timeout 120 $NCU --metrics $MET --profile-from-start off -o $O/cfg5 python tools/ncu_targets.py cfg5 > $O/cfg5.log 2>&1
-AMGB_NCU_SELECT="0:3:1,1:3:1,2:3:1,0:1:1,0:0:1,0:2:1" timeout 150 $NCU --metrics $MET --profile-from-start off -o $O/cfg2 python tools/ncu_targets.py cfg2 > $O/cfg2.log 2>&1
+AMGB_GPU_RHO=0 AMGB_NCU_SELECT="0:3:1,1:3:1,2:3:1,0:1:1,0:0:1,0:2:1" timeout 200 $NCU --metrics $MET --profile-from-start off -o $O/cfg2 python tools/ncu_targets.py cfg2 > $O/cfg2.log 2>&1
 step "launch list of one bench run (headline only; first 2500 launches)"
 timeout 400 $NCU --metrics gpu__time_duration.sum -c 2500 --csv --log-file $O/launches.csv \
     python bench.py --steps 2 --warmup 3 --configs "" --cpu-sample 1 > $O/launches_bench.log 2>&1
