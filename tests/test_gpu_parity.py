@@ -359,3 +359,33 @@ def test_out_buffer_and_pinned_result(load_golden):
     assert np.array_equal(x0, ex["x0"]) and relerr(x, ex["x_ref_tol"]) < TOL
     with pytest.raises(ValueError):
         ml.solve(ex["b"], out=np.zeros(n - 1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["sa_jacobi", "sa_block_jacobi"])
+def test_large_levels_take_the_tile_path_at_default_thresholds(kind):
+    """The goldens are small (<= 2 305 rows), so at the DEFAULT tile threshold (1.5 M entries per launch) they run on the
+    lanes-per-row kernels.  Here the level-0 operators exceed the threshold -- smoothed aggregation + weighted Jacobi on
+    Poisson 700^2 (2.4 M entries) and + block Jacobi on elasticity 260^2 (BSR(2,2), 2.4 M entries) -- so the TMA tile
+    kernels (OP_JACOBI with the fused residual, OP_RESID, the flat-gather restriction) and block_jacobi_kernel run with
+    the shipped defaults; two V-cycles against the oracle driving the reference's compiled kernels."""
+    from pyamg_b200.aggregation import smoothed_aggregation_solver
+    from pyamg_b200.gallery import linear_elasticity, poisson
+    np.random.seed(7)
+    if kind == "sa_jacobi":
+        sm = ("jacobi", {"omega": 4.0 / 3.0})
+        ml = smoothed_aggregation_solver(poisson((700, 700)), presmoother=sm, postsmoother=sm)
+    else:
+        A, B = linear_elasticity((260, 260))
+        ml = smoothed_aggregation_solver(A, B=B, presmoother="block_jacobi", postsmoother="block_jacobi")
+    A0 = ml.levels[0].A
+    assert A0.nnz >= 1_500_000
+    b = np.random.default_rng(11).random(A0.shape[0])
+    kern = "ref" if oracle.have_ref() else "oracle"
+    cyc = oracle.Cycle(oracle.hierarchy_spec(ml), coarse_pinv=ml.coarse_solver.dense_operator(ml.levels[-1].A),
+                       kernels=kern)
+    res_o, res_g = [], []
+    xo = cyc.solve(b, tol=0, maxiter=2, residuals=res_o)
+    xg = ml.solve(b, tol=0, maxiter=2, residuals=res_g)
+    assert relerr(xg, xo) < TOL
+    assert np.allclose(res_g, res_o, rtol=1e-10)
