@@ -26,7 +26,10 @@ pytestmark = pytest.mark.skipif(platform.machine() != "x86_64" or shutil.which("
 # fast, broad: every golden's V/W/F cycles, single-kernel goldens, quirks, KATs, PCG, a few forced kernel paths
 SUBSET = ("vcycle_matches_reference_golden or w_and_f or relaxation_kernels or matvecs_match or quirks "
           "or reference_kats or pcg_matches or single_level or polynomial_matches or jacobi_indexed_and "
-          "or block_gauss_seidel_matches or schwarz_matches or normal_equation_smoothers_match or (every_kernel_path and cfg3 and (env0 or env4 or env6 or env11))")
+          "or block_gauss_seidel_matches or schwarz_matches or normal_equation_smoothers_match or device_mis "
+          # round 2: the persistent grid kernel (env17 / env20), forced tile paths (env21), the second tile geometry and
+          # flat gathers for R / coarse P (env25 / env28)
+          "or (every_kernel_path and cfg3 and (env0 or env4 or env6 or env11 or env17 or env20 or env21 or env25 or env28))")
 
 
 def _run(extra_env, k, files=("tests/test_gpu_parity.py", "tests/test_zz_gpu_widening.py"), timeout=900):
