@@ -1,25 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- V-cycles/s of the B200 AMG solve-phase engine on BASELINE.json's headline config.
+"""bench.py -- V-cycles/s of the B200 AMG solve-phase engine on BASELINE.json's configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid G]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg4|cfg5]
+                    [--grid G] [--configs cfg2,cfg5,cfg4]
 
-Workload (config.workload): BASELINE.json configs[2] -- gallery.poisson((256,256,256)) 7-pt fp64,
-ruge_stuben_solver hierarchy (classical strength 0.25, RS splitting, classical interpolation),
-multi-colour Gauss-Seidel (symmetric, gauss_seidel_indexed over colour-sorted rows) pre and post,
-'pinv' coarse solve; rhs = default_rng(20260922).random(n), x0 = 0.  The reference package is not
-installed on the GPU box, so the hierarchy is built by this repo's host-side setup
-(pyamg_b200.classical, validated to reproduce the reference's hierarchies: tests/test_setup.py).
+Headline workload (config.workload): BASELINE.json configs[2] -- gallery.poisson((256,256,256)) 7-pt fp64,
+ruge_stuben_solver hierarchy (classical strength 0.25, RS splitting, classical interpolation), multi-colour
+Gauss-Seidel (symmetric, gauss_seidel_indexed over colour-sorted rows) pre and post, 'pinv' coarse solve;
+rhs = default_rng(20260922).random(n), x0 = 0.  The hierarchy is built by this repo's host-side setup
+(pyamg_b200.classical: 28 s instead of ~150 s with the reference; validated to reproduce the reference's
+hierarchies, tests/test_setup.py).  At N = 1 the same line carries, under `configs`, BASELINE configs[1] (cfg2),
+configs[4] (cfg5) and configs[3] (cfg4) with the same measurements each.
 
 A "step" is one V-cycle plus the per-cycle residual-norm check, exactly what one iteration of the
 reference's MultilevelSolver.solve does (pyamg/multilevel.py:558-582).
   value    : V-cycles/s with b, x resident in HBM (CUDA events on the launching stream, max over ranks)
-  e2e      : V-cycles/s through the C-ABI amgb_solve with pinned HOST b/x, one cycle per call (the
-             aspreconditioner() pattern): H2D b + x0 and D2H x inside the timed region every step
+  e2e      : V-cycles/s through the C-ABI amgb_solve_ex with pinned HOST b/x, one cycle per call (the
+             aspreconditioner() pattern): H2D b and D2H x inside the timed region every step
   roofline : the dominant kernel class of the cycle, algorithmic bytes / CUDA-event time, vs
-             MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline / --impl reference : the reference's compiled relaxation.h (oracle/_ref) + SciPy
-             matvecs driven by the oracle's restatement of __solve, 1 host core (the reference is
-             single-threaded and holds the GIL), same hierarchy
+             MEASURED_PEAKS.json hbm_gbs; traffic = DRAM bytes per launch from the committed ncu capture of the
+             SAME library build (profiles/r02_ncu_traffic.json), else null
+  fine_level : level-0 SpMV and the fused Jacobi+residual kernel in isolation, outputs checked at size
+  cpu_baseline / --impl reference : the REAL pyamg.MultilevelSolver.solve of the unmodified reference
+             (oracle/_ref/site, installed by oracle/build.py; travels to the GPU box) on the same operators and
+             smoother parameters, 1 host core (the reference is single-threaded and holds the GIL); falls back to
+             the oracle's restatement over the compiled relaxation.h when the package is absent
+  --gpus N : torchrun, one rank per GPU: cfg3 and cfg4 row-partitioned (pyamg_b200/dist.py), peer-memory halo
+             exchange, one CUDA graph per rank, parity_vs_n1, time_model_us
 Inputs are far larger than L2 (level-0 operator alone is 1.4 GB), so no explicit L2 flush is needed.
 """
 import argparse
