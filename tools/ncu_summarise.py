@@ -65,6 +65,7 @@ def main():
         ("l1_gs_full", "cfg3 V-cycle, level-1 GS wave (--set full)", "cfg3"),
         ("cfg5", "cfg5 V-cycle (elasticity 300^2)", "cfg5"),
         ("cfg2", "cfg2 V-cycle (SA + Jacobi 2000^2)", "cfg2"),
+        ("dense", "cfg5 coarsest level: pinv apply (dense_matvec_kernel)", None),
     ]
     fine_ops = ["spmv", "residual", "jacobi+residual (fused)", "jacobi"]
     for fname, what, cfg in captures:
@@ -96,6 +97,8 @@ def main():
                 level = 0
             elif fname == "fine_jacobi_full":
                 role, level = "jacobi+residual (fused)", 0
+            elif fname == "dense":
+                role, level = "coarse pinv apply", 5
             else:
                 role = OPS.get(op, "") if op is not None else ""
                 if order is not None and k < len(order) and order[k] is not None and (op is None or order[k][1] == op):
