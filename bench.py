@@ -22,7 +22,7 @@ reference's MultilevelSolver.solve does (pyamg/multilevel.py:558-582).
              SAME library build (profiles/r02_ncu_traffic.json), else null
   fine_level : level-0 SpMV and the fused Jacobi+residual kernel in isolation, outputs checked at size
   cpu_baseline / --impl reference : the REAL pyamg.MultilevelSolver.solve of the unmodified reference
-             (oracle/_ref/site, installed by oracle/build.py; travels to the GPU box) on the same operators and
+             (baseline/_ref, installed by oracle/build.py; travels to the GPU box) on the same operators and
              smoother parameters, 1 host core (the reference is single-threaded and holds the GIL); falls back to
              the oracle's restatement over the compiled relaxation.h when the package is absent
   --gpus N : torchrun, one rank per GPU: cfg3 and cfg4 row-partitioned (pyamg_b200/dist.py), peer-memory halo
@@ -152,7 +152,7 @@ def reference_solver(ml):
     """The reference's CPU implementation of the path for hierarchy `ml`: (callable cycles(b, k) -> x after k
     V-cycles from x0 = 0 incl. the per-cycle residual checks, kind, description).
 
-    With oracle/_ref/site present (the unmodified reference, compiled in place by oracle/build.py; it travels to
+    With baseline/_ref present (the unmodified reference, compiled in place by oracle/build.py; it travels to
     the GPU box) this is the REAL ``pyamg.MultilevelSolver.solve`` (multilevel.py:398-582) on the same operators
     and smoother parameters (oracle/reference_adapter.py); otherwise the oracle's restatement of ``__solve`` driving
     the compiled ``relaxation.h`` (oracle/_ref/libamg_ref.so) or, last, the C port."""
@@ -161,7 +161,7 @@ def reference_solver(ml):
         from oracle.reference_adapter import to_reference
         ref = to_reference(ml)
         return (lambda b, k: ref.solve(b, tol=0, maxiter=k)), "reference", \
-            "pyamg.MultilevelSolver.solve of the unmodified reference (oracle/_ref/site), amg_core + SciPy matvec"
+            "pyamg.MultilevelSolver.solve of the unmodified reference (baseline/_ref), amg_core + SciPy matvec"
     except ImportError:
         pass
     kernels = "ref" if oracle.have_ref() else "oracle"

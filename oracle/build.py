@@ -57,7 +57,10 @@ def build_oracle(force=False, verbose=False):
 # The WHOLE reference package, importable (SURVEY 8(c) recipe): test infrastructure and the `--impl reference` arm.
 # ---------------------------------------------------------------------------------------------------------------
 REF_PKG = "/root/reference/pyamg"
-REF_SITE = os.path.join(HERE, "_ref", "site")          # git-ignored, NOT gpurun-ignored: travels to the GPU box
+# the contract's place for the unmodified reference: <repo>/baseline/_ref (git-ignored, NOT gpurun-ignored: it travels
+# to the GPU box).  `pip install --target baseline/_ref /root/reference` needs meson-python, which this image lacks, so
+# the same install is produced by hand below.
+REF_SITE = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
 _EXT = ["air", "evolution_strength", "graph", "krylov", "linalg", "relaxation", "ruge_stuben", "smoothed_aggregation"]
 
 
@@ -67,7 +70,7 @@ def reference_site():
 
 
 def build_reference_package(force=False, verbose=False, jobs=8):
-    """Install the unmodified reference into oracle/_ref/site: the package tree is copied there as an INSTALL (the
+    """Install the unmodified reference into baseline/_ref: the package tree is copied there as an INSTALL (the
     directory is git-ignored; nothing of it enters this repo's history) and its eight checked-in pybind11 binding
     units are compiled in place with the flags of the reference's meson.build:4,7 -- meson itself is not in this
     image.  A dist-info stub answers pyamg/__init__.py:12-13's importlib.metadata.version call."""
@@ -107,12 +110,12 @@ def build_reference_package(force=False, verbose=False, jobs=8):
 
 
 def import_reference():
-    """`import pyamg` = the unmodified reference from oracle/_ref/site (raises ImportError when it was never built).
+    """`import pyamg` = the unmodified reference from baseline/_ref (raises ImportError when it was never built).
     Only tests/, smoke() and bench.py's reference / cpu_baseline legs may call this."""
     import sys
     site = reference_site()
     if site is None:
-        raise ImportError("oracle/_ref/site is absent: run oracle/build.py where /root/reference exists")
+        raise ImportError("baseline/_ref is absent: run oracle/build.py where /root/reference exists")
     if site not in sys.path:
         sys.path.insert(0, site)
     import pyamg

@@ -1,4 +1,4 @@
-"""Drive the UNMODIFIED reference (oracle/_ref/site: /root/reference's pyamg compiled in place by oracle/build.py)
+"""Drive the UNMODIFIED reference (baseline/_ref: /root/reference's pyamg compiled in place by oracle/build.py)
 on a hierarchy this repo holds.  TEST INFRASTRUCTURE ONLY -- bench.py's `--impl reference` / `cpu_baseline` legs and
 tests/ use it; the product never imports it.
 

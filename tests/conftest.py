@@ -13,9 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# The unmodified reference, installed by oracle/build.py into oracle/_ref/site (git-ignored, travels with the gpurun
+# The unmodified reference, installed by oracle/build.py into baseline/_ref (git-ignored, travels with the gpurun
 # snapshot): with it `import pyamg` works on the GPU box too, so the from_pyamg adoption tests run there.
-_REF_SITE = os.path.join(ROOT, "oracle", "_ref", "site")
+_REF_SITE = os.path.join(ROOT, "baseline", "_ref")
 if os.path.exists(os.path.join(_REF_SITE, "pyamg", "__init__.py")) and _REF_SITE not in sys.path:
     sys.path.append(_REF_SITE)
 

@@ -201,7 +201,7 @@ def test_vector_sa_setup_reproduces_reference_elasticity_hierarchy(load_golden):
 def test_mis_colouring_is_the_references():
     """pyamg.graph.vertex_coloring(G, 'MIS') (amg_core/graph.h:218-235: repeated lexicographically-first maximal
     independent sets) equals natural-order first fit vertex by vertex -- checked against the REAL reference (installed
-    by oracle/build.py into oracle/_ref/site) on every level of two Ruge-Stuben hierarchies and a random graph."""
+    by oracle/build.py into baseline/_ref) on every level of two Ruge-Stuben hierarchies and a random graph."""
     pyamg = pytest.importorskip("pyamg")
     import scipy.sparse as sp
     from pyamg.graph import vertex_coloring as reference_coloring

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2, GPU call 1: parity of everything (reference importable from oracle/_ref/site), A/B of the opt-in kernel
+# Round-2, GPU call 1: parity of everything (reference importable from baseline/_ref), A/B of the opt-in kernel
 # variants on the 256^3 hierarchy, first numbers for BASELINE configs[1] and [4].
 mkdir -p gpurun_out
 echo "=== pytest -m gpu (whole suite; the reference is importable: no from_pyamg skips expected)"
