@@ -13,10 +13,7 @@ from scipy import sparse
 from . import _host as H
 
 
-GPU_COLORING_MIN_ROWS = 200_000
-
-
-def _device_coloring_wanted(n, where):
+def _device_coloring_wanted(where):
     import os
     if where is not None:
         if where not in ("host", "gpu"):
@@ -77,7 +74,7 @@ def vertex_coloring(G, method="greedy", where=None):
         H.lib().amgb_setup_greedy_coloring_ordered(n, H.ip(Ap), H.ip(Aj), orders[method], H.ip(colors))
         return colors, bool(H.lib().amgb_setup_coloring_is_valid(n, H.ip(Ap), H.ip(Aj), H.ip(colors)))
 
-    if orders[method] == 0 and _device_coloring_wanted(n, where):
+    if orders[method] == 0 and _device_coloring_wanted(where):
         Ap = np.ascontiguousarray(G.indptr, dtype=np.int32)
         Aj = np.ascontiguousarray(G.indices, dtype=np.int32)
         colors = _mis_coloring_device(G)
